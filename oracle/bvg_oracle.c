@@ -1,0 +1,768 @@
+/*
+ * bvg_oracle.c -- fp64 CPU restatement of the bayesVG SVG hot path.  TEST INFRASTRUCTURE ONLY
+ * (see bvg_oracle.h: "PARITY UNPINNED").  Each function cites the reference lines it follows;
+ * paths are relative to /root/reference.  [U] marks upstream CmdStan/Stan behaviour restated
+ * from its published algorithm (not vendored in the reference).
+ *
+ * Build: make -C oracle   (gcc -O3 -march=x86-64-v3 -fopenmp -shared)
+ */
+#include "bvg_oracle.h"
+#include <float.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define LOG_TWO_PI 1.8378770664093454835606594728112
+#define LOG_PI 1.1447298858494001741434273513531
+#define LOG_TWO 0.69314718055994530941723212145818
+
+/* ------------------------------------------------------------------------------------------
+ * Parameter layout: Stan declaration order = serialisation order of the unconstrained vector
+ * [U].  inst/approxGP.stan:12-23 (gaussian) and inst/approxGP4.stan:12-23 (nb).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  int64_t mu_beta0, sigma_beta0, z_beta0, mu_amp, sigma_amp, amp, mu_alpha, sigma_alpha, z_alpha,
+      tail; /* tail = sigma_y (gaussian) | phi_nb (nb) */
+  int64_t D;
+} layout_t;
+
+static layout_t make_layout(int model, int64_t G, int k) {
+  layout_t L;
+  L.mu_beta0 = 0;
+  L.sigma_beta0 = 1;
+  L.z_beta0 = 2;
+  if (model == BVGO_GAUSSIAN) { /* approxGP.stan:13-22 */
+    L.mu_amp = 2 + G;
+    L.sigma_amp = 3 + G;
+    L.amp = 4 + G;
+    L.mu_alpha = 4 + 2 * G;
+    L.sigma_alpha = L.mu_alpha + k;
+    L.z_alpha = L.sigma_alpha + k;
+    L.tail = L.z_alpha + (int64_t)k * G;
+  } else { /* approxGP4.stan:13-22: phi_nb after z_beta0, amplitude before its hyper-parameters */
+    L.tail = 2 + G;
+    L.amp = 3 + G;
+    L.mu_amp = 3 + 2 * G;
+    L.sigma_amp = 4 + 2 * G;
+    L.mu_alpha = 5 + 2 * G;
+    L.sigma_alpha = L.mu_alpha + k;
+    L.z_alpha = L.sigma_alpha + k;
+  }
+  L.D = 5 + 2 * G + 2 * (int64_t)k + (int64_t)k * G;
+  return L;
+}
+
+int64_t bvgo_dim(int model, int64_t G, int k) { return make_layout(model, G, k).D; }
+
+struct bvgo_ctx {
+  int model;
+  int64_t M, G;
+  int k;
+  const double *phi, *y;
+  int nthreads;
+  layout_t L;
+};
+
+bvgo_ctx *bvgo_create(int model, int64_t M, int64_t G, int k, const double *phi, const double *y,
+                      int nthreads) {
+  bvgo_ctx *c = (bvgo_ctx *)calloc(1, sizeof(*c));
+  c->model = model;
+  c->M = M;
+  c->G = G;
+  c->k = k;
+  c->phi = phi;
+  c->y = y;
+  c->nthreads = nthreads > 0 ? nthreads : 1;
+  c->L = make_layout(model, G, k);
+  return c;
+}
+void bvgo_destroy(bvgo_ctx *c) { free(c); }
+
+/* digamma: recurrence to x >= 10 then the asymptotic series (Abramowitz & Stegun 6.3.18) */
+double bvgo_digamma(double x) {
+  double r = 0.0;
+  while (x < 10.0) {
+    r -= 1.0 / x;
+    x += 1.0;
+  }
+  double f = 1.0 / (x * x);
+  double t = f * (-1.0 / 12.0 +
+                  f * (1.0 / 120.0 +
+                       f * (-1.0 / 252.0 +
+                            f * (1.0 / 240.0 + f * (-1.0 / 132.0 + f * (691.0 / 32760.0 + f * (-1.0 / 12.0)))))));
+  return r + log(x) - 0.5 / x + t;
+}
+
+static inline double lgam(double x) { int sg; return lgamma_r(x, &sg); } /* thread-safe */
+static inline double log1p_exp(double a) { return a > 0 ? a + log1p(exp(-a)) : log1p(exp(a)); }
+static inline double inv_logit(double a) {
+  if (a >= 0) return 1.0 / (1.0 + exp(-a));
+  double e = exp(a);
+  return e / (1.0 + e);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * log density + analytic gradient.
+ *   gaussian: inst/approxGP.stan:25-49 ; nb: inst/approxGP4.stan:25-49
+ *   alpha_t   = mu_alpha 1' + diag(sigma_alpha) z_alpha_t         (:31-32)
+ *   phi_alpha = phi * alpha_t                                     (:33)
+ *   w[i] = phi_alpha[spot_id[i], gene_id[i]] -- identity gather since N = M*G, gene-major
+ *          (R/findSpatiallyVariableFeaturesBayes.R:176-183, :290-291)
+ *   y ~ normal(beta0[g] + amplitude_sq[g] * w, sigma_y)           (approxGP.stan:48)
+ *   y ~ neg_binomial_2_log(beta0[g] + amplitude_sq[g] * w, phi_nb) (approxGP4.stan:48)
+ * The only O(N) quantities are R_g = sum_s r, P_g = Phi' r, SSE.
+ * ---------------------------------------------------------------------------------------- */
+#define SB 256 /* spot block kept in L1 */
+
+double bvgo_log_prob(bvgo_ctx *c, const double *th, int jac, int propto, double *grad) {
+  const layout_t L = c->L;
+  const int64_t M = c->M, G = c->G;
+  const int k = c->k;
+  const int nb = c->model == BVGO_NB;
+  const double mb = th[L.mu_beta0], lsb = th[L.sigma_beta0], sb = exp(lsb);
+  const double ma = th[L.mu_amp], lsa = th[L.sigma_amp], sa = exp(lsa);
+  const double lt = th[L.tail], tl = exp(lt); /* sigma_y or phi_nb */
+  const double *mua = th + L.mu_alpha, *lsal = th + L.sigma_alpha;
+  double *sal = (double *)malloc(sizeof(double) * k);
+  for (int j = 0; j < k; ++j) sal[j] = exp(lsal[j]);
+  const double inv_s2 = nb ? 1.0 : 1.0 / (tl * tl);
+  const double lg_phi = nb ? lgam(tl) : 0.0, dg_phi = nb ? bvgo_digamma(tl) : 0.0;
+
+  /* reductions over genes */
+  double sse = 0, lik = 0, sumR = 0, sumRz = 0, sdu = 0, sdu2 = 0, sz2 = 0, su = 0, dphi = 0;
+  double *APs = (double *)calloc(2 * (size_t)k, sizeof(double)), *APz = APs + k;
+
+#pragma omp parallel num_threads(c->nthreads)
+  {
+    double *cj = (double *)malloc(sizeof(double) * (4 * (size_t)k + 2 * SB));
+    double *al = cj + k, *P = al + k, *lAP = P + k, *f = lAP + k, *r = f + SB;
+    double t_sse = 0, t_lik = 0, t_R = 0, t_Rz = 0, t_du = 0, t_du2 = 0, t_z2 = 0, t_u = 0, t_dphi = 0;
+    double *t_APs = (double *)calloc(2 * (size_t)k, sizeof(double)), *t_APz = t_APs + k;
+#pragma omp for schedule(static)
+    for (int64_t g = 0; g < G; ++g) {
+      const double zb = th[L.z_beta0 + g], u = th[L.amp + g];
+      const double *z = th + L.z_alpha + g * k;
+      const double beta = mb + sb * zb; /* approxGP.stan:26 */
+      const double A = exp(2.0 * u);    /* amplitude_sq, :27 */
+      for (int j = 0; j < k; ++j) {
+        al[j] = mua[j] + sal[j] * z[j]; /* :32 */
+        cj[j] = A * al[j];
+        P[j] = 0;
+        t_z2 += z[j] * z[j];
+      }
+      t_z2 += zb * zb;
+      const double *yg = c->y + g * M;
+      double Rg = 0, sse_g = 0, lik_g = 0, dphi_g = 0;
+      for (int64_t s0 = 0; s0 < M; s0 += SB) {
+        const int n = (int)((M - s0) < SB ? (M - s0) : SB);
+        for (int i = 0; i < n; ++i) f[i] = beta;
+        for (int j = 0; j < k; ++j) {
+          const double *pj = c->phi + (int64_t)j * M + s0;
+          const double cc = cj[j];
+          for (int i = 0; i < n; ++i) f[i] += pj[i] * cc; /* :33 + :48 mean */
+        }
+        if (!nb) {
+          for (int i = 0; i < n; ++i) {
+            const double e = yg[s0 + i] - f[i];
+            r[i] = e;
+            sse_g += e * e;
+            Rg += e;
+          }
+        } else {
+          for (int i = 0; i < n; ++i) {
+            const double yy = yg[s0 + i], eta = f[i], d = eta - lt;
+            const double Lq = log1p_exp(d), sg = inv_logit(d);
+            /* neg_binomial_2_log_lpmf [U]: lchoose(y+phi-1,y) + y eta - phi L - y (log phi + L) */
+            lik_g += lgam(yy + tl) - lgam(yy + 1.0) - lg_phi + yy * eta - tl * Lq - yy * (lt + Lq);
+            const double ri = yy - (yy + tl) * sg;
+            r[i] = ri;
+            Rg += ri;
+            if (grad) dphi_g += bvgo_digamma(yy + tl) - dg_phi - Lq - ri / tl;
+          }
+        }
+        if (grad)
+          for (int j = 0; j < k; ++j) {
+            const double *pj = c->phi + (int64_t)j * M + s0;
+            double a = 0;
+            for (int i = 0; i < n; ++i) a += pj[i] * r[i];
+            P[j] += a;
+          }
+      }
+      t_sse += sse_g;
+      t_lik += lik_g;
+      t_dphi += dphi_g;
+      Rg *= inv_s2;
+      const double du = u - ma;
+      t_du += du;
+      t_du2 += du * du;
+      t_u += u;
+      if (grad) {
+        double aP = 0;
+        for (int j = 0; j < k; ++j) {
+          const double Pj = P[j] * inv_s2;
+          aP += al[j] * Pj;
+          const double AP = A * Pj;
+          t_APs[j] += AP;
+          t_APz[j] += AP * z[j];
+          grad[L.z_alpha + g * k + j] = sal[j] * AP - z[j];
+        }
+        t_R += Rg;
+        t_Rz += Rg * zb;
+        grad[L.z_beta0 + g] = sb * Rg - zb;
+        grad[L.amp + g] = 2.0 * A * aP - du / (sa * sa) - (jac ? 0.0 : 1.0);
+      }
+    }
+#pragma omp critical
+    {
+      sse += t_sse; lik += t_lik; sumR += t_R; sumRz += t_Rz; sdu += t_du; sdu2 += t_du2;
+      sz2 += t_z2; su += t_u; dphi += t_dphi;
+      for (int j = 0; j < k; ++j) { APs[j] += t_APs[j]; APz[j] += t_APz[j]; }
+    }
+    free(t_APs);
+    free(cj);
+  }
+
+  const double N = (double)M * (double)G;
+  double lp = 0;
+  if (!nb) lp += -N * lt - 0.5 * sse * inv_s2; /* normal_lpdf, approxGP.stan:48 */
+  else lp += lik;
+  lp += -0.5 * sz2;                                              /* :38-39 std_normal on z's */
+  lp += -mb * mb / 8.0 - 0.5 * sb * sb - ma * ma / 8.0 - 0.5 * sa * sa; /* :40-43 */
+  lp += -(double)G * lsa - su - 0.5 * sdu2 / (sa * sa);          /* :44 lognormal */
+  for (int j = 0; j < k; ++j) lp += -mua[j] * mua[j] / 8.0 - 0.5 * sal[j] * sal[j]; /* :45-46 */
+  if (!nb) lp += -0.5 * tl * tl;                                 /* :47 sigma_y ~ std_normal */
+  else lp += -log1p(tl * tl / 4.0);                              /* approxGP4.stan:41 cauchy(0,2) */
+  if (jac) {
+    lp += lsb + lsa + su + lt;
+    for (int j = 0; j < k; ++j) lp += lsal[j];
+  }
+  if (!propto) {
+    if (!nb)
+      lp += -0.5 * LOG_TWO_PI * (N + (double)k * G + 2.0 * G + 2.0 * k + 5.0) - (k + 2.0) * LOG_TWO;
+    else /* cauchy: -log(pi*2); T[0,]: -log(1/2) [U] */
+      lp += -0.5 * LOG_TWO_PI * ((double)k * G + 2.0 * G + 2.0 * k + 4.0) - (k + 2.0) * LOG_TWO - LOG_PI;
+  }
+  if (grad) {
+    const double j1 = jac ? 1.0 : 0.0;
+    grad[L.mu_beta0] = sumR - mb / 4.0;
+    grad[L.sigma_beta0] = sb * (sumRz - sb) + j1;
+    grad[L.mu_amp] = sdu / (sa * sa) - ma / 4.0;
+    grad[L.sigma_amp] = -(double)G + sdu2 / (sa * sa) - sa * sa + j1;
+    for (int j = 0; j < k; ++j) {
+      grad[L.mu_alpha + j] = APs[j] - mua[j] / 4.0;
+      grad[L.sigma_alpha + j] = sal[j] * (APz[j] - sal[j]) + j1;
+    }
+    if (!nb) grad[L.tail] = -N + sse * inv_s2 - tl * tl + j1;
+    else grad[L.tail] = tl * dphi - 0.5 * tl * tl / (1.0 + tl * tl / 4.0) + j1;
+  }
+  free(APs);
+  free(sal);
+  return lp;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * RNG specification shared with the CUDA engine (DESIGN.md "RNG"): Philox4x32-10 (Salmon et
+ * al., SC'11), key = seed, counter = (i_lo, i_hi, t, stream); one standard normal per call via
+ * Box-Muller on a 53-bit and a 32-bit uniform.  Stan itself uses a boost generator seeded with
+ * random.seed (findSpatiallyVariableFeaturesBayes.R:347,358); bit-identical draws to CmdStan are
+ * neither possible nor required.
+ * ---------------------------------------------------------------------------------------- */
+void bvgo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+  uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3], k0 = key[0], k1 = key[1];
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1;
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+double bvgo_normal(uint64_t seed, uint32_t stream, uint32_t t, uint64_t i) {
+  uint32_t ctr[4] = {(uint32_t)i, (uint32_t)(i >> 32), t, stream};
+  uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)}, o[4];
+  bvgo_philox4x32_10(ctr, key, o);
+  const double u1 = ((double)(((uint64_t)o[0] << 21) | (o[2] >> 11)) + 0.5) * (1.0 / 9007199254740992.0);
+  const double u2 = ((double)o[1] + 0.5) * (1.0 / 4294967296.0);
+  return sqrt(-2.0 * log(u1)) * cos(6.283185307179586476925286766559 * u2);
+}
+enum { STREAM_GRAD = 1, STREAM_ELBO = 2, STREAM_DRAW = 3 };
+
+/* ------------------------------------------------------------------------------------------
+ * Meanfield ADVI [U: stan::variational::advi<normal_meanfield>], invoked by
+ * R/findSpatiallyVariableFeaturesBayes.R:357-364 (iter = n.iter, draws = n.draws,
+ * elbo_samples = elbo.samples; grad_samples = 1, adapt_iter = 50, eval_elbo = 100,
+ * tol_rel_obj = 0.01 left at CmdStan defaults).  SURVEY A.4.
+ * ---------------------------------------------------------------------------------------- */
+double bvgo_elbo(bvgo_ctx *c, const double *mu, const double *om, int S, uint64_t seed, uint32_t t0) {
+  const int64_t D = c->L.D;
+  double *zeta = (double *)malloc(sizeof(double) * D);
+  double acc = 0;
+  int ok = 0;
+  for (int s = 0; s < S; ++s) {
+    for (int64_t i = 0; i < D; ++i) zeta[i] = mu[i] + exp(om[i]) * bvgo_normal(seed, STREAM_ELBO, t0 + s, i);
+    const double lp = bvgo_log_prob(c, zeta, 1, 0, NULL); /* log_prob<propto=false, jacobian=true> */
+    if (isfinite(lp)) { acc += lp; ++ok; } /* non-finite draws are dropped */
+  }
+  free(zeta);
+  if (ok == 0) return -INFINITY;
+  double ent = 0.5 * (double)D * (1.0 + LOG_TWO_PI);
+  for (int64_t i = 0; i < D; ++i) ent += om[i];
+  /* Stan divides by n_monte_carlo_elbo after re-drawing failed samples; with no failures the two
+   * agree.  We divide by the number of finite draws. */
+  return acc / ok + ent;
+}
+
+int bvgo_advi_step(bvgo_ctx *c, double *mu, double *om, double *hist, double eta, int it,
+                   uint64_t seed, uint32_t t) {
+  const int64_t D = c->L.D;
+  double *zeta = (double *)malloc(sizeof(double) * 3 * D), *eps = zeta + D, *g = eps + D;
+  for (int64_t i = 0; i < D; ++i) {
+    eps[i] = bvgo_normal(seed, STREAM_GRAD, t, i);
+    zeta[i] = mu[i] + exp(om[i]) * eps[i];
+  }
+  const double lp = bvgo_log_prob(c, zeta, 1, 1, g);
+  int finite = isfinite(lp);
+  for (int64_t i = 0; i < D && finite; ++i) finite = isfinite(g[i]);
+  const double es = eta / sqrt((double)it);
+  for (int64_t i = 0; i < D; ++i) {
+    /* failing gradient -> zero gradient (adapt_eta's catch) */
+    const double gm = finite ? g[i] : 0.0;
+    const double go = finite ? g[i] * eps[i] * exp(om[i]) + 1.0 : 0.0;
+    double *hm = hist + i, *ho = hist + D + i;
+    if (it == 1) { *hm += gm * gm; *ho += go * go; }
+    else { *hm = 0.9 * *hm + 0.1 * gm * gm; *ho = 0.9 * *ho + 0.1 * go * go; }
+    mu[i] += es * gm / (1.0 + sqrt(*hm));
+    om[i] += es * go / (1.0 + sqrt(*ho));
+  }
+  free(zeta);
+  return finite ? 0 : 1;
+}
+
+static int cmp_d(const void *a, const void *b) {
+  const double x = *(const double *)a, y = *(const double *)b;
+  return (x > y) - (x < y);
+}
+
+int bvgo_advi(bvgo_ctx *c, const double *th0, const bvgo_advi_cfg *cfg, double *mu, double *om,
+              bvgo_advi_result *res, double *trace, int trace_cap) {
+  const int64_t D = c->L.D;
+  double *hist = (double *)calloc(2 * (size_t)D, sizeof(double));
+  uint32_t tg = 0, te = 0; /* running draw counters */
+  int gevals = 0, eevals = 0;
+  double eta = cfg->eta;
+  memset(res, 0, sizeof(*res));
+  if (eta <= 0) { /* adapt_eta */
+    static const double seq[5] = {100, 10, 1, 0.1, 0.01};
+    memcpy(mu, th0, sizeof(double) * D);
+    memset(om, 0, sizeof(double) * D);
+    const double e0 = bvgo_elbo(c, mu, om, cfg->elbo_samples, cfg->seed, te);
+    te += cfg->elbo_samples; ++eevals;
+    if (!isfinite(e0)) { free(hist); return -2; }
+    double ebest = -INFINITY, e = -INFINITY, eta_best = 0;
+    for (int q = 0;; ++q) {
+      memcpy(mu, th0, sizeof(double) * D);
+      memset(om, 0, sizeof(double) * D);
+      for (int it = 1; it <= cfg->adapt_iter; ++it) {
+        bvgo_advi_step(c, mu, om, hist, seq[q], it, cfg->seed, tg++);
+        ++gevals;
+      }
+      e = bvgo_elbo(c, mu, om, cfg->elbo_samples, cfg->seed, te);
+      te += cfg->elbo_samples; ++eevals;
+      if (isnan(e)) e = -INFINITY;
+      if (e < ebest && ebest > e0) break; /* previous eta stands */
+      if (q < 4) { ebest = e; eta_best = seq[q]; }
+      else {
+        if (e > e0) { ebest = e; eta_best = seq[q]; break; }
+        free(hist);
+        return -3; /* "All proposed step-sizes failed" */
+      }
+      memset(hist, 0, sizeof(double) * 2 * D);
+    }
+    eta = eta_best;
+  }
+  /* stochastic_gradient_ascent */
+  memcpy(mu, th0, sizeof(double) * D);
+  memset(om, 0, sizeof(double) * D);
+  memset(hist, 0, sizeof(double) * 2 * D);
+  int cbn = (int)fmax(0.1 * cfg->iter / cfg->eval_elbo, 2.0);
+  double *cb = (double *)malloc(sizeof(double) * 2 * cbn), *tmp = cb + cbn;
+  int cbc = 0, cbh = 0, ntr = 0, conv = 0, it;
+  double elbo = 0, elbo_prev;
+  for (it = 1; it <= cfg->iter; ++it) {
+    if (bvgo_advi_step(c, mu, om, hist, eta, it, cfg->seed, tg++)) {
+      /* main loop: a failing gradient is an error in Stan; report it */
+      free(cb); free(hist);
+      res->eta = eta; res->iters = it; res->grad_evals = gevals + it;
+      return -4;
+    }
+    if (it % cfg->eval_elbo == 0) {
+      elbo_prev = elbo;
+      elbo = bvgo_elbo(c, mu, om, cfg->elbo_samples, cfg->seed, te);
+      te += cfg->elbo_samples; ++eevals;
+      const double d = fabs((elbo - elbo_prev) / elbo);
+      cb[cbh] = d; cbh = (cbh + 1) % cbn; if (cbc < cbn) ++cbc;
+      double mean = 0;
+      for (int i = 0; i < cbc; ++i) { mean += cb[i]; tmp[i] = cb[i]; }
+      mean /= cbc;
+      qsort(tmp, cbc, sizeof(double), cmp_d);
+      /* Stan's circ_buff_median: nth_element at size/2 */
+      const double med = tmp[cbc / 2];
+      if (trace && ntr < trace_cap) {
+        trace[4 * ntr + 0] = it; trace[4 * ntr + 1] = elbo; trace[4 * ntr + 2] = mean; trace[4 * ntr + 3] = med;
+        ++ntr;
+      }
+      if (mean < cfg->tol_rel_obj) conv |= 1;
+      if (med < cfg->tol_rel_obj) conv |= 2;
+      if (conv) break;
+    }
+  }
+  if (it > cfg->iter) it = cfg->iter;
+  res->eta = eta; res->iters = it; res->grad_evals = gevals + it; res->elbo_evals = eevals;
+  res->converged = conv; res->elbo = elbo; res->n_trace = ntr;
+  free(cb);
+  free(hist);
+  return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * L-BFGS [U: stan::optimization::BFGSMinimizer<LBFGSUpdate>], invoked by
+ * R/findSpatiallyVariableFeaturesBayes.R:346-353 (init = 0, jacobian = FALSE, iter = mle.iter,
+ * history_size = 25).  Minimises f = -log_prob<propto=false, jacobian=false>.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct { bvgo_ctx *c; int64_t D; int fevals; } fobj;
+static int feval(fobj *o, const double *x, double *f, double *g) {
+  const double lp = bvgo_log_prob(o->c, x, 0, 0, g);
+  o->fevals++;
+  *f = -lp;
+  int ok = isfinite(lp);
+  for (int64_t i = 0; i < o->D; ++i) { g[i] = -g[i]; if (!isfinite(g[i])) ok = 0; }
+  return ok ? 0 : 1;
+}
+static double dot(const double *a, const double *b, int64_t n) {
+  double s = 0;
+  for (int64_t i = 0; i < n; ++i) s += a[i] * b[i];
+  return s;
+}
+/* minimiser on [lo,hi] of the cubic through (0,0) slope df0 and (x1,f1) slope df1 */
+static double cubic_interp(double df0, double x1, double f1, double df1, double lo, double hi) {
+  const double c3 = (-12 * f1 + 6 * x1 * (df0 + df1)) / (x1 * x1 * x1);
+  const double c2 = -(4 * df0 + 2 * df1) / x1 + 6 * f1 / (x1 * x1);
+  const double c1 = df0;
+  const double ts = sqrt(c2 * c2 - 2.0 * c1 * c3);
+  const double s1 = -(c2 + ts) / c3, s2 = -(c2 - ts) / c3;
+#define CUB(x) ((x) * ((x) * ((x) * c3 / 3.0 + c2) / 2.0 + c1))
+  double minx = lo, minf = CUB(lo), t = CUB(hi);
+  if (t < minf) { minf = t; minx = hi; }
+  if (lo < s1 && s1 < hi) { t = CUB(s1); if (t < minf) { minf = t; minx = s1; } }
+  if (lo < s2 && s2 < hi) { t = CUB(s2); if (t < minf) { minf = t; minx = s2; } }
+#undef CUB
+  return minx;
+}
+static int ls_zoom(fobj *o, double *alpha, double *x1, double *f1, double *g1, const double *x0,
+                   double f0, double c1dfp, double c2dfp, const double *p, double alo, double aloF,
+                   double aloD, double ahi, double ahiF, double ahiD) {
+  const int64_t D = o->D;
+  for (int itn = 1;; ++itn) {
+    if (fabs(alo - ahi) < 1e-16) return 1;
+    double a;
+    if (itn % 5 == 0) a = 0.5 * (alo + ahi);
+    else {
+      const double d1 = aloD + ahiD - 3 * (aloF - ahiF) / (alo - ahi);
+      double d2 = sqrt(d1 * d1 - aloD * ahiD);
+      if (ahi < alo) d2 = -d2;
+      a = ahi - (ahi - alo) * (ahiD + d2 - d1) / (ahiD - aloD + 2 * d2);
+      const double mn = fmin(alo, ahi), mx = fmax(alo, ahi), w = fabs(alo - ahi);
+      if (!isfinite(a) || a < mn + 0.01 * w || a > mx - 0.01 * w) a = 0.5 * (alo + ahi);
+    }
+    for (int64_t i = 0; i < D; ++i) x1[i] = x0[i] + a * p[i];
+    while (feval(o, x1, f1, g1)) {
+      a = 0.5 * (a + fmin(alo, ahi));
+      if (fabs(fmin(alo, ahi) - a) < 1e-16) return 1;
+      for (int64_t i = 0; i < D; ++i) x1[i] = x0[i] + a * p[i];
+    }
+    const double nd = dot(g1, p, D);
+    *alpha = a;
+    if (*f1 > f0 + a * c1dfp || *f1 >= aloF) { ahi = a; ahiF = *f1; ahiD = nd; }
+    else {
+      if (fabs(nd) <= -c2dfp) return 0;
+      if (nd * (ahi - alo) >= 0) { ahi = alo; ahiF = aloF; ahiD = aloD; }
+      alo = a; aloF = *f1; aloD = nd;
+    }
+  }
+}
+static int wolfe_ls(fobj *o, double *alpha, double *x1, double *f1, double *g1, const double *p,
+                    const double *x0, double f0, const double *g0) {
+  const int64_t D = o->D;
+  const double c1 = 1e-4, c2 = 0.9, min_alpha = 1e-12;
+  const int max_its = 20, max_restarts = 10;
+  const double dfp = dot(g0, p, D), c1dfp = c1 * dfp, c2dfp = c2 * dfp;
+  double a0 = min_alpha, prevF = f0, prevD = dfp;
+  int nits = 0, restarts = 0;
+  for (;;) {
+    if (nits >= max_its) return 1;
+    for (int64_t i = 0; i < D; ++i) x1[i] = x0[i] + *alpha * p[i];
+    if (feval(o, x1, f1, g1)) {
+      if (restarts >= max_restarts) return 1;
+      *alpha = 0.5 * (a0 + *alpha);
+      ++restarts;
+      continue;
+    }
+    restarts = 0;
+    const double nd = dot(g1, p, D);
+    if (*f1 > f0 + *alpha * c1dfp || (*f1 >= prevF && nits > 0))
+      return ls_zoom(o, alpha, x1, f1, g1, x0, f0, c1dfp, c2dfp, p, a0, prevF, prevD, *alpha, *f1, nd);
+    if (fabs(nd) <= -c2dfp) return 0;
+    if (nd >= 0)
+      return ls_zoom(o, alpha, x1, f1, g1, x0, f0, c1dfp, c2dfp, p, *alpha, *f1, nd, a0, prevF, prevD);
+    a0 = *alpha; prevF = *f1; prevD = nd;
+    *alpha *= 10.0;
+    ++nits;
+  }
+}
+
+int bvgo_lbfgs(bvgo_ctx *c, const double *th0, const bvgo_lbfgs_cfg *cfg, double *out,
+               bvgo_lbfgs_result *res) {
+  const int64_t D = c->L.D;
+  const int m = cfg->history;
+  fobj o = {c, D, 0};
+  double *buf = (double *)malloc(sizeof(double) * D * (size_t)(8 + 2 * m));
+  double *xk = buf, *gk = xk + D, *pk = gk + D, *xk1 = pk + D, *gk1 = xk1 + D, *pk1 = gk1 + D,
+         *sk = pk1 + D, *yk = sk + D, *Sh = yk + D, *Yh = Sh + (size_t)m * D;
+  double *rho = (double *)malloc(sizeof(double) * 2 * m), *alph = rho + m;
+  int nh = 0, head = 0; /* circular history */
+  double fk, fk1 = 0, gamma = 1, alpha = cfg->init_alpha, alphak1 = 0;
+  memcpy(xk, th0, sizeof(double) * D);
+  int term = 0, it = 0;
+  if (feval(&o, xk, &fk, gk)) { free(buf); free(rho); return -1; }
+  for (int64_t i = 0; i < D; ++i) pk[i] = -gk[i];
+  const double eps = DBL_EPSILON;
+  while (!term) {
+    ++it;
+    int resetB = (it == 1) ? 1 : 0;
+    for (;;) {
+      if (resetB) for (int64_t i = 0; i < D; ++i) pk[i] = -gk[i];
+      if (it > 1 && resetB != 2)
+        alpha = fmin(1.0, 1.01 * cubic_interp(dot(gk1, pk1, D), alphak1, fk - fk1, dot(gk, pk, D), 1e-12, 1.0));
+      else alpha = cfg->init_alpha;
+      const int rc = wolfe_ls(&o, &alpha, xk1, &fk1, gk1, pk, xk, fk, gk);
+      if (rc) {
+        if (resetB) { term = -1; break; } /* TERM_LSFAIL */
+        resetB = 2;
+        continue;
+      }
+      break;
+    }
+    if (term) break;
+    /* swap so that k is the newest iterate */
+    { double t = fk; fk = fk1; fk1 = t; }
+    { double *t; t = xk; xk = xk1; xk1 = t; t = gk; gk = gk1; gk1 = t; t = pk; pk = pk1; pk1 = t; }
+    for (int64_t i = 0; i < D; ++i) { sk[i] = xk[i] - xk1[i]; yk[i] = gk[i] - gk1[i]; }
+    const double gnorm = sqrt(dot(gk, gk, D)), snorm = sqrt(dot(sk, sk, D));
+    const double skyk = dot(sk, yk, D), ykyk = dot(yk, yk, D);
+    if (resetB) {
+      const double B0 = ykyk / skyk;
+      nh = 0; head = 0;
+      for (int64_t i = 0; i < D; ++i) pk1[i] /= B0;
+      alphak1 = alpha * B0;
+    } else alphak1 = alpha;
+    gamma = skyk / ykyk;
+    memcpy(Sh + (size_t)head * D, sk, sizeof(double) * D);
+    memcpy(Yh + (size_t)head * D, yk, sizeof(double) * D);
+    rho[head] = 1.0 / skyk;
+    head = (head + 1) % m;
+    if (nh < m) ++nh;
+    /* convergence tests */
+    if (fabs(fk1 - fk) < cfg->tol_obj) term = 1;
+    else if (fabs(fk1 - fk) < cfg->tol_rel_obj * eps * fmax(fabs(fk1), fmax(fabs(fk), 1.0))) term = 2;
+    else if (gnorm < cfg->tol_grad) term = 3;
+    else if (snorm < cfg->tol_param) term = 4;
+    else if (it >= cfg->max_iter) term = 5;
+    /* new direction: two-loop recursion, pk = -H gk */
+    for (int64_t i = 0; i < D; ++i) pk[i] = -gk[i];
+    for (int q = 0; q < nh; ++q) {
+      const int h = (head - 1 - q + 2 * m) % m;
+      alph[h] = rho[h] * dot(Sh + (size_t)h * D, pk, D);
+      const double a = alph[h];
+      const double *Y = Yh + (size_t)h * D;
+      for (int64_t i = 0; i < D; ++i) pk[i] -= a * Y[i];
+    }
+    for (int64_t i = 0; i < D; ++i) pk[i] *= gamma;
+    for (int q = nh - 1; q >= 0; --q) {
+      const int h = (head - 1 - q + 2 * m) % m;
+      const double b = rho[h] * dot(Yh + (size_t)h * D, pk, D);
+      const double *S = Sh + (size_t)h * D;
+      const double a = alph[h] - b;
+      for (int64_t i = 0; i < D; ++i) pk[i] += a * S[i];
+    }
+    if (!term) { /* relative gradient test: g' H g / max(|f|, 1) */
+      const double rg = -dot(gk, pk, D) / fmax(fabs(fk), 1.0);
+      if (rg < cfg->tol_rel_grad * eps) term = 6;
+    }
+  }
+  memcpy(out, xk, sizeof(double) * D);
+  res->iters = it; res->fevals = o.fevals; res->term = term; res->lp = -fk;
+  free(buf);
+  free(rho);
+  return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Posterior draws + amplitude summary.
+ * R/findSpatiallyVariableFeaturesBayes.R:419-432: fit_vi$summary("amplitude") over the n.draws
+ * draws -> mean, median, sd (n-1), mad (1.4826 * median|x - med|), q5, q95 (quantile type 7) [U:
+ * posterior::default_summary_measures], dispersion = sd^2/mean (:428), rank by mean desc (:429-430).
+ * ---------------------------------------------------------------------------------------- */
+static double quantile7(const double *sorted, int n, double p) {
+  const double h = (n - 1) * p;
+  const int lo = (int)floor(h);
+  const int hi = lo + 1 < n ? lo + 1 : lo;
+  return sorted[lo] + (h - lo) * (sorted[hi] - sorted[lo]);
+}
+typedef struct { double v; int64_t i; } rank_t;
+static int cmp_rank(const void *a, const void *b) {
+  const rank_t *x = (const rank_t *)a, *y = (const rank_t *)b;
+  if (x->v > y->v) return -1;
+  if (x->v < y->v) return 1;
+  return (x->i > y->i) - (x->i < y->i);
+}
+int bvgo_summary(int model, int64_t G, int k, const double *mu, const double *om, int nd,
+                 uint64_t seed, int64_t gene_offset, int64_t G_total, double *out) {
+  const layout_t L = make_layout(model, G, k), LG = make_layout(model, G_total, k);
+  double *x = (double *)malloc(sizeof(double) * 2 * nd), *d = x + nd;
+  rank_t *rk = (rank_t *)malloc(sizeof(rank_t) * G);
+  for (int64_t g = 0; g < G; ++g) {
+    const double m = mu[L.amp + g], s = exp(om[L.amp + g]);
+    const uint64_t gi = (uint64_t)(LG.amp + gene_offset + g); /* global index of amplitude[g] */
+    double mean = 0;
+    for (int t = 0; t < nd; ++t) {
+      x[t] = exp(m + s * bvgo_normal(seed, STREAM_DRAW, (uint32_t)t, gi));
+      mean += x[t];
+    }
+    mean /= nd;
+    double ss = 0;
+    for (int t = 0; t < nd; ++t) ss += (x[t] - mean) * (x[t] - mean);
+    const double sd = sqrt(ss / (nd - 1));
+    qsort(x, nd, sizeof(double), cmp_d);
+    const double med = quantile7(x, nd, 0.5);
+    for (int t = 0; t < nd; ++t) d[t] = fabs(x[t] - med);
+    qsort(d, nd, sizeof(double), cmp_d);
+    out[0 * G + g] = mean;
+    out[1 * G + g] = med;
+    out[2 * G + g] = sd;
+    out[3 * G + g] = 1.4826 * quantile7(d, nd, 0.5);
+    out[4 * G + g] = quantile7(x, nd, 0.05);
+    out[5 * G + g] = quantile7(x, nd, 0.95);
+    out[6 * G + g] = sd * sd / mean;
+    rk[g].v = mean;
+    rk[g].i = g;
+  }
+  qsort(rk, G, sizeof(rank_t), cmp_rank);
+  for (int64_t r = 0; r < G; ++r) out[7 * G + rk[r].i] = (double)(r + 1);
+  free(rk);
+  free(x);
+  return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Basis builder.  R/findSpatiallyVariableFeaturesBayes.R:265-281 (kernel between every spot and
+ * every k-means centroid on SQUARED distances), R/maternKernel.R:22-26, R/expQuadKernel.R:17,
+ * R/periodicKernel.R:20, then :283-288 qr.Q(qr(phi, LAPACK = TRUE)) = thin Q of column-pivoted
+ * Householder QR [U: LAPACK dgeqp3 + dorgqr].
+ * ---------------------------------------------------------------------------------------- */
+static double kern(double d2, double ls, int kernel, double nu, double period) {
+  if (kernel == BVGO_KERNEL_EXP_QUAD) return exp(-d2 / (2.0 * ls * ls));
+  if (kernel == BVGO_KERNEL_PERIODIC) {
+    const double sn = sin(M_PI * sqrt(d2) / period);
+    return exp(-2.0 * sn * sn / (ls * ls));
+  }
+  /* Matern: (2^(1-nu)/Gamma(nu)) s^nu K_nu(s), s = sqrt(2 nu) sqrt(d)/l; non-finite (d = 0) -> 1.
+   * For nu in {1/2, 3/2, 5/2} (the only values accepted, :106) the Bessel form equals: */
+  const double s = sqrt(2.0 * nu) * sqrt(d2) / ls;
+  if (nu == 0.5) return exp(-s);
+  if (nu == 1.5) return (1.0 + s) * exp(-s);
+  return (1.0 + s + s * s / 3.0) * exp(-s);
+}
+static double nrm2(const double *x, int64_t n) {
+  /* scaled 2-norm (dnrm2 semantics) */
+  double scale = 0, ssq = 1;
+  for (int64_t i = 0; i < n; ++i)
+    if (x[i] != 0) {
+      const double a = fabs(x[i]);
+      if (scale < a) { ssq = 1 + ssq * (scale / a) * (scale / a); scale = a; }
+      else ssq += (a / scale) * (a / scale);
+    }
+  return scale * sqrt(ssq);
+}
+int bvgo_basis(const double *X, int64_t M, const double *C, int k, double ls, int kernel, double nu,
+               double period, double *Q, double *raw) {
+  double *A = (double *)malloc(sizeof(double) * M * k);
+  for (int j = 0; j < k; ++j)
+    for (int64_t s = 0; s < M; ++s) {
+      const double dx = X[s] - C[j], dy = X[M + s] - C[k + j];
+      A[(int64_t)j * M + s] = kern(dx * dx + dy * dy, ls, kernel, nu, period);
+    }
+  if (raw) memcpy(raw, A, sizeof(double) * M * k);
+  double *vn1 = (double *)malloc(sizeof(double) * 3 * k), *vn2 = vn1 + k, *tau = vn2 + k;
+  for (int j = 0; j < k; ++j) vn1[j] = vn2[j] = nrm2(A + (int64_t)j * M, M);
+  const double tol3z = sqrt(DBL_EPSILON);
+  for (int j = 0; j < k && j < M; ++j) {
+    int pv = j;
+    for (int c2 = j + 1; c2 < k; ++c2) if (vn1[c2] > vn1[pv]) pv = c2; /* idamax: first maximum */
+    if (pv != j) {
+      for (int64_t s = 0; s < M; ++s) { double t = A[(int64_t)pv * M + s]; A[(int64_t)pv * M + s] = A[(int64_t)j * M + s]; A[(int64_t)j * M + s] = t; }
+      vn1[pv] = vn1[j]; vn2[pv] = vn2[j];
+    }
+    double *a = A + (int64_t)j * M;
+    /* dlarfg */
+    const double alpha = a[j], xn = nrm2(a + j + 1, M - j - 1);
+    if (xn == 0) tau[j] = 0;
+    else {
+      const double beta = -copysign(hypot(alpha, xn), alpha);
+      tau[j] = (beta - alpha) / beta;
+      const double sc = 1.0 / (alpha - beta);
+      for (int64_t s = j + 1; s < M; ++s) a[s] *= sc;
+      a[j] = beta;
+    }
+    /* apply H_j to trailing columns */
+    for (int c2 = j + 1; c2 < k; ++c2) {
+      double *b = A + (int64_t)c2 * M;
+      double w = b[j];
+      for (int64_t s = j + 1; s < M; ++s) w += a[s] * b[s];
+      w *= tau[j];
+      b[j] -= w;
+      for (int64_t s = j + 1; s < M; ++s) b[s] -= w * a[s];
+      /* dlaqp2 partial-norm downdate */
+      if (vn1[c2] != 0) {
+        double t = 1.0 - (fabs(b[j]) / vn1[c2]) * (fabs(b[j]) / vn1[c2]);
+        t = t > 0 ? t : 0;
+        const double t2 = t * (vn1[c2] / vn2[c2]) * (vn1[c2] / vn2[c2]);
+        if (t2 <= tol3z) { vn1[c2] = nrm2(b + j + 1, M - j - 1); vn2[c2] = vn1[c2]; }
+        else vn1[c2] *= sqrt(t);
+      }
+    }
+  }
+  /* dorg2r: Q = H_0 ... H_{k-1} [I; 0] */
+  memset(Q, 0, sizeof(double) * M * k);
+  for (int j = 0; j < k; ++j) Q[(int64_t)j * M + j] = 1.0;
+  for (int j = k - 1; j >= 0; --j) {
+    const double *a = A + (int64_t)j * M;
+    for (int c2 = j; c2 < k; ++c2) {
+      double *b = Q + (int64_t)c2 * M;
+      double w = b[j];
+      for (int64_t s = j + 1; s < M; ++s) w += a[s] * b[s];
+      w *= tau[j];
+      b[j] -= w;
+      for (int64_t s = j + 1; s < M; ++s) b[s] -= w * a[s];
+    }
+  }
+  free(vn1);
+  free(A);
+  return 0;
+}

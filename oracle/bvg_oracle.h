@@ -1,0 +1,101 @@
+/*
+ * bvg_oracle.h -- CPU oracle for the bayesVG SVG hot path.  TEST INFRASTRUCTURE ONLY.
+ *
+ * PARITY UNPINNED: the reference's arithmetic for this path lives in CmdStan / Stan Math
+ * (un-vendored, version-unpinned: DESCRIPTION:58 "SystemRequirements: CmdStan") and the
+ * reference's own tests hold no numeric golden vectors (tests/testthat/test_bayesVG.R:144-219
+ * assert classes and shapes only).  Neither R nor CmdStan exists in this image, so this file is a
+ * restatement of inst/approxGP.stan / inst/approxGP4.stan and of the published Stan algorithms
+ * (meanfield ADVI, L-BFGS), pinned only against an independent literal transcription of the Stan
+ * programs (tests/golden/make_golden.py: scipy.stats log-densities + torch-autograd fp64).
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+ * load this library.  The product (bayesvg_b200/) never does.
+ */
+#ifndef BVG_ORACLE_H
+#define BVG_ORACLE_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { BVGO_GAUSSIAN = 0 /* inst/approxGP.stan */, BVGO_NB = 1 /* inst/approxGP4.stan */ };
+enum { BVGO_KERNEL_EXP_QUAD = 0, BVGO_KERNEL_MATERN = 1, BVGO_KERNEL_PERIODIC = 2 };
+
+typedef struct bvgo_ctx bvgo_ctx;
+
+/* y: M x G column-major (R's gene-major long vector, findSpatiallyVariableFeaturesBayes.R:176-183),
+ * phi: M x k column-major (inst/approxGP.stan:8).  Buffers are borrowed, not copied. */
+bvgo_ctx *bvgo_create(int model, int64_t M, int64_t G, int k, const double *phi, const double *y,
+                      int nthreads);
+void bvgo_destroy(bvgo_ctx *);
+int64_t bvgo_dim(int model, int64_t G, int k);
+
+/* log density at an unconstrained vector (Stan declaration order);
+ * grad may be NULL (forward only).  Mirrors log_prob<propto, jacobian>. */
+double bvgo_log_prob(bvgo_ctx *, const double *theta, int jacobian, int propto, double *grad);
+
+/* counter-based RNG shared (by specification, not by code) with the CUDA engine */
+void bvgo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+double bvgo_normal(uint64_t seed, uint32_t stream, uint32_t t, uint64_t i);
+
+typedef struct {
+  int iter;          /* n.iter   = 3000  (findSpatiallyVariableFeaturesBayes.R:82)  */
+  int elbo_samples;  /* 150 (:110-116) */
+  int eval_elbo;     /* CmdStan default 100 */
+  int adapt_iter;    /* CmdStan default 50  */
+  double tol_rel_obj;/* CmdStan default 0.01 */
+  double eta;        /* <=0: adapt (CmdStan default) */
+  uint64_t seed;     /* random.seed = 312 (:95) */
+} bvgo_advi_cfg;
+
+typedef struct {
+  double eta;        /* chosen step size */
+  int iters;         /* main-loop iterations executed */
+  int grad_evals;    /* calc_ELBO_grad calls (adapt + main) */
+  int elbo_evals;    /* calc_ELBO calls */
+  int converged;     /* 1 mean, 2 median, 3 both, 0 max-iter */
+  double elbo;       /* last ELBO */
+  int n_trace;       /* rows written to trace */
+} bvgo_advi_result;
+
+/* meanfield ADVI started at theta_init (mu = theta_init, omega = 0).
+ * trace: optional [iter/eval_elbo][4] = (iter, elbo, delta_mean, delta_med). */
+int bvgo_advi(bvgo_ctx *, const double *theta_init, const bvgo_advi_cfg *, double *mu, double *omega,
+              bvgo_advi_result *, double *trace, int trace_cap);
+
+/* single ADVI pieces exposed so the CUDA engine can be checked step by step */
+double bvgo_elbo(bvgo_ctx *, const double *mu, const double *omega, int S, uint64_t seed,
+                 uint32_t t0);
+/* one calc_ELBO_grad + step; hist is the running s (2D); t = gradient draw counter (global),
+ * it = 1-based iteration counter inside the current phase */
+int bvgo_advi_step(bvgo_ctx *, double *mu, double *omega, double *hist, double eta, int it,
+                   uint64_t seed, uint32_t t);
+
+typedef struct {
+  int max_iter;      /* mle.iter = 1000 (:89) */
+  int history;       /* 25 (:353) */
+  double init_alpha; /* 1e-3 */
+  double tol_obj, tol_rel_obj, tol_grad, tol_rel_grad, tol_param; /* CmdStan defaults */
+} bvgo_lbfgs_cfg;
+typedef struct { int iters; int fevals; int term; double lp; } bvgo_lbfgs_result;
+int bvgo_lbfgs(bvgo_ctx *, const double *theta0, const bvgo_lbfgs_cfg *, double *theta_out,
+               bvgo_lbfgs_result *);
+
+/* amplitude summaries from n_draws draws of exp(mu_u + exp(omega_u) eps):
+ * out G x 8 col-major: mean, median, sd, mad, q5, q95, dispersion, rank (1 = largest mean) */
+int bvgo_summary(int model, int64_t G, int k, const double *mu, const double *omega, int n_draws,
+                 uint64_t seed, int64_t gene_offset, int64_t G_total, double *out);
+
+/* basis builder (findSpatiallyVariableFeaturesBayes.R:265-288): kernel at centroids + pivoted
+ * Householder QR (dgeqp3-equivalent), thin Q out (M x k col-major).  raw_out optional. */
+int bvgo_basis(const double *coords /*M x 2 col-major*/, int64_t M, const double *centers /*k x 2*/,
+               int k, double lscale, int kernel, double nu, double period, double *phi_out,
+               double *raw_out);
+
+double bvgo_digamma(double x);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,189 @@
+"""ctypes binding of the CPU oracle (oracle/libbvg_oracle.so).  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
+this module; the product package (bayesvg_b200/) never does.  PARITY UNPINNED -- see bvg_oracle.h.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libbvg_oracle.so")
+
+GAUSSIAN, NB = 0, 1
+KERNELS = {"exp_quad": 0, "matern": 1, "periodic": 2}
+
+
+def build(force=False):
+    src = [os.path.join(_HERE, f) for f in ("bvg_oracle.c", "bvg_oracle.h")]
+    if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in src):
+        subprocess.check_call(["make", "-C", _HERE, "-s"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    return _SO
+
+
+class _AdviCfg(C.Structure):
+    _fields_ = [("iter", C.c_int), ("elbo_samples", C.c_int), ("eval_elbo", C.c_int),
+                ("adapt_iter", C.c_int), ("tol_rel_obj", C.c_double), ("eta", C.c_double),
+                ("seed", C.c_uint64)]
+
+
+class _AdviRes(C.Structure):
+    _fields_ = [("eta", C.c_double), ("iters", C.c_int), ("grad_evals", C.c_int),
+                ("elbo_evals", C.c_int), ("converged", C.c_int), ("elbo", C.c_double),
+                ("n_trace", C.c_int)]
+
+
+class _LbfgsCfg(C.Structure):
+    _fields_ = [("max_iter", C.c_int), ("history", C.c_int), ("init_alpha", C.c_double),
+                ("tol_obj", C.c_double), ("tol_rel_obj", C.c_double), ("tol_grad", C.c_double),
+                ("tol_rel_grad", C.c_double), ("tol_param", C.c_double)]
+
+
+class _LbfgsRes(C.Structure):
+    _fields_ = [("iters", C.c_int), ("fevals", C.c_int), ("term", C.c_int), ("lp", C.c_double)]
+
+
+_lib = None
+_dp = C.POINTER(C.c_double)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            build()
+        L = C.CDLL(_SO)
+        L.bvgo_create.restype = C.c_void_p
+        L.bvgo_create.argtypes = [C.c_int, C.c_int64, C.c_int64, C.c_int, _dp, _dp, C.c_int]
+        L.bvgo_destroy.argtypes = [C.c_void_p]
+        L.bvgo_dim.restype = C.c_int64
+        L.bvgo_dim.argtypes = [C.c_int, C.c_int64, C.c_int]
+        L.bvgo_log_prob.restype = C.c_double
+        L.bvgo_log_prob.argtypes = [C.c_void_p, _dp, C.c_int, C.c_int, _dp]
+        L.bvgo_normal.restype = C.c_double
+        L.bvgo_normal.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64]
+        L.bvgo_philox4x32_10.argtypes = [C.POINTER(C.c_uint32)] * 3
+        L.bvgo_elbo.restype = C.c_double
+        L.bvgo_elbo.argtypes = [C.c_void_p, _dp, _dp, C.c_int, C.c_uint64, C.c_uint32]
+        L.bvgo_advi_step.argtypes = [C.c_void_p, _dp, _dp, _dp, C.c_double, C.c_int, C.c_uint64, C.c_uint32]
+        L.bvgo_advi.argtypes = [C.c_void_p, _dp, C.POINTER(_AdviCfg), _dp, _dp, C.POINTER(_AdviRes), _dp, C.c_int]
+        L.bvgo_lbfgs.argtypes = [C.c_void_p, _dp, C.POINTER(_LbfgsCfg), _dp, C.POINTER(_LbfgsRes)]
+        L.bvgo_summary.argtypes = [C.c_int, C.c_int64, C.c_int, _dp, _dp, C.c_int, C.c_uint64, C.c_int64, C.c_int64, _dp]
+        L.bvgo_basis.argtypes = [_dp, C.c_int64, _dp, C.c_int, C.c_double, C.c_int, C.c_double, C.c_double, _dp, _dp]
+        L.bvgo_digamma.restype = C.c_double
+        L.bvgo_digamma.argtypes = [C.c_double]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(_dp)
+
+
+def _f(a):
+    return np.asfortranarray(np.asarray(a, dtype=np.float64))
+
+
+class Oracle:
+    """One dataset: Y (M x G), Phi (M x k).  model: 'gaussian' | 'nb'."""
+
+    def __init__(self, phi, y, model="gaussian", nthreads=1):
+        self.model = {"gaussian": GAUSSIAN, "nb": NB}[model]
+        self.phi, self.y = _f(phi), _f(y)
+        self.M, self.k = self.phi.shape
+        assert self.y.shape[0] == self.M
+        self.G = self.y.shape[1]
+        self.D = int(lib().bvgo_dim(self.model, self.G, self.k))
+        self._h = lib().bvgo_create(self.model, self.M, self.G, self.k, _p(self.phi), _p(self.y), nthreads)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().bvgo_destroy(self._h)
+            self._h = None
+
+    def log_prob(self, theta, jacobian=True, propto=True, grad=True):
+        th = np.ascontiguousarray(theta, dtype=np.float64)
+        assert th.shape == (self.D,)
+        g = np.empty(self.D) if grad else None
+        lp = lib().bvgo_log_prob(self._h, _p(th), int(jacobian), int(propto), _p(g) if grad else None)
+        return (lp, g) if grad else lp
+
+    def elbo(self, mu, omega, S=150, seed=312, t0=0):
+        mu = np.ascontiguousarray(mu, dtype=np.float64)
+        om = np.ascontiguousarray(omega, dtype=np.float64)
+        return lib().bvgo_elbo(self._h, _p(mu), _p(om), S, seed, t0)
+
+    def advi_step(self, mu, omega, hist, eta, it, seed, t):
+        """in-place on mu, omega (D) and hist (2D)"""
+        return lib().bvgo_advi_step(self._h, _p(mu), _p(omega), _p(hist), eta, it, seed, t)
+
+    def advi(self, theta_init, iter=3000, elbo_samples=150, eval_elbo=100, adapt_iter=50,
+             tol_rel_obj=0.01, eta=0.0, seed=312):
+        cfg = _AdviCfg(iter, elbo_samples, eval_elbo, adapt_iter, tol_rel_obj, eta, seed)
+        res = _AdviRes()
+        th = np.ascontiguousarray(theta_init, dtype=np.float64)
+        mu, om = np.empty(self.D), np.empty(self.D)
+        cap = iter // eval_elbo + 1
+        tr = np.zeros((cap, 4))
+        rc = lib().bvgo_advi(self._h, _p(th), C.byref(cfg), _p(mu), _p(om), C.byref(res), _p(tr), cap)
+        info = {f: getattr(res, f) for f, _ in _AdviRes._fields_}
+        info["rc"] = rc
+        info["trace"] = tr[: res.n_trace].copy()
+        return mu, om, info
+
+    def lbfgs(self, theta0=None, max_iter=1000, history=25):
+        th0 = np.zeros(self.D) if theta0 is None else np.ascontiguousarray(theta0, dtype=np.float64)
+        cfg = _LbfgsCfg(max_iter, history, 1e-3, 1e-12, 1e4, 1e-8, 1e7, 1e-8)
+        res = _LbfgsRes()
+        out = np.empty(self.D)
+        rc = lib().bvgo_lbfgs(self._h, _p(th0), C.byref(cfg), _p(out), C.byref(res))
+        return out, {"rc": rc, "iters": res.iters, "fevals": res.fevals, "term": res.term, "lp": res.lp}
+
+    def summary(self, mu, omega, n_draws=1000, seed=312, gene_offset=0, G_total=None):
+        mu = np.ascontiguousarray(mu, dtype=np.float64)
+        om = np.ascontiguousarray(omega, dtype=np.float64)
+        out = np.empty((self.G, 8), order="F")
+        lib().bvgo_summary(self.model, self.G, self.k, _p(mu), _p(om), n_draws, seed, gene_offset,
+                           self.G if G_total is None else G_total, _p(out))
+        return out
+
+
+def normal(seed, stream, t, i):
+    return lib().bvgo_normal(seed, stream, t, i)
+
+
+def philox(ctr, key):
+    c = (C.c_uint32 * 4)(*ctr)
+    k = (C.c_uint32 * 2)(*key)
+    o = (C.c_uint32 * 4)()
+    lib().bvgo_philox4x32_10(c, k, o)
+    return [int(x) for x in o]
+
+
+def basis(coords, centers, lscale, kernel="matern", nu=2.5, period=100.0, return_raw=False):
+    X, Cc = _f(coords), _f(centers)
+    M, k = X.shape[0], Cc.shape[0]
+    Q = np.empty((M, k), order="F")
+    raw = np.empty((M, k), order="F") if return_raw else None
+    lib().bvgo_basis(_p(X), M, _p(Cc), k, lscale, KERNELS[kernel], nu, period, _p(Q), _p(raw) if return_raw else None)
+    return (Q, raw) if return_raw else Q
+
+
+def digamma(x):
+    return lib().bvgo_digamma(x)
+
+
+def layout(model, G, k):
+    """slot offsets of the unconstrained vector"""
+    if model in ("gaussian", GAUSSIAN):
+        o = dict(mu_beta0=0, sigma_beta0=1, z_beta0=2, mu_amplitude=2 + G, sigma_amplitude=3 + G,
+                 amplitude=4 + G, mu_alpha=4 + 2 * G, sigma_alpha=4 + 2 * G + k, z_alpha_t=4 + 2 * G + 2 * k,
+                 sigma_y=4 + 2 * G + 2 * k + k * G)
+    else:
+        o = dict(mu_beta0=0, sigma_beta0=1, z_beta0=2, phi_nb=2 + G, amplitude=3 + G, mu_amplitude=3 + 2 * G,
+                 sigma_amplitude=4 + 2 * G, mu_alpha=5 + 2 * G, sigma_alpha=5 + 2 * G + k,
+                 z_alpha_t=5 + 2 * G + 2 * k)
+    o["D"] = 5 + 2 * G + 2 * k + k * G
+    return o

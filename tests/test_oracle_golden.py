@@ -1,0 +1,105 @@
+"""CPU: the oracle (oracle/bvg_oracle.c) against the committed golden vectors.
+
+The golden vectors come from tests/golden/make_golden.py -- a literal, statement-by-statement
+transcription of inst/approxGP.stan / inst/approxGP4.stan evaluated with scipy.stats + torch
+autograd (fp64).  Tolerance: 1e-9 relative on log-density, 1e-8 norm-wise on gradients (fp64
+round-off of two different summation orders).
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+
+CASES = [("gp_small", "gaussian"), ("gp4_small", "nb"), ("gp_ragged", "gaussian"), ("gp4_ragged", "nb")]
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name + ".npz"))
+
+
+@pytest.mark.parametrize("name,model", CASES)
+@pytest.mark.parametrize("nthreads", [1, 3])
+def test_log_prob_and_grad_match_stan_transcription(golden_dir, name, model, nthreads):
+    z = _load(golden_dir, name)
+    o = orc.Oracle(z["phi"], z["y"], model, nthreads=nthreads)
+    assert o.D == z["thetas"].shape[1]
+    for jac in (0, 1):
+        for pro in (0, 1):
+            for t, th in enumerate(z["thetas"]):
+                lp, g = o.log_prob(th, jacobian=jac, propto=pro)
+                ref_lp, ref_g = z[f"lp_j{jac}_p{pro}"][t], z[f"grad_j{jac}_p{pro}"][t]
+                assert abs(lp - ref_lp) <= 1e-9 * max(1.0, abs(ref_lp)), (name, jac, pro, t, lp, ref_lp)
+                assert np.linalg.norm(g - ref_g) <= 1e-8 * np.linalg.norm(ref_g), (name, jac, pro, t)
+                assert np.max(np.abs(g - ref_g) / (1e-6 + np.abs(ref_g))) < 1e-6
+                lp2 = o.log_prob(th, jacobian=jac, propto=pro, grad=False)
+                assert lp2 == pytest.approx(lp, rel=1e-13)
+
+
+@pytest.mark.parametrize("name,model", CASES[:2])
+def test_gradient_central_differences(golden_dir, name, model):
+    z = _load(golden_dir, name)
+    o = orc.Oracle(z["phi"], z["y"], model)
+    th = z["thetas"][1]
+    _, g = o.log_prob(th, jacobian=1, propto=1)
+    rng = np.random.default_rng(0)
+    for i in rng.choice(o.D, 25, replace=False):
+        h = 1e-5
+        e = np.zeros(o.D)
+        e[i] = h
+        fd = (o.log_prob(th + e, grad=False) - o.log_prob(th - e, grad=False)) / (2 * h)
+        assert fd == pytest.approx(g[i], rel=2e-5, abs=2e-5)
+
+
+def test_philox_known_answers():
+    # Random123 kat_vectors, philox4x32-10
+    assert orc.philox([0] * 4, [0] * 2) == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+    assert orc.philox([0xFFFFFFFF] * 4, [0xFFFFFFFF] * 2) == [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]
+    assert orc.philox([0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344], [0xA4093822, 0x299F31D0]) == [
+        0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]
+
+
+def test_normal_moments():
+    x = np.array([orc.normal(312, 1, 3, i) for i in range(100000)])
+    assert abs(x.mean()) < 0.01 and abs(x.std() - 1) < 0.01 and abs((x ** 4).mean() - 3) < 0.1
+    assert orc.normal(312, 1, 3, 5) != orc.normal(312, 2, 3, 5) != orc.normal(313, 1, 3, 5)
+
+
+def test_digamma():
+    from scipy.special import digamma
+    for x in (1e-3, 0.3, 1.0, 2.5, 9.99, 10.0, 57.0, 1e5):
+        assert orc.digamma(x) == pytest.approx(digamma(x), rel=1e-13, abs=1e-13)
+
+
+@pytest.mark.parametrize("kname,kernel,nu,period", [
+    ("exp_quad", "exp_quad", 0.0, 1.0), ("matern0.5", "matern", 0.5, 1.0), ("matern1.5", "matern", 1.5, 1.0),
+    ("matern2.5", "matern", 2.5, 1.0), ("periodic", "periodic", 0.0, 3.0)])
+def test_basis_matches_lapack_dgeqp3(golden_dir, kname, kernel, nu, period):
+    z = _load(golden_dir, "basis")
+    Q, raw = orc.basis(z["coords"], z["centers"], float(z["lscale"]), kernel, nu, period, return_raw=True)
+    # kernel values: closed forms == besselK form of R/maternKernel.R:22-26
+    assert np.max(np.abs(raw - z[f"raw_{kname}"])) < 5e-15
+    Qref = z[f"Q_{kname}"]
+    assert np.max(np.abs(Q.T @ Q - np.eye(Q.shape[1]))) < 1e-12
+    # same pivots + same Householder sign convention -> same Q, sign included
+    cond = np.linalg.cond(z[f"raw_{kname}"])
+    assert np.max(np.abs(Q - Qref)) < 1e-15 * cond * 50 + 1e-12, (kname, cond)
+
+
+def test_summary_against_numpy():
+    G, k, nd, seed = 7, 3, 1000, 312
+    lay = orc.layout("gaussian", G, k)
+    rng = np.random.default_rng(1)
+    mu, om = rng.normal(size=lay["D"]), rng.normal(-1, 0.3, size=lay["D"])
+    phi, y = np.linalg.qr(rng.normal(size=(11, k)))[0], rng.normal(size=(11, G))
+    out = orc.Oracle(phi, y).summary(mu, om, nd, seed)
+    for g in range(G):
+        i = lay["amplitude"] + g
+        x = np.exp(mu[i] + np.exp(om[i]) * np.array([orc.normal(seed, 3, t, i) for t in range(nd)]))
+        med = np.median(x)
+        ref = [x.mean(), med, x.std(ddof=1), 1.4826 * np.median(np.abs(x - med)), np.quantile(x, 0.05),
+               np.quantile(x, 0.95), x.var(ddof=1) / x.mean()]
+        assert np.allclose(out[g, :7], ref, rtol=1e-12)
+    assert sorted(out[:, 7]) == list(range(1, G + 1))
+    assert np.all(np.diff(out[np.argsort(out[:, 7]), 0]) <= 0)
