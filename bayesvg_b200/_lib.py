@@ -1,0 +1,107 @@
+"""ctypes binding of include/bayesvg_b200.h (the C ABI an R package would reach through .Call).
+
+There is no CPU fallback: if libbayesvg_b200.so is missing this module raises at import of the
+library handle, and every compute entry point fails with BVG_ERR_CUDA when no device is present.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libbayesvg_b200.so")
+
+ABI_VERSION = 1
+GAUSSIAN, NB = 0, 1
+KERNELS = {"exp_quad": 0, "matern": 1, "periodic": 2}
+PREC_FP64, PREC_FAST = 0, 1
+ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05 = 0, 1, 2
+
+EXPORTS = [
+    "bvg_version", "bvg_last_error", "bvg_device_count", "bvg_config_default", "bvg_basis_build",
+    "bvg_fit_create", "bvg_fit_destroy", "bvg_fit_set_phi", "bvg_fit_set_y_f64", "bvg_fit_set_y_i32",
+    "bvg_fit_dim", "bvg_comm_unique_id", "bvg_fit_comm_init", "bvg_log_prob", "bvg_fit_run", "bvg_fit_mle",
+    "bvg_fit_advi", "bvg_fit_summarize", "bvg_fit_set_variational", "bvg_fit_get_variational",
+    "bvg_fit_advi_steps", "bvg_fit_elbo", "bvg_fit_time_lik_kernel", "bvg_fit_flush_l2", "bvg_fit_get_summary",
+    "bvg_fit_get_draws", "bvg_fit_get_trace", "bvg_fit_get_stats",
+]
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32), ("likelihood", C.c_int32), ("precision", C.c_int32), ("engine", C.c_int32),
+        ("device", C.c_int32), ("n_iter", C.c_int32), ("mle_init", C.c_int32), ("mle_iter", C.c_int32),
+        ("n_draws", C.c_int32), ("elbo_samples", C.c_int32), ("eval_elbo", C.c_int32), ("adapt_iter", C.c_int32),
+        ("lbfgs_history", C.c_int32), ("verbose", C.c_int32), ("tol_rel_obj", C.c_double), ("eta", C.c_double),
+        ("seed", C.c_uint64), ("rank", C.c_int32), ("world_size", C.c_int32), ("gene_offset", C.c_int64),
+        ("G_total", C.c_int64),
+    ]
+
+
+class Stats(C.Structure):
+    _fields_ = [
+        ("eta", C.c_double), ("advi_iters", C.c_int32), ("grad_evals", C.c_int32), ("elbo_evals", C.c_int32),
+        ("converged", C.c_int32), ("mle_iters", C.c_int32), ("mle_fevals", C.c_int32), ("mle_term", C.c_int32),
+        ("mle_lp", C.c_double), ("elbo", C.c_double), ("sec_h2d", C.c_double), ("sec_mle", C.c_double),
+        ("sec_adapt", C.c_double), ("sec_sga", C.c_double), ("sec_draws", C.c_double), ("sec_total", C.c_double),
+        ("kernel_launches", C.c_int64), ("engine_used", C.c_int32), ("pad", C.c_int32),
+    ]
+
+
+class BvgError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"bayesvg_b200 error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+_dp = C.POINTER(C.c_double)
+_fp = C.POINTER(C.c_float)
+_vp = C.c_void_p
+
+
+def lib():
+    """Load the shared library; fail loudly if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO_PATH):
+        raise ImportError(
+            f"{SO_PATH} not found: build the CUDA engine first (python -c 'import __graft_entry__ as g; g.build()' "
+            "or make -C bayesvg_b200/csrc). bayesvg_b200 has no CPU fallback.")
+    L = C.CDLL(SO_PATH, mode=C.RTLD_GLOBAL)
+    L.bvg_last_error.restype = C.c_char_p
+    L.bvg_config_default.argtypes = [C.POINTER(Config)]
+    L.bvg_config_default.restype = None
+    L.bvg_basis_build.argtypes = [C.c_int, _dp, C.c_int64, _dp, C.c_int, C.c_double, C.c_int, C.c_double, C.c_double, _dp]
+    L.bvg_fit_create.argtypes = [C.POINTER(Config), C.POINTER(_vp)]
+    L.bvg_fit_destroy.argtypes = [_vp]
+    L.bvg_fit_destroy.restype = None
+    L.bvg_fit_set_phi.argtypes = [_vp, _dp, C.c_int64, C.c_int]
+    L.bvg_fit_set_y_f64.argtypes = [_vp, _dp, C.c_int64, C.c_int64]
+    L.bvg_fit_set_y_i32.argtypes = [_vp, C.POINTER(C.c_int32), C.c_int64, C.c_int64]
+    L.bvg_fit_dim.argtypes = [_vp, C.POINTER(C.c_int64)]
+    L.bvg_comm_unique_id.argtypes = [_vp, C.c_size_t, C.POINTER(C.c_size_t)]
+    L.bvg_fit_comm_init.argtypes = [_vp, _vp, C.c_size_t]
+    L.bvg_log_prob.argtypes = [_vp, _dp, C.c_int, C.c_int, _dp, _dp]
+    L.bvg_fit_run.argtypes = [_vp]
+    L.bvg_fit_mle.argtypes = [_vp, _dp, _dp]
+    L.bvg_fit_advi.argtypes = [_vp, _dp]
+    L.bvg_fit_summarize.argtypes = [_vp]
+    L.bvg_fit_set_variational.argtypes = [_vp, _dp, _dp]
+    L.bvg_fit_get_variational.argtypes = [_vp, _dp, _dp]
+    L.bvg_fit_advi_steps.argtypes = [_vp, C.c_int, C.c_double, C.c_int, _fp]
+    L.bvg_fit_elbo.argtypes = [_vp, C.c_int, _dp, _fp]
+    L.bvg_fit_time_lik_kernel.argtypes = [_vp, C.c_int, C.c_int, C.c_int, _fp]
+    L.bvg_fit_flush_l2.argtypes = [_vp]
+    L.bvg_fit_get_summary.argtypes = [_vp, _dp]
+    L.bvg_fit_get_draws.argtypes = [_vp, _dp]
+    L.bvg_fit_get_trace.argtypes = [_vp, _dp, C.c_int, C.POINTER(C.c_int)]
+    L.bvg_fit_get_stats.argtypes = [_vp, C.POINTER(Stats)]
+    if L.bvg_version() != ABI_VERSION:
+        raise ImportError(f"libbayesvg_b200.so ABI {L.bvg_version()} != binding {ABI_VERSION}")
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        raise BvgError(rc, lib().bvg_last_error().decode("utf-8", "replace"))

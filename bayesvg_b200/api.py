@@ -1,0 +1,223 @@
+"""Host-side mirror of the reference's R interface for the SVG hot path.
+
+`findSpatiallyVariableFeaturesBayes` keeps the argument names (dots -> underscores), defaults,
+validation messages and output table of /root/reference/R/findSpatiallyVariableFeaturesBayes.R:78-508;
+the numeric middle (basis QR, L-BFGS init, mean-field ADVI, draws, summaries) is one sequence of
+C-ABI calls into libbayesvg_b200.so instead of cmdstanr/CmdStan.  `SpatialData` is a minimal stand-in
+for the Seurat / SpatialExperiment containers (R is not available in this image; the R-side shim is
+in r_shim/ and INTEGRATION.md).
+"""
+import time
+
+import numpy as np
+import pandas as pd
+
+from . import engine as E
+
+_SUMMARY_COLS = E.SUMMARY_COLUMNS
+
+
+class SpatialData:
+    """coords: M x 2; data / counts: G x M (genes x spots) like Seurat's assay layers."""
+
+    def __init__(self, coords, data=None, counts=None, genes=None, spots=None):
+        self.coords = np.asarray(coords, dtype=np.float64)
+        self.data = None if data is None else np.asarray(data)
+        self.counts = None if counts is None else np.asarray(counts)
+        ref = self.data if self.data is not None else self.counts
+        if ref is None:
+            raise ValueError("provide at least one of data / counts")
+        G, M = ref.shape
+        if self.coords.shape[0] != M:
+            raise ValueError("coords rows must equal the number of spots")
+        self.genes = [f"gene{g + 1}" for g in range(G)] if genes is None else list(genes)
+        self.spots = [f"spot{s + 1}" for s in range(M)] if spots is None else list(spots)
+        self.meta_features = pd.DataFrame(index=pd.Index(self.genes, name="gene"))
+        self.variable_features = []
+        self.misc = {}
+
+    def rownames(self):
+        return self.genes
+
+
+def scale_coords(coords):
+    """coop::scaler: column z-score, sd with n-1 (:160)."""
+    X = np.asarray(coords, dtype=np.float64)[:, :2]
+    return (X - X.mean(0)) / X.std(0, ddof=1)
+
+
+def kmeans_centers(X, k, iter_max=100, nstart=10, rng=None):
+    """stats::kmeans(X, centers = k, iter.max = 100, nstart = 10)$centers (:200-204).
+
+    R runs Hartigan-Wong from `nstart` random starts drawn from the ambient RNG and keeps the best;
+    here: Lloyd iterations from `nstart` random starts (rows of X), best within-SS kept.  `rng=None`
+    uses numpy's global state, mirroring the reference's un-seeded call."""
+    X = np.asarray(X, dtype=np.float64)
+    M = X.shape[0]
+    if k > M:
+        raise ValueError("more cluster centers than distinct data points.")
+    rs = np.random if rng is None else rng
+    best, best_ss = None, np.inf
+    for _ in range(nstart):
+        C = X[rs.choice(M, k, replace=False)].copy()
+        for _ in range(iter_max):
+            d = ((X[:, None, :] - C[None]) ** 2).sum(-1)
+            lab = d.argmin(1)
+            newC = C.copy()
+            for j in range(k):
+                m = lab == j
+                if m.any():
+                    newC[j] = X[m].mean(0)
+            if np.allclose(newC, C, rtol=0, atol=1e-12):
+                C = newC
+                break
+            C = newC
+        ss = ((X - C[((X[:, None, :] - C[None]) ** 2).sum(-1).argmin(1)]) ** 2).sum()
+        if ss < best_ss:
+            best, best_ss = C, ss
+    return best
+
+
+def length_scale_kmeans(centers):
+    """median(dist(centers)) over the k(k-1)/2 pairs (:205-207)."""
+    C = np.asarray(centers)
+    d = np.sqrt(((C[:, None, :] - C[None]) ** 2).sum(-1))
+    return float(np.median(d[np.triu_indices(C.shape[0], 1)]))
+
+
+def _abort(msg):
+    raise ValueError(msg)
+
+
+def findSpatiallyVariableFeaturesBayes(sp_obj=None, naive_hvgs=None, likelihood="gaussian", lscale_estimator="kmeans",
+                                       n_iter=3000, kernel="exp_quad", kernel_smoothness=1.5, kernel_period=100,
+                                       n_basis_fns=20, algorithm="meanfield", mle_init=True, mle_iter=1000,
+                                       gene_depth_adjust=False, n_draws=1000, elbo_samples=None, opencl_params=None,
+                                       n_cores=2, random_seed=312, verbose=True, save_model=False, *,
+                                       centers=None, precision="fast", engine="auto", device=0, kmeans_rng=None,
+                                       shard=None):
+    """Drop-in for the reference function (:78-97).  Extra keyword-only arguments: `centers` (k x 2
+    precomputed centroids in scaled coordinates, so that Phi is reproducible), `precision`
+    ("fast" | "fp64"), `engine`, `device`, `shard` (a bayesvg_b200.dist.Shard for multi-GPU)."""
+    # check & parse inputs (:99-138)
+    if sp_obj is None:
+        _abort("Please provide a spatial data object to findSpatiallyVariableFeaturesBayes().")
+    if not isinstance(sp_obj, SpatialData):
+        _abort("Please provide an object of class Seurat or SpatialExperiment.")
+    if naive_hvgs is None:
+        _abort("Please identify a set of naive HVGs prior to running findSpatiallyVariableFeaturesBayes().")
+    likelihood = likelihood.lower()
+    if likelihood not in ("gaussian", "nb"):
+        _abort("Please provide a valid likelihood.")
+    kernel = kernel.lower()
+    if kernel not in ("exp_quad", "matern", "periodic"):
+        _abort("Please provide a valid covariance kernel.")
+    if kernel == "matern" and kernel_smoothness not in (0.5, 1.5, 2.5):
+        _abort("When utilizing the Matern kernel you must provide a valid smoothness parameter value.")
+    algorithm = algorithm.lower()
+    if algorithm not in ("meanfield", "fullrank", "pathfinder"):
+        _abort("Please provide a valid variational inference approximation algorithm.")
+    if elbo_samples is None:
+        elbo_samples = 50 if algorithm == "pathfinder" else 150
+    # accepted by the reference, rejected clearly here (north_star: no fallback)
+    if algorithm != "meanfield":
+        raise NotImplementedError(f"algorithm = '{algorithm}' is not built in bayesvg_b200; only 'meanfield' is.")
+    if opencl_params is not None:
+        raise NotImplementedError("opencl.params is meaningless here: the fit always runs on the CUDA device.")
+    if lscale_estimator != "kmeans":
+        raise NotImplementedError("lscale.estimator = 'variogram' is not built in bayesvg_b200; use 'kmeans'.")
+    if gene_depth_adjust:
+        raise NotImplementedError("gene.depth.adjust = TRUE (approxGP2/approxGP3) is not built yet.")
+    t_start = time.time()
+    # coordinates (:154-161)
+    X = scale_coords(sp_obj.coords)
+    # expression (:163-193)
+    layer = sp_obj.data if likelihood == "gaussian" else sp_obj.counts
+    if layer is None:
+        _abort("the object has no '%s' layer" % ("data" if likelihood == "gaussian" else "counts"))
+    gidx = {g: i for i, g in enumerate(sp_obj.genes)}
+    missing = [g for g in naive_hvgs if g not in gidx]
+    if missing:
+        raise KeyError(f"subscript out of bounds: {missing[:3]}")
+    rows = [gidx[g] for g in naive_hvgs]
+    expr = np.asarray(layer)[rows, :]  # G x M
+    if likelihood == "gaussian":
+        v = expr.astype(np.float64)
+        Y = np.asfortranarray(((v - v.mean()) / v.std(ddof=1)).T)  # global z-score (:185); M x G
+    else:
+        Y = np.asfortranarray(expr.astype(np.int32).T)
+    # length-scale + basis (:200-288)
+    if centers is None:
+        centers = kmeans_centers(X, n_basis_fns, 100, 10, kmeans_rng)
+    centers = np.asarray(centers, dtype=np.float64)
+    if centers.shape != (n_basis_fns, 2):
+        _abort("centers must be n.basis.fns x 2")
+    lscale = length_scale_kmeans(centers)
+    if verbose:
+        print(f"i Estimated length-scale: {round(lscale, 4)}")
+    phi = E.basis_build(X, centers, lscale, kernel, kernel_smoothness, float(kernel_period), device)
+    # fit (:337-413)
+    cfg = dict(n_iter=int(n_iter), mle_init=int(bool(mle_init)), mle_iter=int(mle_iter), n_draws=int(n_draws),
+               elbo_samples=int(elbo_samples), seed=int(random_seed), verbose=int(bool(verbose)), device=device)
+    if shard is not None:
+        from . import dist
+        table, model = dist.fit_sharded(phi, Y, shard, likelihood, precision, engine, cfg)
+    else:
+        fit = E.Fit(phi, Y, likelihood, precision, engine, **cfg)
+        table = fit.run()
+        model = None
+        if save_model:
+            mu, om = fit.get_variational()
+            model = dict(mu=mu, omega=om, trace=fit.trace(), stats=fit.stats(), draws=fit.draws(), phi=phi,
+                         lscale=lscale, centers=centers)
+        stats = fit.stats()
+        fit.close()
+        if verbose:
+            print(f"v ADVI: eta = {stats['eta']}, {stats['advi_iters']} iterations, ELBO = {stats['elbo']:.6g}")
+    # summarise (:419-432)
+    summ = pd.DataFrame(table[:, :7], columns=_SUMMARY_COLS[:7])
+    summ.insert(0, "gene", list(naive_hvgs))
+    summ = summ.sort_values("amplitude_mean", ascending=False, kind="stable").reset_index(drop=True)
+    summ["amplitude_mean_rank"] = np.arange(1, len(summ) + 1)
+    summ.index = pd.Index(summ["gene"], name=None)
+    if verbose:
+        print("v Posterior summarization complete.")
+    # write-back (:436-481): untested genes get NA rows, order = rownames(sp.obj)
+    full = summ.reindex(sp_obj.genes)
+    full["gene"] = sp_obj.genes
+    for c in _SUMMARY_COLS:
+        sp_obj.meta_features[c] = full[c].to_numpy()
+    if save_model:
+        sp_obj.misc["model_fit"] = model
+    if verbose:
+        print(f"v bayesVG modeling of {len(naive_hvgs)} naive HVGs completed in {round(time.time() - t_start, 3)} seconds.")
+    return sp_obj
+
+
+def getBayesianGeneStats(obj, sort_values=True):
+    """R/getBayesianGeneStats.R:60-68: drop untested genes, sort by amplitude_mean descending."""
+    df = obj.meta_features.copy()
+    df.insert(0, "gene", df.index)
+    df = df[~df["amplitude_mean"].isna()]
+    if sort_values:
+        df = df.sort_values("amplitude_mean", ascending=False, kind="stable")
+    return df
+
+
+def classifySVGs(obj, selection_method="rank", n_SVG=1000, quantile_SVG=0.75, cutoff=0.1):
+    """R/classifySVGs.R:60-82: label the top genes by amplitude_mean_rank / quantile / cutoff."""
+    df = obj.meta_features
+    if "amplitude_mean_rank" not in df:
+        _abort("Please run findSpatiallyVariableFeaturesBayes() first.")
+    if selection_method == "rank":
+        sel = df["amplitude_mean_rank"] <= n_SVG
+    elif selection_method == "quantile":
+        sel = df["amplitude_mean"] >= df["amplitude_mean"].quantile(quantile_SVG)
+    elif selection_method == "cutoff":
+        sel = df["amplitude_mean"] >= cutoff
+    else:
+        _abort("Please provide a valid SVG selection method.")
+    obj.meta_features["svg_status"] = np.where(df["amplitude_mean"].isna(), None, sel.fillna(False))
+    order = df.loc[sel.fillna(False)].sort_values("amplitude_mean_rank").index
+    obj.variable_features = list(order)
+    return obj

@@ -1,0 +1,632 @@
+// api.cu -- C-ABI entry points (include/bayesvg_b200.h) and the host-side drivers of the fit:
+// data staging, log_prob, mean-field ADVI (eta adaptation + stochastic gradient ascent + ELBO
+// convergence test), draws + summaries.  Algorithms follow SURVEY.md A.4, which restates what
+// R/findSpatiallyVariableFeaturesBayes.R:346-364 asks CmdStan to do.
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <map>
+#include <vector>
+
+#include "bvg_vec.cuh"
+
+static thread_local char g_err[1024] = "";
+void bvg_set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+extern "C" const char *bvg_last_error(void) { return g_err; }
+extern "C" int bvg_version(void) { return BVG_ABI_VERSION; }
+extern "C" int bvg_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+extern "C" void bvg_config_default(bvg_config *c) {
+  memset(c, 0, sizeof(*c));
+  c->abi_version = BVG_ABI_VERSION;
+  c->likelihood = BVG_GAUSSIAN;
+  c->precision = BVG_PREC_FAST;
+  c->engine = BVG_ENGINE_AUTO;
+  c->device = 0;
+  c->n_iter = 3000;
+  c->mle_init = 1;
+  c->mle_iter = 1000;
+  c->n_draws = 1000;
+  c->elbo_samples = 150;
+  c->eval_elbo = 100;
+  c->adapt_iter = 50;
+  c->lbfgs_history = 25;
+  c->verbose = 0;
+  c->tol_rel_obj = 0.01;
+  c->eta = 0.0;
+  c->seed = 312;
+  c->rank = 0;
+  c->world_size = 1;
+  c->gene_offset = 0;
+  c->G_total = 0;
+}
+
+int lbfgs_run(bvg_fit *f, const double *d_theta0, double *d_out);  // lbfgs.cu
+int launch_summary(bvg_fit *f);                                    // k_summary.cu
+int basis_build_device(cudaStream_t st, const double *d_X, int64_t M, const double *d_C, int k, double ls, int kernel,
+                       double nu, double period, double *d_Q, double *d_work);
+void comm_destroy(bvg_fit *f);
+
+static double now_s() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+static int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+
+// ---- lifecycle ----------------------------------------------------------------------------------
+extern "C" int bvg_fit_create(const bvg_config *cfg, bvg_fit **out) {
+  if (!cfg || !out) { bvg_set_error("null argument"); return BVG_ERR_ARG; }
+  if (cfg->abi_version != BVG_ABI_VERSION) { bvg_set_error("ABI version mismatch: caller %d, library %d", cfg->abi_version, BVG_ABI_VERSION); return BVG_ERR_ARG; }
+  if (cfg->likelihood != BVG_GAUSSIAN && cfg->likelihood != BVG_NB) { bvg_set_error("Please provide a valid likelihood."); return BVG_ERR_ARG; }
+  if (cfg->precision != BVG_PREC_FP64 && cfg->precision != BVG_PREC_FAST) { bvg_set_error("invalid precision"); return BVG_ERR_ARG; }
+  if (cfg->engine == BVG_ENGINE_TCGEN05 && cfg->precision != BVG_PREC_FAST) { bvg_set_error("the tcgen05 engine has no fp64 kind; use precision = FAST"); return BVG_ERR_ARG; }
+  if (cfg->n_iter < 1 || cfg->elbo_samples < 1 || cfg->eval_elbo < 1 || cfg->adapt_iter < 1 || cfg->n_draws < 2) { bvg_set_error("iteration / sample counts must be positive"); return BVG_ERR_ARG; }
+  if (cfg->world_size < 1 || cfg->rank < 0 || cfg->rank >= cfg->world_size) { bvg_set_error("bad rank/world_size"); return BVG_ERR_ARG; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    bvg_set_error("no CUDA device: bayesvg_b200 has no CPU fallback");
+    return BVG_ERR_CUDA;
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) { bvg_set_error("device %d out of range (have %d)", cfg->device, ndev); return BVG_ERR_ARG; }
+  CUDA_TRY(cudaSetDevice(cfg->device));
+  bvg_fit *f = new bvg_fit();
+  memset(f, 0, sizeof(*f));
+  f->cfg = *cfg;
+  CUDA_TRY(cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaEventCreate(&f->ev0));
+  CUDA_TRY(cudaEventCreate(&f->ev1));
+  *out = f;
+  return BVG_OK;
+}
+
+static void free_model(bvg_fit *f) {
+  tc_destroy(f);
+  cudaFree(f->Y); cudaFree(f->Phi); cudaFree(f->dvec); cudaFree(f->summary); cudaFree(f->draws);
+  cudaFree(f->m.C); cudaFree(f->m.Ppart); cudaFree(f->m.Spart); cudaFree(f->m.blk); cudaFree(f->m.ctl);
+  cudaFree((void *)f->m.hist_val);
+  f->Y = f->Phi = nullptr; f->dvec = f->summary = f->draws = nullptr;
+  f->m.C = f->m.Ppart = f->m.Spart = nullptr; f->m.blk = nullptr; f->m.ctl = nullptr; f->m.hist_val = nullptr;
+}
+
+extern "C" void bvg_fit_destroy(bvg_fit *f) {
+  if (!f) return;
+  cudaSetDevice(f->cfg.device);
+  cudaStreamSynchronize(f->stream);
+  comm_destroy(f);
+  free_model(f);
+  cudaFree(f->phi64);
+  cudaFree(f->flush);
+  delete[] f->h_theta_mle;
+  cudaEventDestroy(f->ev0); cudaEventDestroy(f->ev1);
+  cudaStreamDestroy(f->stream);
+  delete f;
+}
+
+// allocate everything that depends on (M, G, k) once both phi and y are known
+static int finalize_model(bvg_fit *f) {
+  DevModel &m = f->m;
+  const bool fp64 = f->cfg.precision == BVG_PREC_FP64;
+  const size_t ts = fp64 ? 8 : 4;
+  m.lik = f->cfg.likelihood;
+  m.KP = (int)round_up(m.k + 1, 8);
+  m.Gpad = round_up(m.G, BVG_GENE_TILE);
+  m.G_total = f->cfg.G_total > 0 ? f->cfg.G_total : m.G;
+  m.gene_offset = f->cfg.gene_offset;
+  if (m.gene_offset < 0 || m.gene_offset + m.G > m.G_total) { bvg_set_error("gene shard [%lld, %lld) outside G_total = %lld", (long long)m.gene_offset, (long long)(m.gene_offset + m.G), (long long)m.G_total); return BVG_ERR_ARG; }
+  m.L = make_layout(m.lik, m.G, m.k);
+  m.LG = make_layout(m.lik, m.G_total, m.k);
+  m.seed = f->cfg.seed;
+  const int64_t D = m.L.D;
+  // engine resolution
+  f->engine = f->cfg.engine;
+  if (f->engine == BVG_ENGINE_AUTO) f->engine = (!fp64 && m.KP <= 24 && tc_available()) ? BVG_ENGINE_TCGEN05 : BVG_ENGINE_SIMT;
+  if (f->engine == BVG_ENGINE_TCGEN05 && m.KP > 24) { bvg_set_error("tcgen05 engine supports k <= 23 basis functions in this build (k = %d)", m.k); return BVG_ERR_ARG; }
+  f->st.engine_used = f->engine;
+  // state vectors: mu | omega | hist(2D) | zeta | grad | init | weights
+  CUDA_TRY(cudaMalloc(&f->dvec, sizeof(double) * 8 * D));
+  CUDA_TRY(cudaMemsetAsync(f->dvec, 0, sizeof(double) * 8 * D, f->stream));
+  m.mu = f->dvec; m.omega = m.mu + D; m.hist = m.omega + D; m.zeta = m.hist + 2 * D; m.grad = m.zeta + D;
+  f->scratch = m.grad + D;  // [D] theta_init, then [D] weights
+  BVG_TRY(vec_make_weights(f->stream, f->scratch + D, m, f->cfg.rank));
+  // split the spots so that (gene tiles x splits) covers the machine a few times over
+  int nsm = 148;
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, f->cfg.device);
+  const int ntiles = (int)(m.Gpad / BVG_GENE_TILE);
+  const int64_t nchunks = (m.M + 31) / 32;
+  const int ctas_per_sm = f->engine == BVG_ENGINE_TCGEN05 ? 1 : 4;
+  int nsplit = (nsm * ctas_per_sm + ntiles - 1) / ntiles;
+  nsplit = (int)std::max<int64_t>(1, std::min<int64_t>(nsplit, nchunks));
+  const int64_t cps = (nchunks + nsplit - 1) / nsplit;
+  m.nsplit = (int)((nchunks + cps - 1) / cps);
+  CUDA_TRY(cudaMalloc(&m.C, ts * m.Gpad * m.KP * 3));  // x3: room for the tf32 hi/lo split rows
+  CUDA_TRY(cudaMemsetAsync(m.C, 0, ts * m.Gpad * m.KP * 3, f->stream));
+  CUDA_TRY(cudaMalloc(&m.Ppart, ts * (size_t)m.nsplit * m.Gpad * m.KP));
+  CUDA_TRY(cudaMalloc(&m.Spart, ts * (size_t)m.nsplit * m.Gpad * 2));
+  CUDA_TRY(cudaMemsetAsync(m.Ppart, 0, ts * (size_t)m.nsplit * m.Gpad * m.KP, f->stream));
+  CUDA_TRY(cudaMemsetAsync(m.Spart, 0, ts * (size_t)m.nsplit * m.Gpad * 2, f->stream));
+  m.nblk_gene = (int)std::min<int64_t>((m.G + 7) / 8, nsm * 4);
+  const int NS = bvg_ns(m.k);
+  CUDA_TRY(cudaMalloc(&m.blk, sizeof(double) * ((size_t)m.nblk_gene + 1) * NS));
+  m.tot = m.blk + (size_t)m.nblk_gene * NS;
+  CUDA_TRY(cudaMalloc(&m.ctl, sizeof(Ctl)));
+  CUDA_TRY(cudaMemsetAsync(m.ctl, 0, sizeof(Ctl), f->stream));
+  CUDA_TRY(cudaMalloc(&f->summary, sizeof(double) * 8 * m.G));
+  CUDA_TRY(cudaMalloc(&f->draws, sizeof(double) * m.G * f->cfg.n_draws));
+  // Phi' in the compute type
+  f->Mpad = round_up(m.M, 64);
+  CUDA_TRY(cudaMalloc(&f->Phi, ts * f->Mpad * m.KP));
+  if (fp64) BVG_TRY(stage_phi<double>(f->phi64, (double *)f->Phi, m.M, f->Mpad, m.k, m.KP, f->stream));
+  else BVG_TRY(stage_phi<float>(f->phi64, (float *)f->Phi, m.M, f->Mpad, m.k, m.KP, f->stream));
+  if (f->engine == BVG_ENGINE_TCGEN05) BVG_TRY(tc_setup(f));
+  CUDA_TRY(cudaStreamSynchronize(f->stream));
+  return BVG_OK;
+}
+
+extern "C" int bvg_fit_set_phi(bvg_fit *f, const double *phi, int64_t M, int k) {
+  if (!f || !phi) { bvg_set_error("null argument"); return BVG_ERR_ARG; }
+  if (M < 1 || k < 1) { bvg_set_error("phi must be M x k with M, k >= 1"); return BVG_ERR_ARG; }
+  if (k > BVG_MAX_K) { bvg_set_error("n.basis.fns = %d exceeds this build's limit of %d", k, BVG_MAX_K); return BVG_ERR_ARG; }
+  CUDA_TRY(cudaSetDevice(f->cfg.device));
+  const double t0 = now_s();
+  if (f->have_y) { free_model(f); f->have_y = false; }  // a new basis invalidates the staged model; set y again
+  if (f->have_phi) { cudaFree(f->phi64); f->phi64 = nullptr; }
+  CUDA_TRY(cudaMalloc(&f->phi64, sizeof(double) * M * k));
+  CUDA_TRY(cudaMemcpyAsync(f->phi64, phi, sizeof(double) * M * k, cudaMemcpyHostToDevice, f->stream));
+  f->m.M = M; f->m.k = k;
+  f->have_phi = true;
+  CUDA_TRY(cudaStreamSynchronize(f->stream));
+  f->st.sec_h2d += now_s() - t0;
+  return BVG_OK;
+}
+
+template <typename SRC>
+static int set_y_impl(bvg_fit *f, const SRC *y, int64_t M, int64_t G) {
+  if (!f || !y) { bvg_set_error("null argument"); return BVG_ERR_ARG; }
+  if (!f->have_phi) { bvg_set_error("call bvg_fit_set_phi before bvg_fit_set_y"); return BVG_ERR_STATE; }
+  if (M != f->m.M) { bvg_set_error("y has %lld spots but phi has %lld rows", (long long)M, (long long)f->m.M); return BVG_ERR_ARG; }
+  if (G < 1) { bvg_set_error("y must have at least one gene"); return BVG_ERR_ARG; }
+  CUDA_TRY(cudaSetDevice(f->cfg.device));
+  const double t0 = now_s();
+  if (f->have_y) free_model(f);
+  f->have_y = f->have_mle = f->have_vi = f->have_summary = false;
+  const bool fp64 = f->cfg.precision == BVG_PREC_FP64;
+  f->m.G = G;
+  f->ldY = fp64 ? M : round_up(M, 64);
+  const size_t ts = fp64 ? 8 : 4;
+  CUDA_TRY(cudaMalloc(&f->Y, ts * (size_t)G * f->ldY));
+  // stage through a bounded device buffer (host layout -> compute type + padding)
+  const int64_t genes_per_chunk = std::max<int64_t>(1, std::min<int64_t>(G, (int64_t)(128u << 20) / (M * (int64_t)sizeof(SRC))));
+  SRC *stage = nullptr;
+  CUDA_TRY(cudaMalloc(&stage, sizeof(SRC) * genes_per_chunk * M));
+  for (int64_t g0 = 0; g0 < G; g0 += genes_per_chunk) {
+    const int64_t ng = std::min(genes_per_chunk, G - g0);
+    CUDA_TRY(cudaMemcpyAsync(stage, y + g0 * M, sizeof(SRC) * ng * M, cudaMemcpyHostToDevice, f->stream));
+    int rc;
+    if (fp64) rc = stage_y<SRC, double>(stage, (double *)f->Y + g0 * f->ldY, M, f->ldY, ng, f->stream);
+    else rc = stage_y<SRC, float>(stage, (float *)f->Y + g0 * f->ldY, M, f->ldY, ng, f->stream);
+    if (rc != BVG_OK) { cudaFree(stage); return rc; }
+  }
+  // nb: histogram of distinct counts for the lgamma / digamma terms (they depend on y and phi_nb only)
+  if (f->cfg.likelihood == BVG_NB) {
+    std::map<int64_t, double> h;
+    double lg1 = 0;
+    const int64_t n = M * G;
+    std::vector<double> dense(1 << 16, 0.0);
+    for (int64_t i = 0; i < n; ++i) {
+      const double v = (double)y[i];
+      if (!(v >= 0) || v != std::floor(v)) { cudaFree(stage); bvg_set_error("nb likelihood needs non-negative integer counts (found %g)", v); return BVG_ERR_ARG; }
+      const int64_t c = (int64_t)v;
+      if (c < (int64_t)dense.size()) dense[c] += 1.0; else h[c] += 1.0;
+    }
+    std::vector<double> hv, hc;
+    for (size_t c = 0; c < dense.size(); ++c) if (dense[c] > 0) { hv.push_back((double)c); hc.push_back(dense[c]); }
+    for (auto &kv : h) { hv.push_back((double)kv.first); hc.push_back(kv.second); }
+    for (size_t i = 0; i < hv.size(); ++i) lg1 += hc[i] * lgamma(hv[i] + 1.0);
+    double *d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, sizeof(double) * 2 * hv.size()));
+    CUDA_TRY(cudaMemcpyAsync(d, hv.data(), sizeof(double) * hv.size(), cudaMemcpyHostToDevice, f->stream));
+    CUDA_TRY(cudaMemcpyAsync(d + hv.size(), hc.data(), sizeof(double) * hv.size(), cudaMemcpyHostToDevice, f->stream));
+    CUDA_TRY(cudaStreamSynchronize(f->stream));
+    f->m.hist_val = d; f->m.hist_cnt = d + hv.size(); f->m.nhist = (int)hv.size(); f->m.lgam_y1 = lg1;
+  }
+  CUDA_TRY(cudaStreamSynchronize(f->stream));
+  cudaFree(stage);
+  BVG_TRY(finalize_model(f));
+  f->have_y = true;
+  f->st.sec_h2d += now_s() - t0;
+  return BVG_OK;
+}
+extern "C" int bvg_fit_set_y_f64(bvg_fit *f, const double *y, int64_t M, int64_t G) { return set_y_impl<double>(f, y, M, G); }
+extern "C" int bvg_fit_set_y_i32(bvg_fit *f, const int32_t *y, int64_t M, int64_t G) {
+  if (f && f->cfg.likelihood != BVG_NB) { bvg_set_error("integer counts are the nb likelihood's input; gaussian takes doubles"); return BVG_ERR_ARG; }
+  return set_y_impl<int32_t>(f, y, M, G);
+}
+
+static int need_ready(bvg_fit *f) {
+  if (!f) { bvg_set_error("null fit"); return BVG_ERR_ARG; }
+  if (!f->have_phi || !f->have_y) { bvg_set_error("set phi and y first"); return BVG_ERR_STATE; }
+  CUDA_TRY(cudaSetDevice(f->cfg.device));
+  return BVG_OK;
+}
+extern "C" int bvg_fit_dim(bvg_fit *f, int64_t *D) {
+  BVG_TRY(need_ready(f));
+  *D = f->m.L.D;
+  return BVG_OK;
+}
+
+// ---- one evaluation -----------------------------------------------------------------------------
+int launch_lik(bvg_fit *f, bool backward) {
+  return f->engine == BVG_ENGINE_TCGEN05 ? launch_lik_tc(f, backward) : launch_lik_simt(f, backward);
+}
+// zeta already holds the point (or is drawn by prep when mode is a draw mode)
+int eval_log_prob_device(bvg_fit *f, int mode, int jac, int propto, bool backward) {
+  const int prep = mode == MODE_ADVI_UPDATE ? PREP_GRAD : (mode == MODE_ELBO_DRAW ? PREP_ELBO : PREP_NONE);
+  BVG_TRY(launch_prep(f, prep));
+  BVG_TRY(launch_lik(f, backward));
+  BVG_TRY(launch_gene(f, mode, jac));
+  BVG_TRY(launch_finish(f, mode, jac, propto));
+  return BVG_OK;
+}
+
+extern "C" int bvg_log_prob(bvg_fit *f, const double *theta, int jacobian, int propto, double *lp, double *grad) {
+  BVG_TRY(need_ready(f));
+  if (!theta || !lp) { bvg_set_error("null argument"); return BVG_ERR_ARG; }
+  const int64_t D = f->m.L.D;
+  CUDA_TRY(cudaMemcpyAsync(f->m.zeta, theta, sizeof(double) * D, cudaMemcpyHostToDevice, f->stream));
+  BVG_TRY(eval_log_prob_device(f, grad ? MODE_GRAD_OUT : MODE_LP_ONLY, jacobian, propto, grad != nullptr));
+  Ctl h;
+  CUDA_TRY(cudaMemcpyAsync(&h, f->m.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, f->stream));
+  if (grad) CUDA_TRY(cudaMemcpyAsync(grad, f->m.grad, sizeof(double) * D, cudaMemcpyDeviceToHost, f->stream));
+  CUDA_TRY(cudaStreamSynchronize(f->stream));
+  *lp = h.lp;
+  return BVG_OK;
+}
+
+// ---- mean-field ADVI ----------------------------------------------------------------------------
+static int advi_reset(bvg_fit *f, const double *d_init /* device, NULL keeps mu */, bool zero_omega) {
+  const int64_t D = f->m.L.D;
+  if (d_init) CUDA_TRY(cudaMemcpyAsync(f->m.mu, d_init, sizeof(double) * D, cudaMemcpyDeviceToDevice, f->stream));
+  if (zero_omega) CUDA_TRY(cudaMemsetAsync(f->m.omega, 0, sizeof(double) * D, f->stream));
+  CUDA_TRY(cudaMemsetAsync(f->m.hist, 0, sizeof(double) * 2 * D, f->stream));
+  return BVG_OK;
+}
+static int ctl_set(bvg_fit *f, const Ctl &h) {
+  CUDA_TRY(cudaMemcpyAsync(f->m.ctl, &h, sizeof(Ctl), cudaMemcpyHostToDevice, f->stream));
+  CUDA_TRY(cudaStreamSynchronize(f->stream));  // h lives on the caller's stack
+  return BVG_OK;
+}
+static int ctl_get(bvg_fit *f, Ctl *h) {
+  CUDA_TRY(cudaMemcpyAsync(h, f->m.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, f->stream));
+  CUDA_TRY(cudaStreamSynchronize(f->stream));
+  return BVG_OK;
+}
+static int advi_steps(bvg_fit *f, int n) {
+  for (int i = 0; i < n; ++i) BVG_TRY(eval_log_prob_device(f, MODE_ADVI_UPDATE, 1, 1, true));
+  f->st.grad_evals += n;
+  return BVG_OK;
+}
+// ELBO = mean_s log_prob<propto=false, jacobian=true>(zeta_s) + entropy; non-finite draws are dropped
+static int advi_elbo(bvg_fit *f, int S, double *out) {
+  Ctl h;
+  BVG_TRY(ctl_get(f, &h));
+  h.elbo_acc = 0; h.elbo_ok = 0;
+  BVG_TRY(ctl_set(f, h));
+  for (int s = 0; s < S; ++s) BVG_TRY(eval_log_prob_device(f, MODE_ELBO_DRAW, 1, 0, false));
+  const int64_t D = f->m.L.D;
+  BVG_TRY(vec_dot_sum(f->stream, f->m.omega, nullptr, f->scratch + D, D, f->m.tot));
+  BVG_TRY(comm_allreduce(f, f->m.tot, 2));
+  double hs[2];
+  CUDA_TRY(cudaMemcpyAsync(hs, f->m.tot, sizeof(hs), cudaMemcpyDeviceToHost, f->stream));
+  BVG_TRY(ctl_get(f, &h));
+  f->st.elbo_evals++;
+  if (h.elbo_ok == 0) { *out = -INFINITY; return BVG_OK; }
+  const double Dt = (double)f->m.LG.D;
+  *out = h.elbo_acc / h.elbo_ok + 0.5 * Dt * (1.0 + BVG_LOG_TWO_PI) + hs[1];
+  if (std::isnan(*out)) *out = -INFINITY;
+  return BVG_OK;
+}
+static int set_phase(bvg_fit *f, double eta) {  // restart the step-size schedule, keep the draw counters
+  Ctl h;
+  BVG_TRY(ctl_get(f, &h));
+  h.it = 1; h.eta = eta; h.bad = 0;
+  return ctl_set(f, h);
+}
+
+static int run_advi(bvg_fit *f, const double *d_init) {
+  const bvg_config &c = f->cfg;
+  const int64_t D = f->m.L.D;
+  double *init = f->scratch;  // device copy of theta_init
+  if (d_init) CUDA_TRY(cudaMemcpyAsync(init, d_init, sizeof(double) * D, cudaMemcpyDeviceToDevice, f->stream));
+  else CUDA_TRY(cudaMemsetAsync(init, 0, sizeof(double) * D, f->stream));
+  Ctl h;
+  memset(&h, 0, sizeof(h));
+  h.it = 1;
+  BVG_TRY(ctl_set(f, h));
+  f->n_trace = 0;
+  f->st.grad_evals = 0; f->st.elbo_evals = 0; f->st.converged = 0;
+  double eta = c.eta;
+  const double t_adapt = now_s();
+  if (eta <= 0) {  // adapt_eta
+    static const double seq[5] = {100, 10, 1, 0.1, 0.01};
+    BVG_TRY(advi_reset(f, init, true));
+    double e0;
+    BVG_TRY(advi_elbo(f, c.elbo_samples, &e0));
+    if (!std::isfinite(e0)) { bvg_set_error("ADVI: the ELBO is not finite at the initial point"); return BVG_ERR_NUMERIC; }
+    double ebest = -INFINITY, eta_best = 0;
+    for (int q = 0;; ++q) {
+      BVG_TRY(advi_reset(f, init, true));
+      BVG_TRY(set_phase(f, seq[q]));
+      BVG_TRY(advi_steps(f, c.adapt_iter));
+      double e;
+      BVG_TRY(advi_elbo(f, c.elbo_samples, &e));
+      if (c.verbose) fprintf(stderr, "[bayesvg_b200] adapt eta = %-6g ELBO = %.6g (init %.6g)\n", seq[q], e, e0);
+      if (e < ebest && ebest > e0) break;
+      if (q < 4) { ebest = e; eta_best = seq[q]; }
+      else {
+        if (e > e0) { ebest = e; eta_best = seq[q]; break; }
+        bvg_set_error("ADVI: all proposed step-sizes failed; the model may be ill-conditioned");
+        return BVG_ERR_NUMERIC;
+      }
+    }
+    eta = eta_best;
+  }
+  f->st.eta = eta;
+  f->st.sec_adapt = now_s() - t_adapt;
+  const double t_sga = now_s();
+  BVG_TRY(advi_reset(f, init, true));
+  BVG_TRY(set_phase(f, eta));
+  const int cbn = (int)std::max(0.1 * c.n_iter / c.eval_elbo, 2.0);
+  std::vector<double> cb(cbn, 0.0), tmp(cbn);
+  int cbc = 0, cbh = 0, conv = 0, it = 0;
+  double elbo = 0, elbo_prev;
+  while (it < c.n_iter) {
+    const int n = std::min(c.eval_elbo - it % c.eval_elbo, c.n_iter - it);
+    BVG_TRY(advi_steps(f, n));
+    it += n;
+    if (it % c.eval_elbo == 0) {
+      elbo_prev = elbo;
+      BVG_TRY(advi_elbo(f, c.elbo_samples, &elbo));
+      Ctl hh;
+      BVG_TRY(ctl_get(f, &hh));
+      if (hh.bad) { bvg_set_error("ADVI: non-finite gradient during stochastic gradient ascent (%d evaluations)", hh.bad); return BVG_ERR_NUMERIC; }
+      const double d = std::fabs((elbo - elbo_prev) / elbo);
+      cb[cbh] = d; cbh = (cbh + 1) % cbn; if (cbc < cbn) ++cbc;
+      double mean = 0;
+      for (int i = 0; i < cbc; ++i) { mean += cb[i]; tmp[i] = cb[i]; }
+      mean /= cbc;
+      std::sort(tmp.begin(), tmp.begin() + cbc);
+      const double med = tmp[cbc / 2];
+      if (f->n_trace < 64) { double *r = f->trace + 4 * f->n_trace++; r[0] = it; r[1] = elbo; r[2] = mean; r[3] = med; }
+      if (c.verbose) fprintf(stderr, "[bayesvg_b200] %6d  ELBO %-14.6g delta_mean %-10.4g delta_med %-10.4g\n", it, elbo, mean, med);
+      if (mean < c.tol_rel_obj) conv |= 1;
+      if (med < c.tol_rel_obj) conv |= 2;
+      if (conv) break;
+    }
+  }
+  CUDA_TRY(cudaStreamSynchronize(f->stream));
+  f->st.advi_iters = it; f->st.converged = conv; f->st.elbo = elbo;
+  f->st.sec_sga = now_s() - t_sga;
+  f->have_vi = true;
+  return BVG_OK;
+}
+
+extern "C" int bvg_fit_mle(bvg_fit *f, const double *theta0, double *theta_out) {
+  BVG_TRY(need_ready(f));
+  const int64_t D = f->m.L.D;
+  const double t0 = now_s();
+  double *d0 = nullptr;
+  if (theta0) {
+    CUDA_TRY(cudaMemcpyAsync(f->m.mu, theta0, sizeof(double) * D, cudaMemcpyHostToDevice, f->stream));
+    d0 = f->m.mu;
+  }
+  BVG_TRY(lbfgs_run(f, d0, f->scratch));
+  if (!f->h_theta_mle) f->h_theta_mle = new double[D];
+  CUDA_TRY(cudaMemcpyAsync(f->h_theta_mle, f->scratch, sizeof(double) * D, cudaMemcpyDeviceToHost, f->stream));
+  CUDA_TRY(cudaStreamSynchronize(f->stream));
+  if (theta_out) memcpy(theta_out, f->h_theta_mle, sizeof(double) * D);
+  f->have_mle = true;
+  f->st.sec_mle = now_s() - t0;
+  return BVG_OK;
+}
+
+extern "C" int bvg_fit_advi(bvg_fit *f, const double *theta_init) {
+  BVG_TRY(need_ready(f));
+  const int64_t D = f->m.L.D;
+  const double *src = theta_init ? theta_init : (f->have_mle ? f->h_theta_mle : nullptr);
+  if (src) {
+    CUDA_TRY(cudaMemcpyAsync(f->m.grad, src, sizeof(double) * D, cudaMemcpyHostToDevice, f->stream));
+    return run_advi(f, f->m.grad);
+  }
+  return run_advi(f, nullptr);
+}
+
+extern "C" int bvg_fit_summarize(bvg_fit *f) {
+  BVG_TRY(need_ready(f));
+  if (!f->have_vi) { bvg_set_error("no variational fit to summarise"); return BVG_ERR_STATE; }
+  const double t0 = now_s();
+  BVG_TRY(launch_summary(f));
+  CUDA_TRY(cudaStreamSynchronize(f->stream));
+  f->have_summary = true;
+  f->st.sec_draws = now_s() - t0;
+  return BVG_OK;
+}
+
+extern "C" int bvg_fit_run(bvg_fit *f) {
+  BVG_TRY(need_ready(f));
+  const double t0 = now_s();
+  if (f->cfg.mle_init) BVG_TRY(bvg_fit_mle(f, nullptr, nullptr));
+  else f->have_mle = false;
+  BVG_TRY(bvg_fit_advi(f, nullptr));
+  BVG_TRY(bvg_fit_summarize(f));
+  f->st.sec_total = now_s() - t0 + f->st.sec_h2d;
+  return BVG_OK;
+}
+
+// ---- fine-grained hooks -------------------------------------------------------------------------
+extern "C" int bvg_fit_set_variational(bvg_fit *f, const double *mu, const double *omega) {
+  BVG_TRY(need_ready(f));
+  if (!mu) { bvg_set_error("null mu"); return BVG_ERR_ARG; }
+  const int64_t D = f->m.L.D;
+  CUDA_TRY(cudaMemcpyAsync(f->m.mu, mu, sizeof(double) * D, cudaMemcpyHostToDevice, f->stream));
+  if (omega) CUDA_TRY(cudaMemcpyAsync(f->m.omega, omega, sizeof(double) * D, cudaMemcpyHostToDevice, f->stream));
+  else CUDA_TRY(cudaMemsetAsync(f->m.omega, 0, sizeof(double) * D, f->stream));
+  CUDA_TRY(cudaStreamSynchronize(f->stream));
+  f->have_vi = true;
+  return BVG_OK;
+}
+extern "C" int bvg_fit_get_variational(bvg_fit *f, double *mu, double *omega) {
+  BVG_TRY(need_ready(f));
+  const int64_t D = f->m.L.D;
+  if (mu) CUDA_TRY(cudaMemcpyAsync(mu, f->m.mu, sizeof(double) * D, cudaMemcpyDeviceToHost, f->stream));
+  if (omega) CUDA_TRY(cudaMemcpyAsync(omega, f->m.omega, sizeof(double) * D, cudaMemcpyDeviceToHost, f->stream));
+  CUDA_TRY(cudaStreamSynchronize(f->stream));
+  return BVG_OK;
+}
+extern "C" int bvg_fit_advi_steps(bvg_fit *f, int n, double eta, int reset_counters, float *ms_out) {
+  BVG_TRY(need_ready(f));
+  if (n < 0 || !(eta > 0)) { bvg_set_error("n >= 0 and eta > 0 required"); return BVG_ERR_ARG; }
+  Ctl h;
+  BVG_TRY(ctl_get(f, &h));
+  if (reset_counters) { memset(&h, 0, sizeof(h)); h.it = 1; BVG_TRY(advi_reset(f, nullptr, false)); }
+  if (h.it < 1) h.it = 1;
+  h.eta = eta;
+  BVG_TRY(ctl_set(f, h));
+  CUDA_TRY(cudaEventRecord(f->ev0, f->stream));
+  BVG_TRY(advi_steps(f, n));
+  CUDA_TRY(cudaEventRecord(f->ev1, f->stream));
+  CUDA_TRY(cudaEventSynchronize(f->ev1));
+  if (ms_out) CUDA_TRY(cudaEventElapsedTime(ms_out, f->ev0, f->ev1));
+  f->have_vi = true;
+  return BVG_OK;
+}
+extern "C" int bvg_fit_elbo(bvg_fit *f, int n_samples, double *elbo_out, float *ms_out) {
+  BVG_TRY(need_ready(f));
+  if (n_samples < 1 || !elbo_out) { bvg_set_error("bad argument"); return BVG_ERR_ARG; }
+  CUDA_TRY(cudaEventRecord(f->ev0, f->stream));
+  BVG_TRY(advi_elbo(f, n_samples, elbo_out));
+  CUDA_TRY(cudaEventRecord(f->ev1, f->stream));
+  CUDA_TRY(cudaEventSynchronize(f->ev1));
+  if (ms_out) CUDA_TRY(cudaEventElapsedTime(ms_out, f->ev0, f->ev1));
+  return BVG_OK;
+}
+__global__ void k_flush(float *p, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = (float)i;
+}
+static int ensure_flush(bvg_fit *f) {
+  if (!f->flush) {
+    f->flush_bytes = (size_t)512 << 20;  // > 126 MB L2
+    CUDA_TRY(cudaMalloc(&f->flush, f->flush_bytes));
+  }
+  return BVG_OK;
+}
+extern "C" int bvg_fit_flush_l2(bvg_fit *f) {
+  BVG_TRY(need_ready(f));
+  BVG_TRY(ensure_flush(f));
+  k_flush<<<148 * 8, 256, 0, f->stream>>>((float *)f->flush, f->flush_bytes / 4);
+  CUDA_TRY(cudaGetLastError());
+  return BVG_OK;
+}
+extern "C" int bvg_fit_time_lik_kernel(bvg_fit *f, int n, int flush_l2, int backward, float *ms_avg_out) {
+  BVG_TRY(need_ready(f));
+  if (n < 1 || !ms_avg_out) { bvg_set_error("bad argument"); return BVG_ERR_ARG; }
+  if (flush_l2) BVG_TRY(ensure_flush(f));
+  double total = 0;
+  if (flush_l2) {
+    for (int i = 0; i < n; ++i) {
+      k_flush<<<148 * 8, 256, 0, f->stream>>>((float *)f->flush, f->flush_bytes / 4);
+      CUDA_TRY(cudaEventRecord(f->ev0, f->stream));
+      BVG_TRY(launch_lik(f, backward != 0));
+      CUDA_TRY(cudaEventRecord(f->ev1, f->stream));
+      CUDA_TRY(cudaEventSynchronize(f->ev1));
+      float ms;
+      CUDA_TRY(cudaEventElapsedTime(&ms, f->ev0, f->ev1));
+      total += ms;
+    }
+  } else {
+    CUDA_TRY(cudaEventRecord(f->ev0, f->stream));
+    for (int i = 0; i < n; ++i) BVG_TRY(launch_lik(f, backward != 0));
+    CUDA_TRY(cudaEventRecord(f->ev1, f->stream));
+    CUDA_TRY(cudaEventSynchronize(f->ev1));
+    float ms;
+    CUDA_TRY(cudaEventElapsedTime(&ms, f->ev0, f->ev1));
+    total = ms;
+  }
+  *ms_avg_out = (float)(total / n);
+  return BVG_OK;
+}
+
+// ---- results ------------------------------------------------------------------------------------
+extern "C" int bvg_fit_get_summary(bvg_fit *f, double *out) {
+  BVG_TRY(need_ready(f));
+  if (!f->have_summary) { bvg_set_error("call bvg_fit_summarize (or bvg_fit_run) first"); return BVG_ERR_STATE; }
+  const int64_t G = f->m.G;
+  CUDA_TRY(cudaMemcpyAsync(out, f->summary, sizeof(double) * 8 * G, cudaMemcpyDeviceToHost, f->stream));
+  CUDA_TRY(cudaStreamSynchronize(f->stream));
+  // amplitude_mean_rank: arrange(desc(amplitude_mean)) then row_number()  (:429-430); within a shard
+  std::vector<int64_t> idx(G);
+  for (int64_t g = 0; g < G; ++g) idx[g] = g;
+  std::stable_sort(idx.begin(), idx.end(), [&](int64_t a, int64_t b) { return out[a] > out[b]; });
+  for (int64_t r = 0; r < G; ++r) out[7 * G + idx[r]] = (double)(r + 1);
+  return BVG_OK;
+}
+extern "C" int bvg_fit_get_draws(bvg_fit *f, double *out) {
+  BVG_TRY(need_ready(f));
+  if (!f->have_summary) { bvg_set_error("call bvg_fit_summarize (or bvg_fit_run) first"); return BVG_ERR_STATE; }
+  CUDA_TRY(cudaMemcpyAsync(out, f->draws, sizeof(double) * f->m.G * f->cfg.n_draws, cudaMemcpyDeviceToHost, f->stream));
+  CUDA_TRY(cudaStreamSynchronize(f->stream));
+  return BVG_OK;
+}
+extern "C" int bvg_fit_get_trace(bvg_fit *f, double *out, int cap, int *n) {
+  if (!f || !out || !n) { bvg_set_error("null argument"); return BVG_ERR_ARG; }
+  const int m = std::min(cap, f->n_trace);
+  memcpy(out, f->trace, sizeof(double) * 4 * m);
+  *n = m;
+  return BVG_OK;
+}
+extern "C" int bvg_fit_get_stats(bvg_fit *f, bvg_fit_stats *out) {
+  if (!f || !out) { bvg_set_error("null argument"); return BVG_ERR_ARG; }
+  *out = f->st;
+  return BVG_OK;
+}
+
+// ---- basis builder ------------------------------------------------------------------------------
+extern "C" int bvg_basis_build(int device, const double *coords, int64_t M, const double *centers, int k, double lscale,
+                               int kernel, double nu, double period, double *phi_out) {
+  if (!coords || !centers || !phi_out) { bvg_set_error("null argument"); return BVG_ERR_ARG; }
+  if (M < 1 || k < 1 || k > M) { bvg_set_error("need 1 <= k <= M"); return BVG_ERR_ARG; }
+  if (kernel < 0 || kernel > 2) { bvg_set_error("Please provide a valid covariance kernel."); return BVG_ERR_ARG; }
+  if (kernel == BVG_KERNEL_MATERN && !(nu == 0.5 || nu == 1.5 || nu == 2.5)) { bvg_set_error("When utilizing the Matern kernel you must provide a valid smoothness parameter value."); return BVG_ERR_ARG; }
+  if (!(lscale > 0)) { bvg_set_error("length-scale must be positive"); return BVG_ERR_ARG; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); bvg_set_error("no CUDA device: bayesvg_b200 has no CPU fallback"); return BVG_ERR_CUDA; }
+  CUDA_TRY(cudaSetDevice(device));
+  double *d = nullptr;
+  const size_t n = (size_t)2 * M + 2 * k + (size_t)2 * M * k + 3 * k;
+  CUDA_TRY(cudaMalloc(&d, sizeof(double) * n));
+  double *dX = d, *dC = dX + 2 * M, *dQ = dC + 2 * k, *dW = dQ + (size_t)M * k;
+  cudaStream_t st;
+  CUDA_TRY(cudaStreamCreate(&st));
+  CUDA_TRY(cudaMemcpyAsync(dX, coords, sizeof(double) * 2 * M, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(dC, centers, sizeof(double) * 2 * k, cudaMemcpyHostToDevice, st));
+  int rc = basis_build_device(st, dX, M, dC, k, lscale, kernel, nu, period, dQ, dW);
+  if (rc == BVG_OK) {
+    if (cudaMemcpyAsync(phi_out, dQ, sizeof(double) * M * k, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) {
+      bvg_set_error("basis build failed: %s", cudaGetErrorString(cudaGetLastError()));
+      rc = BVG_ERR_CUDA;
+    }
+  }
+  cudaStreamDestroy(st);
+  cudaFree(d);
+  return rc;
+}

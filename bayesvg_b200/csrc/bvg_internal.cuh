@@ -1,0 +1,180 @@
+// bvg_internal.cuh -- shared declarations of the CUDA engine (not part of the C ABI).
+//
+// Data layout in HBM:
+//   Y     : [G][ldY]  gene-major (= R's M x G column-major), fp64 (PREC_FP64) or fp32 (PREC_FAST),
+//           ldY = M rounded up to 64 spots and zero padded in FAST mode.
+//   Phi'  : [Mpad][KP] row-major, KP = k+1 rounded up to 8; column k is the all-ones column that
+//           carries the intercept beta0[g] forward and R_g = sum_s r backward; padded rows are zero.
+//   C     : [Gpad][KP] coefficient rows c'_g = (A_g * alpha_{1..k,g}, beta0_g, 0...) rebuilt each eval.
+//   theta-like vectors (mu, omega, hist, zeta, grad): fp64, Stan declaration order.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/bayesvg_b200.h"
+
+#define BVG_MAX_K 30           // k+2 per-gene parameters map onto one warp in k_gene
+#define BVG_GENE_TILE 128      // genes per likelihood CTA (= TMEM lanes in the tcgen05 kernel)
+#define BVG_LOG_TWO_PI 1.8378770664093454835606594728112
+#define BVG_LOG_PI 1.1447298858494001741434273513531
+#define BVG_LOG_TWO 0.69314718055994530941723212145818
+
+enum { STREAM_GRAD = 1, STREAM_ELBO = 2, STREAM_DRAW = 3 };
+
+// slots of the cross-gene reduction vector (the only thing that crosses GPUs each evaluation)
+enum { S_R = 0, S_RZ, S_DU, S_DU2, S_SSE /* nb: sum of y*eta - (y+phi)*L */, S_Z2, S_U, S_L, S_LG, S_DG, S_AP };
+__host__ __device__ inline int bvg_ns(int k) { return S_AP + 2 * k; }
+
+struct Layout {
+  int64_t mu_beta0, sigma_beta0, z_beta0, mu_amp, sigma_amp, amp, mu_alpha, sigma_alpha, z_alpha, tail, D;
+};
+// inst/approxGP.stan:12-23 and inst/approxGP4.stan:12-23 (declaration order)
+__host__ __device__ inline Layout make_layout(int lik, int64_t G, int k) {
+  Layout L;
+  L.mu_beta0 = 0; L.sigma_beta0 = 1; L.z_beta0 = 2;
+  if (lik == BVG_GAUSSIAN) {
+    L.mu_amp = 2 + G; L.sigma_amp = 3 + G; L.amp = 4 + G; L.mu_alpha = 4 + 2 * G;
+    L.sigma_alpha = L.mu_alpha + k; L.z_alpha = L.sigma_alpha + k; L.tail = L.z_alpha + (int64_t)k * G;
+  } else {
+    L.tail = 2 + G; L.amp = 3 + G; L.mu_amp = 3 + 2 * G; L.sigma_amp = 4 + 2 * G; L.mu_alpha = 5 + 2 * G;
+    L.sigma_alpha = L.mu_alpha + k; L.z_alpha = L.sigma_alpha + k;
+  }
+  L.D = 5 + 2 * G + 2 * (int64_t)k + (int64_t)k * G;
+  return L;
+}
+// compact index of the 2k+5 gene-shared parameters:
+//   0 mu_beta0, 1 log sigma_beta0, 2 mu_amplitude, 3 log sigma_amplitude, 4 log tail,
+//   5..5+k mu_alpha, 5+k..5+2k log sigma_alpha
+__host__ __device__ inline int64_t shared_index(const Layout &L, int k, int i) {
+  switch (i) {
+    case 0: return L.mu_beta0;
+    case 1: return L.sigma_beta0;
+    case 2: return L.mu_amp;
+    case 3: return L.sigma_amp;
+    case 4: return L.tail;
+    default: return i < 5 + k ? L.mu_alpha + (i - 5) : L.sigma_alpha + (i - 5 - k);
+  }
+}
+
+// device-resident control block: everything that changes between iterations lives here so the
+// same launch sequence can be replayed without host involvement
+struct Ctl {
+  uint32_t t_grad;   // running counter of gradient draws   (Philox counter word 2, stream 1)
+  uint32_t t_elbo;   // running counter of ELBO draws        (stream 2)
+  int32_t it;        // 1-based iteration inside the current phase (step-size schedule eta/sqrt(it))
+  int32_t bad;       // number of evaluations whose gradient was non-finite
+  double eta;
+  double lp;         // last log density
+  double elbo_acc;   // sum of finite log densities of the current ELBO estimate
+  int32_t elbo_ok, pad;
+};
+
+struct DevModel {
+  int lik, k, KP, nsplit;
+  int64_t M, G, Gpad, gene_offset, G_total;
+  Layout L, LG;  // local layout (this rank's genes) and global layout (RNG indices)
+  uint64_t seed;
+  double *mu, *omega, *hist, *zeta, *grad;
+  Ctl *ctl;
+  void *C;       // [Gpad][KP]
+  void *Ppart;   // [nsplit][Gpad][KP]
+  void *Spart;   // [nsplit][Gpad][2]
+  double *blk;   // [nblk_gene][NS]
+  double *tot;   // [NS]
+  int nblk_gene;
+  int nhist;                 // nb: distinct count values
+  const double *hist_val;    // nb: value c
+  const double *hist_cnt;    // nb: #pairs with y == c
+  double lgam_y1;            // nb: sum lgamma(y+1) over local pairs
+};
+
+// ---- Philox4x32-10 + Box-Muller: the RNG specification of DESIGN.md section 5 ----------------
+__host__ __device__ inline void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t out[4]) {
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1;
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+__host__ __device__ inline double bvg_normal(uint64_t seed, uint32_t stream, uint32_t t, uint64_t i) {
+  uint32_t o[4];
+  philox4x32_10((uint32_t)i, (uint32_t)(i >> 32), t, stream, (uint32_t)seed, (uint32_t)(seed >> 32), o);
+  const double u1 = ((double)(((uint64_t)o[0] << 21) | (o[2] >> 11)) + 0.5) * (1.0 / 9007199254740992.0);
+  const double u2 = ((double)o[1] + 0.5) * (1.0 / 4294967296.0);
+  return sqrt(-2.0 * log(u1)) * cos(6.283185307179586476925286766559 * u2);
+}
+
+__device__ inline double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---- host-side fit object ---------------------------------------------------------------------
+struct NcclApi;
+struct bvg_fit {
+  bvg_config cfg;
+  int engine;  // resolved bvg_engine
+  cudaStream_t stream;
+  cudaEvent_t ev0, ev1;
+  DevModel m;
+  int64_t ldY, Mpad;
+  void *Y;             // T [G][ldY]
+  void *Phi;           // T [Mpad][KP]
+  double *phi64;       // k x M? kept for basis-independent checks: col-major M x k copy
+  double *dvec;        // backing store of mu|omega|hist(2D)|zeta|grad
+  double *scratch;     // D-length scratch vectors for L-BFGS etc.
+  double *summary;     // [8][G] device
+  double *draws;       // [G][n_draws] device
+  void *flush;         // L2 flush buffer
+  size_t flush_bytes;
+  bool have_phi, have_y, have_mle, have_vi, have_summary;
+  double *h_theta_mle;
+  // trace / stats
+  double trace[4 * 64];
+  int n_trace;
+  bvg_fit_stats st;
+  // tcgen05 engine state (k_lik_tc.cu)
+  void *tc;
+  // comm
+  NcclApi *nccl;
+  void *comm;
+};
+
+void bvg_set_error(const char *fmt, ...);
+#define CUDA_TRY(x)                                                                          \
+  do {                                                                                       \
+    cudaError_t e_ = (x);                                                                    \
+    if (e_ != cudaSuccess) {                                                                 \
+      bvg_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #x, cudaGetErrorString(e_));       \
+      return BVG_ERR_CUDA;                                                                   \
+    }                                                                                        \
+  } while (0)
+#define BVG_TRY(x)              \
+  do {                          \
+    int r_ = (x);               \
+    if (r_ != BVG_OK) return r_; \
+  } while (0)
+
+// launchers (one per translation unit)
+int launch_prep(bvg_fit *f, int mode);                       // k_model.cu: draw + transform -> C
+int launch_lik(bvg_fit *f, bool backward);                   // k_lik_simt.cu / k_lik_tc.cu dispatch
+int launch_lik_simt(bvg_fit *f, bool backward);
+int launch_lik_tc(bvg_fit *f, bool backward);
+bool tc_available();                                         // false until the tcgen05 kernel is linked in
+int tc_setup(bvg_fit *f);                                    // build TMA descriptors etc.
+void tc_destroy(bvg_fit *f);
+int launch_gene(bvg_fit *f, int mode, int jacobian);         // per-gene backward (+ update)
+int launch_finish(bvg_fit *f, int mode, int jacobian, int propto);  // cross-gene reduce + shared params
+int comm_allreduce(bvg_fit *f, double *buf, int n);          // comm.cu
+enum { MODE_GRAD_OUT = 0, MODE_ADVI_UPDATE = 1, MODE_ELBO_DRAW = 2, MODE_LP_ONLY = 3 };
+enum { PREP_NONE = 0, PREP_GRAD = 1, PREP_ELBO = 2 };

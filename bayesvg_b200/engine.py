@@ -1,0 +1,162 @@
+"""Thin object wrapper over the C ABI: one `Fit` = one bvg_fit handle (one gene shard on one GPU)."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as B
+
+SUMMARY_COLUMNS = ["amplitude_mean", "amplitude_median", "amplitude_sd", "amplitude_mad", "amplitude_ci_ll",
+                   "amplitude_ci_ul", "amplitude_dispersion", "amplitude_mean_rank"]
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def default_config(**kw):
+    cfg = B.Config()
+    B.lib().bvg_config_default(C.byref(cfg))
+    for k, v in kw.items():
+        if not hasattr(cfg, k):
+            raise TypeError(f"unknown config field {k}")
+        setattr(cfg, k, v)
+    return cfg
+
+
+def basis_build(coords, centers, lscale, kernel="exp_quad", nu=1.5, period=100.0, device=0):
+    """Phi = qr.Q(qr(kernel(|x - c|^2))) on the GPU (findSpatiallyVariableFeaturesBayes.R:265-288)."""
+    X = np.asfortranarray(coords, dtype=np.float64)
+    Cc = np.asfortranarray(centers, dtype=np.float64)
+    if X.ndim != 2 or X.shape[1] != 2 or Cc.ndim != 2 or Cc.shape[1] != 2:
+        raise ValueError("coords must be M x 2 and centers k x 2")
+    if kernel not in B.KERNELS:
+        raise ValueError("Please provide a valid covariance kernel.")
+    M, k = X.shape[0], Cc.shape[0]
+    out = np.empty((M, k), order="F")
+    B.check(B.lib().bvg_basis_build(device, _dp(X), M, _dp(Cc), k, float(lscale), B.KERNELS[kernel], float(nu),
+                                    float(period), _dp(out)))
+    return out
+
+
+class Fit:
+    def __init__(self, phi, y, likelihood="gaussian", precision="fast", engine="auto", **cfg):
+        lik = {"gaussian": B.GAUSSIAN, "nb": B.NB}.get(likelihood)
+        if lik is None:
+            raise ValueError("Please provide a valid likelihood.")
+        self.cfg = default_config(likelihood=lik, precision={"fp64": B.PREC_FP64, "fast": B.PREC_FAST}[precision],
+                                  engine={"auto": B.ENGINE_AUTO, "simt": B.ENGINE_SIMT, "tcgen05": B.ENGINE_TCGEN05}[engine],
+                                  **cfg)
+        self._h = C.c_void_p()
+        B.check(B.lib().bvg_fit_create(C.byref(self.cfg), C.byref(self._h)))
+        phi = np.asfortranarray(phi, dtype=np.float64)
+        self.M, self.k = phi.shape
+        B.check(B.lib().bvg_fit_set_phi(self._h, _dp(phi), self.M, self.k))
+        self.set_y(y)
+
+    def set_y(self, y):
+        if y.ndim != 2 or y.shape[0] != self.M:
+            raise ValueError(f"y must be M x G with M = {self.M}")
+        self.G = y.shape[1]
+        if np.issubdtype(y.dtype, np.integer):
+            y = np.asfortranarray(y, dtype=np.int32)
+            B.check(B.lib().bvg_fit_set_y_i32(self._h, y.ctypes.data_as(C.POINTER(C.c_int32)), self.M, self.G))
+        else:
+            y = np.asfortranarray(y, dtype=np.float64)
+            B.check(B.lib().bvg_fit_set_y_f64(self._h, _dp(y), self.M, self.G))
+        d = C.c_int64()
+        B.check(B.lib().bvg_fit_dim(self._h, C.byref(d)))
+        self.D = d.value
+
+    def close(self):
+        if getattr(self, "_h", None):
+            B.lib().bvg_fit_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def comm_init(self, unique_id: bytes):
+        buf = C.create_string_buffer(unique_id, len(unique_id))
+        B.check(B.lib().bvg_fit_comm_init(self._h, C.cast(buf, C.c_void_p), len(unique_id)))
+
+    def log_prob(self, theta, jacobian=True, propto=True, grad=True):
+        th = np.ascontiguousarray(theta, dtype=np.float64)
+        if th.shape != (self.D,):
+            raise ValueError(f"theta must have length {self.D}")
+        lp = C.c_double()
+        g = np.empty(self.D) if grad else None
+        B.check(B.lib().bvg_log_prob(self._h, _dp(th), int(jacobian), int(propto), C.byref(lp), _dp(g) if grad else None))
+        return (lp.value, g) if grad else lp.value
+
+    def run(self):
+        B.check(B.lib().bvg_fit_run(self._h))
+        return self.summary()
+
+    def mle(self, theta0=None):
+        out = np.empty(self.D)
+        t0 = None if theta0 is None else _dp(np.ascontiguousarray(theta0, dtype=np.float64))
+        B.check(B.lib().bvg_fit_mle(self._h, t0, _dp(out)))
+        return out
+
+    def advi(self, theta_init=None):
+        t0 = None if theta_init is None else _dp(np.ascontiguousarray(theta_init, dtype=np.float64))
+        B.check(B.lib().bvg_fit_advi(self._h, t0))
+
+    def summarize(self):
+        B.check(B.lib().bvg_fit_summarize(self._h))
+        return self.summary()
+
+    def set_variational(self, mu, omega=None):
+        mu = np.ascontiguousarray(mu, dtype=np.float64)
+        om = None if omega is None else np.ascontiguousarray(omega, dtype=np.float64)
+        B.check(B.lib().bvg_fit_set_variational(self._h, _dp(mu), None if om is None else _dp(om)))
+
+    def get_variational(self):
+        mu, om = np.empty(self.D), np.empty(self.D)
+        B.check(B.lib().bvg_fit_get_variational(self._h, _dp(mu), _dp(om)))
+        return mu, om
+
+    def advi_steps(self, n, eta, reset=False):
+        ms = C.c_float()
+        B.check(B.lib().bvg_fit_advi_steps(self._h, n, float(eta), int(reset), C.byref(ms)))
+        return ms.value
+
+    def elbo(self, n_samples=150):
+        e, ms = C.c_double(), C.c_float()
+        B.check(B.lib().bvg_fit_elbo(self._h, n_samples, C.byref(e), C.byref(ms)))
+        return e.value, ms.value
+
+    def time_lik_kernel(self, n=10, flush_l2=True, backward=True):
+        ms = C.c_float()
+        B.check(B.lib().bvg_fit_time_lik_kernel(self._h, n, int(flush_l2), int(backward), C.byref(ms)))
+        return ms.value
+
+    def flush_l2(self):
+        B.check(B.lib().bvg_fit_flush_l2(self._h))
+
+    def summary(self):
+        out = np.empty((self.G, 8), order="F")
+        B.check(B.lib().bvg_fit_get_summary(self._h, _dp(out)))
+        return out
+
+    def draws(self):
+        out = np.empty((self.cfg.n_draws, self.G), order="F")
+        B.check(B.lib().bvg_fit_get_draws(self._h, _dp(out)))
+        return out
+
+    def trace(self):
+        out = np.zeros((64, 4))
+        n = C.c_int()
+        B.check(B.lib().bvg_fit_get_trace(self._h, _dp(out), 64, C.byref(n)))
+        return out[: n.value].copy()
+
+    def stats(self):
+        st = B.Stats()
+        B.check(B.lib().bvg_fit_get_stats(self._h, C.byref(st)))
+        return {f: getattr(st, f) for f, _ in B.Stats._fields_ if f != "pad"}
+
+
+def comm_unique_id():
+    buf = C.create_string_buffer(128)
+    n = C.c_size_t()
+    B.check(B.lib().bvg_comm_unique_id(C.cast(buf, C.c_void_p), 128, C.byref(n)))
+    return buf.raw[: n.value]

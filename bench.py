@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""bench.py -- ELBO-gradient evaluations per second of the bayesVG SVG hot path on B200.
+
+Workload (BASELINE.json configs[1]): synthetic full Visium grid, 4,992 spots x 3,000 genes, k = 20
+Matern-2.5 basis, Gaussian likelihood, mean-field ADVI.  One STEP = --evals-per-step (100) consecutive
+ELBO-gradient evaluations = the stretch of the ADVI loop between two convergence checks; one
+evaluation = one Philox draw of all D = 66,045 parameters, the fused likelihood pass over all
+spot x gene pairs (forward + analytic backward) and the mean-field update.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+N > 1 (torchrun, one rank per GPU): weak scaling -- every rank holds its own 3,000 genes (G_total =
+3,000 N), the 2k+10 cross-gene sums are all-reduced (NCCL) inside every evaluation, and `value` counts
+3,000-gene evaluations (N per global evaluation).
+
+--impl reference times the reference's CPU path.  The reference is R + CmdStan, neither of which
+exists in this image, so that arm is the fp64 C restatement in oracle/ ("port") running
+the same evaluation with all host threads.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+M_SPOTS, G_GENES, K_BASIS = 4992, 3000, 20
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """samples SM clock + throttle reasons through NVML while the timed region runs"""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz, self.ok = index, [], set(), False, None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def summary(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def make_dataset(basis_fn, seed):
+    from bayesvg_b200 import synth
+    X = synth.scale_coords(synth.visium_grid())
+    C = synth.det_kmeans(X, K_BASIS, 312)
+    from bayesvg_b200.api import length_scale_kmeans
+    ls = length_scale_kmeans(C)
+    phi = basis_fn(X, C, ls)
+    Y, _ = synth.expression(phi, G_GENES, "gaussian", seed)
+    return phi, Y
+
+
+def cpu_evals(phi, Y, min_seconds, min_evals, nthreads):
+    """time ELBO-gradient evaluations (draw + log_prob_grad + meanfield update) of the CPU restatement"""
+    from oracle import oracle as orc
+    o = orc.Oracle(phi, Y, "gaussian", nthreads=nthreads)
+    mu, om, hist = np.zeros(o.D), np.zeros(o.D), np.zeros(2 * o.D)
+    o.advi_step(mu, om, hist, 0.1, 1, 312, 0)  # warm-up (page in Y)
+    n, t0 = 0, time.perf_counter()
+    while n < min_evals or time.perf_counter() - t0 < min_seconds:
+        o.advi_step(mu, om, hist, 0.1, n + 2, 312, n + 1)
+        n += 1
+    return n, time.perf_counter() - t0
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    from oracle import oracle as orc
+    nthreads = os.cpu_count() or 1
+    phi, Y = make_dataset(lambda X, C, ls: orc.basis(X, C, ls, "matern", 2.5), 312)
+    o = orc.Oracle(phi, Y, "gaussian", nthreads=nthreads)
+    mu, om, hist = np.zeros(o.D), np.zeros(o.D), np.zeros(2 * o.D)
+    per_step = args.ref_evals_per_step
+    t = 0
+    for _ in range(args.warmup):
+        for _ in range(per_step):
+            o.advi_step(mu, om, hist, 0.1, t + 1, 312, t)
+            t += 1
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        for _ in range(per_step):
+            o.advi_step(mu, om, hist, 0.1, t + 1, 312, t)
+            t += 1
+    dt = time.perf_counter() - t0
+    value = args.steps * per_step / dt
+    sample = f"{args.steps} steps x {per_step} ELBO-gradient evals of the full 4,992 x 3,000 workload (fp64, OpenMP x {nthreads})"
+    print(json.dumps({
+        "impl": "reference", "metric": "elbo_grad_evals_per_sec", "value": value, "unit": "evals/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "cfg2: 4,992 spots x 3,000 genes, k=20 Matern-2.5, gaussian, meanfield ADVI",
+                   "evals_per_step": per_step,
+                   "note": "R/CmdStan are absent from the image: this is the fp64 C restatement (oracle/) of the "
+                           "reference's log-density/gradient + ADVI update; it has no AD tape, no JSON/CSV, no g++ "
+                           "compile, so it is faster than the real CmdStan path"},
+        "cpu_baseline": {"value": value, "unit": "evals/s", "cores": nthreads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+
+    import bayesvg_b200 as bvg
+    from bayesvg_b200 import dist as bdist
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as td
+        td.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    phi, Y = make_dataset(lambda X, C, ls: bvg.basis_build(X, C, ls, "matern", 2.5, device=local_rank), 312 + rank)
+    E = args.evals_per_step
+    cfg = dict(device=local_rank, seed=312)
+    if world > 1:
+        fit = bdist.make_sharded_fit(phi, Y, bdist.Shard(rank, world), G_GENES * world, G_GENES * rank, "gaussian",
+                                     "fast", args.engine, cfg)
+    else:
+        fit = bvg.Fit(phi, Y, "gaussian", "fast", args.engine, **cfg)
+    D = fit.D
+    fit.set_variational(np.zeros(D), None)
+    fit.advi_steps(0, 0.1, reset=True)
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as td
+            td.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-timed steps ----
+    for _ in range(max(args.warmup, 3)):
+        fit.advi_steps(E, 0.1)
+    sampler = ClockSampler(local_rank)
+    launches0 = fit.stats()["kernel_launches"]
+    barrier()
+    sampler.start()
+    ms_total = 0.0
+    for _ in range(args.steps):
+        if not args.no_flush:
+            fit.flush_l2()
+        ms_total += fit.advi_steps(E, 0.1)  # CUDA events on the engine's stream
+    barrier()
+    sampler.stop_flag = True
+    sampler.join()
+    launches = fit.stats()["kernel_launches"] - launches0
+    if world > 1:
+        import torch.distributed as td
+        t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
+        td.all_reduce(t, op=td.ReduceOp.MAX)
+        ms_total = float(t.item())
+    value = world * args.steps * E / (ms_total * 1e-3)
+
+    # ---- the dominant kernel against its roofline ----
+    peak, peak_src = load_peaks()
+    KP = 24
+    bytes_launch = 4 * M_SPOTS * G_GENES + 4 * M_SPOTS * K_BASIS + 8 * K_BASIS * G_GENES
+    ms_cold = fit.time_lik_kernel(20, True, True)
+    ms_warm = fit.time_lik_kernel(50, False, True)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    st = fit.stats()
+    eng_name = {1: "simt", 2: "tcgen05"}.get(st["engine_used"], "?")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(eng_name)
+    roofline = {"bound": "hbm", "kernel": f"k_lik_{eng_name} (forward+backward, cold L2)",
+                "achieved": bytes_launch / (ms_cold * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                "frac": bytes_launch / (ms_cold * 1e-3) / 1e9 / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": bytes_launch, "ms_per_launch_cold_l2": ms_cold,
+                "ms_per_launch_l2_resident": ms_warm,
+                "l2_resident_equiv_gbs": bytes_launch / (ms_warm * 1e-3) / 1e9}
+
+    # ---- end to end through the C ABI with host buffers (pinned), rank-local ----
+    Yp = torch.from_numpy(Y).pin_memory() if args.pin else None
+    Yh = Yp.numpy() if Yp is not None else Y
+    Yh = np.asfortranarray(Yh) if not Yh.flags.f_contiguous else Yh
+    e2e_steps = max(2, min(args.steps, 5))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        if world > 1:
+            f2 = bdist.make_sharded_fit(phi, Yh, bdist.Shard(rank, world), G_GENES * world, G_GENES * rank,
+                                        "gaussian", "fast", args.engine, cfg)
+        else:
+            f2 = bvg.Fit(phi, Yh, "gaussian", "fast", args.engine, **cfg)   # H2D of phi + Y
+        f2.set_variational(np.zeros(D), None)
+        f2.advi_steps(0, 0.1, reset=True)
+        f2.advi_steps(E, 0.1)
+        mu, om = f2.get_variational()                                      # D2H of the step's result
+        f2.close()
+    barrier()
+    e2e_dt = time.perf_counter() - t0
+    if world > 1:
+        import torch.distributed as td
+        t = torch.tensor([e2e_dt], device="cuda", dtype=torch.float64)
+        td.all_reduce(t, op=td.ReduceOp.MAX)
+        e2e_dt = float(t.item())
+    e2e = {"value": world * e2e_steps * E / e2e_dt, "unit": "evals/s",
+           "h2d_bytes_per_step": int(Y.nbytes + phi.nbytes + 8 * D), "d2h_bytes_per_step": int(16 * D),
+           "what": f"Fit(phi, Y) from host + {E} ELBO-gradient evals + read-back of (mu, omega); the H2D of Y is "
+                   f"amortised over {E} evals here, over >= 3,250 in a real fit"}
+
+    # ---- full default fit (the other half of the metric: SVG fit wall-clock), N = 1 only ----
+    fit_info = None
+    if world == 1 and not args.skip_fit:
+        t0 = time.perf_counter()
+        f3 = bvg.Fit(phi, Y, "gaussian", "fast", args.engine, **cfg)
+        f3.run()
+        s3 = f3.stats()
+        fit_info = {"wall_s": time.perf_counter() - t0, "grad_evals": s3["grad_evals"], "elbo_evals": s3["elbo_evals"],
+                    "advi_iters": s3["advi_iters"], "eta": s3["eta"], "mle_iters": s3["mle_iters"],
+                    "mle_fevals": s3["mle_fevals"], "sec_mle": s3["sec_mle"], "sec_adapt": s3["sec_adapt"],
+                    "sec_sga": s3["sec_sga"], "sec_draws": s3["sec_draws"], "converged": s3["converged"]}
+        f3.close()
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.skip_cpu:
+        nthreads = os.cpu_count() or 1
+        n, dt = cpu_evals(phi, Y, args.cpu_seconds, 3, nthreads)
+        cpu = {"value": n / dt, "unit": "evals/s", "cores": nthreads, "kind": "port",
+               "sample": f"{n} ELBO-gradient evals of the full 4,992 x 3,000 workload in {dt:.1f} s (fp64 C restatement, OpenMP)"}
+    fit.close()
+    if rank == 0:
+        print(json.dumps({
+            "metric": "elbo_grad_evals_per_sec", "value": value, "unit": "evals/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "cfg2: 4,992 spots x 3,000 genes per GPU, k=20 Matern-2.5, gaussian, meanfield ADVI",
+                       "evals_per_step": E, "engine": eng_name,
+                       "l2": ("L2 flushed (512 MB write) before every timed step; inside a step the evals re-read "
+                              "the 60 MB Y as the real fit does" if not args.no_flush else "no flush"),
+                       "genes_total": G_GENES * world},
+            "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+            "cpu_baseline": cpu, "fit": fit_info,
+        }))
+    if world > 1:
+        import torch.distributed as td
+        td.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--evals-per-step", type=int, default=100)
+    ap.add_argument("--ref-evals-per-step", type=int, default=2)
+    ap.add_argument("--engine", default="auto", choices=["auto", "simt", "tcgen05"])
+    ap.add_argument("--no-flush", action="store_true")
+    ap.add_argument("--pin", action="store_true", default=True)
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-fit", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

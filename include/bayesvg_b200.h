@@ -1,0 +1,149 @@
+/*
+ * bayesvg_b200.h -- C ABI of the B200-native engine for bayesVG's SVG hot path.
+ *
+ * The reference has no FFI: its only seam for this path is the sequence of cmdstanr method calls
+ * in R/findSpatiallyVariableFeaturesBayes.R:337-364 and :419 (paths relative to the reference):
+ *     cmdstan_model() / $compile()      :337-341   -> nothing (kernels are precompiled)
+ *     data_list                          :320-327   -> bvg_fit_set_phi / bvg_fit_set_y_*
+ *     mod$optimize(init=0, jacobian=F)   :346-353   -> bvg_fit_mle            (or bvg_fit_run)
+ *     mod$variational(meanfield, ...)    :357-364   -> bvg_fit_advi           (or bvg_fit_run)
+ *     fit_vi$summary("amplitude")        :419-432   -> bvg_fit_summarize + bvg_fit_get_summary
+ *     fit$log_prob / fit$grad_log_prob   (cmdstanr) -> bvg_log_prob           (the parity hook)
+ *     phi <- kernel(...); qr.Q(qr(phi))  :265-288   -> bvg_basis_build
+ * An R package binds these through a logic-free .Call shim.
+ *
+ * Conventions: every matrix is COLUMN-MAJOR like R.  All pointers are HOST pointers owned by the
+ * caller; the library copies on set_* and writes results into caller-allocated buffers.  Every
+ * function returns 0 on success or a negative bvg_status; the message is in bvg_last_error()
+ * (thread-local).  Nothing throws across the ABI.  There is no CPU fallback: without a CUDA
+ * device every compute entry point fails with BVG_ERR_CUDA.
+ */
+#ifndef BAYESVG_B200_H
+#define BAYESVG_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BVG_ABI_VERSION 1
+
+typedef enum {
+  BVG_OK = 0,
+  BVG_ERR_ARG = -1,      /* invalid argument / unsupported configuration */
+  BVG_ERR_CUDA = -2,     /* CUDA runtime or driver error, or no device */
+  BVG_ERR_STATE = -3,    /* call order (e.g. run before set_y) */
+  BVG_ERR_NUMERIC = -4,  /* non-finite log density where Stan would raise */
+  BVG_ERR_COMM = -5      /* NCCL error */
+} bvg_status;
+
+typedef enum { BVG_GAUSSIAN = 0 /* inst/approxGP.stan */, BVG_NB = 1 /* inst/approxGP4.stan */ } bvg_likelihood;
+typedef enum { BVG_KERNEL_EXP_QUAD = 0, BVG_KERNEL_MATERN = 1, BVG_KERNEL_PERIODIC = 2 } bvg_kernel;
+typedef enum {
+  BVG_PREC_FP64 = 0, /* Y and all arithmetic fp64: the <=1e-6 parity path */
+  BVG_PREC_FAST = 1  /* Y fp32, likelihood contraction fp32 / 3xTF32; parameters stay fp64 */
+} bvg_precision;
+typedef enum {
+  BVG_ENGINE_AUTO = 0,    /* tcgen05 when precision = FAST and k+1 <= 24, else SIMT */
+  BVG_ENGINE_SIMT = 1,    /* CUDA-core kernel (fp64 or fp32) */
+  BVG_ENGINE_TCGEN05 = 2  /* TMA + tcgen05/TMEM kernel (FAST only) */
+} bvg_engine;
+
+/* Mirrors the arguments of findSpatiallyVariableFeaturesBayes() (:78-97) that reach the fit, plus
+ * the CmdStan defaults the reference leaves untouched. */
+typedef struct {
+  int32_t abi_version;   /* BVG_ABI_VERSION */
+  int32_t likelihood;    /* bvg_likelihood   (likelihood = "gaussian" | "nb", :80) */
+  int32_t precision;     /* bvg_precision */
+  int32_t engine;        /* bvg_engine */
+  int32_t device;        /* CUDA ordinal */
+  int32_t n_iter;        /* n.iter = 3000 (:82) */
+  int32_t mle_init;      /* mle.init = TRUE (:88) */
+  int32_t mle_iter;      /* mle.iter = 1000 (:89) */
+  int32_t n_draws;       /* n.draws = 1000 (:91) */
+  int32_t elbo_samples;  /* elbo.samples = 150 for meanfield (:110-116) */
+  int32_t eval_elbo;     /* CmdStan default 100 */
+  int32_t adapt_iter;    /* CmdStan default 50 */
+  int32_t lbfgs_history; /* history_size = 25 (:353) */
+  int32_t verbose;       /* print the ELBO table to stderr */
+  double tol_rel_obj;    /* CmdStan default 0.01 */
+  double eta;            /* <= 0: adapt over {100,10,1,0.1,0.01} (CmdStan default) */
+  uint64_t seed;         /* random.seed = 312 (:95) */
+  /* gene sharding: this process holds genes [gene_offset, gene_offset + G) of G_total */
+  int32_t rank, world_size;
+  int64_t gene_offset, G_total; /* G_total = 0 -> unsharded */
+} bvg_config;
+
+typedef struct bvg_fit bvg_fit;
+
+int bvg_version(void);
+const char *bvg_last_error(void);
+int bvg_device_count(void);
+void bvg_config_default(bvg_config *cfg);
+
+/* Basis builder (:265-288): phi_out = thin Q of column-pivoted Householder QR of
+ * kernel(|x_s - c_i|^2, lscale).  coords M x 2 (already z-scored, :160), centers k x 2. */
+int bvg_basis_build(int device, const double *coords, int64_t M, const double *centers, int k,
+                    double lscale, int kernel, double nu, double period, double *phi_out);
+
+int bvg_fit_create(const bvg_config *cfg, bvg_fit **out);
+void bvg_fit_destroy(bvg_fit *);
+
+/* data_list$phi (M x k) and data_list$y (the gene-major long vector = M x G column-major).
+ * spot_id / gene_id are implied (N = M*G). */
+int bvg_fit_set_phi(bvg_fit *, const double *phi, int64_t M, int k);
+int bvg_fit_set_y_f64(bvg_fit *, const double *y, int64_t M, int64_t G);
+int bvg_fit_set_y_i32(bvg_fit *, const int32_t *y, int64_t M, int64_t G);
+int bvg_fit_dim(bvg_fit *, int64_t *D);
+
+/* multi-GPU: rank 0 calls bvg_comm_unique_id, the host broadcasts the bytes, every rank calls
+ * bvg_fit_comm_init.  NCCL is resolved with dlopen("libnccl.so.2") at that point. */
+int bvg_comm_unique_id(void *out, size_t cap, size_t *len);
+int bvg_fit_comm_init(bvg_fit *, const void *unique_id, size_t len);
+
+/* log density and gradient at an unconstrained vector in Stan declaration order (local layout
+ * when sharded).  Stands in for cmdstanr's $log_prob / $grad_log_prob.  grad may be NULL. */
+int bvg_log_prob(bvg_fit *, const double *theta, int jacobian, int propto, double *lp, double *grad);
+
+/* whole path: [L-BFGS init] -> eta adaptation -> stochastic gradient ascent -> draws -> summary */
+int bvg_fit_run(bvg_fit *);
+
+/* the stages of bvg_fit_run, individually callable */
+int bvg_fit_mle(bvg_fit *, const double *theta0 /* NULL = 0 */, double *theta_out /* may be NULL */);
+int bvg_fit_advi(bvg_fit *, const double *theta_init /* NULL = MLE result or 0 */);
+int bvg_fit_summarize(bvg_fit *);
+
+/* finer-grained hooks used by the parity tests and the benchmark */
+int bvg_fit_set_variational(bvg_fit *, const double *mu, const double *omega /* NULL = 0 */);
+int bvg_fit_get_variational(bvg_fit *, double *mu, double *omega);
+/* n stochastic-gradient steps (iteration counter continues from the last reset);
+ * ms_out (optional) = device time from CUDA events on the engine's stream */
+int bvg_fit_advi_steps(bvg_fit *, int n, double eta, int reset_counters, float *ms_out);
+int bvg_fit_elbo(bvg_fit *, int n_samples, double *elbo_out, float *ms_out);
+/* time n launches of the likelihood kernel alone; flush_l2 != 0 evicts L2 before each launch */
+int bvg_fit_time_lik_kernel(bvg_fit *, int n, int flush_l2, int backward, float *ms_avg_out);
+
+/* evict the L2 (writes a 512 MB scratch buffer) -- benchmark hygiene between timed steps */
+int bvg_fit_flush_l2(bvg_fit *);
+
+/* results */
+int bvg_fit_get_summary(bvg_fit *, double *out /* G x 8 col-major: mean, median, sd, mad, q5, q95, dispersion, rank */);
+int bvg_fit_get_draws(bvg_fit *, double *out /* n_draws x G col-major amplitude draws */);
+int bvg_fit_get_trace(bvg_fit *, double *out /* cap x 4 row-major: iter, elbo, delta_mean, delta_med */, int cap, int *n);
+
+typedef struct {
+  double eta;
+  int32_t advi_iters, grad_evals, elbo_evals, converged; /* converged: 1 mean, 2 median, 3 both, 0 max-iter */
+  int32_t mle_iters, mle_fevals, mle_term;
+  double mle_lp, elbo;
+  double sec_h2d, sec_mle, sec_adapt, sec_sga, sec_draws, sec_total;
+  int64_t kernel_launches;
+  int32_t engine_used; /* bvg_engine actually running the likelihood */
+  int32_t pad;
+} bvg_fit_stats;
+int bvg_fit_get_stats(bvg_fit *, bvg_fit_stats *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
