@@ -144,13 +144,16 @@ static int finalize_model(bvg_fit *f) {
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, f->cfg.device);
   const int ntiles = (int)(m.Gpad / BVG_GENE_TILE);
   const int64_t nchunks = (m.M + 31) / 32;
-  const int ctas_per_sm = f->engine == BVG_ENGINE_TCGEN05 ? 1 : 4;
-  int nsplit = (nsm * ctas_per_sm + ntiles - 1) / ntiles;
+  // SIMT: ~4 resident CTAs per SM; tcgen05: one 176 KB CTA per SM and never more CTAs than SMs (a
+  // partial second wave would double the kernel time), so round DOWN
+  int nsplit = f->engine == BVG_ENGINE_TCGEN05 ? std::max(1, nsm / ntiles) : (nsm * 4 + ntiles - 1) / ntiles;
   nsplit = (int)std::max<int64_t>(1, std::min<int64_t>(nsplit, nchunks));
   const int64_t cps = (nchunks + nsplit - 1) / nsplit;
   m.nsplit = (int)((nchunks + cps - 1) / cps);
-  CUDA_TRY(cudaMalloc(&m.C, ts * m.Gpad * m.KP * 3));  // x3: room for the tf32 hi/lo split rows
-  CUDA_TRY(cudaMemsetAsync(m.C, 0, ts * m.Gpad * m.KP * 3, f->stream));
+  // coefficient rows: [Gpad][KP] in the compute type, or (tcgen05) two [Gpad][32] fp32 arrays (tf32 hi / lo)
+  const size_t c_bytes = std::max<size_t>(ts * m.Gpad * m.KP, (size_t)2 * 4 * m.Gpad * 32);
+  CUDA_TRY(cudaMalloc(&m.C, c_bytes));
+  CUDA_TRY(cudaMemsetAsync(m.C, 0, c_bytes, f->stream));
   CUDA_TRY(cudaMalloc(&m.Ppart, ts * (size_t)m.nsplit * m.Gpad * m.KP));
   CUDA_TRY(cudaMalloc(&m.Spart, ts * (size_t)m.nsplit * m.Gpad * 2));
   CUDA_TRY(cudaMemsetAsync(m.Ppart, 0, ts * (size_t)m.nsplit * m.Gpad * m.KP, f->stream));

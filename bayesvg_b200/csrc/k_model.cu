@@ -11,7 +11,7 @@
 
 // ------------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(256) k_prep(DevModel m, int mode) {
+__global__ void __launch_bounds__(256) k_prep(DevModel m, int mode, int tc) {
   extern __shared__ double sh[];  // [2k+5] shared zeta | [k] sigma_alpha
   const int k = m.k, nsh = 2 * k + 5;
   const uint32_t stream = mode == PREP_GRAD ? STREAM_GRAD : STREAM_ELBO;
@@ -51,7 +51,18 @@ __global__ void __launch_bounds__(256) k_prep(DevModel m, int mode) {
   const double zb = __shfl_sync(0xffffffffu, v, 0), u = __shfl_sync(0xffffffffu, v, 1);
   const double A = exp(2.0 * u);        // amplitude_sq (approxGP.stan:27)
   const double beta = mb + sb * zb;     // beta0        (approxGP.stan:26)
-  T *Crow = (T *)m.C + g * m.KP;
+  // tc != 0: rows of width 32, split into tf32 hi / lo parts for the 3xTF32 tensor-core contraction
+  const int cw = tc ? 32 : m.KP;
+  T *Crow = (T *)m.C + g * cw, *Clo = (T *)m.C + (m.Gpad + g) * cw;
+  auto put = [&](int j, double v) {
+    if (!tc) { Crow[j] = (T)v; return; }
+    const float x = (float)v;
+    uint32_t hb;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(x));
+    const float hi = __uint_as_float(hb);
+    Crow[j] = (T)hi;
+    Clo[j] = (T)(x - hi);
+  };
   for (int j = lane; j < k; j += 32) {
     const int64_t li = m.L.z_alpha + g * k + j;
     double z;
@@ -61,17 +72,17 @@ __global__ void __launch_bounds__(256) k_prep(DevModel m, int mode) {
     } else {
       z = m.zeta[li];
     }
-    Crow[j] = (T)(A * (sh[5 + j] + sal[j] * z));  // A_g * alpha_t[j,g] (approxGP.stan:32)
+    put(j, A * (sh[5 + j] + sal[j] * z));  // A_g * alpha_t[j,g] (approxGP.stan:32)
   }
-  if (lane == 0) Crow[k] = (T)beta;
+  if (lane == 0) put(k, beta);
 }
 
 int launch_prep(bvg_fit *f, int mode) {
   const int wpb = 8;
   const int grid = (int)((f->m.G + wpb - 1) / wpb);
   const size_t sh = sizeof(double) * (3 * f->m.k + 5);
-  if (f->cfg.precision == BVG_PREC_FP64) k_prep<double><<<grid, wpb * 32, sh, f->stream>>>(f->m, mode);
-  else k_prep<float><<<grid, wpb * 32, sh, f->stream>>>(f->m, mode);
+  if (f->cfg.precision == BVG_PREC_FP64) k_prep<double><<<grid, wpb * 32, sh, f->stream>>>(f->m, mode, 0);
+  else k_prep<float><<<grid, wpb * 32, sh, f->stream>>>(f->m, mode, f->engine == BVG_ENGINE_TCGEN05);
   f->st.kernel_launches++;
   CUDA_TRY(cudaGetLastError());
   return BVG_OK;
