@@ -158,10 +158,12 @@ static int finalize_model(bvg_fit *f) {
   CUDA_TRY(cudaMalloc(&m.Spart, ts * (size_t)m.nsplit * m.Gpad * 2));
   CUDA_TRY(cudaMemsetAsync(m.Ppart, 0, ts * (size_t)m.nsplit * m.Gpad * m.KP, f->stream));
   CUDA_TRY(cudaMemsetAsync(m.Spart, 0, ts * (size_t)m.nsplit * m.Gpad * 2, f->stream));
-  m.nblk_gene = (int)std::min<int64_t>((m.G + 7) / 8, nsm * 4);
+  m.nblk_gene = (int)std::min<int64_t>((m.G + 15) / 16, nsm);  // 16 gene-warps per CTA, at most one CTA per SM
   const int NS = bvg_ns(m.k);
-  CUDA_TRY(cudaMalloc(&m.blk, sizeof(double) * ((size_t)m.nblk_gene + 1) * NS));
+  CUDA_TRY(cudaMalloc(&m.blk, sizeof(double) * (((size_t)m.nblk_gene + 1) * NS + 3 + m.k + m.G)));
   m.tot = m.blk + (size_t)m.nblk_gene * NS;
+  m.shx = m.tot + NS;
+  m.Aexp = m.shx + 3 + m.k;
   CUDA_TRY(cudaMalloc(&m.ctl, sizeof(Ctl)));
   CUDA_TRY(cudaMemsetAsync(m.ctl, 0, sizeof(Ctl), f->stream));
   CUDA_TRY(cudaMalloc(&f->summary, sizeof(double) * 8 * m.G));
@@ -277,8 +279,7 @@ int eval_log_prob_device(bvg_fit *f, int mode, int jac, int propto, bool backwar
   const int prep = mode == MODE_ADVI_UPDATE ? PREP_GRAD : (mode == MODE_ELBO_DRAW ? PREP_ELBO : PREP_NONE);
   BVG_TRY(launch_prep(f, prep));
   BVG_TRY(launch_lik(f, backward));
-  BVG_TRY(launch_gene(f, mode, jac));
-  BVG_TRY(launch_finish(f, mode, jac, propto));
+  BVG_TRY(launch_gene_finish(f, mode, jac, propto));
   return BVG_OK;
 }
 
@@ -566,6 +567,52 @@ extern "C" int bvg_fit_time_lik_kernel(bvg_fit *f, int n, int flush_l2, int back
     total = ms;
   }
   *ms_avg_out = (float)(total / n);
+  return BVG_OK;
+}
+
+// diagnostics: %globaltimer stamps (ns) inside one k_gene launch: [0] block 0 start, [1] after setup,
+// [2] after the gene loop, [3] after the block partials, [4] last block enters finish, [5] after the
+// cross-block reduction, [6] after lp / shared update, [7] end
+extern "C" int bvg_debug_gene_trace(bvg_fit *f, long long *out8) {
+  BVG_TRY(need_ready(f));
+  long long *d = nullptr;
+  CUDA_TRY(cudaMalloc(&d, 16 * sizeof(long long)));
+  CUDA_TRY(cudaMemsetAsync(d, 0, 16 * sizeof(long long), f->stream));
+  BVG_TRY(launch_prep(f, PREP_GRAD));
+  BVG_TRY(launch_lik(f, true));
+  f->m.dbg = d;
+  int rc = launch_gene_finish(f, MODE_ADVI_UPDATE, 1, 1);
+  f->m.dbg = nullptr;
+  if (rc == BVG_OK && (cudaMemcpyAsync(out8, d, 8 * sizeof(long long), cudaMemcpyDeviceToHost, f->stream) != cudaSuccess || cudaStreamSynchronize(f->stream) != cudaSuccess)) rc = BVG_ERR_CUDA;
+  cudaFree(d);
+  return rc;
+}
+
+// diagnostics: average device time (ms) of the four stages of one ELBO-gradient evaluation
+extern "C" int bvg_debug_stage_times(bvg_fit *f, int n, float *out4) {
+  BVG_TRY(need_ready(f));
+  cudaEvent_t ev[5];
+  for (auto &e : ev) CUDA_TRY(cudaEventCreate(&e));
+  double acc[4] = {0, 0, 0, 0};
+  Ctl h;
+  BVG_TRY(ctl_get(f, &h));
+  if (h.it < 1) h.it = 1;
+  if (!(h.eta > 0)) h.eta = 0.1;
+  BVG_TRY(ctl_set(f, h));
+  for (int i = 0; i < n; ++i) {
+    CUDA_TRY(cudaEventRecord(ev[0], f->stream));
+    BVG_TRY(launch_prep(f, PREP_GRAD));
+    CUDA_TRY(cudaEventRecord(ev[1], f->stream));
+    BVG_TRY(launch_lik(f, true));
+    CUDA_TRY(cudaEventRecord(ev[2], f->stream));
+    BVG_TRY(launch_gene_finish(f, MODE_ADVI_UPDATE, 1, 1));
+    CUDA_TRY(cudaEventRecord(ev[3], f->stream));
+    CUDA_TRY(cudaEventRecord(ev[4], f->stream));
+    CUDA_TRY(cudaEventSynchronize(ev[4]));
+    for (int q = 0; q < 4; ++q) { float ms; CUDA_TRY(cudaEventElapsedTime(&ms, ev[q], ev[q + 1])); acc[q] += ms; }
+  }
+  for (int q = 0; q < 4; ++q) out4[q] = (float)(acc[q] / n);
+  for (auto &e : ev) cudaEventDestroy(e);
   return BVG_OK;
 }
 

@@ -68,7 +68,8 @@ struct Ctl {
   double eta;
   double lp;         // last log density
   double elbo_acc;   // sum of finite log densities of the current ELBO estimate
-  int32_t elbo_ok, pad;
+  int32_t elbo_ok;
+  uint32_t ticket;   // last-block-done counter of k_gene (fused finish)
 };
 
 struct DevModel {
@@ -83,11 +84,14 @@ struct DevModel {
   void *Spart;   // [nsplit][Gpad][2]
   double *blk;   // [nblk_gene][NS]
   double *tot;   // [NS]
+  double *shx;   // [3+k] exp of the shared log-scales of the current draw: sigma_beta0, sigma_amplitude, tail, sigma_alpha[k]
+  double *Aexp;  // [G] amplitude_sq of the current draw
   int nblk_gene;
   int nhist;                 // nb: distinct count values
   const double *hist_val;    // nb: value c
   const double *hist_cnt;    // nb: #pairs with y == c
   double lgam_y1;            // nb: sum lgamma(y+1) over local pairs
+  long long *dbg;            // diagnostics: %globaltimer stamps (NULL unless bvg_debug_* is running)
 };
 
 // ---- Philox4x32-10 + Box-Muller: the RNG specification of DESIGN.md section 5 ----------------
@@ -173,8 +177,7 @@ int launch_lik_tc(bvg_fit *f, bool backward);
 bool tc_available();                                         // false until the tcgen05 kernel is linked in
 int tc_setup(bvg_fit *f);                                    // build TMA descriptors etc.
 void tc_destroy(bvg_fit *f);
-int launch_gene(bvg_fit *f, int mode, int jacobian);         // per-gene backward (+ update)
-int launch_finish(bvg_fit *f, int mode, int jacobian, int propto);  // cross-gene reduce + shared params
+int launch_gene_finish(bvg_fit *f, int mode, int jacobian, int propto);  // per-gene backward (+ update) + cross-gene finish
 int comm_allreduce(bvg_fit *f, double *buf, int n);          // comm.cu
 enum { MODE_GRAD_OUT = 0, MODE_ADVI_UPDATE = 1, MODE_ELBO_DRAW = 2, MODE_LP_ONLY = 3 };
 enum { PREP_NONE = 0, PREP_GRAD = 1, PREP_ELBO = 2 };

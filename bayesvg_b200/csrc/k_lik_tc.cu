@@ -1,5 +1,5 @@
 // k_lik_tc.cu -- the fused likelihood kernel for sm_100a: TMA-fed tcgen05 (TF32, 3-term split)
-// contractions with TMEM accumulators, one pass over Y per evaluation.
+// contractions with TMEM accumulators AND TMEM-resident A operands, one pass over Y per evaluation.
 //
 // Per CTA: one tile of 128 genes (= the 128 TMEM lanes) x one contiguous range of spots, walked
 // in chunks of 32 spots (one 128-byte swizzle row of fp32).  For every chunk
@@ -7,39 +7,53 @@
 //                                                                                       inst/approxGP.stan:33 and :48 of the reference)
 //   epilogue (8 warps, thread = gene row x 16 spots): f <- TMEM, y <- smem (the TMA-written Y tile),
 //         r = y - f (gaussian) | y - (y+phi) sigmoid(f - log phi) (nb), SSE / log-lik partials in
-//         registers, r written BACK IN PLACE over the Y tile (tf32 hi part) + a second tile (lo part)
+//         registers, r -> TMEM (tf32 hi and lo parts) with tcgen05.st
 //   MMA2  D2[128 genes x 32]       += R[128 x 32 spots] . Phi'^T_chunk[32 x 32 spots]^T (backward: Phi^T r and R_g = 1^T r)
-// D2 stays in TMEM for the whole spot range and is read once at the end.  All operands are K-major,
-// 128B-swizzled, written by TMA (or, for R, by the epilogue in the same swizzled layout).
+// Both 128-row operands (the coefficient rows C' and the residuals R) live in TENSOR MEMORY (A-from-
+// TMEM form of tcgen05.mma): shared memory only carries what TMA brings in (Y tile + four 4 KB basis
+// tiles per chunk) and is read once by the epilogue (Y) and once per term by the tensor core (basis).
+// With both A operands in shared memory the kernel was shared-memory-bandwidth bound (~200 KB of
+// smem traffic per 16 KB of Y; profiles/README.md, "v1").  D2 stays in TMEM for the whole spot range.
 // "3xTF32": every product is evaluated as hi*hi + lo*hi + hi*lo with hi = rna_tf32(x), lo = x - hi, so
 // the tensor-core result carries ~2^-21 relative error instead of TF32's 2^-11.
 //
-// Warp roles (320 threads, 1 CTA/SM): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
-// warps 2..9 = epilogue (two warps per TMEM lane quarter, 16 columns each).
-// Pipelines: smem stage full/empty (3 stages), D1 full/empty (2 TMEM buffers), residual-ready.
+// Warp roles (352 threads, 1 CTA/SM): warp 0 = TMA producer, warp 1 = TMEM owner + forward-MMA issuer,
+// warp 2 = backward-MMA issuer (two issue streams: the MMAs are small, so instruction issue, not the
+// tensor pipe, is the scarce resource), warps 3..10 = epilogue (two warps per TMEM lane quarter, 16
+// columns each).  MMA warps stay convergent and issue from one elected lane (elect.sync).
+// Pipelines: smem stage full/empty (6 stages), D1 full/empty (2 TMEM buffers), R ready/free (2).
 #include <cuda.h>
 
 #include "bvg_internal.cuh"
 
-#define TC_THREADS 320
-#define TC_STAGES 3
+#define TC_THREADS 352
+#define TC_STAGES 6
 #define TC_CHUNK 32   // spots per chunk
 #define TC_KW 32      // padded operand width (k+1 -> 32 floats = one 128B swizzle row)
 #define TILE_A_BYTES (BVG_GENE_TILE * 128)  // 16 KB: 128 rows x 128 B
 #define TILE_B_BYTES (32 * 128)             // 4 KB: 32 rows x 128 B
-#define STAGE_BYTES (2 * TILE_A_BYTES + 4 * TILE_B_BYTES)
-#define TC_SMEM_BYTES (2 * TILE_A_BYTES + TC_STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/)
+#define STAGE_BYTES (TILE_A_BYTES + 4 * TILE_B_BYTES)
+#define TC_SMEM_BYTES (TC_STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/)
+// TMEM column map (512 allocated)
+#define TM_CHI 0
+#define TM_CLO 32
+#define TM_D1 64     // + 32 * buf
+#define TM_R 128     // + 64 * buf : hi at +0, lo at +32
+#define TM_D2 256
+#define TM_COLS 512
 
 struct TcArgs {
   float *Ppart, *Spart;
+  const float *CH, *CL;  // [Gpad][32] tf32 hi / lo coefficient rows written by k_prep
   int64_t M, G, Gpad;
   int KP, cps, nchunks;
   const double *zeta;
   int64_t tail_idx;
+  long long *trace;  // optional [chunk][8] clock64 stamps of CTA (0,0) (diagnostics)
 };
 
 struct TcState {
-  CUtensorMap tmY, tmPhiH, tmPhiL, tmPhiTH, tmPhiTL, tmCH, tmCL;
+  CUtensorMap tmY, tmPhiH, tmPhiL, tmPhiTH, tmPhiTL;
   float *PhiH, *PhiL, *PhiTH, *PhiTL;
 };
 
@@ -81,13 +95,13 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-// D[tmem] (+)= A[smem] . B[smem]^T, kind::tf32, M = 128, N = 32, K = 8
-__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+// D[tmem] (+)= A[tmem] . B[smem]^T, kind::tf32, M = 128, N = 32, K = 8 (A: 128 lanes x 8 columns)
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc)
       : "memory");
 }
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start >> 4,
@@ -110,6 +124,22 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float *v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+      ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+        "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])),
+        "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])),
+        "r"(__float_as_uint(v[11])), "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])),
+        "r"(__float_as_uint(v[15]))
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t p;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(p));
+  return p != 0;
+}
 __device__ __forceinline__ float tf32_rna(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -120,29 +150,23 @@ __device__ __forceinline__ float4 lds128(uint32_t a) {
   asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
   return v;
 }
-__device__ __forceinline__ void sts128(uint32_t a, float4 v) {
-  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
 
 // ------------------------------------------------------------------------------------------------
 template <int LIK, bool BWD>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_lik_tc(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmPhiH,
          const __grid_constant__ CUtensorMap tmPhiL, const __grid_constant__ CUtensorMap tmPhiTH,
-         const __grid_constant__ CUtensorMap tmPhiTL, const __grid_constant__ CUtensorMap tmCH,
-         const __grid_constant__ CUtensorMap tmCL, TcArgs a) {
+         const __grid_constant__ CUtensorMap tmPhiTL, TcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024 B alignment
-  const uint32_t sCH = base, sCL = base + TILE_A_BYTES, sStage0 = base + 2 * TILE_A_BYTES;
-  const uint32_t sBar = sStage0 + TC_STAGES * STAGE_BYTES;
+  const uint32_t sBar = base + TC_STAGES * STAGE_BYTES;
   // barrier map (8 B each)
-  const uint32_t bFull = sBar, bEmpty = sBar + 8 * TC_STAGES, bRes = sBar + 16 * TC_STAGES;
-  const uint32_t bD1Full = sBar + 24 * TC_STAGES, bD1Empty = bD1Full + 16, bCFull = bD1Empty + 16, bD2Full = bCFull + 8;
-  const uint32_t sTmemPtr = bD2Full + 8;
+  const uint32_t bFull = sBar, bEmpty = bFull + 8 * TC_STAGES;
+  const uint32_t bD1Full = bEmpty + 8 * TC_STAGES, bD1Empty = bD1Full + 16, bRFull = bD1Empty + 16, bRFree = bRFull + 16;
+  const uint32_t bCFull = bRFree + 16, bD2Full = bCFull + 8, sTmemPtr = bD2Full + 8;
   __shared__ float s_half[2][BVG_GENE_TILE];
-  auto stY = [&](int s) { return sStage0 + s * STAGE_BYTES; };
-  auto stL = [&](int s) { return sStage0 + s * STAGE_BYTES + TILE_A_BYTES; };
-  auto stPh = [&](int s, int w) { return sStage0 + s * STAGE_BYTES + 2 * TILE_A_BYTES + w * TILE_B_BYTES; };  // w: 0 PhiH 1 PhiL 2 PhiTH 3 PhiTL
+  auto stY = [&](int s) { return base + s * STAGE_BYTES; };
+  auto stPh = [&](int s, int w) { return base + s * STAGE_BYTES + TILE_A_BYTES + w * TILE_B_BYTES; };  // w: 0 PhiH 1 PhiL 2 PhiTH 3 PhiTL
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile = blockIdx.x, split = blockIdx.y;
@@ -156,15 +180,19 @@ k_lik_tc(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtens
     for (int s = 0; s < TC_STAGES; ++s) {
       mbar_init(bFull + 8 * s, 1);
       mbar_init(bEmpty + 8 * s, BWD ? 1 : NEPI);
-      mbar_init(bRes + 8 * s, NEPI);
     }
-    for (int b = 0; b < 2; ++b) { mbar_init(bD1Full + 8 * b, 1); mbar_init(bD1Empty + 8 * b, NEPI); }
-    mbar_init(bCFull, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bD1Full + 8 * b, 1);
+      mbar_init(bD1Empty + 8 * b, NEPI);
+      mbar_init(bRFull + 8 * b, NEPI);
+      mbar_init(bRFree + 8 * b, 1);
+    }
+    mbar_init(bCFull, NEPI);
     mbar_init(bD2Full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {  // TMEM: 128 columns (2 x 32 for D1, 32 for D2; power of two)
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sTmemPtr), "r"(128u) : "memory");
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sTmemPtr), "r"((uint32_t)TM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -175,10 +203,7 @@ k_lik_tc(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtens
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0 && n > 0) {
-      mbar_expect_tx(bCFull, 2 * TILE_A_BYTES);
-      tma_load_2d(sCH, &tmCH, bCFull, 0, tile * BVG_GENE_TILE);
-      tma_load_2d(sCL, &tmCL, bCFull, 0, tile * BVG_GENE_TILE);
+    if (lane == 0) {
       for (int c = 0; c < n; ++c) {
         const int s = c % TC_STAGES;
         if (c >= TC_STAGES) mbar_wait(bEmpty + 8 * s, ((c / TC_STAGES) - 1) & 1);
@@ -194,70 +219,103 @@ k_lik_tc(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtens
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0 && n > 0) {
-      constexpr uint32_t idesc = make_idesc(128, 32);
-      const uint32_t d2 = tmem + 64;
-      auto mma1 = [&](int c) {
-        const int s = c % TC_STAGES, b = c & 1;
-        mbar_wait(bFull + 8 * s, (c / TC_STAGES) & 1);
-        if (c >= 2) mbar_wait(bD1Empty + 8 * b, ((c >> 1) - 1) & 1);
-        tc_fence_after();
-        const uint32_t d1 = tmem + 32 * b;
-        const uint32_t A[3] = {sCH, sCL, sCH}, B[3] = {stPh(s, 0), stPh(s, 0), stPh(s, 1)};
+    // ===================== forward MMA issuer (whole warp convergent, one elected lane issues) =====
+    constexpr uint32_t idesc = make_idesc(128, 32);
+    const bool tr = a.trace && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0;
+    if (n > 0) mbar_wait(bCFull, 0);
+    for (int c = 0; c < n; ++c) {
+      const int s = c % TC_STAGES, b = c & 1;
+      if (tr) a.trace[c * 8 + 0] = clock64();
+      mbar_wait(bFull + 8 * s, (c / TC_STAGES) & 1);
+      if (c >= 2) mbar_wait(bD1Empty + 8 * b, ((c >> 1) - 1) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t d1 = tmem + TM_D1 + 32 * b;
+        const uint64_t bh = make_desc(stPh(s, 0)), bl = make_desc(stPh(s, 1));
 #pragma unroll
-        for (int t = 0; t < 3; ++t)
+        for (int kk = 0; kk < 4; ++kk) tc_mma_tf32_ts(d1, tmem + TM_CHI + 8 * kk, bh + 2 * kk, idesc, kk ? 1u : 0u);
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk)
-            tc_mma_tf32(d1, make_desc(A[t] + 32 * kk), make_desc(B[t] + 32 * kk), idesc, (t | kk) ? 1u : 0u);
+        for (int kk = 0; kk < 4; ++kk) tc_mma_tf32_ts(d1, tmem + TM_CLO + 8 * kk, bh + 2 * kk, idesc, 1u);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) tc_mma_tf32_ts(d1, tmem + TM_CHI + 8 * kk, bl + 2 * kk, idesc, 1u);
         tc_commit(bD1Full + 8 * b);
-      };
-      auto mma2 = [&](int c) {
-        const int s = c % TC_STAGES;
-        mbar_wait(bRes + 8 * s, (c / TC_STAGES) & 1);
-        tc_fence_after();
-        const uint32_t A[3] = {stY(s), stL(s), stY(s)}, B[3] = {stPh(s, 2), stPh(s, 2), stPh(s, 3)};
-#pragma unroll
-        for (int t = 0; t < 3; ++t)
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk)
-            tc_mma_tf32(d2, make_desc(A[t] + 32 * kk), make_desc(B[t] + 32 * kk), idesc, (c | t | kk) ? 1u : 0u);
-        tc_commit(bEmpty + 8 * s);
-      };
-      mbar_wait(bCFull, 0);
-      for (int c = 0; c < n; ++c) {
-        mma1(c);
-        if (BWD && c >= 1) mma2(c - 1);
       }
-      if (BWD) {
-        mma2(n - 1);
-        tc_commit(bD2Full);
+      __syncwarp();
+      if (tr) a.trace[c * 8 + 1] = clock64();
+    }
+  } else if (warp == 2) {
+    // ===================== backward MMA issuer =====================
+    if (BWD) {
+      constexpr uint32_t idesc = make_idesc(128, 32);
+      const uint32_t d2 = tmem + TM_D2;
+      const bool tr = a.trace && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0;
+      for (int c = 0; c < n; ++c) {
+        const int s = c % TC_STAGES, b = c & 1;
+        mbar_wait(bFull + 8 * s, (c / TC_STAGES) & 1);   // basis tiles of this stage (acquire)
+        mbar_wait(bRFull + 8 * b, (c >> 1) & 1);         // residuals published by the epilogue
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t rh = tmem + TM_R + 64 * b, rl = rh + 32;
+          const uint64_t th = make_desc(stPh(s, 2)), tl = make_desc(stPh(s, 3));
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) tc_mma_tf32_ts(d2, rh + 8 * kk, th + 2 * kk, idesc, (c | kk) ? 1u : 0u);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) tc_mma_tf32_ts(d2, rl + 8 * kk, th + 2 * kk, idesc, 1u);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) tc_mma_tf32_ts(d2, rh + 8 * kk, tl + 2 * kk, idesc, 1u);
+          tc_commit(bEmpty + 8 * s);   // smem stage free for the producer
+          tc_commit(bRFree + 8 * b);   // residual buffer free for the epilogue of chunk c + 2
+          if (c == n - 1) tc_commit(bD2Full);
+        }
+        __syncwarp();
+        if (tr) a.trace[c * 8 + 2] = clock64();
       }
     }
   } else {
     // ===================== epilogue: 8 warps =====================
-    const int e = warp - 2, q = warp & 3, h = e >> 2;  // TMEM lane quarter of this warp, column half
+    const int e = warp - 3, q = warp & 3, h = e >> 2;  // TMEM lane quarter of this warp, column half
     const int r = 32 * q + lane;                       // gene row inside the tile = TMEM lane
     const uint32_t trow = tmem + ((uint32_t)(32 * q) << 16);
+    const int64_t g = (int64_t)tile * BVG_GENE_TILE + r;
+    {  // coefficient rows -> TMEM (A operand of MMA1), once per CTA
+      float ch[16], cl[16];
+      const float4 *ph = reinterpret_cast<const float4 *>(a.CH + g * TC_KW + 16 * h);
+      const float4 *pl = reinterpret_cast<const float4 *>(a.CL + g * TC_KW + 16 * h);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 x = ph[i], y = pl[i];
+        ch[4 * i] = x.x; ch[4 * i + 1] = x.y; ch[4 * i + 2] = x.z; ch[4 * i + 3] = x.w;
+        cl[4 * i] = y.x; cl[4 * i + 1] = y.y; cl[4 * i + 2] = y.z; cl[4 * i + 3] = y.w;
+      }
+      tmem_st16(trow + TM_CHI + 16 * h, ch);
+      tmem_st16(trow + TM_CLO + 16 * h, cl);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(bCFull);
+    }
     float acc0 = 0.f, acc1 = 0.f, lt = 0.f, phi = 0.f;
     if (LIK == BVG_NB) { lt = (float)a.zeta[a.tail_idx]; phi = __expf(lt); }
+    const bool tr = a.trace && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 96;
     for (int c = 0; c < n; ++c) {
       const int s = c % TC_STAGES, b = c & 1;
       mbar_wait(bFull + 8 * s, (c / TC_STAGES) & 1);   // Y tile landed (acquire for this thread)
+      if (tr) a.trace[c * 8 + 3] = clock64();
       mbar_wait(bD1Full + 8 * b, (c >> 1) & 1);        // MMA1 of this chunk retired
       tc_fence_after();
+      if (tr) a.trace[c * 8 + 4] = clock64();
       float f[16];
-      tmem_ld16(trow + 32 * b + 16 * h, f);
+      tmem_ld16(trow + TM_D1 + 32 * b + 16 * h, f);
+      if (tr) a.trace[c * 8 + 5] = clock64();
       tc_fence_before();
       mbar_arrive(bD1Empty + 8 * b);
-      const uint32_t yrow = stY(s) + r * 128, lrow = stL(s) + r * 128;
+      const uint32_t yrow = stY(s) + r * 128;
       const int64_t spot0 = (int64_t)(c_begin + c) * TC_CHUNK + 16 * h;
+      float hi[16], lo[16];
 #pragma unroll
       for (int c4 = 0; c4 < 4; ++c4) {
         const uint32_t off = (uint32_t)(((4 * h + c4) ^ (r & 7)) << 4);  // 128B swizzle: 16B chunk index ^ (row & 7)
         const float4 y4 = lds128(yrow + off);
         const float yv[4] = {y4.x, y4.y, y4.z, y4.w};
-        float hi[4], lo[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const float ff = f[4 * c4 + i];
@@ -276,30 +334,32 @@ k_lik_tc(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtens
               acc1 += Lq;
             }
           }
-          hi[i] = tf32_rna(res);
-          lo[i] = res - hi[i];
-        }
-        if (BWD) {
-          sts128(yrow + off, make_float4(hi[0], hi[1], hi[2], hi[3]));
-          sts128(lrow + off, make_float4(lo[0], lo[1], lo[2], lo[3]));
+          hi[4 * c4 + i] = tf32_rna(res);
+          lo[4 * c4 + i] = res - hi[4 * c4 + i];
         }
       }
       if (BWD) {
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA (async proxy)
-        mbar_arrive(bRes + 8 * s);
+        if (tr) a.trace[c * 8 + 6] = clock64();
+        if (c >= 2) mbar_wait(bRFree + 8 * b, ((c >> 1) - 1) & 1);  // MMA2 of chunk c-2 has consumed this buffer
+        tc_fence_after();
+        tmem_st16(trow + TM_R + 64 * b + 16 * h, hi);
+        tmem_st16(trow + TM_R + 64 * b + 32 + 16 * h, lo);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(bRFull + 8 * b);
+        if (tr) a.trace[c * 8 + 7] = clock64();
       } else {
         mbar_arrive(bEmpty + 8 * s);
       }
     }
     // ---- drain: P' = D2 (k+1 values per gene) and the scalar partials ----
-    const int64_t g = (int64_t)tile * BVG_GENE_TILE + r;
     const int64_t row = (int64_t)split * a.Gpad + g;
     if (BWD) {
       float p[16];
       if (n > 0) {
         mbar_wait(bD2Full, 0);
         tc_fence_after();
-        tmem_ld16(trow + 64 + 16 * h, p);
+        tmem_ld16(trow + TM_D2 + 16 * h, p);
       } else {
 #pragma unroll
         for (int i = 0; i < 16; ++i) p[i] = 0.f;
@@ -319,7 +379,7 @@ k_lik_tc(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtens
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)TM_COLS) : "memory");
   }
 }
 
@@ -380,14 +440,11 @@ int tc_setup(bvg_fit *f) {
   t->PhiL = t->PhiH + (size_t)f->Mpad * TC_KW; t->PhiTH = t->PhiL + (size_t)f->Mpad * TC_KW; t->PhiTL = t->PhiTH + (size_t)f->Mpad * TC_KW;
   k_tc_stage_phi<<<148 * 2, 256, 0, f->stream>>>(f->phi64, m.M, f->Mpad, m.k, t->PhiH, t->PhiL, t->PhiTH, t->PhiTL);
   CUDA_TRY(cudaGetLastError());
-  float *CH = (float *)m.C, *CL = CH + (size_t)m.Gpad * TC_KW;  // k_prep writes the hi/lo coefficient rows here
   BVG_TRY(make_map(&t->tmY, f->Y, (uint64_t)f->ldY, (uint64_t)m.G, (uint64_t)f->ldY, BVG_GENE_TILE));
   BVG_TRY(make_map(&t->tmPhiH, t->PhiH, TC_KW, (uint64_t)f->Mpad, TC_KW, 32));
   BVG_TRY(make_map(&t->tmPhiL, t->PhiL, TC_KW, (uint64_t)f->Mpad, TC_KW, 32));
   BVG_TRY(make_map(&t->tmPhiTH, t->PhiTH, (uint64_t)f->Mpad, TC_KW, (uint64_t)f->Mpad, 32));
   BVG_TRY(make_map(&t->tmPhiTL, t->PhiTL, (uint64_t)f->Mpad, TC_KW, (uint64_t)f->Mpad, 32));
-  BVG_TRY(make_map(&t->tmCH, CH, TC_KW, (uint64_t)m.Gpad, TC_KW, BVG_GENE_TILE));
-  BVG_TRY(make_map(&t->tmCL, CL, TC_KW, (uint64_t)m.Gpad, TC_KW, BVG_GENE_TILE));
   CUDA_TRY(cudaFuncSetAttribute(k_lik_tc<BVG_GAUSSIAN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(k_lik_tc<BVG_GAUSSIAN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(k_lik_tc<BVG_NB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
@@ -403,17 +460,38 @@ void tc_destroy(bvg_fit *f) {
   f->tc = nullptr;
 }
 
+static long long *g_tc_trace = nullptr;
+int launch_lik_tc(bvg_fit *f, bool bwd);
+// diagnostics: one backward launch with per-chunk clock64 stamps of CTA (0,0): [chunk][8] =
+// mma: begin, after mma1 issue, after mma2 issue | epilogue warp 2 lane 0: Y ready, D1 ready, after tcgen05.ld,
+// after math, after R published
+extern "C" int bvg_debug_tc_trace(bvg_fit *f, long long *out, int nchunk_cap) {
+  if (!f || !f->tc || !out) { bvg_set_error("tcgen05 engine not active"); return BVG_ERR_STATE; }
+  CUDA_TRY(cudaSetDevice(f->cfg.device));
+  long long *d = nullptr;
+  CUDA_TRY(cudaMalloc(&d, sizeof(long long) * 8 * nchunk_cap));
+  CUDA_TRY(cudaMemsetAsync(d, 0, sizeof(long long) * 8 * nchunk_cap, f->stream));
+  g_tc_trace = d;
+  int rc = launch_lik_tc(f, true);
+  g_tc_trace = nullptr;
+  if (rc == BVG_OK && (cudaMemcpyAsync(out, d, sizeof(long long) * 8 * nchunk_cap, cudaMemcpyDeviceToHost, f->stream) != cudaSuccess || cudaStreamSynchronize(f->stream) != cudaSuccess)) rc = BVG_ERR_CUDA;
+  cudaFree(d);
+  return rc;
+}
+
 int launch_lik_tc(bvg_fit *f, bool bwd) {
   const DevModel &m = f->m;
   TcState *t = (TcState *)f->tc;
   TcArgs a;
   a.Ppart = (float *)m.Ppart; a.Spart = (float *)m.Spart;
+  a.CH = (const float *)m.C; a.CL = a.CH + (size_t)m.Gpad * TC_KW;  // k_prep writes the hi/lo coefficient rows here
   a.M = m.M; a.G = m.G; a.Gpad = m.Gpad; a.KP = m.KP;
   a.nchunks = (int)((m.M + TC_CHUNK - 1) / TC_CHUNK);
   a.cps = (a.nchunks + m.nsplit - 1) / m.nsplit;
   a.zeta = m.zeta; a.tail_idx = m.L.tail;
+  a.trace = g_tc_trace;
   dim3 grid((unsigned)(m.Gpad / BVG_GENE_TILE), (unsigned)m.nsplit);
-#define TCL(LIK, BWD) k_lik_tc<LIK, BWD><<<grid, TC_THREADS, TC_SMEM_BYTES, f->stream>>>(t->tmY, t->tmPhiH, t->tmPhiL, t->tmPhiTH, t->tmPhiTL, t->tmCH, t->tmCL, a)
+#define TCL(LIK, BWD) k_lik_tc<LIK, BWD><<<grid, TC_THREADS, TC_SMEM_BYTES, f->stream>>>(t->tmY, t->tmPhiH, t->tmPhiL, t->tmPhiTH, t->tmPhiTL, a)
   if (m.lik == BVG_GAUSSIAN) { if (bwd) TCL(BVG_GAUSSIAN, true); else TCL(BVG_GAUSSIAN, false); }
   else { if (bwd) TCL(BVG_NB, true); else TCL(BVG_NB, false); }
 #undef TCL

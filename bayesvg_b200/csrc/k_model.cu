@@ -10,182 +10,95 @@
 #include "bvg_internal.cuh"
 
 // ------------------------------------------------------------------------------------------------
+// k_prep: ONE thread per parameter.  A block owns `gpb` genes ((k+2) parameters each) and, redundantly,
+// the 2k+5 gene-shared parameters, so every normal draw of the block is generated in one parallel
+// phase (Philox + Box-Muller in fp64 is a ~1000-cycle dependent chain; the first version chained
+// three of them per block).
 template <typename T>
-__global__ void __launch_bounds__(256) k_prep(DevModel m, int mode, int tc) {
-  extern __shared__ double sh[];  // [2k+5] shared zeta | [k] sigma_alpha
-  const int k = m.k, nsh = 2 * k + 5;
+__global__ void __launch_bounds__(256) k_prep(DevModel m, int mode, int tc, int gpb) {
+  extern __shared__ double sh[];  // [2k+5] shared zeta | [k] sigma_alpha | [gpb][k+2] gene zeta | [gpb] A_g
+  const int k = m.k, nsh = 2 * k + 5, npg = k + 2, tid = threadIdx.x;
+  double *sal = sh + nsh, *zg = sal + k, *Ag = zg + gpb * npg;
   const uint32_t stream = mode == PREP_GRAD ? STREAM_GRAD : STREAM_ELBO;
   const uint32_t t = mode == PREP_GRAD ? m.ctl->t_grad : m.ctl->t_elbo;
-  for (int i = threadIdx.x; i < nsh; i += blockDim.x) {
-    const int64_t li = shared_index(m.L, k, i);
+  // ---- phase 1: every parameter's zeta ----
+  const int t2 = tid - nsh, gl = t2 >= 0 ? t2 / npg : -1, j = t2 >= 0 ? t2 - gl * npg : 0;
+  const int64_t g = (int64_t)blockIdx.x * gpb + gl;
+  const bool is_sh = tid < nsh, is_gene = gl >= 0 && gl < gpb && g < m.G;
+  if (is_sh || is_gene) {
+    int64_t li, gi;
+    if (is_sh) { li = shared_index(m.L, k, tid); gi = shared_index(m.LG, k, tid); }
+    else {
+      const int64_t gg = m.gene_offset + g;
+      if (j < k) { li = m.L.z_alpha + g * k + j; gi = m.LG.z_alpha + gg * k + j; }
+      else if (j == k) { li = m.L.z_beta0 + g; gi = m.LG.z_beta0 + gg; }
+      else { li = m.L.amp + g; gi = m.LG.amp + gg; }
+    }
     double z;
     if (mode != PREP_NONE) {
-      z = m.mu[li] + exp(m.omega[li]) * bvg_normal(m.seed, stream, t, (uint64_t)shared_index(m.LG, k, i));
-      if (blockIdx.x == 0) m.zeta[li] = z;
+      z = m.mu[li] + exp(m.omega[li]) * bvg_normal(m.seed, stream, t, (uint64_t)gi);
+      if (is_gene || blockIdx.x == 0) m.zeta[li] = z;
     } else {
       z = m.zeta[li];
     }
-    sh[i] = z;
+    if (is_sh) sh[tid] = z; else zg[gl * npg + j] = z;
   }
   __syncthreads();
-  double *sal = sh + nsh;
-  for (int j = threadIdx.x; j < k; j += blockDim.x) sal[j] = exp(sh[5 + k + j]);
+  // ---- phase 2: the exponentials (sigma_alpha, sigma_beta0 in place, A_g = amplitude^2) ----
+  // (also published for k_gene / finish_body: shx = [sigma_beta0, sigma_amplitude, tail, sigma_alpha[k]], Aexp[g])
+  if (tid < k) { const double e = exp(sh[5 + k + tid]); sal[tid] = e; if (blockIdx.x == 0) m.shx[3 + tid] = e; }
+  else if (tid == k) { const double e = exp(sh[1]); sh[1] = e; if (blockIdx.x == 0) m.shx[0] = e; }
+  else if (tid > k && tid <= k + gpb) {
+    const int q = tid - k - 1;
+    const double e = exp(2.0 * zg[q * npg + k + 1]);  // approxGP.stan:27
+    Ag[q] = e;
+    if ((int64_t)blockIdx.x * gpb + q < m.G) m.Aexp[(int64_t)blockIdx.x * gpb + q] = e;
+  } else if (blockIdx.x == 0 && tid == k + gpb + 1) m.shx[1] = exp(sh[3]);
+  else if (blockIdx.x == 0 && tid == k + gpb + 2) m.shx[2] = exp(sh[4]);
   __syncthreads();
-  const double mb = sh[0], sb = exp(sh[1]);
-  const int lane = threadIdx.x & 31;
-  const int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (g >= m.G) return;
-  const int64_t gg = m.gene_offset + g;
-  // lane 0: z_beta0[g], lane 1: log amplitude[g]
-  double v = 0;
-  if (lane < 2) {
-    const int64_t li = lane == 0 ? m.L.z_beta0 + g : m.L.amp + g;
-    if (mode != PREP_NONE) {
-      const int64_t gi = lane == 0 ? m.LG.z_beta0 + gg : m.LG.amp + gg;
-      v = m.mu[li] + exp(m.omega[li]) * bvg_normal(m.seed, stream, t, (uint64_t)gi);
-      m.zeta[li] = v;
-    } else {
-      v = m.zeta[li];
-    }
-  }
-  const double zb = __shfl_sync(0xffffffffu, v, 0), u = __shfl_sync(0xffffffffu, v, 1);
-  const double A = exp(2.0 * u);        // amplitude_sq (approxGP.stan:27)
-  const double beta = mb + sb * zb;     // beta0        (approxGP.stan:26)
-  // tc != 0: rows of width 32, split into tf32 hi / lo parts for the 3xTF32 tensor-core contraction
-  const int cw = tc ? 32 : m.KP;
-  T *Crow = (T *)m.C + g * cw, *Clo = (T *)m.C + (m.Gpad + g) * cw;
-  auto put = [&](int j, double v) {
-    if (!tc) { Crow[j] = (T)v; return; }
-    const float x = (float)v;
-    uint32_t hb;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(x));
-    const float hi = __uint_as_float(hb);
-    Crow[j] = (T)hi;
-    Clo[j] = (T)(x - hi);
-  };
-  for (int j = lane; j < k; j += 32) {
-    const int64_t li = m.L.z_alpha + g * k + j;
-    double z;
-    if (mode != PREP_NONE) {
-      z = m.mu[li] + exp(m.omega[li]) * bvg_normal(m.seed, stream, t, (uint64_t)(m.LG.z_alpha + gg * k + j));
-      m.zeta[li] = z;
-    } else {
-      z = m.zeta[li];
-    }
-    put(j, A * (sh[5 + j] + sal[j] * z));  // A_g * alpha_t[j,g] (approxGP.stan:32)
-  }
-  if (lane == 0) put(k, beta);
+  // ---- phase 3: coefficient rows c'_g = (A_g alpha_t[,g], beta0_g) ----
+  if (!is_gene || j == k + 1) return;
+  const double v = j < k ? Ag[gl] * (sh[5 + j] + sal[j] * zg[gl * npg + j])  // A_g * alpha_t[j,g] (approxGP.stan:32)
+                         : sh[0] + sh[1] * zg[gl * npg + k];                  // beta0 (approxGP.stan:26)
+  if (!tc) { ((T *)m.C)[g * m.KP + j] = (T)v; return; }
+  // tcgen05 engine: rows of width 32 split into tf32 hi / lo parts for the 3xTF32 contraction
+  const float x = (float)v;
+  uint32_t hb;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(x));
+  const float hi = __uint_as_float(hb);
+  ((float *)m.C)[g * 32 + j] = hi;
+  ((float *)m.C)[(m.Gpad + g) * 32 + j] = x - hi;
 }
 
 int launch_prep(bvg_fit *f, int mode) {
-  const int wpb = 8;
-  const int grid = (int)((f->m.G + wpb - 1) / wpb);
-  const size_t sh = sizeof(double) * (3 * f->m.k + 5);
-  if (f->cfg.precision == BVG_PREC_FP64) k_prep<double><<<grid, wpb * 32, sh, f->stream>>>(f->m, mode, 0);
-  else k_prep<float><<<grid, wpb * 32, sh, f->stream>>>(f->m, mode, f->engine == BVG_ENGINE_TCGEN05);
+  const int k = f->m.k;
+  const int gpb = (256 - (2 * k + 5)) / (k + 2);
+  const int grid = (int)((f->m.G + gpb - 1) / gpb);
+  const size_t sh = sizeof(double) * (3 * k + 5 + gpb * (k + 3));
+  if (f->cfg.precision == BVG_PREC_FP64) k_prep<double><<<grid, 256, sh, f->stream>>>(f->m, mode, 0, gpb);
+  else k_prep<float><<<grid, 256, sh, f->stream>>>(f->m, mode, f->engine == BVG_ENGINE_TCGEN05, gpb);
   f->st.kernel_launches++;
   CUDA_TRY(cudaGetLastError());
   return BVG_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
-// mean-field ADVI update of one parameter: grad_mu = g, grad_omega = g*eps*exp(omega)+1,
-// s <- (it==1 ? g^2 : 0.9 s + 0.1 g^2),  x += eta/sqrt(it) * grad / (1 + sqrt(s))
-__device__ inline void advi_update(const DevModel &m, int64_t li, int64_t gi, double gv, bool fin, uint32_t t,
-                                   int it, double es) {
-  const double om = m.omega[li];
-  const double eps = bvg_normal(m.seed, STREAM_GRAD, t, (uint64_t)gi);
+// mean-field ADVI update of one parameter: grad_mu = g, grad_omega = g*eps*exp(omega)+1
+// = g*(zeta - mu) + 1 (zeta = mu + exp(omega)*eps is the stored draw, so neither eps nor exp(omega) is
+// recomputed),  s <- (it==1 ? g^2 : 0.9 s + 0.1 g^2),  x += eta/sqrt(it) * grad / (1 + sqrt(s))
+__device__ inline void advi_update(const DevModel &m, int64_t li, double gv, bool fin, int it, double es) {
+  const double mu = m.mu[li];
   const double gm = fin ? gv : 0.0;
-  const double go = fin ? gv * eps * exp(om) + 1.0 : 0.0;
+  const double go = fin ? gv * (m.zeta[li] - mu) + 1.0 : 0.0;
   double hm = m.hist[li], ho = m.hist[m.L.D + li];
   if (it == 1) { hm += gm * gm; ho += go * go; }
   else { hm = 0.9 * hm + 0.1 * gm * gm; ho = 0.9 * ho + 0.1 * go * go; }
   m.hist[li] = hm;
   m.hist[m.L.D + li] = ho;
-  m.mu[li] += es * gm / (1.0 + sqrt(hm));
-  m.omega[li] = om + es * go / (1.0 + sqrt(ho));
+  m.mu[li] = mu + es * gm / (1.0 + sqrt(hm));
+  m.omega[li] += es * go / (1.0 + sqrt(ho));
 }
 
-template <typename T>
-__global__ void __launch_bounds__(256) k_gene(DevModel m, int mode, int jac) {
-  extern __shared__ double sm[];  // [nwarps][NS]
-  const int k = m.k, KP = m.KP, NS = bvg_ns(k);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  const Layout &L = m.L;
-  const double *zt = m.zeta;
-  const double sb = exp(zt[L.sigma_beta0]), ma = zt[L.mu_amp], sa = exp(zt[L.sigma_amp]);
-  const double tail = exp(zt[L.tail]);
-  const double inv_s2 = m.lik == BVG_GAUSSIAN ? 1.0 / (tail * tail) : 1.0;
-  const double mual = lane < k ? zt[L.mu_alpha + lane] : 0.0;
-  const double sal = lane < k ? exp(zt[L.sigma_alpha + lane]) : 0.0;
-  const uint32_t t = m.ctl->t_grad;
-  const int it = m.ctl->it;
-  const double es = m.ctl->eta / sqrt((double)it);
-  double aR = 0, aRz = 0, aDu = 0, aDu2 = 0, aS0 = 0, aS1 = 0, aZ2 = 0, aU = 0, aAP = 0, aAPz = 0;
-  const T *Pp = (const T *)m.Ppart, *Sp = (const T *)m.Spart;
-  for (int64_t g = (int64_t)blockIdx.x * nw + warp; g < m.G; g += (int64_t)gridDim.x * nw) {
-    double Pj = 0, s0 = 0;
-    for (int sp = 0; sp < m.nsplit; ++sp) {  // fixed order -> deterministic
-      const int64_t row = (int64_t)sp * m.Gpad + g;
-      if (lane < KP) Pj += (double)Pp[row * KP + lane];
-      if (lane < 2) s0 += (double)Sp[row * 2 + lane];
-    }
-    const double s1 = __shfl_sync(0xffffffffu, s0, 1);
-    s0 = __shfl_sync(0xffffffffu, s0, 0);
-    Pj *= inv_s2;
-    const double R = __shfl_sync(0xffffffffu, Pj, k);  // ones column of Phi' -> R_g = sum_s r_sg
-    const double zj = lane < k ? zt[L.z_alpha + g * k + lane] : 0.0;
-    const double zb = zt[L.z_beta0 + g], u = zt[L.amp + g];
-    const double A = exp(2.0 * u), alpha = mual + sal * zj;
-    const double aP = warp_sum(lane < k ? alpha * Pj : 0.0);
-    const double z2 = warp_sum(zj * zj) + zb * zb;
-    const double AP = lane < k ? A * Pj : 0.0;
-    const double du = u - ma;
-    aAP += AP; aAPz += AP * zj;
-    aR += R; aRz += R * zb; aDu += du; aDu2 += du * du; aS0 += s0; aS1 += s1; aZ2 += z2; aU += u;
-    if (mode == MODE_GRAD_OUT || mode == MODE_ADVI_UPDATE) {
-      const int64_t gg = m.gene_offset + g;
-      double gv = 0;
-      int64_t li = 0, gi = 0;
-      bool has = true;
-      if (lane < k) { gv = sal * AP - zj; li = L.z_alpha + g * k + lane; gi = m.LG.z_alpha + gg * k + lane; }
-      else if (lane == k) { gv = sb * R - zb; li = L.z_beta0 + g; gi = m.LG.z_beta0 + gg; }
-      else if (lane == k + 1) { gv = 2.0 * A * aP - du / (sa * sa) - (jac ? 0.0 : 1.0); li = L.amp + g; gi = m.LG.amp + gg; }
-      else has = false;
-      if (mode == MODE_GRAD_OUT) {
-        if (has) m.grad[li] = gv;
-      } else {
-        const bool fin = __all_sync(0xffffffffu, has ? isfinite(gv) : true);
-        if (!fin && lane == 0) atomicAdd(&m.ctl->bad, 1);
-        if (has) advi_update(m, li, gi, gv, fin, t, it, es);
-      }
-    }
-  }
-  double *row = sm + warp * NS;
-  if (lane == 0) {
-    row[S_R] = aR; row[S_RZ] = aRz; row[S_DU] = aDu; row[S_DU2] = aDu2; row[S_SSE] = aS0; row[S_Z2] = aZ2;
-    row[S_U] = aU; row[S_L] = aS1; row[S_LG] = 0; row[S_DG] = 0;
-  }
-  if (lane < k) { row[S_AP + lane] = aAP; row[S_AP + k + lane] = aAPz; }
-  __syncthreads();
-  for (int c = threadIdx.x; c < NS; c += blockDim.x) {
-    double s = 0;
-    for (int w = 0; w < nw; ++w) s += sm[w * NS + c];
-    m.blk[(int64_t)blockIdx.x * NS + c] = s;
-  }
-}
-
-int launch_gene(bvg_fit *f, int mode, int jac) {
-  const int wpb = 8;
-  const size_t sh = sizeof(double) * wpb * bvg_ns(f->m.k);
-  if (f->cfg.precision == BVG_PREC_FP64) k_gene<double><<<f->m.nblk_gene, wpb * 32, sh, f->stream>>>(f->m, mode, jac);
-  else k_gene<float><<<f->m.nblk_gene, wpb * 32, sh, f->stream>>>(f->m, mode, jac);
-  f->st.kernel_launches++;
-  CUDA_TRY(cudaGetLastError());
-  return BVG_OK;
-}
-
-// ------------------------------------------------------------------------------------------------
 __device__ inline double dev_digamma(double x) {
   double r = 0.0;
   while (x < 10.0) { r -= 1.0 / x; x += 1.0; }
@@ -194,24 +107,59 @@ __device__ inline double dev_digamma(double x) {
   return r + log(x) - 0.5 / x + t;
 }
 
-// phase bit 0: reduce block partials (+ nb histogram terms) into tot[]; bit 1: finish.
-// Between the two phases a multi-GPU fit all-reduces tot[] (comm.cu).
-__global__ void __launch_bounds__(256) k_finish(DevModel m, int mode, int jac, int propto, int phase) {
-  __shared__ double red[2][8];
+__device__ inline long long gtime() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define DBG(i) do { if (m.dbg && threadIdx.x == 0) m.dbg[i] = gtime(); } while (0)
+#define DBG0(i) do { if (m.dbg && threadIdx.x == 0 && blockIdx.x == 0) m.dbg[i] = gtime(); } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// finish_body (one CTA, >= 128 threads).  phase bit 0: fixed-order reduction of the per-block
+// partials (+ nb histogram terms) into tot[]; bit 1: log density, gradient / ADVI update of the 2k+5
+// gene-shared parameters, counters.  A multi-GPU fit all-reduces tot[] between the two phases.
+__device__ void finish_body(const DevModel &m, int mode, int jac, int propto, int phase) {
+  __shared__ double red[2][32];
   __shared__ double s_lp;
-  const int k = m.k, NS = bvg_ns(k), tid = threadIdx.x;
+  const int k = m.k, NS = bvg_ns(k), tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const Layout &L = m.L;
   const double *zt = m.zeta;
+  const int nwarps = blockDim.x >> 5;
   if (phase & 1) {
-    for (int c = tid; c < NS; c += blockDim.x) {
-      double s = 0;
-      for (int b = 0; b < m.nblk_gene; ++b) s += m.blk[(int64_t)b * NS + c];
-      m.tot[c] = s;
+    // every warp owns up to 4 columns and requests all their rows at once (nblk_gene <= 148 rows:
+    // 5 per lane), then sums in a fixed order and finishes with a fixed shuffle tree -> deterministic
+    {
+      double acc[4] = {0, 0, 0, 0};
+      for (int b0 = lane; b0 < m.nblk_gene; b0 += 160) {
+        double v[4][5];
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci)
+#pragma unroll
+          for (int q = 0; q < 5; ++q) {
+            const int c = warp + ci * nwarps, b = b0 + 32 * q;
+            v[ci][q] = (c < NS && b < m.nblk_gene) ? __ldcg(&m.blk[(int64_t)c * m.nblk_gene + b]) : 0.0;
+          }
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci)
+#pragma unroll
+          for (int q = 0; q < 5; ++q) acc[ci] += v[ci][q];
+      }
+#pragma unroll
+      for (int ci = 0; ci < 4; ++ci) {
+        const int c = warp + ci * nwarps;
+        const double t = warp_sum(acc[ci]);
+        if (lane == 0 && c < NS) m.tot[c] = t;
+      }
+      for (int c = warp + 4 * nwarps; c < NS; c += nwarps) {  // only when NS > 4 * nwarps
+        double s2 = 0;
+        for (int b = lane; b < m.nblk_gene; b += 32) s2 += __ldcg(&m.blk[(int64_t)c * m.nblk_gene + b]);
+        s2 = warp_sum(s2);
+        if (lane == 0) m.tot[c] = s2;
+      }
     }
+    __syncthreads();
+    DBG(5);
     if (m.lik == BVG_NB) {
       // sum_sg lgamma(y+phi) - lgamma(phi) and its digamma derivative depend only on (y, phi):
       // evaluate on the histogram of distinct counts
-      const double phi = exp(zt[L.tail]), lg0 = lgamma(phi), dg0 = dev_digamma(phi);
+      const double phi = m.shx[2], lg0 = lgamma(phi), dg0 = dev_digamma(phi);
       double lg = 0, dg = 0;
       for (int i = tid; i < m.nhist; i += blockDim.x) {
         const double c = m.hist_val[i], n = m.hist_cnt[i];
@@ -219,32 +167,33 @@ __global__ void __launch_bounds__(256) k_finish(DevModel m, int mode, int jac, i
         dg += n * (dev_digamma(c + phi) - dg0);
       }
       lg = warp_sum(lg); dg = warp_sum(dg);
-      if ((tid & 31) == 0) { red[0][tid >> 5] = lg; red[1][tid >> 5] = dg; }
+      if (lane == 0) { red[0][warp] = lg; red[1][warp] = dg; }
       __syncthreads();
       if (tid == 0) {
         double a = 0, b = 0;
-        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { a += red[0][w]; b += red[1][w]; }
+        for (int w = 0; w < nwarps; ++w) { a += red[0][w]; b += red[1][w]; }
         m.tot[S_LG] = a - m.lgam_y1;
         m.tot[S_DG] = b;
       }
+      __syncthreads();
     }
-    __syncthreads();
   }
   if (!(phase & 2)) return;
   const double *tot = m.tot;
-  const double mb = zt[L.mu_beta0], lsb = zt[L.sigma_beta0], sb = exp(lsb);
-  const double ma = zt[L.mu_amp], lsa = zt[L.sigma_amp], sa = exp(lsa);
-  const double lt = zt[L.tail], tl = exp(lt);
+  const double mb = zt[L.mu_beta0], lsb = zt[L.sigma_beta0], sb = m.shx[0];
+  const double ma = zt[L.mu_amp], lsa = zt[L.sigma_amp], sa = m.shx[1];
+  const double lt = zt[L.tail], tl = m.shx[2];
   const double Gt = (double)m.G_total, N = (double)m.M * Gt;
   const double j1 = jac ? 1.0 : 0.0;
-  if (tid < 32) {  // warp 0: log density
+  const int it = m.ctl->it;
+  if (warp == (blockDim.x >> 5) - 1) {  // log density (last warp, concurrently with the gradient threads below)
     double pa = 0;  // prior terms of mu_alpha, sigma_alpha + jacobian of sigma_alpha
-    for (int j = tid; j < k; j += 32) {
-      const double a = zt[L.mu_alpha + j], ls = zt[L.sigma_alpha + j], s = exp(ls);
+    for (int j = lane; j < k; j += 32) {
+      const double a = zt[L.mu_alpha + j], ls = zt[L.sigma_alpha + j], s = m.shx[3 + j];
       pa += -a * a / 8.0 - 0.5 * s * s + j1 * ls;
     }
     pa = warp_sum(pa);
-    if (tid == 0) {
+    if (lane == 0) {
       double lp;
       if (m.lik == BVG_GAUSSIAN) lp = -N * lt - 0.5 * tot[S_SSE] / (tl * tl) - 0.5 * tl * tl;
       else lp = tot[S_SSE] + tot[S_LG] - log1p(tl * tl / 4.0);
@@ -260,41 +209,37 @@ __global__ void __launch_bounds__(256) k_finish(DevModel m, int mode, int jac, i
       }
       s_lp = lp;
     }
-  }
-  __syncthreads();
-  const double lp = s_lp;
-  const uint32_t t = m.ctl->t_grad;
-  const int it = m.ctl->it;
-  if (mode == MODE_GRAD_OUT || mode == MODE_ADVI_UPDATE) {
+  } else if ((mode == MODE_GRAD_OUT || mode == MODE_ADVI_UPDATE) && tid < 2 * k + 5) {
     const double es = m.ctl->eta / sqrt((double)it);
-    for (int i = tid; i < 2 * k + 5; i += blockDim.x) {
-      double gv;
-      if (i == 0) gv = tot[S_R] - mb / 4.0;
-      else if (i == 1) gv = sb * (tot[S_RZ] - sb) + j1;
-      else if (i == 2) gv = tot[S_DU] / (sa * sa) - ma / 4.0;
-      else if (i == 3) gv = -Gt + tot[S_DU2] / (sa * sa) - sa * sa + j1;
-      else if (i == 4) {
-        if (m.lik == BVG_GAUSSIAN) gv = -N + tot[S_SSE] / (tl * tl) - tl * tl + j1;
-        else gv = tl * (tot[S_DG] - tot[S_L] - tot[S_R] / tl) - 0.5 * tl * tl / (1.0 + tl * tl / 4.0) + j1;
-      } else if (i < 5 + k) gv = tot[S_AP + (i - 5)] - zt[L.mu_alpha + (i - 5)] / 4.0;
-      else {
-        const int j = i - 5 - k;
-        const double s = exp(zt[L.sigma_alpha + j]);
-        gv = s * (tot[S_AP + k + j] - s) + j1;
-      }
-      const int64_t li = shared_index(L, k, i);
-      if (mode == MODE_GRAD_OUT) m.grad[li] = gv;
-      else {
-        const bool fin = isfinite(gv);
-        if (!fin) atomicAdd(&m.ctl->bad, 1);
-        advi_update(m, li, shared_index(m.LG, k, i), gv, fin, t, it, es);
-      }
+    const int i = tid;
+    double gv;
+    if (i == 0) gv = tot[S_R] - mb / 4.0;
+    else if (i == 1) gv = sb * (tot[S_RZ] - sb) + j1;
+    else if (i == 2) gv = tot[S_DU] / (sa * sa) - ma / 4.0;
+    else if (i == 3) gv = -Gt + tot[S_DU2] / (sa * sa) - sa * sa + j1;
+    else if (i == 4) {
+      if (m.lik == BVG_GAUSSIAN) gv = -N + tot[S_SSE] / (tl * tl) - tl * tl + j1;
+      else gv = tl * (tot[S_DG] - tot[S_L] - tot[S_R] / tl) - 0.5 * tl * tl / (1.0 + tl * tl / 4.0) + j1;
+    } else if (i < 5 + k) gv = tot[S_AP + (i - 5)] - zt[L.mu_alpha + (i - 5)] / 4.0;
+    else {
+      const int j = i - 5 - k;
+      const double s = m.shx[3 + j];
+      gv = s * (tot[S_AP + k + j] - s) + j1;
+    }
+    const int64_t li = shared_index(L, k, i);
+    if (mode == MODE_GRAD_OUT) m.grad[li] = gv;
+    else {
+      const bool fin = isfinite(gv);
+      if (!fin) atomicAdd(&m.ctl->bad, 1);
+      advi_update(m, li, gv, fin, it, es);
     }
   }
   __syncthreads();
+  DBG(6);
   if (tid == 0) {
+    const double lp = s_lp;
     m.ctl->lp = lp;
-    if (mode == MODE_ADVI_UPDATE) { m.ctl->t_grad = t + 1; m.ctl->it = it + 1; }
+    if (mode == MODE_ADVI_UPDATE) { m.ctl->t_grad += 1; m.ctl->it = it + 1; }
     else if (mode == MODE_ELBO_DRAW) {
       if (isfinite(lp)) { m.ctl->elbo_acc += lp; m.ctl->elbo_ok += 1; }
       m.ctl->t_elbo += 1;
@@ -302,17 +247,135 @@ __global__ void __launch_bounds__(256) k_finish(DevModel m, int mode, int jac, i
   }
 }
 
-int launch_finish(bvg_fit *f, int mode, int jac, int propto) {
-  if (f->comm) {
-    k_finish<<<1, 256, 0, f->stream>>>(f->m, mode, jac, propto, 1);
+__global__ void __launch_bounds__(512) k_finish(DevModel m, int mode, int jac, int propto, int phase) {
+  finish_body(m, mode, jac, propto, phase);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_gene: one warp per gene (lane j < k: z_alpha_t[j,g]; lane k: z_beta0[g]; lane k+1: amplitude[g]).
+// Everything a gene needs is requested up front (8 split partials in flight per lane, the lane's own
+// zeta / mu / omega / step-size history) so the warp pays ~2 L2 round trips, not one per load.
+// fuse != 0 (single-GPU): the last CTA to retire also runs finish_body, saving a launch per evaluation.
+template <typename T>
+__global__ void __launch_bounds__(512) k_gene(DevModel m, int mode, int jac, int propto, int fuse) {
+  extern __shared__ double sm[];  // [nwarps][NS]
+  __shared__ int s_last;
+  const int k = m.k, KP = m.KP, NS = bvg_ns(k);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const Layout &L = m.L;
+  const double *zt = m.zeta;
+  const double sb = m.shx[0], ma = zt[L.mu_amp], sa = m.shx[1];  // exponentials precomputed by k_prep
+  const double tail = m.shx[2];
+  const double inv_s2 = m.lik == BVG_GAUSSIAN ? 1.0 / (tail * tail) : 1.0;
+  const double mual = lane < k ? zt[L.mu_alpha + lane] : 0.0;
+  const double sal = lane < k ? m.shx[3 + lane] : 0.0;
+  const int it = m.ctl->it;
+  const double es = m.ctl->eta / sqrt((double)it);
+  const bool has = lane < k + 2, upd = mode == MODE_ADVI_UPDATE;
+  DBG0(0);
+  if (m.dbg && threadIdx.x == 0 && blockIdx.x == 0) m.dbg[1] = (long long)(es * 1e9) * 0 + gtime();
+  double aR = 0, aRz = 0, aDu = 0, aDu2 = 0, aS0 = 0, aS1 = 0, aZ2 = 0, aU = 0, aAP = 0, aAPz = 0;
+  const T *Pp = (const T *)m.Ppart, *Sp = (const T *)m.Spart;
+  for (int64_t g = (int64_t)blockIdx.x * nw + warp; g < m.G; g += (int64_t)gridDim.x * nw) {
+    const int64_t li = lane < k ? L.z_alpha + g * k + lane : (lane == k ? L.z_beta0 + g : L.amp + g);
+    const double zi = has ? zt[li] : 0.0;  // this lane's own parameter value
+    const double Aexp_g = m.Aexp[g];
+    double mu_i = 0, om_i = 0, hm = 0, ho = 0;
+    if (upd && has) { mu_i = m.mu[li]; om_i = m.omega[li]; hm = m.hist[li]; ho = m.hist[L.D + li]; }
+    double Pj = 0, s0 = 0;
+    for (int sp0 = 0; sp0 < m.nsplit; sp0 += 8) {  // fixed order -> deterministic
+      T pv[8], sv[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int64_t row = (int64_t)(sp0 + q) * m.Gpad + g;
+        const bool ok = sp0 + q < m.nsplit;
+        pv[q] = (ok && lane < KP) ? Pp[row * KP + lane] : (T)0;
+        sv[q] = (ok && lane < 2) ? Sp[row * 2 + lane] : (T)0;
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { Pj += (double)pv[q]; s0 += (double)sv[q]; }
+    }
+    const double s1 = __shfl_sync(0xffffffffu, s0, 1);
+    s0 = __shfl_sync(0xffffffffu, s0, 0);
+    Pj *= inv_s2;
+    const double R = __shfl_sync(0xffffffffu, Pj, k);  // ones column of Phi' -> R_g = sum_s r_sg
+    const double zj = lane < k ? zi : 0.0;
+    const double zb = __shfl_sync(0xffffffffu, zi, k), u = __shfl_sync(0xffffffffu, zi, k + 1);
+    const double A = Aexp_g, alpha = mual + sal * zj;
+    const double aP = warp_sum(lane < k ? alpha * Pj : 0.0);
+    const double z2 = warp_sum(zj * zj) + zb * zb;
+    const double AP = lane < k ? A * Pj : 0.0;
+    const double du = u - ma;
+    aAP += AP; aAPz += AP * zj;
+    aR += R; aRz += R * zb; aDu += du; aDu2 += du * du; aS0 += s0; aS1 += s1; aZ2 += z2; aU += u;
+    if (mode == MODE_GRAD_OUT || upd) {
+      double gv = 0;
+      if (lane < k) gv = sal * AP - zj;
+      else if (lane == k) gv = sb * R - zb;
+      else if (lane == k + 1) gv = 2.0 * A * aP - du / (sa * sa) - (jac ? 0.0 : 1.0);
+      if (!upd) {
+        if (has) m.grad[li] = gv;
+      } else {
+        // mean-field ADVI update (see advi_update); a gene whose gradient is not finite keeps its parameters
+        const bool fin = __all_sync(0xffffffffu, has ? isfinite(gv) : true);
+        if (!fin && lane == 0) atomicAdd(&m.ctl->bad, 1);
+        if (has) {
+          const double gm = fin ? gv : 0.0, go = fin ? gv * (zi - mu_i) + 1.0 : 0.0;
+          if (it == 1) { hm += gm * gm; ho += go * go; }
+          else { hm = 0.9 * hm + 0.1 * gm * gm; ho = 0.9 * ho + 0.1 * go * go; }
+          m.hist[li] = hm;
+          m.hist[L.D + li] = ho;
+          m.mu[li] = mu_i + es * gm / (1.0 + sqrt(hm));
+          m.omega[li] = om_i + es * go / (1.0 + sqrt(ho));
+        }
+      }
+    }
+  }
+  DBG0(2);
+  double *row = sm + warp * NS;
+  if (lane == 0) {
+    row[S_R] = aR; row[S_RZ] = aRz; row[S_DU] = aDu; row[S_DU2] = aDu2; row[S_SSE] = aS0; row[S_Z2] = aZ2;
+    row[S_U] = aU; row[S_L] = aS1; row[S_LG] = 0; row[S_DG] = 0;
+  }
+  if (lane < k) { row[S_AP + lane] = aAP; row[S_AP + k + lane] = aAPz; }
+  __syncthreads();
+  for (int c = threadIdx.x; c < NS; c += blockDim.x) {
+    double s = 0;
+    for (int w = 0; w < nw; ++w) s += sm[w * NS + c];
+    m.blk[(int64_t)c * gridDim.x + blockIdx.x] = s;  // column-major [NS][nblk]: finish_body reads it coalesced
+  }
+  DBG0(3);
+  if (!fuse) return;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned ticket = atomicAdd(&m.ctl->ticket, 1u);
+    s_last = ticket == gridDim.x - 1;
+    if (s_last) m.ctl->ticket = 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  DBG(4);
+  finish_body(m, mode, jac, propto, 3);
+  DBG(7);
+}
+
+int launch_gene_finish(bvg_fit *f, int mode, int jac, int propto) {
+  const int wpb = 16;
+  const size_t sh = sizeof(double) * wpb * bvg_ns(f->m.k);
+  const int fuse = f->comm ? 0 : 1;
+  if (f->cfg.precision == BVG_PREC_FP64) k_gene<double><<<f->m.nblk_gene, wpb * 32, sh, f->stream>>>(f->m, mode, jac, propto, fuse);
+  else k_gene<float><<<f->m.nblk_gene, wpb * 32, sh, f->stream>>>(f->m, mode, jac, propto, fuse);
+  f->st.kernel_launches++;
+  CUDA_TRY(cudaGetLastError());
+  if (!fuse) {
+    k_finish<<<1, 512, 0, f->stream>>>(f->m, mode, jac, propto, 1);
     CUDA_TRY(cudaGetLastError());
     BVG_TRY(comm_allreduce(f, f->m.tot, bvg_ns(f->m.k)));
-    k_finish<<<1, 256, 0, f->stream>>>(f->m, mode, jac, propto, 2);
+    k_finish<<<1, 512, 0, f->stream>>>(f->m, mode, jac, propto, 2);
     f->st.kernel_launches += 2;
-  } else {
-    k_finish<<<1, 256, 0, f->stream>>>(f->m, mode, jac, propto, 3);
-    f->st.kernel_launches++;
+    CUDA_TRY(cudaGetLastError());
   }
-  CUDA_TRY(cudaGetLastError());
   return BVG_OK;
 }
