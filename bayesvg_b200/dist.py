@@ -72,3 +72,42 @@ def _gather_ragged(bufs, local, dev, sizes):
     td.all_gather(out, pad)
     for b, o, s in zip(bufs, out, sizes):
         b.copy_(o[:s])
+
+
+def layout(likelihood, G, k):
+    """slot offsets of the unconstrained vector (Stan declaration order; inst/approxGP.stan:12-23,
+    inst/approxGP4.stan:12-23 of the reference)"""
+    if likelihood == "gaussian":
+        o = dict(mu_beta0=0, sigma_beta0=1, z_beta0=2, mu_amplitude=2 + G, sigma_amplitude=3 + G, amplitude=4 + G,
+                 mu_alpha=4 + 2 * G, sigma_alpha=4 + 2 * G + k, z_alpha_t=4 + 2 * G + 2 * k, tail=4 + 2 * G + 2 * k + k * G)
+    else:
+        o = dict(mu_beta0=0, sigma_beta0=1, z_beta0=2, tail=2 + G, amplitude=3 + G, mu_amplitude=3 + 2 * G,
+                 sigma_amplitude=4 + 2 * G, mu_alpha=5 + 2 * G, sigma_alpha=5 + 2 * G + k, z_alpha_t=5 + 2 * G + 2 * k)
+    o["D"] = 5 + 2 * G + 2 * k + k * G
+    return o
+
+
+def shard_index(likelihood, G_total, k, g0, g1):
+    """indices into the GLOBAL unconstrained vector that make up the LOCAL vector of the shard holding genes
+    [g0, g1): local = global[shard_index(...)].  The 2k+5 gene-shared entries appear in every shard."""
+    Gl = g1 - g0
+    LG, LL = layout(likelihood, G_total, k), layout(likelihood, Gl, k)
+    idx = np.empty(LL["D"], dtype=np.int64)
+    for name in ("mu_beta0", "sigma_beta0", "mu_amplitude", "sigma_amplitude", "tail"):
+        idx[LL[name]] = LG[name]
+    idx[LL["mu_alpha"]:LL["mu_alpha"] + k] = LG["mu_alpha"] + np.arange(k)
+    idx[LL["sigma_alpha"]:LL["sigma_alpha"] + k] = LG["sigma_alpha"] + np.arange(k)
+    idx[LL["z_beta0"]:LL["z_beta0"] + Gl] = LG["z_beta0"] + np.arange(g0, g1)
+    idx[LL["amplitude"]:LL["amplitude"] + Gl] = LG["amplitude"] + np.arange(g0, g1)
+    idx[LL["z_alpha_t"]:LL["z_alpha_t"] + k * Gl] = LG["z_alpha_t"] + np.arange(k * g0, k * g1)
+    return idx
+
+
+def shared_mask(likelihood, G, k):
+    """boolean mask of the 2k+5 gene-shared entries of a (local or global) vector"""
+    L = layout(likelihood, G, k)
+    m = np.zeros(L["D"], dtype=bool)
+    for name in ("mu_beta0", "sigma_beta0", "mu_amplitude", "sigma_amplitude", "tail"):
+        m[L[name]] = True
+    m[L["mu_alpha"]:L["mu_alpha"] + 2 * k] = True
+    return m
