@@ -21,7 +21,8 @@ EXPORTS = [
     "bvg_fit_dim", "bvg_comm_unique_id", "bvg_fit_comm_init", "bvg_log_prob", "bvg_fit_run", "bvg_fit_mle",
     "bvg_fit_advi", "bvg_fit_summarize", "bvg_fit_set_variational", "bvg_fit_get_variational",
     "bvg_fit_advi_steps", "bvg_fit_elbo", "bvg_fit_time_lik_kernel", "bvg_fit_flush_l2", "bvg_fit_get_summary",
-    "bvg_fit_get_draws", "bvg_fit_get_trace", "bvg_fit_get_stats",
+    "bvg_fit_get_draws", "bvg_fit_get_trace", "bvg_fit_get_stats", "bvg_debug_stage_times", "bvg_debug_gene_trace",
+    "bvg_debug_tc_trace",
 ]
 
 

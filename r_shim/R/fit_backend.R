@@ -1,0 +1,47 @@
+# fit_backend.R -- what replaces lines 290-432 of R/findSpatiallyVariableFeaturesBayes.R in the
+# reference when the B200 engine is used.  Everything before (:99-288: argument checks, coordinate
+# scaling, expression extraction, k-means centroids, length-scale) and after (:436-508: write-back
+# into the Seurat / SpatialExperiment object) stays exactly as it is.  NOT exercised in this
+# repository's image (no R); the Python mirror bayesvg_b200/api.py runs the same sequence of C-ABI
+# calls and is what the tests drive.
+#
+# in scope at :290  : spatial_mtx (M x 2, scaled), kmeans_centers (k x 2), lscale, expr_df (long,
+#                     gene-major), gene_mapping, likelihood, kernel, kernel.smoothness, kernel.period,
+#                     n.iter, mle.init, mle.iter, n.draws, elbo.samples, random.seed, verbose
+bvg_fit_backend <- function(spatial_mtx, kmeans_centers, lscale, expr_df, gene_mapping, likelihood, kernel,
+                            kernel.smoothness, kernel.period, n.iter, mle.init, mle.iter, n.draws,
+                            elbo.samples, random.seed, verbose, device = 0L) {
+  M <- nrow(spatial_mtx)
+  G <- length(unique(expr_df$gene))
+  kernel_id <- match(kernel, c("exp_quad", "matern", "periodic")) - 1L
+  # :265-288  phi <- kernel(...); phi_ortho <- qr.Q(qr(phi, LAPACK = TRUE))
+  phi_ortho <- .Call("R_bvg_basis_build", spatial_mtx, kmeans_centers, as.double(lscale), kernel_id,
+                     as.double(kernel.smoothness), as.double(kernel.period), as.integer(device))
+  # :320-327  data_list: y is the gene-major long vector, i.e. an M x G column-major matrix
+  y <- expr_df$gene_expression
+  dim(y) <- c(M, G)
+  # :337-364  cmdstan_model / compile / optimize / variational  ->  one handle, one run
+  fit <- .Call("R_bvg_fit_create", list(likelihood = ifelse(likelihood == "gaussian", 0L, 1L), n_iter = as.integer(n.iter),
+                                        mle_init = as.integer(mle.init), mle_iter = as.integer(mle.iter),
+                                        n_draws = as.integer(n.draws), elbo_samples = as.integer(elbo.samples),
+                                        seed = as.integer(random.seed), verbose = as.integer(verbose),
+                                        device = as.integer(device)))
+  on.exit(.Call("R_bvg_fit_destroy", fit), add = TRUE)
+  .Call("R_bvg_fit_set_phi", fit, phi_ortho)
+  .Call("R_bvg_fit_set_y", fit, y)
+  .Call("R_bvg_fit_run", fit)
+  # :419-432  fit_vi$summary(variables = "amplitude") %>% rename / join / dispersion / rank
+  s <- .Call("R_bvg_fit_summary", fit, G)
+  amplitude_summary <- data.frame(gene_id = as.character(seq_len(G)),
+                                  amplitude_mean = s[, 1], amplitude_median = s[, 2], amplitude_sd = s[, 3],
+                                  amplitude_mad = s[, 4], amplitude_ci_ll = s[, 5], amplitude_ci_ul = s[, 6]) %>%
+                       dplyr::inner_join(gene_mapping, by = "gene_id") %>%
+                       dplyr::relocate(gene) %>%
+                       dplyr::select(-gene_id) %>%
+                       dplyr::mutate(amplitude_dispersion = amplitude_sd^2 / amplitude_mean) %>%
+                       dplyr::arrange(dplyr::desc(amplitude_mean)) %>%
+                       dplyr::mutate(amplitude_mean_rank = dplyr::row_number()) %>%
+                       as.data.frame() %>%
+                       magrittr::set_rownames(.$gene)
+  amplitude_summary
+}

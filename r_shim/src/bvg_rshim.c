@@ -1,0 +1,110 @@
+/* bvg_rshim.c -- logic-free .Call shim between R and libbayesvg_b200.so (include/bayesvg_b200.h).
+ * NOT compiled in this repository's image (no R, no Rinternals.h); see INTEGRATION.md.
+ * Build inside an R package:  PKG_CPPFLAGS = -I<repo>/include ; PKG_LIBS = -L<libdir> -lbayesvg_b200
+ * Every entry point converts SEXP <-> plain pointers, calls one bvg_* function and turns a non-zero
+ * status into an R error carrying bvg_last_error().  The fit handle is an external pointer with a
+ * finalizer, so an Rf_error long-jump cannot leak device memory. */
+#include <R.h>
+#include <Rinternals.h>
+#include <R_ext/Rdynload.h>
+#include "bayesvg_b200.h"
+
+static void chk(int rc) { if (rc != BVG_OK) Rf_error("bayesvg_b200: %s", bvg_last_error()); }
+static void fit_finalizer(SEXP p) {
+  bvg_fit *f = (bvg_fit *)R_ExternalPtrAddr(p);
+  if (f) { bvg_fit_destroy(f); R_ClearExternalPtr(p); }
+}
+static bvg_fit *get_fit(SEXP p) {
+  bvg_fit *f = (bvg_fit *)R_ExternalPtrAddr(p);
+  if (!f) Rf_error("bayesvg_b200: fit handle already released");
+  return f;
+}
+
+/* .Call("R_bvg_basis_build", coords (M x 2), centers (k x 2), lscale, kernel_id, nu, period, device) */
+SEXP R_bvg_basis_build(SEXP coords, SEXP centers, SEXP lscale, SEXP kernel, SEXP nu, SEXP period, SEXP device) {
+  const R_xlen_t M = Rf_nrows(coords);
+  const int k = Rf_nrows(centers);
+  SEXP out = PROTECT(Rf_allocMatrix(REALSXP, (int)M, k));
+  chk(bvg_basis_build(Rf_asInteger(device), REAL(coords), (int64_t)M, REAL(centers), k, Rf_asReal(lscale),
+                      Rf_asInteger(kernel), Rf_asReal(nu), Rf_asReal(period), REAL(out)));
+  UNPROTECT(1);
+  return out;
+}
+
+/* .Call("R_bvg_fit_create", list(likelihood=, precision=, n_iter=, mle_init=, mle_iter=, n_draws=,
+ *        elbo_samples=, seed=, verbose=, device=)) -> external pointer */
+static int geti(SEXP lst, const char *name, int dflt) {
+  SEXP names = Rf_getAttrib(lst, R_NamesSymbol);
+  for (R_xlen_t i = 0; i < Rf_xlength(lst); ++i)
+    if (strcmp(CHAR(STRING_ELT(names, i)), name) == 0) return Rf_asInteger(VECTOR_ELT(lst, i));
+  return dflt;
+}
+SEXP R_bvg_fit_create(SEXP opts) {
+  bvg_config cfg;
+  bvg_config_default(&cfg);
+  cfg.likelihood = geti(opts, "likelihood", cfg.likelihood);
+  cfg.precision = geti(opts, "precision", cfg.precision);
+  cfg.engine = geti(opts, "engine", cfg.engine);
+  cfg.device = geti(opts, "device", cfg.device);
+  cfg.n_iter = geti(opts, "n_iter", cfg.n_iter);
+  cfg.mle_init = geti(opts, "mle_init", cfg.mle_init);
+  cfg.mle_iter = geti(opts, "mle_iter", cfg.mle_iter);
+  cfg.n_draws = geti(opts, "n_draws", cfg.n_draws);
+  cfg.elbo_samples = geti(opts, "elbo_samples", cfg.elbo_samples);
+  cfg.verbose = geti(opts, "verbose", cfg.verbose);
+  cfg.seed = (uint64_t)geti(opts, "seed", (int)cfg.seed);
+  bvg_fit *f = NULL;
+  chk(bvg_fit_create(&cfg, &f));
+  SEXP p = PROTECT(R_MakeExternalPtr(f, R_NilValue, R_NilValue));
+  R_RegisterCFinalizerEx(p, fit_finalizer, TRUE);
+  UNPROTECT(1);
+  return p;
+}
+SEXP R_bvg_fit_set_phi(SEXP p, SEXP phi) {
+  chk(bvg_fit_set_phi(get_fit(p), REAL(phi), (int64_t)Rf_nrows(phi), Rf_ncols(phi)));
+  return R_NilValue;
+}
+/* y: M x G matrix (= the gene-major long vector of :176-183 with dim(y) <- c(M, G)); double or integer */
+SEXP R_bvg_fit_set_y(SEXP p, SEXP y) {
+  const int64_t M = Rf_nrows(y), G = Rf_ncols(y);
+  if (TYPEOF(y) == INTSXP) chk(bvg_fit_set_y_i32(get_fit(p), INTEGER(y), M, G));
+  else chk(bvg_fit_set_y_f64(get_fit(p), REAL(y), M, G));
+  return R_NilValue;
+}
+SEXP R_bvg_fit_run(SEXP p) { chk(bvg_fit_run(get_fit(p))); return R_NilValue; }
+/* -> G x 8 matrix: mean, median, sd, mad, q5, q95, dispersion, rank */
+SEXP R_bvg_fit_summary(SEXP p, SEXP G) {
+  SEXP out = PROTECT(Rf_allocMatrix(REALSXP, Rf_asInteger(G), 8));
+  chk(bvg_fit_get_summary(get_fit(p), REAL(out)));
+  UNPROTECT(1);
+  return out;
+}
+/* the parity hook: list(lp =, grad =) at an unconstrained vector, like fit$log_prob / fit$grad_log_prob */
+SEXP R_bvg_log_prob(SEXP p, SEXP theta, SEXP jacobian, SEXP propto) {
+  SEXP grad = PROTECT(Rf_allocVector(REALSXP, Rf_xlength(theta)));
+  double lp = 0;
+  chk(bvg_log_prob(get_fit(p), REAL(theta), Rf_asLogical(jacobian), Rf_asLogical(propto), &lp, REAL(grad)));
+  SEXP out = PROTECT(Rf_allocVector(VECSXP, 2));
+  SET_VECTOR_ELT(out, 0, Rf_ScalarReal(lp));
+  SET_VECTOR_ELT(out, 1, grad);
+  UNPROTECT(2);
+  return out;
+}
+SEXP R_bvg_fit_variational(SEXP p, SEXP D) {
+  SEXP out = PROTECT(Rf_allocMatrix(REALSXP, Rf_asInteger(D), 2));
+  chk(bvg_fit_get_variational(get_fit(p), REAL(out), REAL(out) + Rf_asInteger(D)));
+  UNPROTECT(1);
+  return out;
+}
+SEXP R_bvg_fit_destroy(SEXP p) { fit_finalizer(p); return R_NilValue; }
+
+static const R_CallMethodDef calls[] = {
+  {"R_bvg_basis_build", (DL_FUNC)&R_bvg_basis_build, 7}, {"R_bvg_fit_create", (DL_FUNC)&R_bvg_fit_create, 1},
+  {"R_bvg_fit_set_phi", (DL_FUNC)&R_bvg_fit_set_phi, 2}, {"R_bvg_fit_set_y", (DL_FUNC)&R_bvg_fit_set_y, 2},
+  {"R_bvg_fit_run", (DL_FUNC)&R_bvg_fit_run, 1},         {"R_bvg_fit_summary", (DL_FUNC)&R_bvg_fit_summary, 2},
+  {"R_bvg_log_prob", (DL_FUNC)&R_bvg_log_prob, 4},       {"R_bvg_fit_variational", (DL_FUNC)&R_bvg_fit_variational, 2},
+  {"R_bvg_fit_destroy", (DL_FUNC)&R_bvg_fit_destroy, 1}, {NULL, NULL, 0}};
+void R_init_bayesVGb200(DllInfo *dll) {
+  R_registerRoutines(dll, NULL, calls, NULL, NULL);
+  R_useDynamicSymbols(dll, FALSE);
+}
