@@ -117,6 +117,23 @@ __host__ __device__ inline double bvg_normal(uint64_t seed, uint32_t stream, uin
   return sqrt(-2.0 * log(u1)) * cos(6.283185307179586476925286766559 * u2);
 }
 
+// Programmatic dependent launch: every kernel of the evaluation chain is launched with the
+// programmatic-stream-serialization attribute, so its CTAs may start (and run their prologue) while the
+// previous kernel drains; griddep_wait() blocks until the previous grid has completed and its writes
+// are visible.  launch_dependents only says "my successor may start launching".
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 __device__ inline double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

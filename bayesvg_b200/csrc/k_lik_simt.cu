@@ -26,6 +26,8 @@ __global__ void __launch_bounds__(BVG_GENE_TILE) k_lik_simt(const T *__restrict_
                                                             T *__restrict__ Ppart, T *__restrict__ Spart, int64_t M,
                                                             int64_t G, int64_t Gpad, int chunks_per_split,
                                                             const double *__restrict__ zeta, int64_t tail_idx) {
+  griddep_wait();    // the coefficient rows C come from k_prep
+  griddep_launch();
   __shared__ T Ys[BVG_GENE_TILE][ST + 1];
   __shared__ __align__(16) T Ps[ST * KP];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -95,15 +97,14 @@ static int launch_t(bvg_fit *f, bool bwd) {
   const int64_t nchunks = (m.M + ST - 1) / ST;
   const int cps = (int)((nchunks + m.nsplit - 1) / m.nsplit);
   dim3 grid(ntiles, m.nsplit);
-#define LAUNCH(LIK, BWD)                                                                                   \
-  k_lik_simt<T, KP, LIK, BWD><<<grid, BVG_GENE_TILE, 0, f->stream>>>(                                      \
-      (const T *)f->Y, f->ldY, (const T *)f->Phi, (const T *)m.C, (T *)m.Ppart, (T *)m.Spart, m.M, m.G, m.Gpad, \
-      cps, m.zeta, m.L.tail)
+#define LAUNCH(LIK, BWD)                                                                                      \
+  CUDA_TRY(launch_pdl(k_lik_simt<T, KP, LIK, BWD>, grid, dim3(BVG_GENE_TILE), 0, f->stream, (const T *)f->Y, f->ldY, \
+                      (const T *)f->Phi, (const T *)m.C, (T *)m.Ppart, (T *)m.Spart, m.M, m.G, m.Gpad, cps,     \
+                      (const double *)m.zeta, m.L.tail))
   if (m.lik == BVG_GAUSSIAN) { if (bwd) LAUNCH(BVG_GAUSSIAN, true); else LAUNCH(BVG_GAUSSIAN, false); }
   else { if (bwd) LAUNCH(BVG_NB, true); else LAUNCH(BVG_NB, false); }
 #undef LAUNCH
   f->st.kernel_launches++;
-  CUDA_TRY(cudaGetLastError());
   return BVG_OK;
 }
 

@@ -158,6 +158,8 @@ k_lik_tc(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtens
          const __grid_constant__ CUtensorMap tmPhiL, const __grid_constant__ CUtensorMap tmPhiTH,
          const __grid_constant__ CUtensorMap tmPhiTL, TcArgs a) {
   extern __shared__ uint8_t smem_raw[];
+  const bool tr0 = a.trace && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0;
+  if (tr0) { a.trace[8 * 30 + 0] = clock64(); asm volatile("mov.u64 %0, %globaltimer;" : "=l"(a.trace[8 * 30 + 4])); }
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024 B alignment
   const uint32_t sBar = base + TC_STAGES * STAGE_BYTES;
   // barrier map (8 B each)
@@ -176,6 +178,7 @@ k_lik_tc(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtens
   if (n < 0) n = 0;
   constexpr uint32_t NEPI = 256;
 
+  griddep_launch();  // PDL: the successor (k_gene) may begin launching; it waits for this grid to finish
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_STAGES; ++s) {
       mbar_init(bFull + 8 * s, 1);
@@ -200,6 +203,7 @@ k_lik_tc(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtens
   tc_fence_after();
   uint32_t tmem;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(sTmemPtr));
+  if (tr0) a.trace[8 * 30 + 1] = clock64();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -278,6 +282,9 @@ k_lik_tc(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtens
     const uint32_t trow = tmem + ((uint32_t)(32 * q) << 16);
     const int64_t g = (int64_t)tile * BVG_GENE_TILE + r;
     {  // coefficient rows -> TMEM (A operand of MMA1), once per CTA
+      // PDL: everything above (barriers, TMEM, and the producer's first TMA loads of Y / basis tiles, which
+      // no kernel writes) overlaps the tail of k_prep; its output C is first touched here
+      griddep_wait();
       float ch[16], cl[16];
       const float4 *ph = reinterpret_cast<const float4 *>(a.CH + g * TC_KW + 16 * h);
       const float4 *pl = reinterpret_cast<const float4 *>(a.CL + g * TC_KW + 16 * h);
@@ -375,8 +382,10 @@ k_lik_tc(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtens
       a.Spart[row * 2 + 1] = acc1 + s_half[1][r];
     }
   }
+  if (tr0) a.trace[8 * 30 + 2] = clock64();
   tc_fence_before();
   __syncthreads();
+  if (tr0) { a.trace[8 * 30 + 3] = clock64(); asm volatile("mov.u64 %0, %globaltimer;" : "=l"(a.trace[8 * 30 + 5])); }
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)TM_COLS) : "memory");
@@ -491,11 +500,10 @@ int launch_lik_tc(bvg_fit *f, bool bwd) {
   a.zeta = m.zeta; a.tail_idx = m.L.tail;
   a.trace = g_tc_trace;
   dim3 grid((unsigned)(m.Gpad / BVG_GENE_TILE), (unsigned)m.nsplit);
-#define TCL(LIK, BWD) k_lik_tc<LIK, BWD><<<grid, TC_THREADS, TC_SMEM_BYTES, f->stream>>>(t->tmY, t->tmPhiH, t->tmPhiL, t->tmPhiTH, t->tmPhiTL, a)
+#define TCL(LIK, BWD) CUDA_TRY(launch_pdl(k_lik_tc<LIK, BWD>, grid, dim3(TC_THREADS), (size_t)TC_SMEM_BYTES, f->stream, t->tmY, t->tmPhiH, t->tmPhiL, t->tmPhiTH, t->tmPhiTL, a))
   if (m.lik == BVG_GAUSSIAN) { if (bwd) TCL(BVG_GAUSSIAN, true); else TCL(BVG_GAUSSIAN, false); }
   else { if (bwd) TCL(BVG_NB, true); else TCL(BVG_NB, false); }
 #undef TCL
   f->st.kernel_launches++;
-  CUDA_TRY(cudaGetLastError());
   return BVG_OK;
 }

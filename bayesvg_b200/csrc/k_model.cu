@@ -17,6 +17,8 @@
 template <typename T>
 __global__ void __launch_bounds__(256) k_prep(DevModel m, int mode, int tc, int gpb) {
   extern __shared__ double sh[];  // [2k+5] shared zeta | [k] sigma_alpha | [gpb][k+2] gene zeta | [gpb] A_g
+  griddep_wait();    // mu / omega come from the previous evaluation's k_gene
+  griddep_launch();
   const int k = m.k, nsh = 2 * k + 5, npg = k + 2, tid = threadIdx.x;
   double *sal = sh + nsh, *zg = sal + k, *Ag = zg + gpb * npg;
   const uint32_t stream = mode == PREP_GRAD ? STREAM_GRAD : STREAM_ELBO;
@@ -75,10 +77,9 @@ int launch_prep(bvg_fit *f, int mode) {
   const int gpb = (256 - (2 * k + 5)) / (k + 2);
   const int grid = (int)((f->m.G + gpb - 1) / gpb);
   const size_t sh = sizeof(double) * (3 * k + 5 + gpb * (k + 3));
-  if (f->cfg.precision == BVG_PREC_FP64) k_prep<double><<<grid, 256, sh, f->stream>>>(f->m, mode, 0, gpb);
-  else k_prep<float><<<grid, 256, sh, f->stream>>>(f->m, mode, f->engine == BVG_ENGINE_TCGEN05, gpb);
+  if (f->cfg.precision == BVG_PREC_FP64) CUDA_TRY(launch_pdl(k_prep<double>, dim3(grid), dim3(256), sh, f->stream, f->m, mode, 0, gpb));
+  else CUDA_TRY(launch_pdl(k_prep<float>, dim3(grid), dim3(256), sh, f->stream, f->m, mode, (int)(f->engine == BVG_ENGINE_TCGEN05), gpb));
   f->st.kernel_launches++;
-  CUDA_TRY(cudaGetLastError());
   return BVG_OK;
 }
 
@@ -260,6 +261,8 @@ template <typename T>
 __global__ void __launch_bounds__(512) k_gene(DevModel m, int mode, int jac, int propto, int fuse) {
   extern __shared__ double sm[];  // [nwarps][NS]
   __shared__ int s_last;
+  griddep_wait();    // Ppart / Spart come from the likelihood kernel
+  griddep_launch();
   const int k = m.k, KP = m.KP, NS = bvg_ns(k);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const Layout &L = m.L;
@@ -365,10 +368,9 @@ int launch_gene_finish(bvg_fit *f, int mode, int jac, int propto) {
   const int wpb = 16;
   const size_t sh = sizeof(double) * wpb * bvg_ns(f->m.k);
   const int fuse = f->comm ? 0 : 1;
-  if (f->cfg.precision == BVG_PREC_FP64) k_gene<double><<<f->m.nblk_gene, wpb * 32, sh, f->stream>>>(f->m, mode, jac, propto, fuse);
-  else k_gene<float><<<f->m.nblk_gene, wpb * 32, sh, f->stream>>>(f->m, mode, jac, propto, fuse);
+  if (f->cfg.precision == BVG_PREC_FP64) CUDA_TRY(launch_pdl(k_gene<double>, dim3(f->m.nblk_gene), dim3(wpb * 32), sh, f->stream, f->m, mode, jac, propto, fuse));
+  else CUDA_TRY(launch_pdl(k_gene<float>, dim3(f->m.nblk_gene), dim3(wpb * 32), sh, f->stream, f->m, mode, jac, propto, fuse));
   f->st.kernel_launches++;
-  CUDA_TRY(cudaGetLastError());
   if (!fuse) {
     k_finish<<<1, 512, 0, f->stream>>>(f->m, mode, jac, propto, 1);
     CUDA_TRY(cudaGetLastError());
