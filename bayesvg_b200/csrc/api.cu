@@ -143,7 +143,8 @@ static int finalize_model(bvg_fit *f) {
   int nsm = 148;
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, f->cfg.device);
   const int ntiles = (int)(m.Gpad / BVG_GENE_TILE);
-  const int64_t nchunks = (m.M + 31) / 32;
+  const int64_t chunk = f->engine == BVG_ENGINE_TCGEN05 ? 64 : 32;  // spots per pipeline chunk of the likelihood kernel
+  const int64_t nchunks = (m.M + chunk - 1) / chunk;
   // SIMT: ~4 resident CTAs per SM; tcgen05: one 176 KB CTA per SM and never more CTAs than SMs (a
   // partial second wave would double the kernel time), so round DOWN
   int nsplit = f->engine == BVG_ENGINE_TCGEN05 ? std::max(1, nsm / ntiles) : (nsm * 4 + ntiles - 1) / ntiles;

@@ -1,60 +1,63 @@
-// k_lik_tc.cu -- the fused likelihood kernel for sm_100a: TMA-fed tcgen05 (TF32, 3-term split)
-// contractions with TMEM accumulators AND TMEM-resident A operands, one pass over Y per evaluation.
+// k_lik_tc.cu -- the fused likelihood kernel for sm_100a: TMA-fed tcgen05 (BF16x3 split) contractions
+// with TMEM accumulators AND TMEM-resident A operands, one pass over Y per evaluation.
 //
-// Per CTA: one tile of 128 genes (= the 128 TMEM lanes) x one contiguous range of spots, walked
-// in chunks of 32 spots (one 128-byte swizzle row of fp32).  For every chunk
-//   MMA1  D1[128 genes x 32 spots]  = C'[128 x 32] . Phi'_chunk[32 spots x 32]^T      (forward:  f = beta0 + A * Phi alpha;
-//                                                                                       inst/approxGP.stan:33 and :48 of the reference)
-//   epilogue (8 warps, thread = gene row x 16 spots): f <- TMEM, y <- smem (the TMA-written Y tile),
-//         r = y - f (gaussian) | y - (y+phi) sigmoid(f - log phi) (nb), SSE / log-lik partials in
-//         registers, r -> TMEM (tf32 hi and lo parts) with tcgen05.st
-//   MMA2  D2[128 genes x 32]       += R[128 x 32 spots] . Phi'^T_chunk[32 x 32 spots]^T (backward: Phi^T r and R_g = 1^T r)
-// Both 128-row operands (the coefficient rows C' and the residuals R) live in TENSOR MEMORY (A-from-
-// TMEM form of tcgen05.mma): shared memory only carries what TMA brings in (Y tile + four 4 KB basis
-// tiles per chunk) and is read once by the epilogue (Y) and once per term by the tensor core (basis).
-// With both A operands in shared memory the kernel was shared-memory-bandwidth bound (~200 KB of
-// smem traffic per 16 KB of Y; profiles/README.md, "v1").  D2 stays in TMEM for the whole spot range.
-// "3xTF32": every product is evaluated as hi*hi + lo*hi + hi*lo with hi = rna_tf32(x), lo = x - hi, so
-// the tensor-core result carries ~2^-21 relative error instead of TF32's 2^-11.
+// Per CTA: one tile of 128 genes (= the 128 TMEM lanes) x one contiguous range of spots, walked in
+// chunks of 64 spots.  For every chunk
+//   MMA1  D1[128 genes x 64 spots] = C'[128 x 32] . Phi'_chunk[64 spots x 32]^T       (forward:  f = beta0 + A * Phi alpha;
+//                                                                                      inst/approxGP.stan:33 and :48 of the reference)
+//   epilogue (8 warps, thread = gene row x 32 spots): f <- TMEM, y <- smem (the TMA-written, 128B-
+//         swizzled fp32 Y tile), r = y - f (gaussian) | y - (y+phi) sigmoid(f - log phi) (nb), SSE /
+//         log-lik partials in registers (serial per thread: no shuffles, no atomics), r -> TMEM as two
+//         packed bf16 parts with tcgen05.st
+//   MMA2  D2[128 genes x 32]      += R[128 x 64 spots] . Phi'^T_chunk[32 x 64 spots]^T (backward: Phi^T r and R_g = 1^T r)
+// Both 128-row operands (coefficient rows C' and residuals R) live in TENSOR MEMORY (A-from-TMEM form
+// of tcgen05.mma); shared memory only carries what TMA brings in.  D2 stays in TMEM for the CTA's whole
+// spot range and is read once.
+// "BF16x3": x = x1 + x2 (x1 = bf16(x), x2 = bf16(x - x1)); every product is x1*y1 + x2*y1 + x1*y2, i.e.
+// ~2^-16 relative error per product with fp32 accumulation -- and kind::f16 moves K = 16 per instruction
+// at twice the TF32 MAC rate.  History (profiles/README.md): 3xTF32 with 32-spot chunks needed 24 small
+// MMAs per 32 spots and ran at the tensor pipe's limit for that shape (~30 cycles per 128x32x8 MMA,
+// 19 us per launch at cfg2); this version needs 9 per 32 spots.
 //
 // Warp roles (352 threads, 1 CTA/SM): warp 0 = TMA producer, warp 1 = TMEM owner + forward-MMA issuer,
-// warp 2 = backward-MMA issuer (two issue streams: the MMAs are small, so instruction issue, not the
-// tensor pipe, is the scarce resource), warps 3..10 = epilogue (two warps per TMEM lane quarter, 16
-// columns each).  MMA warps stay convergent and issue from one elected lane (elect.sync).
-// Pipelines: smem stage full/empty (6 stages), D1 full/empty (2 TMEM buffers), R ready/free (2).
+// warp 2 = backward-MMA issuer, warps 3..10 = epilogue (two warps per TMEM lane quarter, one 32-spot
+// half each).  MMA warps stay convergent and issue from one elected lane (elect.sync).
+// Pipelines: smem stage full/empty (3 stages of 56 KB), D1 full/empty (2 TMEM buffers), R full/free (2).
 #include <cuda.h>
+#include <cuda_bf16.h>
 
 #include "bvg_internal.cuh"
 
 #define TC_THREADS 352
-#define TC_STAGES 6
-#define TC_CHUNK 32   // spots per chunk
-#define TC_KW 32      // padded operand width (k+1 -> 32 floats = one 128B swizzle row)
-#define TILE_A_BYTES (BVG_GENE_TILE * 128)  // 16 KB: 128 rows x 128 B
-#define TILE_B_BYTES (32 * 128)             // 4 KB: 32 rows x 128 B
-#define STAGE_BYTES (TILE_A_BYTES + 4 * TILE_B_BYTES)
+#define TC_STAGES 3
+#define TC_CHUNK 64   // spots per chunk
+#define TC_KW 32      // coefficient row width (k+1 <= 24 padded to 32)
+#define YT_BYTES (BVG_GENE_TILE * 128)   // 16 KB: 128 genes x 32 spots fp32
+#define FT_BYTES (64 * 128)              // 8 KB: 64 spots x 64 bf16 (first 32 columns = Phi' row)
+#define TT_BYTES (32 * 128)              // 4 KB: 32 basis rows x 64 spots bf16
+#define STAGE_BYTES (2 * YT_BYTES + 2 * FT_BYTES + 2 * TT_BYTES)
 #define TC_SMEM_BYTES (TC_STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/)
 // TMEM column map (512 allocated)
-#define TM_CHI 0
-#define TM_CLO 32
-#define TM_D1 64     // + 32 * buf
-#define TM_R 128     // + 64 * buf : hi at +0, lo at +32
-#define TM_D2 256
+#define TM_C1 0      // 16 columns: bf16 part 1 of the coefficient rows (32 values, packed in pairs)
+#define TM_C2 16
+#define TM_D1 64     // + 64 * buf : forward accumulator, 64 spots
+#define TM_R 192     // + 64 * buf : residual part 1 at +0 (32 columns = 64 spots packed), part 2 at +32
+#define TM_D2 320    // 32 columns: backward accumulator
 #define TM_COLS 512
 
 struct TcArgs {
   float *Ppart, *Spart;
-  const float *CH, *CL;  // [Gpad][32] tf32 hi / lo coefficient rows written by k_prep
+  const float *C;  // [Gpad][32] fp32 coefficient rows written by k_prep
   int64_t M, G, Gpad;
-  int KP, cps, nchunks;
+  int KP, cps, nchunks, nk1;  // nk1 = ceil((k+1)/16): K steps of the forward MMA
   const double *zeta;
   int64_t tail_idx;
   long long *trace;  // optional [chunk][8] clock64 stamps of CTA (0,0) (diagnostics)
 };
 
 struct TcState {
-  CUtensorMap tmY, tmPhiH, tmPhiL, tmPhiTH, tmPhiTL;
-  float *PhiH, *PhiL, *PhiTH, *PhiTL;
+  CUtensorMap tmY, tmF1, tmF2, tmT1, tmT2;
+  __nv_bfloat16 *F1, *F2, *T1, *T2;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -151,12 +154,58 @@ __device__ __forceinline__ float4 lds128(uint32_t a) {
   return v;
 }
 
+// D[tmem] (+)= A[tmem] . B[smem]^T, kind::f16 (bf16 inputs, fp32 accumulate), M = 128, K = 16
+__device__ __forceinline__ void tc_mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 (1 << 4), A = B = BF16 (1 << 7, 1 << 10), K-major
+__device__ __forceinline__ constexpr uint32_t make_idesc_bf16(int Mdim, int Ndim) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(Ndim >> 3) << 17) | ((uint32_t)(Mdim >> 4) << 24);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_st16u(uint32_t taddr, const uint32_t *v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8u(uint32_t taddr, const uint32_t *v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+// (e0, e1) -> packed bf16 pair (e0 in the low half = lower K index) and the packed pair of the remainders
+__device__ __forceinline__ void split_bf16x2(float e0, float e1, uint32_t &p1, uint32_t &p2) {
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p1) : "f"(e1), "f"(e0));
+  const float r0 = e0 - __uint_as_float(p1 << 16), r1 = e1 - __uint_as_float(p1 & 0xffff0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p2) : "f"(r1), "f"(r0));
+}
+
 // ------------------------------------------------------------------------------------------------
 template <int LIK, bool BWD>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-k_lik_tc(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmPhiH,
-         const __grid_constant__ CUtensorMap tmPhiL, const __grid_constant__ CUtensorMap tmPhiTH,
-         const __grid_constant__ CUtensorMap tmPhiTL, TcArgs a) {
+k_lik_tc(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmF1,
+         const __grid_constant__ CUtensorMap tmF2, const __grid_constant__ CUtensorMap tmT1,
+         const __grid_constant__ CUtensorMap tmT2, TcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const bool tr0 = a.trace && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0;
   if (tr0) { a.trace[8 * 30 + 0] = clock64(); asm volatile("mov.u64 %0, %globaltimer;" : "=l"(a.trace[8 * 30 + 4])); }
@@ -167,8 +216,9 @@ k_lik_tc(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtens
   const uint32_t bD1Full = bEmpty + 8 * TC_STAGES, bD1Empty = bD1Full + 16, bRFull = bD1Empty + 16, bRFree = bRFull + 16;
   const uint32_t bCFull = bRFree + 16, bD2Full = bCFull + 8, sTmemPtr = bD2Full + 8;
   __shared__ float s_half[2][BVG_GENE_TILE];
-  auto stY = [&](int s) { return base + s * STAGE_BYTES; };
-  auto stPh = [&](int s, int w) { return base + s * STAGE_BYTES + TILE_A_BYTES + w * TILE_B_BYTES; };  // w: 0 PhiH 1 PhiL 2 PhiTH 3 PhiTL
+  auto stY = [&](int s, int h) { return base + s * STAGE_BYTES + h * YT_BYTES; };
+  auto stF = [&](int s, int w) { return base + s * STAGE_BYTES + 2 * YT_BYTES + w * FT_BYTES; };
+  auto stT = [&](int s, int w) { return base + s * STAGE_BYTES + 2 * YT_BYTES + 2 * FT_BYTES + w * TT_BYTES; };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile = blockIdx.x, split = blockIdx.y;
@@ -206,25 +256,26 @@ k_lik_tc(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtens
   if (tr0) a.trace[8 * 30 + 1] = clock64();
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer (Y and the basis tiles are written by no kernel: no PDL wait) =====
     if (lane == 0) {
       for (int c = 0; c < n; ++c) {
         const int s = c % TC_STAGES;
         if (c >= TC_STAGES) mbar_wait(bEmpty + 8 * s, ((c / TC_STAGES) - 1) & 1);
         const int spot0 = (c_begin + c) * TC_CHUNK;
-        mbar_expect_tx(bFull + 8 * s, TILE_A_BYTES + (BWD ? 4 : 2) * TILE_B_BYTES);
-        tma_load_2d(stY(s), &tmY, bFull + 8 * s, spot0, tile * BVG_GENE_TILE);
-        tma_load_2d(stPh(s, 0), &tmPhiH, bFull + 8 * s, 0, spot0);
-        tma_load_2d(stPh(s, 1), &tmPhiL, bFull + 8 * s, 0, spot0);
+        mbar_expect_tx(bFull + 8 * s, 2 * YT_BYTES + 2 * FT_BYTES + (BWD ? 2 * TT_BYTES : 0));
+        tma_load_2d(stY(s, 0), &tmY, bFull + 8 * s, spot0, tile * BVG_GENE_TILE);
+        tma_load_2d(stY(s, 1), &tmY, bFull + 8 * s, spot0 + 32, tile * BVG_GENE_TILE);
+        tma_load_2d(stF(s, 0), &tmF1, bFull + 8 * s, 0, spot0);
+        tma_load_2d(stF(s, 1), &tmF2, bFull + 8 * s, 0, spot0);
         if (BWD) {
-          tma_load_2d(stPh(s, 2), &tmPhiTH, bFull + 8 * s, spot0, 0);
-          tma_load_2d(stPh(s, 3), &tmPhiTL, bFull + 8 * s, spot0, 0);
+          tma_load_2d(stT(s, 0), &tmT1, bFull + 8 * s, spot0, 0);
+          tma_load_2d(stT(s, 1), &tmT2, bFull + 8 * s, spot0, 0);
         }
       }
     }
   } else if (warp == 1) {
     // ===================== forward MMA issuer (whole warp convergent, one elected lane issues) =====
-    constexpr uint32_t idesc = make_idesc(128, 32);
+    constexpr uint32_t idesc = make_idesc_bf16(128, 64);
     const bool tr = a.trace && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0;
     if (n > 0) mbar_wait(bCFull, 0);
     for (int c = 0; c < n; ++c) {
@@ -234,14 +285,11 @@ k_lik_tc(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtens
       if (c >= 2) mbar_wait(bD1Empty + 8 * b, ((c >> 1) - 1) & 1);
       tc_fence_after();
       if (elect_one()) {
-        const uint32_t d1 = tmem + TM_D1 + 32 * b;
-        const uint64_t bh = make_desc(stPh(s, 0)), bl = make_desc(stPh(s, 1));
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) tc_mma_tf32_ts(d1, tmem + TM_CHI + 8 * kk, bh + 2 * kk, idesc, kk ? 1u : 0u);
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) tc_mma_tf32_ts(d1, tmem + TM_CLO + 8 * kk, bh + 2 * kk, idesc, 1u);
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) tc_mma_tf32_ts(d1, tmem + TM_CHI + 8 * kk, bl + 2 * kk, idesc, 1u);
+        const uint32_t d1 = tmem + TM_D1 + 64 * b;
+        const uint64_t f1 = make_desc(stF(s, 0)), f2 = make_desc(stF(s, 1));
+        for (int kk = 0; kk < a.nk1; ++kk) tc_mma_bf16_ts(d1, tmem + TM_C1 + 8 * kk, f1 + 2 * kk, idesc, kk ? 1u : 0u);
+        for (int kk = 0; kk < a.nk1; ++kk) tc_mma_bf16_ts(d1, tmem + TM_C2 + 8 * kk, f1 + 2 * kk, idesc, 1u);
+        for (int kk = 0; kk < a.nk1; ++kk) tc_mma_bf16_ts(d1, tmem + TM_C1 + 8 * kk, f2 + 2 * kk, idesc, 1u);
         tc_commit(bD1Full + 8 * b);
       }
       __syncwarp();
@@ -250,7 +298,7 @@ k_lik_tc(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtens
   } else if (warp == 2) {
     // ===================== backward MMA issuer =====================
     if (BWD) {
-      constexpr uint32_t idesc = make_idesc(128, 32);
+      constexpr uint32_t idesc = make_idesc_bf16(128, 32);
       const uint32_t d2 = tmem + TM_D2;
       const bool tr = a.trace && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0;
       for (int c = 0; c < n; ++c) {
@@ -259,14 +307,14 @@ k_lik_tc(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtens
         mbar_wait(bRFull + 8 * b, (c >> 1) & 1);         // residuals published by the epilogue
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t rh = tmem + TM_R + 64 * b, rl = rh + 32;
-          const uint64_t th = make_desc(stPh(s, 2)), tl = make_desc(stPh(s, 3));
+          const uint32_t r1 = tmem + TM_R + 64 * b, r2 = r1 + 32;
+          const uint64_t t1 = make_desc(stT(s, 0)), t2 = make_desc(stT(s, 1));
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) tc_mma_tf32_ts(d2, rh + 8 * kk, th + 2 * kk, idesc, (c | kk) ? 1u : 0u);
+          for (int kk = 0; kk < 4; ++kk) tc_mma_bf16_ts(d2, r1 + 8 * kk, t1 + 2 * kk, idesc, (c | kk) ? 1u : 0u);
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) tc_mma_tf32_ts(d2, rl + 8 * kk, th + 2 * kk, idesc, 1u);
+          for (int kk = 0; kk < 4; ++kk) tc_mma_bf16_ts(d2, r2 + 8 * kk, t1 + 2 * kk, idesc, 1u);
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) tc_mma_tf32_ts(d2, rh + 8 * kk, tl + 2 * kk, idesc, 1u);
+          for (int kk = 0; kk < 4; ++kk) tc_mma_bf16_ts(d2, r1 + 8 * kk, t2 + 2 * kk, idesc, 1u);
           tc_commit(bEmpty + 8 * s);   // smem stage free for the producer
           tc_commit(bRFree + 8 * b);   // residual buffer free for the epilogue of chunk c + 2
           if (c == n - 1) tc_commit(bD2Full);
@@ -277,25 +325,24 @@ k_lik_tc(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtens
     }
   } else {
     // ===================== epilogue: 8 warps =====================
-    const int e = warp - 3, q = warp & 3, h = e >> 2;  // TMEM lane quarter of this warp, column half
+    const int e = warp - 3, q = warp & 3, h = e >> 2;  // TMEM lane quarter of this warp, 32-spot half of the chunk
     const int r = 32 * q + lane;                       // gene row inside the tile = TMEM lane
     const uint32_t trow = tmem + ((uint32_t)(32 * q) << 16);
     const int64_t g = (int64_t)tile * BVG_GENE_TILE + r;
-    {  // coefficient rows -> TMEM (A operand of MMA1), once per CTA
-      // PDL: everything above (barriers, TMEM, and the producer's first TMA loads of Y / basis tiles, which
-      // no kernel writes) overlaps the tail of k_prep; its output C is first touched here
+    {  // coefficient rows -> TMEM (A operand of MMA1), once per CTA, as two packed bf16 parts
+      // PDL: everything above (barriers, TMEM, and the producer's first TMA loads) overlaps the tail of
+      // k_prep; its output C is first touched here
       griddep_wait();
-      float ch[16], cl[16];
-      const float4 *ph = reinterpret_cast<const float4 *>(a.CH + g * TC_KW + 16 * h);
-      const float4 *pl = reinterpret_cast<const float4 *>(a.CL + g * TC_KW + 16 * h);
+      const float4 *pc = reinterpret_cast<const float4 *>(a.C + g * TC_KW + 16 * h);
+      uint32_t c1[8], c2[8];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const float4 x = ph[i], y = pl[i];
-        ch[4 * i] = x.x; ch[4 * i + 1] = x.y; ch[4 * i + 2] = x.z; ch[4 * i + 3] = x.w;
-        cl[4 * i] = y.x; cl[4 * i + 1] = y.y; cl[4 * i + 2] = y.z; cl[4 * i + 3] = y.w;
+        const float4 x = pc[i];
+        split_bf16x2(x.x, x.y, c1[2 * i], c2[2 * i]);
+        split_bf16x2(x.z, x.w, c1[2 * i + 1], c2[2 * i + 1]);
       }
-      tmem_st16(trow + TM_CHI + 16 * h, ch);
-      tmem_st16(trow + TM_CLO + 16 * h, cl);
+      tmem_st8u(trow + TM_C1 + 8 * h, c1);
+      tmem_st8u(trow + TM_C2 + 8 * h, c2);
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(bCFull);
@@ -310,47 +357,47 @@ k_lik_tc(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtens
       mbar_wait(bD1Full + 8 * b, (c >> 1) & 1);        // MMA1 of this chunk retired
       tc_fence_after();
       if (tr) a.trace[c * 8 + 4] = clock64();
-      float f[16];
-      tmem_ld16(trow + TM_D1 + 32 * b + 16 * h, f);
+      float f[32];
+      tmem_ld32(trow + TM_D1 + 64 * b + 32 * h, f);
       if (tr) a.trace[c * 8 + 5] = clock64();
       tc_fence_before();
       mbar_arrive(bD1Empty + 8 * b);
-      const uint32_t yrow = stY(s) + r * 128;
-      const int64_t spot0 = (int64_t)(c_begin + c) * TC_CHUNK + 16 * h;
-      float hi[16], lo[16];
+      const uint32_t yrow = stY(s, h) + r * 128;
+      const int64_t spot0 = (int64_t)(c_begin + c) * TC_CHUNK + 32 * h;
+      uint32_t p1[16], p2[16];
 #pragma unroll
-      for (int c4 = 0; c4 < 4; ++c4) {
-        const uint32_t off = (uint32_t)(((4 * h + c4) ^ (r & 7)) << 4);  // 128B swizzle: 16B chunk index ^ (row & 7)
+      for (int c4 = 0; c4 < 8; ++c4) {
+        const uint32_t off = (uint32_t)((c4 ^ (r & 7)) << 4);  // 128B swizzle: 16B chunk index ^ (row & 7)
         const float4 y4 = lds128(yrow + off);
         const float yv[4] = {y4.x, y4.y, y4.z, y4.w};
+        float res[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const float ff = f[4 * c4 + i];
-          float res;
           if (LIK == BVG_GAUSSIAN) {
-            res = yv[i] - ff;
-            acc0 = fmaf(res, res, acc0);
+            res[i] = yv[i] - ff;
+            acc0 = fmaf(res[i], res[i], acc0);
           } else {
             const float d = ff - lt;
             const float ex = __expf(-fabsf(d));
             const float Lq = fmaxf(d, 0.f) + log1pf(ex);
             const float sg = (d >= 0.f ? 1.f : ex) / (1.f + ex);
-            res = yv[i] - (yv[i] + phi) * sg;
+            res[i] = yv[i] - (yv[i] + phi) * sg;
             if (spot0 + 4 * c4 + i < a.M) {
               acc0 += yv[i] * ff - (yv[i] + phi) * Lq - yv[i] * lt;
               acc1 += Lq;
             }
           }
-          hi[4 * c4 + i] = tf32_rna(res);
-          lo[4 * c4 + i] = res - hi[4 * c4 + i];
         }
+        split_bf16x2(res[0], res[1], p1[2 * c4], p2[2 * c4]);
+        split_bf16x2(res[2], res[3], p1[2 * c4 + 1], p2[2 * c4 + 1]);
       }
       if (BWD) {
         if (tr) a.trace[c * 8 + 6] = clock64();
         if (c >= 2) mbar_wait(bRFree + 8 * b, ((c >> 1) - 1) & 1);  // MMA2 of chunk c-2 has consumed this buffer
         tc_fence_after();
-        tmem_st16(trow + TM_R + 64 * b + 16 * h, hi);
-        tmem_st16(trow + TM_R + 64 * b + 32 + 16 * h, lo);
+        tmem_st16u(trow + TM_R + 64 * b + 16 * h, p1);
+        tmem_st16u(trow + TM_R + 64 * b + 32 + 16 * h, p2);
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(bRFull + 8 * b);
@@ -395,20 +442,20 @@ k_lik_tc(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtens
 // ------------------------------------------------------------------------------------------------
 // host side: operand staging, tensor maps, launch
 // ------------------------------------------------------------------------------------------------
-// Phi (M x k col-major fp64) -> tf32 hi/lo splits of Phi' in both orientations
-__global__ void k_tc_stage_phi(const double *__restrict__ phi, int64_t M, int64_t Mpad, int k, float *__restrict__ PhiH,
-                               float *__restrict__ PhiL, float *__restrict__ PhiTH, float *__restrict__ PhiTL) {
-  const int64_t n = Mpad * TC_KW;
+// Phi (M x k col-major fp64) -> bf16 part 1 / part 2 of Phi' in both orientations:
+//   F*: [Mpad][64]  (row = spot, 128 B; columns 0..k = Phi' row, rest zero)   B operand of the forward MMA
+//   T*: [32][Mpad]  (row = basis index, spots contiguous)                      B operand of the backward MMA
+__global__ void k_tc_stage_phi(const double *__restrict__ phi, int64_t M, int64_t Mpad, int k, __nv_bfloat16 *__restrict__ F1,
+                               __nv_bfloat16 *__restrict__ F2, __nv_bfloat16 *__restrict__ T1, __nv_bfloat16 *__restrict__ T2) {
+  const int64_t n = Mpad * 64;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t s = i / TC_KW;
-    const int j = (int)(i - s * TC_KW);
+    const int64_t s = i / 64;
+    const int j = (int)(i - s * 64);
     float v = 0.f;
-    if (s < M) v = j < k ? (float)phi[(int64_t)j * M + s] : (j == k ? 1.f : 0.f);
-    uint32_t hb;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
-    const float hi = __uint_as_float(hb), lo = v - hi;
-    PhiH[i] = hi; PhiL[i] = lo;
-    PhiTH[(int64_t)j * Mpad + s] = hi; PhiTL[(int64_t)j * Mpad + s] = lo;
+    if (s < M && j <= k) v = j < k ? (float)phi[(int64_t)j * M + s] : 1.f;
+    const __nv_bfloat16 b1 = __float2bfloat16_rn(v), b2 = __float2bfloat16_rn(v - __bfloat162float(b1));
+    F1[i] = b1; F2[i] = b2;
+    if (j < 32) { T1[(int64_t)j * Mpad + s] = b1; T2[(int64_t)j * Mpad + s] = b2; }
   }
 }
 
@@ -425,13 +472,14 @@ static EncodeTiledFn get_encode() {
   }
   return fn;
 }
-// 2-D fp32 tensor [rows][cols] (cols contiguous, row pitch ld floats), box = box_rows x 32 floats, SWIZZLE_128B
-static int make_map(CUtensorMap *m, void *ptr, uint64_t cols, uint64_t rows, uint64_t ld, uint32_t box_rows) {
+// 2-D tensor [rows][cols] (cols contiguous, row pitch ld elements), box = box_rows x 128 bytes, SWIZZLE_128B
+static int make_map(CUtensorMap *m, void *ptr, bool bf16, uint64_t cols, uint64_t rows, uint64_t ld, uint32_t box_rows) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { bvg_set_error("cuTensorMapEncodeTiled is not available from this driver"); return BVG_ERR_CUDA; }
-  cuuint64_t dims[2] = {cols, rows}, strides[1] = {ld * sizeof(float)};
-  cuuint32_t box[2] = {32, box_rows}, es[2] = {1, 1};
-  const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  const size_t es_bytes = bf16 ? 2 : 4;
+  cuuint64_t dims[2] = {cols, rows}, strides[1] = {ld * es_bytes};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / es_bytes), box_rows}, es[2] = {1, 1};
+  const CUresult r = enc(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { bvg_set_error("cuTensorMapEncodeTiled failed with %d", (int)r); return BVG_ERR_CUDA; }
   return BVG_OK;
@@ -444,16 +492,16 @@ int tc_setup(bvg_fit *f) {
   if (m.k + 1 > 24) { bvg_set_error("tcgen05 engine: k + 1 = %d exceeds 24", m.k + 1); return BVG_ERR_ARG; }
   TcState *t = new TcState();
   f->tc = t;
-  const size_t nb = sizeof(float) * (size_t)f->Mpad * TC_KW;
-  CUDA_TRY(cudaMalloc(&t->PhiH, 4 * nb));
-  t->PhiL = t->PhiH + (size_t)f->Mpad * TC_KW; t->PhiTH = t->PhiL + (size_t)f->Mpad * TC_KW; t->PhiTL = t->PhiTH + (size_t)f->Mpad * TC_KW;
-  k_tc_stage_phi<<<148 * 2, 256, 0, f->stream>>>(f->phi64, m.M, f->Mpad, m.k, t->PhiH, t->PhiL, t->PhiTH, t->PhiTL);
+  const size_t nF = (size_t)f->Mpad * 64, nT = (size_t)32 * f->Mpad;
+  CUDA_TRY(cudaMalloc(&t->F1, sizeof(__nv_bfloat16) * (2 * nF + 2 * nT)));
+  t->F2 = t->F1 + nF; t->T1 = t->F2 + nF; t->T2 = t->T1 + nT;
+  k_tc_stage_phi<<<148 * 2, 256, 0, f->stream>>>(f->phi64, m.M, f->Mpad, m.k, t->F1, t->F2, t->T1, t->T2);
   CUDA_TRY(cudaGetLastError());
-  BVG_TRY(make_map(&t->tmY, f->Y, (uint64_t)f->ldY, (uint64_t)m.G, (uint64_t)f->ldY, BVG_GENE_TILE));
-  BVG_TRY(make_map(&t->tmPhiH, t->PhiH, TC_KW, (uint64_t)f->Mpad, TC_KW, 32));
-  BVG_TRY(make_map(&t->tmPhiL, t->PhiL, TC_KW, (uint64_t)f->Mpad, TC_KW, 32));
-  BVG_TRY(make_map(&t->tmPhiTH, t->PhiTH, (uint64_t)f->Mpad, TC_KW, (uint64_t)f->Mpad, 32));
-  BVG_TRY(make_map(&t->tmPhiTL, t->PhiTL, (uint64_t)f->Mpad, TC_KW, (uint64_t)f->Mpad, 32));
+  BVG_TRY(make_map(&t->tmY, f->Y, false, (uint64_t)f->ldY, (uint64_t)m.G, (uint64_t)f->ldY, BVG_GENE_TILE));
+  BVG_TRY(make_map(&t->tmF1, t->F1, true, 64, (uint64_t)f->Mpad, 64, 64));
+  BVG_TRY(make_map(&t->tmF2, t->F2, true, 64, (uint64_t)f->Mpad, 64, 64));
+  BVG_TRY(make_map(&t->tmT1, t->T1, true, (uint64_t)f->Mpad, 32, (uint64_t)f->Mpad, 32));
+  BVG_TRY(make_map(&t->tmT2, t->T2, true, (uint64_t)f->Mpad, 32, (uint64_t)f->Mpad, 32));
   CUDA_TRY(cudaFuncSetAttribute(k_lik_tc<BVG_GAUSSIAN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(k_lik_tc<BVG_GAUSSIAN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(k_lik_tc<BVG_NB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
@@ -464,7 +512,7 @@ int tc_setup(bvg_fit *f) {
 void tc_destroy(bvg_fit *f) {
   TcState *t = (TcState *)f->tc;
   if (!t) return;
-  cudaFree(t->PhiH);
+  cudaFree(t->F1);
   delete t;
   f->tc = nullptr;
 }
@@ -493,14 +541,15 @@ int launch_lik_tc(bvg_fit *f, bool bwd) {
   TcState *t = (TcState *)f->tc;
   TcArgs a;
   a.Ppart = (float *)m.Ppart; a.Spart = (float *)m.Spart;
-  a.CH = (const float *)m.C; a.CL = a.CH + (size_t)m.Gpad * TC_KW;  // k_prep writes the hi/lo coefficient rows here
+  a.C = (const float *)m.C;  // k_prep writes the fp32 coefficient rows [Gpad][32] here
+  a.nk1 = (m.k + 1 + 15) / 16;
   a.M = m.M; a.G = m.G; a.Gpad = m.Gpad; a.KP = m.KP;
   a.nchunks = (int)((m.M + TC_CHUNK - 1) / TC_CHUNK);
   a.cps = (a.nchunks + m.nsplit - 1) / m.nsplit;
   a.zeta = m.zeta; a.tail_idx = m.L.tail;
   a.trace = g_tc_trace;
   dim3 grid((unsigned)(m.Gpad / BVG_GENE_TILE), (unsigned)m.nsplit);
-#define TCL(LIK, BWD) CUDA_TRY(launch_pdl(k_lik_tc<LIK, BWD>, grid, dim3(TC_THREADS), (size_t)TC_SMEM_BYTES, f->stream, t->tmY, t->tmPhiH, t->tmPhiL, t->tmPhiTH, t->tmPhiTL, a))
+#define TCL(LIK, BWD) CUDA_TRY(launch_pdl(k_lik_tc<LIK, BWD>, grid, dim3(TC_THREADS), (size_t)TC_SMEM_BYTES, f->stream, t->tmY, t->tmF1, t->tmF2, t->tmT1, t->tmT2, a))
   if (m.lik == BVG_GAUSSIAN) { if (bwd) TCL(BVG_GAUSSIAN, true); else TCL(BVG_GAUSSIAN, false); }
   else { if (bwd) TCL(BVG_NB, true); else TCL(BVG_NB, false); }
 #undef TCL

@@ -63,13 +63,8 @@ __global__ void __launch_bounds__(256) k_prep(DevModel m, int mode, int tc, int 
   const double v = j < k ? Ag[gl] * (sh[5 + j] + sal[j] * zg[gl * npg + j])  // A_g * alpha_t[j,g] (approxGP.stan:32)
                          : sh[0] + sh[1] * zg[gl * npg + k];                  // beta0 (approxGP.stan:26)
   if (!tc) { ((T *)m.C)[g * m.KP + j] = (T)v; return; }
-  // tcgen05 engine: rows of width 32 split into tf32 hi / lo parts for the 3xTF32 contraction
-  const float x = (float)v;
-  uint32_t hb;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(x));
-  const float hi = __uint_as_float(hb);
-  ((float *)m.C)[g * 32 + j] = hi;
-  ((float *)m.C)[(m.Gpad + g) * 32 + j] = x - hi;
+  // tcgen05 engine: fp32 rows of width 32 (the likelihood kernel splits them into bf16 parts itself)
+  ((float *)m.C)[g * 32 + j] = (float)v;
 }
 
 int launch_prep(bvg_fit *f, int mode) {
