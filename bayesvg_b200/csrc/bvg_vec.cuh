@@ -8,6 +8,8 @@ struct LinCoef { double d[2 * LBFGS_MAX_HISTORY + 1]; };
 
 template <typename SRC, typename DST>
 int stage_y(const SRC *src, DST *dst, int64_t M, int64_t ldY, int64_t ngenes, cudaStream_t st);
+template <typename SRC>
+int stage_y_tiled(const SRC *src, float *dst, int64_t M, int64_t ldY, int64_t g0, int64_t ngenes, cudaStream_t st);
 template <typename T>
 int stage_phi(const double *phi, T *out, int64_t M, int64_t Mpad, int k, int KP, cudaStream_t st);
 int vec_multidot3(cudaStream_t st, const double *B, int64_t D, int nrows, int ra, int rb, int rc, const double *w,

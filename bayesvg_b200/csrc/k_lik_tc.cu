@@ -19,24 +19,28 @@
 // MMAs per 32 spots and ran at the tensor pipe's limit for that shape (~30 cycles per 128x32x8 MMA,
 // 19 us per launch at cfg2); this version needs 9 per 32 spots.
 //
-// Warp roles (352 threads, 1 CTA/SM): warp 0 = TMA producer, warp 1 = TMEM owner + forward-MMA issuer,
-// warp 2 = backward-MMA issuer, warps 3..10 = epilogue (two warps per TMEM lane quarter, one 32-spot
-// half each).  MMA warps stay convergent and issue from one elected lane (elect.sync).
-// Pipelines: smem stage full/empty (3 stages of 56 KB), D1 full/empty (2 TMEM buffers), R full/free (2).
+// Warp roles (384 threads, 1 CTA/SM): warp 0 = TMA producer of the Y ring, warp 11 = TMA producer of the
+// basis ring, warp 1 = TMEM owner + forward-MMA issuer, warp 2 = backward-MMA issuer, warps 3..10 =
+// epilogue (two warps per TMEM lane quarter, one 32-spot half each).  MMA warps stay convergent and
+// issue from one elected lane (elect.sync).
+// Pipelines: Y ring full/empty (5 x 32 KB, released by the epilogue as soon as y is in registers), basis
+// ring full/empty (2 x 24 KB, released by the MMA that read it), D1 full/empty (2 TMEM buffers), R full/free (2).
 #include <cuda.h>
 #include <cuda_bf16.h>
 
 #include "bvg_internal.cuh"
 
-#define TC_THREADS 352
-#define TC_STAGES 3
+#define TC_THREADS 384
+#define TC_NY 4       // Y ring: HBM latency needs depth (4 x 32 KB in flight per SM)
+#define TC_NB 3       // basis ring (24 KB per stage; tiles are L2-resident but the refill sits in the MMA1 -> epilogue -> MMA2 loop)
 #define TC_CHUNK 64   // spots per chunk
 #define TC_KW 32      // coefficient row width (k+1 <= 24 padded to 32)
 #define YT_BYTES (BVG_GENE_TILE * 128)   // 16 KB: 128 genes x 32 spots fp32
 #define FT_BYTES (64 * 128)              // 8 KB: 64 spots x 64 bf16 (first 32 columns = Phi' row)
 #define TT_BYTES (32 * 128)              // 4 KB: 32 basis rows x 64 spots bf16
-#define STAGE_BYTES (2 * YT_BYTES + 2 * FT_BYTES + 2 * TT_BYTES)
-#define TC_SMEM_BYTES (TC_STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/)
+#define YSTAGE_BYTES (2 * YT_BYTES)
+#define BSTAGE_BYTES (2 * FT_BYTES + 2 * TT_BYTES)
+#define TC_SMEM_BYTES (TC_NY * YSTAGE_BYTES + TC_NB * BSTAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/)
 // TMEM column map (512 allocated)
 #define TM_C1 0      // 16 columns: bf16 part 1 of the coefficient rows (32 values, packed in pairs)
 #define TM_C2 16
@@ -49,7 +53,7 @@ struct TcArgs {
   float *Ppart, *Spart;
   const float *C;  // [Gpad][32] fp32 coefficient rows written by k_prep
   int64_t M, G, Gpad;
-  int KP, cps, nchunks, nk1;  // nk1 = ceil((k+1)/16): K steps of the forward MMA
+  int KP, cps, nchunks, nk1, nch32;  // nk1 = ceil((k+1)/16): K steps of the forward MMA; nch32 = ldY / 32
   const double *zeta;
   int64_t tail_idx;
   long long *trace;  // optional [chunk][8] clock64 stamps of CTA (0,0) (diagnostics)
@@ -210,15 +214,15 @@ k_lik_tc(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtens
   const bool tr0 = a.trace && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0;
   if (tr0) { a.trace[8 * 30 + 0] = clock64(); asm volatile("mov.u64 %0, %globaltimer;" : "=l"(a.trace[8 * 30 + 4])); }
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024 B alignment
-  const uint32_t sBar = base + TC_STAGES * STAGE_BYTES;
+  const uint32_t sB0 = base + TC_NY * YSTAGE_BYTES, sBar = sB0 + TC_NB * BSTAGE_BYTES;
   // barrier map (8 B each)
-  const uint32_t bFull = sBar, bEmpty = bFull + 8 * TC_STAGES;
-  const uint32_t bD1Full = bEmpty + 8 * TC_STAGES, bD1Empty = bD1Full + 16, bRFull = bD1Empty + 16, bRFree = bRFull + 16;
+  const uint32_t bFullY = sBar, bEmptyY = bFullY + 8 * TC_NY, bFullB = bEmptyY + 8 * TC_NY, bEmptyB = bFullB + 8 * TC_NB;
+  const uint32_t bD1Full = bEmptyB + 8 * TC_NB, bD1Empty = bD1Full + 16, bRFull = bD1Empty + 16, bRFree = bRFull + 16;
   const uint32_t bCFull = bRFree + 16, bD2Full = bCFull + 8, sTmemPtr = bD2Full + 8;
   __shared__ float s_half[2][BVG_GENE_TILE];
-  auto stY = [&](int s, int h) { return base + s * STAGE_BYTES + h * YT_BYTES; };
-  auto stF = [&](int s, int w) { return base + s * STAGE_BYTES + 2 * YT_BYTES + w * FT_BYTES; };
-  auto stT = [&](int s, int w) { return base + s * STAGE_BYTES + 2 * YT_BYTES + 2 * FT_BYTES + w * TT_BYTES; };
+  auto stY = [&](int s, int h) { return base + s * YSTAGE_BYTES + h * YT_BYTES; };
+  auto stF = [&](int s, int w) { return sB0 + s * BSTAGE_BYTES + w * FT_BYTES; };
+  auto stT = [&](int s, int w) { return sB0 + s * BSTAGE_BYTES + 2 * FT_BYTES + w * TT_BYTES; };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile = blockIdx.x, split = blockIdx.y;
@@ -230,10 +234,8 @@ k_lik_tc(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtens
 
   griddep_launch();  // PDL: the successor (k_gene) may begin launching; it waits for this grid to finish
   if (threadIdx.x == 0) {
-    for (int s = 0; s < TC_STAGES; ++s) {
-      mbar_init(bFull + 8 * s, 1);
-      mbar_init(bEmpty + 8 * s, BWD ? 1 : NEPI);
-    }
+    for (int s = 0; s < TC_NY; ++s) { mbar_init(bFullY + 8 * s, 1); mbar_init(bEmptyY + 8 * s, NEPI); }
+    for (int s = 0; s < TC_NB; ++s) { mbar_init(bFullB + 8 * s, 1); mbar_init(bEmptyB + 8 * s, 1); }
     for (int b = 0; b < 2; ++b) {
       mbar_init(bD1Full + 8 * b, 1);
       mbar_init(bD1Empty + 8 * b, NEPI);
@@ -256,20 +258,29 @@ k_lik_tc(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtens
   if (tr0) a.trace[8 * 30 + 1] = clock64();
 
   if (warp == 0) {
-    // ===================== TMA producer (Y and the basis tiles are written by no kernel: no PDL wait) =====
+    // ===================== TMA producer, Y ring (Y is written by no kernel: no PDL wait) =====
     if (lane == 0) {
       for (int c = 0; c < n; ++c) {
-        const int s = c % TC_STAGES;
-        if (c >= TC_STAGES) mbar_wait(bEmpty + 8 * s, ((c / TC_STAGES) - 1) & 1);
+        const int s = c % TC_NY;
+        if (c >= TC_NY) mbar_wait(bEmptyY + 8 * s, ((c / TC_NY) - 1) & 1);
+        mbar_expect_tx(bFullY + 8 * s, YSTAGE_BYTES);
+        // one 32 KB contiguous run of the tile-major Y: rows [0,128) = spots spot0..+31, rows [128,256) = +32..+63
+        tma_load_2d(stY(s, 0), &tmY, bFullY + 8 * s, 0, (tile * a.nch32 + 2 * (c_begin + c)) * BVG_GENE_TILE);
+      }
+    }
+  } else if (warp == 11) {
+    // ===================== TMA producer, basis ring =====
+    if (lane == 0) {
+      for (int c = 0; c < n; ++c) {
+        const int s = c % TC_NB;
+        if (c >= TC_NB) mbar_wait(bEmptyB + 8 * s, ((c / TC_NB) - 1) & 1);
         const int spot0 = (c_begin + c) * TC_CHUNK;
-        mbar_expect_tx(bFull + 8 * s, 2 * YT_BYTES + 2 * FT_BYTES + (BWD ? 2 * TT_BYTES : 0));
-        tma_load_2d(stY(s, 0), &tmY, bFull + 8 * s, spot0, tile * BVG_GENE_TILE);
-        tma_load_2d(stY(s, 1), &tmY, bFull + 8 * s, spot0 + 32, tile * BVG_GENE_TILE);
-        tma_load_2d(stF(s, 0), &tmF1, bFull + 8 * s, 0, spot0);
-        tma_load_2d(stF(s, 1), &tmF2, bFull + 8 * s, 0, spot0);
+        mbar_expect_tx(bFullB + 8 * s, 2 * FT_BYTES + (BWD ? 2 * TT_BYTES : 0));
+        tma_load_2d(stF(s, 0), &tmF1, bFullB + 8 * s, 0, spot0);
+        tma_load_2d(stF(s, 1), &tmF2, bFullB + 8 * s, 0, spot0);
         if (BWD) {
-          tma_load_2d(stT(s, 0), &tmT1, bFull + 8 * s, spot0, 0);
-          tma_load_2d(stT(s, 1), &tmT2, bFull + 8 * s, spot0, 0);
+          tma_load_2d(stT(s, 0), &tmT1, bFullB + 8 * s, spot0, 0);
+          tma_load_2d(stT(s, 1), &tmT2, bFullB + 8 * s, spot0, 0);
         }
       }
     }
@@ -279,9 +290,9 @@ k_lik_tc(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtens
     const bool tr = a.trace && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0;
     if (n > 0) mbar_wait(bCFull, 0);
     for (int c = 0; c < n; ++c) {
-      const int s = c % TC_STAGES, b = c & 1;
+      const int s = c % TC_NB, b = c & 1;
       if (tr) a.trace[c * 8 + 0] = clock64();
-      mbar_wait(bFull + 8 * s, (c / TC_STAGES) & 1);
+      mbar_wait(bFullB + 8 * s, (c / TC_NB) & 1);
       if (c >= 2) mbar_wait(bD1Empty + 8 * b, ((c >> 1) - 1) & 1);
       tc_fence_after();
       if (elect_one()) {
@@ -291,6 +302,7 @@ k_lik_tc(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtens
         for (int kk = 0; kk < a.nk1; ++kk) tc_mma_bf16_ts(d1, tmem + TM_C2 + 8 * kk, f1 + 2 * kk, idesc, 1u);
         for (int kk = 0; kk < a.nk1; ++kk) tc_mma_bf16_ts(d1, tmem + TM_C1 + 8 * kk, f2 + 2 * kk, idesc, 1u);
         tc_commit(bD1Full + 8 * b);
+        if (!BWD) tc_commit(bEmptyB + 8 * s);  // forward-only: the basis stage is free once MMA1 has read it
       }
       __syncwarp();
       if (tr) a.trace[c * 8 + 1] = clock64();
@@ -302,8 +314,8 @@ k_lik_tc(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtens
       const uint32_t d2 = tmem + TM_D2;
       const bool tr = a.trace && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0;
       for (int c = 0; c < n; ++c) {
-        const int s = c % TC_STAGES, b = c & 1;
-        mbar_wait(bFull + 8 * s, (c / TC_STAGES) & 1);   // basis tiles of this stage (acquire)
+        const int s = c % TC_NB, b = c & 1;
+        mbar_wait(bFullB + 8 * s, (c / TC_NB) & 1);      // basis tiles of this stage (acquire)
         mbar_wait(bRFull + 8 * b, (c >> 1) & 1);         // residuals published by the epilogue
         tc_fence_after();
         if (elect_one()) {
@@ -315,7 +327,7 @@ k_lik_tc(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtens
           for (int kk = 0; kk < 4; ++kk) tc_mma_bf16_ts(d2, r2 + 8 * kk, t1 + 2 * kk, idesc, 1u);
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) tc_mma_bf16_ts(d2, r1 + 8 * kk, t2 + 2 * kk, idesc, 1u);
-          tc_commit(bEmpty + 8 * s);   // smem stage free for the producer
+          tc_commit(bEmptyB + 8 * s);  // basis stage free for its producer
           tc_commit(bRFree + 8 * b);   // residual buffer free for the epilogue of chunk c + 2
           if (c == n - 1) tc_commit(bD2Full);
         }
@@ -351,8 +363,8 @@ k_lik_tc(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtens
     if (LIK == BVG_NB) { lt = (float)a.zeta[a.tail_idx]; phi = __expf(lt); }
     const bool tr = a.trace && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 96;
     for (int c = 0; c < n; ++c) {
-      const int s = c % TC_STAGES, b = c & 1;
-      mbar_wait(bFull + 8 * s, (c / TC_STAGES) & 1);   // Y tile landed (acquire for this thread)
+      const int s = c % TC_NY, b = c & 1;
+      mbar_wait(bFullY + 8 * s, (c / TC_NY) & 1);      // Y tile landed (acquire for this thread)
       if (tr) a.trace[c * 8 + 3] = clock64();
       mbar_wait(bD1Full + 8 * b, (c >> 1) & 1);        // MMA1 of this chunk retired
       tc_fence_after();
@@ -392,6 +404,7 @@ k_lik_tc(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtens
         split_bf16x2(res[0], res[1], p1[2 * c4], p2[2 * c4]);
         split_bf16x2(res[2], res[3], p1[2 * c4 + 1], p2[2 * c4 + 1]);
       }
+      mbar_arrive(bEmptyY + 8 * s);  // y is in registers: the Y stage can be refilled
       if (BWD) {
         if (tr) a.trace[c * 8 + 6] = clock64();
         if (c >= 2) mbar_wait(bRFree + 8 * b, ((c >> 1) - 1) & 1);  // MMA2 of chunk c-2 has consumed this buffer
@@ -402,8 +415,6 @@ k_lik_tc(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtens
         tc_fence_before();
         mbar_arrive(bRFull + 8 * b);
         if (tr) a.trace[c * 8 + 7] = clock64();
-      } else {
-        mbar_arrive(bEmpty + 8 * s);
       }
     }
     // ---- drain: P' = D2 (k+1 values per gene) and the scalar partials ----
@@ -497,7 +508,8 @@ int tc_setup(bvg_fit *f) {
   t->F2 = t->F1 + nF; t->T1 = t->F2 + nF; t->T2 = t->T1 + nT;
   k_tc_stage_phi<<<148 * 2, 256, 0, f->stream>>>(f->phi64, m.M, f->Mpad, m.k, t->F1, t->F2, t->T1, t->T2);
   CUDA_TRY(cudaGetLastError());
-  BVG_TRY(make_map(&t->tmY, f->Y, false, (uint64_t)f->ldY, (uint64_t)m.G, (uint64_t)f->ldY, BVG_GENE_TILE));
+  // Y is tile-major: rows of 32 spots, 128 gene rows per (tile, 32-spot chunk); one box = one 64-spot stage
+  BVG_TRY(make_map(&t->tmY, f->Y, false, 32, (uint64_t)(m.Gpad / BVG_GENE_TILE) * (uint64_t)(f->ldY / 32) * BVG_GENE_TILE, 32, 2 * BVG_GENE_TILE));
   BVG_TRY(make_map(&t->tmF1, t->F1, true, 64, (uint64_t)f->Mpad, 64, 64));
   BVG_TRY(make_map(&t->tmF2, t->F2, true, 64, (uint64_t)f->Mpad, 64, 64));
   BVG_TRY(make_map(&t->tmT1, t->T1, true, (uint64_t)f->Mpad, 32, (uint64_t)f->Mpad, 32));
@@ -543,6 +555,7 @@ int launch_lik_tc(bvg_fit *f, bool bwd) {
   a.Ppart = (float *)m.Ppart; a.Spart = (float *)m.Spart;
   a.C = (const float *)m.C;  // k_prep writes the fp32 coefficient rows [Gpad][32] here
   a.nk1 = (m.k + 1 + 15) / 16;
+  a.nch32 = (int)(f->ldY / 32);
   a.M = m.M; a.G = m.G; a.Gpad = m.Gpad; a.KP = m.KP;
   a.nchunks = (int)((m.M + TC_CHUNK - 1) / TC_CHUNK);
   a.cps = (a.nchunks + m.nsplit - 1) / m.nsplit;

@@ -25,6 +25,26 @@ template int stage_y<double, float>(const double *, float *, int64_t, int64_t, i
 template int stage_y<int32_t, double>(const int32_t *, double *, int64_t, int64_t, int64_t, cudaStream_t);
 template int stage_y<int32_t, float>(const int32_t *, float *, int64_t, int64_t, int64_t, cudaStream_t);
 
+// tile-major layout for the tcgen05 engine: dst[((tile*nch32 + c32)*128 + r)*32 + i], gene = 128*tile + r,
+// spot = 32*c32 + i (dst is zero-filled beforehand: padded genes / spots stay zero)
+template <typename SRC>
+__global__ void k_stage_y_tiled(const SRC *__restrict__ src, float *__restrict__ dst, int64_t M, int64_t ldY, int64_t g0, int64_t ngenes) {
+  const int64_t n = ngenes * M, nch32 = ldY / 32;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t gl = i / M, s = i - gl * M, g = g0 + gl;
+    const int64_t tile = g / BVG_GENE_TILE, r = g - tile * BVG_GENE_TILE, c32 = s / 32, w = s - c32 * 32;
+    dst[((tile * nch32 + c32) * BVG_GENE_TILE + r) * 32 + w] = (float)src[i];
+  }
+}
+template <typename SRC>
+int stage_y_tiled(const SRC *src, float *dst, int64_t M, int64_t ldY, int64_t g0, int64_t ngenes, cudaStream_t st) {
+  k_stage_y_tiled<SRC><<<148 * 16, 256, 0, st>>>(src, dst, M, ldY, g0, ngenes);
+  CUDA_TRY(cudaGetLastError());
+  return BVG_OK;
+}
+template int stage_y_tiled<double>(const double *, float *, int64_t, int64_t, int64_t, int64_t, cudaStream_t);
+template int stage_y_tiled<int32_t>(const int32_t *, float *, int64_t, int64_t, int64_t, int64_t, cudaStream_t);
+
 // Phi (M x k col-major fp64) -> Phi' [Mpad][KP] row-major with the ones column at index k
 template <typename T>
 __global__ void k_stage_phi(const double *__restrict__ phi, T *__restrict__ out, int64_t M, int64_t Mpad, int k, int KP) {
