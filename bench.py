@@ -261,6 +261,29 @@ def run_ours(args, rank, world, local_rank):
                     "sec_sga": s3["sec_sga"], "sec_draws": s3["sec_draws"], "converged": s3["converged"]}
         f3.close()
 
+    # ---- the same kernel on an input that does NOT fit in L2: one config-4 shard (50,000 spots x 1,250 genes =
+    # what each of 8 GPUs holds at 50k x 10k; Y = 250 MB), back-to-back launches, no flush needed ----
+    roofline_large = None
+    if world == 1 and not args.skip_large:
+        from bayesvg_b200 import synth
+        Ml, Gl = 50000, 1250
+        Xl = synth.scale_coords(synth.random_points(Ml, 1))
+        Cl = synth.det_kmeans(Xl, K_BASIS, 312, iters=30)
+        from bayesvg_b200.api import length_scale_kmeans
+        phil = bvg.basis_build(Xl, Cl, length_scale_kmeans(Cl), "matern", 1.5, device=local_rank)
+        Yl, _ = synth.expression(phil, Gl, "gaussian", 312)
+        fl = bvg.Fit(phil, Yl, "gaussian", "fast", args.engine, **cfg)
+        fl.set_variational(np.zeros(fl.D), None)
+        fl.advi_steps(5, 0.1, reset=True)
+        ms_l = fl.time_lik_kernel(20, False, True)
+        ms_eval_l = fl.advi_steps(50, 0.1) / 50
+        bl = 4 * Ml * Gl + 4 * Ml * K_BASIS + 8 * K_BASIS * Gl
+        roofline_large = {"workload": "one cfg4 shard: 50,000 spots x 1,250 genes (Y = 250 MB > L2), k=20 Matern-1.5",
+                          "bound": "hbm", "achieved": bl / (ms_l * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                          "frac": bl / (ms_l * 1e-3) / 1e9 / peak, "ms_per_launch": ms_l,
+                          "algorithmic_bytes_per_launch": bl, "ms_per_elbo_grad_eval": ms_eval_l}
+        fl.close()
+
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
         nthreads = os.cpu_count() or 1
@@ -280,7 +303,7 @@ def run_ours(args, rank, world, local_rank):
                               "the 60 MB Y as the real fit does" if not args.no_flush else "no flush"),
                        "genes_total": G_GENES * world},
             "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-            "cpu_baseline": cpu, "fit": fit_info,
+            "roofline_input_larger_than_l2": roofline_large, "cpu_baseline": cpu, "fit": fit_info,
         }))
     if world > 1:
         import torch.distributed as td
@@ -300,6 +323,7 @@ def main():
     ap.add_argument("--pin", action="store_true", default=True)
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-fit", action="store_true")
+    ap.add_argument("--skip-large", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
