@@ -33,7 +33,7 @@ class Config(C.Structure):
         ("n_draws", C.c_int32), ("elbo_samples", C.c_int32), ("eval_elbo", C.c_int32), ("adapt_iter", C.c_int32),
         ("lbfgs_history", C.c_int32), ("verbose", C.c_int32), ("tol_rel_obj", C.c_double), ("eta", C.c_double),
         ("seed", C.c_uint64), ("rank", C.c_int32), ("world_size", C.c_int32), ("gene_offset", C.c_int64),
-        ("G_total", C.c_int64),
+        ("G_total", C.c_int64), ("elbo_suffstat", C.c_int32), ("reserved", C.c_int32),
     ]
 
 

@@ -92,6 +92,7 @@ extern "C" int bvg_fit_create(const bvg_config *cfg, bvg_fit **out) {
 
 static void free_model(bvg_fit *f) {
   tc_destroy(f);
+  suff_destroy(f);
   cudaFree(f->Y); cudaFree(f->Phi); cudaFree(f->dvec); cudaFree(f->summary); cudaFree(f->draws);
   cudaFree(f->m.C); cudaFree(f->m.Ppart); cudaFree(f->m.Spart); cudaFree(f->m.blk); cudaFree(f->m.ctl);
   cudaFree((void *)f->m.hist_val);
@@ -215,6 +216,7 @@ static int set_y_impl(bvg_fit *f, const SRC *y, int64_t M, int64_t G) {
   f->m.G = G;
   BVG_TRY(resolve_engine(f));
   const bool tiled = f->engine == BVG_ENGINE_TCGEN05;
+  f->tiledY = tiled;
   f->ldY = fp64 ? M : round_up(M, 64);
   const size_t ts = fp64 ? 8 : 4;
   // tcgen05 engine: Y is stored TILE-MAJOR, [gene tile][32-spot chunk][128 genes][32 spots], so that every
@@ -338,6 +340,26 @@ static int advi_steps(bvg_fit *f, int n) {
 static int advi_elbo(bvg_fit *f, int S, double *out) {
   Ctl h;
   BVG_TRY(ctl_get(f, &h));
+  if (f->cfg.elbo_suffstat && f->cfg.likelihood == BVG_GAUSSIAN) {
+    // all S draws in two launches, from per-gene sufficient statistics (k_suff.cu)
+    std::vector<double> lps(S);
+    BVG_TRY(suff_elbo(f, S, lps.data()));
+    const int64_t D = f->m.L.D;
+    BVG_TRY(vec_dot_sum(f->stream, f->m.omega, nullptr, f->scratch + D, D, f->m.tot));
+    BVG_TRY(comm_allreduce(f, f->m.tot, 2));
+    double hs[2];
+    CUDA_TRY(cudaMemcpyAsync(hs, f->m.tot, sizeof(hs), cudaMemcpyDeviceToHost, f->stream));
+    h.t_elbo += (uint32_t)S;
+    BVG_TRY(ctl_set(f, h));
+    f->st.elbo_evals++;
+    double acc = 0;
+    int ok = 0;
+    for (double v : lps) if (std::isfinite(v)) { acc += v; ++ok; }
+    if (!ok) { *out = -INFINITY; return BVG_OK; }
+    *out = acc / ok + 0.5 * (double)f->m.LG.D * (1.0 + BVG_LOG_TWO_PI) + hs[1];
+    if (std::isnan(*out)) *out = -INFINITY;
+    return BVG_OK;
+  }
   h.elbo_acc = 0; h.elbo_ok = 0;
   BVG_TRY(ctl_set(f, h));
   for (int s = 0; s < S; ++s) BVG_TRY(eval_log_prob_device(f, MODE_ELBO_DRAW, 1, 0, false));

@@ -91,6 +91,9 @@ struct DevModel {
   const double *hist_val;    // nb: value c
   const double *hist_cnt;    // nb: #pairs with y == c
   double lgam_y1;            // nb: sum lgamma(y+1) over local pairs
+  const double *suffU;       // [G][k+1] Phi'^T y_g   (sufficient-statistic ELBO, gaussian)
+  const double *suffS2;      // [G] sum_s y^2
+  const double *suffGram;    // [(k+1)^2] Phi'^T Phi'
   long long *dbg;            // diagnostics: %globaltimer stamps (NULL unless bvg_debug_* is running)
 };
 
@@ -166,6 +169,8 @@ struct bvg_fit {
   bvg_fit_stats st;
   // tcgen05 engine state (k_lik_tc.cu)
   void *tc;
+  double *suff;        // sufficient statistics + scratch (k_suff.cu), lazily built
+  bool tiledY;         // Y is stored tile-major (tcgen05 engine)
   // comm
   NcclApi *nccl;
   void *comm;
@@ -196,5 +201,7 @@ int tc_setup(bvg_fit *f);                                    // build TMA descri
 void tc_destroy(bvg_fit *f);
 int launch_gene_finish(bvg_fit *f, int mode, int jacobian, int propto);  // per-gene backward (+ update) + cross-gene finish
 int comm_allreduce(bvg_fit *f, double *buf, int n);          // comm.cu
+int suff_elbo(bvg_fit *f, int S, double *lps_host);          // k_suff.cu: S log densities from sufficient statistics
+void suff_destroy(bvg_fit *f);
 enum { MODE_GRAD_OUT = 0, MODE_ADVI_UPDATE = 1, MODE_ELBO_DRAW = 2, MODE_LP_ONLY = 3 };
 enum { PREP_NONE = 0, PREP_GRAD = 1, PREP_ELBO = 2 };

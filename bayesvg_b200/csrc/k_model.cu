@@ -251,7 +251,8 @@ __global__ void __launch_bounds__(512) k_finish(DevModel m, int mode, int jac, i
 // k_gene: one warp per gene (lane j < k: z_alpha_t[j,g]; lane k: z_beta0[g]; lane k+1: amplitude[g]).
 // Everything a gene needs is requested up front (8 split partials in flight per lane, the lane's own
 // zeta / mu / omega / step-size history) so the warp pays ~2 L2 round trips, not one per load.
-// fuse != 0 (single-GPU): the last CTA to retire also runs finish_body, saving a launch per evaluation.
+// The last CTA to retire also runs finish_body (fuse = 3: everything; fuse = 1, multi-GPU: only the
+// cross-block reduction, because the NCCL all-reduce of tot[] comes next), saving a launch per evaluation.
 template <typename T>
 __global__ void __launch_bounds__(512) k_gene(DevModel m, int mode, int jac, int propto, int fuse) {
   extern __shared__ double sm[];  // [nwarps][NS]
@@ -355,23 +356,21 @@ __global__ void __launch_bounds__(512) k_gene(DevModel m, int mode, int jac, int
   if (!s_last) return;
   __threadfence();
   DBG(4);
-  finish_body(m, mode, jac, propto, 3);
+  finish_body(m, mode, jac, propto, fuse);  // fuse = 3: reduce + finish; fuse = 1 (multi-GPU): reduce only, the all-reduce follows
   DBG(7);
 }
 
 int launch_gene_finish(bvg_fit *f, int mode, int jac, int propto) {
   const int wpb = 16;
   const size_t sh = sizeof(double) * wpb * bvg_ns(f->m.k);
-  const int fuse = f->comm ? 0 : 1;
+  const int fuse = f->comm ? 1 : 3;
   if (f->cfg.precision == BVG_PREC_FP64) CUDA_TRY(launch_pdl(k_gene<double>, dim3(f->m.nblk_gene), dim3(wpb * 32), sh, f->stream, f->m, mode, jac, propto, fuse));
   else CUDA_TRY(launch_pdl(k_gene<float>, dim3(f->m.nblk_gene), dim3(wpb * 32), sh, f->stream, f->m, mode, jac, propto, fuse));
   f->st.kernel_launches++;
-  if (!fuse) {
-    k_finish<<<1, 512, 0, f->stream>>>(f->m, mode, jac, propto, 1);
-    CUDA_TRY(cudaGetLastError());
+  if (fuse == 1) {
     BVG_TRY(comm_allreduce(f, f->m.tot, bvg_ns(f->m.k)));
     k_finish<<<1, 512, 0, f->stream>>>(f->m, mode, jac, propto, 2);
-    f->st.kernel_launches += 2;
+    f->st.kernel_launches += 1;
     CUDA_TRY(cudaGetLastError());
   }
   return BVG_OK;

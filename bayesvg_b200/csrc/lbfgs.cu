@@ -106,26 +106,26 @@ int lbfgs_run(bvg_fit *f, const double *d_theta0, double *d_out) {
   x0 = B + (size_t)nb * D; p = x0 + D; w = p + D; part = w + D; dots = part + (size_t)nb * VEC_NCHUNK * 3; scal = dots + nb * 3;
   double *g0 = B + (size_t)(2 * mh) * D;  // the gradient row of the basis
   int rc = BVG_OK;
-  auto fail = [&](int code) { cudaFree(B); return code; };
+  double *h_scal = nullptr;  // pinned: [0] grad.p, [1] sum grad, [2] lp  -- one small D2H per evaluation
+  auto fail = [&](int code) { cudaFree(B); cudaFreeHost(h_scal); return code; };
+  if (cudaMallocHost(&h_scal, 4 * sizeof(double)) != cudaSuccess) { bvg_set_error("cudaMallocHost failed"); return fail(BVG_ERR_CUDA); }
   if ((rc = vec_make_weights(st, w, m, f->cfg.rank)) != BVG_OK) return fail(rc);
   if (d_theta0) CUDA_TRY(cudaMemcpyAsync(x0, d_theta0, D * sizeof(double), cudaMemcpyDeviceToDevice, st));
 
   int fevals = 0;
-  double h_scal[2];
-  Ctl h_ctl;
   // f(x0 + alpha p) and its directional derivative; leaves x in m.zeta and grad(lp) in m.grad
   EvalFn ev = [&](double alpha, double *fv, double *dg) -> int {
     if (vec_axpy_to(st, m.zeta, x0, alpha, p, D) != BVG_OK) return 2;
     if (eval_log_prob_device(f, MODE_GRAD_OUT, 0, 0, true) != BVG_OK) return 2;
     if (vec_dot_sum(st, m.grad, p, w, D, scal) != BVG_OK) return 2;
     if (f->comm && comm_allreduce(f, scal, 2) != BVG_OK) return 2;
-    if (cudaMemcpyAsync(h_scal, scal, 2 * sizeof(double), cudaMemcpyDeviceToHost, st) != cudaSuccess) return 2;
-    if (cudaMemcpyAsync(&h_ctl, m.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, st) != cudaSuccess) return 2;
+    if (cudaMemcpyAsync(scal + 2, &m.ctl->lp, sizeof(double), cudaMemcpyDeviceToDevice, st) != cudaSuccess) return 2;
+    if (cudaMemcpyAsync(h_scal, scal, 3 * sizeof(double), cudaMemcpyDeviceToHost, st) != cudaSuccess) return 2;
     if (cudaStreamSynchronize(st) != cudaSuccess) return 2;
     ++fevals;
-    *fv = -h_ctl.lp;
+    *fv = -h_scal[2];
     *dg = -h_scal[0];
-    return (std::isfinite(h_ctl.lp) && std::isfinite(h_scal[0]) && std::isfinite(h_scal[1])) ? 0 : 1;
+    return (std::isfinite(h_scal[2]) && std::isfinite(h_scal[0]) && std::isfinite(h_scal[1])) ? 0 : 1;
   };
 
   std::vector<double> Gm((size_t)nb * nb, 0.0), hd((size_t)nb * 3), delta(nb), al(mh);
@@ -237,5 +237,6 @@ int lbfgs_run(bvg_fit *f, const double *d_theta0, double *d_out) {
   f->st.mle_term = term;
   f->st.mle_lp = -fk;
   cudaFree(B);
+  cudaFreeHost(h_scal);
   return BVG_OK;
 }

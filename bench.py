@@ -260,6 +260,15 @@ def run_ours(args, rank, world, local_rank):
                     "mle_fevals": s3["mle_fevals"], "sec_mle": s3["sec_mle"], "sec_adapt": s3["sec_adapt"],
                     "sec_sga": s3["sec_sga"], "sec_draws": s3["sec_draws"], "converged": s3["converged"]}
         f3.close()
+        # separately reported fast path: forward-only ELBO estimates from sufficient statistics (gaussian)
+        t0 = time.perf_counter()
+        f4 = bvg.Fit(phi, Y, "gaussian", "fast", args.engine, elbo_suffstat=1, **cfg)
+        f4.run()
+        s4 = f4.stats()
+        fit_info["suffstat_elbo"] = {"wall_s": time.perf_counter() - t0, "sec_mle": s4["sec_mle"], "sec_adapt": s4["sec_adapt"],
+                                     "sec_sga": s4["sec_sga"], "advi_iters": s4["advi_iters"], "eta": s4["eta"],
+                                     "elbo": s4["elbo"], "elbo_dense": s3["elbo"]}
+        f4.close()
 
     # ---- the same kernel on an input that does NOT fit in L2: one config-4 shard (50,000 spots x 1,250 genes =
     # what each of 8 GPUs holds at 50k x 10k; Y = 250 MB), back-to-back launches, no flush needed ----

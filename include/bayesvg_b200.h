@@ -72,6 +72,11 @@ typedef struct {
   /* gene sharding: this process holds genes [gene_offset, gene_offset + G) of G_total */
   int32_t rank, world_size;
   int64_t gene_offset, G_total; /* G_total = 0 -> unsharded */
+  /* gaussian only, default 0: evaluate the forward-only ELBO estimates (150 draws every 100 iterations) from
+   * per-gene sufficient statistics (sum y^2, Phi'^T y, Phi'^T Phi') instead of 150 dense passes over Y.
+   * Same value up to round-off; the gradient path is always the dense kernel. */
+  int32_t elbo_suffstat;
+  int32_t reserved;
 } bvg_config;
 
 typedef struct bvg_fit bvg_fit;

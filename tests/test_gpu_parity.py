@@ -95,6 +95,31 @@ def test_advi_trajectory_matches_oracle_fp64(lik):
     f.close()
 
 
+@pytest.mark.parametrize("prec,eng", ENGINES)
+@pytest.mark.parametrize("M,G,k", [(300, 50, 6), (1000, 257, 20)])
+def test_sufficient_statistic_elbo_equals_dense_elbo(prec, eng, M, G, k):
+    """gaussian: the forward-only ELBO estimate from (sum y^2, Phi'^T y, Phi'^T Phi') must equal the dense
+    pass over Y (same Philox draws) and the oracle's"""
+    p = make_problem(M, G, k, "gaussian", seed=17)
+    o = orc.Oracle(p["phi"], p["y"], "gaussian", nthreads=4)
+    rng = np.random.default_rng(2)
+    mu, om = rng.normal(0, 0.2, o.D), rng.normal(-2, 0.3, o.D)
+    fd = _fit(p["phi"], p["y"], "gaussian", prec, eng, seed=5)
+    fs = _fit(p["phi"], p["y"], "gaussian", prec, eng, seed=5, elbo_suffstat=1)
+    for f in (fd, fs):
+        f.set_variational(mu, om)
+        f.advi_steps(0, 0.1, reset=True)
+    ref = o.elbo(mu, om, 40, 5, 0)
+    ed, es = fd.elbo(40)[0], fs.elbo(40)[0]
+    tol = 1e-10 if prec == "fp64" else 2e-6
+    assert es == pytest.approx(ref, rel=tol) and ed == pytest.approx(ref, rel=tol)
+    # the draw counter advanced identically: a second estimate uses draws 40..79 on both paths
+    assert fs.elbo(40)[0] == pytest.approx(fd.elbo(40)[0], rel=tol)
+    assert fs.elbo(40)[0] == pytest.approx(o.elbo(mu, om, 40, 5, 80), rel=tol)
+    fd.close()
+    fs.close()
+
+
 @pytest.mark.parametrize("prec,eng", ENGINES[1:])
 def test_advi_trajectory_fast_path(prec, eng):
     p = make_problem(400, 150, 20, "gaussian", seed=12)
