@@ -72,6 +72,19 @@ struct Ctl {
   uint32_t ticket;   // last-block-done counter of k_gene (fused finish)
 };
 
+// ---- peer-memory exchange (multi-GPU) ------------------------------------------
+// Every rank owns one exchange buffer, mapped into every peer with CUDA IPC (one process per GPU).
+// Layout: cells[2 parities][world ranks][2 * BVG_PEER_CAP] of 8-byte cells {32 data bits, 32-bit
+// sequence number}: a cell is valid exactly when its flag equals the current sequence number, so one
+// 8-byte store over NVLink carries data + arrival flag and no fence / second round trip is needed.
+#define BVG_MAX_PEERS 8
+#define BVG_PEER_CAP 1024  // doubles per exchange
+struct PeerCtx {
+  int world, rank;
+  uint32_t *seq;                 // exchanges completed so far (advances in lockstep on every rank)
+  uint2 *cells[BVG_MAX_PEERS];   // cells[r] = rank r's exchange buffer as mapped here (cells[rank] is local)
+};
+
 struct DevModel {
   int lik, k, KP, nsplit;
   int64_t M, G, Gpad, gene_offset, G_total;
@@ -95,7 +108,57 @@ struct DevModel {
   const double *suffS2;      // [G] sum_s y^2
   const double *suffGram;    // [(k+1)^2] Phi'^T Phi'
   long long *dbg;            // diagnostics: %globaltimer stamps (NULL unless bvg_debug_* is running)
+  PeerCtx peer;              // world <= 1: no in-kernel exchange
 };
+
+// Sum-all-reduce of vals[0..n) (global memory, n <= min(BVG_PEER_CAP, blockDim.x)) across the ranks of p,
+// executed by ALL threads of ONE CTA.  Push: every 8-byte cell goes straight into each peer's buffer;
+// pull: poll the local buffer until every peer's cells carry this exchange's sequence number.  The sum
+// runs in rank order on every rank, so all ranks end with bit-identical results (the replicated
+// gene-shared parameters stay identical without a broadcast).  Parity double-buffering is enough: a
+// rank can only be one exchange ahead of a peer it is waiting for.
+__device__ inline void peer_allreduce_cta(const PeerCtx &p, double *vals, int n) {
+  __shared__ uint32_t s_seq;
+  __syncthreads();  // the caller's writes to vals[] (same CTA) are visible
+  if (threadIdx.x == 0) s_seq = *p.seq + 1;
+  __syncthreads();
+  const uint32_t seq = s_seq;
+  const size_t per_rank = 2 * BVG_PEER_CAP, slot = (size_t)(seq & 1u) * p.world * per_rank;
+  for (int i = threadIdx.x; i < 2 * n; i += blockDim.x) {
+    const double v = vals[i >> 1];
+    const uint32_t half = (i & 1) ? (uint32_t)__double2hiint(v) : (uint32_t)__double2loint(v);
+    for (int r = 0; r < p.world; ++r) {
+      if (r == p.rank) continue;
+      uint2 *dst = p.cells[r] + slot + (size_t)p.rank * per_rank + i;
+      asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(half), "r"(seq) : "memory");
+    }
+  }
+  double s = 0.0;
+  const int c = threadIdx.x;
+  if (c < n) {
+    const long long t0 = clock64();
+    for (int r = 0; r < p.world; ++r) {
+      double v;
+      if (r == p.rank) v = vals[c];
+      else {
+        const uint2 *src = p.cells[p.rank] + slot + (size_t)r * per_rank + 2 * c;
+        uint32_t lo, fl, hi, fh;
+        for (;;) {
+          asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(fl) : "l"(src) : "memory");
+          asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(hi), "=r"(fh) : "l"(src + 1) : "memory");
+          if (fl == seq && fh == seq) break;
+          if (clock64() - t0 > 40000000000LL) __trap();  // ~20 s: a peer never arrived -> fail instead of hanging the GPU
+        }
+        v = __hiloint2double((int)hi, (int)lo);
+      }
+      s += v;
+    }
+  }
+  __syncthreads();  // every push has read vals[] before it is overwritten
+  if (c < n) vals[c] = s;
+  if (threadIdx.x == 0) *p.seq = seq;
+  __syncthreads();
+}
 
 // ---- Philox4x32-10 + Box-Muller: the RNG specification of DESIGN.md section 5 ----------------
 __host__ __device__ inline void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
@@ -171,9 +234,12 @@ struct bvg_fit {
   void *tc;
   double *suff;        // sufficient statistics + scratch (k_suff.cu), lazily built
   bool tiledY;         // Y is stored tile-major (tcgen05 engine)
-  // comm
+  // comm: 0 = single GPU, 1 = NCCL all-reduce between kernels, 2 = in-kernel exchange over peer memory
+  int comm_mode;
   NcclApi *nccl;
   void *comm;
+  void *peer_buf;      // this rank's exchange buffer (cudaMalloc, exported with cudaIpcGetMemHandle)
+  void *peer_map[BVG_MAX_PEERS];  // peers' buffers opened with cudaIpcOpenMemHandle
 };
 
 void bvg_set_error(const char *fmt, ...);

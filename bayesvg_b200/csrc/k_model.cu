@@ -175,6 +175,9 @@ __device__ void finish_body(const DevModel &m, int mode, int jac, int propto, in
     }
   }
   if (!(phase & 2)) return;
+  // multi-GPU, fused: the cross-gene sums of every gene shard meet here, inside the kernel that produced
+  // them -- stores into the peers' exchange buffers over NVLink, no extra launch (bvg_internal.cuh)
+  if ((phase & 1) && m.peer.world > 1) peer_allreduce_cta(m.peer, m.tot, NS);
   const double *tot = m.tot;
   const double mb = zt[L.mu_beta0], lsb = zt[L.sigma_beta0], sb = m.shx[0];
   const double ma = zt[L.mu_amp], lsa = zt[L.sigma_amp], sa = m.shx[1];
@@ -363,7 +366,9 @@ __global__ void __launch_bounds__(512) k_gene(DevModel m, int mode, int jac, int
 int launch_gene_finish(bvg_fit *f, int mode, int jac, int propto) {
   const int wpb = 16;
   const size_t sh = sizeof(double) * wpb * bvg_ns(f->m.k);
-  const int fuse = f->comm ? 1 : 3;
+  // single GPU or peer-memory exchange: everything in one launch; NCCL (or k > 251): reduce, all-reduce, finish
+  const bool split = f->comm_mode == 1 || (f->comm_mode == 2 && bvg_ns(f->m.k) > wpb * 32);
+  const int fuse = split ? 1 : 3;
   if (f->cfg.precision == BVG_PREC_FP64) CUDA_TRY(launch_pdl(k_gene<double>, dim3(f->m.nblk_gene), dim3(wpb * 32), sh, f->stream, f->m, mode, jac, propto, fuse));
   else CUDA_TRY(launch_pdl(k_gene<float>, dim3(f->m.nblk_gene), dim3(wpb * 32), sh, f->stream, f->m, mode, jac, propto, fuse));
   f->st.kernel_launches++;

@@ -206,7 +206,7 @@ int suff_elbo(bvg_fit *f, int S, double *lps_host) {
   const int k = m.k;
   const size_t sh = sizeof(double) * (3 * k + 5 + st->gpb * (k + 2) + st->gpb + 2 * st->gpb * (k + 1) + 8);
   k_suff_elbo<<<dim3(st->nblk, S), 256, sh, f->stream>>>(m, st->gpb, st->part);
-  if (f->comm) {
+  if (f->comm_mode) {
     k_suff_finish<<<S, 128, 0, f->stream>>>(m, st->nblk, st->part, st->tot4, st->lps, 1);
     BVG_TRY(comm_allreduce(f, st->tot4, 4 * S));
     k_suff_finish<<<S, 128, 0, f->stream>>>(m, st->nblk, st->part, st->tot4, st->lps, 2);

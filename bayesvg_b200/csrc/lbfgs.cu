@@ -118,7 +118,7 @@ int lbfgs_run(bvg_fit *f, const double *d_theta0, double *d_out) {
     if (vec_axpy_to(st, m.zeta, x0, alpha, p, D) != BVG_OK) return 2;
     if (eval_log_prob_device(f, MODE_GRAD_OUT, 0, 0, true) != BVG_OK) return 2;
     if (vec_dot_sum(st, m.grad, p, w, D, scal) != BVG_OK) return 2;
-    if (f->comm && comm_allreduce(f, scal, 2) != BVG_OK) return 2;
+    if (f->comm_mode && comm_allreduce(f, scal, 2) != BVG_OK) return 2;
     if (cudaMemcpyAsync(scal + 2, &m.ctl->lp, sizeof(double), cudaMemcpyDeviceToDevice, st) != cudaSuccess) return 2;
     if (cudaMemcpyAsync(h_scal, scal, 3 * sizeof(double), cudaMemcpyDeviceToHost, st) != cudaSuccess) return 2;
     if (cudaStreamSynchronize(st) != cudaSuccess) return 2;
@@ -135,7 +135,7 @@ int lbfgs_run(bvg_fit *f, const double *d_theta0, double *d_out) {
   if ((rc = vec_accept(st, nullptr, nullptr, x0, g0, m.zeta, m.grad, D)) != BVG_OK) return fail(rc);
   CUDA_TRY(cudaMemcpyAsync(p, m.grad, D * sizeof(double), cudaMemcpyDeviceToDevice, st));
   if ((rc = vec_dot_sum(st, g0, g0, w, D, scal)) != BVG_OK) return fail(rc);
-  if (f->comm && (rc = comm_allreduce(f, scal, 2)) != BVG_OK) return fail(rc);
+  if (f->comm_mode && (rc = comm_allreduce(f, scal, 2)) != BVG_OK) return fail(rc);
   CUDA_TRY(cudaMemcpyAsync(h_scal, scal, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
   double gg = h_scal[0];   // g.g
@@ -180,7 +180,7 @@ int lbfgs_run(bvg_fit *f, const double *d_theta0, double *d_out) {
       nh = 0;
     }
     if ((rc = vec_multidot3(st, B, D, nb, head, mh + head, 2 * mh, w, part, dots)) != BVG_OK) return fail(rc);
-    if (f->comm && (rc = comm_allreduce(f, dots, nb * 3)) != BVG_OK) return fail(rc);
+    if (f->comm_mode && (rc = comm_allreduce(f, dots, nb * 3)) != BVG_OK) return fail(rc);
     CUDA_TRY(cudaMemcpyAsync(hd.data(), dots, nb * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     const int rs = head, ry = mh + head, rg = 2 * mh;

@@ -1,7 +1,8 @@
 """Gene sharding across GPUs: one process per GPU (torchrun), contiguous gene ranges, one
-all-reduce of 2k+10 doubles per evaluation inside the library (NCCL, csrc/comm.cu).
-torch.distributed is used only as plumbing: to broadcast the NCCL unique id and gather the
-per-shard summary tables."""
+all-reduce of 2k+10 doubles per evaluation inside the library (csrc/comm.cu): by default fused into
+the per-gene kernel over CUDA-IPC peer memory (NVLink), optionally NCCL between kernels.
+torch.distributed is used only as plumbing: to exchange the IPC handles / the NCCL unique id and to
+gather the per-shard summary tables."""
 from dataclasses import dataclass
 
 import numpy as np
@@ -34,24 +35,42 @@ def _bcast_bytes(b, src=0):
     return bytes(t.cpu().tolist())
 
 
-def make_sharded_fit(phi, Y_local, shard, G_total, gene_offset, likelihood, precision, engine, cfg):
-    """Create this rank's Fit and join the NCCL communicator (collective: every rank must call)."""
+def _allgather_bytes(b):
+    """every rank contributes len(b) bytes; returns the concatenation in rank order"""
+    import torch
+    import torch.distributed as td
+    dev = "cuda" if td.get_backend() == "nccl" else "cpu"
+    mine = torch.tensor(list(b), dtype=torch.uint8, device=dev)
+    out = [torch.zeros_like(mine) for _ in range(td.get_world_size())]
+    td.all_gather(out, mine)
+    return b"".join(bytes(t.cpu().tolist()) for t in out)
+
+
+def make_sharded_fit(phi, Y_local, shard, G_total, gene_offset, likelihood, precision, engine, cfg, comm="peer"):
+    """Create this rank's Fit and connect it to the other shards (collective: every rank must call).
+    comm = "peer": in-kernel all-reduce over CUDA-IPC peer memory; "nccl": ncclAllReduce between kernels."""
     from . import engine as E
-    uid = E.comm_unique_id() if shard.rank == 0 else b""
-    uid = _bcast_bytes(uid)[:128]
+    if comm not in ("peer", "nccl"):
+        raise ValueError("comm must be 'peer' or 'nccl'")
     fit = E.Fit(phi, Y_local, likelihood, precision, engine, rank=shard.rank, world_size=shard.world_size,
                 gene_offset=gene_offset, G_total=G_total, **cfg)
-    fit.comm_init(uid)
+    if shard.world_size == 1:
+        return fit
+    if comm == "peer":
+        fit.peer_init(_allgather_bytes(fit.peer_handle()))
+    else:
+        uid = E.comm_unique_id() if shard.rank == 0 else b""
+        fit.comm_init(_bcast_bytes(uid)[:128])
     return fit
 
 
-def fit_sharded(phi, Y, shard, likelihood, precision, engine, cfg):
+def fit_sharded(phi, Y, shard, likelihood, precision, engine, cfg, comm="peer"):
     """Y: full M x G on every rank (each keeps its slice).  Returns the gathered G x 8 table."""
     import torch
     import torch.distributed as td
     G = Y.shape[1]
     g0, g1 = shard.gene_range(G)
-    fit = make_sharded_fit(phi, np.asfortranarray(Y[:, g0:g1]), shard, G, g0, likelihood, precision, engine, cfg)
+    fit = make_sharded_fit(phi, np.asfortranarray(Y[:, g0:g1]), shard, G, g0, likelihood, precision, engine, cfg, comm)
     local = fit.run()
     fit.close()
     dev = "cuda" if td.get_backend() == "nccl" else "cpu"

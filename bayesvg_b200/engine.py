@@ -78,6 +78,16 @@ class Fit:
         buf = C.create_string_buffer(unique_id, len(unique_id))
         B.check(B.lib().bvg_fit_comm_init(self._h, C.cast(buf, C.c_void_p), len(unique_id)))
 
+    def peer_handle(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        n = C.c_size_t()
+        B.check(B.lib().bvg_fit_peer_handle(self._h, C.cast(buf, C.c_void_p), 64, C.byref(n)))
+        return buf.raw[: n.value]
+
+    def peer_init(self, handles: bytes):
+        buf = C.create_string_buffer(handles, len(handles))
+        B.check(B.lib().bvg_fit_peer_init(self._h, C.cast(buf, C.c_void_p), len(handles)))
+
     def log_prob(self, theta, jacobian=True, propto=True, grad=True):
         th = np.ascontiguousarray(theta, dtype=np.float64)
         if th.shape != (self.D,):

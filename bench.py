@@ -10,7 +10,8 @@ spot x gene pairs (forward + analytic backward) and the mean-field update.
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
 N > 1 (torchrun, one rank per GPU): weak scaling -- every rank holds its own 3,000 genes (G_total =
-3,000 N), the 2k+10 cross-gene sums are all-reduced (NCCL) inside every evaluation, and `value` counts
+3,000 N), the 2k+10 cross-gene sums are all-reduced inside every evaluation (--comm peer: fused into the
+per-gene kernel over peer memory; --comm nccl: ncclAllReduce between kernels), and `value` counts
 3,000-gene evaluations (N per global evaluation).
 
 --impl reference times the reference's CPU path.  The reference is R + CmdStan, neither of which
@@ -162,7 +163,7 @@ def run_ours(args, rank, world, local_rank):
     cfg = dict(device=local_rank, seed=312)
     if world > 1:
         fit = bdist.make_sharded_fit(phi, Y, bdist.Shard(rank, world), G_GENES * world, G_GENES * rank, "gaussian",
-                                     "fast", args.engine, cfg)
+                                     "fast", args.engine, cfg, args.comm)
     else:
         fit = bvg.Fit(phi, Y, "gaussian", "fast", args.engine, **cfg)
     D = fit.D
@@ -224,7 +225,7 @@ def run_ours(args, rank, world, local_rank):
     e2e_steps = max(2, min(args.steps, 5))
     if world > 1:   # the NCCL communicator belongs to the fit object and is created once, like a user would
         f2 = bdist.make_sharded_fit(phi, Yh, bdist.Shard(rank, world), G_GENES * world, G_GENES * rank,
-                                    "gaussian", "fast", args.engine, cfg)
+                                    "gaussian", "fast", args.engine, cfg, args.comm)
     else:
         f2 = bvg.Fit(phi, Yh, "gaussian", "fast", args.engine, **cfg)
     barrier()
@@ -310,7 +311,10 @@ def run_ours(args, rank, world, local_rank):
                        "evals_per_step": E, "engine": eng_name,
                        "l2": ("L2 flushed (512 MB write) before every timed step; inside a step the evals re-read "
                               "the 60 MB Y as the real fit does" if not args.no_flush else "no flush"),
-                       "genes_total": G_GENES * world},
+                       "genes_total": G_GENES * world,
+                       "exchange": (None if world == 1 else
+                                    ("2k+10 fp64 sums per eval, all-reduced inside k_gene's last CTA over CUDA-IPC peer memory (NVLink)"
+                                     if args.comm == "peer" else "2k+10 fp64 sums per eval, ncclAllReduce between k_gene and k_finish"))},
             "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "roofline_input_larger_than_l2": roofline_large, "cpu_baseline": cpu, "fit": fit_info,
         }))
@@ -328,6 +332,7 @@ def main():
     ap.add_argument("--evals-per-step", type=int, default=100)
     ap.add_argument("--ref-evals-per-step", type=int, default=2)
     ap.add_argument("--engine", default="auto", choices=["auto", "simt", "tcgen05"])
+    ap.add_argument("--comm", default="peer", choices=["peer", "nccl"])
     ap.add_argument("--no-flush", action="store_true")
     ap.add_argument("--pin", action="store_true", default=True)
     ap.add_argument("--skip-cpu", action="store_true")

@@ -101,8 +101,17 @@ int bvg_fit_set_y_f64(bvg_fit *, const double *y, int64_t M, int64_t G);
 int bvg_fit_set_y_i32(bvg_fit *, const int32_t *y, int64_t M, int64_t G);
 int bvg_fit_dim(bvg_fit *, int64_t *D);
 
-/* multi-GPU: rank 0 calls bvg_comm_unique_id, the host broadcasts the bytes, every rank calls
- * bvg_fit_comm_init.  NCCL is resolved with dlopen("libnccl.so.2") at that point. */
+/* multi-GPU (one process per GPU of one node; the reference has no counterpart -- its fit is one
+ * CPU thread, R/findSpatiallyVariableFeaturesBayes.R:123-129).  Two transports for the one exchange
+ * step of the path, the sum of 2k+10 cross-gene scalars per evaluation; choose ONE per fit:
+ *  - peer memory (default of the host wrapper): every rank calls bvg_fit_peer_handle (64 opaque bytes,
+ *    a CUDA IPC handle of its exchange buffer), the host all-gathers them in rank order, every rank
+ *    calls bvg_fit_peer_init.  The all-reduce then runs inside the per-gene kernel itself (stores into
+ *    the peers' buffers over NVLink), with no extra launch.
+ *  - NCCL: rank 0 calls bvg_comm_unique_id, the host broadcasts the bytes, every rank calls
+ *    bvg_fit_comm_init.  NCCL is resolved with dlopen("libnccl.so.2") at that point. */
+int bvg_fit_peer_handle(bvg_fit *, void *out, size_t cap, size_t *len);
+int bvg_fit_peer_init(bvg_fit *, const void *handles /* world_size x 64 bytes, rank order */, size_t len);
 int bvg_comm_unique_id(void *out, size_t cap, size_t *len);
 int bvg_fit_comm_init(bvg_fit *, const void *unique_id, size_t len);
 

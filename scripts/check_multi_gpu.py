@@ -1,7 +1,8 @@
 """torchrun --nproc-per-node N scripts/check_multi_gpu.py
 
-Gene-sharded fit (one rank per GPU, NCCL all-reduce of the 2k+10 cross-gene sums inside every
-evaluation) against the unsharded fit on one GPU: same log density, same gradients, and -- because
+Gene-sharded fit (one rank per GPU; the 2k+10 cross-gene sums are all-reduced inside every
+evaluation, once through the in-kernel peer-memory exchange and once through NCCL) against the
+unsharded fit on one GPU: same log density, same gradients, and -- because
 Philox counters are keyed by the GLOBAL parameter index -- the same ADVI trajectory."""
 import os
 import sys
@@ -21,7 +22,9 @@ def main():
     torch.cuda.set_device(local)
     td.init_process_group("nccl", device_id=torch.device("cuda", local))
     ok = True
-    for lik, prec, eng in (("gaussian", "fp64", "simt"), ("nb", "fp64", "simt"), ("gaussian", "fast", "tcgen05")):
+    for lik, prec, eng, comm in (("gaussian", "fp64", "simt", "peer"), ("nb", "fp64", "simt", "peer"),
+                                 ("gaussian", "fast", "tcgen05", "peer"), ("gaussian", "fp64", "simt", "nccl"),
+                                 ("nb", "fast", "tcgen05", "nccl")):
         M, G, k = 400, 301, 12
         p = make_problem(M, G, k, lik, seed=3)
         LG = dist.layout(lik, G, k)
@@ -30,7 +33,7 @@ def main():
         g0, g1 = sh.gene_range(G)
         idx = dist.shard_index(lik, G, k, g0, g1)
         cfg = dict(device=local, seed=312)
-        fs = dist.make_sharded_fit(p["phi"], np.asfortranarray(p["y"][:, g0:g1]), sh, G, g0, lik, prec, eng, cfg)
+        fs = dist.make_sharded_fit(p["phi"], np.asfortranarray(p["y"][:, g0:g1]), sh, G, g0, lik, prec, eng, cfg, comm)
         ff = bvg.Fit(p["phi"], p["y"], lik, prec, eng, **cfg)  # every rank also holds the unsharded problem
         tol = 1e-11 if prec == "fp64" else 2e-5
         lp_s, g_s = fs.log_prob(theta[idx], True, False)
@@ -52,7 +55,20 @@ def main():
         e4 = abs(el_s - el_f) / abs(el_f)
         good = max(e1, e2, e3 * (1e-3 if prec == "fast" else 1), e4) < tol * (100 if prec == "fp64" else 1)
         ok &= good
-        print(f"[rank {rank}] {lik}/{prec}/{eng}: lp {e1:.1e} grad {e2:.1e} traj {e3:.1e} elbo {e4:.1e} -> {'ok' if good else 'FAIL'}", flush=True)
+        # full fit (L-BFGS scalars, ELBO sums and the summaries all cross the same transport)
+        if prec == "fp64":
+            small = dict(cfg, n_iter=200, mle_iter=30, n_draws=200, elbo_samples=20, eta=0.1)
+            f2 = dist.make_sharded_fit(p["phi"], np.asfortranarray(p["y"][:, g0:g1]), sh, G, g0, lik, prec, eng, small, comm)
+            f1 = bvg.Fit(p["phi"], p["y"], lik, prec, eng, **small)
+            t2, t1 = f2.run(), f1.run()
+            e5 = float(np.abs(t2[:, :6] - t1[g0:g1, :6]).max() / np.abs(t1[:, :6]).max())
+            good &= e5 < 1e-5  # reduction order differs between 1 and N shards; L-BFGS + 200 SGA steps amplify round-off
+            f2.close()
+            f1.close()
+        else:
+            e5 = 0.0
+        ok &= good
+        print(f"[rank {rank}] {lik}/{prec}/{eng}/{comm}: fit {e5:.1e} lp {e1:.1e} grad {e2:.1e} traj {e3:.1e} elbo {e4:.1e} -> {'ok' if good else 'FAIL'}", flush=True)
         fs.close()
         ff.close()
     t = torch.tensor([0 if ok else 1], device="cuda")
