@@ -21,7 +21,7 @@ EXPORTS = [
     "bvg_fit_dim", "bvg_comm_unique_id", "bvg_fit_comm_init", "bvg_fit_peer_handle", "bvg_fit_peer_init", "bvg_log_prob", "bvg_fit_run", "bvg_fit_mle",
     "bvg_fit_advi", "bvg_fit_summarize", "bvg_fit_set_variational", "bvg_fit_get_variational",
     "bvg_fit_advi_steps", "bvg_fit_elbo", "bvg_fit_time_lik_kernel", "bvg_fit_flush_l2", "bvg_fit_get_summary",
-    "bvg_fit_get_draws", "bvg_fit_get_trace", "bvg_fit_get_stats", "bvg_debug_stage_times", "bvg_debug_gene_trace",
+    "bvg_fit_get_draws", "bvg_fit_get_trace", "bvg_fit_get_stats", "bvg_debug_stage_times", "bvg_debug_gene_trace", "bvg_debug_time_gene",
     "bvg_debug_tc_trace",
 ]
 
@@ -95,6 +95,9 @@ def lib():
     L.bvg_fit_elbo.argtypes = [_vp, C.c_int, _dp, _fp]
     L.bvg_fit_time_lik_kernel.argtypes = [_vp, C.c_int, C.c_int, C.c_int, _fp]
     L.bvg_fit_flush_l2.argtypes = [_vp]
+    L.bvg_debug_stage_times.argtypes = [_vp, C.c_int, _fp]
+    L.bvg_debug_time_gene.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _fp]
+    L.bvg_debug_gene_trace.argtypes = [_vp, C.POINTER(C.c_longlong), C.c_int]
     L.bvg_fit_get_summary.argtypes = [_vp, _dp]
     L.bvg_fit_get_draws.argtypes = [_vp, _dp]
     L.bvg_fit_get_trace.argtypes = [_vp, _dp, C.c_int, C.POINTER(C.c_int)]

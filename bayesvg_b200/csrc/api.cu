@@ -108,6 +108,11 @@ extern "C" void bvg_fit_destroy(bvg_fit *f) {
   free_model(f);
   cudaFree(f->phi64);
   cudaFree(f->flush);
+  cudaFree(f->stage_buf);
+  if (f->copy_stream) {
+    cudaStreamDestroy(f->copy_stream);
+    for (int b = 0; b < 2; ++b) { cudaEventDestroy(f->ev_copied[b]); cudaEventDestroy(f->ev_staged[b]); }
+  }
   delete[] f->h_theta_mle;
   cudaEventDestroy(f->ev0); cudaEventDestroy(f->ev1);
   cudaStreamDestroy(f->stream);
@@ -210,11 +215,14 @@ static int set_y_impl(bvg_fit *f, const SRC *y, int64_t M, int64_t G) {
   if (G < 1) { bvg_set_error("y must have at least one gene"); return BVG_ERR_ARG; }
   CUDA_TRY(cudaSetDevice(f->cfg.device));
   const double t0 = now_s();
-  if (f->have_y) free_model(f);
+  // same shape as the resident model (a refit on new expression values): keep every allocation, the staged
+  // basis and the tensor maps; only Y is restaged
+  const bool reuse = f->have_y && f->m.G == G && f->Y != nullptr;
+  if (f->have_y && !reuse) free_model(f);
   f->have_y = f->have_mle = f->have_vi = f->have_summary = false;
   const bool fp64 = f->cfg.precision == BVG_PREC_FP64;
   f->m.G = G;
-  BVG_TRY(resolve_engine(f));
+  if (!reuse) BVG_TRY(resolve_engine(f));
   const bool tiled = f->engine == BVG_ENGINE_TCGEN05;
   f->tiledY = tiled;
   f->ldY = fp64 ? M : round_up(M, 64);
@@ -223,22 +231,43 @@ static int set_y_impl(bvg_fit *f, const SRC *y, int64_t M, int64_t G) {
   // TMA box (and every 64-spot pipeline stage) is one contiguous 16 KB (32 KB) run of HBM instead of 128
   // separate 128-byte pieces 4*ldY bytes apart
   const size_t y_elems = tiled ? (size_t)round_up(G, BVG_GENE_TILE) * f->ldY : (size_t)G * f->ldY;
-  CUDA_TRY(cudaMalloc(&f->Y, ts * y_elems));
-  if (tiled) CUDA_TRY(cudaMemsetAsync(f->Y, 0, ts * y_elems, f->stream));
-  // stage through a bounded device buffer (host layout -> compute type + padding)
-  const int64_t genes_per_chunk = std::max<int64_t>(1, std::min<int64_t>(G, (int64_t)(128u << 20) / (M * (int64_t)sizeof(SRC))));
-  SRC *stage = nullptr;
-  CUDA_TRY(cudaMalloc(&stage, sizeof(SRC) * genes_per_chunk * M));
-  for (int64_t g0 = 0; g0 < G; g0 += genes_per_chunk) {
+  if (!reuse) {
+    CUDA_TRY(cudaMalloc(&f->Y, ts * y_elems));
+    if (tiled) CUDA_TRY(cudaMemsetAsync(f->Y, 0, ts * y_elems, f->stream));  // pads stay zero: staging writes real entries only
+  }
+  // stage through two bounded device buffers (host layout -> compute type + padding): the H2D copy of chunk
+  // i+1 runs on a second stream while chunk i is converted
+  const int64_t genes_per_chunk = std::max<int64_t>(1, std::min<int64_t>(G, (int64_t)(32u << 20) / (M * (int64_t)sizeof(SRC))));
+  const size_t stage_bytes = 2 * sizeof(SRC) * genes_per_chunk * M;
+  if (f->stage_bytes < stage_bytes) {
+    cudaFree(f->stage_buf);
+    f->stage_buf = nullptr; f->stage_bytes = 0;
+    CUDA_TRY(cudaMalloc(&f->stage_buf, stage_bytes));
+    f->stage_bytes = stage_bytes;
+  }
+  if (!f->copy_stream) {
+    CUDA_TRY(cudaStreamCreateWithFlags(&f->copy_stream, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; ++b) { CUDA_TRY(cudaEventCreateWithFlags(&f->ev_copied[b], cudaEventDisableTiming)); CUDA_TRY(cudaEventCreateWithFlags(&f->ev_staged[b], cudaEventDisableTiming)); }
+  }
+  CUDA_TRY(cudaStreamSynchronize(f->stream));  // earlier work on the compute stream no longer reads Y
+  int64_t ci = 0;
+  for (int64_t g0 = 0; g0 < G; g0 += genes_per_chunk, ++ci) {
+    const int b = (int)(ci & 1);
     const int64_t ng = std::min(genes_per_chunk, G - g0);
-    CUDA_TRY(cudaMemcpyAsync(stage, y + g0 * M, sizeof(SRC) * ng * M, cudaMemcpyHostToDevice, f->stream));
+    SRC *stage = (SRC *)f->stage_buf + (size_t)b * genes_per_chunk * M;
+    if (ci >= 2) CUDA_TRY(cudaStreamWaitEvent(f->copy_stream, f->ev_staged[b], 0));  // buffer b has been consumed
+    CUDA_TRY(cudaMemcpyAsync(stage, y + g0 * M, sizeof(SRC) * ng * M, cudaMemcpyHostToDevice, f->copy_stream));
+    CUDA_TRY(cudaEventRecord(f->ev_copied[b], f->copy_stream));
+    CUDA_TRY(cudaStreamWaitEvent(f->stream, f->ev_copied[b], 0));
     int rc;
     if (tiled) rc = stage_y_tiled<SRC>(stage, (float *)f->Y, M, f->ldY, g0, ng, f->stream);
     else if (fp64) rc = stage_y<SRC, double>(stage, (double *)f->Y + g0 * f->ldY, M, f->ldY, ng, f->stream);
     else rc = stage_y<SRC, float>(stage, (float *)f->Y + g0 * f->ldY, M, f->ldY, ng, f->stream);
-    if (rc != BVG_OK) { cudaFree(stage); return rc; }
+    if (rc != BVG_OK) return rc;
+    CUDA_TRY(cudaEventRecord(f->ev_staged[b], f->stream));
   }
-  // nb: histogram of distinct counts for the lgamma / digamma terms (they depend on y and phi_nb only)
+  // nb: histogram of distinct counts for the lgamma / digamma terms (they depend on y and phi_nb only);
+  // the host pass overlaps the copies above
   if (f->cfg.likelihood == BVG_NB) {
     std::map<int64_t, double> h;
     double lg1 = 0;
@@ -246,7 +275,7 @@ static int set_y_impl(bvg_fit *f, const SRC *y, int64_t M, int64_t G) {
     std::vector<double> dense(1 << 16, 0.0);
     for (int64_t i = 0; i < n; ++i) {
       const double v = (double)y[i];
-      if (!(v >= 0) || v != std::floor(v)) { cudaFree(stage); bvg_set_error("nb likelihood needs non-negative integer counts (found %g)", v); return BVG_ERR_ARG; }
+      if (!(v >= 0) || v != std::floor(v)) { cudaStreamSynchronize(f->copy_stream); cudaStreamSynchronize(f->stream); bvg_set_error("nb likelihood needs non-negative integer counts (found %g)", v); return BVG_ERR_ARG; }
       const int64_t c = (int64_t)v;
       if (c < (int64_t)dense.size()) dense[c] += 1.0; else h[c] += 1.0;
     }
@@ -254,6 +283,8 @@ static int set_y_impl(bvg_fit *f, const SRC *y, int64_t M, int64_t G) {
     for (size_t c = 0; c < dense.size(); ++c) if (dense[c] > 0) { hv.push_back((double)c); hc.push_back(dense[c]); }
     for (auto &kv : h) { hv.push_back((double)kv.first); hc.push_back(kv.second); }
     for (size_t i = 0; i < hv.size(); ++i) lg1 += hc[i] * lgamma(hv[i] + 1.0);
+    CUDA_TRY(cudaStreamSynchronize(f->stream));
+    if (f->m.hist_val) { cudaFree((void *)f->m.hist_val); f->m.hist_val = nullptr; }
     double *d = nullptr;
     CUDA_TRY(cudaMalloc(&d, sizeof(double) * 2 * hv.size()));
     CUDA_TRY(cudaMemcpyAsync(d, hv.data(), sizeof(double) * hv.size(), cudaMemcpyHostToDevice, f->stream));
@@ -262,8 +293,8 @@ static int set_y_impl(bvg_fit *f, const SRC *y, int64_t M, int64_t G) {
     f->m.hist_val = d; f->m.hist_cnt = d + hv.size(); f->m.nhist = (int)hv.size(); f->m.lgam_y1 = lg1;
   }
   CUDA_TRY(cudaStreamSynchronize(f->stream));
-  cudaFree(stage);
-  BVG_TRY(finalize_model(f));
+  if (!reuse) BVG_TRY(finalize_model(f));
+  else suff_destroy(f);  // sufficient statistics belong to the previous Y
   f->have_y = true;
   f->st.sec_h2d += now_s() - t0;
   return BVG_OK;
@@ -331,8 +362,16 @@ static int ctl_get(bvg_fit *f, Ctl *h) {
   CUDA_TRY(cudaStreamSynchronize(f->stream));
   return BVG_OK;
 }
+// n consecutive ELBO-gradient evaluations.  tcgen05 engine: only the first one launches k_prep; every
+// k_gene draws the next evaluation's zeta itself ("draw-ahead"), and the likelihood kernel builds its
+// coefficient rows from zeta, so an evaluation is two launches.
 static int advi_steps(bvg_fit *f, int n) {
-  for (int i = 0; i < n; ++i) BVG_TRY(eval_log_prob_device(f, MODE_ADVI_UPDATE, 1, 1, true));
+  const bool ahead = f->engine == BVG_ENGINE_TCGEN05;
+  for (int i = 0; i < n; ++i) {
+    if (!ahead || i == 0) BVG_TRY(launch_prep(f, PREP_GRAD));
+    BVG_TRY(launch_lik(f, true));
+    BVG_TRY(launch_gene_finish(f, MODE_ADVI_UPDATE, 1, 1, ahead && i + 1 < n));
+  }
   f->st.grad_evals += n;
   return BVG_OK;
 }
@@ -619,7 +658,8 @@ extern "C" int bvg_fit_time_lik_kernel(bvg_fit *f, int n, int flush_l2, int back
 // diagnostics: %globaltimer stamps (ns) inside one k_gene launch: [0] block 0 start, [1] after setup,
 // [2] after the gene loop, [3] after the block partials, [4] last block enters finish, [5] after the
 // cross-block reduction, [6] after lp / shared update, [7] end
-extern "C" int bvg_debug_gene_trace(bvg_fit *f, long long *out8) {
+// [8] first gene of block 0: split partials loaded, [9] gradient formed, [10] mean-field update done, [11] next draw done
+extern "C" int bvg_debug_gene_trace(bvg_fit *f, long long *out16, int ahead) {
   BVG_TRY(need_ready(f));
   long long *d = nullptr;
   CUDA_TRY(cudaMalloc(&d, 16 * sizeof(long long)));
@@ -627,11 +667,38 @@ extern "C" int bvg_debug_gene_trace(bvg_fit *f, long long *out8) {
   BVG_TRY(launch_prep(f, PREP_GRAD));
   BVG_TRY(launch_lik(f, true));
   f->m.dbg = d;
-  int rc = launch_gene_finish(f, MODE_ADVI_UPDATE, 1, 1);
+  // ahead bit 0: draw-ahead; bit 2: gradient-out mode (idempotent); bit 1: run an untraced launch first, so the
+  // traced one starts with whatever k_gene left in the instruction / data caches
+  const int mode = (ahead & 4) ? MODE_GRAD_OUT : MODE_ADVI_UPDATE;
+  if (ahead & 2) { f->m.dbg = nullptr; BVG_TRY(launch_gene_finish(f, mode, 1, 1, 0)); f->m.dbg = d; }
+  int rc = launch_gene_finish(f, mode, 1, 1, ahead & 1);
   f->m.dbg = nullptr;
-  if (rc == BVG_OK && (cudaMemcpyAsync(out8, d, 8 * sizeof(long long), cudaMemcpyDeviceToHost, f->stream) != cudaSuccess || cudaStreamSynchronize(f->stream) != cudaSuccess)) rc = BVG_ERR_CUDA;
+  if (rc == BVG_OK && (cudaMemcpyAsync(out16, d, 16 * sizeof(long long), cudaMemcpyDeviceToHost, f->stream) != cudaSuccess || cudaStreamSynchronize(f->stream) != cudaSuccess)) rc = BVG_ERR_CUDA;
   cudaFree(d);
   return rc;
+}
+
+// diagnostics: average device time (ms) of n back-to-back k_gene launches in a given mode, with or without
+// the fused finish (fuse = 0: per-gene part only, 3: + cross-gene finish) -- attribution without in-kernel probes
+extern int g_gene_fuse_override;
+extern "C" int bvg_debug_time_gene(bvg_fit *f, int n, int mode, int fuse, int ahead, float *ms_avg) {
+  BVG_TRY(need_ready(f));
+  if (n < 1 || !ms_avg || f->comm_mode) { bvg_set_error("bad argument"); return BVG_ERR_ARG; }
+  BVG_TRY(launch_prep(f, PREP_GRAD));
+  BVG_TRY(launch_lik(f, true));
+  g_gene_fuse_override = fuse;
+  int rc = launch_gene_finish(f, mode, 1, 1, ahead);
+  if (rc == BVG_OK && cudaEventRecord(f->ev0, f->stream) != cudaSuccess) rc = BVG_ERR_CUDA;
+  for (int i = 0; i < n && rc == BVG_OK; ++i) rc = launch_gene_finish(f, mode, 1, 1, ahead);
+  g_gene_fuse_override = -1;
+  BVG_TRY(rc);
+  CUDA_TRY(cudaEventRecord(f->ev1, f->stream));
+  CUDA_TRY(cudaEventSynchronize(f->ev1));
+  float ms;
+  CUDA_TRY(cudaEventElapsedTime(&ms, f->ev0, f->ev1));
+  *ms_avg = ms / n;
+  if (fuse != 3) CUDA_TRY(cudaMemsetAsync(&f->m.ctl->ticket, 0, sizeof(uint32_t), f->stream));
+  return BVG_OK;
 }
 
 // diagnostics: average device time (ms) of the four stages of one ELBO-gradient evaluation

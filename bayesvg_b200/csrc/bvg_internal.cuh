@@ -224,6 +224,10 @@ struct bvg_fit {
   double *draws;       // [G][n_draws] device
   void *flush;         // L2 flush buffer
   size_t flush_bytes;
+  void *stage_buf;     // two H2D staging buffers of set_y (kept across calls)
+  size_t stage_bytes;
+  cudaStream_t copy_stream;
+  cudaEvent_t ev_copied[2], ev_staged[2];
   bool have_phi, have_y, have_mle, have_vi, have_summary;
   double *h_theta_mle;
   // trace / stats
@@ -265,7 +269,7 @@ int launch_lik_tc(bvg_fit *f, bool backward);
 bool tc_available();                                         // false until the tcgen05 kernel is linked in
 int tc_setup(bvg_fit *f);                                    // build TMA descriptors etc.
 void tc_destroy(bvg_fit *f);
-int launch_gene_finish(bvg_fit *f, int mode, int jacobian, int propto);  // per-gene backward (+ update) + cross-gene finish
+int launch_gene_finish(bvg_fit *f, int mode, int jacobian, int propto, int ahead = 0);  // per-gene backward (+ update, + next draw) + cross-gene finish
 int comm_allreduce(bvg_fit *f, double *buf, int n);          // comm.cu
 int suff_elbo(bvg_fit *f, int S, double *lps_host);          // k_suff.cu: S log densities from sufficient statistics
 void suff_destroy(bvg_fit *f);

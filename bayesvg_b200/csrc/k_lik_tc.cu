@@ -26,6 +26,7 @@
 // Pipelines: Y ring full/empty (5 x 32 KB, released by the epilogue as soon as y is in registers), basis
 // ring full/empty (2 x 24 KB, released by the MMA that read it), D1 full/empty (2 TMEM buffers), R full/free (2).
 #include <cuda.h>
+#include <string.h>
 #include <cuda_bf16.h>
 
 #include "bvg_internal.cuh"
@@ -51,7 +52,10 @@
 
 struct TcArgs {
   float *Ppart, *Spart;
-  const float *C;  // [Gpad][32] fp32 coefficient rows written by k_prep
+  // coefficient rows c'_g = (A_g alpha_t[,g], beta0_g) are built here from the current draw (approxGP.stan:26-27, :32)
+  const double *shx, *Aexp;                                 // exponentials published by k_prep / k_gene
+  int64_t i_mu_alpha, i_z_alpha, i_mu_beta0, i_z_beta0;     // slots of the unconstrained vector
+  int k;
   int64_t M, G, Gpad;
   int KP, cps, nchunks, nk1, nch32;  // nk1 = ceil((k+1)/16): K steps of the forward MMA; nch32 = ldY / 32
   const double *zeta;
@@ -345,14 +349,23 @@ k_lik_tc(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtens
       // PDL: everything above (barriers, TMEM, and the producer's first TMA loads) overlaps the tail of
       // k_prep; its output C is first touched here
       griddep_wait();
-      const float4 *pc = reinterpret_cast<const float4 *>(a.C + g * TC_KW + 16 * h);
+      float cv[16];
+      {
+        const bool live = g < a.G;
+        const double Ag = live ? a.Aexp[g] : 0.0;
+        const double *zr = a.zeta + a.i_z_alpha + g * a.k;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int j = 16 * h + i;
+          double v = 0.0;
+          if (live && j < a.k) v = Ag * (a.zeta[a.i_mu_alpha + j] + a.shx[3 + j] * zr[j]);
+          else if (live && j == a.k) v = a.zeta[a.i_mu_beta0] + a.shx[0] * a.zeta[a.i_z_beta0 + g];
+          cv[i] = (float)v;
+        }
+      }
       uint32_t c1[8], c2[8];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float4 x = pc[i];
-        split_bf16x2(x.x, x.y, c1[2 * i], c2[2 * i]);
-        split_bf16x2(x.z, x.w, c1[2 * i + 1], c2[2 * i + 1]);
-      }
+      for (int i = 0; i < 8; ++i) split_bf16x2(cv[2 * i], cv[2 * i + 1], c1[i], c2[i]);
       tmem_st8u(trow + TM_C1 + 8 * h, c1);
       tmem_st8u(trow + TM_C2 + 8 * h, c2);
       tmem_st_wait();
@@ -552,8 +565,10 @@ int launch_lik_tc(bvg_fit *f, bool bwd) {
   const DevModel &m = f->m;
   TcState *t = (TcState *)f->tc;
   TcArgs a;
+  memset(&a, 0, sizeof(a));  // padding bytes take part in the change check below
   a.Ppart = (float *)m.Ppart; a.Spart = (float *)m.Spart;
-  a.C = (const float *)m.C;  // k_prep writes the fp32 coefficient rows [Gpad][32] here
+  a.shx = m.shx; a.Aexp = m.Aexp; a.k = m.k;
+  a.i_mu_alpha = m.L.mu_alpha; a.i_z_alpha = m.L.z_alpha; a.i_mu_beta0 = m.L.mu_beta0; a.i_z_beta0 = m.L.z_beta0;
   a.nk1 = (m.k + 1 + 15) / 16;
   a.nch32 = (int)(f->ldY / 32);
   a.M = m.M; a.G = m.G; a.Gpad = m.Gpad; a.KP = m.KP;

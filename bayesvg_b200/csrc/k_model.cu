@@ -59,12 +59,11 @@ __global__ void __launch_bounds__(256) k_prep(DevModel m, int mode, int tc, int 
   else if (blockIdx.x == 0 && tid == k + gpb + 2) m.shx[2] = exp(sh[4]);
   __syncthreads();
   // ---- phase 3: coefficient rows c'_g = (A_g alpha_t[,g], beta0_g) ----
-  if (!is_gene || j == k + 1) return;
+  // (the tcgen05 likelihood kernel builds its coefficient rows itself from zeta / shx / Aexp)
+  if (tc || !is_gene || j == k + 1) return;
   const double v = j < k ? Ag[gl] * (sh[5 + j] + sal[j] * zg[gl * npg + j])  // A_g * alpha_t[j,g] (approxGP.stan:32)
                          : sh[0] + sh[1] * zg[gl * npg + k];                  // beta0 (approxGP.stan:26)
-  if (!tc) { ((T *)m.C)[g * m.KP + j] = (T)v; return; }
-  // tcgen05 engine: fp32 rows of width 32 (the likelihood kernel splits them into bf16 parts itself)
-  ((float *)m.C)[g * 32 + j] = (float)v;
+  ((T *)m.C)[g * m.KP + j] = (T)v;
 }
 
 int launch_prep(bvg_fit *f, int mode) {
@@ -103,15 +102,21 @@ __device__ inline double dev_digamma(double x) {
   return r + log(x) - 0.5 / x + t;
 }
 
-__device__ inline long long gtime() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+// stamps use the SM cycle counter: a %globaltimer read stalls the warp for about a microsecond (four of them
+// in a row looked like a 3.6 us "load latency" in an earlier trace)
+__device__ inline long long gtime() { return clock64(); }
 #define DBG(i) do { if (m.dbg && threadIdx.x == 0) m.dbg[i] = gtime(); } while (0)
 #define DBG0(i) do { if (m.dbg && threadIdx.x == 0 && blockIdx.x == 0) m.dbg[i] = gtime(); } while (0)
+// stamp that cannot be scheduled before `dep` is available
+#define DBGV(i, dep) do { if (m.dbg && threadIdx.x == 0 && blockIdx.x == 0 && (dep) != 1.2345e300) m.dbg[i] = gtime(); } while (0)
 
 // ------------------------------------------------------------------------------------------------
 // finish_body (one CTA, >= 128 threads).  phase bit 0: fixed-order reduction of the per-block
 // partials (+ nb histogram terms) into tot[]; bit 1: log density, gradient / ADVI update of the 2k+5
 // gene-shared parameters, counters.  A multi-GPU fit all-reduces tot[] between the two phases.
-__device__ void finish_body(const DevModel &m, int mode, int jac, int propto, int phase) {
+// ahead != 0 (ADVI update only): also draw the NEXT evaluation's zeta of the gene-shared parameters and
+// publish their exponentials, so that no k_prep launch sits between this evaluation and the next.
+__device__ void finish_body(const DevModel &m, int mode, int jac, int propto, int phase, int ahead) {
   __shared__ double red[2][32];
   __shared__ double s_lp;
   const int k = m.k, NS = bvg_ns(k), tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -185,6 +190,7 @@ __device__ void finish_body(const DevModel &m, int mode, int jac, int propto, in
   const double Gt = (double)m.G_total, N = (double)m.M * Gt;
   const double j1 = jac ? 1.0 : 0.0;
   const int it = m.ctl->it;
+  const uint32_t tg = m.ctl->t_grad;  // read before the barrier that precedes thread 0's increment
   if (warp == (blockDim.x >> 5) - 1) {  // log density (last warp, concurrently with the gradient threads below)
     double pa = 0;  // prior terms of mu_alpha, sigma_alpha + jacobian of sigma_alpha
     for (int j = lane; j < k; j += 32) {
@@ -235,6 +241,16 @@ __device__ void finish_body(const DevModel &m, int mode, int jac, int propto, in
   }
   __syncthreads();
   DBG(6);
+  if (ahead && mode == MODE_ADVI_UPDATE && tid < 2 * k + 5) {
+    // every thread of the CTA has finished reading this evaluation's shared zeta (barrier above)
+    const int64_t li = shared_index(L, k, tid), gi = shared_index(m.LG, k, tid);
+    const double z = m.mu[li] + exp(m.omega[li]) * bvg_normal(m.seed, STREAM_GRAD, tg + 1, (uint64_t)gi);
+    m.zeta[li] = z;
+    if (tid == 1) m.shx[0] = exp(z);
+    else if (tid == 3) m.shx[1] = exp(z);
+    else if (tid == 4) m.shx[2] = exp(z);
+    else if (tid >= 5 + k) m.shx[3 + tid - 5 - k] = exp(z);
+  }
   if (tid == 0) {
     const double lp = s_lp;
     m.ctl->lp = lp;
@@ -246,8 +262,8 @@ __device__ void finish_body(const DevModel &m, int mode, int jac, int propto, in
   }
 }
 
-__global__ void __launch_bounds__(512) k_finish(DevModel m, int mode, int jac, int propto, int phase) {
-  finish_body(m, mode, jac, propto, phase);
+__global__ void __launch_bounds__(512) k_finish(DevModel m, int mode, int jac, int propto, int phase, int ahead) {
+  finish_body(m, mode, jac, propto, phase, ahead);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -256,8 +272,11 @@ __global__ void __launch_bounds__(512) k_finish(DevModel m, int mode, int jac, i
 // zeta / mu / omega / step-size history) so the warp pays ~2 L2 round trips, not one per load.
 // The last CTA to retire also runs finish_body (fuse = 3: everything; fuse = 1, multi-GPU: only the
 // cross-block reduction, because the NCCL all-reduce of tot[] comes next), saving a launch per evaluation.
+// ahead != 0 (ADVI update): every lane also draws its parameter's zeta for the NEXT evaluation right after
+// the update (Philox counter t_grad + 1), so consecutive ADVI evaluations are two launches -- likelihood,
+// k_gene -- instead of three; k_prep then only runs at the start of a batch of steps.
 template <typename T>
-__global__ void __launch_bounds__(512) k_gene(DevModel m, int mode, int jac, int propto, int fuse) {
+__global__ void __launch_bounds__(512) k_gene(DevModel m, int mode, int jac, int propto, int fuse, int ahead) {
   extern __shared__ double sm[];  // [nwarps][NS]
   __shared__ int s_last;
   griddep_wait();    // Ppart / Spart come from the likelihood kernel
@@ -272,18 +291,23 @@ __global__ void __launch_bounds__(512) k_gene(DevModel m, int mode, int jac, int
   const double mual = lane < k ? zt[L.mu_alpha + lane] : 0.0;
   const double sal = lane < k ? m.shx[3 + lane] : 0.0;
   const int it = m.ctl->it;
+  const uint32_t tg = m.ctl->t_grad;
   const double es = m.ctl->eta / sqrt((double)it);
   const bool has = lane < k + 2, upd = mode == MODE_ADVI_UPDATE;
   DBG0(0);
-  if (m.dbg && threadIdx.x == 0 && blockIdx.x == 0) m.dbg[1] = (long long)(es * 1e9) * 0 + gtime();
+  DBGV(12, sb + ma + sa + tail);
+  DBGV(1, es);
   double aR = 0, aRz = 0, aDu = 0, aDu2 = 0, aS0 = 0, aS1 = 0, aZ2 = 0, aU = 0, aAP = 0, aAPz = 0;
   const T *Pp = (const T *)m.Ppart, *Sp = (const T *)m.Spart;
   for (int64_t g = (int64_t)blockIdx.x * nw + warp; g < m.G; g += (int64_t)gridDim.x * nw) {
     const int64_t li = lane < k ? L.z_alpha + g * k + lane : (lane == k ? L.z_beta0 + g : L.amp + g);
+    DBGV(15, es + (double)li);
     const double zi = has ? zt[li] : 0.0;  // this lane's own parameter value
     const double Aexp_g = m.Aexp[g];
     double mu_i = 0, om_i = 0, hm = 0, ho = 0;
     if (upd && has) { mu_i = m.mu[li]; om_i = m.omega[li]; hm = m.hist[li]; ho = m.hist[L.D + li]; }
+    DBGV(13, zi + Aexp_g);
+    DBGV(14, mu_i + om_i + hm + ho);
     double Pj = 0, s0 = 0;
     for (int sp0 = 0; sp0 < m.nsplit; sp0 += 8) {  // fixed order -> deterministic
       T pv[8], sv[8];
@@ -297,6 +321,7 @@ __global__ void __launch_bounds__(512) k_gene(DevModel m, int mode, int jac, int
 #pragma unroll
       for (int q = 0; q < 8; ++q) { Pj += (double)pv[q]; s0 += (double)sv[q]; }
     }
+    DBGV(8, Pj);
     const double s1 = __shfl_sync(0xffffffffu, s0, 1);
     s0 = __shfl_sync(0xffffffffu, s0, 0);
     Pj *= inv_s2;
@@ -315,6 +340,7 @@ __global__ void __launch_bounds__(512) k_gene(DevModel m, int mode, int jac, int
       if (lane < k) gv = sal * AP - zj;
       else if (lane == k) gv = sb * R - zb;
       else if (lane == k + 1) gv = 2.0 * A * aP - du / (sa * sa) - (jac ? 0.0 : 1.0);
+      DBGV(9, gv);
       if (!upd) {
         if (has) m.grad[li] = gv;
       } else {
@@ -327,8 +353,18 @@ __global__ void __launch_bounds__(512) k_gene(DevModel m, int mode, int jac, int
           else { hm = 0.9 * hm + 0.1 * gm * gm; ho = 0.9 * ho + 0.1 * go * go; }
           m.hist[li] = hm;
           m.hist[L.D + li] = ho;
-          m.mu[li] = mu_i + es * gm / (1.0 + sqrt(hm));
-          m.omega[li] = om_i + es * go / (1.0 + sqrt(ho));
+          const double mu_n = mu_i + es * gm / (1.0 + sqrt(hm)), om_n = om_i + es * go / (1.0 + sqrt(ho));
+          m.mu[li] = mu_n;
+          m.omega[li] = om_n;
+          DBGV(10, mu_n + om_n);
+          if (ahead) {  // next evaluation's draw of this parameter (what k_prep would compute)
+            const int64_t gg = m.gene_offset + g;
+            const int64_t gi = lane < k ? m.LG.z_alpha + gg * k + lane : (lane == k ? m.LG.z_beta0 + gg : m.LG.amp + gg);
+            const double zn = mu_n + exp(om_n) * bvg_normal(m.seed, STREAM_GRAD, tg + 1, (uint64_t)gi);
+            m.zeta[li] = zn;
+            if (lane == k + 1) m.Aexp[g] = exp(2.0 * zn);  // approxGP.stan:27
+            DBGV(11, zn);
+          }
         }
       }
     }
@@ -359,22 +395,23 @@ __global__ void __launch_bounds__(512) k_gene(DevModel m, int mode, int jac, int
   if (!s_last) return;
   __threadfence();
   DBG(4);
-  finish_body(m, mode, jac, propto, fuse);  // fuse = 3: reduce + finish; fuse = 1 (multi-GPU): reduce only, the all-reduce follows
+  finish_body(m, mode, jac, propto, fuse, ahead);  // fuse = 3: reduce + finish; fuse = 1 (multi-GPU): reduce only, the all-reduce follows
   DBG(7);
 }
 
-int launch_gene_finish(bvg_fit *f, int mode, int jac, int propto) {
+int g_gene_fuse_override = -1;  // diagnostics (bvg_debug_time_gene): force the fuse argument
+int launch_gene_finish(bvg_fit *f, int mode, int jac, int propto, int ahead) {
   const int wpb = 16;
   const size_t sh = sizeof(double) * wpb * bvg_ns(f->m.k);
   // single GPU or peer-memory exchange: everything in one launch; NCCL (or k > 251): reduce, all-reduce, finish
   const bool split = f->comm_mode == 1 || (f->comm_mode == 2 && bvg_ns(f->m.k) > wpb * 32);
-  const int fuse = split ? 1 : 3;
-  if (f->cfg.precision == BVG_PREC_FP64) CUDA_TRY(launch_pdl(k_gene<double>, dim3(f->m.nblk_gene), dim3(wpb * 32), sh, f->stream, f->m, mode, jac, propto, fuse));
-  else CUDA_TRY(launch_pdl(k_gene<float>, dim3(f->m.nblk_gene), dim3(wpb * 32), sh, f->stream, f->m, mode, jac, propto, fuse));
+  const int fuse = g_gene_fuse_override >= 0 ? g_gene_fuse_override : (split ? 1 : 3);
+  if (f->cfg.precision == BVG_PREC_FP64) CUDA_TRY(launch_pdl(k_gene<double>, dim3(f->m.nblk_gene), dim3(wpb * 32), sh, f->stream, f->m, mode, jac, propto, fuse, ahead));
+  else CUDA_TRY(launch_pdl(k_gene<float>, dim3(f->m.nblk_gene), dim3(wpb * 32), sh, f->stream, f->m, mode, jac, propto, fuse, ahead));
   f->st.kernel_launches++;
   if (fuse == 1) {
     BVG_TRY(comm_allreduce(f, f->m.tot, bvg_ns(f->m.k)));
-    k_finish<<<1, 512, 0, f->stream>>>(f->m, mode, jac, propto, 2);
+    k_finish<<<1, 512, 0, f->stream>>>(f->m, mode, jac, propto, 2, ahead);
     f->st.kernel_launches += 1;
     CUDA_TRY(cudaGetLastError());
   }

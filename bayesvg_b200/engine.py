@@ -140,6 +140,26 @@ class Fit:
         B.check(B.lib().bvg_fit_time_lik_kernel(self._h, n, int(flush_l2), int(backward), C.byref(ms)))
         return ms.value
 
+    def stage_times(self, n=20):
+        """diagnostics: average device ms of (k_prep, likelihood, k_gene + finish) run back to back"""
+        out = (C.c_float * 4)()
+        B.check(B.lib().bvg_debug_stage_times(self._h, n, out))
+        return list(out)[:3]
+
+    def time_gene(self, n=100, mode=1, fuse=3, ahead=0):
+        """diagnostics: average device ms of n back-to-back k_gene launches"""
+        ms = C.c_float()
+        B.check(B.lib().bvg_debug_time_gene(self._h, n, mode, fuse, ahead, C.byref(ms)))
+        return ms.value
+
+    def gene_trace(self, ahead=0):
+        """diagnostics: SM cycle-counter stamps inside one k_gene launch.  Stamps 0-3 and 8-15 come from CTA 0
+        (relative to stamp 0); stamps 4-7 from the last CTA to retire, on another SM (relative to stamp 4)."""
+        out = (C.c_longlong * 16)()
+        B.check(B.lib().bvg_debug_gene_trace(self._h, out, int(ahead)))
+        v = list(out)
+        return [(x - (v[4] if 4 <= i <= 7 else v[0])) if x else None for i, x in enumerate(v)]
+
     def flush_l2(self):
         B.check(B.lib().bvg_fit_flush_l2(self._h))
 

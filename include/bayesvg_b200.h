@@ -159,7 +159,8 @@ int bvg_fit_get_stats(bvg_fit *, bvg_fit_stats *out);
 
 /* diagnostics (not needed by a binding; used by scripts/ and profiles/) */
 int bvg_debug_stage_times(bvg_fit *, int n, float *out4 /* ms: prep, likelihood, gene+finish, - */);
-int bvg_debug_gene_trace(bvg_fit *, long long *out8 /* %globaltimer ns stamps inside k_gene */);
+int bvg_debug_gene_trace(bvg_fit *, long long *out16 /* %globaltimer ns stamps inside k_gene */, int ahead);
+int bvg_debug_time_gene(bvg_fit *, int n, int mode /* 0 grad out, 1 advi update, 3 lp only */, int fuse /* 0 | 3 */, int ahead, float *ms_avg);
 int bvg_debug_tc_trace(bvg_fit *, long long *out /* [chunk][8] clock64 stamps of CTA (0,0) */, int nchunk_cap);
 
 #ifdef __cplusplus

@@ -136,6 +136,51 @@ def test_advi_trajectory_fast_path(prec, eng):
     f.close()
 
 
+@pytest.mark.parametrize("lik", ["gaussian", "nb"])
+@pytest.mark.parametrize("prec,eng", ENGINES)
+def test_set_y_again_reuses_the_model_and_matches_a_fresh_fit(lik, prec, eng):
+    """a second bvg_fit_set_y of the same shape keeps the allocations and restages only Y (double-buffered H2D)"""
+    p1 = make_problem(333, 140, 9, lik, seed=31)
+    p2 = make_problem(333, 140, 9, lik, seed=32)
+    f = _fit(p1["phi"], p1["y"], lik, prec, eng)
+    th = np.random.default_rng(2).normal(0, 0.3, f.D)
+    f.log_prob(th)
+    f.set_y(p2["y"])                       # same shape: reuse path
+    lp_a, g_a = f.log_prob(th, True, False)
+    f.set_y(p2["y"][:, :77].copy(order="F"))  # different G: full re-allocation
+    th77 = np.random.default_rng(3).normal(0, 0.3, f.D)
+    lp_c, g_c = f.log_prob(th77, True, False)
+    f.close()
+    f2 = _fit(p1["phi"], p2["y"], lik, prec, eng)
+    lp_b, g_b = f2.log_prob(th, True, False)
+    f2.close()
+    f3 = _fit(p1["phi"], p2["y"][:, :77].copy(order="F"), lik, prec, eng)
+    lp_d, g_d = f3.log_prob(th77, True, False)
+    f3.close()
+    assert lp_a == lp_b and np.array_equal(g_a, g_b)
+    assert lp_c == lp_d and np.array_equal(g_c, g_d)
+
+
+@pytest.mark.parametrize("lik", ["gaussian", "nb"])
+def test_draw_ahead_batches_are_bitwise_identical(lik):
+    """tcgen05 engine: inside a batch of steps k_gene draws the next evaluation's zeta itself; a batch boundary
+    re-draws it with k_prep.  Both must give the same numbers: 10 steps == 3 + 1 + 6 steps, bit for bit, and an
+    ELBO estimate in between (which overwrites zeta with its own draws) must not disturb the trajectory."""
+    p = make_problem(300, 200, 17, lik, seed=21)
+    out = []
+    for batches in ((10,), (3, 1, 6)):
+        f = _fit(p["phi"], p["y"], lik, "fast", "tcgen05", seed=11)
+        f.set_variational(np.zeros(f.D), None)
+        f.advi_steps(0, 0.05, reset=True)
+        for i, n in enumerate(batches):
+            f.advi_steps(n, 0.05)
+            if i == 0 and len(batches) > 1:
+                f.elbo(3)
+        out.append(f.get_variational())
+        f.close()
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+
+
 @pytest.mark.parametrize("iters,tol_lp,tol_th", [(8, 1e-10, 1e-7), (60, 1e-5, 5e-2)])
 def test_lbfgs_matches_oracle_fp64(iters, tol_lp, tol_th):
     """same algorithm (two-loop vs its vector-free Gram form): identical iterates early on, the same
