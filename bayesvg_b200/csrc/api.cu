@@ -172,10 +172,12 @@ static int finalize_model(bvg_fit *f) {
   CUDA_TRY(cudaMemsetAsync(m.Spart, 0, ts * (size_t)m.nsplit * m.Gpad * 2, f->stream));
   m.nblk_gene = (int)std::min<int64_t>((m.G + 15) / 16, nsm);  // 16 gene-warps per CTA, at most one CTA per SM
   const int NS = bvg_ns(m.k);
-  CUDA_TRY(cudaMalloc(&m.blk, sizeof(double) * (((size_t)m.nblk_gene + 1) * NS + 3 + m.k + m.G)));
+  CUDA_TRY(cudaMalloc(&m.blk, sizeof(double) * (((size_t)m.nblk_gene + 1) * NS + 4 + m.k + m.G + 48)));
   m.tot = m.blk + (size_t)m.nblk_gene * NS;
   m.shx = m.tot + NS;
-  m.Aexp = m.shx + 3 + m.k;
+  m.Aexp = m.shx + 4 + m.k;
+  m.U = (float *)(m.blk + ((((size_t)m.nblk_gene + 1) * NS + 4 + m.k + m.G + 1) & ~(size_t)1));  // 96 floats, 16-byte aligned (float4 loads)
+  m.W = (float *)m.C;             // tcgen05 engine: the coefficient-row allocation holds the fp32 draw rows instead
   CUDA_TRY(cudaMalloc(&m.ctl, sizeof(Ctl)));
   CUDA_TRY(cudaMemsetAsync(m.ctl, 0, sizeof(Ctl), f->stream));
   CUDA_TRY(cudaMalloc(&f->summary, sizeof(double) * 8 * m.G));
@@ -352,7 +354,9 @@ static int advi_reset(bvg_fit *f, const double *d_init /* device, NULL keeps mu 
   CUDA_TRY(cudaMemsetAsync(f->m.hist, 0, sizeof(double) * 2 * D, f->stream));
   return BVG_OK;
 }
-static int ctl_set(bvg_fit *f, const Ctl &h) {
+static int ctl_set(bvg_fit *f, const Ctl &h0) {
+  Ctl h = h0;
+  h.es = h.eta / sqrt((double)(h.it < 1 ? 1 : h.it));
   CUDA_TRY(cudaMemcpyAsync(f->m.ctl, &h, sizeof(Ctl), cudaMemcpyHostToDevice, f->stream));
   CUDA_TRY(cudaStreamSynchronize(f->stream));  // h lives on the caller's stack
   return BVG_OK;
@@ -658,7 +662,8 @@ extern "C" int bvg_fit_time_lik_kernel(bvg_fit *f, int n, int flush_l2, int back
 // diagnostics: %globaltimer stamps (ns) inside one k_gene launch: [0] block 0 start, [1] after setup,
 // [2] after the gene loop, [3] after the block partials, [4] last block enters finish, [5] after the
 // cross-block reduction, [6] after lp / shared update, [7] end
-// [8] first gene of block 0: split partials loaded, [9] gradient formed, [10] mean-field update done, [11] next draw done
+// (stamps are SM cycle counters and are only ordered by data dependencies; for attribution without probe effects
+// use bvg_debug_time_gene)
 extern "C" int bvg_debug_gene_trace(bvg_fit *f, long long *out16, int ahead) {
   BVG_TRY(need_ready(f));
   long long *d = nullptr;

@@ -70,6 +70,7 @@ struct Ctl {
   double elbo_acc;   // sum of finite log densities of the current ELBO estimate
   int32_t elbo_ok;
   uint32_t ticket;   // last-block-done counter of k_gene (fused finish)
+  double es;         // eta / sqrt(it): kept next to `it` so that k_gene starts without a sqrt + divide chain
 };
 
 // ---- peer-memory exchange (multi-GPU) ------------------------------------------
@@ -97,8 +98,14 @@ struct DevModel {
   void *Spart;   // [nsplit][Gpad][2]
   double *blk;   // [nblk_gene][NS]
   double *tot;   // [NS]
-  double *shx;   // [3+k] exp of the shared log-scales of the current draw: sigma_beta0, sigma_amplitude, tail, sigma_alpha[k]
+  double *shx;   // [4+k] exp of the shared log-scales of the current draw: sigma_beta0, sigma_amplitude, tail, sigma_alpha[k];
+                 //       [3+k] = 1 / sigma_y^2 (gaussian) or 1 (nb)
   double *Aexp;  // [G] amplitude_sq of the current draw
+  // tcgen05 engine: the current draw as the likelihood kernel wants it, fp32.  W[g][0..k) = z_alpha_t[,g],
+  // W[g][k] = z_beta0[g], W[g][k+1] = amplitude_sq[g]; U[0..k) = mu_alpha, U[32..32+k) = sigma_alpha,
+  // U[64] = mu_beta0, U[65] = sigma_beta0.  The kernel forms c'_g = (A_g (mu_alpha + sigma_alpha z), mu_beta0 + sigma_beta0 z_b).
+  float *W;      // [Gpad][32]
+  float *U;      // [96]
   int nblk_gene;
   int nhist;                 // nb: distinct count values
   const double *hist_val;    // nb: value c

@@ -52,9 +52,9 @@
 
 struct TcArgs {
   float *Ppart, *Spart;
-  // coefficient rows c'_g = (A_g alpha_t[,g], beta0_g) are built here from the current draw (approxGP.stan:26-27, :32)
-  const double *shx, *Aexp;                                 // exponentials published by k_prep / k_gene
-  int64_t i_mu_alpha, i_z_alpha, i_mu_beta0, i_z_beta0;     // slots of the unconstrained vector
+  // coefficient rows c'_g = (A_g alpha_t[,g], beta0_g) are built here from the current draw (approxGP.stan:26-27, :32),
+  // published in fp32 by k_prep / k_gene: W[g] = (z_alpha_t[,g], z_beta0[g], A_g), U = (mu_alpha | sigma_alpha | mu_beta0, sigma_beta0)
+  const float *W, *U;
   int k;
   int64_t M, G, Gpad;
   int KP, cps, nchunks, nk1, nch32;  // nk1 = ceil((k+1)/16): K steps of the forward MMA; nch32 = ldY / 32
@@ -351,16 +351,25 @@ k_lik_tc(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtens
       griddep_wait();
       float cv[16];
       {
+        const float4 *pw = reinterpret_cast<const float4 *>(a.W + g * TC_KW + 16 * h);
+        const float4 *pm = reinterpret_cast<const float4 *>(a.U + 16 * h), *ps = reinterpret_cast<const float4 *>(a.U + 32 + 16 * h);
+        const float Ag = a.W[g * TC_KW + a.k + 1], mb = a.U[64], sb = a.U[65];
+        float w[16], um[16], us[16];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 x = pw[i], y = __ldg(pm + i), z = __ldg(ps + i);
+          w[4 * i] = x.x; w[4 * i + 1] = x.y; w[4 * i + 2] = x.z; w[4 * i + 3] = x.w;
+          um[4 * i] = y.x; um[4 * i + 1] = y.y; um[4 * i + 2] = y.z; um[4 * i + 3] = y.w;
+          us[4 * i] = z.x; us[4 * i + 1] = z.y; us[4 * i + 2] = z.z; us[4 * i + 3] = z.w;
+        }
         const bool live = g < a.G;
-        const double Ag = live ? a.Aexp[g] : 0.0;
-        const double *zr = a.zeta + a.i_z_alpha + g * a.k;
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const int j = 16 * h + i;
-          double v = 0.0;
-          if (live && j < a.k) v = Ag * (a.zeta[a.i_mu_alpha + j] + a.shx[3 + j] * zr[j]);
-          else if (live && j == a.k) v = a.zeta[a.i_mu_beta0] + a.shx[0] * a.zeta[a.i_z_beta0 + g];
-          cv[i] = (float)v;
+          float v = 0.f;
+          if (j < a.k) v = Ag * fmaf(us[i], w[i], um[i]);
+          else if (j == a.k) v = fmaf(sb, w[i], mb);
+          cv[i] = live ? v : 0.f;
         }
       }
       uint32_t c1[8], c2[8];
@@ -567,8 +576,7 @@ int launch_lik_tc(bvg_fit *f, bool bwd) {
   TcArgs a;
   memset(&a, 0, sizeof(a));  // padding bytes take part in the change check below
   a.Ppart = (float *)m.Ppart; a.Spart = (float *)m.Spart;
-  a.shx = m.shx; a.Aexp = m.Aexp; a.k = m.k;
-  a.i_mu_alpha = m.L.mu_alpha; a.i_z_alpha = m.L.z_alpha; a.i_mu_beta0 = m.L.mu_beta0; a.i_z_beta0 = m.L.z_beta0;
+  a.W = m.W; a.U = m.U; a.k = m.k;
   a.nk1 = (m.k + 1 + 15) / 16;
   a.nch32 = (int)(f->ldY / 32);
   a.M = m.M; a.G = m.G; a.Gpad = m.Gpad; a.KP = m.KP;

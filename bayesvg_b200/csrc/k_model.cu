@@ -56,11 +56,20 @@ __global__ void __launch_bounds__(256) k_prep(DevModel m, int mode, int tc, int 
     Ag[q] = e;
     if ((int64_t)blockIdx.x * gpb + q < m.G) m.Aexp[(int64_t)blockIdx.x * gpb + q] = e;
   } else if (blockIdx.x == 0 && tid == k + gpb + 1) m.shx[1] = exp(sh[3]);
-  else if (blockIdx.x == 0 && tid == k + gpb + 2) m.shx[2] = exp(sh[4]);
+  else if (blockIdx.x == 0 && tid == k + gpb + 2) {
+    const double e = exp(sh[4]);
+    m.shx[2] = e;
+    m.shx[3 + k] = m.lik == BVG_GAUSSIAN ? 1.0 / (e * e) : 1.0;
+  }
   __syncthreads();
   // ---- phase 3: coefficient rows c'_g = (A_g alpha_t[,g], beta0_g) ----
-  // (the tcgen05 likelihood kernel builds its coefficient rows itself from zeta / shx / Aexp)
-  if (tc || !is_gene || j == k + 1) return;
+  if (tc) {  // tcgen05 engine: publish the draw in fp32 (W rows, U vector); the likelihood kernel forms c'_g itself
+    if (is_gene) m.W[g * 32 + j] = (float)(j == k + 1 ? Ag[gl] : zg[gl * npg + j]);
+    if (blockIdx.x == 0 && tid < k) { m.U[tid] = (float)sh[5 + tid]; m.U[32 + tid] = (float)sal[tid]; }
+    if (blockIdx.x == 0 && tid == k) { m.U[64] = (float)sh[0]; m.U[65] = (float)sh[1]; }
+    return;
+  }
+  if (!is_gene || j == k + 1) return;
   const double v = j < k ? Ag[gl] * (sh[5 + j] + sal[j] * zg[gl * npg + j])  // A_g * alpha_t[j,g] (approxGP.stan:32)
                          : sh[0] + sh[1] * zg[gl * npg + k];                  // beta0 (approxGP.stan:26)
   ((T *)m.C)[g * m.KP + j] = (T)v;
@@ -107,8 +116,6 @@ __device__ inline double dev_digamma(double x) {
 __device__ inline long long gtime() { return clock64(); }
 #define DBG(i) do { if (m.dbg && threadIdx.x == 0) m.dbg[i] = gtime(); } while (0)
 #define DBG0(i) do { if (m.dbg && threadIdx.x == 0 && blockIdx.x == 0) m.dbg[i] = gtime(); } while (0)
-// stamp that cannot be scheduled before `dep` is available
-#define DBGV(i, dep) do { if (m.dbg && threadIdx.x == 0 && blockIdx.x == 0 && (dep) != 1.2345e300) m.dbg[i] = gtime(); } while (0)
 
 // ------------------------------------------------------------------------------------------------
 // finish_body (one CTA, >= 128 threads).  phase bit 0: fixed-order reduction of the per-block
@@ -215,7 +222,7 @@ __device__ void finish_body(const DevModel &m, int mode, int jac, int propto, in
       s_lp = lp;
     }
   } else if ((mode == MODE_GRAD_OUT || mode == MODE_ADVI_UPDATE) && tid < 2 * k + 5) {
-    const double es = m.ctl->eta / sqrt((double)it);
+    const double es = m.ctl->es;
     const int i = tid;
     double gv;
     if (i == 0) gv = tot[S_R] - mb / 4.0;
@@ -246,11 +253,14 @@ __device__ void finish_body(const DevModel &m, int mode, int jac, int propto, in
     const int64_t li = shared_index(L, k, tid), gi = shared_index(m.LG, k, tid);
     const double z = m.mu[li] + exp(m.omega[li]) * bvg_normal(m.seed, STREAM_GRAD, tg + 1, (uint64_t)gi);
     m.zeta[li] = z;
-    if (tid == 1) m.shx[0] = exp(z);
+    if (tid == 0) m.U[64] = (float)z;
+    else if (tid == 1) { const double e = exp(z); m.shx[0] = e; m.U[65] = (float)e; }
     else if (tid == 3) m.shx[1] = exp(z);
-    else if (tid == 4) m.shx[2] = exp(z);
-    else if (tid >= 5 + k) m.shx[3 + tid - 5 - k] = exp(z);
+    else if (tid == 4) { const double e = exp(z); m.shx[2] = e; m.shx[3 + k] = m.lik == BVG_GAUSSIAN ? 1.0 / (e * e) : 1.0; }
+    else if (tid >= 5 + k) { const double e = exp(z); m.shx[3 + tid - 5 - k] = e; m.U[32 + tid - 5 - k] = (float)e; }
+    else if (tid >= 5) m.U[tid - 5] = (float)z;
   }
+  if (mode == MODE_ADVI_UPDATE && tid == 2 * k + 5) m.ctl->es = m.ctl->eta / sqrt((double)(it + 1));
   if (tid == 0) {
     const double lp = s_lp;
     m.ctl->lp = lp;
@@ -286,42 +296,42 @@ __global__ void __launch_bounds__(512) k_gene(DevModel m, int mode, int jac, int
   const Layout &L = m.L;
   const double *zt = m.zeta;
   const double sb = m.shx[0], ma = zt[L.mu_amp], sa = m.shx[1];  // exponentials precomputed by k_prep
-  const double tail = m.shx[2];
-  const double inv_s2 = m.lik == BVG_GAUSSIAN ? 1.0 / (tail * tail) : 1.0;
+  const double inv_s2 = m.shx[3 + k];  // 1 / sigma_y^2 (gaussian) | 1 (nb), published with the draw
   const double mual = lane < k ? zt[L.mu_alpha + lane] : 0.0;
   const double sal = lane < k ? m.shx[3 + lane] : 0.0;
   const int it = m.ctl->it;
   const uint32_t tg = m.ctl->t_grad;
-  const double es = m.ctl->eta / sqrt((double)it);
+  const double es = m.ctl->es;        // eta / sqrt(it)
   const bool has = lane < k + 2, upd = mode == MODE_ADVI_UPDATE;
   DBG0(0);
-  DBGV(12, sb + ma + sa + tail);
-  DBGV(1, es);
   double aR = 0, aRz = 0, aDu = 0, aDu2 = 0, aS0 = 0, aS1 = 0, aZ2 = 0, aU = 0, aAP = 0, aAPz = 0;
   const T *Pp = (const T *)m.Ppart, *Sp = (const T *)m.Spart;
   for (int64_t g = (int64_t)blockIdx.x * nw + warp; g < m.G; g += (int64_t)gridDim.x * nw) {
     const int64_t li = lane < k ? L.z_alpha + g * k + lane : (lane == k ? L.z_beta0 + g : L.amp + g);
-    DBGV(15, es + (double)li);
     const double zi = has ? zt[li] : 0.0;  // this lane's own parameter value
     const double Aexp_g = m.Aexp[g];
     double mu_i = 0, om_i = 0, hm = 0, ho = 0;
     if (upd && has) { mu_i = m.mu[li]; om_i = m.omega[li]; hm = m.hist[li]; ho = m.hist[L.D + li]; }
-    DBGV(13, zi + Aexp_g);
-    DBGV(14, mu_i + om_i + hm + ho);
     double Pj = 0, s0 = 0;
     for (int sp0 = 0; sp0 < m.nsplit; sp0 += 8) {  // fixed order -> deterministic
+      // unconditional loads from clamped (always valid) addresses: all 16 go out in one round trip; the
+      // predicated form was compiled into several dependent load -> convert rounds
       T pv[8], sv[8];
+      const int lp = lane < KP ? lane : KP - 1, ls = lane & 1;
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        const int64_t row = (int64_t)(sp0 + q) * m.Gpad + g;
-        const bool ok = sp0 + q < m.nsplit;
-        pv[q] = (ok && lane < KP) ? Pp[row * KP + lane] : (T)0;
-        sv[q] = (ok && lane < 2) ? Sp[row * 2 + lane] : (T)0;
+        const int sp = sp0 + q < m.nsplit ? sp0 + q : m.nsplit - 1;
+        const int64_t row = (int64_t)sp * m.Gpad + g;
+        pv[q] = Pp[row * KP + lp];
+        sv[q] = Sp[row * 2 + ls];
       }
 #pragma unroll
-      for (int q = 0; q < 8; ++q) { Pj += (double)pv[q]; s0 += (double)sv[q]; }
+      for (int q = 0; q < 8; ++q) {
+        const bool ok = sp0 + q < m.nsplit;
+        Pj += (ok && lane < KP) ? (double)pv[q] : 0.0;
+        s0 += (ok && lane < 2) ? (double)sv[q] : 0.0;
+      }
     }
-    DBGV(8, Pj);
     const double s1 = __shfl_sync(0xffffffffu, s0, 1);
     s0 = __shfl_sync(0xffffffffu, s0, 0);
     Pj *= inv_s2;
@@ -340,7 +350,6 @@ __global__ void __launch_bounds__(512) k_gene(DevModel m, int mode, int jac, int
       if (lane < k) gv = sal * AP - zj;
       else if (lane == k) gv = sb * R - zb;
       else if (lane == k + 1) gv = 2.0 * A * aP - du / (sa * sa) - (jac ? 0.0 : 1.0);
-      DBGV(9, gv);
       if (!upd) {
         if (has) m.grad[li] = gv;
       } else {
@@ -356,14 +365,18 @@ __global__ void __launch_bounds__(512) k_gene(DevModel m, int mode, int jac, int
           const double mu_n = mu_i + es * gm / (1.0 + sqrt(hm)), om_n = om_i + es * go / (1.0 + sqrt(ho));
           m.mu[li] = mu_n;
           m.omega[li] = om_n;
-          DBGV(10, mu_n + om_n);
           if (ahead) {  // next evaluation's draw of this parameter (what k_prep would compute)
             const int64_t gg = m.gene_offset + g;
             const int64_t gi = lane < k ? m.LG.z_alpha + gg * k + lane : (lane == k ? m.LG.z_beta0 + gg : m.LG.amp + gg);
             const double zn = mu_n + exp(om_n) * bvg_normal(m.seed, STREAM_GRAD, tg + 1, (uint64_t)gi);
             m.zeta[li] = zn;
-            if (lane == k + 1) m.Aexp[g] = exp(2.0 * zn);  // approxGP.stan:27
-            DBGV(11, zn);
+            if (lane == k + 1) {
+              const double An = exp(2.0 * zn);  // approxGP.stan:27
+              m.Aexp[g] = An;
+              m.W[g * 32 + lane] = (float)An;
+            } else {
+              m.W[g * 32 + lane] = (float)zn;
+            }
           }
         }
       }
