@@ -170,7 +170,11 @@ static int finalize_model(bvg_fit *f) {
   CUDA_TRY(cudaMalloc(&m.Spart, ts * (size_t)m.nsplit * m.Gpad * 2));
   CUDA_TRY(cudaMemsetAsync(m.Ppart, 0, ts * (size_t)m.nsplit * m.Gpad * m.KP, f->stream));
   CUDA_TRY(cudaMemsetAsync(m.Spart, 0, ts * (size_t)m.nsplit * m.Gpad * 2, f->stream));
-  m.nblk_gene = (int)std::min<int64_t>((m.G + 15) / 16, nsm);  // 16 gene-warps per CTA, at most one CTA per SM
+  // one gene per warp, at most one CTA per SM: 16 warps per CTA, or 21 when that lets every gene be served in a
+  // single pass (a warp that owns two genes runs two dependent latency chains back to back)
+  f->gene_wpb = (m.G > (int64_t)16 * nsm && m.G <= (int64_t)(BVG_GENE_MAX_THREADS / 32) * nsm) ? BVG_GENE_MAX_THREADS / 32 : 16;
+  m.nblk_gene = (int)std::min<int64_t>((m.G + f->gene_wpb - 1) / f->gene_wpb, nsm);
+  f->h_t_grad = 0;
   const int NS = bvg_ns(m.k);
   CUDA_TRY(cudaMalloc(&m.blk, sizeof(double) * (((size_t)m.nblk_gene + 1) * NS + 4 + m.k + m.G + 48)));
   m.tot = m.blk + (size_t)m.nblk_gene * NS;
@@ -357,6 +361,7 @@ static int advi_reset(bvg_fit *f, const double *d_init /* device, NULL keeps mu 
 static int ctl_set(bvg_fit *f, const Ctl &h0) {
   Ctl h = h0;
   h.es = h.eta / sqrt((double)(h.it < 1 ? 1 : h.it));
+  f->h_t_grad = h.t_grad;
   CUDA_TRY(cudaMemcpyAsync(f->m.ctl, &h, sizeof(Ctl), cudaMemcpyHostToDevice, f->stream));
   CUDA_TRY(cudaStreamSynchronize(f->stream));  // h lives on the caller's stack
   return BVG_OK;

@@ -17,6 +17,7 @@
 
 #define BVG_MAX_K 30           // k+2 per-gene parameters map onto one warp in k_gene
 #define BVG_GENE_TILE 128      // genes per likelihood CTA (= TMEM lanes in the tcgen05 kernel)
+#define BVG_GENE_MAX_THREADS 672  // k_gene: up to 21 gene-warps per CTA (one CTA per SM), so 148 SMs hold 3,108 genes in ONE pass
 #define BVG_LOG_TWO_PI 1.8378770664093454835606594728112
 #define BVG_LOG_PI 1.1447298858494001741434273513531
 #define BVG_LOG_TWO 0.69314718055994530941723212145818
@@ -243,6 +244,8 @@ struct bvg_fit {
   bvg_fit_stats st;
   // tcgen05 engine state (k_lik_tc.cu)
   void *tc;
+  int gene_wpb;        // gene-warps per k_gene CTA
+  uint32_t h_t_grad;   // host mirror of ctl->t_grad (lets k_gene draw ahead before its PDL wait)
   double *suff;        // sufficient statistics + scratch (k_suff.cu), lazily built
   bool tiledY;         // Y is stored tile-major (tcgen05 engine)
   // comm: 0 = single GPU, 1 = NCCL all-reduce between kernels, 2 = in-kernel exchange over peer memory

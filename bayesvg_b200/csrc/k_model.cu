@@ -130,10 +130,27 @@ __device__ void finish_body(const DevModel &m, int mode, int jac, int propto, in
   const Layout &L = m.L;
   const double *zt = m.zeta;
   const int nwarps = blockDim.x >> 5;
+  // The threads that own a gene-shared parameter (tid < 2k+5) fetch everything their update needs -- and draw
+  // the next evaluation's normal -- up front; when this CTA also reduces (phase 3) their warps are left out of
+  // the reduction, so those loads and the Philox / Box-Muller chain overlap it instead of following it.
+  const bool gthr = (phase & 2) && (mode == MODE_GRAD_OUT || mode == MODE_ADVI_UPDATE) && tid < 2 * k + 5;
+  const int gw = (2 * k + 5 + 31) >> 5;  // warps holding gradient threads
+  const int w0 = ((phase & 3) == 3 && (mode == MODE_GRAD_OUT || mode == MODE_ADVI_UPDATE) && nwarps >= gw + 4) ? gw : 0;
+  int64_t li_sh = 0;
+  double p_mu = 0, p_om = 0, p_hm = 0, p_ho = 0, p_zeta = 0, p_eps = 0;
+  if (gthr) {
+    li_sh = shared_index(L, k, tid);
+    p_zeta = zt[li_sh];
+    if (mode == MODE_ADVI_UPDATE) {
+      p_mu = m.mu[li_sh]; p_om = m.omega[li_sh]; p_hm = m.hist[li_sh]; p_ho = m.hist[L.D + li_sh];
+      if (ahead) p_eps = bvg_normal(m.seed, STREAM_GRAD, m.ctl->t_grad + 1, (uint64_t)shared_index(m.LG, k, tid));
+    }
+  }
   if (phase & 1) {
-    // every warp owns up to 4 columns and requests all their rows at once (nblk_gene <= 148 rows:
+    // every reducing warp owns up to 4 columns and requests all their rows at once (nblk_gene <= 148 rows:
     // 5 per lane), then sums in a fixed order and finishes with a fixed shuffle tree -> deterministic
-    {
+    const int warp_r = warp - w0, nwr = nwarps - w0;
+    if (warp >= w0) {
       double acc[4] = {0, 0, 0, 0};
       for (int b0 = lane; b0 < m.nblk_gene; b0 += 160) {
         double v[4][5];
@@ -141,7 +158,7 @@ __device__ void finish_body(const DevModel &m, int mode, int jac, int propto, in
         for (int ci = 0; ci < 4; ++ci)
 #pragma unroll
           for (int q = 0; q < 5; ++q) {
-            const int c = warp + ci * nwarps, b = b0 + 32 * q;
+            const int c = warp_r + ci * nwr, b = b0 + 32 * q;
             v[ci][q] = (c < NS && b < m.nblk_gene) ? __ldcg(&m.blk[(int64_t)c * m.nblk_gene + b]) : 0.0;
           }
 #pragma unroll
@@ -151,11 +168,11 @@ __device__ void finish_body(const DevModel &m, int mode, int jac, int propto, in
       }
 #pragma unroll
       for (int ci = 0; ci < 4; ++ci) {
-        const int c = warp + ci * nwarps;
+        const int c = warp_r + ci * nwr;
         const double t = warp_sum(acc[ci]);
         if (lane == 0 && c < NS) m.tot[c] = t;
       }
-      for (int c = warp + 4 * nwarps; c < NS; c += nwarps) {  // only when NS > 4 * nwarps
+      for (int c = warp_r + 4 * nwr; c < NS; c += nwr) {  // only when NS > 4 * reducing warps
         double s2 = 0;
         for (int b = lane; b < m.nblk_gene; b += 32) s2 += __ldcg(&m.blk[(int64_t)c * m.nblk_gene + b]);
         s2 = warp_sum(s2);
@@ -197,7 +214,6 @@ __device__ void finish_body(const DevModel &m, int mode, int jac, int propto, in
   const double Gt = (double)m.G_total, N = (double)m.M * Gt;
   const double j1 = jac ? 1.0 : 0.0;
   const int it = m.ctl->it;
-  const uint32_t tg = m.ctl->t_grad;  // read before the barrier that precedes thread 0's increment
   if (warp == (blockDim.x >> 5) - 1) {  // log density (last warp, concurrently with the gradient threads below)
     double pa = 0;  // prior terms of mu_alpha, sigma_alpha + jacobian of sigma_alpha
     for (int j = lane; j < k; j += 32) {
@@ -238,21 +254,28 @@ __device__ void finish_body(const DevModel &m, int mode, int jac, int propto, in
       const double s = m.shx[3 + j];
       gv = s * (tot[S_AP + k + j] - s) + j1;
     }
-    const int64_t li = shared_index(L, k, i);
-    if (mode == MODE_GRAD_OUT) m.grad[li] = gv;
+    if (mode == MODE_GRAD_OUT) m.grad[li_sh] = gv;
     else {
+      // mean-field update (advi_update) on the prefetched state, then the next evaluation's draw of this parameter
       const bool fin = isfinite(gv);
       if (!fin) atomicAdd(&m.ctl->bad, 1);
-      advi_update(m, li, gv, fin, it, es);
+      const double gm = fin ? gv : 0.0, go = fin ? gv * (p_zeta - p_mu) + 1.0 : 0.0;
+      if (it == 1) { p_hm += gm * gm; p_ho += go * go; }
+      else { p_hm = 0.9 * p_hm + 0.1 * gm * gm; p_ho = 0.9 * p_ho + 0.1 * go * go; }
+      m.hist[li_sh] = p_hm;
+      m.hist[L.D + li_sh] = p_ho;
+      p_mu += es * gm / (1.0 + sqrt(p_hm));
+      p_om += es * go / (1.0 + sqrt(p_ho));
+      m.mu[li_sh] = p_mu;
+      m.omega[li_sh] = p_om;
     }
   }
   __syncthreads();
   DBG(6);
   if (ahead && mode == MODE_ADVI_UPDATE && tid < 2 * k + 5) {
     // every thread of the CTA has finished reading this evaluation's shared zeta (barrier above)
-    const int64_t li = shared_index(L, k, tid), gi = shared_index(m.LG, k, tid);
-    const double z = m.mu[li] + exp(m.omega[li]) * bvg_normal(m.seed, STREAM_GRAD, tg + 1, (uint64_t)gi);
-    m.zeta[li] = z;
+    const double z = p_mu + exp(p_om) * p_eps;
+    m.zeta[li_sh] = z;
     if (tid == 0) m.U[64] = (float)z;
     else if (tid == 1) { const double e = exp(z); m.shx[0] = e; m.U[65] = (float)e; }
     else if (tid == 3) m.shx[1] = exp(z);
@@ -285,14 +308,23 @@ __global__ void __launch_bounds__(512) k_finish(DevModel m, int mode, int jac, i
 // ahead != 0 (ADVI update): every lane also draws its parameter's zeta for the NEXT evaluation right after
 // the update (Philox counter t_grad + 1), so consecutive ADVI evaluations are two launches -- likelihood,
 // k_gene -- instead of three; k_prep then only runs at the start of a batch of steps.
+// tg_next = Philox counter of that next draw (the host mirrors the device counter): the normal of a warp's first
+// gene is generated BEFORE the wait on the likelihood kernel, i.e. while its slower CTAs are still running.
 template <typename T>
-__global__ void __launch_bounds__(512) k_gene(DevModel m, int mode, int jac, int propto, int fuse, int ahead) {
+__global__ void __launch_bounds__(BVG_GENE_MAX_THREADS) k_gene(DevModel m, int mode, int jac, int propto, int fuse, int ahead, uint32_t tg_next) {
   extern __shared__ double sm[];  // [nwarps][NS]
   __shared__ int s_last;
-  griddep_wait();    // Ppart / Spart come from the likelihood kernel
-  griddep_launch();
   const int k = m.k, KP = m.KP, NS = bvg_ns(k);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int64_t gfirst = (int64_t)blockIdx.x * nw + warp;
+  auto global_index = [&](int64_t g) {
+    const int64_t gg = m.gene_offset + g;
+    return (uint64_t)(lane < k ? m.LG.z_alpha + gg * k + lane : (lane == k ? m.LG.z_beta0 + gg : m.LG.amp + gg));
+  };
+  double eps_first = 0.0;
+  if (ahead && lane < k + 2 && gfirst < m.G) eps_first = bvg_normal(m.seed, STREAM_GRAD, tg_next, global_index(gfirst));
+  griddep_wait();    // Ppart / Spart come from the likelihood kernel
+  griddep_launch();
   const Layout &L = m.L;
   const double *zt = m.zeta;
   const double sb = m.shx[0], ma = zt[L.mu_amp], sa = m.shx[1];  // exponentials precomputed by k_prep
@@ -300,7 +332,6 @@ __global__ void __launch_bounds__(512) k_gene(DevModel m, int mode, int jac, int
   const double mual = lane < k ? zt[L.mu_alpha + lane] : 0.0;
   const double sal = lane < k ? m.shx[3 + lane] : 0.0;
   const int it = m.ctl->it;
-  const uint32_t tg = m.ctl->t_grad;
   const double es = m.ctl->es;        // eta / sqrt(it)
   const bool has = lane < k + 2, upd = mode == MODE_ADVI_UPDATE;
   DBG0(0);
@@ -366,9 +397,8 @@ __global__ void __launch_bounds__(512) k_gene(DevModel m, int mode, int jac, int
           m.mu[li] = mu_n;
           m.omega[li] = om_n;
           if (ahead) {  // next evaluation's draw of this parameter (what k_prep would compute)
-            const int64_t gg = m.gene_offset + g;
-            const int64_t gi = lane < k ? m.LG.z_alpha + gg * k + lane : (lane == k ? m.LG.z_beta0 + gg : m.LG.amp + gg);
-            const double zn = mu_n + exp(om_n) * bvg_normal(m.seed, STREAM_GRAD, tg + 1, (uint64_t)gi);
+            const double eps = g == gfirst ? eps_first : bvg_normal(m.seed, STREAM_GRAD, tg_next, global_index(g));
+            const double zn = mu_n + exp(om_n) * eps;
             m.zeta[li] = zn;
             if (lane == k + 1) {
               const double An = exp(2.0 * zn);  // approxGP.stan:27
@@ -414,13 +444,14 @@ __global__ void __launch_bounds__(512) k_gene(DevModel m, int mode, int jac, int
 
 int g_gene_fuse_override = -1;  // diagnostics (bvg_debug_time_gene): force the fuse argument
 int launch_gene_finish(bvg_fit *f, int mode, int jac, int propto, int ahead) {
-  const int wpb = 16;
+  const int wpb = f->gene_wpb;
   const size_t sh = sizeof(double) * wpb * bvg_ns(f->m.k);
-  // single GPU or peer-memory exchange: everything in one launch; NCCL (or k > 251): reduce, all-reduce, finish
+  // single GPU or peer-memory exchange: everything in one launch; NCCL (or 2k+10 > CTA size): reduce, all-reduce, finish
   const bool split = f->comm_mode == 1 || (f->comm_mode == 2 && bvg_ns(f->m.k) > wpb * 32);
   const int fuse = g_gene_fuse_override >= 0 ? g_gene_fuse_override : (split ? 1 : 3);
-  if (f->cfg.precision == BVG_PREC_FP64) CUDA_TRY(launch_pdl(k_gene<double>, dim3(f->m.nblk_gene), dim3(wpb * 32), sh, f->stream, f->m, mode, jac, propto, fuse, ahead));
-  else CUDA_TRY(launch_pdl(k_gene<float>, dim3(f->m.nblk_gene), dim3(wpb * 32), sh, f->stream, f->m, mode, jac, propto, fuse, ahead));
+  const uint32_t tg_next = f->h_t_grad + 1;
+  if (f->cfg.precision == BVG_PREC_FP64) CUDA_TRY(launch_pdl(k_gene<double>, dim3(f->m.nblk_gene), dim3(wpb * 32), sh, f->stream, f->m, mode, jac, propto, fuse, ahead, tg_next));
+  else CUDA_TRY(launch_pdl(k_gene<float>, dim3(f->m.nblk_gene), dim3(wpb * 32), sh, f->stream, f->m, mode, jac, propto, fuse, ahead, tg_next));
   f->st.kernel_launches++;
   if (fuse == 1) {
     BVG_TRY(comm_allreduce(f, f->m.tot, bvg_ns(f->m.k)));
@@ -428,5 +459,6 @@ int launch_gene_finish(bvg_fit *f, int mode, int jac, int propto, int ahead) {
     f->st.kernel_launches += 1;
     CUDA_TRY(cudaGetLastError());
   }
+  if (mode == MODE_ADVI_UPDATE) f->h_t_grad++;  // mirrors ctl->t_grad (incremented by the finish of every ADVI evaluation)
   return BVG_OK;
 }
