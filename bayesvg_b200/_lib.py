@@ -97,6 +97,7 @@ def lib():
     L.bvg_fit_flush_l2.argtypes = [_vp]
     L.bvg_debug_stage_times.argtypes = [_vp, C.c_int, _fp]
     L.bvg_debug_time_gene.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _fp]
+    L.bvg_debug_tc_trace.argtypes = [_vp, C.POINTER(C.c_longlong), C.c_int]
     L.bvg_debug_gene_trace.argtypes = [_vp, C.POINTER(C.c_longlong), C.c_int]
     L.bvg_fit_get_summary.argtypes = [_vp, _dp]
     L.bvg_fit_get_draws.argtypes = [_vp, _dp]

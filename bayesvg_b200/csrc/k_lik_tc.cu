@@ -32,8 +32,8 @@
 #include "bvg_internal.cuh"
 
 #define TC_THREADS 384
-#define TC_NY 4       // Y ring: HBM latency needs depth (4 x 32 KB in flight per SM)
-#define TC_NB 3       // basis ring (24 KB per stage; tiles are L2-resident but the refill sits in the MMA1 -> epilogue -> MMA2 loop)
+#define TC_NY 3       // Y ring: a stage lives from its TMA issue until the epilogue has y in registers (3 x 32 KB in flight per SM = 14 MB chip-wide)
+#define TC_NB 5       // basis ring (24 KB per stage): a stage lives from TMA issue to the END of MMA2 of its chunk (~3,300 cycles); with 3 stages that lifetime, not the tensor pipe, set the chunk period (1,060 cycles measured; tcgen05 floor 480)
 #define TC_CHUNK 64   // spots per chunk
 #define TC_KW 32      // coefficient row width (k+1 <= 24 padded to 32)
 #define YT_BYTES (BVG_GENE_TILE * 128)   // 16 KB: 128 genes x 32 spots fp32

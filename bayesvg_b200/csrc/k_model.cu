@@ -427,16 +427,18 @@ __global__ void __launch_bounds__(BVG_GENE_MAX_THREADS) k_gene(DevModel m, int m
   }
   DBG0(3);
   if (!fuse) return;
-  __threadfence();
+  // last-CTA-done: the barrier orders this CTA's blk[] stores before thread 0's RELEASE on the ticket (release is
+  // cumulative), and the last CTA's ACQUIRE on the same ticket + its barrier make every CTA's stores visible to all
+  // of its threads -- no full-strength __threadfence (MEMBAR.SC) on either side
   __syncthreads();
   if (threadIdx.x == 0) {
-    const unsigned ticket = atomicAdd(&m.ctl->ticket, 1u);
+    unsigned ticket;
+    asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(ticket) : "l"(&m.ctl->ticket) : "memory");
     s_last = ticket == gridDim.x - 1;
     if (s_last) m.ctl->ticket = 0;
   }
   __syncthreads();
   if (!s_last) return;
-  __threadfence();
   DBG(4);
   finish_body(m, mode, jac, propto, fuse, ahead);  // fuse = 3: reduce + finish; fuse = 1 (multi-GPU): reduce only, the all-reduce follows
   DBG(7);

@@ -146,6 +146,16 @@ class Fit:
         B.check(B.lib().bvg_debug_stage_times(self._h, n, out))
         return list(out)[:3]
 
+    def tc_trace(self, nchunk=31):
+        """diagnostics: clock64 stamps of CTA (0,0) of one backward launch of the tcgen05 kernel, [chunk][8]:
+        0 fwd issuer loop top, 1 after MMA1 issue, 2 after MMA2 issue | epilogue thread 96: 3 Y landed, 4 D1 ready,
+        5 after tcgen05.ld, 6 after the residual math, 7 residual published.  Row 30: kernel start / after setup /
+        before final sync / end."""
+        import numpy as np
+        out = (C.c_longlong * (8 * nchunk))()
+        B.check(B.lib().bvg_debug_tc_trace(self._h, out, nchunk))
+        return np.array(list(out), dtype=np.int64).reshape(nchunk, 8)
+
     def time_gene(self, n=100, mode=1, fuse=3, ahead=0):
         """diagnostics: average device ms of n back-to-back k_gene launches"""
         ms = C.c_float()

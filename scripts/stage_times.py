@@ -26,6 +26,14 @@ def main():
     print(f"M={M} G={G} k={k} {lik}: prep {1e3 * st[0]:.1f} us, likelihood {1e3 * st[1]:.1f} us, gene+finish {1e3 * st[2]:.1f} us "
           f"(each stage timed alone); chained evaluation {1e3 * ms:.1f} us = {1e3 / ms:.0f} evals/s; "
           f"likelihood kernel alone back-to-back {1e3 * f.time_lik_kernel(50, False, True):.1f} us, cold L2 {1e3 * f.time_lik_kernel(20, True, True):.1f} us")
+    if os.environ.get("BVG_TC_TRACE"):
+        for rep in range(2):
+            t = f.tc_trace(31)
+            t0 = t[30, 0]
+            print("tc trace (cycles since kernel start): setup done", t[30, 1] - t0, " before final sync", t[30, 2] - t0, " end", t[30, 3] - t0)
+            for c in range(14):
+                if t[c, 0]:
+                    print(f"  chunk {c:2d}: " + " ".join(f"{(x - t0) if x else 0:6d}" for x in t[c]))
     if os.environ.get("BVG_TRACE"):
         for mode, fuse, ah, what in ((3, 0, 0, "lp only, no finish"), (3, 3, 0, "lp only + finish"), (0, 0, 0, "grad out, no finish"),
                                      (1, 0, 0, "update, no finish"), (1, 3, 0, "update + finish"), (1, 0, 1, "update + draw-ahead, no finish"),
