@@ -15,7 +15,8 @@
 
 #include "../../include/bayesvg_b200.h"
 
-#define BVG_MAX_K 30           // k+2 per-gene parameters map onto one warp in k_gene
+#define BVG_SMALL_K 30         // k+2 per-gene parameters map onto one warp: the tuned k_prep / k_gene / sufficient-statistic kernels
+#define BVG_MAX_K 510          // general path (k_prep_big / k_gene_big / k_lik_gen): KP = round_up(k+1, 8) <= 512
 #define BVG_GENE_TILE 128      // genes per likelihood CTA (= TMEM lanes in the tcgen05 kernel)
 #define BVG_GENE_MAX_THREADS 672  // k_gene: up to 21 gene-warps per CTA (one CTA per SM), so 148 SMs hold 3,108 genes in ONE pass
 #define BVG_LOG_TWO_PI 1.8378770664093454835606594728112

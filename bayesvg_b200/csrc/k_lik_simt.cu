@@ -108,8 +108,154 @@ static int launch_t(bvg_fit *f, bool bwd) {
   return BVG_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// k_lik_gen: the same fused pass for a LARGE basis (KP > 32, up to 512: config 5 has k ~ 400), where a thread
+// can no longer hold a whole coefficient row.  CTA = 32 genes x one contiguous range of spots, 256 threads,
+// chunks of 32 spots, the basis dimension walked in blocks of 32:
+//   forward : thread (gene gt, spot group sg) accumulates f for spots sg, sg+8, sg+16, sg+24 over the k-blocks
+//             (Phi' block [32 spots][32] and C block [32][32 genes] staged in shared memory);
+//   residual: as in k_lik_simt; r goes to shared memory;
+//   backward: thread (gene gt, basis group jg) owns P'[j][gt] for j = jg, jg+8, ... (NKB*4 register accumulators
+//             for the CTA's whole spot range), Phi' blocks staged again.
+// It is the fp64 parity path and the fp32 fallback for k > 23; the tcgen05 kernel covers k <= 23.
+template <typename T, int NKB, int LIK, bool BWD>
+__global__ void __launch_bounds__(256) k_lik_gen(const T *__restrict__ Y, int64_t ldY, const T *__restrict__ Phi,
+                                                 const T *__restrict__ C, T *__restrict__ Ppart, T *__restrict__ Spart,
+                                                 int64_t M, int64_t G, int64_t Gpad, int KP, int chunks_per_split,
+                                                 const double *__restrict__ zeta, int64_t tail_idx) {
+  griddep_wait();
+  griddep_launch();
+  __shared__ T Ys[32][33];   // [gene][spot]
+  __shared__ T Pk[32][33];   // [spot][basis within block]
+  __shared__ T Ck[32][33];   // [basis within block][gene]
+  __shared__ T Rs[32][33];   // [spot][gene]
+  __shared__ T red[2][8][32];
+  const int tid = threadIdx.x, gt = tid & 31, grp = tid >> 5;  // grp = spot group (forward) = basis group (backward)
+  const int64_t g0 = (int64_t)blockIdx.x * 32;
+  const int split = blockIdx.y;
+  T Pacc[NKB * 4];
+#pragma unroll
+  for (int i = 0; i < NKB * 4; ++i) Pacc[i] = 0;
+  T acc0 = 0, acc1 = 0, lt = 0, phi = 0;
+  if (LIK == BVG_NB) { lt = (T)zeta[tail_idx]; phi = t_exp(lt); }
+  const int nkb = (KP + 31) / 32;
+  const int64_t s_begin = (int64_t)split * chunks_per_split * 32;
+  for (int ch = 0; ch < chunks_per_split; ++ch) {
+    const int64_t s0 = s_begin + (int64_t)ch * 32;
+    if (s0 >= M) break;
+    for (int r = grp; r < 32; r += 8) {  // Y tile: one 32-spot run of one gene per warp instruction
+      const int64_t gr = g0 + r, s = s0 + gt;
+      Ys[r][gt] = (gr < G && s < M) ? Y[gr * ldY + s] : (T)0;
+    }
+    T f[4] = {0, 0, 0, 0};
+    for (int kb = 0; kb < nkb; ++kb) {
+      __syncthreads();  // previous users of Pk / Ck are done (and Ys is complete on the first pass)
+      for (int r = grp; r < 32; r += 8) {
+        const int j = kb * 32 + gt;
+        Pk[r][gt] = j < KP ? Phi[(s0 + r) * KP + j] : (T)0;   // Phi' has zero-padded rows up to Mpad
+        Ck[gt][r] = j < KP ? C[(g0 + r) * KP + j] : (T)0;     // C has Gpad rows, pads are zero
+      }
+      __syncthreads();
+#pragma unroll 8
+      for (int j = 0; j < 32; ++j) {
+        const T c = Ck[j][gt];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) f[i] += Pk[grp + 8 * i][j] * c;
+      }
+    }
+    const int ns = (int)((M - s0) < 32 ? (M - s0) : 32);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int s = grp + 8 * i;
+      const T y = Ys[gt][s];
+      T r;
+      if (LIK == BVG_GAUSSIAN) {
+        r = y - f[i];
+        acc0 += r * r;
+      } else {
+        const T d = f[i] - lt;
+        const T e = t_exp(-fabs(d));
+        const T Lq = (d > 0 ? d : (T)0) + t_log1p(e);
+        const T sg = (d >= 0 ? (T)1 : e) / ((T)1 + e);
+        r = y - (y + phi) * sg;
+        if (s < ns) {
+          acc0 += y * f[i] - (y + phi) * Lq - y * lt;
+          acc1 += Lq;
+        }
+      }
+      Rs[s][gt] = r;
+    }
+    if (BWD) {
+#pragma unroll
+      for (int kb = 0; kb < NKB; ++kb) {
+        if (kb < nkb) {
+          __syncthreads();  // Rs complete (first pass) / previous Pk consumed
+          for (int r = grp; r < 32; r += 8) {
+            const int j = kb * 32 + gt;
+            Pk[r][gt] = j < KP ? Phi[(s0 + r) * KP + j] : (T)0;
+          }
+          __syncthreads();
+#pragma unroll 8
+          for (int s = 0; s < 32; ++s) {
+            const T r = Rs[s][gt];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) Pacc[kb * 4 + i] += Pk[s][grp + 8 * i] * r;
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  const int64_t g = g0 + gt;
+  const int64_t row = (int64_t)split * Gpad + g;
+  if (BWD) {
+#pragma unroll
+    for (int kb = 0; kb < NKB; ++kb)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int j = kb * 32 + grp + 8 * i;
+        if (j < KP) Ppart[row * KP + j] = Pacc[kb * 4 + i];
+      }
+  }
+  red[0][grp][gt] = acc0;
+  red[1][grp][gt] = acc1;
+  __syncthreads();
+  if (grp == 0) {
+    T a = 0, b = 0;
+    for (int q = 0; q < 8; ++q) { a += red[0][q][gt]; b += red[1][q][gt]; }  // fixed order
+    Spart[row * 2 + 0] = a;
+    Spart[row * 2 + 1] = b;
+  }
+}
+
+template <typename T, int NKB>
+static int launch_gen(bvg_fit *f, bool bwd) {
+  const DevModel &m = f->m;
+  const int64_t nchunks = (m.M + 31) / 32;
+  const int cps = (int)((nchunks + m.nsplit - 1) / m.nsplit);
+  dim3 grid((unsigned)(m.Gpad / 32), (unsigned)m.nsplit);
+#define LAUNCHG(LIK, BWD)                                                                                          \
+  CUDA_TRY(launch_pdl(k_lik_gen<T, NKB, LIK, BWD>, grid, dim3(256), 0, f->stream, (const T *)f->Y, f->ldY, (const T *)f->Phi, \
+                      (const T *)m.C, (T *)m.Ppart, (T *)m.Spart, m.M, m.G, m.Gpad, m.KP, cps, (const double *)m.zeta, m.L.tail))
+  if (m.lik == BVG_GAUSSIAN) { if (bwd) LAUNCHG(BVG_GAUSSIAN, true); else LAUNCHG(BVG_GAUSSIAN, false); }
+  else { if (bwd) LAUNCHG(BVG_NB, true); else LAUNCHG(BVG_NB, false); }
+#undef LAUNCHG
+  f->st.kernel_launches++;
+  return BVG_OK;
+}
+
 template <typename T>
 static int launch_kp(bvg_fit *f, bool bwd) {
+  if (f->m.KP > 32) {
+    const int nkb = (f->m.KP + 31) / 32;
+    if (nkb <= 2) return launch_gen<T, 2>(f, bwd);
+    if (nkb <= 4) return launch_gen<T, 4>(f, bwd);
+    if (nkb <= 8) return launch_gen<T, 8>(f, bwd);
+    if (nkb <= 16) return launch_gen<T, 16>(f, bwd);
+    bvg_set_error("unsupported padded basis width %d", f->m.KP);
+    return BVG_ERR_ARG;
+  }
   switch (f->m.KP) {
     case 8: return launch_t<T, 8>(f, bwd);
     case 16: return launch_t<T, 16>(f, bwd);

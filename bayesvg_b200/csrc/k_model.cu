@@ -7,6 +7,8 @@
 //              gene-shared parameters.
 // Formulas: SURVEY.md A.3 (restating inst/approxGP.stan:25-49 and inst/approxGP4.stan:25-49 of the
 // reference); ADVI update: SURVEY.md A.4 [stan::variational::normal_meanfield::calc_grad].
+#include <algorithm>
+
 #include "bvg_internal.cuh"
 
 // ------------------------------------------------------------------------------------------------
@@ -75,8 +77,80 @@ __global__ void __launch_bounds__(256) k_prep(DevModel m, int mode, int tc, int 
   ((T *)m.C)[g * m.KP + j] = (T)v;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// k_prep_big: the same three phases for any k <= BVG_MAX_K (config 5: k ~ 400).  A block owns gpb genes and
+// walks its parameters in strides of the block size.
+template <typename T>
+__global__ void __launch_bounds__(256) k_prep_big(DevModel m, int mode, int gpb) {
+  extern __shared__ double sh[];  // [2k+5] shared zeta | [k] sigma_alpha | [gpb][k+2] gene zeta | [gpb] A_g
+  griddep_wait();
+  griddep_launch();
+  const int k = m.k, nsh = 2 * k + 5, npg = k + 2, tid = threadIdx.x;
+  double *sal = sh + nsh, *zg = sal + k, *Ag = zg + gpb * npg;
+  const uint32_t stream = mode == PREP_GRAD ? STREAM_GRAD : STREAM_ELBO;
+  const uint32_t t = mode == PREP_GRAD ? m.ctl->t_grad : m.ctl->t_elbo;
+  const int64_t gbase = (int64_t)blockIdx.x * gpb;
+  for (int i = tid; i < nsh + gpb * npg; i += blockDim.x) {
+    const bool is_sh = i < nsh;
+    const int t2 = i - nsh, gl = is_sh ? 0 : t2 / npg, j = is_sh ? 0 : t2 - gl * npg;
+    const int64_t g = gbase + gl;
+    if (!is_sh && g >= m.G) continue;
+    int64_t li, gi;
+    if (is_sh) { li = shared_index(m.L, k, i); gi = shared_index(m.LG, k, i); }
+    else {
+      const int64_t gg = m.gene_offset + g;
+      if (j < k) { li = m.L.z_alpha + g * k + j; gi = m.LG.z_alpha + gg * k + j; }
+      else if (j == k) { li = m.L.z_beta0 + g; gi = m.LG.z_beta0 + gg; }
+      else { li = m.L.amp + g; gi = m.LG.amp + gg; }
+    }
+    double z;
+    if (mode != PREP_NONE) {
+      z = m.mu[li] + exp(m.omega[li]) * bvg_normal(m.seed, stream, t, (uint64_t)gi);
+      if (!is_sh || blockIdx.x == 0) m.zeta[li] = z;
+    } else {
+      z = m.zeta[li];
+    }
+    if (is_sh) sh[i] = z; else zg[gl * npg + j] = z;
+  }
+  __syncthreads();
+  for (int i = tid; i < k + 3 + gpb; i += blockDim.x) {
+    if (i < k) { const double e = exp(sh[5 + k + i]); sal[i] = e; if (blockIdx.x == 0) m.shx[3 + i] = e; }
+    else if (i == k) { if (blockIdx.x == 0) m.shx[1] = exp(sh[3]); }
+    else if (i == k + 1) {
+      if (blockIdx.x == 0) { const double e = exp(sh[4]); m.shx[2] = e; m.shx[3 + k] = m.lik == BVG_GAUSSIAN ? 1.0 / (e * e) : 1.0; }
+    } else if (i == k + 2) { /* sigma_beta0: written after the barrier below (sh[1] is still read as a log here) */ }
+    else {
+      const int q = i - k - 3;
+      const double e = exp(2.0 * zg[q * npg + k + 1]);  // approxGP.stan:27
+      Ag[q] = e;
+      if (gbase + q < m.G) m.Aexp[gbase + q] = e;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) { const double e = exp(sh[1]); sh[1] = e; if (blockIdx.x == 0) m.shx[0] = e; }
+  __syncthreads();
+  for (int i = tid; i < gpb * (k + 1); i += blockDim.x) {
+    const int gl = i / (k + 1), j = i - gl * (k + 1);
+    const int64_t g = gbase + gl;
+    if (g >= m.G) continue;
+    const double v = j < k ? Ag[gl] * (sh[5 + j] + sal[j] * zg[gl * npg + j])  // A_g * alpha_t[j,g] (approxGP.stan:32)
+                           : sh[0] + sh[1] * zg[gl * npg + k];                  // beta0 (approxGP.stan:26)
+    ((T *)m.C)[g * m.KP + j] = (T)v;
+  }
+}
+
 int launch_prep(bvg_fit *f, int mode) {
   const int k = f->m.k;
+  if (k > BVG_SMALL_K) {
+    const int gpb = std::max(1, std::min(8, 512 / (k + 2)));
+    const int grid = (int)((f->m.G + gpb - 1) / gpb);
+    const size_t sh = sizeof(double) * (3 * k + 5 + gpb * (k + 3));
+    if (f->cfg.precision == BVG_PREC_FP64) CUDA_TRY(launch_pdl(k_prep_big<double>, dim3(grid), dim3(256), sh, f->stream, f->m, mode, gpb));
+    else CUDA_TRY(launch_pdl(k_prep_big<float>, dim3(grid), dim3(256), sh, f->stream, f->m, mode, gpb));
+    f->st.kernel_launches++;
+    return BVG_OK;
+  }
   const int gpb = (256 - (2 * k + 5)) / (k + 2);
   const int grid = (int)((f->m.G + gpb - 1) / gpb);
   const size_t sh = sizeof(double) * (3 * k + 5 + gpb * (k + 3));
@@ -133,9 +207,10 @@ __device__ void finish_body(const DevModel &m, int mode, int jac, int propto, in
   // The threads that own a gene-shared parameter (tid < 2k+5) fetch everything their update needs -- and draw
   // the next evaluation's normal -- up front; when this CTA also reduces (phase 3) their warps are left out of
   // the reduction, so those loads and the Philox / Box-Muller chain overlap it instead of following it.
-  const bool gthr = (phase & 2) && (mode == MODE_GRAD_OUT || mode == MODE_ADVI_UPDATE) && tid < 2 * k + 5;
+  const bool big = 2 * k + 5 > (int)blockDim.x - 32;  // large basis: shared parameters are walked in a loop (no prefetch, no draw-ahead)
+  const bool gthr = !big && (phase & 2) && (mode == MODE_GRAD_OUT || mode == MODE_ADVI_UPDATE) && tid < 2 * k + 5;
   const int gw = (2 * k + 5 + 31) >> 5;  // warps holding gradient threads
-  const int w0 = ((phase & 3) == 3 && (mode == MODE_GRAD_OUT || mode == MODE_ADVI_UPDATE) && nwarps >= gw + 4) ? gw : 0;
+  const int w0 = (!big && (phase & 3) == 3 && (mode == MODE_GRAD_OUT || mode == MODE_ADVI_UPDATE) && nwarps >= gw + 4) ? gw : 0;
   int64_t li_sh = 0;
   double p_mu = 0, p_om = 0, p_hm = 0, p_ho = 0, p_zeta = 0, p_eps = 0;
   if (gthr) {
@@ -237,6 +312,31 @@ __device__ void finish_body(const DevModel &m, int mode, int jac, int propto, in
       }
       s_lp = lp;
     }
+  } else if (big && (mode == MODE_GRAD_OUT || mode == MODE_ADVI_UPDATE)) {
+    const double es = m.ctl->es;
+    for (int i = tid; i < 2 * k + 5; i += blockDim.x - 32) {  // every warp but the last (which forms the log density)
+      double gv;
+      if (i == 0) gv = tot[S_R] - mb / 4.0;
+      else if (i == 1) gv = sb * (tot[S_RZ] - sb) + j1;
+      else if (i == 2) gv = tot[S_DU] / (sa * sa) - ma / 4.0;
+      else if (i == 3) gv = -Gt + tot[S_DU2] / (sa * sa) - sa * sa + j1;
+      else if (i == 4) {
+        if (m.lik == BVG_GAUSSIAN) gv = -N + tot[S_SSE] / (tl * tl) - tl * tl + j1;
+        else gv = tl * (tot[S_DG] - tot[S_L] - tot[S_R] / tl) - 0.5 * tl * tl / (1.0 + tl * tl / 4.0) + j1;
+      } else if (i < 5 + k) gv = tot[S_AP + (i - 5)] - zt[L.mu_alpha + (i - 5)] / 4.0;
+      else {
+        const int j = i - 5 - k;
+        const double s = m.shx[3 + j];
+        gv = s * (tot[S_AP + k + j] - s) + j1;
+      }
+      const int64_t li = shared_index(L, k, i);
+      if (mode == MODE_GRAD_OUT) m.grad[li] = gv;
+      else {
+        const bool fin = isfinite(gv);
+        if (!fin) atomicAdd(&m.ctl->bad, 1);
+        advi_update(m, li, gv, fin, it, es);
+      }
+    }
   } else if ((mode == MODE_GRAD_OUT || mode == MODE_ADVI_UPDATE) && tid < 2 * k + 5) {
     const double es = m.ctl->es;
     const int i = tid;
@@ -272,7 +372,7 @@ __device__ void finish_body(const DevModel &m, int mode, int jac, int propto, in
   }
   __syncthreads();
   DBG(6);
-  if (ahead && mode == MODE_ADVI_UPDATE && tid < 2 * k + 5) {
+  if (ahead && !big && mode == MODE_ADVI_UPDATE && tid < 2 * k + 5) {
     // every thread of the CTA has finished reading this evaluation's shared zeta (barrier above)
     const double z = p_mu + exp(p_om) * p_eps;
     m.zeta[li_sh] = z;
@@ -283,7 +383,7 @@ __device__ void finish_body(const DevModel &m, int mode, int jac, int propto, in
     else if (tid >= 5 + k) { const double e = exp(z); m.shx[3 + tid - 5 - k] = e; m.U[32 + tid - 5 - k] = (float)e; }
     else if (tid >= 5) m.U[tid - 5] = (float)z;
   }
-  if (mode == MODE_ADVI_UPDATE && tid == 2 * k + 5) m.ctl->es = m.ctl->eta / sqrt((double)(it + 1));
+  if (mode == MODE_ADVI_UPDATE && tid == (big ? 0 : 2 * k + 5)) m.ctl->es = m.ctl->eta / sqrt((double)(it + 1));
   if (tid == 0) {
     const double lp = s_lp;
     m.ctl->lp = lp;
@@ -444,6 +544,108 @@ __global__ void __launch_bounds__(BVG_GENE_MAX_THREADS) k_gene(DevModel m, int m
   DBG(7);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// k_gene_big: k_gene for any k <= BVG_MAX_K.  One warp per gene; the k+2 parameters of the gene are walked in
+// chunks of 32 lanes.  The amplitude gradient needs sum_j alpha_j P_j over ALL chunks, so lane 0 updates it after
+// the walk.  The per-basis cross-gene sums (S_AP slots) accumulate in the warp's shared-memory row.
+template <typename T>
+__global__ void __launch_bounds__(512) k_gene_big(DevModel m, int mode, int jac, int propto, int fuse) {
+  extern __shared__ double sm[];  // [nwarps][NS]
+  __shared__ int s_last;
+  griddep_wait();
+  griddep_launch();
+  const int k = m.k, KP = m.KP, NS = bvg_ns(k);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const Layout &L = m.L;
+  const double *zt = m.zeta;
+  const double sb = m.shx[0], ma = zt[L.mu_amp], sa = m.shx[1], inv_s2 = m.shx[3 + k];
+  const int it = m.ctl->it;
+  const double es = m.ctl->es;
+  const bool upd = mode == MODE_ADVI_UPDATE, wr = mode == MODE_GRAD_OUT || upd;
+  double *row = sm + warp * NS;
+  for (int c = lane; c < NS; c += 32) row[c] = 0.0;
+  __syncwarp();
+  double aR = 0, aRz = 0, aDu = 0, aDu2 = 0, aS0 = 0, aS1 = 0, aZ2 = 0, aU = 0;
+  const T *Pp = (const T *)m.Ppart, *Sp = (const T *)m.Spart;
+  for (int64_t g = (int64_t)blockIdx.x * nw + warp; g < m.G; g += (int64_t)gridDim.x * nw) {
+    const double A = m.Aexp[g];
+    double s0 = 0, s1 = 0;
+    for (int sp = lane; sp < m.nsplit; sp += 32) {
+      const int64_t r = (int64_t)sp * m.Gpad + g;
+      s0 += (double)Sp[r * 2];
+      s1 += (double)Sp[r * 2 + 1];
+    }
+    // lanes hold different splits: a fixed shuffle tree keeps the sum deterministic
+    s0 = warp_sum(s0); s1 = warp_sum(s1);
+    double aP = 0, z2 = 0, R = 0, zb = 0, u = 0;
+    for (int j0 = 0; j0 < k + 2; j0 += 32) {
+      const int j = j0 + lane;
+      if (j >= k + 2) continue;
+      const int64_t li = j < k ? L.z_alpha + g * k + j : (j == k ? L.z_beta0 + g : L.amp + g);
+      const double z = zt[li];
+      if (j == k + 1) { u = z; continue; }
+      double Pj = 0;
+      for (int sp = 0; sp < m.nsplit; ++sp) Pj += (double)Pp[((int64_t)sp * m.Gpad + g) * KP + j];  // fixed order
+      Pj *= inv_s2;
+      double gv;
+      if (j < k) {
+        const double sal = m.shx[3 + j], alpha = zt[L.mu_alpha + j] + sal * z, AP = A * Pj;
+        aP += alpha * Pj;
+        z2 += z * z;
+        row[S_AP + j] += AP;
+        row[S_AP + k + j] += AP * z;
+        gv = sal * AP - z;
+      } else {  // j == k: the ones column of Phi' -> R_g = sum_s r_sg
+        R = Pj; zb = z;
+        gv = sb * R - zb;
+      }
+      if (mode == MODE_GRAD_OUT) m.grad[li] = gv;
+      else if (upd) {
+        const bool fin = isfinite(gv);
+        if (!fin) atomicAdd(&m.ctl->bad, 1);
+        advi_update(m, li, gv, fin, it, es);
+      }
+    }
+    aP = warp_sum(aP); z2 = warp_sum(z2); R = warp_sum(R); zb = warp_sum(zb); u = warp_sum(u);
+    z2 += zb * zb;
+    const double du = u - ma;
+    aR += R; aRz += R * zb; aDu += du; aDu2 += du * du; aS0 += s0; aS1 += s1; aZ2 += z2; aU += u;
+    if (wr && lane == 0) {
+      const int64_t li = L.amp + g;
+      const double gv = 2.0 * A * aP - du / (sa * sa) - (jac ? 0.0 : 1.0);
+      if (mode == MODE_GRAD_OUT) m.grad[li] = gv;
+      else {
+        const bool fin = isfinite(gv);
+        if (!fin) atomicAdd(&m.ctl->bad, 1);
+        advi_update(m, li, gv, fin, it, es);
+      }
+    }
+  }
+  __syncwarp();
+  if (lane == 0) {
+    row[S_R] = aR; row[S_RZ] = aRz; row[S_DU] = aDu; row[S_DU2] = aDu2; row[S_SSE] = aS0; row[S_Z2] = aZ2;
+    row[S_U] = aU; row[S_L] = aS1; row[S_LG] = 0; row[S_DG] = 0;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < NS; c += blockDim.x) {
+    double s = 0;
+    for (int w = 0; w < nw; ++w) s += sm[w * NS + c];
+    m.blk[(int64_t)c * gridDim.x + blockIdx.x] = s;
+  }
+  if (!fuse) return;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned ticket;
+    asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(ticket) : "l"(&m.ctl->ticket) : "memory");
+    s_last = ticket == gridDim.x - 1;
+    if (s_last) m.ctl->ticket = 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  finish_body(m, mode, jac, propto, fuse, 0);
+}
+
 int g_gene_fuse_override = -1;  // diagnostics (bvg_debug_time_gene): force the fuse argument
 int launch_gene_finish(bvg_fit *f, int mode, int jac, int propto, int ahead) {
   const int wpb = f->gene_wpb;
@@ -452,6 +654,30 @@ int launch_gene_finish(bvg_fit *f, int mode, int jac, int propto, int ahead) {
   const bool split = f->comm_mode == 1 || (f->comm_mode == 2 && bvg_ns(f->m.k) > wpb * 32);
   const int fuse = g_gene_fuse_override >= 0 ? g_gene_fuse_override : (split ? 1 : 3);
   const uint32_t tg_next = f->h_t_grad + 1;
+  if (f->m.k > BVG_SMALL_K) {
+    // large basis: 8 gene-warps per CTA keep the [warps][2k+10] shared-memory rows small; no draw-ahead
+    const int wb = 8;
+    const size_t shb = sizeof(double) * wb * bvg_ns(f->m.k);
+    const bool splitb = f->comm_mode != 0;  // 2k+10 sums exceed one CTA's exchange width: reduce, all-reduce, finish
+    const int fuseb = g_gene_fuse_override >= 0 ? g_gene_fuse_override : (splitb ? 1 : 3);
+    static bool attr_set = false;
+    if (!attr_set) {
+      CUDA_TRY(cudaFuncSetAttribute(k_gene_big<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      CUDA_TRY(cudaFuncSetAttribute(k_gene_big<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      attr_set = true;
+    }
+    if (f->cfg.precision == BVG_PREC_FP64) CUDA_TRY(launch_pdl(k_gene_big<double>, dim3(f->m.nblk_gene), dim3(wb * 32), shb, f->stream, f->m, mode, jac, propto, fuseb));
+    else CUDA_TRY(launch_pdl(k_gene_big<float>, dim3(f->m.nblk_gene), dim3(wb * 32), shb, f->stream, f->m, mode, jac, propto, fuseb));
+    f->st.kernel_launches++;
+    if (fuseb == 1) {
+      BVG_TRY(comm_allreduce(f, f->m.tot, bvg_ns(f->m.k)));
+      k_finish<<<1, 512, 0, f->stream>>>(f->m, mode, jac, propto, 2, 0);
+      f->st.kernel_launches += 1;
+      CUDA_TRY(cudaGetLastError());
+    }
+    if (mode == MODE_ADVI_UPDATE) f->h_t_grad++;
+    return BVG_OK;
+  }
   if (f->cfg.precision == BVG_PREC_FP64) CUDA_TRY(launch_pdl(k_gene<double>, dim3(f->m.nblk_gene), dim3(wpb * 32), sh, f->stream, f->m, mode, jac, propto, fuse, ahead, tg_next));
   else CUDA_TRY(launch_pdl(k_gene<float>, dim3(f->m.nblk_gene), dim3(wpb * 32), sh, f->stream, f->m, mode, jac, propto, fuse, ahead, tg_next));
   f->st.kernel_launches++;

@@ -26,7 +26,7 @@ __global__ void __launch_bounds__(256) k_suff_stats(const T *__restrict__ Y, int
   __shared__ double red[8];
   const int64_t g = blockIdx.x;
   const int64_t tile = g / BVG_GENE_TILE, r = g - tile * BVG_GENE_TILE, nch32 = ldY / 32;
-  double acc[BVG_MAX_K + 2];
+  double acc[BVG_SMALL_K + 2];
   for (int j = 0; j < k + 2; ++j) acc[j] = 0;
   for (int64_t s = threadIdx.x; s < M; s += blockDim.x) {
     const int64_t yi = tiled ? ((tile * nch32 + s / 32) * BVG_GENE_TILE + r) * 32 + (s & 31) : g * ldY + s;
@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(256) k_suff_elbo(DevModel m, int gpb, double *
 // log_prob<propto=false, jacobian=true> from the (all-reduced) sums and the draw's shared parameters
 __global__ void __launch_bounds__(128) k_suff_finish(DevModel m, int nblk, const double *__restrict__ part, double *__restrict__ tot4,
                                                      double *__restrict__ lps, int phase) {
-  __shared__ double sz[2 * BVG_MAX_K + 5];
+  __shared__ double sz[2 * BVG_SMALL_K + 5];
   __shared__ double red[4];
   const int k = m.k, d = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (phase & 1) {  // warp q sums column q
@@ -200,6 +200,7 @@ void suff_destroy(bvg_fit *f) {
 // S log densities log_prob<false, true>(zeta_d), d = 0..S-1, draws t_elbo .. t_elbo+S-1 (the caller advances t_elbo)
 int suff_elbo(bvg_fit *f, int S, double *lps_host) {
   if (f->cfg.likelihood != BVG_GAUSSIAN) { bvg_set_error("sufficient-statistic ELBO exists for the gaussian likelihood only"); return BVG_ERR_ARG; }
+  if (f->m.k > BVG_SMALL_K) { bvg_set_error("sufficient-statistic ELBO supports n.basis.fns <= %d", BVG_SMALL_K); return BVG_ERR_ARG; }
   BVG_TRY(suff_build(f, S));
   SuffState *st = (SuffState *)f->suff;
   const DevModel &m = f->m;

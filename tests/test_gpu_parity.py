@@ -64,6 +64,48 @@ def test_log_prob_vs_oracle(lik, prec, eng, M, G, k):
     f.close()
 
 
+@pytest.mark.parametrize("lik", ["gaussian", "nb"])
+@pytest.mark.parametrize("prec", ["fp64", "fast"])
+@pytest.mark.parametrize("M,G,k", [(300, 70, 31), (640, 45, 64), (700, 33, 200), (900, 40, 401)])
+def test_log_prob_large_basis_vs_oracle(lik, prec, M, G, k):
+    """BASELINE config 5 has k ~ 400 basis functions: the general path (k_prep_big / k_lik_gen / k_gene_big)"""
+    p = make_problem(M, G, k, lik, seed=M + k)
+    o = orc.Oracle(p["phi"], p["y"], lik, nthreads=4)
+    f = _fit(p["phi"], p["y"], lik, prec, "auto")
+    assert f.stats()["engine_used"] == 1
+    rng = np.random.default_rng(6)
+    for scale, jac, pro in ((0.0, True, True), (0.2, True, False), (0.5, False, False)):
+        th = rng.normal(0, 1, o.D) * scale
+        lp, g = f.log_prob(th, jac, pro)
+        rlp, rg = o.log_prob(th, jac, pro)
+        assert abs(lp - rlp) <= ACHIEVED[prec] * max(1.0, abs(rlp)), (lp, rlp)
+        assert rel_err(g, rg) <= ACHIEVED[prec] * 5
+        assert f.log_prob(th, jac, pro, grad=False) == pytest.approx(lp, rel=1e-12 if prec == "fp64" else 1e-5)
+    f.close()
+
+
+def test_large_basis_advi_trajectory_and_fit():
+    """same-Philox ADVI steps on the general path against the oracle (fp64), then a short full fit at k = 64"""
+    p = make_problem(500, 24, 64, "gaussian", seed=77)
+    o = orc.Oracle(p["phi"], p["y"], "gaussian", nthreads=4)
+    f = _fit(p["phi"], p["y"], "gaussian", "fp64", "auto", seed=5)
+    mu, om, hist = np.zeros(o.D), np.zeros(o.D), np.zeros(2 * o.D)
+    f.set_variational(mu, None)
+    f.advi_steps(0, 0.1, reset=True)
+    for it in range(1, 13):
+        o.advi_step(mu, om, hist, 0.1, it, 5, it - 1)
+    f.advi_steps(12, 0.1)
+    gmu, gom = f.get_variational()
+    assert rel_err(gmu, mu) < 1e-9 and rel_err(gom, om) < 1e-9
+    e, _ = f.elbo(8)
+    assert np.isfinite(e)
+    f.close()
+    f = _fit(p["phi"], p["y"], "gaussian", "fast", "auto", seed=5, n_iter=300, mle_iter=40, n_draws=256, elbo_samples=20)
+    tab = f.run()
+    assert tab.shape == (24, 8) and np.all(np.isfinite(tab)) and np.all(tab[:, 0] > 0)
+    f.close()
+
+
 def test_nb_integer_input_equals_double_input():
     p = make_problem(200, 40, 5, "nb", seed=3)
     th = np.random.default_rng(0).normal(0, 0.3, 5 + 2 * 40 + 10 + 200)
@@ -295,7 +337,7 @@ def test_error_paths():
     with pytest.raises(ValueError):
         f.log_prob(np.zeros(3))
     with pytest.raises(bvg._lib.BvgError):
-        bvg.Fit(np.linalg.qr(np.random.default_rng(0).normal(size=(60, 31)))[0], np.zeros((60, 2)))
+        bvg.Fit(np.linalg.qr(np.random.default_rng(0).normal(size=(600, 511)))[0], np.zeros((600, 2)))  # k > 510
     with pytest.raises(bvg._lib.BvgError):
         bvg.Fit(p["phi"], -np.ones((40, 5), dtype=np.int32), "nb")
 
