@@ -126,8 +126,6 @@ def findSpatiallyVariableFeaturesBayes(sp_obj=None, naive_hvgs=None, likelihood=
         raise NotImplementedError("opencl.params is meaningless here: the fit always runs on the CUDA device.")
     if lscale_estimator != "kmeans":
         raise NotImplementedError("lscale.estimator = 'variogram' is not built in bayesvg_b200; use 'kmeans'.")
-    if gene_depth_adjust:
-        raise NotImplementedError("gene.depth.adjust = TRUE (approxGP2/approxGP3) is not built yet.")
     t_start = time.time()
     # coordinates (:154-161)
     X = scale_coords(sp_obj.coords)
@@ -146,6 +144,13 @@ def findSpatiallyVariableFeaturesBayes(sp_obj=None, naive_hvgs=None, likelihood=
         Y = np.asfortranarray(((v - v.mean()) / v.std(ddof=1)).T)  # global z-score (:185); M x G
     else:
         Y = np.asfortranarray(expr.astype(np.int32).T)
+    # gene.depth.adjust (:293-303): gene_depths = log(rowSums(counts[naive.hvgs, ])) -> approxGP2 / approxGP3
+    gene_depths = None
+    if gene_depth_adjust:
+        if sp_obj.counts is None:
+            _abort("gene.depth.adjust = TRUE needs the 'counts' layer")
+        with np.errstate(divide="ignore"):
+            gene_depths = np.log(np.asarray(sp_obj.counts)[rows, :].sum(axis=1).astype(np.float64))
     # length-scale + basis (:200-288)
     if centers is None:
         centers = kmeans_centers(X, n_basis_fns, 100, 10, kmeans_rng)
@@ -161,9 +166,9 @@ def findSpatiallyVariableFeaturesBayes(sp_obj=None, naive_hvgs=None, likelihood=
                elbo_samples=int(elbo_samples), seed=int(random_seed), verbose=int(bool(verbose)), device=device)
     if shard is not None:
         from . import dist
-        table, model = dist.fit_sharded(phi, Y, shard, likelihood, precision, engine, cfg)
+        table, model = dist.fit_sharded(phi, Y, shard, likelihood, precision, engine, cfg, gene_depths=gene_depths)
     else:
-        fit = E.Fit(phi, Y, likelihood, precision, engine, **cfg)
+        fit = E.Fit(phi, Y, likelihood, precision, engine, gene_depths=gene_depths, **cfg)
         table = fit.run()
         model = None
         if save_model:

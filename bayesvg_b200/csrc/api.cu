@@ -50,6 +50,8 @@ extern "C" void bvg_config_default(bvg_config *c) {
   c->world_size = 1;
   c->gene_offset = 0;
   c->G_total = 0;
+  c->elbo_suffstat = 0;
+  c->depth_adjust = 0;
 }
 
 int lbfgs_run(bvg_fit *f, const double *d_theta0, double *d_out);  // lbfgs.cu
@@ -96,6 +98,8 @@ static void free_model(bvg_fit *f) {
   cudaFree(f->Y); cudaFree(f->Phi); cudaFree(f->dvec); cudaFree(f->summary); cudaFree(f->draws);
   cudaFree(f->m.C); cudaFree(f->m.Ppart); cudaFree(f->m.Spart); cudaFree(f->m.blk); cudaFree(f->m.ctl);
   cudaFree((void *)f->m.hist_val);
+  cudaFree((void *)f->m.depths);
+  f->m.depths = nullptr;
   f->Y = f->Phi = nullptr; f->dvec = f->summary = f->draws = nullptr;
   f->m.C = f->m.Ppart = f->m.Spart = nullptr; f->m.blk = nullptr; f->m.ctl = nullptr; f->m.hist_val = nullptr;
 }
@@ -114,6 +118,7 @@ extern "C" void bvg_fit_destroy(bvg_fit *f) {
     for (int b = 0; b < 2; ++b) { cudaEventDestroy(f->ev_copied[b]); cudaEventDestroy(f->ev_staged[b]); }
   }
   delete[] f->h_theta_mle;
+  delete[] f->h_depths;
   cudaEventDestroy(f->ev0); cudaEventDestroy(f->ev1);
   cudaStreamDestroy(f->stream);
   delete f;
@@ -140,8 +145,9 @@ static int finalize_model(bvg_fit *f) {
   m.G_total = f->cfg.G_total > 0 ? f->cfg.G_total : m.G;
   m.gene_offset = f->cfg.gene_offset;
   if (m.gene_offset < 0 || m.gene_offset + m.G > m.G_total) { bvg_set_error("gene shard [%lld, %lld) outside G_total = %lld", (long long)m.gene_offset, (long long)(m.gene_offset + m.G), (long long)m.G_total); return BVG_ERR_ARG; }
-  m.L = make_layout(m.lik, m.G, m.k);
-  m.LG = make_layout(m.lik, m.G_total, m.k);
+  m.depth = f->cfg.depth_adjust ? 1 : 0;
+  m.L = make_layout(m.lik, m.G, m.k, m.depth);
+  m.LG = make_layout(m.lik, m.G_total, m.k, m.depth);
   m.seed = f->cfg.seed;
   const int64_t D = m.L.D;
   // state vectors: mu | omega | hist(2D) | zeta | grad | init | weights
@@ -193,7 +199,36 @@ static int finalize_model(bvg_fit *f) {
   if (fp64) BVG_TRY(stage_phi<double>(f->phi64, (double *)f->Phi, m.M, f->Mpad, m.k, m.KP, f->stream));
   else BVG_TRY(stage_phi<float>(f->phi64, (float *)f->Phi, m.M, f->Mpad, m.k, m.KP, f->stream));
   if (f->engine == BVG_ENGINE_TCGEN05) BVG_TRY(tc_setup(f));
+  if (m.depth) {
+    double *d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, sizeof(double) * m.G));
+    CUDA_TRY(cudaMemsetAsync(d, 0, sizeof(double) * m.G, f->stream));
+    m.depths = d;
+    if (f->have_depths) {
+      if (f->n_depths != m.G) { bvg_set_error("gene_depths has %lld entries but y has %lld genes", (long long)f->n_depths, (long long)m.G); return BVG_ERR_ARG; }
+      CUDA_TRY(cudaMemcpyAsync(d, f->h_depths, sizeof(double) * m.G, cudaMemcpyHostToDevice, f->stream));
+    }
+  }
   CUDA_TRY(cudaStreamSynchronize(f->stream));
+  return BVG_OK;
+}
+
+extern "C" int bvg_fit_set_gene_depths(bvg_fit *f, const double *gene_depths, int64_t G) {
+  if (!f || !gene_depths || G < 1) { bvg_set_error("null or empty gene_depths"); return BVG_ERR_ARG; }
+  if (!f->cfg.depth_adjust) { bvg_set_error("gene_depths belong to the depth-adjusted model: create the fit with depth_adjust = 1"); return BVG_ERR_STATE; }
+  for (int64_t g = 0; g < G; ++g)
+    if (!std::isfinite(gene_depths[g])) { bvg_set_error("gene_depths[%lld] is not finite (a gene with zero total count?)", (long long)g); return BVG_ERR_ARG; }
+  if (f->have_y && G != f->m.G) { bvg_set_error("gene_depths has %lld entries but y has %lld genes", (long long)G, (long long)f->m.G); return BVG_ERR_ARG; }
+  CUDA_TRY(cudaSetDevice(f->cfg.device));
+  delete[] f->h_depths;
+  f->h_depths = new double[G];
+  memcpy(f->h_depths, gene_depths, sizeof(double) * G);
+  f->n_depths = G;
+  f->have_depths = true;
+  if (f->have_y) {
+    CUDA_TRY(cudaMemcpyAsync((void *)f->m.depths, f->h_depths, sizeof(double) * G, cudaMemcpyHostToDevice, f->stream));
+    CUDA_TRY(cudaStreamSynchronize(f->stream));
+  }
   return BVG_OK;
 }
 
@@ -312,14 +347,15 @@ extern "C" int bvg_fit_set_y_i32(bvg_fit *f, const int32_t *y, int64_t M, int64_
   return set_y_impl<int32_t>(f, y, M, G);
 }
 
-static int need_ready(bvg_fit *f) {
+static int need_ready(bvg_fit *f, bool need_depths = true) {
   if (!f) { bvg_set_error("null fit"); return BVG_ERR_ARG; }
   if (!f->have_phi || !f->have_y) { bvg_set_error("set phi and y first"); return BVG_ERR_STATE; }
+  if (need_depths && f->cfg.depth_adjust && !f->have_depths) { bvg_set_error("gene.depth.adjust: call bvg_fit_set_gene_depths first"); return BVG_ERR_STATE; }
   CUDA_TRY(cudaSetDevice(f->cfg.device));
   return BVG_OK;
 }
 extern "C" int bvg_fit_dim(bvg_fit *f, int64_t *D) {
-  BVG_TRY(need_ready(f));
+  BVG_TRY(need_ready(f, false));
   *D = f->m.L.D;
   return BVG_OK;
 }

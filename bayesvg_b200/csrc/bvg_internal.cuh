@@ -32,10 +32,19 @@ __host__ __device__ inline int bvg_ns(int k) { return S_AP + 2 * k; }
 struct Layout {
   int64_t mu_beta0, sigma_beta0, z_beta0, mu_amp, sigma_amp, amp, mu_alpha, sigma_alpha, z_alpha, tail, D;
 };
-// inst/approxGP.stan:12-23 and inst/approxGP4.stan:12-23 (declaration order)
-__host__ __device__ inline Layout make_layout(int lik, int64_t G, int k) {
+// inst/approxGP.stan:12-23 and inst/approxGP4.stan:12-23 (declaration order); depth-adjusted programs
+// inst/approxGP2.stan:13-23 / approxGP3.stan:13-23: beta0, beta1, sigma_y | phi_nb, amplitude[G], mu_amplitude,
+// sigma_amplitude, mu_alpha[k], sigma_alpha[k], z_alpha_t[k,G] -- there mu_beta0 / sigma_beta0 are the slots of
+// beta0 / beta1 (beta1 unconstrained) and z_beta0 does not exist.
+__host__ __device__ inline Layout make_layout(int lik, int64_t G, int k, int depth) {
   Layout L;
   L.mu_beta0 = 0; L.sigma_beta0 = 1; L.z_beta0 = 2;
+  if (depth) {
+    L.z_beta0 = -1; L.tail = 2; L.amp = 3; L.mu_amp = 3 + G; L.sigma_amp = 4 + G; L.mu_alpha = 5 + G;
+    L.sigma_alpha = L.mu_alpha + k; L.z_alpha = L.sigma_alpha + k;
+    L.D = 5 + G + 2 * (int64_t)k + (int64_t)k * G;
+    return L;
+  }
   if (lik == BVG_GAUSSIAN) {
     L.mu_amp = 2 + G; L.sigma_amp = 3 + G; L.amp = 4 + G; L.mu_alpha = 4 + 2 * G;
     L.sigma_alpha = L.mu_alpha + k; L.z_alpha = L.sigma_alpha + k; L.tail = L.z_alpha + (int64_t)k * G;
@@ -90,6 +99,8 @@ struct PeerCtx {
 
 struct DevModel {
   int lik, k, KP, nsplit;
+  int depth, pad0;           // depth-adjusted program (approxGP2/3): the intercept "z" of gene g is the datum depths[g]
+  const double *depths;      // [G] gene_depths
   int64_t M, G, Gpad, gene_offset, G_total;
   Layout L, LG;  // local layout (this rank's genes) and global layout (RNG indices)
   uint64_t seed;
@@ -237,7 +248,9 @@ struct bvg_fit {
   size_t stage_bytes;
   cudaStream_t copy_stream;
   cudaEvent_t ev_copied[2], ev_staged[2];
-  bool have_phi, have_y, have_mle, have_vi, have_summary;
+  bool have_phi, have_y, have_mle, have_vi, have_summary, have_depths;
+  double *h_depths;    // host copy of gene_depths (uploaded when the model is finalised)
+  int64_t n_depths;
   double *h_theta_mle;
   // trace / stats
   double trace[4 * 64];

@@ -29,7 +29,9 @@ __global__ void __launch_bounds__(256) k_prep(DevModel m, int mode, int tc, int 
   const int t2 = tid - nsh, gl = t2 >= 0 ? t2 / npg : -1, j = t2 >= 0 ? t2 - gl * npg : 0;
   const int64_t g = (int64_t)blockIdx.x * gpb + gl;
   const bool is_sh = tid < nsh, is_gene = gl >= 0 && gl < gpb && g < m.G;
-  if (is_sh || is_gene) {
+  if (is_gene && m.depth && j == k) {
+    zg[gl * npg + k] = m.depths[g];  // depth-adjusted programs: the intercept "z" of the gene is data (approxGP2.stan:46)
+  } else if (is_sh || is_gene) {
     int64_t li, gi;
     if (is_sh) { li = shared_index(m.L, k, tid); gi = shared_index(m.LG, k, tid); }
     else {
@@ -51,7 +53,7 @@ __global__ void __launch_bounds__(256) k_prep(DevModel m, int mode, int tc, int 
   // ---- phase 2: the exponentials (sigma_alpha, sigma_beta0 in place, A_g = amplitude^2) ----
   // (also published for k_gene / finish_body: shx = [sigma_beta0, sigma_amplitude, tail, sigma_alpha[k]], Aexp[g])
   if (tid < k) { const double e = exp(sh[5 + k + tid]); sal[tid] = e; if (blockIdx.x == 0) m.shx[3 + tid] = e; }
-  else if (tid == k) { const double e = exp(sh[1]); sh[1] = e; if (blockIdx.x == 0) m.shx[0] = e; }
+  else if (tid == k) { const double e = m.depth ? sh[1] : exp(sh[1]); sh[1] = e; if (blockIdx.x == 0) m.shx[0] = e; }  // sigma_beta0 | beta1
   else if (tid > k && tid <= k + gpb) {
     const int q = tid - k - 1;
     const double e = exp(2.0 * zg[q * npg + k + 1]);  // approxGP.stan:27
@@ -96,6 +98,7 @@ __global__ void __launch_bounds__(256) k_prep_big(DevModel m, int mode, int gpb)
     const int t2 = i - nsh, gl = is_sh ? 0 : t2 / npg, j = is_sh ? 0 : t2 - gl * npg;
     const int64_t g = gbase + gl;
     if (!is_sh && g >= m.G) continue;
+    if (!is_sh && m.depth && j == k) { zg[gl * npg + k] = m.depths[g]; continue; }  // the intercept "z" is data (approxGP2.stan:46)
     int64_t li, gi;
     if (is_sh) { li = shared_index(m.L, k, i); gi = shared_index(m.LG, k, i); }
     else {
@@ -128,7 +131,7 @@ __global__ void __launch_bounds__(256) k_prep_big(DevModel m, int mode, int gpb)
     }
   }
   __syncthreads();
-  if (tid == 0) { const double e = exp(sh[1]); sh[1] = e; if (blockIdx.x == 0) m.shx[0] = e; }
+  if (tid == 0) { const double e = m.depth ? sh[1] : exp(sh[1]); sh[1] = e; if (blockIdx.x == 0) m.shx[0] = e; }  // sigma_beta0 | beta1
   __syncthreads();
   for (int i = tid; i < gpb * (k + 1); i += blockDim.x) {
     const int gl = i / (k + 1), j = i - gl * (k + 1);
@@ -300,15 +303,23 @@ __device__ void finish_body(const DevModel &m, int mode, int jac, int propto, in
       double lp;
       if (m.lik == BVG_GAUSSIAN) lp = -N * lt - 0.5 * tot[S_SSE] / (tl * tl) - 0.5 * tl * tl;
       else lp = tot[S_SSE] + tot[S_LG] - log1p(tl * tl / 4.0);
-      lp += -0.5 * tot[S_Z2] - mb * mb / 8.0 - 0.5 * sb * sb - ma * ma / 8.0 - 0.5 * sa * sa;
+      if (m.depth && m.lik == BVG_GAUSSIAN) lp += 0.5 * tl * tl - tl * tl / 8.0;  // sigma_y ~ normal(0, 2) (approxGP2.stan:44)
+      lp += -0.5 * tot[S_Z2] - mb * mb / 8.0 - (m.depth ? sb * sb / 8.0 : 0.5 * sb * sb) - ma * ma / 8.0 - 0.5 * sa * sa;
       lp += -Gt * lsa - tot[S_U] - 0.5 * tot[S_DU2] / (sa * sa);
       lp += pa;
-      if (jac) lp += lsb + lsa + tot[S_U] + lt;
+      if (jac) lp += (m.depth ? 0.0 : lsb) + lsa + tot[S_U] + lt;
       if (!propto) {
-        if (m.lik == BVG_GAUSSIAN)
-          lp += -0.5 * BVG_LOG_TWO_PI * (N + (double)k * Gt + 2.0 * Gt + 2.0 * k + 5.0) - (k + 2.0) * BVG_LOG_TWO;
-        else
-          lp += -0.5 * BVG_LOG_TWO_PI * ((double)k * Gt + 2.0 * Gt + 2.0 * k + 4.0) - (k + 2.0) * BVG_LOG_TWO - BVG_LOG_PI;
+        if (!m.depth) {
+          if (m.lik == BVG_GAUSSIAN)
+            lp += -0.5 * BVG_LOG_TWO_PI * (N + (double)k * Gt + 2.0 * Gt + 2.0 * k + 5.0) - (k + 2.0) * BVG_LOG_TWO;
+          else
+            lp += -0.5 * BVG_LOG_TWO_PI * ((double)k * Gt + 2.0 * Gt + 2.0 * k + 4.0) - (k + 2.0) * BVG_LOG_TWO - BVG_LOG_PI;
+        } else {  // approxGP2/3: no z_beta0 terms; normal(0, 2) on beta0, beta1, mu_amplitude, mu_alpha[k] (and sigma_y)
+          if (m.lik == BVG_GAUSSIAN)
+            lp += -0.5 * BVG_LOG_TWO_PI * (N + (double)k * Gt + Gt + 2.0 * k + 5.0) - (k + 4.0) * BVG_LOG_TWO;
+          else
+            lp += -0.5 * BVG_LOG_TWO_PI * ((double)k * Gt + Gt + 2.0 * k + 4.0) - (k + 3.0) * BVG_LOG_TWO - BVG_LOG_PI;
+        }
       }
       s_lp = lp;
     }
@@ -317,11 +328,11 @@ __device__ void finish_body(const DevModel &m, int mode, int jac, int propto, in
     for (int i = tid; i < 2 * k + 5; i += blockDim.x - 32) {  // every warp but the last (which forms the log density)
       double gv;
       if (i == 0) gv = tot[S_R] - mb / 4.0;
-      else if (i == 1) gv = sb * (tot[S_RZ] - sb) + j1;
+      else if (i == 1) gv = m.depth ? tot[S_RZ] - sb / 4.0 : sb * (tot[S_RZ] - sb) + j1;
       else if (i == 2) gv = tot[S_DU] / (sa * sa) - ma / 4.0;
       else if (i == 3) gv = -Gt + tot[S_DU2] / (sa * sa) - sa * sa + j1;
       else if (i == 4) {
-        if (m.lik == BVG_GAUSSIAN) gv = -N + tot[S_SSE] / (tl * tl) - tl * tl + j1;
+        if (m.lik == BVG_GAUSSIAN) gv = -N + tot[S_SSE] / (tl * tl) - (m.depth ? tl * tl / 4.0 : tl * tl) + j1;
         else gv = tl * (tot[S_DG] - tot[S_L] - tot[S_R] / tl) - 0.5 * tl * tl / (1.0 + tl * tl / 4.0) + j1;
       } else if (i < 5 + k) gv = tot[S_AP + (i - 5)] - zt[L.mu_alpha + (i - 5)] / 4.0;
       else {
@@ -342,11 +353,11 @@ __device__ void finish_body(const DevModel &m, int mode, int jac, int propto, in
     const int i = tid;
     double gv;
     if (i == 0) gv = tot[S_R] - mb / 4.0;
-    else if (i == 1) gv = sb * (tot[S_RZ] - sb) + j1;
+    else if (i == 1) gv = m.depth ? tot[S_RZ] - sb / 4.0 : sb * (tot[S_RZ] - sb) + j1;
     else if (i == 2) gv = tot[S_DU] / (sa * sa) - ma / 4.0;
     else if (i == 3) gv = -Gt + tot[S_DU2] / (sa * sa) - sa * sa + j1;
     else if (i == 4) {
-      if (m.lik == BVG_GAUSSIAN) gv = -N + tot[S_SSE] / (tl * tl) - tl * tl + j1;
+      if (m.lik == BVG_GAUSSIAN) gv = -N + tot[S_SSE] / (tl * tl) - (m.depth ? tl * tl / 4.0 : tl * tl) + j1;
       else gv = tl * (tot[S_DG] - tot[S_L] - tot[S_R] / tl) - 0.5 * tl * tl / (1.0 + tl * tl / 4.0) + j1;
     } else if (i < 5 + k) gv = tot[S_AP + (i - 5)] - zt[L.mu_alpha + (i - 5)] / 4.0;
     else {
@@ -377,7 +388,7 @@ __device__ void finish_body(const DevModel &m, int mode, int jac, int propto, in
     const double z = p_mu + exp(p_om) * p_eps;
     m.zeta[li_sh] = z;
     if (tid == 0) m.U[64] = (float)z;
-    else if (tid == 1) { const double e = exp(z); m.shx[0] = e; m.U[65] = (float)e; }
+    else if (tid == 1) { const double e = m.depth ? z : exp(z); m.shx[0] = e; m.U[65] = (float)e; }  // sigma_beta0 | beta1
     else if (tid == 3) m.shx[1] = exp(z);
     else if (tid == 4) { const double e = exp(z); m.shx[2] = e; m.shx[3 + k] = m.lik == BVG_GAUSSIAN ? 1.0 / (e * e) : 1.0; }
     else if (tid >= 5 + k) { const double e = exp(z); m.shx[3 + tid - 5 - k] = e; m.U[32 + tid - 5 - k] = (float)e; }
@@ -421,8 +432,9 @@ __global__ void __launch_bounds__(BVG_GENE_MAX_THREADS) k_gene(DevModel m, int m
     const int64_t gg = m.gene_offset + g;
     return (uint64_t)(lane < k ? m.LG.z_alpha + gg * k + lane : (lane == k ? m.LG.z_beta0 + gg : m.LG.amp + gg));
   };
+  const bool has = lane < k + 2 && !(m.depth && lane == k);  // depth-adjusted programs have no z_beta0: lane k carries gene_depths[g]
   double eps_first = 0.0;
-  if (ahead && lane < k + 2 && gfirst < m.G) eps_first = bvg_normal(m.seed, STREAM_GRAD, tg_next, global_index(gfirst));
+  if (ahead && has && gfirst < m.G) eps_first = bvg_normal(m.seed, STREAM_GRAD, tg_next, global_index(gfirst));
   griddep_wait();    // Ppart / Spart come from the likelihood kernel
   griddep_launch();
   const Layout &L = m.L;
@@ -433,13 +445,13 @@ __global__ void __launch_bounds__(BVG_GENE_MAX_THREADS) k_gene(DevModel m, int m
   const double sal = lane < k ? m.shx[3 + lane] : 0.0;
   const int it = m.ctl->it;
   const double es = m.ctl->es;        // eta / sqrt(it)
-  const bool has = lane < k + 2, upd = mode == MODE_ADVI_UPDATE;
+  const bool upd = mode == MODE_ADVI_UPDATE;
   DBG0(0);
   double aR = 0, aRz = 0, aDu = 0, aDu2 = 0, aS0 = 0, aS1 = 0, aZ2 = 0, aU = 0, aAP = 0, aAPz = 0;
   const T *Pp = (const T *)m.Ppart, *Sp = (const T *)m.Spart;
   for (int64_t g = (int64_t)blockIdx.x * nw + warp; g < m.G; g += (int64_t)gridDim.x * nw) {
     const int64_t li = lane < k ? L.z_alpha + g * k + lane : (lane == k ? L.z_beta0 + g : L.amp + g);
-    const double zi = has ? zt[li] : 0.0;  // this lane's own parameter value
+    const double zi = has ? zt[li] : ((m.depth && lane == k) ? m.depths[g] : 0.0);  // this lane's own parameter value
     const double Aexp_g = m.Aexp[g];
     double mu_i = 0, om_i = 0, hm = 0, ho = 0;
     if (upd && has) { mu_i = m.mu[li]; om_i = m.omega[li]; hm = m.hist[li]; ho = m.hist[L.D + li]; }
@@ -471,7 +483,7 @@ __global__ void __launch_bounds__(BVG_GENE_MAX_THREADS) k_gene(DevModel m, int m
     const double zb = __shfl_sync(0xffffffffu, zi, k), u = __shfl_sync(0xffffffffu, zi, k + 1);
     const double A = Aexp_g, alpha = mual + sal * zj;
     const double aP = warp_sum(lane < k ? alpha * Pj : 0.0);
-    const double z2 = warp_sum(zj * zj) + zb * zb;
+    const double z2 = warp_sum(zj * zj) + (m.depth ? 0.0 : zb * zb);
     const double AP = lane < k ? A * Pj : 0.0;
     const double du = u - ma;
     aAP += AP; aAPz += AP * zj;
@@ -583,7 +595,8 @@ __global__ void __launch_bounds__(512) k_gene_big(DevModel m, int mode, int jac,
       const int j = j0 + lane;
       if (j >= k + 2) continue;
       const int64_t li = j < k ? L.z_alpha + g * k + j : (j == k ? L.z_beta0 + g : L.amp + g);
-      const double z = zt[li];
+      const bool datum = m.depth && j == k;  // depth-adjusted programs: gene_depths[g] in place of z_beta0[g]
+      const double z = datum ? m.depths[g] : zt[li];
       if (j == k + 1) { u = z; continue; }
       double Pj = 0;
       for (int sp = 0; sp < m.nsplit; ++sp) Pj += (double)Pp[((int64_t)sp * m.Gpad + g) * KP + j];  // fixed order
@@ -599,6 +612,7 @@ __global__ void __launch_bounds__(512) k_gene_big(DevModel m, int mode, int jac,
       } else {  // j == k: the ones column of Phi' -> R_g = sum_s r_sg
         R = Pj; zb = z;
         gv = sb * R - zb;
+        if (datum) continue;
       }
       if (mode == MODE_GRAD_OUT) m.grad[li] = gv;
       else if (upd) {
@@ -608,7 +622,7 @@ __global__ void __launch_bounds__(512) k_gene_big(DevModel m, int mode, int jac,
       }
     }
     aP = warp_sum(aP); z2 = warp_sum(z2); R = warp_sum(R); zb = warp_sum(zb); u = warp_sum(u);
-    z2 += zb * zb;
+    if (!m.depth) z2 += zb * zb;
     const double du = u - ma;
     aR += R; aRz += R * zb; aDu += du; aDu2 += du * du; aS0 += s0; aS1 += s1; aZ2 += z2; aU += u;
     if (wr && lane == 0) {

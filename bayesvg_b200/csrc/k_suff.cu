@@ -200,6 +200,7 @@ void suff_destroy(bvg_fit *f) {
 // S log densities log_prob<false, true>(zeta_d), d = 0..S-1, draws t_elbo .. t_elbo+S-1 (the caller advances t_elbo)
 int suff_elbo(bvg_fit *f, int S, double *lps_host) {
   if (f->cfg.likelihood != BVG_GAUSSIAN) { bvg_set_error("sufficient-statistic ELBO exists for the gaussian likelihood only"); return BVG_ERR_ARG; }
+  if (f->cfg.depth_adjust) { bvg_set_error("sufficient-statistic ELBO is not available for the depth-adjusted model"); return BVG_ERR_ARG; }
   if (f->m.k > BVG_SMALL_K) { bvg_set_error("sufficient-statistic ELBO supports n.basis.fns <= %d", BVG_SMALL_K); return BVG_ERR_ARG; }
   BVG_TRY(suff_build(f, S));
   SuffState *st = (SuffState *)f->suff;

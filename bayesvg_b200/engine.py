@@ -39,19 +39,30 @@ def basis_build(coords, centers, lscale, kernel="exp_quad", nu=1.5, period=100.0
 
 
 class Fit:
-    def __init__(self, phi, y, likelihood="gaussian", precision="fast", engine="auto", **cfg):
+    """gene_depths (length G, log of each gene's total count) selects the depth-adjusted programs
+    inst/approxGP2.stan / approxGP3.stan (gene.depth.adjust = TRUE in the reference)."""
+
+    def __init__(self, phi, y, likelihood="gaussian", precision="fast", engine="auto", gene_depths=None, **cfg):
         lik = {"gaussian": B.GAUSSIAN, "nb": B.NB}.get(likelihood)
         if lik is None:
             raise ValueError("Please provide a valid likelihood.")
         self.cfg = default_config(likelihood=lik, precision={"fp64": B.PREC_FP64, "fast": B.PREC_FAST}[precision],
                                   engine={"auto": B.ENGINE_AUTO, "simt": B.ENGINE_SIMT, "tcgen05": B.ENGINE_TCGEN05}[engine],
-                                  **cfg)
+                                  depth_adjust=int(gene_depths is not None), **cfg)
         self._h = C.c_void_p()
         B.check(B.lib().bvg_fit_create(C.byref(self.cfg), C.byref(self._h)))
         phi = np.asfortranarray(phi, dtype=np.float64)
         self.M, self.k = phi.shape
         B.check(B.lib().bvg_fit_set_phi(self._h, _dp(phi), self.M, self.k))
+        if gene_depths is not None:
+            self.set_gene_depths(gene_depths)
         self.set_y(y)
+
+    def set_gene_depths(self, gene_depths):
+        d = np.ascontiguousarray(gene_depths, dtype=np.float64)
+        if d.ndim != 1:
+            raise ValueError("gene_depths must be a vector with one entry per gene")
+        B.check(B.lib().bvg_fit_set_gene_depths(self._h, _dp(d), d.shape[0]))
 
     def set_y(self, y):
         if y.ndim != 2 or y.shape[0] != self.M:

@@ -37,7 +37,9 @@ typedef enum {
   BVG_ERR_COMM = -5      /* NCCL error */
 } bvg_status;
 
-typedef enum { BVG_GAUSSIAN = 0 /* inst/approxGP.stan */, BVG_NB = 1 /* inst/approxGP4.stan */ } bvg_likelihood;
+/* likelihood x gene.depth.adjust selects the Stan program (R/findSpatiallyVariableFeaturesBayes.R:293-333):
+ *   gaussian: inst/approxGP.stan, depth-adjusted inst/approxGP2.stan;  nb: inst/approxGP4.stan, depth-adjusted inst/approxGP3.stan */
+typedef enum { BVG_GAUSSIAN = 0, BVG_NB = 1 } bvg_likelihood;
 typedef enum { BVG_KERNEL_EXP_QUAD = 0, BVG_KERNEL_MATERN = 1, BVG_KERNEL_PERIODIC = 2 } bvg_kernel;
 typedef enum {
   BVG_PREC_FP64 = 0, /* Y and all arithmetic fp64: the <=1e-6 parity path */
@@ -76,7 +78,9 @@ typedef struct {
    * per-gene sufficient statistics (sum y^2, Phi'^T y, Phi'^T Phi') instead of 150 dense passes over Y.
    * Same value up to round-off; the gradient path is always the dense kernel. */
   int32_t elbo_suffstat;
-  int32_t reserved;
+  /* gene.depth.adjust (:85): intercept beta0 + beta1 * gene_depths[g] (approxGP2/3.stan) instead of the
+   * hierarchical per-gene intercept; needs bvg_fit_set_gene_depths */
+  int32_t depth_adjust;
 } bvg_config;
 
 typedef struct bvg_fit bvg_fit;
@@ -99,6 +103,9 @@ void bvg_fit_destroy(bvg_fit *);
 int bvg_fit_set_phi(bvg_fit *, const double *phi, int64_t M, int k);
 int bvg_fit_set_y_f64(bvg_fit *, const double *y, int64_t M, int64_t G);
 int bvg_fit_set_y_i32(bvg_fit *, const int32_t *y, int64_t M, int64_t G);
+/* data_list$gene_depths (:303): log of each gene's total count, length G; only with cfg.depth_adjust = 1.
+ * May be called before or after bvg_fit_set_y; must be set before any evaluation. */
+int bvg_fit_set_gene_depths(bvg_fit *, const double *gene_depths, int64_t G);
 int bvg_fit_dim(bvg_fit *, int64_t *D);
 
 /* multi-GPU (one process per GPU of one node; the reference has no counterpart -- its fit is one

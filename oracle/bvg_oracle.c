@@ -35,6 +35,21 @@ static layout_t make_layout(int model, int64_t G, int k) {
   L.mu_beta0 = 0;
   L.sigma_beta0 = 1;
   L.z_beta0 = 2;
+  if (model == BVGO_GAUSSIAN_DEPTH || model == BVGO_NB_DEPTH) {
+    /* approxGP2.stan:13-23 / approxGP3.stan:13-23: beta0, beta1, sigma_y | phi_nb, amplitude[G], mu_amplitude,
+     * sigma_amplitude, mu_alpha[k], sigma_alpha[k], z_alpha_t[k,G].  mu_beta0 / sigma_beta0 name the slots of
+     * beta0 / beta1 (beta1 is unconstrained); there is no z_beta0. */
+    L.z_beta0 = -1;
+    L.tail = 2;
+    L.amp = 3;
+    L.mu_amp = 3 + G;
+    L.sigma_amp = 4 + G;
+    L.mu_alpha = 5 + G;
+    L.sigma_alpha = L.mu_alpha + k;
+    L.z_alpha = L.sigma_alpha + k;
+    L.D = 5 + G + 2 * (int64_t)k + (int64_t)k * G;
+    return L;
+  }
   if (model == BVGO_GAUSSIAN) { /* approxGP.stan:13-22 */
     L.mu_amp = 2 + G;
     L.sigma_amp = 3 + G;
@@ -63,9 +78,11 @@ struct bvgo_ctx {
   int64_t M, G;
   int k;
   const double *phi, *y;
+  const double *depths; /* gene_depths[G] of approxGP2/3.stan:9 (NULL for the hierarchical-intercept models) */
   int nthreads;
   layout_t L;
 };
+void bvgo_set_depths(bvgo_ctx *c, const double *gene_depths) { c->depths = gene_depths; }
 
 bvgo_ctx *bvgo_create(int model, int64_t M, int64_t G, int k, const double *phi, const double *y,
                       int nthreads) {
@@ -122,8 +139,12 @@ double bvgo_log_prob(bvgo_ctx *c, const double *th, int jac, int propto, double 
   const layout_t L = c->L;
   const int64_t M = c->M, G = c->G;
   const int k = c->k;
-  const int nb = c->model == BVGO_NB;
-  const double mb = th[L.mu_beta0], lsb = th[L.sigma_beta0], sb = exp(lsb);
+  const int nb = c->model == BVGO_NB || c->model == BVGO_NB_DEPTH;
+  /* depth-adjusted models (approxGP2.stan:46, approxGP3.stan:46): the per-gene intercept is beta0 + beta1 *
+   * gene_depths[g]; in the formulas below (mb, sb, zb) = (beta0, beta1, gene_depths[g]) and beta1 has no
+   * constraint, no z_beta0 prior and a normal(0, 2) prior (approxGP2.stan:39) */
+  const int dep = c->model == BVGO_GAUSSIAN_DEPTH || c->model == BVGO_NB_DEPTH;
+  const double mb = th[L.mu_beta0], lsb = th[L.sigma_beta0], sb = dep ? lsb : exp(lsb);
   const double ma = th[L.mu_amp], lsa = th[L.sigma_amp], sa = exp(lsa);
   const double lt = th[L.tail], tl = exp(lt); /* sigma_y or phi_nb */
   const double *mua = th + L.mu_alpha, *lsal = th + L.sigma_alpha;
@@ -144,7 +165,7 @@ double bvgo_log_prob(bvgo_ctx *c, const double *th, int jac, int propto, double 
     double *t_APs = (double *)calloc(2 * (size_t)k, sizeof(double)), *t_APz = t_APs + k;
 #pragma omp for schedule(static)
     for (int64_t g = 0; g < G; ++g) {
-      const double zb = th[L.z_beta0 + g], u = th[L.amp + g];
+      const double zb = dep ? c->depths[g] : th[L.z_beta0 + g], u = th[L.amp + g];
       const double *z = th + L.z_alpha + g * k;
       const double beta = mb + sb * zb; /* approxGP.stan:26 */
       const double A = exp(2.0 * u);    /* amplitude_sq, :27 */
@@ -154,7 +175,7 @@ double bvgo_log_prob(bvgo_ctx *c, const double *th, int jac, int propto, double 
         P[j] = 0;
         t_z2 += z[j] * z[j];
       }
-      t_z2 += zb * zb;
+      if (!dep) t_z2 += zb * zb;
       const double *yg = c->y + g * M;
       double Rg = 0, sse_g = 0, lik_g = 0, dphi_g = 0;
       for (int64_t s0 = 0; s0 < M; s0 += SB) {
@@ -212,7 +233,7 @@ double bvgo_log_prob(bvgo_ctx *c, const double *th, int jac, int propto, double 
         }
         t_R += Rg;
         t_Rz += Rg * zb;
-        grad[L.z_beta0 + g] = sb * Rg - zb;
+        if (!dep) grad[L.z_beta0 + g] = sb * Rg - zb;
         grad[L.amp + g] = 2.0 * A * aP - du / (sa * sa) - (jac ? 0.0 : 1.0);
       }
     }
@@ -231,32 +252,43 @@ double bvgo_log_prob(bvgo_ctx *c, const double *th, int jac, int propto, double 
   if (!nb) lp += -N * lt - 0.5 * sse * inv_s2; /* normal_lpdf, approxGP.stan:48 */
   else lp += lik;
   lp += -0.5 * sz2;                                              /* :38-39 std_normal on z's */
-  lp += -mb * mb / 8.0 - 0.5 * sb * sb - ma * ma / 8.0 - 0.5 * sa * sa; /* :40-43 */
+  if (!dep) lp += -mb * mb / 8.0 - 0.5 * sb * sb - ma * ma / 8.0 - 0.5 * sa * sa; /* :40-43 */
+  else lp += -mb * mb / 8.0 - sb * sb / 8.0 - ma * ma / 8.0 - 0.5 * sa * sa;  /* approxGP2.stan:38-39, :42-43 */
   lp += -(double)G * lsa - su - 0.5 * sdu2 / (sa * sa);          /* :44 lognormal */
   for (int j = 0; j < k; ++j) lp += -mua[j] * mua[j] / 8.0 - 0.5 * sal[j] * sal[j]; /* :45-46 */
-  if (!nb) lp += -0.5 * tl * tl;                                 /* :47 sigma_y ~ std_normal */
+  if (!nb) lp += dep ? -tl * tl / 8.0 : -0.5 * tl * tl; /* :47 sigma_y ~ std_normal; approxGP2.stan:44 normal(0, 2) */
   else lp += -log1p(tl * tl / 4.0);                              /* approxGP4.stan:41 cauchy(0,2) */
   if (jac) {
-    lp += lsb + lsa + su + lt;
+    lp += (dep ? 0.0 : lsb) + lsa + su + lt;
     for (int j = 0; j < k; ++j) lp += lsal[j];
   }
   if (!propto) {
-    if (!nb)
-      lp += -0.5 * LOG_TWO_PI * (N + (double)k * G + 2.0 * G + 2.0 * k + 5.0) - (k + 2.0) * LOG_TWO;
-    else /* cauchy: -log(pi*2); T[0,]: -log(1/2) [U] */
-      lp += -0.5 * LOG_TWO_PI * ((double)k * G + 2.0 * G + 2.0 * k + 4.0) - (k + 2.0) * LOG_TWO - LOG_PI;
+    if (!dep) {
+      if (!nb)
+        lp += -0.5 * LOG_TWO_PI * (N + (double)k * G + 2.0 * G + 2.0 * k + 5.0) - (k + 2.0) * LOG_TWO;
+      else /* cauchy: -log(pi*2); T[0,]: -log(1/2) [U] */
+        lp += -0.5 * LOG_TWO_PI * ((double)k * G + 2.0 * G + 2.0 * k + 4.0) - (k + 2.0) * LOG_TWO - LOG_PI;
+    } else {
+      /* approxGP2: N likelihood terms, kG std-normal z, G lognormal, normal(0,2) on beta0, beta1, mu_amplitude,
+       * mu_alpha[k], sigma_y (k + 4, each also -log 2), std_normal on sigma_amplitude, sigma_alpha[k] (k + 1);
+       * approxGP3: no likelihood / sigma_y normal terms, the truncated cauchy contributes -log(pi) */
+      if (!nb)
+        lp += -0.5 * LOG_TWO_PI * (N + (double)k * G + (double)G + 2.0 * k + 5.0) - (k + 4.0) * LOG_TWO;
+      else
+        lp += -0.5 * LOG_TWO_PI * ((double)k * G + (double)G + 2.0 * k + 4.0) - (k + 3.0) * LOG_TWO - LOG_PI;
+    }
   }
   if (grad) {
     const double j1 = jac ? 1.0 : 0.0;
     grad[L.mu_beta0] = sumR - mb / 4.0;
-    grad[L.sigma_beta0] = sb * (sumRz - sb) + j1;
+    grad[L.sigma_beta0] = dep ? sumRz - sb / 4.0 : sb * (sumRz - sb) + j1;
     grad[L.mu_amp] = sdu / (sa * sa) - ma / 4.0;
     grad[L.sigma_amp] = -(double)G + sdu2 / (sa * sa) - sa * sa + j1;
     for (int j = 0; j < k; ++j) {
       grad[L.mu_alpha + j] = APs[j] - mua[j] / 4.0;
       grad[L.sigma_alpha + j] = sal[j] * (APz[j] - sal[j]) + j1;
     }
-    if (!nb) grad[L.tail] = -N + sse * inv_s2 - tl * tl + j1;
+    if (!nb) grad[L.tail] = -N + sse * inv_s2 - (dep ? tl * tl / 4.0 : tl * tl) + j1;
     else grad[L.tail] = tl * dphi - 0.5 * tl * tl / (1.0 + tl * tl / 4.0) + j1;
   }
   free(APs);

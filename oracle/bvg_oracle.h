@@ -19,7 +19,10 @@
 extern "C" {
 #endif
 
-enum { BVGO_GAUSSIAN = 0 /* inst/approxGP.stan */, BVGO_NB = 1 /* inst/approxGP4.stan */ };
+enum {
+  BVGO_GAUSSIAN = 0 /* inst/approxGP.stan */, BVGO_NB = 1 /* inst/approxGP4.stan */,
+  BVGO_GAUSSIAN_DEPTH = 2 /* inst/approxGP2.stan */, BVGO_NB_DEPTH = 3 /* inst/approxGP3.stan */
+};
 enum { BVGO_KERNEL_EXP_QUAD = 0, BVGO_KERNEL_MATERN = 1, BVGO_KERNEL_PERIODIC = 2 };
 
 typedef struct bvgo_ctx bvgo_ctx;
@@ -30,6 +33,9 @@ bvgo_ctx *bvgo_create(int model, int64_t M, int64_t G, int k, const double *phi,
                       int nthreads);
 void bvgo_destroy(bvgo_ctx *);
 int64_t bvgo_dim(int model, int64_t G, int k);
+/* depth-adjusted models: gene_depths[G] (log of the gene's total count, R/findSpatiallyVariableFeaturesBayes.R:303);
+ * the pointer must outlive the context */
+void bvgo_set_depths(bvgo_ctx *c, const double *gene_depths);
 
 /* log density at an unconstrained vector (Stan declaration order);
  * grad may be NULL (forward only).  Mirrors log_prob<propto, jacobian>. */

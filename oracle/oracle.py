@@ -58,6 +58,8 @@ def lib():
         L.bvgo_create.restype = C.c_void_p
         L.bvgo_create.argtypes = [C.c_int, C.c_int64, C.c_int64, C.c_int, _dp, _dp, C.c_int]
         L.bvgo_destroy.argtypes = [C.c_void_p]
+        L.bvgo_set_depths.argtypes = [C.c_void_p, _dp]
+        L.bvgo_set_depths.restype = None
         L.bvgo_dim.restype = C.c_int64
         L.bvgo_dim.argtypes = [C.c_int, C.c_int64, C.c_int]
         L.bvgo_log_prob.restype = C.c_double
@@ -87,16 +89,21 @@ def _f(a):
 
 
 class Oracle:
-    """One dataset: Y (M x G), Phi (M x k).  model: 'gaussian' | 'nb'."""
+    """One dataset: Y (M x G), Phi (M x k).  model: 'gaussian' | 'nb'; gene_depths (length G) selects the
+    depth-adjusted programs inst/approxGP2.stan / approxGP3.stan."""
 
-    def __init__(self, phi, y, model="gaussian", nthreads=1):
-        self.model = {"gaussian": GAUSSIAN, "nb": NB}[model]
+    def __init__(self, phi, y, model="gaussian", nthreads=1, gene_depths=None):
+        self.model = {"gaussian": GAUSSIAN, "nb": NB}[model] + (0 if gene_depths is None else 2)
         self.phi, self.y = _f(phi), _f(y)
         self.M, self.k = self.phi.shape
         assert self.y.shape[0] == self.M
         self.G = self.y.shape[1]
         self.D = int(lib().bvgo_dim(self.model, self.G, self.k))
         self._h = lib().bvgo_create(self.model, self.M, self.G, self.k, _p(self.phi), _p(self.y), nthreads)
+        if gene_depths is not None:
+            self.depths = np.ascontiguousarray(gene_depths, dtype=np.float64)
+            assert self.depths.shape == (self.G,)
+            lib().bvgo_set_depths(self._h, _p(self.depths))
 
     def __del__(self):
         if getattr(self, "_h", None):
@@ -175,8 +182,13 @@ def digamma(x):
     return lib().bvgo_digamma(x)
 
 
-def layout(model, G, k):
+def layout(model, G, k, depth=False):
     """slot offsets of the unconstrained vector"""
+    if depth:  # inst/approxGP2.stan:13-23, inst/approxGP3.stan:13-23
+        o = dict(beta0=0, beta1=1, amplitude=3, mu_amplitude=3 + G, sigma_amplitude=4 + G, mu_alpha=5 + G,
+                 sigma_alpha=5 + G + k, z_alpha_t=5 + G + 2 * k, D=5 + G + 2 * k + k * G)
+        o["sigma_y" if model in ("gaussian", GAUSSIAN) else "phi_nb"] = 2
+        return o
     if model in ("gaussian", GAUSSIAN):
         o = dict(mu_beta0=0, sigma_beta0=1, z_beta0=2, mu_amplitude=2 + G, sigma_amplitude=3 + G,
                  amplitude=4 + G, mu_alpha=4 + 2 * G, sigma_alpha=4 + 2 * G + k, z_alpha_t=4 + 2 * G + 2 * k,

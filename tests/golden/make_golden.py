@@ -2,7 +2,8 @@
 
 The reference (R + CmdStan) cannot run in this image and its own tests
 hold no numeric vectors, so the pin is a *literal transcription* of the Stan programs
-(/root/reference/inst/approxGP.stan, inst/approxGP4.stan), statement by statement -- including
+(/root/reference/inst/approxGP.stan, inst/approxGP4.stan and the depth-adjusted inst/approxGP2.stan,
+inst/approxGP3.stan), statement by statement -- including
 the spot_id/gene_id gather loop that the oracle and the engine optimise away -- evaluated with
 scipy.stats log-densities (values) and torch-autograd fp64 (gradients).  It shares no code with
 oracle/bvg_oracle.c (analytic gradient) or with the CUDA kernels.
@@ -154,6 +155,108 @@ def stan_gp4(theta, phi, y, spot_id, gene_id, G, k, jacobian, propto):
     return lp + (lj if jacobian else 0.0)
 
 
+def stan_gp2(theta, phi, y, spot_id, gene_id, G, k, jacobian, propto, gene_depths):
+    """inst/approxGP2.stan"""
+    i = 0
+    lj = 0.0
+
+    def take(n, lower0=False):
+        nonlocal i, lj
+        u = theta[i:i + n]
+        i += n
+        if lower0:
+            lj = lj + u.sum()
+            return torch.exp(u)
+        return u
+
+    beta0 = take(1)             # :14
+    beta1 = take(1)             # :15
+    sigma_y = take(1, True)     # :16
+    amplitude = take(G, True)   # :17
+    mu_amplitude = take(1)      # :18
+    sigma_amplitude = take(1, True)  # :19
+    mu_alpha = take(k)          # :20
+    sigma_alpha = take(k, True)  # :21
+    z_alpha_t = take(k * G).reshape(G, k).T  # :22
+    assert i == theta.numel()
+    amplitude_sq = amplitude ** 2            # :26
+    alpha_t = mu_alpha[:, None].expand(k, G) + sigma_alpha[:, None] * z_alpha_t  # :31
+    phi_alpha = phi @ alpha_t                # :32
+    w = phi_alpha[spot_id, gene_id]          # :33-36
+    lp = std_normal(z_alpha_t, propto)       # :37
+    lp = lp + normal_const_scale(beta0, 2.0, propto)         # :38
+    lp = lp + normal_const_scale(beta1, 2.0, propto)         # :39
+    lp = lp + normal_const_scale(mu_alpha, 2.0, propto)      # :40
+    lp = lp + std_normal(sigma_alpha, propto)                # :41
+    lp = lp + normal_const_scale(mu_amplitude, 2.0, propto)  # :42
+    lp = lp + std_normal(sigma_amplitude, propto)            # :43
+    lp = lp + normal_const_scale(sigma_y, 2.0, propto)       # :44
+    lp = lp + lognormal_lpdf(amplitude, mu_amplitude, sigma_amplitude, propto)  # :45
+    lp = lp + normal_lpdf(y, beta0 + beta1 * gene_depths[gene_id] + amplitude_sq[gene_id] * w, sigma_y, propto)  # :46
+    return lp + (lj if jacobian else 0.0)
+
+
+def stan_gp3(theta, phi, y, spot_id, gene_id, G, k, jacobian, propto, gene_depths):
+    """inst/approxGP3.stan"""
+    i = 0
+    lj = 0.0
+
+    def take(n, lower0=False):
+        nonlocal i, lj
+        u = theta[i:i + n]
+        i += n
+        if lower0:
+            lj = lj + u.sum()
+            return torch.exp(u)
+        return u
+
+    beta0 = take(1)             # :14
+    beta1 = take(1)             # :15
+    phi_nb = take(1, True)      # :16
+    amplitude = take(G, True)   # :17
+    mu_amplitude = take(1)
+    sigma_amplitude = take(1, True)
+    mu_alpha = take(k)
+    sigma_alpha = take(k, True)
+    z_alpha_t = take(k * G).reshape(G, k).T
+    assert i == theta.numel()
+    amplitude_sq = amplitude ** 2
+    lp = normal_const_scale(beta0, 2.0, propto)              # :30
+    lp = lp + normal_const_scale(beta1, 2.0, propto)         # :31
+    alpha_t = mu_alpha[:, None].expand(k, G) + sigma_alpha[:, None] * z_alpha_t
+    phi_alpha = phi @ alpha_t
+    lp = lp + std_normal(z_alpha_t, propto)
+    lp = lp + normal_const_scale(mu_alpha, 2.0, propto)
+    lp = lp + std_normal(sigma_alpha, propto)
+    lp = lp + normal_const_scale(mu_amplitude, 2.0, propto)
+    lp = lp + std_normal(sigma_amplitude, propto)
+    lp = lp + lognormal_lpdf(amplitude, mu_amplitude, sigma_amplitude, propto)
+    lp = lp + cauchy_trunc0(phi_nb, 2.0, propto).sum()       # :41
+    w = phi_alpha[spot_id, gene_id]                           # :42-45
+    lp = lp + neg_binomial_2_log(y, beta0 + beta1 * gene_depths[gene_id] + amplitude_sq[gene_id] * w, phi_nb)  # :46
+    return lp + (lj if jacobian else 0.0)
+
+
+def scipy_value_check_gp23(theta, phi, y, G, k, depths, nb):
+    """values only (propto = FALSE, jacobian = FALSE) for the depth-adjusted programs"""
+    th = theta
+    b0, b1, tail = th[0], th[1], np.exp(th[2])
+    amp = np.exp(th[3:3 + G]); mu_a, s_a = th[3 + G], np.exp(th[4 + G])
+    mu_al = th[5 + G:5 + G + k]; s_al = np.exp(th[5 + G + k:5 + G + 2 * k])
+    z = th[5 + G + 2 * k:].reshape(G, k).T
+    alpha = mu_al[:, None] + s_al[:, None] * z
+    eta = (b0 + b1 * depths)[None, :] + (amp ** 2)[None, :] * (phi @ alpha)
+    lp = st.norm.logpdf(z).sum() + st.norm.logpdf(b0, 0, 2) + st.norm.logpdf(b1, 0, 2)
+    lp += st.norm.logpdf(mu_a, 0, 2) + st.norm.logpdf(s_a) + st.lognorm.logpdf(amp, s=s_a, scale=np.exp(mu_a)).sum()
+    lp += st.norm.logpdf(mu_al, 0, 2).sum() + st.norm.logpdf(s_al).sum()
+    if nb:
+        lp += st.cauchy.logpdf(tail, 0, 2) - st.cauchy.logsf(0, 0, 2)
+        lp += st.nbinom.logpmf(y, tail, tail / (tail + np.exp(eta))).sum()
+    else:
+        lp += st.norm.logpdf(tail, 0, 2) + st.norm.logpdf(y, eta, tail).sum()
+    return lp
+
+
 def scipy_value_check_gp(theta, phi, y, G, k):
     """values only, with scipy.stats frozen distributions (propto = FALSE, jacobian = FALSE)"""
     th = theta
@@ -189,7 +292,7 @@ def scipy_value_check_gp4(theta, phi, y, G, k):
     return lp
 
 
-def make_case(model, M, G, k, seed, n_theta=3):
+def make_case(model, M, G, k, seed, n_theta=3, depth=False):
     rng = np.random.default_rng(seed)
     coords = rng.normal(size=(M, 2))
     raw = np.exp(-0.5 * ((coords[:, None, :] - coords[rng.choice(M, k, replace=False)][None]) ** 2).sum(-1))
@@ -206,6 +309,15 @@ def make_case(model, M, G, k, seed, n_theta=3):
         y = rng.negative_binomial(2.0, 2.0 / (2.0 + np.exp(np.log(0.5) + np.clip(mean, -4, 4)))).astype(np.float64)
         fn, sfn = stan_gp4, scipy_value_check_gp4
     D = 5 + 2 * G + 2 * k + k * G
+    depths = None
+    if depth:
+        # gene_depths = log(rowSums(counts)) (R/findSpatiallyVariableFeaturesBayes.R:303); synthetic stand-in
+        depths = np.log(rng.integers(500, 50000, G).astype(np.float64))
+        td = torch.tensor(depths)
+        base = stan_gp2 if model == "gaussian" else stan_gp3
+        fn = lambda th, a, b, c, d, G_, k_, j, p: base(th, a, b, c, d, G_, k_, j, p, td)  # noqa: E731
+        sfn = lambda t, ph, yy, G_, k_: scipy_value_check_gp23(t, ph, yy, G_, k_, depths, model != "gaussian")  # noqa: E731
+        D = 5 + G + 2 * k + k * G
     gene_id = np.repeat(np.arange(G), M)  # gene-major long vector (:176-183)
     spot_id = np.tile(np.arange(M), G)
     ylong = y.T.reshape(-1)  # y[(g-1)*M + s]
@@ -214,6 +326,8 @@ def make_case(model, M, G, k, seed, n_theta=3):
     thetas = rng.normal(0, 0.6, size=(n_theta, D))
     thetas[0] = 0.0  # init = 0 (the L-BFGS start, :348)
     out = dict(phi=phi, y=y, thetas=thetas, M=M, G=G, k=k)
+    if depth:
+        out["gene_depths"] = depths
     for jac in (0, 1):
         for pro in (0, 1):
             lps, grads = [], []
@@ -265,6 +379,10 @@ def main():
     np.savez_compressed(os.path.join(HERE, "gp4_small.npz"), **make_case("nb", 41, 6, 3, 2))
     np.savez_compressed(os.path.join(HERE, "gp_ragged.npz"), **make_case("gaussian", 131, 9, 20, 3, n_theta=2))
     np.savez_compressed(os.path.join(HERE, "gp4_ragged.npz"), **make_case("nb", 67, 7, 20, 4, n_theta=2))
+    np.savez_compressed(os.path.join(HERE, "gp2_small.npz"), **make_case("gaussian", 43, 6, 5, 5, depth=True))
+    np.savez_compressed(os.path.join(HERE, "gp3_small.npz"), **make_case("nb", 39, 5, 4, 6, depth=True))
+    np.savez_compressed(os.path.join(HERE, "gp2_ragged.npz"), **make_case("gaussian", 97, 11, 20, 7, n_theta=2, depth=True))
+    np.savez_compressed(os.path.join(HERE, "gp3_ragged.npz"), **make_case("nb", 71, 9, 20, 8, n_theta=2, depth=True))
     np.savez_compressed(os.path.join(HERE, "basis.npz"), **make_basis_case())
     print("golden fixtures written to", HERE)
 

@@ -16,7 +16,9 @@ import bayesvg_b200 as bvg  # noqa: E402
 
 TOL = {"fp64": 1e-6, "fast": 1e-3}
 ACHIEVED = {"fp64": 1e-10, "fast": 2e-4}
-GOLDEN = [("gp_small", "gaussian"), ("gp4_small", "nb"), ("gp_ragged", "gaussian"), ("gp4_ragged", "nb")]
+GOLDEN = [("gp_small", "gaussian"), ("gp4_small", "nb"), ("gp_ragged", "gaussian"), ("gp4_ragged", "nb"),
+          # gene.depth.adjust = TRUE: inst/approxGP2.stan / approxGP3.stan
+          ("gp2_small", "gaussian"), ("gp3_small", "nb"), ("gp2_ragged", "gaussian"), ("gp3_ragged", "nb")]
 ENGINES = [("fp64", "simt"), ("fast", "simt"), ("fast", "tcgen05")]
 
 
@@ -33,7 +35,7 @@ def _fit(phi, y, lik, prec, eng, **kw):
 @pytest.mark.parametrize("prec,eng", ENGINES)
 def test_log_prob_golden(golden_dir, name, lik, prec, eng):
     z = np.load(os.path.join(golden_dir, name + ".npz"))
-    f = _fit(z["phi"], z["y"], lik, prec, eng)
+    f = _fit(z["phi"], z["y"], lik, prec, eng, gene_depths=z["gene_depths"] if "gene_depths" in z.files else None)
     for jac in (0, 1):
         for pro in (0, 1):
             for t, th in enumerate(z["thetas"]):
@@ -103,6 +105,57 @@ def test_large_basis_advi_trajectory_and_fit():
     f = _fit(p["phi"], p["y"], "gaussian", "fast", "auto", seed=5, n_iter=300, mle_iter=40, n_draws=256, elbo_samples=20)
     tab = f.run()
     assert tab.shape == (24, 8) and np.all(np.isfinite(tab)) and np.all(tab[:, 0] > 0)
+    f.close()
+
+
+@pytest.mark.parametrize("lik", ["gaussian", "nb"])
+@pytest.mark.parametrize("prec,eng", ENGINES)
+@pytest.mark.parametrize("M,G,k", [(500, 300, 20), (97, 130, 7), (260, 50, 64)])
+def test_depth_adjusted_models_vs_oracle(lik, prec, eng, M, G, k):
+    """gene.depth.adjust = TRUE (inst/approxGP2.stan, approxGP3.stan): log density, gradient, same-Philox ADVI steps"""
+    if eng == "tcgen05" and k > 23:
+        pytest.skip("tcgen05 engine covers k <= 23")
+    p = make_problem(M, G, k, lik, seed=M + G + 1)
+    depths = np.log(np.random.default_rng(4).integers(300, 90000, G).astype(np.float64))
+    o = orc.Oracle(p["phi"], p["y"], lik, nthreads=4, gene_depths=depths)
+    f = _fit(p["phi"], p["y"], lik, prec, eng, gene_depths=depths, seed=9)
+    assert f.D == o.D == 5 + G + 2 * k + k * G
+    rng = np.random.default_rng(5)
+    for scale, jac, pro in ((0.0, True, True), (0.3, True, False), (0.3, False, True), (1.0, False, False)):
+        th = rng.normal(0, 1, o.D) * scale
+        th[1] *= 0.05  # beta1 multiplies gene_depths ~ 6..11
+        lp, g = f.log_prob(th, jac, pro)
+        rlp, rg = o.log_prob(th, jac, pro)
+        assert abs(lp - rlp) <= ACHIEVED[prec] * max(1.0, abs(rlp)), (lp, rlp)
+        assert rel_err(g, rg) <= ACHIEVED[prec] * 5
+    mu, om, hist = np.zeros(o.D), np.zeros(o.D), np.zeros(2 * o.D)
+    f.set_variational(mu, None)
+    f.advi_steps(0, 0.01, reset=True)
+    for it in range(1, 9):
+        o.advi_step(mu, om, hist, 0.01, it, 9, it - 1)
+    f.advi_steps(8, 0.01)
+    gmu, gom = f.get_variational()
+    tol = 1e-9 if prec == "fp64" else 1e-3
+    assert rel_err(gmu, mu) < tol and rel_err(gom, om) < tol
+    e, _ = f.elbo(6)
+    eo = o.elbo(gmu, gom, 6, 9, 0)  # same Philox stream / counters as the engine's first ELBO estimate
+    assert e == pytest.approx(eo, rel=1e-10 if prec == "fp64" else 2e-4)
+    f.close()
+
+
+def test_depth_adjusted_full_fit_and_errors():
+    p = make_problem(400, 60, 12, "gaussian", seed=8)
+    depths = np.log(np.random.default_rng(1).integers(300, 90000, 60).astype(np.float64))
+    with pytest.raises(bvg._lib.BvgError):
+        bvg.Fit(p["phi"], p["y"], "gaussian", gene_depths=depths[:-1])     # wrong length
+    with pytest.raises(bvg._lib.BvgError):
+        bvg.Fit(p["phi"], p["y"], "gaussian", gene_depths=np.full(60, -np.inf))  # a gene with zero counts
+    f = bvg.Fit(p["phi"], p["y"], "gaussian", "fast", "auto", gene_depths=depths, n_iter=400, mle_iter=60, n_draws=300,
+                elbo_samples=30, seed=3)
+    tab = f.run()
+    assert tab.shape == (60, 8) and np.all(np.isfinite(tab[:, :7])) and np.all(tab[:, 0] > 0)
+    with pytest.raises(bvg._lib.BvgError):
+        f.set_y(p["y"][:, :10].copy(order="F"))  # the staged gene_depths no longer match
     f.close()
 
 

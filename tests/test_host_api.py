@@ -33,7 +33,7 @@ def test_validation_messages_match_the_reference():
         f(o, ["gene1"], algorithm="hmc")
     # accepted by the reference, rejected clearly here (no fallback)
     for kw in (dict(algorithm="fullrank"), dict(algorithm="pathfinder"), dict(opencl_params=[0, 0]),
-               dict(lscale_estimator="variogram"), dict(gene_depth_adjust=True)):
+               dict(lscale_estimator="variogram")):
         with pytest.raises(NotImplementedError):
             f(o, ["gene1"], **kw)
     with pytest.raises(KeyError):

@@ -12,7 +12,9 @@ import pytest
 
 from oracle import oracle as orc
 
-CASES = [("gp_small", "gaussian"), ("gp4_small", "nb"), ("gp_ragged", "gaussian"), ("gp4_ragged", "nb")]
+CASES = [("gp_small", "gaussian"), ("gp4_small", "nb"), ("gp_ragged", "gaussian"), ("gp4_ragged", "nb"),
+         # depth-adjusted programs inst/approxGP2.stan / approxGP3.stan (gene.depth.adjust = TRUE)
+         ("gp2_small", "gaussian"), ("gp3_small", "nb"), ("gp2_ragged", "gaussian"), ("gp3_ragged", "nb")]
 
 
 def _load(golden_dir, name):
@@ -23,7 +25,7 @@ def _load(golden_dir, name):
 @pytest.mark.parametrize("nthreads", [1, 3])
 def test_log_prob_and_grad_match_stan_transcription(golden_dir, name, model, nthreads):
     z = _load(golden_dir, name)
-    o = orc.Oracle(z["phi"], z["y"], model, nthreads=nthreads)
+    o = orc.Oracle(z["phi"], z["y"], model, nthreads=nthreads, gene_depths=z["gene_depths"] if "gene_depths" in z.files else None)
     assert o.D == z["thetas"].shape[1]
     for jac in (0, 1):
         for pro in (0, 1):
@@ -37,10 +39,10 @@ def test_log_prob_and_grad_match_stan_transcription(golden_dir, name, model, nth
                 assert lp2 == pytest.approx(lp, rel=1e-13)
 
 
-@pytest.mark.parametrize("name,model", CASES[:2])
+@pytest.mark.parametrize("name,model", CASES[:2] + CASES[4:6])
 def test_gradient_central_differences(golden_dir, name, model):
     z = _load(golden_dir, name)
-    o = orc.Oracle(z["phi"], z["y"], model)
+    o = orc.Oracle(z["phi"], z["y"], model, gene_depths=z["gene_depths"] if "gene_depths" in z.files else None)
     th = z["thetas"][1]
     _, g = o.log_prob(th, jacobian=1, propto=1)
     rng = np.random.default_rng(0)
