@@ -7,7 +7,9 @@
 
 #include <algorithm>
 #include <chrono>
+#include <climits>
 #include <cmath>
+#include <cstdint>
 #include <map>
 #include <vector>
 
@@ -100,6 +102,8 @@ static void free_model(bvg_fit *f) {
   cudaFree((void *)f->m.hist_val);
   cudaFree((void *)f->m.depths);
   f->m.depths = nullptr;
+  cudaFree(f->m.elbo_lps);
+  f->m.elbo_lps = nullptr; f->elbo_cap = 0;
   f->Y = f->Phi = nullptr; f->dvec = f->summary = f->draws = nullptr;
   f->m.C = f->m.Ppart = f->m.Spart = nullptr; f->m.blk = nullptr; f->m.ctl = nullptr; f->m.hist_val = nullptr;
 }
@@ -162,9 +166,22 @@ static int finalize_model(bvg_fit *f) {
   const int ntiles = (int)(m.Gpad / BVG_GENE_TILE);
   const int64_t chunk = f->engine == BVG_ENGINE_TCGEN05 ? 64 : 32;  // spots per pipeline chunk of the likelihood kernel
   const int64_t nchunks = (m.M + chunk - 1) / chunk;
-  // SIMT: ~4 resident CTAs per SM; tcgen05: one 176 KB CTA per SM and never more CTAs than SMs (a
-  // partial second wave would double the kernel time), so round DOWN
-  int nsplit = f->engine == BVG_ENGINE_TCGEN05 ? std::max(1, nsm / ntiles) : (nsm * 4 + ntiles - 1) / ntiles;
+  // SIMT: ~4 resident CTAs per SM.  tcgen05: one ~220 KB CTA per SM, so the grid runs in whole waves of nsm CTAs;
+  // pick the split count that minimises waves x (chunks per CTA + ~4 chunk-times of prologue / drain per wave).
+  // (With "as many CTAs as fit in ONE wave" a 79-tile problem -- config 4 on one GPU -- ran on 79 of 148 SMs.)
+  int nsplit;
+  if (f->engine == BVG_ENGINE_TCGEN05) {
+    int64_t best_cost = INT64_MAX;
+    nsplit = 1;
+    const int64_t smax = std::max<int64_t>(1, std::min<int64_t>(nchunks / 6, 96));
+    for (int64_t s = 1; s <= smax; ++s) {
+      const int64_t c = (nchunks + s - 1) / s, se = (nchunks + c - 1) / c;
+      const int64_t waves = (ntiles * se + nsm - 1) / nsm, cost = waves * (c + 4);
+      if (cost < best_cost) { best_cost = cost; nsplit = (int)se; }
+    }
+  } else {
+    nsplit = (nsm * 4 + ntiles - 1) / ntiles;
+  }
   nsplit = (int)std::max<int64_t>(1, std::min<int64_t>(nsplit, nchunks));
   const int64_t cps = (nchunks + nsplit - 1) / nsplit;
   m.nsplit = (int)((nchunks + cps - 1) / cps);
@@ -447,8 +464,40 @@ static int advi_elbo(bvg_fit *f, int S, double *out) {
   }
   h.elbo_acc = 0; h.elbo_ok = 0;
   BVG_TRY(ctl_set(f, h));
-  for (int s = 0; s < S; ++s) BVG_TRY(eval_log_prob_device(f, MODE_ELBO_DRAW, 1, 0, false));
   const int64_t D = f->m.L.D;
+  if (f->comm_mode) {
+    // gene-sharded: every draw leaves its LOCAL share of the log density in elbo_lps[draw] with no exchange; one
+    // all-reduce of the S scalars (and of the entropy sum) follows
+    if (f->elbo_cap < S) {
+      cudaFree(f->m.elbo_lps);
+      f->m.elbo_lps = nullptr; f->elbo_cap = 0;
+      CUDA_TRY(cudaMalloc(&f->m.elbo_lps, sizeof(double) * S));
+      f->elbo_cap = S;
+    }
+    f->m.elbo_local = 1;
+    f->m.rank_id = f->cfg.rank;
+    int rc = BVG_OK;
+    for (int s = 0; s < S && rc == BVG_OK; ++s) rc = eval_log_prob_device(f, MODE_ELBO_DRAW, 1, 0, false);
+    f->m.elbo_local = 0;
+    BVG_TRY(rc);
+    BVG_TRY(comm_allreduce(f, f->m.elbo_lps, S));
+    std::vector<double> lps(S);
+    CUDA_TRY(cudaMemcpyAsync(lps.data(), f->m.elbo_lps, sizeof(double) * S, cudaMemcpyDeviceToHost, f->stream));
+    BVG_TRY(vec_dot_sum(f->stream, f->m.omega, nullptr, f->scratch + D, D, f->m.tot));
+    BVG_TRY(comm_allreduce(f, f->m.tot, 2));
+    double hs[2];
+    CUDA_TRY(cudaMemcpyAsync(hs, f->m.tot, sizeof(hs), cudaMemcpyDeviceToHost, f->stream));
+    CUDA_TRY(cudaStreamSynchronize(f->stream));
+    f->st.elbo_evals++;
+    double acc = 0;
+    int ok = 0;
+    for (double v : lps) if (std::isfinite(v)) { acc += v; ++ok; }
+    if (!ok) { *out = -INFINITY; return BVG_OK; }
+    *out = acc / ok + 0.5 * (double)f->m.LG.D * (1.0 + BVG_LOG_TWO_PI) + hs[1];
+    if (std::isnan(*out)) *out = -INFINITY;
+    return BVG_OK;
+  }
+  for (int s = 0; s < S; ++s) BVG_TRY(eval_log_prob_device(f, MODE_ELBO_DRAW, 1, 0, false));
   BVG_TRY(vec_dot_sum(f->stream, f->m.omega, nullptr, f->scratch + D, D, f->m.tot));
   BVG_TRY(comm_allreduce(f, f->m.tot, 2));
   double hs[2];

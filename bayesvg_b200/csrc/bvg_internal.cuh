@@ -129,6 +129,11 @@ struct DevModel {
   const double *suffGram;    // [(k+1)^2] Phi'^T Phi'
   long long *dbg;            // diagnostics: %globaltimer stamps (NULL unless bvg_debug_* is running)
   PeerCtx peer;              // world <= 1: no in-kernel exchange
+  // gene-sharded ELBO estimates: a draw's log density is linear in the cross-gene sums, so every rank forms its
+  // LOCAL share (gene-shared prior terms on rank 0 only) with no exchange per draw, stores it in elbo_lps[draw],
+  // and ONE all-reduce of the S scalars follows the S draws.
+  int elbo_local, rank_id;
+  double *elbo_lps;
 };
 
 // Sum-all-reduce of vals[0..n) (global memory, n <= min(BVG_PEER_CAP, blockDim.x)) across the ranks of p,
@@ -137,7 +142,19 @@ struct DevModel {
 // runs in rank order on every rank, so all ranks end with bit-identical results (the replicated
 // gene-shared parameters stay identical without a broadcast).  Parity double-buffering is enough: a
 // rank can only be one exchange ahead of a peer it is waiting for.
-__device__ inline void peer_allreduce_cta(const PeerCtx &p, double *vals, int n) {
+__device__ inline double peer_poll(const uint2 *src, uint32_t seq, long long t0) {
+  uint32_t lo, fl, hi, fh;
+  for (;;) {
+    asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(fl) : "l"(src) : "memory");
+    asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(hi), "=r"(fh) : "l"(src + 1) : "memory");
+    if (fl == seq && fh == seq) break;
+    if (clock64() - t0 > 40000000000LL) __trap();  // ~20 s: a peer never arrived -> fail instead of hanging the GPU
+  }
+  return __hiloint2double((int)hi, (int)lo);
+}
+// scratch: shared memory for (world - 1) * n doubles, or NULL.  With scratch every (peer, value) pair is polled by
+// its own thread, so the wait is one round trip instead of world - 1 of them in sequence.
+__device__ inline void peer_allreduce_cta(const PeerCtx &p, double *vals, int n, double *scratch) {
   __shared__ uint32_t s_seq;
   __syncthreads();  // the caller's writes to vals[] (same CTA) are visible
   if (threadIdx.x == 0) s_seq = *p.seq + 1;
@@ -153,26 +170,20 @@ __device__ inline void peer_allreduce_cta(const PeerCtx &p, double *vals, int n)
       asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(half), "r"(seq) : "memory");
     }
   }
+  const long long t0 = clock64();
+  const uint2 *mine = p.cells[p.rank] + slot;
   double s = 0.0;
   const int c = threadIdx.x;
-  if (c < n) {
-    const long long t0 = clock64();
-    for (int r = 0; r < p.world; ++r) {
-      double v;
-      if (r == p.rank) v = vals[c];
-      else {
-        const uint2 *src = p.cells[p.rank] + slot + (size_t)r * per_rank + 2 * c;
-        uint32_t lo, fl, hi, fh;
-        for (;;) {
-          asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(fl) : "l"(src) : "memory");
-          asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(hi), "=r"(fh) : "l"(src + 1) : "memory");
-          if (fl == seq && fh == seq) break;
-          if (clock64() - t0 > 40000000000LL) __trap();  // ~20 s: a peer never arrived -> fail instead of hanging the GPU
-        }
-        v = __hiloint2double((int)hi, (int)lo);
-      }
-      s += v;
+  if (scratch) {
+    for (int t = threadIdx.x; t < n * (p.world - 1); t += blockDim.x) {
+      const int ri = t / n, cc = t - ri * n, r = ri < p.rank ? ri : ri + 1;
+      scratch[t] = peer_poll(mine + (size_t)r * per_rank + 2 * cc, seq, t0);
     }
+    __syncthreads();
+    if (c < n)
+      for (int r = 0; r < p.world; ++r) s += r == p.rank ? vals[c] : scratch[(r < p.rank ? r : r - 1) * n + c];  // rank order
+  } else if (c < n) {
+    for (int r = 0; r < p.world; ++r) s += r == p.rank ? vals[c] : peer_poll(mine + (size_t)r * per_rank + 2 * c, seq, t0);
   }
   __syncthreads();  // every push has read vals[] before it is overwritten
   if (c < n) vals[c] = s;
@@ -266,6 +277,7 @@ struct bvg_fit {
   int comm_mode;
   NcclApi *nccl;
   void *comm;
+  int elbo_cap;        // capacity of m.elbo_lps
   void *peer_buf;      // this rank's exchange buffer (cudaMalloc, exported with cudaIpcGetMemHandle)
   void *peer_map[BVG_MAX_PEERS];  // peers' buffers opened with cudaIpcOpenMemHandle
 };

@@ -134,12 +134,17 @@ extern "C" int bvg_fit_peer_init(bvg_fit *f, const void *handles, size_t len) {
 }
 
 // stand-alone form of the exchange for the host-driven reductions (L-BFGS dot products, entropy term)
-__global__ void __launch_bounds__(1024) k_peer_allreduce(PeerCtx p, double *buf, int n) { peer_allreduce_cta(p, buf, n); }
+__global__ void __launch_bounds__(1024) k_peer_allreduce(PeerCtx p, double *buf, int n) {
+  extern __shared__ double scratch[];  // (world - 1) * n doubles
+  peer_allreduce_cta(p, buf, n, scratch);
+}
 
 int comm_allreduce(bvg_fit *f, double *buf, int n) {
   if (f->comm_mode == 2) {
-    for (int o = 0; o < n; o += BVG_PEER_CAP) {
-      k_peer_allreduce<<<1, 1024, 0, f->stream>>>(f->m.peer, buf + o, n - o < BVG_PEER_CAP ? n - o : BVG_PEER_CAP);
+    const int step = 512;  // (world - 1) * 512 doubles of polling scratch stay under the 48 KB default
+    for (int o = 0; o < n; o += step) {
+      const int nn = n - o < step ? n - o : step;
+      k_peer_allreduce<<<1, 1024, sizeof(double) * (f->m.peer.world - 1) * nn, f->stream>>>(f->m.peer, buf + o, nn);
       f->st.kernel_launches++;
     }
     CUDA_TRY(cudaGetLastError());

@@ -223,7 +223,7 @@ k_lik_tc(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtens
   const uint32_t bFullY = sBar, bEmptyY = bFullY + 8 * TC_NY, bFullB = bEmptyY + 8 * TC_NY, bEmptyB = bFullB + 8 * TC_NB;
   const uint32_t bD1Full = bEmptyB + 8 * TC_NB, bD1Empty = bD1Full + 16, bRFull = bD1Empty + 16, bRFree = bRFull + 16;
   const uint32_t bCFull = bRFree + 16, bD2Full = bCFull + 8, sTmemPtr = bD2Full + 8;
-  __shared__ float s_half[2][BVG_GENE_TILE];
+  __shared__ double s_half[2][BVG_GENE_TILE];
   auto stY = [&](int s, int h) { return base + s * YSTAGE_BYTES + h * YT_BYTES; };
   auto stF = [&](int s, int w) { return sB0 + s * BSTAGE_BYTES + w * FT_BYTES; };
   auto stT = [&](int s, int w) { return sB0 + s * BSTAGE_BYTES + 2 * FT_BYTES + w * TT_BYTES; };
@@ -381,7 +381,10 @@ k_lik_tc(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtens
       tc_fence_before();
       mbar_arrive(bCFull);
     }
-    float acc0 = 0.f, acc1 = 0.f, lt = 0.f, phi = 0.f;
+    // per-chunk sums (32 terms) in fp32, running sums over the CTA's spot range in fp64: a serial fp32 sum over
+    // thousands of spots loses ~1e-5 of the log density, enough to stall the L-BFGS line search at config-4 scale
+    double sum0 = 0.0, sum1 = 0.0;
+    float lt = 0.f, phi = 0.f;
     if (LIK == BVG_NB) { lt = (float)a.zeta[a.tail_idx]; phi = __expf(lt); }
     const bool tr = a.trace && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 96;
     for (int c = 0; c < n; ++c) {
@@ -399,6 +402,7 @@ k_lik_tc(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtens
       const uint32_t yrow = stY(s, h) + r * 128;
       const int64_t spot0 = (int64_t)(c_begin + c) * TC_CHUNK + 32 * h;
       uint32_t p1[16], p2[16];
+      float acc0 = 0.f, acc1 = 0.f;
 #pragma unroll
       for (int c4 = 0; c4 < 8; ++c4) {
         const uint32_t off = (uint32_t)((c4 ^ (r & 7)) << 4);  // 128B swizzle: 16B chunk index ^ (row & 7)
@@ -427,6 +431,8 @@ k_lik_tc(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtens
         split_bf16x2(res[2], res[3], p1[2 * c4 + 1], p2[2 * c4 + 1]);
       }
       mbar_arrive(bEmptyY + 8 * s);  // y is in registers: the Y stage can be refilled
+      sum0 += (double)acc0;
+      if (LIK == BVG_NB) sum1 += (double)acc1;
       if (BWD) {
         if (tr) a.trace[c * 8 + 6] = clock64();
         if (c >= 2) mbar_wait(bRFree + 8 * b, ((c >> 1) - 1) & 1);  // MMA2 of chunk c-2 has consumed this buffer
@@ -455,11 +461,11 @@ k_lik_tc(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtens
       for (int i = 0; i < 16; ++i)
         if (16 * h + i < a.KP) a.Ppart[row * a.KP + 16 * h + i] = p[i];
     }
-    if (h == 1) { s_half[0][r] = acc0; s_half[1][r] = acc1; }
+    if (h == 1) { s_half[0][r] = sum0; s_half[1][r] = sum1; }
     asm volatile("bar.sync 1, 256;" ::: "memory");
     if (h == 0) {
-      a.Spart[row * 2 + 0] = acc0 + s_half[0][r];
-      a.Spart[row * 2 + 1] = acc1 + s_half[1][r];
+      a.Spart[row * 2 + 0] = (float)(sum0 + s_half[0][r]);
+      a.Spart[row * 2 + 1] = (float)(sum1 + s_half[1][r]);
     }
   }
   if (tr0) a.trace[8 * 30 + 2] = clock64();

@@ -200,7 +200,7 @@ __device__ inline long long gtime() { return clock64(); }
 // gene-shared parameters, counters.  A multi-GPU fit all-reduces tot[] between the two phases.
 // ahead != 0 (ADVI update only): also draw the NEXT evaluation's zeta of the gene-shared parameters and
 // publish their exponentials, so that no k_prep launch sits between this evaluation and the next.
-__device__ void finish_body(const DevModel &m, int mode, int jac, int propto, int phase, int ahead) {
+__device__ void finish_body(const DevModel &m, int mode, int jac, int propto, int phase, int ahead, double *scratch = nullptr) {
   __shared__ double red[2][32];
   __shared__ double s_lp;
   const int k = m.k, NS = bvg_ns(k), tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -284,12 +284,14 @@ __device__ void finish_body(const DevModel &m, int mode, int jac, int propto, in
   if (!(phase & 2)) return;
   // multi-GPU, fused: the cross-gene sums of every gene shard meet here, inside the kernel that produced
   // them -- stores into the peers' exchange buffers over NVLink, no extra launch (bvg_internal.cuh)
-  if ((phase & 1) && m.peer.world > 1) peer_allreduce_cta(m.peer, m.tot, NS);
+  const bool loc = m.elbo_local && mode == MODE_ELBO_DRAW;  // local share of a sharded ELBO draw: no exchange
+  if ((phase & 1) && m.peer.world > 1 && !loc) peer_allreduce_cta(m.peer, m.tot, NS, scratch);
+  const double shw = (loc && m.rank_id != 0) ? 0.0 : 1.0;   // weight of the terms that involve gene-shared parameters only
   const double *tot = m.tot;
   const double mb = zt[L.mu_beta0], lsb = zt[L.sigma_beta0], sb = m.shx[0];
   const double ma = zt[L.mu_amp], lsa = zt[L.sigma_amp], sa = m.shx[1];
   const double lt = zt[L.tail], tl = m.shx[2];
-  const double Gt = (double)m.G_total, N = (double)m.M * Gt;
+  const double Gt = loc ? (double)m.G : (double)m.G_total, N = (double)m.M * Gt;
   const double j1 = jac ? 1.0 : 0.0;
   const int it = m.ctl->it;
   if (warp == (blockDim.x >> 5) - 1) {  // log density (last warp, concurrently with the gradient threads below)
@@ -300,27 +302,35 @@ __device__ void finish_body(const DevModel &m, int mode, int jac, int propto, in
     }
     pa = warp_sum(pa);
     if (lane == 0) {
-      double lp;
-      if (m.lik == BVG_GAUSSIAN) lp = -N * lt - 0.5 * tot[S_SSE] / (tl * tl) - 0.5 * tl * tl;
-      else lp = tot[S_SSE] + tot[S_LG] - log1p(tl * tl / 4.0);
-      if (m.depth && m.lik == BVG_GAUSSIAN) lp += 0.5 * tl * tl - tl * tl / 8.0;  // sigma_y ~ normal(0, 2) (approxGP2.stan:44)
-      lp += -0.5 * tot[S_Z2] - mb * mb / 8.0 - (m.depth ? sb * sb / 8.0 : 0.5 * sb * sb) - ma * ma / 8.0 - 0.5 * sa * sa;
+      double lp, lsh;  // lp: terms carrying cross-gene sums or gene counts; lsh: gene-shared parameters only
+      if (m.lik == BVG_GAUSSIAN) { lp = -N * lt - 0.5 * tot[S_SSE] / (tl * tl); lsh = -0.5 * tl * tl; }
+      else { lp = tot[S_SSE] + tot[S_LG]; lsh = -log1p(tl * tl / 4.0); }
+      if (m.depth && m.lik == BVG_GAUSSIAN) lsh += 0.5 * tl * tl - tl * tl / 8.0;  // sigma_y ~ normal(0, 2) (approxGP2.stan:44)
+      lp += -0.5 * tot[S_Z2];
+      lsh += -mb * mb / 8.0 - (m.depth ? sb * sb / 8.0 : 0.5 * sb * sb) - ma * ma / 8.0 - 0.5 * sa * sa;
       lp += -Gt * lsa - tot[S_U] - 0.5 * tot[S_DU2] / (sa * sa);
-      lp += pa;
-      if (jac) lp += (m.depth ? 0.0 : lsb) + lsa + tot[S_U] + lt;
+      lsh += pa;
+      if (jac) { lp += tot[S_U]; lsh += (m.depth ? 0.0 : lsb) + lsa + lt; }
       if (!propto) {
         if (!m.depth) {
-          if (m.lik == BVG_GAUSSIAN)
-            lp += -0.5 * BVG_LOG_TWO_PI * (N + (double)k * Gt + 2.0 * Gt + 2.0 * k + 5.0) - (k + 2.0) * BVG_LOG_TWO;
-          else
-            lp += -0.5 * BVG_LOG_TWO_PI * ((double)k * Gt + 2.0 * Gt + 2.0 * k + 4.0) - (k + 2.0) * BVG_LOG_TWO - BVG_LOG_PI;
+          if (m.lik == BVG_GAUSSIAN) {
+            lp += -0.5 * BVG_LOG_TWO_PI * (N + (double)k * Gt + 2.0 * Gt);
+            lsh += -0.5 * BVG_LOG_TWO_PI * (2.0 * k + 5.0) - (k + 2.0) * BVG_LOG_TWO;
+          } else {
+            lp += -0.5 * BVG_LOG_TWO_PI * ((double)k * Gt + 2.0 * Gt);
+            lsh += -0.5 * BVG_LOG_TWO_PI * (2.0 * k + 4.0) - (k + 2.0) * BVG_LOG_TWO - BVG_LOG_PI;
+          }
         } else {  // approxGP2/3: no z_beta0 terms; normal(0, 2) on beta0, beta1, mu_amplitude, mu_alpha[k] (and sigma_y)
-          if (m.lik == BVG_GAUSSIAN)
-            lp += -0.5 * BVG_LOG_TWO_PI * (N + (double)k * Gt + Gt + 2.0 * k + 5.0) - (k + 4.0) * BVG_LOG_TWO;
-          else
-            lp += -0.5 * BVG_LOG_TWO_PI * ((double)k * Gt + Gt + 2.0 * k + 4.0) - (k + 3.0) * BVG_LOG_TWO - BVG_LOG_PI;
+          if (m.lik == BVG_GAUSSIAN) {
+            lp += -0.5 * BVG_LOG_TWO_PI * (N + (double)k * Gt + Gt);
+            lsh += -0.5 * BVG_LOG_TWO_PI * (2.0 * k + 5.0) - (k + 4.0) * BVG_LOG_TWO;
+          } else {
+            lp += -0.5 * BVG_LOG_TWO_PI * ((double)k * Gt + Gt);
+            lsh += -0.5 * BVG_LOG_TWO_PI * (2.0 * k + 4.0) - (k + 3.0) * BVG_LOG_TWO - BVG_LOG_PI;
+          }
         }
       }
+      lp += shw * lsh;
       s_lp = lp;
     }
   } else if (big && (mode == MODE_GRAD_OUT || mode == MODE_ADVI_UPDATE)) {
@@ -400,7 +410,8 @@ __device__ void finish_body(const DevModel &m, int mode, int jac, int propto, in
     m.ctl->lp = lp;
     if (mode == MODE_ADVI_UPDATE) { m.ctl->t_grad += 1; m.ctl->it = it + 1; }
     else if (mode == MODE_ELBO_DRAW) {
-      if (isfinite(lp)) { m.ctl->elbo_acc += lp; m.ctl->elbo_ok += 1; }
+      if (loc) { m.elbo_lps[m.ctl->elbo_ok] = lp; m.ctl->elbo_ok += 1; }  // local share; the host all-reduces the S slots
+      else if (isfinite(lp)) { m.ctl->elbo_acc += lp; m.ctl->elbo_ok += 1; }
       m.ctl->t_elbo += 1;
     }
   }
@@ -552,7 +563,9 @@ __global__ void __launch_bounds__(BVG_GENE_MAX_THREADS) k_gene(DevModel m, int m
   __syncthreads();
   if (!s_last) return;
   DBG(4);
-  finish_body(m, mode, jac, propto, fuse, ahead);  // fuse = 3: reduce + finish; fuse = 1 (multi-GPU): reduce only, the all-reduce follows
+  // fuse = 3: reduce + (exchange) + finish; fuse = 1 (NCCL): reduce only, the all-reduce follows.  The warps' smem
+  // rows are free by now and serve as the exchange's polling scratch when they are large enough.
+  finish_body(m, mode, jac, propto, fuse, ahead, (m.peer.world - 1) * NS <= nw * NS ? sm : nullptr);
   DBG(7);
 }
 
@@ -684,7 +697,7 @@ int launch_gene_finish(bvg_fit *f, int mode, int jac, int propto, int ahead) {
     else CUDA_TRY(launch_pdl(k_gene_big<float>, dim3(f->m.nblk_gene), dim3(wb * 32), shb, f->stream, f->m, mode, jac, propto, fuseb));
     f->st.kernel_launches++;
     if (fuseb == 1) {
-      BVG_TRY(comm_allreduce(f, f->m.tot, bvg_ns(f->m.k)));
+      if (!(f->m.elbo_local && mode == MODE_ELBO_DRAW)) BVG_TRY(comm_allreduce(f, f->m.tot, bvg_ns(f->m.k)));
       k_finish<<<1, 512, 0, f->stream>>>(f->m, mode, jac, propto, 2, 0);
       f->st.kernel_launches += 1;
       CUDA_TRY(cudaGetLastError());
@@ -696,7 +709,7 @@ int launch_gene_finish(bvg_fit *f, int mode, int jac, int propto, int ahead) {
   else CUDA_TRY(launch_pdl(k_gene<float>, dim3(f->m.nblk_gene), dim3(wpb * 32), sh, f->stream, f->m, mode, jac, propto, fuse, ahead, tg_next));
   f->st.kernel_launches++;
   if (fuse == 1) {
-    BVG_TRY(comm_allreduce(f, f->m.tot, bvg_ns(f->m.k)));
+    if (!(f->m.elbo_local && mode == MODE_ELBO_DRAW)) BVG_TRY(comm_allreduce(f, f->m.tot, bvg_ns(f->m.k)));
     k_finish<<<1, 512, 0, f->stream>>>(f->m, mode, jac, propto, 2, ahead);
     f->st.kernel_launches += 1;
     CUDA_TRY(cudaGetLastError());

@@ -31,6 +31,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 M_SPOTS, G_GENES, K_BASIS = 4992, 3000, 20
+# --workload cfg4 (BASELINE.json configs[3]): 50,000 spots x 10,000 genes, Matern-1.5, gene-sharded over the ranks
+# (STRONG scaling: the 10,000 genes are split, `value` counts evaluations of the whole problem)
+CFG4_M, CFG4_G = 50000, 10000
 
 
 def load_peaks():
@@ -88,14 +91,18 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples)}
 
 
-def make_dataset(basis_fn, seed):
+def make_dataset(basis_fn, seed, workload="cfg2", n_genes=G_GENES):
     from bayesvg_b200 import synth
-    X = synth.scale_coords(synth.visium_grid())
-    C = synth.det_kmeans(X, K_BASIS, 312)
     from bayesvg_b200.api import length_scale_kmeans
+    if workload == "cfg4":
+        X = synth.scale_coords(synth.random_points(CFG4_M, 1))
+        C = synth.det_kmeans(X, K_BASIS, 312, iters=30)
+    else:
+        X = synth.scale_coords(synth.visium_grid())
+        C = synth.det_kmeans(X, K_BASIS, 312)
     ls = length_scale_kmeans(C)
     phi = basis_fn(X, C, ls)
-    Y, _ = synth.expression(phi, G_GENES, "gaussian", seed)
+    Y, _ = synth.expression(phi, n_genes, "gaussian", seed)
     return phi, Y
 
 
@@ -157,12 +164,21 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     if world > 1:
         import torch.distributed as td
+        if os.environ.get("NCCL_DEBUG", "VERSION") == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner out of stdout: rank 0 prints ONE JSON line
         td.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    phi, Y = make_dataset(lambda X, C, ls: bvg.basis_build(X, C, ls, "matern", 2.5, device=local_rank), 312 + rank)
+    cfg4 = args.workload == "cfg4"
+    if cfg4:   # strong scaling: this rank's contiguous share of the 10,000 genes
+        g_lo, g_hi = bdist.Shard(rank, world).gene_range(CFG4_G)
+        G_local, G_total, g_off, nu, M_w = g_hi - g_lo, CFG4_G, g_lo, 1.5, CFG4_M
+    else:      # weak scaling: 3,000 genes on every rank
+        G_local, G_total, g_off, nu, M_w = G_GENES, G_GENES * world, G_GENES * rank, 2.5, M_SPOTS
+    phi, Y = make_dataset(lambda X, C, ls: bvg.basis_build(X, C, ls, "matern", nu, device=local_rank), 312 + rank,
+                          args.workload, G_local)
     E = args.evals_per_step
     cfg = dict(device=local_rank, seed=312)
     if world > 1:
-        fit = bdist.make_sharded_fit(phi, Y, bdist.Shard(rank, world), G_GENES * world, G_GENES * rank, "gaussian",
+        fit = bdist.make_sharded_fit(phi, Y, bdist.Shard(rank, world), G_total, g_off, "gaussian",
                                      "fast", args.engine, cfg, args.comm)
     else:
         fit = bvg.Fit(phi, Y, "gaussian", "fast", args.engine, **cfg)
@@ -197,12 +213,14 @@ def run_ours(args, rank, world, local_rank):
         t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
         td.all_reduce(t, op=td.ReduceOp.MAX)
         ms_total = float(t.item())
-    value = world * args.steps * E / (ms_total * 1e-3)
+    # cfg2 (weak): every rank evaluates its own 3,000 genes -> world 3,000-gene evaluations per global evaluation;
+    # cfg4 (strong): one evaluation = all 10,000 genes, whatever the number of ranks
+    value = (1 if cfg4 else world) * args.steps * E / (ms_total * 1e-3)
 
     # ---- the dominant kernel against its roofline ----
     peak, peak_src = load_peaks()
     KP = 24
-    bytes_launch = 4 * M_SPOTS * G_GENES + 4 * M_SPOTS * K_BASIS + 8 * K_BASIS * G_GENES
+    bytes_launch = 4 * M_w * G_local + 4 * M_w * K_BASIS + 8 * K_BASIS * G_local
     ms_cold = fit.time_lik_kernel(20, True, True)
     ms_warm = fit.time_lik_kernel(50, False, True)
     traffic = None
@@ -224,7 +242,7 @@ def run_ours(args, rank, world, local_rank):
     assert Yh.flags.f_contiguous
     e2e_steps = max(2, min(args.steps, 5))
     if world > 1:   # the NCCL communicator belongs to the fit object and is created once, like a user would
-        f2 = bdist.make_sharded_fit(phi, Yh, bdist.Shard(rank, world), G_GENES * world, G_GENES * rank,
+        f2 = bdist.make_sharded_fit(phi, Yh, bdist.Shard(rank, world), G_total, g_off,
                                     "gaussian", "fast", args.engine, cfg, args.comm)
     else:
         f2 = bvg.Fit(phi, Yh, "gaussian", "fast", args.engine, **cfg)
@@ -244,14 +262,27 @@ def run_ours(args, rank, world, local_rank):
         t = torch.tensor([e2e_dt], device="cuda", dtype=torch.float64)
         td.all_reduce(t, op=td.ReduceOp.MAX)
         e2e_dt = float(t.item())
-    e2e = {"value": world * e2e_steps * E / e2e_dt, "unit": "evals/s",
+    e2e = {"value": (1 if cfg4 else world) * e2e_steps * E / e2e_dt, "unit": "evals/s",
            "h2d_bytes_per_step": int(Y.nbytes + 8 * D), "d2h_bytes_per_step": int(16 * D),
            "what": f"bvg_fit_set_y_f64(host Y) + {E} ELBO-gradient evals + read-back of (mu, omega); the H2D of Y is "
                    f"amortised over {E} evals here, over >= 3,250 in a real fit"}
 
     # ---- full default fit (the other half of the metric: SVG fit wall-clock), N = 1 only ----
     fit_info = None
-    if world == 1 and not args.skip_fit:
+    if cfg4 and not args.skip_fit:   # the whole default fit of the 50k x 10k problem, gene-sharded over the ranks
+        barrier()
+        t0 = time.perf_counter()
+        f3 = (bdist.make_sharded_fit(phi, Y, bdist.Shard(rank, world), G_total, g_off, "gaussian", "fast", args.engine, cfg, args.comm)
+              if world > 1 else bvg.Fit(phi, Y, "gaussian", "fast", args.engine, **cfg))
+        f3.run()
+        barrier()
+        s3 = f3.stats()
+        fit_info = {"wall_s": time.perf_counter() - t0, "grad_evals": s3["grad_evals"], "elbo_evals": s3["elbo_evals"],
+                    "advi_iters": s3["advi_iters"], "eta": s3["eta"], "mle_iters": s3["mle_iters"], "mle_fevals": s3["mle_fevals"],
+                    "sec_mle": s3["sec_mle"], "sec_adapt": s3["sec_adapt"], "sec_sga": s3["sec_sga"], "sec_draws": s3["sec_draws"],
+                    "converged": s3["converged"], "elbo": s3["elbo"]}
+        f3.close()
+    if world == 1 and not args.skip_fit and not cfg4:
         t0 = time.perf_counter()
         f3 = bvg.Fit(phi, Y, "gaussian", "fast", args.engine, **cfg)
         f3.run()
@@ -274,7 +305,7 @@ def run_ours(args, rank, world, local_rank):
     # ---- the same kernel on an input that does NOT fit in L2: one config-4 shard (50,000 spots x 1,250 genes =
     # what each of 8 GPUs holds at 50k x 10k; Y = 250 MB), back-to-back launches, no flush needed ----
     roofline_large = None
-    if world == 1 and not args.skip_large:
+    if world == 1 and not args.skip_large and not cfg4:
         from bayesvg_b200 import synth
         Ml, Gl = 50000, 1250
         Xl = synth.scale_coords(synth.random_points(Ml, 1))
@@ -295,7 +326,7 @@ def run_ours(args, rank, world, local_rank):
         fl.close()
 
     cpu = None
-    if rank == 0 and world == 1 and not args.skip_cpu:
+    if rank == 0 and world == 1 and not args.skip_cpu and not cfg4:
         nthreads = os.cpu_count() or 1
         n, dt = cpu_evals(phi, Y, args.cpu_seconds, 3, nthreads)
         cpu = {"value": n / dt, "unit": "evals/s", "cores": nthreads, "kind": "port",
@@ -305,13 +336,14 @@ def run_ours(args, rank, world, local_rank):
         print(json.dumps({
             "metric": "elbo_grad_evals_per_sec", "value": value, "unit": "evals/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "higher_is_better": True, "scaling": "strong" if cfg4 else "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": "cfg2: 4,992 spots x 3,000 genes per GPU, k=20 Matern-2.5, gaussian, meanfield ADVI",
+            "config": {"workload": ("cfg4: 50,000 spots x 10,000 genes in total (gene-sharded), k=20 Matern-1.5, gaussian, meanfield ADVI"
+                                    if cfg4 else "cfg2: 4,992 spots x 3,000 genes per GPU, k=20 Matern-2.5, gaussian, meanfield ADVI"),
                        "evals_per_step": E, "engine": eng_name,
                        "l2": ("L2 flushed (512 MB write) before every timed step; inside a step the evals re-read "
                               "the 60 MB Y as the real fit does" if not args.no_flush else "no flush"),
-                       "genes_total": G_GENES * world,
+                       "genes_total": G_total,
                        "exchange": (None if world == 1 else
                                     ("2k+10 fp64 sums per eval, all-reduced inside k_gene's last CTA over CUDA-IPC peer memory (NVLink)"
                                      if args.comm == "peer" else "2k+10 fp64 sums per eval, ncclAllReduce between k_gene and k_finish"))},
@@ -333,6 +365,7 @@ def main():
     ap.add_argument("--ref-evals-per-step", type=int, default=2)
     ap.add_argument("--engine", default="auto", choices=["auto", "simt", "tcgen05"])
     ap.add_argument("--comm", default="peer", choices=["peer", "nccl"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg4"])
     ap.add_argument("--no-flush", action="store_true")
     ap.add_argument("--pin", action="store_true", default=True)
     ap.add_argument("--skip-cpu", action="store_true")
