@@ -102,6 +102,8 @@ static void free_model(bvg_fit *f) {
   cudaFree((void *)f->m.hist_val);
   cudaFree((void *)f->m.depths);
   f->m.depths = nullptr;
+  cudaFree(f->m.hterm);
+  f->m.hterm = nullptr;
   cudaFree(f->m.elbo_lps);
   f->m.elbo_lps = nullptr; f->elbo_cap = 0;
   f->Y = f->Phi = nullptr; f->dvec = f->summary = f->draws = nullptr;
@@ -350,10 +352,17 @@ static int set_y_impl(bvg_fit *f, const SRC *y, int64_t M, int64_t G) {
     CUDA_TRY(cudaMemcpyAsync(d + hv.size(), hc.data(), sizeof(double) * hv.size(), cudaMemcpyHostToDevice, f->stream));
     CUDA_TRY(cudaStreamSynchronize(f->stream));
     f->m.hist_val = d; f->m.hist_cnt = d + hv.size(); f->m.nhist = (int)hv.size(); f->m.lgam_y1 = lg1;
+    cudaFree(f->m.hterm);
+    f->m.hterm = nullptr;
   }
   CUDA_TRY(cudaStreamSynchronize(f->stream));
   if (!reuse) BVG_TRY(finalize_model(f));
   else suff_destroy(f);  // sufficient statistics belong to the previous Y
+  // nb, tcgen05 engine: the per-count lgamma / digamma terms are evaluated by 31 idle lanes per likelihood CTA --
+  // only when there is a lane for every distinct count; otherwise k_gene's finish evaluates them itself
+  if (f->cfg.likelihood == BVG_NB && f->engine == BVG_ENGINE_TCGEN05 &&
+      (int64_t)(f->m.Gpad / BVG_GENE_TILE) * f->m.nsplit * 31 >= f->m.nhist)
+    CUDA_TRY(cudaMalloc(&f->m.hterm, sizeof(double) * 2 * f->m.nhist));
   f->have_y = true;
   f->st.sec_h2d += now_s() - t0;
   return BVG_OK;

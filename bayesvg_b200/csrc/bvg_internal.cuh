@@ -124,6 +124,7 @@ struct DevModel {
   const double *hist_val;    // nb: value c
   const double *hist_cnt;    // nb: #pairs with y == c
   double lgam_y1;            // nb: sum lgamma(y+1) over local pairs
+  double *hterm;             // nb, tcgen05 engine: [nhist][2] per-count terms written by the likelihood kernel (else NULL)
   const double *suffU;       // [G][k+1] Phi'^T y_g   (sufficient-statistic ELBO, gaussian)
   const double *suffS2;      // [G] sum_s y^2
   const double *suffGram;    // [(k+1)^2] Phi'^T Phi'
@@ -229,6 +230,14 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
+__device__ inline double dev_digamma(double x) {
+  double r = 0.0;
+  while (x < 10.0) { r -= 1.0 / x; x += 1.0; }
+  const double f = 1.0 / (x * x);
+  const double t = f * (-1.0 / 12.0 + f * (1.0 / 120.0 + f * (-1.0 / 252.0 + f * (1.0 / 240.0 + f * (-1.0 / 132.0 + f * (691.0 / 32760.0 + f * (-1.0 / 12.0)))))));
+  return r + log(x) - 0.5 / x + t;
 }
 
 __device__ inline double warp_sum(double v) {

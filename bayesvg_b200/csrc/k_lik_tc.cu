@@ -62,6 +62,11 @@ struct TcArgs {
   int KP, cps, nchunks, nk1, nch32;  // nk1 = ceil((k+1)/16): K steps of the forward MMA; nch32 = ldY / 32
   const double *zeta;
   int64_t tail_idx;
+  // nb: the lgamma / digamma terms of the log density depend only on (distinct count c, phi_nb); the idle lanes of
+  // the basis-producer warp evaluate them here, off the serial finish of k_gene (SURVEY.md A.3 histogram trick)
+  const double *hist_val, *hist_cnt;
+  double *hterm;
+  int nhist;
   long long *trace;  // optional [chunk][8] clock64 stamps of CTA (0,0) (diagnostics)
 };
 
@@ -278,9 +283,9 @@ k_lik_tc(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtens
       }
     }
   } else if (warp == 11) {
-    // ===================== TMA producer, basis ring =====
-    if (lane == 0) {
-      for (int c = 0; c < n; ++c) {
+    // ===================== TMA producer, basis ring (lane 0); nb histogram terms (lanes 1..31) =====
+    auto produce = [&](int c0, int c1) {
+      for (int c = c0; c < c1; ++c) {
         const int s = c % TC_NB;
         if (c >= TC_NB) mbar_wait(bEmptyB + 8 * s, ((c / TC_NB) - 1) & 1);
         const int spot0 = (c_begin + c) * TC_CHUNK;
@@ -292,7 +297,24 @@ k_lik_tc(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtens
           tma_load_2d(stT(s, 1), &tmT2, bFullB + 8 * s, spot0, 0);
         }
       }
+    };
+    const int n0 = n < TC_NB ? n : TC_NB;
+    if (lane == 0) produce(0, n0);  // the whole ring is in flight before anything else happens in this warp
+    if (LIK == BVG_NB && a.hterm) {
+      // the other 31 lanes are idle: each evaluates the lgamma / digamma term of one distinct count (the ring above
+      // gives lane 0 several chunk-times of slack while it waits for them)
+      __syncwarp();
+      const int e = (int)((blockIdx.y * gridDim.x + blockIdx.x) * 31 + lane - 1);
+      if (lane > 0 && e < a.nhist) {
+        griddep_wait();  // phi_nb of this draw comes from k_prep / the previous k_gene
+        const double phi = exp(a.zeta[a.tail_idx]);
+        const double cv = a.hist_val[e], nv = a.hist_cnt[e];
+        a.hterm[2 * e] = nv * (lgamma(cv + phi) - lgamma(phi));
+        a.hterm[2 * e + 1] = nv * (dev_digamma(cv + phi) - dev_digamma(phi));
+      }
+      __syncwarp();
     }
+    if (lane == 0) produce(n0, n);
   } else if (warp == 1) {
     // ===================== forward MMA issuer (whole warp convergent, one elected lane issues) =====
     constexpr uint32_t idesc = make_idesc_bf16(128, 64);
@@ -603,6 +625,8 @@ int launch_lik_tc(bvg_fit *f, bool bwd) {
   memset(&a, 0, sizeof(a));  // padding bytes take part in the change check below
   a.Ppart = (float *)m.Ppart; a.Spart = (float *)m.Spart;
   a.W = m.W; a.U = m.U; a.k = m.k;
+  a.hist_val = m.hist_val; a.hist_cnt = m.hist_cnt; a.nhist = m.nhist;
+  a.hterm = m.lik == BVG_NB ? m.hterm : nullptr;  // allocated only when every distinct count gets a lane (api.cu)
   a.nk1 = (m.k + 1 + 15) / 16;
   a.nch32 = (int)(f->ldY / 32);
   a.M = m.M; a.G = m.G; a.Gpad = m.Gpad; a.KP = m.KP;

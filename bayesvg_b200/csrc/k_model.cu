@@ -180,14 +180,6 @@ __device__ inline void advi_update(const DevModel &m, int64_t li, double gv, boo
   m.omega[li] += es * go / (1.0 + sqrt(ho));
 }
 
-__device__ inline double dev_digamma(double x) {
-  double r = 0.0;
-  while (x < 10.0) { r -= 1.0 / x; x += 1.0; }
-  const double f = 1.0 / (x * x);
-  const double t = f * (-1.0 / 12.0 + f * (1.0 / 120.0 + f * (-1.0 / 252.0 + f * (1.0 / 240.0 + f * (-1.0 / 132.0 + f * (691.0 / 32760.0 + f * (-1.0 / 12.0)))))));
-  return r + log(x) - 0.5 / x + t;
-}
-
 // stamps use the SM cycle counter: a %globaltimer read stalls the warp for about a microsecond (four of them
 // in a row looked like a 3.6 us "load latency" in an earlier trace)
 __device__ inline long long gtime() { return clock64(); }
@@ -262,12 +254,18 @@ __device__ void finish_body(const DevModel &m, int mode, int jac, int propto, in
     if (m.lik == BVG_NB) {
       // sum_sg lgamma(y+phi) - lgamma(phi) and its digamma derivative depend only on (y, phi):
       // evaluate on the histogram of distinct counts
-      const double phi = m.shx[2], lg0 = lgamma(phi), dg0 = dev_digamma(phi);
       double lg = 0, dg = 0;
-      for (int i = tid; i < m.nhist; i += blockDim.x) {
-        const double c = m.hist_val[i], n = m.hist_cnt[i];
-        lg += n * (lgamma(c + phi) - lg0);
-        dg += n * (dev_digamma(c + phi) - dg0);
+      if (m.hterm) {
+        // tcgen05 engine: idle lanes of the likelihood kernel already evaluated n_c (lgamma(c + phi) - lgamma(phi)) and
+        // the digamma analogue for every distinct count c; only the additions are left for this serial section
+        for (int i = tid; i < m.nhist; i += blockDim.x) { lg += m.hterm[2 * i]; dg += m.hterm[2 * i + 1]; }
+      } else {
+        const double phi = m.shx[2], lg0 = lgamma(phi), dg0 = dev_digamma(phi);
+        for (int i = tid; i < m.nhist; i += blockDim.x) {
+          const double c = m.hist_val[i], n = m.hist_cnt[i];
+          lg += n * (lgamma(c + phi) - lg0);
+          dg += n * (dev_digamma(c + phi) - dg0);
+        }
       }
       lg = warp_sum(lg); dg = warp_sum(dg);
       if (lane == 0) { red[0][warp] = lg; red[1][warp] = dg; }
