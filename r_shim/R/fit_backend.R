@@ -7,10 +7,11 @@
 #
 # in scope at :290  : spatial_mtx (M x 2, scaled), kmeans_centers (k x 2), lscale, expr_df (long,
 #                     gene-major), gene_mapping, likelihood, kernel, kernel.smoothness, kernel.period,
-#                     n.iter, mle.init, mle.iter, n.draws, elbo.samples, random.seed, verbose
+#                     n.iter, mle.init, mle.iter, n.draws, elbo.samples, random.seed, verbose;
+#                     gene_depths (:303, log(rowSums(counts[naive.hvgs, ]))) when gene.depth.adjust = TRUE, else NULL
 bvg_fit_backend <- function(spatial_mtx, kmeans_centers, lscale, expr_df, gene_mapping, likelihood, kernel,
                             kernel.smoothness, kernel.period, n.iter, mle.init, mle.iter, n.draws,
-                            elbo.samples, random.seed, verbose, device = 0L) {
+                            elbo.samples, random.seed, verbose, gene_depths = NULL, device = 0L) {
   M <- nrow(spatial_mtx)
   G <- length(unique(expr_df$gene))
   kernel_id <- match(kernel, c("exp_quad", "matern", "periodic")) - 1L
@@ -25,9 +26,11 @@ bvg_fit_backend <- function(spatial_mtx, kmeans_centers, lscale, expr_df, gene_m
                                         mle_init = as.integer(mle.init), mle_iter = as.integer(mle.iter),
                                         n_draws = as.integer(n.draws), elbo_samples = as.integer(elbo.samples),
                                         seed = as.integer(random.seed), verbose = as.integer(verbose),
+                                        depth_adjust = as.integer(!is.null(gene_depths)),  # approxGP2 / approxGP3 (:293-318)
                                         device = as.integer(device)))
   on.exit(.Call("R_bvg_fit_destroy", fit), add = TRUE)
   .Call("R_bvg_fit_set_phi", fit, phi_ortho)
+  if (!is.null(gene_depths)) .Call("R_bvg_fit_set_gene_depths", fit, as.double(gene_depths))
   .Call("R_bvg_fit_set_y", fit, y)
   .Call("R_bvg_fit_run", fit)
   # :419-432  fit_vi$summary(variables = "amplitude") %>% rename / join / dispersion / rank

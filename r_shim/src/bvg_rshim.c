@@ -32,7 +32,7 @@ SEXP R_bvg_basis_build(SEXP coords, SEXP centers, SEXP lscale, SEXP kernel, SEXP
 }
 
 /* .Call("R_bvg_fit_create", list(likelihood=, precision=, n_iter=, mle_init=, mle_iter=, n_draws=,
- *        elbo_samples=, seed=, verbose=, device=)) -> external pointer */
+ *        elbo_samples=, seed=, verbose=, device=, depth_adjust=)) -> external pointer */
 static int geti(SEXP lst, const char *name, int dflt) {
   SEXP names = Rf_getAttrib(lst, R_NamesSymbol);
   for (R_xlen_t i = 0; i < Rf_xlength(lst); ++i)
@@ -52,6 +52,7 @@ SEXP R_bvg_fit_create(SEXP opts) {
   cfg.n_draws = geti(opts, "n_draws", cfg.n_draws);
   cfg.elbo_samples = geti(opts, "elbo_samples", cfg.elbo_samples);
   cfg.verbose = geti(opts, "verbose", cfg.verbose);
+  cfg.depth_adjust = geti(opts, "depth_adjust", cfg.depth_adjust);
   cfg.seed = (uint64_t)geti(opts, "seed", (int)cfg.seed);
   bvg_fit *f = NULL;
   chk(bvg_fit_create(&cfg, &f));
@@ -69,6 +70,11 @@ SEXP R_bvg_fit_set_y(SEXP p, SEXP y) {
   const int64_t M = Rf_nrows(y), G = Rf_ncols(y);
   if (TYPEOF(y) == INTSXP) chk(bvg_fit_set_y_i32(get_fit(p), INTEGER(y), M, G));
   else chk(bvg_fit_set_y_f64(get_fit(p), REAL(y), M, G));
+  return R_NilValue;
+}
+/* gene_depths: log(rowSums(counts[naive.hvgs, ])), findSpatiallyVariableFeaturesBayes.R:303 (gene.depth.adjust = TRUE) */
+SEXP R_bvg_fit_set_gene_depths(SEXP p, SEXP d) {
+  chk(bvg_fit_set_gene_depths(get_fit(p), REAL(d), (int64_t)Rf_xlength(d)));
   return R_NilValue;
 }
 SEXP R_bvg_fit_run(SEXP p) { chk(bvg_fit_run(get_fit(p))); return R_NilValue; }
@@ -103,7 +109,8 @@ static const R_CallMethodDef calls[] = {
   {"R_bvg_fit_set_phi", (DL_FUNC)&R_bvg_fit_set_phi, 2}, {"R_bvg_fit_set_y", (DL_FUNC)&R_bvg_fit_set_y, 2},
   {"R_bvg_fit_run", (DL_FUNC)&R_bvg_fit_run, 1},         {"R_bvg_fit_summary", (DL_FUNC)&R_bvg_fit_summary, 2},
   {"R_bvg_log_prob", (DL_FUNC)&R_bvg_log_prob, 4},       {"R_bvg_fit_variational", (DL_FUNC)&R_bvg_fit_variational, 2},
-  {"R_bvg_fit_destroy", (DL_FUNC)&R_bvg_fit_destroy, 1}, {NULL, NULL, 0}};
+  {"R_bvg_fit_destroy", (DL_FUNC)&R_bvg_fit_destroy, 1}, {"R_bvg_fit_set_gene_depths", (DL_FUNC)&R_bvg_fit_set_gene_depths, 2},
+  {NULL, NULL, 0}};
 void R_init_bayesVGb200(DllInfo *dll) {
   R_registerRoutines(dll, NULL, calls, NULL, NULL);
   R_useDynamicSymbols(dll, FALSE);
