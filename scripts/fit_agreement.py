@@ -1,0 +1,66 @@
+"""python scripts/fit_agreement.py [cfg1|cfg2|tiny] [n_threads] -- the whole default fit (L-BFGS init -> eta adaptation ->
+3,000 SGA iterations -> 1,000 draws -> summaries) on the B200 engine against the fp64 CPU restatement driving the
+same algorithm with the same Philox streams, on the stand-in for BASELINE.json configs[0] (seu_brain: 2,444 spots x
+3,000 HVGs, Matern-2.5, gaussian).  Reports what north_star asks for: Spearman correlation of amplitude_mean, top-1,000
+SVG overlap, both fits' agreement with the planted amplitudes, and the two wall-clocks.  Writes one JSON line."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+from scipy.stats import spearmanr
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bayesvg_b200 as bvg  # noqa: E402
+from bayesvg_b200 import synth  # noqa: E402
+from oracle import oracle as orc  # noqa: E402  (checker only)
+
+
+def main():
+    name = sys.argv[1] if len(sys.argv) > 1 else "cfg1"
+    nthreads = int(sys.argv[2]) if len(sys.argv) > 2 else (os.cpu_count() or 1)
+    ds = synth.dataset(name, lambda X, C, ls, kern, nu: bvg.basis_build(X, C, ls, kern, nu))
+    phi, Y, lik = ds["phi"], ds["Y"], ds["likelihood"]
+    M, G = Y.shape
+    out = dict(workload=f"{name}: {M} spots x {G} genes, k={ds['k']}, {ds['kernel']} {ds['nu']}, {lik}", n_draws=1000,
+               n_iter=3000, elbo_samples=150, seed=312)
+    res = {}
+    for prec, eng in (("fast", "auto"), ("fp64", "simt")):
+        t0 = time.perf_counter()
+        f = bvg.Fit(phi, Y, lik, prec, eng, seed=312)
+        tab = f.run()
+        st = f.stats()
+        res[prec] = tab
+        out[f"gpu_{prec}"] = dict(wall_s=time.perf_counter() - t0, eta=st["eta"], advi_iters=st["advi_iters"], converged=st["converged"],
+                                  elbo=st["elbo"], mle_iters=st["mle_iters"], sec_mle=st["sec_mle"], sec_adapt=st["sec_adapt"],
+                                  sec_sga=st["sec_sga"], engine=st["engine_used"])
+        f.close()
+    t0 = time.perf_counter()
+    o = orc.Oracle(phi, Y, lik, nthreads=nthreads)
+    th, li = o.lbfgs(max_iter=1000)
+    t1 = time.perf_counter()
+    mu, om, info = o.advi(th, iter=3000, elbo_samples=150, seed=312)
+    ref = o.summary(mu, om, 1000, 312)
+    out["cpu_port"] = dict(wall_s=time.perf_counter() - t0, sec_mle=t1 - t0, threads=nthreads, eta=info["eta"], advi_iters=info["iters"],
+                           converged=info["converged"], elbo=info.get("elbo"), mle_iters=li.get("iters") if isinstance(li, dict) else None)
+    top = min(1000, G // 3)
+
+    def agree(a, b):
+        ov = len(set(np.argsort(-a)[:top]) & set(np.argsort(-b)[:top])) / top
+        return dict(spearman=float(spearmanr(a, b).correlation), top_k=top, top_k_overlap=ov,
+                    max_rel_diff=float(np.max(np.abs(a - b) / np.abs(b))))
+
+    out["fast_vs_cpu"] = agree(res["fast"][:, 0], ref[:, 0])
+    out["fp64_vs_cpu"] = agree(res["fp64"][:, 0], ref[:, 0])
+    out["fast_vs_fp64_gpu"] = agree(res["fast"][:, 0], res["fp64"][:, 0])
+    amp = ds["amp"]
+    out["vs_planted_amplitude"] = dict(gpu_fast=float(spearmanr(res["fast"][:, 0], amp).correlation),
+                                       gpu_fp64=float(spearmanr(res["fp64"][:, 0], amp).correlation),
+                                       cpu_port=float(spearmanr(ref[:, 0], amp).correlation))
+    out["speedup_fast_vs_cpu_port"] = out["cpu_port"]["wall_s"] / out["gpu_fast"]["wall_s"]
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
