@@ -96,6 +96,7 @@ extern "C" int bvg_fit_create(const bvg_config *cfg, bvg_fit **out) {
 
 static void free_model(bvg_fit *f) {
   tc_destroy(f);
+  tcbig_destroy(f);
   suff_destroy(f);
   cudaFree(f->Y); cudaFree(f->Phi); cudaFree(f->dvec); cudaFree(f->summary); cudaFree(f->draws);
   cudaFree(f->m.C); cudaFree(f->m.Ppart); cudaFree(f->m.Spart); cudaFree(f->m.blk); cudaFree(f->m.ctl);
@@ -134,8 +135,9 @@ static int resolve_engine(bvg_fit *f) {
   const bool fp64 = f->cfg.precision == BVG_PREC_FP64;
   const int KP = (int)round_up(f->m.k + 1, 8);
   f->engine = f->cfg.engine;
-  if (f->engine == BVG_ENGINE_AUTO) f->engine = (!fp64 && KP <= 24 && tc_available()) ? BVG_ENGINE_TCGEN05 : BVG_ENGINE_SIMT;
-  if (f->engine == BVG_ENGINE_TCGEN05 && KP > 24) { bvg_set_error("tcgen05 engine supports k <= 23 basis functions in this build (k = %d)", f->m.k); return BVG_ERR_ARG; }
+  // tcgen05: the fused kernel for k + 1 <= 24, the two-GEMM large-basis kernels (k_lik_tcbig.cu) above that
+  if (f->engine == BVG_ENGINE_AUTO) f->engine = (!fp64 && tc_available()) ? BVG_ENGINE_TCGEN05 : BVG_ENGINE_SIMT;
+  f->big_tc = f->engine == BVG_ENGINE_TCGEN05 && KP > 24;
   f->st.engine_used = f->engine;
   return BVG_OK;
 }
@@ -166,13 +168,15 @@ static int finalize_model(bvg_fit *f) {
   int nsm = 148;
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, f->cfg.device);
   const int ntiles = (int)(m.Gpad / BVG_GENE_TILE);
-  const int64_t chunk = f->engine == BVG_ENGINE_TCGEN05 ? 64 : 32;  // spots per pipeline chunk of the likelihood kernel
+  const int64_t chunk = f->big_tc ? 128 : (f->engine == BVG_ENGINE_TCGEN05 ? 64 : 32);  // spots per pipeline chunk of the likelihood kernel
   const int64_t nchunks = (m.M + chunk - 1) / chunk;
   // SIMT: ~4 resident CTAs per SM.  tcgen05: one ~220 KB CTA per SM, so the grid runs in whole waves of nsm CTAs;
   // pick the split count that minimises waves x (chunks per CTA + ~4 chunk-times of prologue / drain per wave).
   // (With "as many CTAs as fit in ONE wave" a 79-tile problem -- config 4 on one GPU -- ran on 79 of 148 SMs.)
   int nsplit;
-  if (f->engine == BVG_ENGINE_TCGEN05) {
+  if (f->big_tc) {
+    nsplit = std::max(1, nsm / ntiles);  // forward kernel: one wave of (gene tiles x splits) CTAs
+  } else if (f->engine == BVG_ENGINE_TCGEN05) {
     int64_t best_cost = INT64_MAX;
     nsplit = 1;
     const int64_t smax = std::max<int64_t>(1, std::min<int64_t>(nchunks / 6, 96));
@@ -213,11 +217,14 @@ static int finalize_model(bvg_fit *f) {
   CUDA_TRY(cudaMalloc(&f->summary, sizeof(double) * 8 * m.G));
   CUDA_TRY(cudaMalloc(&f->draws, sizeof(double) * m.G * f->cfg.n_draws));
   // Phi' in the compute type
-  f->Mpad = round_up(m.M, 64);
-  CUDA_TRY(cudaMalloc(&f->Phi, ts * f->Mpad * m.KP));
-  if (fp64) BVG_TRY(stage_phi<double>(f->phi64, (double *)f->Phi, m.M, f->Mpad, m.k, m.KP, f->stream));
-  else BVG_TRY(stage_phi<float>(f->phi64, (float *)f->Phi, m.M, f->Mpad, m.k, m.KP, f->stream));
-  if (f->engine == BVG_ENGINE_TCGEN05) BVG_TRY(tc_setup(f));
+  f->Mpad = round_up(m.M, f->big_tc ? 128 : 64);
+  if (!f->big_tc) {
+    CUDA_TRY(cudaMalloc(&f->Phi, ts * f->Mpad * m.KP));
+    if (fp64) BVG_TRY(stage_phi<double>(f->phi64, (double *)f->Phi, m.M, f->Mpad, m.k, m.KP, f->stream));
+    else BVG_TRY(stage_phi<float>(f->phi64, (float *)f->Phi, m.M, f->Mpad, m.k, m.KP, f->stream));
+  }
+  if (f->big_tc) BVG_TRY(tcbig_setup(f));
+  else if (f->engine == BVG_ENGINE_TCGEN05) BVG_TRY(tc_setup(f));
   if (m.depth) {
     double *d = nullptr;
     CUDA_TRY(cudaMalloc(&d, sizeof(double) * m.G));
@@ -284,9 +291,9 @@ static int set_y_impl(bvg_fit *f, const SRC *y, int64_t M, int64_t G) {
   const bool fp64 = f->cfg.precision == BVG_PREC_FP64;
   f->m.G = G;
   if (!reuse) BVG_TRY(resolve_engine(f));
-  const bool tiled = f->engine == BVG_ENGINE_TCGEN05;
+  const bool tiled = f->engine == BVG_ENGINE_TCGEN05 && !f->big_tc;
   f->tiledY = tiled;
-  f->ldY = fp64 ? M : round_up(M, 64);
+  f->ldY = fp64 ? M : round_up(M, f->big_tc ? 128 : 64);
   const size_t ts = fp64 ? 8 : 4;
   // tcgen05 engine: Y is stored TILE-MAJOR, [gene tile][32-spot chunk][128 genes][32 spots], so that every
   // TMA box (and every 64-spot pipeline stage) is one contiguous 16 KB (32 KB) run of HBM instead of 128
@@ -360,7 +367,7 @@ static int set_y_impl(bvg_fit *f, const SRC *y, int64_t M, int64_t G) {
   else suff_destroy(f);  // sufficient statistics belong to the previous Y
   // nb, tcgen05 engine: the per-count lgamma / digamma terms are evaluated by 31 idle lanes per likelihood CTA --
   // only when there is a lane for every distinct count; otherwise k_gene's finish evaluates them itself
-  if (f->cfg.likelihood == BVG_NB && f->engine == BVG_ENGINE_TCGEN05 &&
+  if (f->cfg.likelihood == BVG_NB && f->engine == BVG_ENGINE_TCGEN05 && !f->big_tc &&
       (int64_t)(f->m.Gpad / BVG_GENE_TILE) * f->m.nsplit * 31 >= f->m.nhist)
     CUDA_TRY(cudaMalloc(&f->m.hterm, sizeof(double) * 2 * f->m.nhist));
   f->have_y = true;
@@ -388,6 +395,7 @@ extern "C" int bvg_fit_dim(bvg_fit *f, int64_t *D) {
 
 // ---- one evaluation -----------------------------------------------------------------------------
 int launch_lik(bvg_fit *f, bool backward) {
+  if (f->big_tc) return launch_lik_tcbig(f, backward);
   return f->engine == BVG_ENGINE_TCGEN05 ? launch_lik_tc(f, backward) : launch_lik_simt(f, backward);
 }
 // zeta already holds the point (or is drawn by prep when mode is a draw mode)
@@ -438,7 +446,7 @@ static int ctl_get(bvg_fit *f, Ctl *h) {
 // k_gene draws the next evaluation's zeta itself ("draw-ahead"), and the likelihood kernel builds its
 // coefficient rows from zeta, so an evaluation is two launches.
 static int advi_steps(bvg_fit *f, int n) {
-  const bool ahead = f->engine == BVG_ENGINE_TCGEN05;
+  const bool ahead = f->engine == BVG_ENGINE_TCGEN05 && !f->big_tc && f->m.k <= BVG_SMALL_K;
   for (int i = 0; i < n; ++i) {
     if (!ahead || i == 0) BVG_TRY(launch_prep(f, PREP_GRAD));
     BVG_TRY(launch_lik(f, true));

@@ -278,6 +278,8 @@ struct bvg_fit {
   bvg_fit_stats st;
   // tcgen05 engine state (k_lik_tc.cu)
   void *tc;
+  void *tcbig;         // large-basis tcgen05 engine state (k_lik_tcbig.cu); non-NULL selects it
+  bool big_tc;         // engine == TCGEN05 with k + 1 > 24
   int gene_wpb;        // gene-warps per k_gene CTA
   uint32_t h_t_grad;   // host mirror of ctl->t_grad (lets k_gene draw ahead before its PDL wait)
   double *suff;        // sufficient statistics + scratch (k_suff.cu), lazily built
@@ -311,6 +313,9 @@ int launch_prep(bvg_fit *f, int mode);                       // k_model.cu: draw
 int launch_lik(bvg_fit *f, bool backward);                   // k_lik_simt.cu / k_lik_tc.cu dispatch
 int launch_lik_simt(bvg_fit *f, bool backward);
 int launch_lik_tc(bvg_fit *f, bool backward);
+int launch_lik_tcbig(bvg_fit *f, bool backward);             // k_lik_tcbig.cu
+int tcbig_setup(bvg_fit *f);
+void tcbig_destroy(bvg_fit *f);
 bool tc_available();                                         // false until the tcgen05 kernel is linked in
 int tc_setup(bvg_fit *f);                                    // build TMA descriptors etc.
 void tc_destroy(bvg_fit *f);

@@ -1,0 +1,328 @@
+// k_lik_tcbig.cu -- the likelihood pass on tensor cores for a LARGE basis (24 <= k+1 <= 512; BASELINE config 5 has
+// k ~ 400), where the whole coefficient row no longer fits the fused kernel's TMEM / shared-memory budget.
+// Two tcgen05 GEMM kernels share one warp-specialised main loop (TMA -> 3-stage smem ring -> tcgen05.mma with both
+// operands K-major in shared memory, 128 x 128 fp32 accumulator in TMEM, BF16x3 split: A1 B1 + A2 B1 + A1 B2):
+//   forward  (k_tcbig<FWD>): D[128 genes x 128 spots] = C'[genes x K] . Phi'[spots x K]^T           (approxGP.stan:33, :48 mean)
+//             epilogue (thread = gene row): f <- TMEM, y <- global, residual r, SSE / nb terms in registers (fp64 running
+//             sums), r -> global as two bf16 parts R1, R2 [gene][spot]
+//   backward (k_tcbig<BWD>): D[128 basis x 128 genes] = Phi'^T[basis x spots] . R[genes x spots]^T   (P' = Phi'^T r)
+//             epilogue (thread = basis row): D -> Ppart[split][gene][basis]
+// The residual makes one round trip through HBM (4 B per pair written + read) -- at k ~ 400 the contraction needs
+// ~4.8k flop per pair (x3 for the split), so the pass stays tensor-bound: 2.4 TFLOP per evaluation of a config-5 shard
+// against 6 GB of traffic.  The per-gene kernels (k_prep_big, k_gene_big) are the same as for the CUDA-core path.
+#include <string.h>
+
+#include "bvg_internal.cuh"
+#include "tc_ptx.cuh"
+
+#define TB_THREADS 192
+#define TB_STAGES 3
+#define TB_TILE_BYTES (128 * 128)                 // 128 rows x 64 bf16 (one 128-byte swizzled row per operand row)
+#define TB_STAGE_BYTES (4 * TB_TILE_BYTES)        // A1 | A2 | B1 | B2
+#define TB_SMEM_BYTES (TB_STAGES * TB_STAGE_BYTES + 1024 + 128)
+
+int tc_make_map(CUtensorMap *m, void *ptr, bool bf16, uint64_t cols, uint64_t rows, uint64_t ld, uint32_t box_rows);
+
+struct TbArgs {
+  // forward
+  const float *Y;           // [G][ldY] fp32
+  int64_t ldY, M, G, Gpad, Mpad;
+  __nv_bfloat16 *R1, *R2;   // [Gpad][Mpad]
+  float *Spart;             // [nsplit][Gpad][2]
+  // backward
+  float *Ppart;             // [nsplit][Gpad][KP]
+  int KP, k1;               // padded row width of Ppart, k + 1
+  int nkb;                  // forward: K blocks of 64 basis columns
+  int tiles_per_split;      // spot tiles (128 spots) per split
+  int ntiles_m;             // spot tiles in total
+  const double *zeta;
+  int64_t tail_idx;
+  int write_r;
+};
+
+struct TbState {
+  CUtensorMap tmC1, tmC2, tmF1, tmF2, tmT1, tmT2, tmR1, tmR2;
+  __nv_bfloat16 *F1, *F2, *T1, *T2, *R1, *R2, *C1, *C2;
+  int Kp, njb;
+};
+
+// MODE 0: forward (A = C' parts, B = F parts, K = basis), MODE 1: backward (A = T parts, B = R parts, K = spots)
+template <int MODE, int LIK>
+__global__ void __launch_bounds__(TB_THREADS, 1)
+k_tcbig(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
+        const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmB2, TbArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sBar = base + TB_STAGES * TB_STAGE_BYTES;
+  const uint32_t bFull = sBar, bEmpty = bFull + 8 * TB_STAGES, bDFull = bEmpty + 8 * TB_STAGES, bDEmpty = bDFull + 8, sTmem = bDEmpty + 8;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // work decomposition
+  //   forward : blockIdx.x = gene tile, blockIdx.y = split; tiles = spot tiles of the split; K loop = nkb basis blocks
+  //   backward: blockIdx.x = gene tile, blockIdx.y = split, blockIdx.z = basis block; one tile; K loop = spot blocks of the split
+  const int gt = blockIdx.x, split = blockIdx.y, jb = MODE == 1 ? blockIdx.z : 0;
+  const int t_begin = split * a.tiles_per_split;
+  int nt = a.ntiles_m - t_begin;
+  nt = nt < a.tiles_per_split ? nt : a.tiles_per_split;
+  if (nt < 0) nt = 0;
+  const int ntile = MODE == 0 ? nt : (nt > 0 ? 1 : 0);   // accumulator tiles this CTA produces
+  const int nk = MODE == 0 ? a.nkb : 2 * nt;              // K blocks (64 wide) per accumulator tile
+
+  griddep_launch();
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TB_STAGES; ++s) { mbar_init(bFull + 8 * s, 1); mbar_init(bEmpty + 8 * s, 1); }
+    mbar_init(bDFull, 1);
+    mbar_init(bDEmpty, 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sTmem), "r"(128u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(sTmem));
+  griddep_wait();  // operands written by the previous kernel (C' parts by k_prep_big, R parts by the forward kernel)
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int it = 0;
+      for (int t = 0; t < ntile; ++t) {
+        for (int kb = 0; kb < nk; ++kb, ++it) {
+          const int s = it % TB_STAGES;
+          if (it >= TB_STAGES) mbar_wait(bEmpty + 8 * s, ((it / TB_STAGES) - 1) & 1);
+          const uint32_t st = base + s * TB_STAGE_BYTES;
+          mbar_expect_tx(bFull + 8 * s, TB_STAGE_BYTES);
+          int ac, ar, bc, br;
+          if (MODE == 0) { ac = kb * 64; ar = gt * 128; bc = kb * 64; br = (t_begin + t) * 128; }
+          else { ac = t_begin * 128 + kb * 64; ar = jb * 128; bc = ac; br = gt * 128; }
+          tma_load_2d(st, &tmA1, bFull + 8 * s, ac, ar);
+          tma_load_2d(st + TB_TILE_BYTES, &tmA2, bFull + 8 * s, ac, ar);
+          tma_load_2d(st + 2 * TB_TILE_BYTES, &tmB1, bFull + 8 * s, bc, br);
+          tma_load_2d(st + 3 * TB_TILE_BYTES, &tmB2, bFull + 8 * s, bc, br);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (convergent warp, one elected lane) =====================
+    constexpr uint32_t idesc = make_idesc_bf16(128, 128);
+    int it = 0;
+    for (int t = 0; t < ntile; ++t) {
+      if (t > 0) mbar_wait(bDEmpty, (t - 1) & 1);  // the epilogue has drained the accumulator of the previous tile
+      tc_fence_after();
+      for (int kb = 0; kb < nk; ++kb, ++it) {
+        const int s = it % TB_STAGES;
+        mbar_wait(bFull + 8 * s, (it / TB_STAGES) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t st = base + s * TB_STAGE_BYTES;
+          const uint64_t a1 = make_desc(st), a2 = make_desc(st + TB_TILE_BYTES), b1 = make_desc(st + 2 * TB_TILE_BYTES),
+                         b2 = make_desc(st + 3 * TB_TILE_BYTES);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {  // 4 x K = 16 inside the 64-wide swizzled block: +32 bytes = +2 in descriptor units
+            tc_mma_bf16_ss(tmem, a1 + 2 * ks, b1 + 2 * ks, idesc, (kb | ks) ? 1u : 0u);
+            tc_mma_bf16_ss(tmem, a2 + 2 * ks, b1 + 2 * ks, idesc, 1u);
+            tc_mma_bf16_ss(tmem, a1 + 2 * ks, b2 + 2 * ks, idesc, 1u);
+          }
+          tc_commit(bEmpty + 8 * s);
+          if (kb == nk - 1) tc_commit(bDFull);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===================== epilogue: 4 warps, thread = accumulator row (TMEM lane) =====================
+    const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    const int r = 32 * q + lane;                  // accumulator row
+    const uint32_t trow = tmem + ((uint32_t)(32 * q) << 16);
+    if (MODE == 0) {
+      const int64_t g = (int64_t)gt * 128 + r;
+      const bool live = g < a.G;
+      double sum0 = 0.0, sum1 = 0.0;
+      float lt = 0.f, phi = 0.f;
+      if (LIK == BVG_NB) { lt = (float)a.zeta[a.tail_idx]; phi = __expf(lt); }
+      for (int t = 0; t < ntile; ++t) {
+        mbar_wait(bDFull, t & 1);
+        tc_fence_after();
+        const int64_t spot0 = (int64_t)(t_begin + t) * 128;
+#pragma unroll 1
+        for (int c32 = 0; c32 < 4; ++c32) {
+          float f[32];
+          tmem_ld32(trow + 32 * c32, f);
+          const int64_t s0 = spot0 + 32 * c32;
+          const float4 *py = reinterpret_cast<const float4 *>(a.Y + g * a.ldY + s0);
+          uint32_t p1[16], p2[16];
+          float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+          for (int c4 = 0; c4 < 8; ++c4) {
+            const float4 y4 = live ? __ldg(py + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float yv[4] = {y4.x, y4.y, y4.z, y4.w};
+            float res[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float ff = f[4 * c4 + i];
+              if (LIK == BVG_GAUSSIAN) {
+                res[i] = yv[i] - ff;
+                acc0 = fmaf(res[i], res[i], acc0);
+              } else {  // see k_lik_tc.cu: one ex2 / rcp / lg2 per element
+                const float d = ff - lt;
+                const float ex = ex2_approx(-fabsf(d) * 1.4426950408889634f);
+                const float tt = 1.f + ex;
+                const float rt = rcp_approx(tt);
+                const float Lq = fmaf(lg2_approx(tt), 0.6931471805599453f, fmaxf(d, 0.f));
+                const float sg = (d >= 0.f ? 1.f : ex) * rt;
+                const float yp = yv[i] + phi;
+                res[i] = fmaf(-yp, sg, yv[i]);
+                if (s0 + 4 * c4 + i < a.M) {
+                  acc0 = fmaf(yv[i], d, acc0);
+                  acc0 = fmaf(-yp, Lq, acc0);
+                  acc1 += Lq;
+                }
+              }
+            }
+            split_bf16x2(res[0], res[1], p1[2 * c4], p2[2 * c4]);
+            split_bf16x2(res[2], res[3], p1[2 * c4 + 1], p2[2 * c4 + 1]);
+          }
+          sum0 += (double)acc0;
+          if (LIK == BVG_NB) sum1 += (double)acc1;
+          if (a.write_r) {
+            uint4 *o1 = reinterpret_cast<uint4 *>(a.R1 + g * a.Mpad + s0), *o2 = reinterpret_cast<uint4 *>(a.R2 + g * a.Mpad + s0);
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+              o1[w] = make_uint4(p1[4 * w], p1[4 * w + 1], p1[4 * w + 2], p1[4 * w + 3]);
+              o2[w] = make_uint4(p2[4 * w], p2[4 * w + 1], p2[4 * w + 2], p2[4 * w + 3]);
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(bDEmpty);
+      }
+      const int64_t row = (int64_t)split * a.Gpad + g;
+      a.Spart[row * 2 + 0] = (float)sum0;
+      a.Spart[row * 2 + 1] = (float)sum1;
+    } else {
+      const int j = jb * 128 + r;  // basis index of this row
+      if (ntile > 0) {
+        mbar_wait(bDFull, 0);
+        tc_fence_after();
+      }
+#pragma unroll 1
+      for (int c32 = 0; c32 < 4; ++c32) {
+        float p[32];
+        if (ntile > 0) tmem_ld32(trow + 32 * c32, p);
+        else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) p[i] = 0.f;
+        }
+        if (j < a.KP) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int64_t g = (int64_t)gt * 128 + 32 * c32 + i;
+            a.Ppart[((int64_t)split * a.Gpad + g) * a.KP + j] = j < a.k1 ? p[i] : 0.f;   // lanes = consecutive j: coalesced per gene
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128u) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// operand staging
+// ------------------------------------------------------------------------------------------------
+// Phi (M x k col-major fp64) -> bf16 parts of Phi' = [Phi, 1]:  F*: [Mpad][Kp] (row = spot), T*: [Kp][Mpad] (row = basis)
+__global__ void k_tb_stage_phi(const double *__restrict__ phi, int64_t M, int64_t Mpad, int k, int Kp, __nv_bfloat16 *__restrict__ F1,
+                               __nv_bfloat16 *__restrict__ F2, __nv_bfloat16 *__restrict__ T1, __nv_bfloat16 *__restrict__ T2) {
+  const int64_t n = Mpad * Kp;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t s = i / Kp;
+    const int j = (int)(i - s * Kp);
+    float v = 0.f;
+    if (s < M && j <= k) v = j < k ? (float)phi[(int64_t)j * M + s] : 1.f;
+    const __nv_bfloat16 b1 = __float2bfloat16_rn(v), b2 = __float2bfloat16_rn(v - __bfloat162float(b1));
+    F1[i] = b1; F2[i] = b2;
+    T1[(int64_t)j * Mpad + s] = b1; T2[(int64_t)j * Mpad + s] = b2;
+  }
+}
+// coefficient rows (fp32 [Gpad][KP], written by k_prep_big) -> bf16 parts [Gpad][Kp]
+__global__ void k_tb_split_c(const float *__restrict__ C, int64_t G, int KP, int Kp, __nv_bfloat16 *__restrict__ C1, __nv_bfloat16 *__restrict__ C2) {
+  griddep_wait();
+  griddep_launch();
+  const int64_t n = G * KP;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t g = i / KP;
+    const int j = (int)(i - g * KP);
+    const float v = C[i];
+    const __nv_bfloat16 b1 = __float2bfloat16_rn(v), b2 = __float2bfloat16_rn(v - __bfloat162float(b1));
+    C1[g * Kp + j] = b1; C2[g * Kp + j] = b2;
+  }
+}
+
+int tcbig_setup(bvg_fit *f) {
+  const DevModel &m = f->m;
+  TbState *t = new TbState();
+  memset(t, 0, sizeof(*t));
+  f->tcbig = t;
+  t->Kp = (int)((m.k + 1 + 63) / 64 * 64);
+  t->njb = (m.k + 1 + 127) / 128;
+  const size_t nF = (size_t)f->Mpad * t->Kp, nR = (size_t)m.Gpad * f->Mpad, nC = (size_t)m.Gpad * t->Kp;
+  CUDA_TRY(cudaMalloc(&t->F1, sizeof(__nv_bfloat16) * (4 * nF + 2 * nR + 2 * nC)));
+  t->F2 = t->F1 + nF; t->T1 = t->F2 + nF; t->T2 = t->T1 + nF; t->R1 = t->T2 + nF; t->R2 = t->R1 + nR; t->C1 = t->R2 + nR; t->C2 = t->C1 + nC;
+  CUDA_TRY(cudaMemsetAsync(t->F1, 0, sizeof(__nv_bfloat16) * (4 * nF + 2 * nR + 2 * nC), f->stream));
+  k_tb_stage_phi<<<148 * 4, 256, 0, f->stream>>>(f->phi64, m.M, f->Mpad, m.k, t->Kp, t->F1, t->F2, t->T1, t->T2);
+  CUDA_TRY(cudaGetLastError());
+  // every operand is K-major with 128-byte (64 bf16) swizzled rows; boxes are 128 rows x 64 columns
+  BVG_TRY(tc_make_map(&t->tmC1, t->C1, true, (uint64_t)t->Kp, (uint64_t)m.Gpad, (uint64_t)t->Kp, 128));
+  BVG_TRY(tc_make_map(&t->tmC2, t->C2, true, (uint64_t)t->Kp, (uint64_t)m.Gpad, (uint64_t)t->Kp, 128));
+  BVG_TRY(tc_make_map(&t->tmF1, t->F1, true, (uint64_t)t->Kp, (uint64_t)f->Mpad, (uint64_t)t->Kp, 128));
+  BVG_TRY(tc_make_map(&t->tmF2, t->F2, true, (uint64_t)t->Kp, (uint64_t)f->Mpad, (uint64_t)t->Kp, 128));
+  BVG_TRY(tc_make_map(&t->tmT1, t->T1, true, (uint64_t)f->Mpad, (uint64_t)t->Kp, (uint64_t)f->Mpad, 128));   // rows beyond Kp: zero fill
+  BVG_TRY(tc_make_map(&t->tmT2, t->T2, true, (uint64_t)f->Mpad, (uint64_t)t->Kp, (uint64_t)f->Mpad, 128));
+  BVG_TRY(tc_make_map(&t->tmR1, t->R1, true, (uint64_t)f->Mpad, (uint64_t)m.Gpad, (uint64_t)f->Mpad, 128));
+  BVG_TRY(tc_make_map(&t->tmR2, t->R2, true, (uint64_t)f->Mpad, (uint64_t)m.Gpad, (uint64_t)f->Mpad, 128));
+  CUDA_TRY(cudaFuncSetAttribute(k_tcbig<0, BVG_GAUSSIAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TB_SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(k_tcbig<0, BVG_NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, TB_SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(k_tcbig<1, BVG_GAUSSIAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TB_SMEM_BYTES));
+  return BVG_OK;
+}
+
+void tcbig_destroy(bvg_fit *f) {
+  TbState *t = (TbState *)f->tcbig;
+  if (!t) return;
+  cudaFree(t->F1);
+  delete t;
+  f->tcbig = nullptr;
+}
+
+int launch_lik_tcbig(bvg_fit *f, bool bwd) {
+  const DevModel &m = f->m;
+  TbState *t = (TbState *)f->tcbig;
+  TbArgs a;
+  memset(&a, 0, sizeof(a));
+  a.Y = (const float *)f->Y; a.ldY = f->ldY; a.M = m.M; a.G = m.G; a.Gpad = m.Gpad; a.Mpad = f->Mpad;
+  a.R1 = t->R1; a.R2 = t->R2; a.Spart = (float *)m.Spart; a.Ppart = (float *)m.Ppart; a.KP = m.KP; a.k1 = m.k + 1;
+  a.nkb = t->Kp / 64;
+  a.ntiles_m = (int)(f->Mpad / 128);
+  a.tiles_per_split = (a.ntiles_m + m.nsplit - 1) / m.nsplit;
+  a.zeta = m.zeta; a.tail_idx = m.L.tail;
+  a.write_r = bwd ? 1 : 0;
+  // coefficient rows -> bf16 parts
+  k_tb_split_c<<<148 * 2, 256, 0, f->stream>>>((const float *)m.C, m.G, m.KP, t->Kp, t->C1, t->C2);
+  CUDA_TRY(cudaGetLastError());
+  const dim3 gridF((unsigned)(m.Gpad / 128), (unsigned)m.nsplit, 1), gridB((unsigned)(m.Gpad / 128), (unsigned)m.nsplit, (unsigned)t->njb);
+  if (m.lik == BVG_GAUSSIAN) CUDA_TRY(launch_pdl(k_tcbig<0, BVG_GAUSSIAN>, gridF, dim3(TB_THREADS), (size_t)TB_SMEM_BYTES, f->stream, t->tmC1, t->tmC2, t->tmF1, t->tmF2, a));
+  else CUDA_TRY(launch_pdl(k_tcbig<0, BVG_NB>, gridF, dim3(TB_THREADS), (size_t)TB_SMEM_BYTES, f->stream, t->tmC1, t->tmC2, t->tmF1, t->tmF2, a));
+  f->st.kernel_launches += 2;
+  if (bwd) {
+    CUDA_TRY(launch_pdl(k_tcbig<1, BVG_GAUSSIAN>, gridB, dim3(TB_THREADS), (size_t)TB_SMEM_BYTES, f->stream, t->tmT1, t->tmT2, t->tmR1, t->tmR2, a));
+    f->st.kernel_launches++;
+  }
+  return BVG_OK;
+}

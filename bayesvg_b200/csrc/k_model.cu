@@ -158,7 +158,7 @@ int launch_prep(bvg_fit *f, int mode) {
   const int grid = (int)((f->m.G + gpb - 1) / gpb);
   const size_t sh = sizeof(double) * (3 * k + 5 + gpb * (k + 3));
   if (f->cfg.precision == BVG_PREC_FP64) CUDA_TRY(launch_pdl(k_prep<double>, dim3(grid), dim3(256), sh, f->stream, f->m, mode, 0, gpb));
-  else CUDA_TRY(launch_pdl(k_prep<float>, dim3(grid), dim3(256), sh, f->stream, f->m, mode, (int)(f->engine == BVG_ENGINE_TCGEN05), gpb));
+  else CUDA_TRY(launch_pdl(k_prep<float>, dim3(grid), dim3(256), sh, f->stream, f->m, mode, (int)(f->engine == BVG_ENGINE_TCGEN05 && !f->big_tc), gpb));
   f->st.kernel_launches++;
   return BVG_OK;
 }

@@ -46,7 +46,7 @@ typedef enum {
   BVG_PREC_FAST = 1  /* Y fp32, likelihood contraction fp32 / 3xTF32; parameters stay fp64 */
 } bvg_precision;
 typedef enum {
-  BVG_ENGINE_AUTO = 0,    /* tcgen05 when precision = FAST and k+1 <= 24, else SIMT */
+  BVG_ENGINE_AUTO = 0,    /* tcgen05 when precision = FAST (fused kernel for k+1 <= 24, two-GEMM kernels above), else SIMT */
   BVG_ENGINE_SIMT = 1,    /* CUDA-core kernel (fp64 or fp32) */
   BVG_ENGINE_TCGEN05 = 2  /* TMA + tcgen05/TMEM kernel (FAST only) */
 } bvg_engine;

@@ -67,14 +67,15 @@ def test_log_prob_vs_oracle(lik, prec, eng, M, G, k):
 
 
 @pytest.mark.parametrize("lik", ["gaussian", "nb"])
-@pytest.mark.parametrize("prec", ["fp64", "fast"])
-@pytest.mark.parametrize("M,G,k", [(300, 70, 31), (640, 45, 64), (700, 33, 200), (900, 40, 401)])
-def test_log_prob_large_basis_vs_oracle(lik, prec, M, G, k):
-    """BASELINE config 5 has k ~ 400 basis functions: the general path (k_prep_big / k_lik_gen / k_gene_big)"""
+@pytest.mark.parametrize("prec,eng", [("fp64", "simt"), ("fast", "simt"), ("fast", "auto")])
+@pytest.mark.parametrize("M,G,k", [(300, 70, 31), (640, 45, 64), (700, 33, 200), (900, 40, 401), (1500, 300, 24)])
+def test_log_prob_large_basis_vs_oracle(lik, prec, eng, M, G, k):
+    """BASELINE config 5 has k ~ 400 basis functions: the general path (k_prep_big / k_gene_big with the CUDA-core
+    kernel k_lik_gen or, fast + auto, the two tcgen05 GEMM kernels of k_lik_tcbig.cu)"""
     p = make_problem(M, G, k, lik, seed=M + k)
     o = orc.Oracle(p["phi"], p["y"], lik, nthreads=4)
-    f = _fit(p["phi"], p["y"], lik, prec, "auto")
-    assert f.stats()["engine_used"] == 1
+    f = _fit(p["phi"], p["y"], lik, prec, eng)
+    assert f.stats()["engine_used"] == (2 if eng == "auto" and prec == "fast" else 1)
     rng = np.random.default_rng(6)
     for scale, jac, pro in ((0.0, True, True), (0.2, True, False), (0.5, False, False)):
         th = rng.normal(0, 1, o.D) * scale
