@@ -610,7 +610,16 @@ __global__ void __launch_bounds__(512) k_gene_big(DevModel m, int mode, int jac,
       const double z = datum ? m.depths[g] : zt[li];
       if (j == k + 1) { u = z; continue; }
       double Pj = 0;
-      for (int sp = 0; sp < m.nsplit; ++sp) Pj += (double)Pp[((int64_t)sp * m.Gpad + g) * KP + j];  // fixed order
+      for (int sp0 = 0; sp0 < m.nsplit; sp0 += 8) {  // 8 independent loads per round trip, summed in a fixed order
+        T pv[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int sp = sp0 + q < m.nsplit ? sp0 + q : m.nsplit - 1;
+          pv[q] = Pp[((int64_t)sp * m.Gpad + g) * KP + j];
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) Pj += sp0 + q < m.nsplit ? (double)pv[q] : 0.0;
+      }
       Pj *= inv_s2;
       double gv;
       if (j < k) {
