@@ -430,8 +430,13 @@ __global__ void __launch_bounds__(512) k_finish(DevModel m, int mode, int jac, i
 // k_gene -- instead of three; k_prep then only runs at the start of a batch of steps.
 // tg_next = Philox counter of that next draw (the host mirrors the device counter): the normal of a warp's first
 // gene is generated BEFORE the wait on the likelihood kernel, i.e. while its slower CTAs are still running.
-template <typename T>
-__global__ void __launch_bounds__(BVG_GENE_MAX_THREADS) k_gene(DevModel m, int mode, int jac, int propto, int fuse, int ahead, uint32_t tg_next) {
+// SPEC = 1 is the instantiation the ADVI loop runs (mode = ADVI update, jacobian on, hierarchical intercept): with those
+// three fixed at compile time the kernel fits the 80 registers that 21 warps per CTA allow (warps are allocated in
+// fours, so 21 count as 24) without spilling.
+template <typename T, int SPEC>
+__global__ void __launch_bounds__(BVG_GENE_MAX_THREADS) k_gene(DevModel m, int mode_rt, int jac_rt, int propto, int fuse, int ahead, uint32_t tg_next) {
+  const int mode = SPEC ? (int)MODE_ADVI_UPDATE : mode_rt, jac = SPEC ? 1 : jac_rt;
+  const bool dep = SPEC ? false : m.depth != 0;
   extern __shared__ double sm[];  // [nwarps][NS]
   __shared__ int s_last;
   const int k = m.k, KP = m.KP, NS = bvg_ns(k);
@@ -441,7 +446,7 @@ __global__ void __launch_bounds__(BVG_GENE_MAX_THREADS) k_gene(DevModel m, int m
     const int64_t gg = m.gene_offset + g;
     return (uint64_t)(lane < k ? m.LG.z_alpha + gg * k + lane : (lane == k ? m.LG.z_beta0 + gg : m.LG.amp + gg));
   };
-  const bool has = lane < k + 2 && !(m.depth && lane == k);  // depth-adjusted programs have no z_beta0: lane k carries gene_depths[g]
+  const bool has = lane < k + 2 && !(dep && lane == k);  // depth-adjusted programs have no z_beta0: lane k carries gene_depths[g]
   double eps_first = 0.0;
   if (ahead && has && gfirst < m.G) eps_first = bvg_normal(m.seed, STREAM_GRAD, tg_next, global_index(gfirst));
   griddep_wait();    // Ppart / Spart come from the likelihood kernel
@@ -460,7 +465,7 @@ __global__ void __launch_bounds__(BVG_GENE_MAX_THREADS) k_gene(DevModel m, int m
   const T *Pp = (const T *)m.Ppart, *Sp = (const T *)m.Spart;
   for (int64_t g = (int64_t)blockIdx.x * nw + warp; g < m.G; g += (int64_t)gridDim.x * nw) {
     const int64_t li = lane < k ? L.z_alpha + g * k + lane : (lane == k ? L.z_beta0 + g : L.amp + g);
-    const double zi = has ? zt[li] : ((m.depth && lane == k) ? m.depths[g] : 0.0);  // this lane's own parameter value
+    const double zi = has ? zt[li] : ((dep && lane == k) ? m.depths[g] : 0.0);  // this lane's own parameter value
     const double Aexp_g = m.Aexp[g];
     double mu_i = 0, om_i = 0, hm = 0, ho = 0;
     if (upd && has) { mu_i = m.mu[li]; om_i = m.omega[li]; hm = m.hist[li]; ho = m.hist[L.D + li]; }
@@ -492,7 +497,7 @@ __global__ void __launch_bounds__(BVG_GENE_MAX_THREADS) k_gene(DevModel m, int m
     const double zb = __shfl_sync(0xffffffffu, zi, k), u = __shfl_sync(0xffffffffu, zi, k + 1);
     const double A = Aexp_g, alpha = mual + sal * zj;
     const double aP = warp_sum(lane < k ? alpha * Pj : 0.0);
-    const double z2 = warp_sum(zj * zj) + (m.depth ? 0.0 : zb * zb);
+    const double z2 = warp_sum(zj * zj) + (dep ? 0.0 : zb * zb);
     const double AP = lane < k ? A * Pj : 0.0;
     const double du = u - ma;
     aAP += AP; aAPz += AP * zj;
@@ -712,8 +717,14 @@ int launch_gene_finish(bvg_fit *f, int mode, int jac, int propto, int ahead) {
     if (mode == MODE_ADVI_UPDATE) f->h_t_grad++;
     return BVG_OK;
   }
-  if (f->cfg.precision == BVG_PREC_FP64) CUDA_TRY(launch_pdl(k_gene<double>, dim3(f->m.nblk_gene), dim3(wpb * 32), sh, f->stream, f->m, mode, jac, propto, fuse, ahead, tg_next));
-  else CUDA_TRY(launch_pdl(k_gene<float>, dim3(f->m.nblk_gene), dim3(wpb * 32), sh, f->stream, f->m, mode, jac, propto, fuse, ahead, tg_next));
+  const bool spec = mode == MODE_ADVI_UPDATE && jac == 1 && !f->m.depth;
+  if (f->cfg.precision == BVG_PREC_FP64) {
+    if (spec) CUDA_TRY(launch_pdl(k_gene<double, 1>, dim3(f->m.nblk_gene), dim3(wpb * 32), sh, f->stream, f->m, mode, jac, propto, fuse, ahead, tg_next));
+    else CUDA_TRY(launch_pdl(k_gene<double, 0>, dim3(f->m.nblk_gene), dim3(wpb * 32), sh, f->stream, f->m, mode, jac, propto, fuse, ahead, tg_next));
+  } else {
+    if (spec) CUDA_TRY(launch_pdl(k_gene<float, 1>, dim3(f->m.nblk_gene), dim3(wpb * 32), sh, f->stream, f->m, mode, jac, propto, fuse, ahead, tg_next));
+    else CUDA_TRY(launch_pdl(k_gene<float, 0>, dim3(f->m.nblk_gene), dim3(wpb * 32), sh, f->stream, f->m, mode, jac, propto, fuse, ahead, tg_next));
+  }
   f->st.kernel_launches++;
   if (fuse == 1) {
     if (!(f->m.elbo_local && mode == MODE_ELBO_DRAW)) BVG_TRY(comm_allreduce(f, f->m.tot, bvg_ns(f->m.k)));
