@@ -15,7 +15,7 @@
 #include "bvg_internal.cuh"
 #include "tc_ptx.cuh"
 
-#define TB_THREADS 192
+#define TB_THREADS 320   // warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2-9 epilogue (two per TMEM lane quarter)
 #define TB_STAGES 3
 #define TB_TILE_BYTES (128 * 128)                 // 128 rows x 64 bf16 (one 128-byte swizzled row per operand row)
 #define TB_STAGE_BYTES (4 * TB_TILE_BYTES)        // A1 | A2 | B1 | B2
@@ -54,12 +54,16 @@ k_tcbig(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtens
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sBar = base + TB_STAGES * TB_STAGE_BYTES;
-  const uint32_t bFull = sBar, bEmpty = bFull + 8 * TB_STAGES, bDFull = bEmpty + 8 * TB_STAGES, bDEmpty = bDFull + 8, sTmem = bDEmpty + 8;
+  const uint32_t bFull = sBar, bEmpty = bFull + 8 * TB_STAGES, bDFull = bEmpty + 8 * TB_STAGES, bDEmpty = bDFull + 16, sTmem = bDEmpty + 16;
+  __shared__ double s_half[2][128];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // work decomposition
   //   forward : blockIdx.x = gene tile, blockIdx.y = split; tiles = spot tiles of the split; K loop = nkb basis blocks
-  //   backward: blockIdx.x = gene tile, blockIdx.y = split, blockIdx.z = basis block; one tile; K loop = spot blocks of the split
-  const int gt = blockIdx.x, split = blockIdx.y, jb = MODE == 1 ? blockIdx.z : 0;
+  //   backward: blockIdx.x = basis block, blockIdx.y = gene tile, blockIdx.z = split; one tile; K loop = spot blocks of the
+  //             split.  Basis blocks vary fastest so that the CTAs sharing an R tile (same gene tile and split) and the
+  //             CTAs sharing a Phi'^T slice (same split) run in the same wave and hit L2: with splits fastest every
+  //             basis block re-read R from HBM and the kernel sat on the HBM roofline (4 GB per launch, 628 us).
+  const int gt = MODE == 1 ? blockIdx.y : blockIdx.x, split = MODE == 1 ? blockIdx.z : blockIdx.y, jb = MODE == 1 ? blockIdx.x : 0;
   const int t_begin = split * a.tiles_per_split;
   int nt = a.ntiles_m - t_begin;
   nt = nt < a.tiles_per_split ? nt : a.tiles_per_split;
@@ -70,12 +74,11 @@ k_tcbig(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtens
   griddep_launch();
   if (threadIdx.x == 0) {
     for (int s = 0; s < TB_STAGES; ++s) { mbar_init(bFull + 8 * s, 1); mbar_init(bEmpty + 8 * s, 1); }
-    mbar_init(bDFull, 1);
-    mbar_init(bDEmpty, 128);
+    for (int b = 0; b < 2; ++b) { mbar_init(bDFull + 8 * b, 1); mbar_init(bDEmpty + 8 * b, 256); }  // two TMEM accumulators
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sTmem), "r"(128u) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sTmem), "r"(256u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -110,8 +113,10 @@ k_tcbig(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtens
     constexpr uint32_t idesc = make_idesc_bf16(128, 128);
     int it = 0;
     for (int t = 0; t < ntile; ++t) {
-      if (t > 0) mbar_wait(bDEmpty, (t - 1) & 1);  // the epilogue has drained the accumulator of the previous tile
+      const int b = t & 1;  // accumulator buffer: the epilogue of tile t - 1 overlaps this tile's main loop
+      if (t >= 2) mbar_wait(bDEmpty + 8 * b, ((t >> 1) - 1) & 1);  // the epilogue has drained this buffer (tile t - 2)
       tc_fence_after();
+      const uint32_t dacc = tmem + 128 * b;
       for (int kb = 0; kb < nk; ++kb, ++it) {
         const int s = it % TB_STAGES;
         mbar_wait(bFull + 8 * s, (it / TB_STAGES) & 1);
@@ -122,43 +127,58 @@ k_tcbig(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtens
                          b2 = make_desc(st + 3 * TB_TILE_BYTES);
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {  // 4 x K = 16 inside the 64-wide swizzled block: +32 bytes = +2 in descriptor units
-            tc_mma_bf16_ss(tmem, a1 + 2 * ks, b1 + 2 * ks, idesc, (kb | ks) ? 1u : 0u);
-            tc_mma_bf16_ss(tmem, a2 + 2 * ks, b1 + 2 * ks, idesc, 1u);
-            tc_mma_bf16_ss(tmem, a1 + 2 * ks, b2 + 2 * ks, idesc, 1u);
+            tc_mma_bf16_ss(dacc, a1 + 2 * ks, b1 + 2 * ks, idesc, (kb | ks) ? 1u : 0u);
+            tc_mma_bf16_ss(dacc, a2 + 2 * ks, b1 + 2 * ks, idesc, 1u);
+            tc_mma_bf16_ss(dacc, a1 + 2 * ks, b2 + 2 * ks, idesc, 1u);
           }
           tc_commit(bEmpty + 8 * s);
-          if (kb == nk - 1) tc_commit(bDFull);
+          if (kb == nk - 1) tc_commit(bDFull + 8 * b);
         }
         __syncwarp();
       }
     }
   } else {
-    // ===================== epilogue: 4 warps, thread = accumulator row (TMEM lane) =====================
-    const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    // ===================== epilogue: 8 warps; thread = accumulator row (TMEM lane) x one 64-column half ================
+    const int q = warp & 3, h = (warp - 2) >> 2;  // TMEM lane quarter this warp may access, column half
     const int r = 32 * q + lane;                  // accumulator row
-    const uint32_t trow = tmem + ((uint32_t)(32 * q) << 16);
+    const uint32_t trow = tmem + ((uint32_t)(32 * q) << 16) + 64 * h;
     if (MODE == 0) {
       const int64_t g = (int64_t)gt * 128 + r;
       const bool live = g < a.G;
       double sum0 = 0.0, sum1 = 0.0;
       float lt = 0.f, phi = 0.f;
       if (LIK == BVG_NB) { lt = (float)a.zeta[a.tail_idx]; phi = __expf(lt); }
+      const float *yrow = a.Y + g * a.ldY + 64 * h;
+      if (live && ntile > 0) {  // this thread's 256 bytes of the first tile into L2
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(yrow + (int64_t)t_begin * 128));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(yrow + (int64_t)t_begin * 128 + 32));
+      }
       for (int t = 0; t < ntile; ++t) {
-        mbar_wait(bDFull, t & 1);
+        const int b = t & 1;
+        const int64_t spot0 = (int64_t)(t_begin + t) * 128 + 64 * h;
+        // y for both 32-spot chunks of this tile is requested before the accumulator is waited for, and the next
+        // tile's rows are pulled into L2: the HBM latency of Y hides under the main loop of the other accumulator
+        float4 y4[16];
+        const float4 *py = reinterpret_cast<const float4 *>(yrow + (int64_t)(t_begin + t) * 128);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) y4[i] = live ? __ldg(py + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (live && t + 1 < ntile) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(yrow + (int64_t)(t_begin + t + 1) * 128));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(yrow + (int64_t)(t_begin + t + 1) * 128 + 32));
+        }
+        mbar_wait(bDFull + 8 * b, (t >> 1) & 1);
         tc_fence_after();
-        const int64_t spot0 = (int64_t)(t_begin + t) * 128;
-#pragma unroll 1
-        for (int c32 = 0; c32 < 4; ++c32) {
+#pragma unroll
+        for (int c32 = 0; c32 < 2; ++c32) {
           float f[32];
-          tmem_ld32(trow + 32 * c32, f);
+          tmem_ld32(trow + 128 * b + 32 * c32, f);
           const int64_t s0 = spot0 + 32 * c32;
-          const float4 *py = reinterpret_cast<const float4 *>(a.Y + g * a.ldY + s0);
           uint32_t p1[16], p2[16];
           float acc0 = 0.f, acc1 = 0.f;
 #pragma unroll
           for (int c4 = 0; c4 < 8; ++c4) {
-            const float4 y4 = live ? __ldg(py + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
-            const float yv[4] = {y4.x, y4.y, y4.z, y4.w};
+            const float4 yq = y4[8 * c32 + c4];
+            const float yv[4] = {yq.x, yq.y, yq.z, yq.w};
             float res[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -197,11 +217,15 @@ k_tcbig(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtens
           }
         }
         tc_fence_before();
-        mbar_arrive(bDEmpty);
+        mbar_arrive(bDEmpty + 8 * b);
       }
-      const int64_t row = (int64_t)split * a.Gpad + g;
-      a.Spart[row * 2 + 0] = (float)sum0;
-      a.Spart[row * 2 + 1] = (float)sum1;
+      if (h == 1) { s_half[0][r] = sum0; s_half[1][r] = sum1; }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (h == 0) {
+        const int64_t row = (int64_t)split * a.Gpad + g;
+        a.Spart[row * 2 + 0] = (float)(sum0 + s_half[0][r]);
+        a.Spart[row * 2 + 1] = (float)(sum1 + s_half[1][r]);
+      }
     } else {
       const int j = jb * 128 + r;  // basis index of this row
       if (ntile > 0) {
@@ -209,7 +233,7 @@ k_tcbig(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtens
         tc_fence_after();
       }
 #pragma unroll 1
-      for (int c32 = 0; c32 < 4; ++c32) {
+      for (int c32 = 0; c32 < 2; ++c32) {
         float p[32];
         if (ntile > 0) tmem_ld32(trow + 32 * c32, p);
         else {
@@ -219,7 +243,7 @@ k_tcbig(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtens
         if (j < a.KP) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            const int64_t g = (int64_t)gt * 128 + 32 * c32 + i;
+            const int64_t g = (int64_t)gt * 128 + 64 * h + 32 * c32 + i;
             a.Ppart[((int64_t)split * a.Gpad + g) * a.KP + j] = j < a.k1 ? p[i] : 0.f;   // lanes = consecutive j: coalesced per gene
           }
         }
@@ -230,7 +254,7 @@ k_tcbig(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtens
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u) : "memory");
   }
 }
 
@@ -316,7 +340,7 @@ int launch_lik_tcbig(bvg_fit *f, bool bwd) {
   // coefficient rows -> bf16 parts
   k_tb_split_c<<<148 * 2, 256, 0, f->stream>>>((const float *)m.C, m.G, m.KP, t->Kp, t->C1, t->C2);
   CUDA_TRY(cudaGetLastError());
-  const dim3 gridF((unsigned)(m.Gpad / 128), (unsigned)m.nsplit, 1), gridB((unsigned)(m.Gpad / 128), (unsigned)m.nsplit, (unsigned)t->njb);
+  const dim3 gridF((unsigned)(m.Gpad / 128), (unsigned)m.nsplit, 1), gridB((unsigned)t->njb, (unsigned)(m.Gpad / 128), (unsigned)m.nsplit);
   if (m.lik == BVG_GAUSSIAN) CUDA_TRY(launch_pdl(k_tcbig<0, BVG_GAUSSIAN>, gridF, dim3(TB_THREADS), (size_t)TB_SMEM_BYTES, f->stream, t->tmC1, t->tmC2, t->tmF1, t->tmF2, a));
   else CUDA_TRY(launch_pdl(k_tcbig<0, BVG_NB>, gridF, dim3(TB_THREADS), (size_t)TB_SMEM_BYTES, f->stream, t->tmC1, t->tmC2, t->tmF1, t->tmF2, a));
   f->st.kernel_launches += 2;
