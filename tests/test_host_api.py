@@ -95,3 +95,54 @@ def test_gene_sharding_helpers():
             seen[idx] += 1
         sm = dist.shared_mask(lik, G, k)
         assert sm.sum() == 2 * k + 5 and np.all(seen[sm] == 3) and np.all(seen[~sm] == 1)
+
+
+def test_depth_adjusted_layout_and_sharding_helpers():
+    """inst/approxGP2.stan:13-23 / approxGP3.stan:13-23: beta0, beta1, tail, amplitude[G], mu_amplitude, sigma_amplitude,
+    mu_alpha[k], sigma_alpha[k], z_alpha_t[k,G] -- no z_beta0, D = 5 + G + 2k + kG"""
+    G, k = 9, 4
+    for lik in ("gaussian", "nb"):
+        L = dist.layout(lik, G, k, depth=True)
+        assert L["D"] == 5 + G + 2 * k + k * G and "z_beta0" not in L
+        assert (L["mu_beta0"], L["sigma_beta0"], L["tail"], L["amplitude"]) == (0, 1, 2, 3)
+        assert L["z_alpha_t"] + k * G == L["D"]
+        seen = np.zeros(L["D"], dtype=int)
+        for g0, g1 in dist.gene_ranges(G, 2):
+            idx = dist.shard_index(lik, G, k, g0, g1, depth=True)
+            LL = dist.layout(lik, g1 - g0, k, depth=True)
+            assert idx.shape == (LL["D"],) and len(set(idx)) == LL["D"]
+            assert idx[LL["amplitude"]] == L["amplitude"] + g0 and idx[LL["z_alpha_t"]] == L["z_alpha_t"] + k * g0
+            seen[idx] += 1
+        sm = dist.shared_mask(lik, G, k, depth=True)
+        assert sm.sum() == 2 * k + 5 and np.all(seen[sm] == 2) and np.all(seen[~sm] == 1)
+
+
+def test_gene_depths_reach_the_fit_only_with_depth_adjust(monkeypatch):
+    """gene.depth.adjust = TRUE: gene_depths = log(rowSums(counts[naive.hvgs, ])) (:293-303) is what the host passes down"""
+    import bayesvg_b200.api as api
+    o = _obj(G=6, M=40, seed=3)
+    seen = {}
+
+    class FakeFit:
+        def __init__(self, phi, Y, lik, prec, eng, gene_depths=None, **cfg):
+            seen["depths"], seen["shape"] = gene_depths, Y.shape
+
+        def run(self):
+            t = np.ones((seen["shape"][1], 8))
+            t[:, 0] = np.arange(seen["shape"][1], 0, -1)
+            return t
+
+        def stats(self):
+            return dict(eta=0.1, advi_iters=1, elbo=0.0)
+
+        def close(self):
+            pass
+
+    monkeypatch.setattr(api.E, "Fit", FakeFit)
+    monkeypatch.setattr(api.E, "basis_build", lambda X, C, ls, *a: np.linalg.qr(np.random.default_rng(0).normal(size=(X.shape[0], C.shape[0])))[0])
+    genes = ["gene2", "gene5", "gene1"]
+    api.findSpatiallyVariableFeaturesBayes(o, genes, n_basis_fns=3, gene_depth_adjust=True, verbose=False)
+    rows = [list(o.genes).index(g) for g in genes]
+    assert np.allclose(seen["depths"], np.log(np.asarray(o.counts)[rows].sum(1)))
+    api.findSpatiallyVariableFeaturesBayes(o, genes, n_basis_fns=3, verbose=False)
+    assert seen["depths"] is None

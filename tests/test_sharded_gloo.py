@@ -58,6 +58,8 @@ def _worker(rank, world, port, lik, q):
         # plumbing: byte broadcast (the NCCL unique id travels this way)
         blob = bytes(range(128)) if rank == 0 else b""
         assert dist._bcast_bytes(blob) == bytes(range(128))
+        # ... and the CUDA-IPC handles of the peer-memory exchange are all-gathered in rank order
+        assert dist._allgather_bytes(bytes([rank] * 64)) == bytes([0] * 64 + [1] * 64)
         g0, g1 = dist.Shard(rank, world).gene_range(G)
         idx = dist.shard_index(lik, G, k, g0, g1)
         o = orc.Oracle(p["phi"], p["y"][:, g0:g1], lik)
