@@ -202,7 +202,7 @@ static int finalize_model(bvg_fit *f) {
   // one gene per warp, at most one CTA per SM: 16 warps per CTA, or 21 when that lets every gene be served in a
   // single pass (a warp that owns two genes runs two dependent latency chains back to back)
   f->gene_wpb = (m.G > (int64_t)16 * nsm && m.G <= (int64_t)(BVG_GENE_MAX_THREADS / 32) * nsm) ? BVG_GENE_MAX_THREADS / 32 : 16;
-  if (m.k > BVG_SMALL_K) f->gene_wpb = 8;  // k_gene_big
+  if (m.k > BVG_SMALL_K) f->gene_wpb = 16;  // k_gene_big
   m.nblk_gene = (int)std::min<int64_t>((m.G + f->gene_wpb - 1) / f->gene_wpb, nsm);
   f->h_t_grad = 0;
   const int NS = bvg_ns(m.k);

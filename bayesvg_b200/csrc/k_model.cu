@@ -221,32 +221,28 @@ __device__ void finish_body(const DevModel &m, int mode, int jac, int propto, in
     // 5 per lane), then sums in a fixed order and finishes with a fixed shuffle tree -> deterministic
     const int warp_r = warp - w0, nwr = nwarps - w0;
     if (warp >= w0) {
-      double acc[4] = {0, 0, 0, 0};
-      for (int b0 = lane; b0 < m.nblk_gene; b0 += 160) {
-        double v[4][5];
+      for (int cbase = 0; cbase < NS; cbase += 4 * nwr) {  // one pass when 2k+10 <= 4 * reducing warps (k <= 27 with 16 warps)
+        double acc[4] = {0, 0, 0, 0};
+        for (int b0 = lane; b0 < m.nblk_gene; b0 += 160) {
+          double v[4][5];
 #pragma unroll
-        for (int ci = 0; ci < 4; ++ci)
+          for (int ci = 0; ci < 4; ++ci)
 #pragma unroll
-          for (int q = 0; q < 5; ++q) {
-            const int c = warp_r + ci * nwr, b = b0 + 32 * q;
-            v[ci][q] = (c < NS && b < m.nblk_gene) ? __ldcg(&m.blk[(int64_t)c * m.nblk_gene + b]) : 0.0;
-          }
+            for (int q = 0; q < 5; ++q) {
+              const int c = cbase + warp_r + ci * nwr, b = b0 + 32 * q;
+              v[ci][q] = (c < NS && b < m.nblk_gene) ? __ldcg(&m.blk[(int64_t)c * m.nblk_gene + b]) : 0.0;
+            }
 #pragma unroll
-        for (int ci = 0; ci < 4; ++ci)
+          for (int ci = 0; ci < 4; ++ci)
 #pragma unroll
-          for (int q = 0; q < 5; ++q) acc[ci] += v[ci][q];
-      }
+            for (int q = 0; q < 5; ++q) acc[ci] += v[ci][q];
+        }
 #pragma unroll
-      for (int ci = 0; ci < 4; ++ci) {
-        const int c = warp_r + ci * nwr;
-        const double t = warp_sum(acc[ci]);
-        if (lane == 0 && c < NS) m.tot[c] = t;
-      }
-      for (int c = warp_r + 4 * nwr; c < NS; c += nwr) {  // only when NS > 4 * reducing warps
-        double s2 = 0;
-        for (int b = lane; b < m.nblk_gene; b += 32) s2 += __ldcg(&m.blk[(int64_t)c * m.nblk_gene + b]);
-        s2 = warp_sum(s2);
-        if (lane == 0) m.tot[c] = s2;
+        for (int ci = 0; ci < 4; ++ci) {
+          const int c = cbase + warp_r + ci * nwr;
+          const double t = warp_sum(acc[ci]);
+          if (lane == 0 && c < NS) m.tot[c] = t;
+        }
       }
     }
     __syncthreads();
@@ -694,15 +690,15 @@ int launch_gene_finish(bvg_fit *f, int mode, int jac, int propto, int ahead) {
   const int fuse = g_gene_fuse_override >= 0 ? g_gene_fuse_override : (split ? 1 : 3);
   const uint32_t tg_next = f->h_t_grad + 1;
   if (f->m.k > BVG_SMALL_K) {
-    // large basis: 8 gene-warps per CTA keep the [warps][2k+10] shared-memory rows small; no draw-ahead
-    const int wb = 8;
+    // large basis: 16 gene-warps per CTA ([warps][2k+10] shared-memory rows: 104 KB at k = 400); no draw-ahead
+    const int wb = 16;
     const size_t shb = sizeof(double) * wb * bvg_ns(f->m.k);
     const bool splitb = f->comm_mode != 0;  // 2k+10 sums exceed one CTA's exchange width: reduce, all-reduce, finish
     const int fuseb = g_gene_fuse_override >= 0 ? g_gene_fuse_override : (splitb ? 1 : 3);
     static bool attr_set = false;
     if (!attr_set) {
-      CUDA_TRY(cudaFuncSetAttribute(k_gene_big<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-      CUDA_TRY(cudaFuncSetAttribute(k_gene_big<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      CUDA_TRY(cudaFuncSetAttribute(k_gene_big<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+      CUDA_TRY(cudaFuncSetAttribute(k_gene_big<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
       attr_set = true;
     }
     if (f->cfg.precision == BVG_PREC_FP64) CUDA_TRY(launch_pdl(k_gene_big<double>, dim3(f->m.nblk_gene), dim3(wb * 32), shb, f->stream, f->m, mode, jac, propto, fuseb));
