@@ -21,7 +21,7 @@ EXPORTS = [
     "bvg_fit_dim", "bvg_fit_set_gene_depths", "bvg_comm_unique_id", "bvg_fit_comm_init", "bvg_fit_peer_handle", "bvg_fit_peer_init", "bvg_log_prob", "bvg_fit_run", "bvg_fit_mle",
     "bvg_fit_advi", "bvg_fit_summarize", "bvg_fit_set_variational", "bvg_fit_get_variational",
     "bvg_fit_advi_steps", "bvg_fit_elbo", "bvg_fit_time_lik_kernel", "bvg_fit_flush_l2", "bvg_fit_get_summary",
-    "bvg_fit_get_draws", "bvg_fit_get_trace", "bvg_fit_get_stats", "bvg_debug_stage_times", "bvg_debug_gene_trace", "bvg_debug_time_gene",
+    "bvg_fit_get_draws", "bvg_fit_posterior_ncol", "bvg_fit_get_posterior", "bvg_fit_get_trace", "bvg_fit_get_stats", "bvg_debug_stage_times", "bvg_debug_gene_trace", "bvg_debug_time_gene",
     "bvg_debug_tc_trace",
 ]
 
@@ -102,6 +102,8 @@ def lib():
     L.bvg_debug_gene_trace.argtypes = [_vp, C.POINTER(C.c_longlong), C.c_int]
     L.bvg_fit_get_summary.argtypes = [_vp, _dp]
     L.bvg_fit_get_draws.argtypes = [_vp, _dp]
+    L.bvg_fit_posterior_ncol.argtypes = [_vp, C.POINTER(C.c_int64)]
+    L.bvg_fit_get_posterior.argtypes = [_vp, C.c_int, _dp]
     L.bvg_fit_get_trace.argtypes = [_vp, _dp, C.c_int, C.POINTER(C.c_int)]
     L.bvg_fit_get_stats.argtypes = [_vp, C.POINTER(Stats)]
     if L.bvg_version() != ABI_VERSION:

@@ -40,6 +40,107 @@ class SpatialData:
         return self.genes
 
 
+class VariationalFit:
+    """What `save.model = TRUE` keeps (:483-489) and `extractModel()` returns: the stand-in for cmdstanr's CmdStanVB
+    object.  It holds the n.draws x ncol draws matrix of the whole model (the content of CmdStan's variational output
+    CSV: lp__, log_p__, log_g__, parameters constrained in declaration order, transformed parameters) plus the
+    variational mean / log-sd, the ELBO trace and the run statistics, and mirrors the CmdStanVB methods the
+    reference and its users call: `$draws(variables)`, `$summary(variables)`, `$lp()`, `$lp_approx()`,
+    `$num_draws()`, `$save_output_files()` (here `save_csv`)."""
+
+    def __init__(self, columns, draws, mu=None, omega=None, trace=None, stats=None, **extra):
+        draws = np.asarray(draws)
+        if draws.ndim != 2 or draws.shape[1] != len(columns):
+            raise ValueError("draws must be n.draws x length(columns)")
+        self.columns = list(columns)
+        self._draws = draws
+        self._index = {c: i for i, c in enumerate(self.columns)}
+        self.mu, self.omega, self.trace, self.stats = mu, omega, trace, stats
+        self.extra = extra
+
+    def _select(self, variables):
+        if variables is None:
+            return list(range(len(self.columns)))
+        if isinstance(variables, str):
+            variables = [variables]
+        idx = []
+        for v in variables:
+            if v in self._index:               # a scalar or one element: "sigma_y", "amplitude[3]"
+                idx.append(self._index[v])
+                continue
+            hit = [i for i, c in enumerate(self.columns) if c.startswith(v + "[")]   # a whole container: "amplitude"
+            if not hit:
+                raise KeyError(f"Can't find the following variable(s) in the output: {v}")
+            idx.extend(hit)
+        return idx
+
+    def num_draws(self):
+        return self._draws.shape[0]
+
+    def mean_row(self):
+        """The first data row of CmdStan's variational CSV: the mean of the approximation, constrained, with
+        lp__ = log_p__ = log_g__ = 0 [U] -- what cmdstanr drops before building `$draws()`."""
+        if self.mu is None:
+            return None
+        D = len(self.mu)
+        names = self.columns[3:3 + D]
+        pos = np.array([n.startswith(("sigma_", "amplitude[")) or n == "phi_nb" for n in names])
+        th = np.where(pos, np.exp(self.mu), self.mu)
+        val = dict(zip(names, th))
+        tp = []
+        for c in self.columns[3 + D:]:
+            g = c[c.index("[") + 1:-1]
+            tp.append(val["mu_beta0"] + val["sigma_beta0"] * val[f"z_beta0[{g}]"] if c.startswith("beta0[")
+                      else val[f"amplitude[{g}]"] ** 2)
+        return np.concatenate([np.zeros(3), th, np.array(tp)])
+
+    def draws(self, variables=None):
+        """`fit$draws(variables, format = "draws_df")`: a DataFrame, one row per draw."""
+        idx = self._select(variables)
+        return pd.DataFrame(self._draws[:, idx], columns=[self.columns[i] for i in idx])
+
+    def lp(self):
+        """`fit$lp()`: log_p__, the log density of the model at each draw (jacobian = TRUE, all constants)."""
+        return self._draws[:, self._index["log_p__"]].copy()
+
+    def lp_approx(self):
+        """`fit$lp_approx()`: log_g__, the log density of the approximation at each draw up to a constant."""
+        return self._draws[:, self._index["log_g__"]].copy()
+
+    def summary(self, variables=None):
+        """`fit$summary(variables)` for a variational fit = posterior::default_summary_measures() [U]:
+        mean, median, sd, mad (constant 1.4826), q5, q95 with R's type-7 quantiles (:419)."""
+        idx = self._select(variables)
+        x = self._draws[:, idx]
+        med = np.median(x, axis=0)
+        out = pd.DataFrame({
+            "variable": [self.columns[i] for i in idx],
+            "mean": x.mean(0), "median": med, "sd": x.std(0, ddof=1) if x.shape[0] > 1 else np.full(len(idx), np.nan),
+            "mad": 1.4826 * np.median(np.abs(x - med), axis=0),
+            "q5": np.quantile(x, 0.05, axis=0), "q95": np.quantile(x, 0.95, axis=0)})
+        return out
+
+    def save_csv(self, path):
+        """CmdStan's variational output CSV: the header, then the mean of the approximation as the first row
+        (lp__ = log_p__ = log_g__ = 0) [U], then the draws."""
+        with open(path, "w") as fh:
+            fh.write("# method = variational (bayesvg_b200)\n")
+            # CmdStan writes container elements as name.i.j; cmdstanr turns them into name[i,j] when it reads the file
+            fh.write(",".join(c.replace("[", ".").replace(",", ".").replace("]", "") for c in self.columns) + "\n")
+            if self.mu is not None:
+                fh.write(",".join(repr(float(v)) for v in self.mean_row()) + "\n")
+            for row in self._draws:
+                fh.write(",".join(repr(float(v)) for v in row) + "\n")
+        return path
+
+
+def extractModel(obj=None):
+    """R/extractModel.R:18-27."""
+    if obj is None:
+        _abort("Argument obj must be non-NULL.")
+    return obj.misc.get("model_fit")
+
+
 def scale_coords(coords):
     """coop::scaler: column z-score, sd with n-1 (:160)."""
     X = np.asarray(coords, dtype=np.float64)[:, :2]
@@ -173,8 +274,8 @@ def findSpatiallyVariableFeaturesBayes(sp_obj=None, naive_hvgs=None, likelihood=
         model = None
         if save_model:
             mu, om = fit.get_variational()
-            model = dict(mu=mu, omega=om, trace=fit.trace(), stats=fit.stats(), draws=fit.draws(), phi=phi,
-                         lscale=lscale, centers=centers)
+            model = VariationalFit(fit.posterior_columns(), fit.posterior(int(n_draws)), mu=mu, omega=om, trace=fit.trace(),
+                                   stats=fit.stats(), phi=phi, lscale=lscale, centers=centers, genes=list(naive_hvgs))
         stats = fit.stats()
         fit.close()
         if verbose:

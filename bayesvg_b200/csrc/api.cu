@@ -400,7 +400,7 @@ int launch_lik(bvg_fit *f, bool backward) {
 }
 // zeta already holds the point (or is drawn by prep when mode is a draw mode)
 int eval_log_prob_device(bvg_fit *f, int mode, int jac, int propto, bool backward) {
-  const int prep = mode == MODE_ADVI_UPDATE ? PREP_GRAD : (mode == MODE_ELBO_DRAW ? PREP_ELBO : PREP_NONE);
+  const int prep = mode == MODE_ADVI_UPDATE ? PREP_GRAD : (mode == MODE_ELBO_DRAW ? PREP_ELBO : (mode == MODE_POST_DRAW ? PREP_DRAW : PREP_NONE));
   BVG_TRY(launch_prep(f, prep));
   BVG_TRY(launch_lik(f, backward));
   BVG_TRY(launch_gene_finish(f, mode, jac, propto));
@@ -863,6 +863,92 @@ extern "C" int bvg_fit_get_draws(bvg_fit *f, double *out) {
   CUDA_TRY(cudaStreamSynchronize(f->stream));
   return BVG_OK;
 }
+// ---- full posterior draws (the content of CmdStan's variational output CSV / cmdstanr's $draws()) -----------------
+// columns: lp__ (0) | log_p__ | log_g__ | the D parameters CONSTRAINED, Stan declaration order | beta0[G] (hierarchical
+// intercept only) | amplitude_sq[G]                                     (approxGP.stan:25-28; SURVEY.md A.4 "output")
+static int64_t posterior_ncol(const bvg_fit *f) { return 3 + f->m.L.D + (f->m.depth ? 1 : 2) * f->m.G; }
+extern "C" int bvg_fit_posterior_ncol(bvg_fit *f, int64_t *ncol) {
+  BVG_TRY(need_ready(f, false));
+  if (!ncol) { bvg_set_error("null argument"); return BVG_ERR_ARG; }
+  *ncol = posterior_ncol(f);
+  return BVG_OK;
+}
+// one draw: constrain zeta into column-major out[col][d]; per-block partial sums of eps^2 for log_g__
+__global__ void __launch_bounds__(256) k_store_draw(DevModel m, int64_t n, int64_t d, double *__restrict__ out, double *__restrict__ part) {
+  __shared__ double red[8];
+  const Layout &L = m.L;
+  const int64_t D = L.D, G = m.G, ntp = (m.depth ? 1 : 2) * G;
+  double acc = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < D + ntp; i += (int64_t)gridDim.x * blockDim.x) {
+    double v;
+    if (i < D) {
+      const double z = m.zeta[i];
+      const bool pos = (!m.depth && i == L.sigma_beta0) || i == L.sigma_amp || (i >= L.amp && i < L.amp + G) ||
+                       (i >= L.sigma_alpha && i < L.sigma_alpha + m.k) || i == L.tail;
+      v = pos ? exp(z) : z;
+      const double e = (z - m.mu[i]) * exp(-m.omega[i]);
+      acc += e * e;
+    } else if (!m.depth && i < D + G) {
+      v = m.zeta[L.mu_beta0] + exp(m.zeta[L.sigma_beta0]) * m.zeta[L.z_beta0 + (i - D)];   // beta0[g], approxGP.stan:26
+    } else {
+      v = exp(2.0 * m.zeta[L.amp + (i - D - (m.depth ? 0 : G))]);                           // amplitude_sq[g], :27
+    }
+    out[(3 + i) * n + d] = v;
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
+    part[blockIdx.x] = s;
+  }
+}
+__global__ void k_store_draw_finish(const double *__restrict__ part, int nblk, const double *__restrict__ lps, int64_t n, int64_t d,
+                                    double *__restrict__ out) {
+  double s = 0;
+  for (int b = 0; b < nblk; ++b) s += part[b];  // fixed order
+  out[d] = 0.0;                 // lp__ is 0 for variational output [U]
+  out[n + d] = lps[d];          // log_p__ = log_prob<propto = false, jacobian = true>(zeta_d)
+  out[2 * n + d] = -0.5 * s;    // log_g__ = -1/2 sum eps^2: the draw's log density under the approximation up to a constant [U]
+}
+extern "C" int bvg_fit_get_posterior(bvg_fit *f, int n, double *out) {
+  BVG_TRY(need_ready(f));
+  if (!f->have_vi) { bvg_set_error("no variational fit to draw from"); return BVG_ERR_STATE; }
+  if (n < 1 || !out) { bvg_set_error("bad argument"); return BVG_ERR_ARG; }
+  if (f->comm_mode) { bvg_set_error("posterior draws of a gene-sharded fit are not built; use bvg_fit_get_draws per shard"); return BVG_ERR_ARG; }
+  const int64_t ncol = posterior_ncol(f);
+  double *d_out = nullptr, *d_part = nullptr;
+  const int nblk = 148 * 2;
+  CUDA_TRY(cudaMalloc(&d_out, sizeof(double) * (size_t)ncol * n + sizeof(double) * nblk));
+  d_part = d_out + (size_t)ncol * n;
+  if (f->elbo_cap < n) {
+    cudaFree(f->m.elbo_lps);
+    f->m.elbo_lps = nullptr; f->elbo_cap = 0;
+    if (cudaMalloc(&f->m.elbo_lps, sizeof(double) * n) != cudaSuccess) { cudaFree(d_out); bvg_set_error("out of device memory"); return BVG_ERR_CUDA; }
+    f->elbo_cap = n;
+  }
+  Ctl h;
+  int rc = ctl_get(f, &h);
+  h.t_draw = 0;
+  if (rc == BVG_OK) rc = ctl_set(f, h);
+  for (int d = 0; d < n && rc == BVG_OK; ++d) {
+    rc = eval_log_prob_device(f, MODE_POST_DRAW, 1, 0, false);
+    if (rc != BVG_OK) break;
+    k_store_draw<<<nblk, 256, 0, f->stream>>>(f->m, n, d, d_out, d_part);
+    k_store_draw_finish<<<1, 1, 0, f->stream>>>(d_part, nblk, f->m.elbo_lps, n, d, d_out);
+    f->st.kernel_launches += 2;
+  }
+  if (rc == BVG_OK && (cudaGetLastError() != cudaSuccess ||
+                       cudaMemcpyAsync(out, d_out, sizeof(double) * (size_t)ncol * n, cudaMemcpyDeviceToHost, f->stream) != cudaSuccess ||
+                       cudaStreamSynchronize(f->stream) != cudaSuccess)) {
+    bvg_set_error("posterior draws failed: %s", cudaGetErrorString(cudaGetLastError()));
+    rc = BVG_ERR_CUDA;
+  }
+  cudaFree(d_out);
+  return rc;
+}
+
 extern "C" int bvg_fit_get_trace(bvg_fit *f, double *out, int cap, int *n) {
   if (!f || !out || !n) { bvg_set_error("null argument"); return BVG_ERR_ARG; }
   const int m = std::min(cap, f->n_trace);

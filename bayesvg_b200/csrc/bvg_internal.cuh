@@ -82,6 +82,8 @@ struct Ctl {
   int32_t elbo_ok;
   uint32_t ticket;   // last-block-done counter of k_gene (fused finish)
   double es;         // eta / sqrt(it): kept next to `it` so that k_gene starts without a sqrt + divide chain
+  uint32_t t_draw;   // running counter of posterior draws (stream 3; bvg_fit_get_posterior)
+  uint32_t pad1;
 };
 
 // ---- peer-memory exchange (multi-GPU) ------------------------------------------
@@ -323,5 +325,6 @@ int launch_gene_finish(bvg_fit *f, int mode, int jacobian, int propto, int ahead
 int comm_allreduce(bvg_fit *f, double *buf, int n);          // comm.cu
 int suff_elbo(bvg_fit *f, int S, double *lps_host);          // k_suff.cu: S log densities from sufficient statistics
 void suff_destroy(bvg_fit *f);
-enum { MODE_GRAD_OUT = 0, MODE_ADVI_UPDATE = 1, MODE_ELBO_DRAW = 2, MODE_LP_ONLY = 3 };
-enum { PREP_NONE = 0, PREP_GRAD = 1, PREP_ELBO = 2 };
+// MODE_POST_DRAW: log_p__ of a posterior draw (Philox stream 3, counter ctl->t_draw), stored in elbo_lps[t_draw]
+enum { MODE_GRAD_OUT = 0, MODE_ADVI_UPDATE = 1, MODE_ELBO_DRAW = 2, MODE_LP_ONLY = 3, MODE_POST_DRAW = 4 };
+enum { PREP_NONE = 0, PREP_GRAD = 1, PREP_ELBO = 2, PREP_DRAW = 3 };

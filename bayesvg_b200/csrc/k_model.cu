@@ -23,8 +23,8 @@ __global__ void __launch_bounds__(256) k_prep(DevModel m, int mode, int tc, int 
   griddep_launch();
   const int k = m.k, nsh = 2 * k + 5, npg = k + 2, tid = threadIdx.x;
   double *sal = sh + nsh, *zg = sal + k, *Ag = zg + gpb * npg;
-  const uint32_t stream = mode == PREP_GRAD ? STREAM_GRAD : STREAM_ELBO;
-  const uint32_t t = mode == PREP_GRAD ? m.ctl->t_grad : m.ctl->t_elbo;
+  const uint32_t stream = mode == PREP_GRAD ? STREAM_GRAD : (mode == PREP_DRAW ? STREAM_DRAW : STREAM_ELBO);
+  const uint32_t t = mode == PREP_GRAD ? m.ctl->t_grad : (mode == PREP_DRAW ? m.ctl->t_draw : m.ctl->t_elbo);
   // ---- phase 1: every parameter's zeta ----
   const int t2 = tid - nsh, gl = t2 >= 0 ? t2 / npg : -1, j = t2 >= 0 ? t2 - gl * npg : 0;
   const int64_t g = (int64_t)blockIdx.x * gpb + gl;
@@ -90,8 +90,8 @@ __global__ void __launch_bounds__(256) k_prep_big(DevModel m, int mode, int gpb)
   griddep_launch();
   const int k = m.k, nsh = 2 * k + 5, npg = k + 2, tid = threadIdx.x;
   double *sal = sh + nsh, *zg = sal + k, *Ag = zg + gpb * npg;
-  const uint32_t stream = mode == PREP_GRAD ? STREAM_GRAD : STREAM_ELBO;
-  const uint32_t t = mode == PREP_GRAD ? m.ctl->t_grad : m.ctl->t_elbo;
+  const uint32_t stream = mode == PREP_GRAD ? STREAM_GRAD : (mode == PREP_DRAW ? STREAM_DRAW : STREAM_ELBO);
+  const uint32_t t = mode == PREP_GRAD ? m.ctl->t_grad : (mode == PREP_DRAW ? m.ctl->t_draw : m.ctl->t_elbo);
   const int64_t gbase = (int64_t)blockIdx.x * gpb;
   for (int i = tid; i < nsh + gpb * npg; i += blockDim.x) {
     const bool is_sh = i < nsh;
@@ -407,6 +407,9 @@ __device__ void finish_body(const DevModel &m, int mode, int jac, int propto, in
       if (loc) { m.elbo_lps[m.ctl->elbo_ok] = lp; m.ctl->elbo_ok += 1; }  // local share; the host all-reduces the S slots
       else if (isfinite(lp)) { m.ctl->elbo_acc += lp; m.ctl->elbo_ok += 1; }
       m.ctl->t_elbo += 1;
+    } else if (mode == MODE_POST_DRAW) {
+      m.elbo_lps[m.ctl->t_draw] = lp;
+      m.ctl->t_draw += 1;
     }
   }
 }

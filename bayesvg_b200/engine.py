@@ -194,6 +194,34 @@ class Fit:
         B.check(B.lib().bvg_fit_get_draws(self._h, _dp(out)))
         return out
 
+    def posterior_columns(self):
+        """CmdStan's variational CSV header for this model: lp__, log_p__, log_g__, the parameters in declaration
+        order (inst/approxGP*.stan `parameters`), then the transformed parameters (approxGP.stan:25-28)."""
+        G, k, nb, depth = self.G, self.k, self.cfg.likelihood == B.NB, bool(self.cfg.depth_adjust)
+        vec = lambda name, n: [f"{name}[{i + 1}]" for i in range(n)]  # noqa: E731
+        z = [f"z_alpha_t[{j + 1},{g + 1}]" for g in range(G) for j in range(k)]  # column-major
+        hyper = ["mu_amplitude", "sigma_amplitude"]
+        alpha = vec("mu_alpha", k) + vec("sigma_alpha", k) + z
+        tail = "phi_nb" if nb else "sigma_y"
+        if depth:      # approxGP2.stan:13-23 / approxGP3.stan:13-23
+            cols = ["beta0", "beta1", tail] + vec("amplitude", G) + hyper + alpha
+        elif nb:       # approxGP4.stan:12-23
+            cols = ["mu_beta0", "sigma_beta0"] + vec("z_beta0", G) + [tail] + vec("amplitude", G) + hyper + alpha
+        else:          # approxGP.stan:12-23
+            cols = ["mu_beta0", "sigma_beta0"] + vec("z_beta0", G) + hyper + vec("amplitude", G) + alpha + [tail]
+        assert len(cols) == self.D
+        tp = ([] if depth else vec("beta0", G)) + vec("amplitude_sq", G)
+        return ["lp__", "log_p__", "log_g__"] + cols + tp
+
+    def posterior(self, n=None):
+        """n x ncol draws of the whole model (what cmdstanr's `fit_vi$draws()` holds; save.model = TRUE, :483-489)."""
+        n = int(self.cfg.n_draws if n is None else n)
+        nc = C.c_int64()
+        B.check(B.lib().bvg_fit_posterior_ncol(self._h, C.byref(nc)))
+        out = np.empty((n, nc.value), order="F")
+        B.check(B.lib().bvg_fit_get_posterior(self._h, n, _dp(out)))
+        return out
+
     def trace(self):
         out = np.zeros((64, 4))
         n = C.c_int()

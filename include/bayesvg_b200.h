@@ -150,6 +150,12 @@ int bvg_fit_flush_l2(bvg_fit *);
 /* results */
 int bvg_fit_get_summary(bvg_fit *, double *out /* G x 8 col-major: mean, median, sd, mad, q5, q95, dispersion, rank */);
 int bvg_fit_get_draws(bvg_fit *, double *out /* n_draws x G col-major amplitude draws */);
+/* save.model = TRUE (:483-489, R/extractModel.R:21-25): the content of the CmdStanVB object's draws, i.e. of CmdStan's
+ * variational output CSV.  out is n x ncol COLUMN-major with columns lp__ (0), log_p__, log_g__, the D parameters
+ * constrained in declaration order, then the transformed parameters beta0[G] (hierarchical intercept only) and
+ * amplitude_sq[G].  Draw d uses Philox stream 3, counter d, so its amplitude columns equal bvg_fit_get_draws. */
+int bvg_fit_posterior_ncol(bvg_fit *, int64_t *ncol);
+int bvg_fit_get_posterior(bvg_fit *, int n, double *out);
 int bvg_fit_get_trace(bvg_fit *, double *out /* cap x 4 row-major: iter, elbo, delta_mean, delta_med */, int cap, int *n);
 
 typedef struct {

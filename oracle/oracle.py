@@ -156,6 +156,38 @@ class Oracle:
                            self.G if G_total is None else G_total, _p(out))
         return out
 
+    def posterior(self, mu, omega, n, seed=312):
+        """n draws of the whole model as CmdStan's variational CSV lays them out [U] (SURVEY A.4 "output"):
+        lp__ = 0, log_p__ = log_prob<propto=false, jacobian=true>(zeta), log_g__ = -1/2 sum eps^2, the parameters
+        constrained in declaration order, then beta0[G] (hierarchical intercept only; approxGP.stan:26) and
+        amplitude_sq[G] (:27).  Draw d of parameter i uses Philox stream 3, counter d (as `summary`)."""
+        depth = self.model >= 2
+        lik = self.model & 1
+        L = layout(lik, self.G, self.k, depth)
+        G, k, D = self.G, self.k, self.D
+        pos = np.zeros(D, bool)
+        pos[L["sigma_amplitude"]] = True
+        pos[L["amplitude"]:L["amplitude"] + G] = True
+        pos[L["sigma_alpha"]:L["sigma_alpha"] + k] = True
+        pos[L["phi_nb" if lik == NB else "sigma_y"]] = True
+        if not depth:
+            pos[L["sigma_beta0"]] = True
+        out = np.empty((n, 3 + D + (1 if depth else 2) * G), order="F")
+        for d in range(n):
+            eps = np.array([normal(seed, 3, d, i) for i in range(D)])
+            zeta = np.asarray(mu) + np.exp(omega) * eps
+            th = np.where(pos, np.exp(zeta), zeta)
+            out[d, 0] = 0.0
+            out[d, 1] = self.log_prob(zeta, True, False, grad=False)
+            out[d, 2] = -0.5 * float(eps @ eps)
+            out[d, 3:3 + D] = th
+            c = 3 + D
+            if not depth:
+                out[d, c:c + G] = th[L["mu_beta0"]] + th[L["sigma_beta0"]] * th[L["z_beta0"]:L["z_beta0"] + G]
+                c += G
+            out[d, c:c + G] = th[L["amplitude"]:L["amplitude"] + G] ** 2
+        return out
+
 
 def normal(seed, stream, t, i):
     return lib().bvgo_normal(seed, stream, t, i)

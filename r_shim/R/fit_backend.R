@@ -11,7 +11,7 @@
 #                     gene_depths (:303, log(rowSums(counts[naive.hvgs, ]))) when gene.depth.adjust = TRUE, else NULL
 bvg_fit_backend <- function(spatial_mtx, kmeans_centers, lscale, expr_df, gene_mapping, likelihood, kernel,
                             kernel.smoothness, kernel.period, n.iter, mle.init, mle.iter, n.draws,
-                            elbo.samples, random.seed, verbose, gene_depths = NULL, device = 0L) {
+                            elbo.samples, random.seed, verbose, gene_depths = NULL, device = 0L, save.model = FALSE) {
   M <- nrow(spatial_mtx)
   G <- length(unique(expr_df$gene))
   kernel_id <- match(kernel, c("exp_quad", "matern", "periodic")) - 1L
@@ -46,5 +46,8 @@ bvg_fit_backend <- function(spatial_mtx, kmeans_centers, lscale, expr_df, gene_m
                        dplyr::mutate(amplitude_mean_rank = dplyr::row_number()) %>%
                        as.data.frame() %>%
                        magrittr::set_rownames(.$gene)
+  # :483-489  save.model = TRUE: the draws of the whole model as a posterior::draws_matrix (what fit_vi$draws() holds);
+  #           column names are built as in bayesvg_b200/engine.py::Fit.posterior_columns
+  if (save.model) attr(amplitude_summary, "draws") <- .Call("R_bvg_fit_posterior", fit, as.integer(n.draws))
   amplitude_summary
 }

@@ -102,6 +102,16 @@ SEXP R_bvg_fit_variational(SEXP p, SEXP D) {
   UNPROTECT(1);
   return out;
 }
+/* save.model = TRUE (:483-489): the n x ncol draws matrix behind cmdstanr's fit_vi$draws(); columns lp__, log_p__,
+ * log_g__, the parameters constrained in declaration order, beta0[G] (hierarchical intercept), amplitude_sq[G] */
+SEXP R_bvg_fit_posterior(SEXP p, SEXP n) {
+  int64_t ncol = 0;
+  chk(bvg_fit_posterior_ncol(get_fit(p), &ncol));
+  SEXP out = PROTECT(Rf_allocMatrix(REALSXP, Rf_asInteger(n), (int)ncol));
+  chk(bvg_fit_get_posterior(get_fit(p), Rf_asInteger(n), REAL(out)));
+  UNPROTECT(1);
+  return out;
+}
 SEXP R_bvg_fit_destroy(SEXP p) { fit_finalizer(p); return R_NilValue; }
 
 static const R_CallMethodDef calls[] = {
@@ -110,6 +120,7 @@ static const R_CallMethodDef calls[] = {
   {"R_bvg_fit_run", (DL_FUNC)&R_bvg_fit_run, 1},         {"R_bvg_fit_summary", (DL_FUNC)&R_bvg_fit_summary, 2},
   {"R_bvg_log_prob", (DL_FUNC)&R_bvg_log_prob, 4},       {"R_bvg_fit_variational", (DL_FUNC)&R_bvg_fit_variational, 2},
   {"R_bvg_fit_destroy", (DL_FUNC)&R_bvg_fit_destroy, 1}, {"R_bvg_fit_set_gene_depths", (DL_FUNC)&R_bvg_fit_set_gene_depths, 2},
+  {"R_bvg_fit_posterior", (DL_FUNC)&R_bvg_fit_posterior, 2},
   {NULL, NULL, 0}};
 void R_init_bayesVGb200(DllInfo *dll) {
   R_registerRoutines(dll, NULL, calls, NULL, NULL);

@@ -313,6 +313,33 @@ def test_summary_matches_oracle(nd):
     f.close()
 
 
+@pytest.mark.parametrize("lik,depth", [("gaussian", False), ("nb", False), ("gaussian", True), ("nb", True)])
+@pytest.mark.parametrize("prec,eng", ENGINES)
+def test_posterior_draws_of_the_whole_model(lik, depth, prec, eng):
+    """save.model = TRUE (R/findSpatiallyVariableFeaturesBayes.R:483-489): the draws matrix behind the CmdStanVB object --
+    lp__, log_p__, log_g__, parameters constrained in declaration order, beta0[G], amplitude_sq[G]."""
+    p = make_problem(97, 21, 6, lik, seed=11)
+    gd = np.log(np.abs(p["y"]).sum(0) + 1.0) if depth else None
+    o = orc.Oracle(p["phi"], p["y"], lik, gene_depths=gd)
+    rng = np.random.default_rng(8)
+    mu, om = rng.normal(0, 0.3, o.D), rng.normal(-2.5, 0.3, o.D)
+    f = _fit(p["phi"], p["y"], lik, prec, eng, gene_depths=gd, n_draws=12, seed=41)
+    f.set_variational(mu, om)
+    cols = f.posterior_columns()
+    got, ref = f.posterior(12), o.posterior(mu, om, 12, seed=41)
+    assert got.shape == ref.shape == (12, len(cols))
+    assert np.all(got[:, 0] == 0)
+    assert np.allclose(got[:, 2:], ref[:, 2:], rtol=1e-11, atol=1e-13)                    # fp64 state in both precisions
+    assert np.allclose(got[:, 1], ref[:, 1], rtol=ACHIEVED[prec], atol=0)                 # log_p__ goes through the engine
+    f.summarize()
+    ia = cols.index("amplitude[1]")
+    assert np.array_equal(got[:, ia:ia + 21], f.draws())                                  # same Philox stream as the summary
+    assert np.array_equal(f.posterior(5), got[:5])                                        # repeatable, counter restarts
+    lp0, _ = f.log_prob(mu, True, False)                                                  # the handle is still usable
+    assert np.isfinite(lp0)
+    f.close()
+
+
 @pytest.mark.parametrize("kname,kernel,nu,period", [
     ("exp_quad", "exp_quad", 0.0, 1.0), ("matern0.5", "matern", 0.5, 1.0), ("matern1.5", "matern", 1.5, 1.0),
     ("matern2.5", "matern", 2.5, 1.0), ("periodic", "periodic", 0.0, 3.0)])

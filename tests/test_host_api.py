@@ -146,3 +146,59 @@ def test_gene_depths_reach_the_fit_only_with_depth_adjust(monkeypatch):
     assert np.allclose(seen["depths"], np.log(np.asarray(o.counts)[rows].sum(1)))
     api.findSpatiallyVariableFeaturesBayes(o, genes, n_basis_fns=3, verbose=False)
     assert seen["depths"] is None
+
+
+def test_variational_fit_object_mirrors_cmdstanvb(tmp_path):
+    """save.model = TRUE / extractModel() (R/findSpatiallyVariableFeaturesBayes.R:483-489, R/extractModel.R:18-27):
+    the host logic of the CmdStanVB stand-in on an oracle-made draws matrix (no device involved)."""
+    from oracle import oracle as orc
+    from tests.util import make_problem
+    from bayesvg_b200.engine import Fit
+
+    p = make_problem(40, 5, 3, "gaussian", seed=4)
+    o = orc.Oracle(p["phi"], p["y"])
+    rng = np.random.default_rng(1)
+    mu, om = rng.normal(0, 0.3, o.D), rng.normal(-2, 0.2, o.D)
+    P = o.posterior(mu, om, 50, seed=7)
+    shell = Fit.__new__(Fit)                       # column names only need the shape and the model kind
+    shell.G, shell.k, shell.D, shell._h = 5, 3, o.D, None
+    shell.cfg = bvg.default_config(likelihood=0, depth_adjust=0)
+    cols = shell.posterior_columns()
+    assert cols[:5] == ["lp__", "log_p__", "log_g__", "mu_beta0", "sigma_beta0"] and cols[-1] == "amplitude_sq[5]"
+    assert cols[3 + o.D - 1] == "sigma_y" and "z_alpha_t[2,4]" in cols and len(cols) == P.shape[1]
+    L = orc.layout("gaussian", 5, 3)
+    assert cols[3 + L["z_alpha_t"] + 3 * 3 + 1] == "z_alpha_t[2,4]"      # column-major: gene 4, basis fn 2
+    vf = bvg.VariationalFit(cols, P, mu=mu, omega=om)
+    assert vf.num_draws() == 50 and list(vf.draws("amplitude").columns) == [f"amplitude[{g}]" for g in range(1, 6)]
+    assert np.array_equal(vf.lp(), P[:, 1]) and np.array_equal(vf.lp_approx(), P[:, 2])
+    s = vf.summary("amplitude")
+    ref = o.summary(mu, om, 50, seed=7)            # the reference's summary call, :419
+    assert np.allclose(s[["mean", "median", "sd", "mad", "q5", "q95"]].to_numpy(), ref[:, :6], rtol=1e-12)
+    a, a2 = vf.draws("amplitude[2]").to_numpy()[:, 0], vf.draws("amplitude_sq[2]").to_numpy()[:, 0]
+    assert np.allclose(a * a, a2, rtol=1e-14)
+    b0 = vf.draws(["mu_beta0", "sigma_beta0", "z_beta0[3]", "beta0[3]"]).to_numpy()
+    assert np.allclose(b0[:, 0] + b0[:, 1] * b0[:, 2], b0[:, 3], rtol=1e-14)
+    with pytest.raises(KeyError, match="Can't find"):
+        vf.draws("nope")
+    m = vf.mean_row()
+    assert m[:3].tolist() == [0, 0, 0] and m[3 + L["sigma_y"]] == np.exp(mu[L["sigma_y"]]) and m[3] == mu[0]
+    path = vf.save_csv(str(tmp_path / "vb.csv"))
+    back = pd.read_csv(path, comment="#")
+    assert "z_alpha_t.2.4" in back.columns and "amplitude_sq.5" in back.columns and len(back.columns) == len(cols)
+    assert back.shape == (51, len(cols)) and np.allclose(back.to_numpy()[1:], P, rtol=1e-15)
+    obj = _obj()
+    assert bvg.extractModel(obj) is None
+    obj.misc["model_fit"] = vf
+    assert bvg.extractModel(obj) is vf
+    with pytest.raises(ValueError, match="must be non-NULL"):
+        bvg.extractModel(None)
+    # the other three programs' headers (declaration order: approxGP4.stan:12-23, approxGP2/3.stan:13-23)
+    for lik, depth, head in ((1, 0, ["mu_beta0", "sigma_beta0", "z_beta0[1]"]), (0, 1, ["beta0", "beta1", "sigma_y"]),
+                             (1, 1, ["beta0", "beta1", "phi_nb"])):
+        shell.cfg = bvg.default_config(likelihood=lik, depth_adjust=depth)
+        shell.D = 5 + (1 if depth else 2) * 5 + 2 * 3 + 3 * 5
+        c = shell.posterior_columns()
+        assert c[3:6] == head and len(c) == 3 + shell.D + (1 if depth else 2) * 5
+        Lx = orc.layout("nb" if lik else "gaussian", 5, 3, bool(depth))
+        assert c[3 + Lx["amplitude"]] == "amplitude[1]" and c[3 + Lx["mu_alpha"]] == "mu_alpha[1]"
+        assert c[3 + Lx["phi_nb" if lik else "sigma_y"]] == ("phi_nb" if lik else "sigma_y")
