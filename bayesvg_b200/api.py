@@ -147,36 +147,22 @@ def scale_coords(coords):
     return (X - X.mean(0)) / X.std(0, ddof=1)
 
 
-def kmeans_centers(X, k, iter_max=100, nstart=10, rng=None):
-    """stats::kmeans(X, centers = k, iter.max = 100, nstart = 10)$centers (:200-204).
+def kmeans_centers(X, k, iter_max=100, nstart=10, rng=None, device=0):
+    """stats::kmeans(X, centers = k, iter.max = 100, nstart = 10)$centers (:200-204), on the device (bvg_kmeans).
 
-    R runs Hartigan-Wong from `nstart` random starts drawn from the ambient RNG and keeps the best;
-    here: Lloyd iterations from `nstart` random starts (rows of X), best within-SS kept.  `rng=None`
-    uses numpy's global state, mirroring the reference's un-seeded call."""
+    R runs Hartigan-Wong from `nstart` random starts drawn from the ambient RNG and keeps the best; here: Lloyd
+    iterations from `nstart` Philox-drawn starts, best within-SS kept.  The Philox key comes from `rng` (a numpy
+    Generator or an int); `rng=None` takes it from numpy's global state, mirroring the reference's un-seeded call."""
     X = np.asarray(X, dtype=np.float64)
-    M = X.shape[0]
-    if k > M:
+    if k > X.shape[0]:
         raise ValueError("more cluster centers than distinct data points.")
-    rs = np.random if rng is None else rng
-    best, best_ss = None, np.inf
-    for _ in range(nstart):
-        C = X[rs.choice(M, k, replace=False)].copy()
-        for _ in range(iter_max):
-            d = ((X[:, None, :] - C[None]) ** 2).sum(-1)
-            lab = d.argmin(1)
-            newC = C.copy()
-            for j in range(k):
-                m = lab == j
-                if m.any():
-                    newC[j] = X[m].mean(0)
-            if np.allclose(newC, C, rtol=0, atol=1e-12):
-                C = newC
-                break
-            C = newC
-        ss = ((X - C[((X[:, None, :] - C[None]) ** 2).sum(-1).argmin(1)]) ** 2).sum()
-        if ss < best_ss:
-            best, best_ss = C, ss
-    return best
+    if rng is None:
+        seed = int(np.random.randint(0, 2**31 - 1))
+    elif isinstance(rng, (int, np.integer)):
+        seed = int(rng)
+    else:
+        seed = int(rng.integers(0, 2**63 - 1))
+    return E.kmeans(X, k, iter_max, nstart, seed, device)
 
 
 def length_scale_kmeans(centers):
@@ -254,7 +240,7 @@ def findSpatiallyVariableFeaturesBayes(sp_obj=None, naive_hvgs=None, likelihood=
             gene_depths = np.log(np.asarray(sp_obj.counts)[rows, :].sum(axis=1).astype(np.float64))
     # length-scale + basis (:200-288)
     if centers is None:
-        centers = kmeans_centers(X, n_basis_fns, 100, 10, kmeans_rng)
+        centers = kmeans_centers(X, n_basis_fns, 100, 10, kmeans_rng, device)
     centers = np.asarray(centers, dtype=np.float64)
     if centers.shape != (n_basis_fns, 2):
         _abort("centers must be n.basis.fns x 2")

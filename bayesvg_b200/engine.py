@@ -38,6 +38,21 @@ def basis_build(coords, centers, lscale, kernel="exp_quad", nu=1.5, period=100.0
     return out
 
 
+def kmeans(coords, k, iter_max=100, nstart=10, seed=312, device=0, return_info=False):
+    """stats::kmeans(coords, centers = k, iter.max, nstart)$centers on the GPU (findSpatiallyVariableFeaturesBayes.R:200-204)."""
+    X = np.asfortranarray(coords, dtype=np.float64)
+    if X.ndim != 2 or X.shape[1] != 2:
+        raise ValueError("coords must be M x 2")
+    out = np.empty((int(k), 2), order="F")
+    ss = C.c_double()
+    info = (C.c_int32 * 3)()
+    B.check(B.lib().bvg_kmeans(device, _dp(X), X.shape[0], int(k), int(iter_max), int(nstart), int(seed), _dp(out),
+                               C.byref(ss), info))
+    if return_info:
+        return out, dict(tot_withinss=ss.value, start=info[0], iters=info[1], converged=bool(info[2]))
+    return out
+
+
 class Fit:
     """gene_depths (length G, log of each gene's total count) selects the depth-adjusted programs
     inst/approxGP2.stan / approxGP3.stan (gene.depth.adjust = TRUE in the reference)."""

@@ -95,6 +95,15 @@ void bvg_config_default(bvg_config *cfg);
 int bvg_basis_build(int device, const double *coords, int64_t M, const double *centers, int k,
                     double lscale, int kernel, double nu, double period, double *phi_out);
 
+/* Centroids (:200-204): stats::kmeans(spatial_mtx, centers = k, iter.max = 100, nstart = 10)$centers on the device.
+ * Lloyd-Forgy from `nstart` sets of k distinct rows drawn with Philox (key = seed; the reference draws its starts from
+ * R's ambient RNG, so its centroids are not reproducible and parity on them is statistical); the start with the
+ * smallest total within-cluster sum of squares wins.  Sums are 64-bit fixed point: the result is bit-reproducible.
+ * coords M x 2 col-major, already z-scored (:160; |x| < 256, M <= 2^22); centers_out k x 2 col-major;
+ * tot_withinss and info = {winning start, its iterations, converged 0/1} may be NULL. */
+int bvg_kmeans(int device, const double *coords, int64_t M, int k, int iter_max, int nstart, uint64_t seed,
+               double *centers_out, double *tot_withinss, int32_t *info);
+
 int bvg_fit_create(const bvg_config *cfg, bvg_fit **out);
 void bvg_fit_destroy(bvg_fit *);
 

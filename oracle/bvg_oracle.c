@@ -798,3 +798,71 @@ int bvgo_basis(const double *X, int64_t M, const double *C, int k, double ls, in
   free(A);
   return 0;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * k-means centroids, R/findSpatiallyVariableFeaturesBayes.R:200-204.  Lloyd-Forgy; sums in 64-bit fixed point
+ * (2^-32 for coordinates, 2^-20 for the within-SS) so that the device version, whose atomics add in any order,
+ * gives the same bits.
+ * ---------------------------------------------------------------------------------------- */
+int bvgo_kmeans(const double *X, int64_t M, int k, int iter_max, int nstart, uint64_t seed, double *centers_out,
+                double *tot_withinss, int32_t *info) {
+  const double FIX = 4294967296.0, SSFIX = 1048576.0;
+  if (M < 1 || k < 1 || k > M || iter_max < 1 || nstart < 1) return -1;
+  int64_t *rows = (int64_t *)malloc(sizeof(int64_t) * k);
+  int32_t *lab = (int32_t *)malloc(sizeof(int32_t) * M);
+  double *C = (double *)malloc(sizeof(double) * 2 * k);
+  int64_t *acc = (int64_t *)malloc(sizeof(int64_t) * 3 * k);
+  uint64_t best_ss = ~(uint64_t)0;
+  for (int r = 0; r < nstart; ++r) {
+    for (int j = 0; j < k; ++j) /* k distinct rows: first Philox value (counter (j, attempt, r, 4)) mod M not yet drawn */
+      for (uint32_t a = 0;; ++a) {
+        uint32_t ctr[4] = {(uint32_t)j, a, (uint32_t)r, 4u}, key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)}, o[4];
+        bvgo_philox4x32_10(ctr, key, o);
+        const int64_t row = (int64_t)((((uint64_t)o[0] << 32) | o[1]) % (uint64_t)M);
+        int dup = 0;
+        for (int q = 0; q < j && !dup; ++q) dup = rows[q] == row;
+        if (!dup) { rows[j] = row; break; }
+      }
+    for (int j = 0; j < k; ++j) { C[j] = X[rows[j]]; C[k + j] = X[M + rows[j]]; }
+    for (int64_t s = 0; s < M; ++s) lab[s] = -1;
+    int it = 0, conv = 0;
+    uint64_t ss;
+    for (;;) {
+      int64_t changed = 0;
+      ss = 0;
+      memset(acc, 0, sizeof(int64_t) * 3 * k);
+      for (int64_t s = 0; s < M; ++s) {
+        const double x = X[s], y = X[M + s];
+        double best = INFINITY;
+        int bj = 0;
+        for (int j = 0; j < k; ++j) {
+          const double dx = x - C[j], dy = y - C[k + j];
+          const double d = fma(dx, dx, dy * dy);
+          if (d < best) { best = d; bj = j; }
+        }
+        changed += lab[s] != bj;
+        lab[s] = bj;
+        ss += (uint64_t)llrint(best * SSFIX);
+        acc[bj] += (int64_t)llrint(x * FIX);
+        acc[k + bj] += (int64_t)llrint(y * FIX);
+        acc[2 * k + bj] += 1;
+      }
+      if (changed == 0) { conv = 1; break; }
+      if (it == iter_max) break;
+      for (int j = 0; j < k; ++j)
+        if (acc[2 * k + j]) {
+          C[j] = (double)acc[j] / (double)acc[2 * k + j] * (1.0 / FIX);
+          C[k + j] = (double)acc[k + j] / (double)acc[2 * k + j] * (1.0 / FIX);
+        }
+      ++it;
+    }
+    if (ss < best_ss) {
+      best_ss = ss;
+      memcpy(centers_out, C, sizeof(double) * 2 * k);
+      if (info) { info[0] = r; info[1] = it; info[2] = conv; }
+    }
+  }
+  if (tot_withinss) *tot_withinss = (double)best_ss / SSFIX;
+  free(rows); free(lab); free(C); free(acc);
+  return 0;
+}

@@ -99,6 +99,12 @@ int bvgo_basis(const double *coords /*M x 2 col-major*/, int64_t M, const double
                int k, double lscale, int kernel, double nu, double period, double *phi_out,
                double *raw_out);
 
+/* centroids (findSpatiallyVariableFeaturesBayes.R:200-204, stats::kmeans(centers = k, iter.max, nstart)): Lloyd-Forgy
+ * from nstart Philox-drawn sets of k distinct rows, fixed-point sums (serial restatement of csrc/k_kmeans.cu; R's own
+ * Hartigan-Wong + ambient RNG is not reproducible).  info = {best start, iterations, converged}. */
+int bvgo_kmeans(const double *coords /*M x 2 col-major*/, int64_t M, int k, int iter_max, int nstart,
+                uint64_t seed, double *centers_out /*k x 2*/, double *tot_withinss, int32_t *info);
+
 double bvgo_digamma(double x);
 
 #ifdef __cplusplus

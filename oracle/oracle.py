@@ -74,6 +74,7 @@ def lib():
         L.bvgo_lbfgs.argtypes = [C.c_void_p, _dp, C.POINTER(_LbfgsCfg), _dp, C.POINTER(_LbfgsRes)]
         L.bvgo_summary.argtypes = [C.c_int, C.c_int64, C.c_int, _dp, _dp, C.c_int, C.c_uint64, C.c_int64, C.c_int64, _dp]
         L.bvgo_basis.argtypes = [_dp, C.c_int64, _dp, C.c_int, C.c_double, C.c_int, C.c_double, C.c_double, _dp, _dp]
+        L.bvgo_kmeans.argtypes = [_dp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_uint64, _dp, _dp, C.POINTER(C.c_int32)]
         L.bvgo_digamma.restype = C.c_double
         L.bvgo_digamma.argtypes = [C.c_double]
         _lib = L
@@ -208,6 +209,16 @@ def basis(coords, centers, lscale, kernel="matern", nu=2.5, period=100.0, return
     raw = np.empty((M, k), order="F") if return_raw else None
     lib().bvgo_basis(_p(X), M, _p(Cc), k, lscale, KERNELS[kernel], nu, period, _p(Q), _p(raw) if return_raw else None)
     return (Q, raw) if return_raw else Q
+
+
+def kmeans(coords, k, iter_max=100, nstart=10, seed=312):
+    X = _f(coords)
+    out = np.empty((k, 2), order="F")
+    ss = C.c_double()
+    info = (C.c_int32 * 3)()
+    rc = lib().bvgo_kmeans(_p(X), X.shape[0], k, iter_max, nstart, seed, _p(out), C.byref(ss), info)
+    assert rc == 0
+    return out, dict(tot_withinss=ss.value, start=info[0], iters=info[1], converged=bool(info[2]))
 
 
 def digamma(x):

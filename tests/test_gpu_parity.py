@@ -351,6 +351,26 @@ def test_basis_matches_lapack_golden(golden_dir, kname, kernel, nu, period):
     assert np.max(np.abs(Q - z[f"Q_{kname}"])) < 1e-15 * cond * 50 + 1e-12
 
 
+@pytest.mark.parametrize("M,k,nstart,iter_max", [(2444, 20, 10, 100), (700, 7, 3, 4), (50, 50, 1, 10), (20000, 400, 2, 100), (33, 1, 2, 5)])
+def test_kmeans_centroids_equal_the_cpu_restatement(M, k, nstart, iter_max):
+    """stats::kmeans(spatial_mtx, centers = k, iter.max = 100, nstart = 10) (R/findSpatiallyVariableFeaturesBayes.R:200-204) on
+    the device: fixed-point sums make it bit-reproducible, so the centroids equal the serial restatement exactly."""
+    X = bvg.scale_coords(np.random.default_rng(M).uniform(0, 100, (M, 2)))
+    C, info = bvg.engine.kmeans(X, k, iter_max, nstart, seed=M + 1, return_info=True)
+    ref, rinfo = orc.kmeans(X, k, iter_max, nstart, seed=M + 1)
+    assert np.array_equal(C, ref) and info == rinfo
+    assert np.array_equal(C, bvg.engine.kmeans(X, k, iter_max, nstart, seed=M + 1))       # run-to-run identical
+    lab = ((X[:, None, :] - C[None]) ** 2).sum(-1).argmin(1) if M * k < 2e6 else None
+    if lab is not None and info["converged"]:
+        assert np.allclose(C, np.array([X[lab == j].mean(0) if np.any(lab == j) else C[j] for j in range(k)]), atol=1e-8)
+        assert info["tot_withinss"] == pytest.approx(((X - C[lab]) ** 2).sum(), rel=1e-4)
+    assert bvg.kmeans_centers(X, k, rng=5).shape == (k, 2)
+    with pytest.raises(ValueError, match="more cluster centers"):
+        bvg.kmeans_centers(X[:3], 5)
+    with pytest.raises(bvg._lib.BvgError, match="scaled"):
+        bvg.engine.kmeans(X * 1e4, k)
+
+
 def test_basis_visium_shape():
     from bayesvg_b200 import synth
     X = bvg.scale_coords(synth.visium_grid())

@@ -44,8 +44,17 @@ def test_preprocessing_helpers():
     X = np.random.default_rng(1).uniform(0, 50, (200, 2))
     S = bvg.scale_coords(X)
     assert np.allclose(S.mean(0), 0) and np.allclose(S.std(0, ddof=1), 1)  # coop::scaler (:160)
-    C = bvg.kmeans_centers(S, 7, rng=np.random.default_rng(3))
-    assert C.shape == (7, 2) and np.all(np.abs(C) < 3)
+    from oracle import oracle as orc
+    C, info = orc.kmeans(S, 7, 100, 10, seed=3)    # the CPU restatement of bvg_kmeans (the product runs on the device only)
+    assert C.shape == (7, 2) and np.all(np.abs(C) < 3) and info["converged"]
+    lab = ((S[:, None, :] - C[None]) ** 2).sum(-1).argmin(1)
+    assert np.allclose(C, np.array([S[lab == j].mean(0) for j in range(7)]), atol=1e-8)   # a Lloyd fixed point
+    assert info["tot_withinss"] == pytest.approx(((S - C[lab]) ** 2).sum(), rel=1e-5)
+    C1, i1 = orc.kmeans(S, 7, 100, 1, seed=3)
+    assert i1["start"] == 0 and i1["tot_withinss"] >= info["tot_withinss"]               # nstart keeps the best start
+    if bvg._lib.lib().bvg_device_count() == 0:
+        with pytest.raises(bvg._lib.BvgError, match="no CUDA device"):                    # no CPU fallback
+            bvg.kmeans_centers(S, 7, rng=3)
     d = np.sqrt(((C[:, None] - C[None]) ** 2).sum(-1))
     assert bvg.length_scale_kmeans(C) == pytest.approx(np.median(d[np.triu_indices(7, 1)]))  # :205-207
     with pytest.raises(ValueError):
@@ -139,6 +148,7 @@ def test_gene_depths_reach_the_fit_only_with_depth_adjust(monkeypatch):
             pass
 
     monkeypatch.setattr(api.E, "Fit", FakeFit)
+    monkeypatch.setattr(api.E, "kmeans", lambda X, k, *a: X[:k].copy())   # device entry points are faked: host logic only
     monkeypatch.setattr(api.E, "basis_build", lambda X, C, ls, *a: np.linalg.qr(np.random.default_rng(0).normal(size=(X.shape[0], C.shape[0])))[0])
     genes = ["gene2", "gene5", "gene1"]
     api.findSpatiallyVariableFeaturesBayes(o, genes, n_basis_fns=3, gene_depth_adjust=True, verbose=False)
