@@ -19,7 +19,8 @@
 #define TB_STAGES 3
 #define TB_TILE_BYTES (128 * 128)                 // 128 rows x 64 bf16 (one 128-byte swizzled row per operand row)
 #define TB_STAGE_BYTES (4 * TB_TILE_BYTES)        // A1 | A2 | B1 | B2
-#define TB_SMEM_BYTES (TB_STAGES * TB_STAGE_BYTES + 1024 + 128)
+#define TB_STAGING_BYTES (8 * 4096)             // forward epilogue: one 4 KB transpose buffer per epilogue warp
+#define TB_SMEM_BYTES (TB_STAGES * TB_STAGE_BYTES + 1024 + 256 + TB_STAGING_BYTES)
 
 int tc_make_map(CUtensorMap *m, void *ptr, bool bf16, uint64_t cols, uint64_t rows, uint64_t ld, uint32_t box_rows);
 
@@ -55,7 +56,7 @@ k_tcbig(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtens
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sBar = base + TB_STAGES * TB_STAGE_BYTES;
   const uint32_t bFull = sBar, bEmpty = bFull + 8 * TB_STAGES, bDFull = bEmpty + 8 * TB_STAGES, bDEmpty = bDFull + 16, sTmem = bDEmpty + 16;
-  __shared__ double s_half[2][128];
+  const uint32_t sStage = sBar + 256;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // work decomposition
   //   forward : blockIdx.x = gene tile, blockIdx.y = split; tiles = spot tiles of the split; K loop = nkb basis blocks
@@ -105,6 +106,10 @@ k_tcbig(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtens
           tma_load_2d(st + TB_TILE_BYTES, &tmA2, bFull + 8 * s, ac, ar);
           tma_load_2d(st + 2 * TB_TILE_BYTES, &tmB1, bFull + 8 * s, bc, br);
           tma_load_2d(st + 3 * TB_TILE_BYTES, &tmB2, bFull + 8 * s, bc, br);
+          // The 3-stage ring covers ~2 K blocks (~0.8 us); the basis tiles stream from HBM: ask L2 for the boxes of the
+          // NEXT spot tile.  (The same prefetch 6 K blocks ahead in the backward kernel made it 8 % slower -- it is bound
+          // by L2 -> SM bandwidth, 13 TB/s aggregate, not by HBM latency -- and was removed.)
+          if (MODE == 0 && t + 1 < ntile) { tma_prefetch_2d(&tmB1, bc, br + 128); tma_prefetch_2d(&tmB2, bc, br + 128); }
         }
       }
     }
@@ -143,88 +148,129 @@ k_tcbig(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtens
     const int r = 32 * q + lane;                  // accumulator row
     const uint32_t trow = tmem + ((uint32_t)(32 * q) << 16) + 64 * h;
     if (MODE == 0) {
-      const int64_t g = (int64_t)gt * 128 + r;
-      const bool live = g < a.G;
+      // Global traffic of the epilogue is COALESCED through a 4 KB per-warp staging buffer (32 rows x 128 bytes, 16-byte
+      // chunks XOR-swizzled by row so that both access patterns are bank-conflict free).  The TMEM layout fixes
+      // "thread = gene row", and Y / R are gene-major: the first version let every lane read / write its own row
+      // directly, i.e. 32 different 128-byte lines per instruction -- ncu (profiles/r1b_ncu_full_k_tcbig.csv): tensor
+      // pipe 33 % active, the kernel sat on the L1 tag stage.  Now a Y chunk (32 genes x 32 spots) is fetched with 8
+      // lanes per row (4 full lines per instruction) into registers one chunk AHEAD, transposed through the buffer, and
+      // the two bf16 residual parts go back the same way (8 rows x 64 bytes per store instruction).
+      const int64_t g0 = (int64_t)gt * 128 + 32 * q;   // first gene row of this warp
+      const int64_t g = g0 + lane;
+      const uint32_t sbuf = sStage + (uint32_t)(warp - 2) * 4096u;
       double sum0 = 0.0, sum1 = 0.0;
       float lt = 0.f, phi = 0.f;
       if (LIK == BVG_NB) { lt = (float)a.zeta[a.tail_idx]; phi = __expf(lt); }
-      const float *yrow = a.Y + g * a.ldY + 64 * h;
-      if (live && ntile > 0) {  // this thread's 256 bytes of the first tile into L2
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(yrow + (int64_t)t_begin * 128));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(yrow + (int64_t)t_begin * 128 + 32));
-      }
-      for (int t = 0; t < ntile; ++t) {
-        const int b = t & 1;
-        const int64_t spot0 = (int64_t)(t_begin + t) * 128 + 64 * h;
-        // y for both 32-spot chunks of this tile is requested before the accumulator is waited for, and the next
-        // tile's rows are pulled into L2: the HBM latency of Y hides under the main loop of the other accumulator
-        float4 y4[16];
-        const float4 *py = reinterpret_cast<const float4 *>(yrow + (int64_t)(t_begin + t) * 128);
+      const int yr = lane >> 3, yc = lane & 7;         // Y pattern: instruction i covers rows 4 i + yr, 16-byte chunk yc
+      const int rr = lane & 7, rc = lane >> 3;         // R pattern: instruction i covers rows 8 i + rr, chunk rc of the part
+      const int nchunk = 2 * ntile;                    // chunk n = (tile n >> 1, 32-spot half n & 1)
+      float4 yq[8];
+      auto load_y = [&](int n) {
+        const float *src = a.Y + ((int64_t)(t_begin + (n >> 1)) * 128 + 64 * h + 32 * (n & 1) + 4 * yc);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) y4[i] = live ? __ldg(py + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-        if (live && t + 1 < ntile) {
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(yrow + (int64_t)(t_begin + t + 1) * 128));
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(yrow + (int64_t)(t_begin + t + 1) * 128 + 32));
+        for (int i = 0; i < 8; ++i) {
+          const int64_t gr = g0 + 4 * i + yr;
+          yq[i] = gr < a.G ? __ldg(reinterpret_cast<const float4 *>(src + gr * a.ldY)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        mbar_wait(bDFull + 8 * b, (t >> 1) & 1);
-        tc_fence_after();
+      };
+      if (nchunk > 0) load_y(0);
+      for (int n = 0; n < nchunk; ++n) {
+        const int t = n >> 1, c32 = n & 1, b = t & 1;
+        const int64_t s0 = (int64_t)(t_begin + t) * 128 + 64 * h + 32 * c32;
+        // ---- y: coalesced registers -> staging -> this thread's row ----
 #pragma unroll
-        for (int c32 = 0; c32 < 2; ++c32) {
-          float f[32];
-          tmem_ld32(trow + 128 * b + 32 * c32, f);
-          const int64_t s0 = spot0 + 32 * c32;
-          uint32_t p1[16], p2[16];
-          float acc0 = 0.f, acc1 = 0.f;
+        for (int i = 0; i < 8; ++i) {
+          const int row = 4 * i + yr;
+          sts128(sbuf + row * 128 + ((yc ^ (row & 7)) << 4), yq[i]);
+        }
+        __syncwarp();
+        float4 y4[8];
 #pragma unroll
-          for (int c4 = 0; c4 < 8; ++c4) {
-            const float4 yq = y4[8 * c32 + c4];
-            const float yv[4] = {yq.x, yq.y, yq.z, yq.w};
-            float res[4];
+        for (int c = 0; c < 8; ++c) y4[c] = lds128m(sbuf + lane * 128 + ((c ^ (lane & 7)) << 4));
+        __syncwarp();
+        if (n + 1 < nchunk) load_y(n + 1);   // in flight during this chunk's wait + math
+        if (n + 3 < nchunk && yc == 0) {     // and the chunk after the next one on its way from HBM to L2
+          const float *nx = a.Y + ((int64_t)(t_begin + ((n + 3) >> 1)) * 128 + 64 * h + 32 * ((n + 3) & 1));
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float ff = f[4 * c4 + i];
-              if (LIK == BVG_GAUSSIAN) {
-                res[i] = yv[i] - ff;
-                acc0 = fmaf(res[i], res[i], acc0);
-              } else {  // see k_lik_tc.cu: one ex2 / rcp / lg2 per element
-                const float d = ff - lt;
-                const float ex = ex2_approx(-fabsf(d) * 1.4426950408889634f);
-                const float tt = 1.f + ex;
-                const float rt = rcp_approx(tt);
-                const float Lq = fmaf(lg2_approx(tt), 0.6931471805599453f, fmaxf(d, 0.f));
-                const float sg = (d >= 0.f ? 1.f : ex) * rt;
-                const float yp = yv[i] + phi;
-                res[i] = fmaf(-yp, sg, yv[i]);
-                if (s0 + 4 * c4 + i < a.M) {
-                  acc0 = fmaf(yv[i], d, acc0);
-                  acc0 = fmaf(-yp, Lq, acc0);
-                  acc1 += Lq;
-                }
+          for (int i = 0; i < 8; ++i) {
+            const int64_t gr = g0 + 4 * i + yr;
+            if (gr < a.G) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + gr * a.ldY));
+          }
+        }
+        if (c32 == 0) {
+          mbar_wait(bDFull + 8 * b, (t >> 1) & 1);
+          tc_fence_after();
+        }
+        float f[32];
+        tmem_ld32(trow + 128 * b + 32 * c32, f);
+        uint32_t p1[16], p2[16];
+        float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+          const float4 yv4 = y4[c4];
+          const float yv[4] = {yv4.x, yv4.y, yv4.z, yv4.w};
+          float res[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float ff = f[4 * c4 + i];
+            if (LIK == BVG_GAUSSIAN) {
+              res[i] = yv[i] - ff;
+              acc0 = fmaf(res[i], res[i], acc0);
+            } else {  // see k_lik_tc.cu: one ex2 / rcp / lg2 per element
+              const float d = ff - lt;
+              const float ex = ex2_approx(-fabsf(d) * 1.4426950408889634f);
+              const float tt = 1.f + ex;
+              const float rt = rcp_approx(tt);
+              const float Lq = fmaf(lg2_approx(tt), 0.6931471805599453f, fmaxf(d, 0.f));
+              const float sg = (d >= 0.f ? 1.f : ex) * rt;
+              const float yp = yv[i] + phi;
+              res[i] = fmaf(-yp, sg, yv[i]);
+              if (s0 + 4 * c4 + i < a.M) {
+                acc0 = fmaf(yv[i], d, acc0);
+                acc0 = fmaf(-yp, Lq, acc0);
+                acc1 += Lq;
               }
             }
-            split_bf16x2(res[0], res[1], p1[2 * c4], p2[2 * c4]);
-            split_bf16x2(res[2], res[3], p1[2 * c4 + 1], p2[2 * c4 + 1]);
           }
+          split_bf16x2(res[0], res[1], p1[2 * c4], p2[2 * c4]);
+          split_bf16x2(res[2], res[3], p1[2 * c4 + 1], p2[2 * c4 + 1]);
+        }
+        if (g < a.G) {
           sum0 += (double)acc0;
           if (LIK == BVG_NB) sum1 += (double)acc1;
-          if (a.write_r) {
-            uint4 *o1 = reinterpret_cast<uint4 *>(a.R1 + g * a.Mpad + s0), *o2 = reinterpret_cast<uint4 *>(a.R2 + g * a.Mpad + s0);
-#pragma unroll
-            for (int w = 0; w < 4; ++w) {
-              o1[w] = make_uint4(p1[4 * w], p1[4 * w + 1], p1[4 * w + 2], p1[4 * w + 3]);
-              o2[w] = make_uint4(p2[4 * w], p2[4 * w + 1], p2[4 * w + 2], p2[4 * w + 3]);
-            }
-          }
         }
-        tc_fence_before();
-        mbar_arrive(bDEmpty + 8 * b);
+        if (c32 == 1) {   // both halves of the accumulator are in registers: hand the buffer back before the stores
+          tc_fence_before();
+          mbar_arrive(bDEmpty + 8 * b);
+        }
+        if (a.write_r) {
+          // ---- r: this thread's row (part 1 = chunks 0-3, part 2 = chunks 4-7) -> staging -> coalesced stores ----
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            sts128u(sbuf + lane * 128 + ((w ^ (lane & 7)) << 4), p1[4 * w], p1[4 * w + 1], p1[4 * w + 2], p1[4 * w + 3]);
+            sts128u(sbuf + lane * 128 + (((4 + w) ^ (lane & 7)) << 4), p2[4 * w], p2[4 * w + 1], p2[4 * w + 2], p2[4 * w + 3]);
+          }
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int row = 8 * i + rr;
+            const int64_t off = (g0 + row) * a.Mpad + s0 + 8 * rc;
+            *reinterpret_cast<float4 *>(a.R1 + off) = lds128m(sbuf + row * 128 + ((rc ^ (row & 7)) << 4));
+            *reinterpret_cast<float4 *>(a.R2 + off) = lds128m(sbuf + row * 128 + (((4 + rc) ^ (row & 7)) << 4));
+          }
+          __syncwarp();
+        }
       }
-      if (h == 1) { s_half[0][r] = sum0; s_half[1][r] = sum1; }
+      // the two column halves of a row meet through the (now idle) staging buffer of the h = 1 warp (warp + 4 of the h = 0 one)
+      const uint32_t sred = sStage + (uint32_t)(warp - 2 + (h == 0 ? 4 : 0)) * 4096u + lane * 16;
+      if (h == 1) st_shared_f64x2(sred, sum0, sum1);
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (h == 0) {
+        double o0, o1;
+        ld_shared_f64x2(sred, o0, o1);
         const int64_t row = (int64_t)split * a.Gpad + g;
-        a.Spart[row * 2 + 0] = (float)(sum0 + s_half[0][r]);
-        a.Spart[row * 2 + 1] = (float)(sum1 + s_half[1][r]);
+        a.Spart[row * 2 + 0] = (float)(sum0 + o0);
+        a.Spart[row * 2 + 1] = (float)(sum1 + o1);
       }
     } else {
       const int j = jb * 128 + r;  // basis index of this row

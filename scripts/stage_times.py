@@ -15,7 +15,7 @@ def main():
     M, G, k = (int(a) for a in sys.argv[1:4]) if len(sys.argv) >= 4 else (4992, 3000, 20)
     lik = sys.argv[4] if len(sys.argv) > 4 else "gaussian"
     X = synth.scale_coords(synth.visium_grid() if M == 4992 else synth.random_points(M, 1))
-    Cc = synth.det_kmeans(X, k, 312, iters=30)
+    Cc = synth.det_kmeans(X, k, 312, iters=30) if k <= 30 else bvg.kmeans_centers(X, k, 30, 1, rng=312)
     phi = bvg.basis_build(X, Cc, length_scale_kmeans(Cc), "matern", 2.5)
     Y, _ = synth.expression(phi, G, lik, 312)
     f = bvg.Fit(phi, Y, lik, "fast", "auto", seed=312)
