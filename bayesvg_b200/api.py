@@ -207,8 +207,10 @@ def findSpatiallyVariableFeaturesBayes(sp_obj=None, naive_hvgs=None, likelihood=
     if elbo_samples is None:
         elbo_samples = 50 if algorithm == "pathfinder" else 150
     # accepted by the reference, rejected clearly here (north_star: no fallback)
-    if algorithm != "meanfield":
-        raise NotImplementedError(f"algorithm = '{algorithm}' is not built in bayesvg_b200; only 'meanfield' is.")
+    if algorithm == "pathfinder":
+        raise NotImplementedError("algorithm = 'pathfinder' is not built in bayesvg_b200; 'meanfield' and 'fullrank' are.")
+    if algorithm == "fullrank" and shard is not None:
+        raise NotImplementedError("algorithm = 'fullrank' couples all parameters and cannot be gene-sharded.")
     if opencl_params is not None:
         raise NotImplementedError("opencl.params is meaningless here: the fit always runs on the CUDA device.")
     if lscale_estimator != "kmeans":
@@ -255,7 +257,7 @@ def findSpatiallyVariableFeaturesBayes(sp_obj=None, naive_hvgs=None, likelihood=
         from . import dist
         table, model = dist.fit_sharded(phi, Y, shard, likelihood, precision, engine, cfg, gene_depths=gene_depths)
     else:
-        fit = E.Fit(phi, Y, likelihood, precision, engine, gene_depths=gene_depths, **cfg)
+        fit = E.Fit(phi, Y, likelihood, precision, engine, gene_depths=gene_depths, algorithm=algorithm, **cfg)
         table = fit.run()
         model = None
         if save_model:
@@ -265,7 +267,7 @@ def findSpatiallyVariableFeaturesBayes(sp_obj=None, naive_hvgs=None, likelihood=
         stats = fit.stats()
         fit.close()
         if verbose:
-            print(f"v ADVI: eta = {stats['eta']}, {stats['advi_iters']} iterations, ELBO = {stats['elbo']:.6g}")
+            print(f"v ADVI ({algorithm}): eta = {stats['eta']}, {stats['advi_iters']} iterations, ELBO = {stats['elbo']:.6g}")
     # summarise (:419-432)
     summ = pd.DataFrame(table[:, :7], columns=_SUMMARY_COLS[:7])
     summ.insert(0, "gene", list(naive_hvgs))

@@ -54,10 +54,10 @@ extern "C" void bvg_config_default(bvg_config *c) {
   c->G_total = 0;
   c->elbo_suffstat = 0;
   c->depth_adjust = 0;
+  c->algorithm = BVG_ALG_MEANFIELD;
 }
 
 int lbfgs_run(bvg_fit *f, const double *d_theta0, double *d_out);  // lbfgs.cu
-int launch_summary(bvg_fit *f);                                    // k_summary.cu
 int basis_build_device(cudaStream_t st, const double *d_X, int64_t M, const double *d_C, int k, double ls, int kernel,
                        double nu, double period, double *d_Q, double *d_work);
 void comm_destroy(bvg_fit *f);
@@ -76,6 +76,8 @@ extern "C" int bvg_fit_create(const bvg_config *cfg, bvg_fit **out) {
   if (cfg->engine == BVG_ENGINE_TCGEN05 && cfg->precision != BVG_PREC_FAST) { bvg_set_error("the tcgen05 engine has no fp64 kind; use precision = FAST"); return BVG_ERR_ARG; }
   if (cfg->n_iter < 1 || cfg->elbo_samples < 1 || cfg->eval_elbo < 1 || cfg->adapt_iter < 1 || cfg->n_draws < 2) { bvg_set_error("iteration / sample counts must be positive"); return BVG_ERR_ARG; }
   if (cfg->world_size < 1 || cfg->rank < 0 || cfg->rank >= cfg->world_size) { bvg_set_error("bad rank/world_size"); return BVG_ERR_ARG; }
+  if (cfg->algorithm != BVG_ALG_MEANFIELD && cfg->algorithm != BVG_ALG_FULLRANK) { bvg_set_error("Please provide a valid variational inference approximation algorithm (meanfield and fullrank are built; pathfinder is not)."); return BVG_ERR_ARG; }
+  if (cfg->algorithm == BVG_ALG_FULLRANK && cfg->world_size > 1) { bvg_set_error("algorithm = 'fullrank' couples all parameters and cannot be gene-sharded"); return BVG_ERR_ARG; }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
     cudaGetLastError();
@@ -95,6 +97,7 @@ extern "C" int bvg_fit_create(const bvg_config *cfg, bvg_fit **out) {
 }
 
 static void free_model(bvg_fit *f) {
+  fr_destroy(f);
   tc_destroy(f);
   tcbig_destroy(f);
   suff_destroy(f);
@@ -534,6 +537,23 @@ static int set_phase(bvg_fit *f, double eta) {  // restart the step-size schedul
   return ctl_set(f, h);
 }
 
+// ---- the variational family behind the driver: meanfield (device-resident control block) or fullrank (k_fullrank.cu) ----
+static inline bool is_fr(const bvg_fit *f) { return f->cfg.algorithm == BVG_ALG_FULLRANK; }
+static int fam_reset(bvg_fit *f, const double *d_init) { return is_fr(f) ? fr_reset(f, d_init, true) : advi_reset(f, d_init, true); }
+static int fam_steps(bvg_fit *f, int n) { return is_fr(f) ? fr_steps(f, n) : advi_steps(f, n); }
+static int fam_elbo(bvg_fit *f, int S, double *out) { return is_fr(f) ? fr_elbo(f, S, out) : advi_elbo(f, S, out); }
+static int fam_phase(bvg_fit *f, double eta) {
+  if (is_fr(f)) { fr_set_phase(f, eta); return BVG_OK; }
+  return set_phase(f, eta);
+}
+static int fam_bad(bvg_fit *f, int *bad) {
+  if (is_fr(f)) return fr_bad(f, bad);
+  Ctl hh;
+  BVG_TRY(ctl_get(f, &hh));
+  *bad = hh.bad;
+  return BVG_OK;
+}
+
 static int run_advi(bvg_fit *f, const double *d_init) {
   const bvg_config &c = f->cfg;
   const int64_t D = f->m.L.D;
@@ -550,17 +570,17 @@ static int run_advi(bvg_fit *f, const double *d_init) {
   const double t_adapt = now_s();
   if (eta <= 0) {  // adapt_eta
     static const double seq[5] = {100, 10, 1, 0.1, 0.01};
-    BVG_TRY(advi_reset(f, init, true));
+    BVG_TRY(fam_reset(f, init));
     double e0;
-    BVG_TRY(advi_elbo(f, c.elbo_samples, &e0));
+    BVG_TRY(fam_elbo(f, c.elbo_samples, &e0));
     if (!std::isfinite(e0)) { bvg_set_error("ADVI: the ELBO is not finite at the initial point"); return BVG_ERR_NUMERIC; }
     double ebest = -INFINITY, eta_best = 0;
     for (int q = 0;; ++q) {
-      BVG_TRY(advi_reset(f, init, true));
-      BVG_TRY(set_phase(f, seq[q]));
-      BVG_TRY(advi_steps(f, c.adapt_iter));
+      BVG_TRY(fam_reset(f, init));
+      BVG_TRY(fam_phase(f, seq[q]));
+      BVG_TRY(fam_steps(f, c.adapt_iter));
       double e;
-      BVG_TRY(advi_elbo(f, c.elbo_samples, &e));
+      BVG_TRY(fam_elbo(f, c.elbo_samples, &e));
       if (c.verbose) fprintf(stderr, "[bayesvg_b200] adapt eta = %-6g ELBO = %.6g (init %.6g)\n", seq[q], e, e0);
       if (e < ebest && ebest > e0) break;
       if (q < 4) { ebest = e; eta_best = seq[q]; }
@@ -575,22 +595,22 @@ static int run_advi(bvg_fit *f, const double *d_init) {
   f->st.eta = eta;
   f->st.sec_adapt = now_s() - t_adapt;
   const double t_sga = now_s();
-  BVG_TRY(advi_reset(f, init, true));
-  BVG_TRY(set_phase(f, eta));
+  BVG_TRY(fam_reset(f, init));
+  BVG_TRY(fam_phase(f, eta));
   const int cbn = (int)std::max(0.1 * c.n_iter / c.eval_elbo, 2.0);
   std::vector<double> cb(cbn, 0.0), tmp(cbn);
   int cbc = 0, cbh = 0, conv = 0, it = 0;
   double elbo = 0, elbo_prev;
   while (it < c.n_iter) {
     const int n = std::min(c.eval_elbo - it % c.eval_elbo, c.n_iter - it);
-    BVG_TRY(advi_steps(f, n));
+    BVG_TRY(fam_steps(f, n));
     it += n;
     if (it % c.eval_elbo == 0) {
       elbo_prev = elbo;
-      BVG_TRY(advi_elbo(f, c.elbo_samples, &elbo));
-      Ctl hh;
-      BVG_TRY(ctl_get(f, &hh));
-      if (hh.bad) { bvg_set_error("ADVI: non-finite gradient during stochastic gradient ascent (%d evaluations)", hh.bad); return BVG_ERR_NUMERIC; }
+      BVG_TRY(fam_elbo(f, c.elbo_samples, &elbo));
+      int bad = 0;
+      BVG_TRY(fam_bad(f, &bad));
+      if (bad) { bvg_set_error("ADVI: non-finite gradient during stochastic gradient ascent (%d evaluations)", bad); return BVG_ERR_NUMERIC; }
       const double d = std::fabs((elbo - elbo_prev) / elbo);
       cb[cbh] = d; cbh = (cbh + 1) % cbn; if (cbc < cbn) ++cbc;
       double mean = 0;
@@ -646,7 +666,8 @@ extern "C" int bvg_fit_summarize(bvg_fit *f) {
   BVG_TRY(need_ready(f));
   if (!f->have_vi) { bvg_set_error("no variational fit to summarise"); return BVG_ERR_STATE; }
   const double t0 = now_s();
-  BVG_TRY(launch_summary(f));
+  if (is_fr(f)) BVG_TRY(fr_amplitude_draws(f));
+  BVG_TRY(launch_summary(f, is_fr(f)));
   CUDA_TRY(cudaStreamSynchronize(f->stream));
   f->have_summary = true;
   f->st.sec_draws = now_s() - t0;
@@ -672,13 +693,27 @@ extern "C" int bvg_fit_set_variational(bvg_fit *f, const double *mu, const doubl
   CUDA_TRY(cudaMemcpyAsync(f->m.mu, mu, sizeof(double) * D, cudaMemcpyHostToDevice, f->stream));
   if (omega) CUDA_TRY(cudaMemcpyAsync(f->m.omega, omega, sizeof(double) * D, cudaMemcpyHostToDevice, f->stream));
   else CUDA_TRY(cudaMemsetAsync(f->m.omega, 0, sizeof(double) * D, f->stream));
+  if (is_fr(f)) BVG_TRY(fr_reset(f, nullptr, true));   // full-rank family: L = I; bvg_fit_set_cholesky installs a factor
   CUDA_TRY(cudaStreamSynchronize(f->stream));
+  f->have_vi = true;
+  return BVG_OK;
+}
+extern "C" int bvg_fit_get_cholesky(bvg_fit *f, double *L_packed) {
+  BVG_TRY(need_ready(f));
+  if (!is_fr(f) || !L_packed) { bvg_set_error("bvg_fit_get_cholesky needs algorithm = fullrank and a buffer of D (D + 1) / 2 doubles"); return BVG_ERR_ARG; }
+  return fr_get_cholesky(f, L_packed);
+}
+extern "C" int bvg_fit_set_cholesky(bvg_fit *f, const double *L_packed) {
+  BVG_TRY(need_ready(f));
+  if (!is_fr(f) || !L_packed) { bvg_set_error("bvg_fit_set_cholesky needs algorithm = fullrank and D (D + 1) / 2 doubles"); return BVG_ERR_ARG; }
+  BVG_TRY(fr_set_cholesky(f, L_packed));
   f->have_vi = true;
   return BVG_OK;
 }
 extern "C" int bvg_fit_get_variational(bvg_fit *f, double *mu, double *omega) {
   BVG_TRY(need_ready(f));
   const int64_t D = f->m.L.D;
+  if (is_fr(f)) BVG_TRY(fr_log_diag(f));   // omega := log |L_ii|
   if (mu) CUDA_TRY(cudaMemcpyAsync(mu, f->m.mu, sizeof(double) * D, cudaMemcpyDeviceToHost, f->stream));
   if (omega) CUDA_TRY(cudaMemcpyAsync(omega, f->m.omega, sizeof(double) * D, cudaMemcpyDeviceToHost, f->stream));
   CUDA_TRY(cudaStreamSynchronize(f->stream));
@@ -689,12 +724,17 @@ extern "C" int bvg_fit_advi_steps(bvg_fit *f, int n, double eta, int reset_count
   if (n < 0 || !(eta > 0)) { bvg_set_error("n >= 0 and eta > 0 required"); return BVG_ERR_ARG; }
   Ctl h;
   BVG_TRY(ctl_get(f, &h));
-  if (reset_counters) { memset(&h, 0, sizeof(h)); h.it = 1; BVG_TRY(advi_reset(f, nullptr, false)); }
+  if (reset_counters) {
+    memset(&h, 0, sizeof(h)); h.it = 1;
+    if (is_fr(f)) { BVG_TRY(fr_reset(f, nullptr, false)); fr_set_phase(f, eta); }   // keeps (mu, L), zeroes the step-size history
+    else BVG_TRY(advi_reset(f, nullptr, false));
+  }
   if (h.it < 1) h.it = 1;
   h.eta = eta;
   BVG_TRY(ctl_set(f, h));
+  if (is_fr(f)) BVG_TRY(fr_setup(f));
   CUDA_TRY(cudaEventRecord(f->ev0, f->stream));
-  BVG_TRY(advi_steps(f, n));
+  BVG_TRY(fam_steps(f, n));
   CUDA_TRY(cudaEventRecord(f->ev1, f->stream));
   CUDA_TRY(cudaEventSynchronize(f->ev1));
   if (ms_out) CUDA_TRY(cudaEventElapsedTime(ms_out, f->ev0, f->ev1));
@@ -705,7 +745,7 @@ extern "C" int bvg_fit_elbo(bvg_fit *f, int n_samples, double *elbo_out, float *
   BVG_TRY(need_ready(f));
   if (n_samples < 1 || !elbo_out) { bvg_set_error("bad argument"); return BVG_ERR_ARG; }
   CUDA_TRY(cudaEventRecord(f->ev0, f->stream));
-  BVG_TRY(advi_elbo(f, n_samples, elbo_out));
+  BVG_TRY(fam_elbo(f, n_samples, elbo_out));
   CUDA_TRY(cudaEventRecord(f->ev1, f->stream));
   CUDA_TRY(cudaEventSynchronize(f->ev1));
   if (ms_out) CUDA_TRY(cudaEventElapsedTime(ms_out, f->ev0, f->ev1));
@@ -874,7 +914,8 @@ extern "C" int bvg_fit_posterior_ncol(bvg_fit *f, int64_t *ncol) {
   return BVG_OK;
 }
 // one draw: constrain zeta into column-major out[col][d]; per-block partial sums of eps^2 for log_g__
-__global__ void __launch_bounds__(256) k_store_draw(DevModel m, int64_t n, int64_t d, double *__restrict__ out, double *__restrict__ part) {
+__global__ void __launch_bounds__(256) k_store_draw(DevModel m, int64_t n, int64_t d, double *__restrict__ out, double *__restrict__ part,
+                                                    const double *__restrict__ eta /* full-rank family: the draw's standard normals */) {
   __shared__ double red[8];
   const Layout &L = m.L;
   const int64_t D = L.D, G = m.G, ntp = (m.depth ? 1 : 2) * G;
@@ -886,7 +927,7 @@ __global__ void __launch_bounds__(256) k_store_draw(DevModel m, int64_t n, int64
       const bool pos = (!m.depth && i == L.sigma_beta0) || i == L.sigma_amp || (i >= L.amp && i < L.amp + G) ||
                        (i >= L.sigma_alpha && i < L.sigma_alpha + m.k) || i == L.tail;
       v = pos ? exp(z) : z;
-      const double e = (z - m.mu[i]) * exp(-m.omega[i]);
+      const double e = eta ? eta[i] : (z - m.mu[i]) * exp(-m.omega[i]);
       acc += e * e;
     } else if (!m.depth && i < D + G) {
       v = m.zeta[L.mu_beta0] + exp(m.zeta[L.sigma_beta0]) * m.zeta[L.z_beta0 + (i - D)];   // beta0[g], approxGP.stan:26
@@ -912,6 +953,15 @@ __global__ void k_store_draw_finish(const double *__restrict__ part, int nblk, c
   out[n + d] = lps[d];          // log_p__ = log_prob<propto = false, jacobian = true>(zeta_d)
   out[2 * n + d] = -0.5 * s;    // log_g__ = -1/2 sum eps^2: the draw's log density under the approximation up to a constant [U]
 }
+static const int kStoreBlocks = 148 * 2;
+int fr_store_draw(bvg_fit *f, int64_t n, int64_t d, double *d_out, const double *d_eta) {
+  double *d_part = d_out + (size_t)posterior_ncol(f) * n;
+  k_store_draw<<<kStoreBlocks, 256, 0, f->stream>>>(f->m, n, d, d_out, d_part, d_eta);
+  k_store_draw_finish<<<1, 1, 0, f->stream>>>(d_part, kStoreBlocks, f->m.elbo_lps, n, d, d_out);
+  f->st.kernel_launches += 2;
+  CUDA_TRY(cudaGetLastError());
+  return BVG_OK;
+}
 extern "C" int bvg_fit_get_posterior(bvg_fit *f, int n, double *out) {
   BVG_TRY(need_ready(f));
   if (!f->have_vi) { bvg_set_error("no variational fit to draw from"); return BVG_ERR_STATE; }
@@ -919,7 +969,7 @@ extern "C" int bvg_fit_get_posterior(bvg_fit *f, int n, double *out) {
   if (f->comm_mode) { bvg_set_error("posterior draws of a gene-sharded fit are not built; use bvg_fit_get_draws per shard"); return BVG_ERR_ARG; }
   const int64_t ncol = posterior_ncol(f);
   double *d_out = nullptr, *d_part = nullptr;
-  const int nblk = 148 * 2;
+  const int nblk = kStoreBlocks;
   CUDA_TRY(cudaMalloc(&d_out, sizeof(double) * (size_t)ncol * n + sizeof(double) * nblk));
   d_part = d_out + (size_t)ncol * n;
   if (f->elbo_cap < n) {
@@ -932,10 +982,11 @@ extern "C" int bvg_fit_get_posterior(bvg_fit *f, int n, double *out) {
   int rc = ctl_get(f, &h);
   h.t_draw = 0;
   if (rc == BVG_OK) rc = ctl_set(f, h);
-  for (int d = 0; d < n && rc == BVG_OK; ++d) {
+  if (rc == BVG_OK && is_fr(f)) rc = fr_posterior(f, n, d_out);   // zeta = mu + L eta, ten draws per pass over L
+  for (int d = 0; d < n && rc == BVG_OK && !is_fr(f); ++d) {
     rc = eval_log_prob_device(f, MODE_POST_DRAW, 1, 0, false);
     if (rc != BVG_OK) break;
-    k_store_draw<<<nblk, 256, 0, f->stream>>>(f->m, n, d, d_out, d_part);
+    k_store_draw<<<nblk, 256, 0, f->stream>>>(f->m, n, d, d_out, d_part, nullptr);
     k_store_draw_finish<<<1, 1, 0, f->stream>>>(d_part, nblk, f->m.elbo_lps, n, d, d_out);
     f->st.kernel_launches += 2;
   }

@@ -290,6 +290,7 @@ struct bvg_fit {
   int comm_mode;
   NcclApi *nccl;
   void *comm;
+  void *fr;            // full-rank ADVI state (k_fullrank.cu), allocated on first use
   int elbo_cap;        // capacity of m.elbo_lps
   void *peer_buf;      // this rank's exchange buffer (cudaMalloc, exported with cudaIpcGetMemHandle)
   void *peer_map[BVG_MAX_PEERS];  // peers' buffers opened with cudaIpcOpenMemHandle
@@ -325,6 +326,22 @@ int launch_gene_finish(bvg_fit *f, int mode, int jacobian, int propto, int ahead
 int comm_allreduce(bvg_fit *f, double *buf, int n);          // comm.cu
 int suff_elbo(bvg_fit *f, int S, double *lps_host);          // k_suff.cu: S log densities from sufficient statistics
 void suff_destroy(bvg_fit *f);
+int eval_log_prob_device(bvg_fit *f, int mode, int jac, int propto, bool backward);  // api.cu
+// full-rank ADVI (k_fullrank.cu): q = N(mu, L L^T), L packed lower-triangular in HBM
+int fr_setup(bvg_fit *f);
+void fr_destroy(bvg_fit *f);
+int fr_reset(bvg_fit *f, const double *d_init, bool reset_L);
+void fr_set_phase(bvg_fit *f, double eta);
+int fr_bad(bvg_fit *f, int *bad);
+int fr_steps(bvg_fit *f, int n);
+int fr_elbo(bvg_fit *f, int S, double *out);
+int fr_amplitude_draws(bvg_fit *f);
+int fr_posterior(bvg_fit *f, int n, double *d_out);
+int fr_get_cholesky(bvg_fit *f, double *L_out);
+int fr_set_cholesky(bvg_fit *f, const double *L_in);
+int fr_log_diag(bvg_fit *f);
+int fr_store_draw(bvg_fit *f, int64_t n, int64_t d, double *d_out, const double *d_eta);  // api.cu: one row of the posterior matrix
+int launch_summary(bvg_fit *f, bool given = false);   // k_summary.cu; given: summarise the draws already in f->draws
 // MODE_POST_DRAW: log_p__ of a posterior draw (Philox stream 3, counter ctl->t_draw), stored in elbo_lps[t_draw]
 enum { MODE_GRAD_OUT = 0, MODE_ADVI_UPDATE = 1, MODE_ELBO_DRAW = 2, MODE_LP_ONLY = 3, MODE_POST_DRAW = 4 };
 enum { PREP_NONE = 0, PREP_GRAD = 1, PREP_ELBO = 2, PREP_DRAW = 3 };

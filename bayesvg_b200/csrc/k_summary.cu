@@ -37,7 +37,7 @@ __device__ inline double block_sum(double v, double *red) {
   return s;
 }
 
-__global__ void __launch_bounds__(256) k_summary(DevModel m, int nd, int npad, double *__restrict__ out, double *__restrict__ draws) {
+__global__ void __launch_bounds__(256) k_summary(DevModel m, int nd, int npad, double *__restrict__ out, double *__restrict__ draws, int given) {
   extern __shared__ double sm[];
   __shared__ double red[8];
   double *x = sm, *d = sm + npad;
@@ -48,9 +48,10 @@ __global__ void __launch_bounds__(256) k_summary(DevModel m, int nd, int npad, d
   for (int t = threadIdx.x; t < npad; t += blockDim.x) {
     double v = INFINITY;
     if (t < nd) {
-      v = exp(mu + sd_u * bvg_normal(m.seed, STREAM_DRAW, (uint32_t)t, gi));
+      v = given ? draws[g * nd + t]   // full-rank family: the draws were made by k_fullrank.cu
+                : exp(mu + sd_u * bvg_normal(m.seed, STREAM_DRAW, (uint32_t)t, gi));
       acc += v;
-      if (draws) draws[g * nd + t] = v;
+      if (draws && !given) draws[g * nd + t] = v;
     }
     x[t] = v;
   }
@@ -77,14 +78,14 @@ __global__ void __launch_bounds__(256) k_summary(DevModel m, int nd, int npad, d
   }
 }
 
-int launch_summary(bvg_fit *f) {
+int launch_summary(bvg_fit *f, bool given) {
   const int nd = f->cfg.n_draws;
   int npad = 2;
   while (npad < nd) npad <<= 1;
   const size_t sh = sizeof(double) * 2 * npad;
   if (nd < 2 || sh > 200 * 1024) { bvg_set_error("n_draws = %d unsupported (2..8192)", nd); return BVG_ERR_ARG; }
   CUDA_TRY(cudaFuncSetAttribute(k_summary, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
-  k_summary<<<(unsigned)f->m.G, 256, sh, f->stream>>>(f->m, nd, npad, f->summary, f->draws);
+  k_summary<<<(unsigned)f->m.G, 256, sh, f->stream>>>(f->m, nd, npad, f->summary, f->draws, given ? 1 : 0);
   f->st.kernel_launches++;
   CUDA_TRY(cudaGetLastError());
   return BVG_OK;

@@ -57,11 +57,15 @@ class Fit:
     """gene_depths (length G, log of each gene's total count) selects the depth-adjusted programs
     inst/approxGP2.stan / approxGP3.stan (gene.depth.adjust = TRUE in the reference)."""
 
-    def __init__(self, phi, y, likelihood="gaussian", precision="fast", engine="auto", gene_depths=None, **cfg):
+    def __init__(self, phi, y, likelihood="gaussian", precision="fast", engine="auto", gene_depths=None,
+                 algorithm="meanfield", **cfg):
         lik = {"gaussian": B.GAUSSIAN, "nb": B.NB}.get(likelihood)
         if lik is None:
             raise ValueError("Please provide a valid likelihood.")
-        self.cfg = default_config(likelihood=lik, precision={"fp64": B.PREC_FP64, "fast": B.PREC_FAST}[precision],
+        alg = {"meanfield": B.ALG_MEANFIELD, "fullrank": B.ALG_FULLRANK}.get(algorithm)
+        if alg is None:
+            raise ValueError("Please provide a valid variational inference approximation algorithm.")
+        self.cfg = default_config(algorithm=alg, likelihood=lik, precision={"fp64": B.PREC_FP64, "fast": B.PREC_FAST}[precision],
                                   engine={"auto": B.ENGINE_AUTO, "simt": B.ENGINE_SIMT, "tcgen05": B.ENGINE_TCGEN05}[engine],
                                   depth_adjust=int(gene_depths is not None), **cfg)
         self._h = C.c_void_p()
@@ -150,6 +154,18 @@ class Fit:
         mu, om = np.empty(self.D), np.empty(self.D)
         B.check(B.lib().bvg_fit_get_variational(self._h, _dp(mu), _dp(om)))
         return mu, om
+
+    def get_cholesky(self):
+        """algorithm = "fullrank": the packed row-major lower-triangular factor L of q = N(mu, L L^T)"""
+        out = np.empty(self.D * (self.D + 1) // 2)
+        B.check(B.lib().bvg_fit_get_cholesky(self._h, _dp(out)))
+        return out
+
+    def set_cholesky(self, L):
+        L = np.ascontiguousarray(L, dtype=np.float64)
+        if L.shape != (self.D * (self.D + 1) // 2,):
+            raise ValueError("L must be the packed lower triangle, D (D + 1) / 2 entries")
+        B.check(B.lib().bvg_fit_set_cholesky(self._h, _dp(L)))
 
     def advi_steps(self, n, eta, reset=False):
         ms = C.c_float()

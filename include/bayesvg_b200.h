@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define BVG_ABI_VERSION 1
+#define BVG_ABI_VERSION 2
 
 typedef enum {
   BVG_OK = 0,
@@ -81,7 +81,14 @@ typedef struct {
   /* gene.depth.adjust (:85): intercept beta0 + beta1 * gene_depths[g] (approxGP2/3.stan) instead of the
    * hierarchical per-gene intercept; needs bvg_fit_set_gene_depths */
   int32_t depth_adjust;
+  /* algorithm (:87, :108): BVG_ALG_MEANFIELD (default) or BVG_ALG_FULLRANK -- q = N(mu, L L^T) with the packed
+   * lower-triangular L and its step-size history resident in HBM (D (D + 1) / 2 * 16 bytes: 35 GB at 3,000 genes,
+   * k = 20); single GPU only.  "pathfinder" is not built. */
+  int32_t algorithm;
+  int32_t reserved0;
 } bvg_config;
+
+typedef enum { BVG_ALG_MEANFIELD = 0, BVG_ALG_FULLRANK = 1 } bvg_algorithm;
 
 typedef struct bvg_fit bvg_fit;
 
@@ -146,6 +153,11 @@ int bvg_fit_summarize(bvg_fit *);
 /* finer-grained hooks used by the parity tests and the benchmark */
 int bvg_fit_set_variational(bvg_fit *, const double *mu, const double *omega /* NULL = 0 */);
 int bvg_fit_get_variational(bvg_fit *, double *mu, double *omega);
+/* algorithm = fullrank: the Cholesky factor of the approximation, PACKED lower-triangular row-major (row i starts at
+ * i (i + 1) / 2; D (D + 1) / 2 doubles).  bvg_fit_set_variational installs (mu, L = I) [U: normal_fullrank's start];
+ * bvg_fit_get_variational reports omega = log |L_ii|. */
+int bvg_fit_get_cholesky(bvg_fit *, double *L_packed);
+int bvg_fit_set_cholesky(bvg_fit *, const double *L_packed);
 /* n stochastic-gradient steps (iteration counter continues from the last reset);
  * ms_out (optional) = device time from CUDA events on the engine's stream */
 int bvg_fit_advi_steps(bvg_fit *, int n, double eta, int reset_counters, float *ms_out);

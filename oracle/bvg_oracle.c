@@ -382,30 +382,94 @@ static int cmp_d(const void *a, const void *b) {
   return (x > y) - (x < y);
 }
 
-int bvgo_advi(bvgo_ctx *c, const double *th0, const bvgo_advi_cfg *cfg, double *mu, double *om,
-              bvgo_advi_result *res, double *trace, int trace_cap) {
+/* Full-rank family [U: stan::variational::normal_fullrank]: q = N(mu, L L^T), L lower triangular, stored PACKED row-major
+ * (row i at i (i + 1) / 2).  zeta = mu + L eta; grad mu = g; grad L_ij = g_i eta_j (j <= i) + [i == j] / L_ii (entropy);
+ * entropy = D/2 (1 + log 2 pi) + sum log |L_ii|; the step-size sequence acts elementwise on (mu, L) as for meanfield. */
+static void fr_transform(int64_t D, const double *mu, const double *Lc, const double *eta, double *zeta) {
+  for (int64_t i = 0; i < D; ++i) {
+    const double *row = Lc + (size_t)i * (i + 1) / 2;
+    double z = 0;
+    for (int64_t j = 0; j <= i; ++j) z += row[j] * eta[j];
+    zeta[i] = mu[i] + z;
+  }
+}
+double bvgo_fr_elbo(bvgo_ctx *c, const double *mu, const double *Lc, int S, uint64_t seed, uint32_t t0) {
   const int64_t D = c->L.D;
-  double *hist = (double *)calloc(2 * (size_t)D, sizeof(double));
+  double *zeta = (double *)malloc(sizeof(double) * 2 * D), *eta = zeta + D;
+  double acc = 0;
+  int ok = 0;
+  for (int s = 0; s < S; ++s) {
+    for (int64_t i = 0; i < D; ++i) eta[i] = bvgo_normal(seed, STREAM_ELBO, t0 + s, i);
+    fr_transform(D, mu, Lc, eta, zeta);
+    const double lp = bvgo_log_prob(c, zeta, 1, 0, NULL);
+    if (isfinite(lp)) { acc += lp; ++ok; }
+  }
+  free(zeta);
+  if (ok == 0) return -INFINITY;
+  double ent = 0.5 * (double)D * (1.0 + LOG_TWO_PI);
+  for (int64_t i = 0; i < D; ++i) {
+    const double d = Lc[(size_t)i * (i + 1) / 2 + i];
+    if (d != 0.0) ent += log(fabs(d));
+  }
+  return acc / ok + ent;
+}
+/* hist = [D for mu | D (D + 1) / 2 for L] */
+int bvgo_fr_step(bvgo_ctx *c, double *mu, double *Lc, double *hist, double eta_s, int it, uint64_t seed, uint32_t t) {
+  const int64_t D = c->L.D;
+  double *zeta = (double *)malloc(sizeof(double) * 3 * D), *eps = zeta + D, *g = eps + D;
+  for (int64_t i = 0; i < D; ++i) eps[i] = bvgo_normal(seed, STREAM_GRAD, t, i);
+  fr_transform(D, mu, Lc, eps, zeta);
+  const double lp = bvgo_log_prob(c, zeta, 1, 1, g);
+  int finite = isfinite(lp);
+  for (int64_t i = 0; i < D && finite; ++i) finite = isfinite(g[i]);
+  const double es = eta_s / sqrt((double)it);
+  double *hL = hist + D;
+  for (int64_t i = 0; i < D; ++i) {
+    const double gm = finite ? g[i] : 0.0;
+    double *row = Lc + (size_t)i * (i + 1) / 2, *hrow = hL + (size_t)i * (i + 1) / 2;
+    const double dinv = 1.0 / row[i]; /* entropy term uses L BEFORE the update */
+    for (int64_t j = 0; j <= i; ++j) {
+      const double gl = finite ? g[i] * eps[j] + (j == i ? dinv : 0.0) : 0.0;
+      if (it == 1) hrow[j] += gl * gl; else hrow[j] = 0.9 * hrow[j] + 0.1 * gl * gl;
+      row[j] += es * gl / (1.0 + sqrt(hrow[j]));
+    }
+    if (it == 1) hist[i] += gm * gm; else hist[i] = 0.9 * hist[i] + 0.1 * gm * gm;
+    mu[i] += es * gm / (1.0 + sqrt(hist[i]));
+  }
+  free(zeta);
+  return finite ? 0 : 1;
+}
+static void fam_init(int fullrank, int64_t D, const double *th0, double *mu, double *var) {
+  memcpy(mu, th0, sizeof(double) * D);
+  if (!fullrank) { memset(var, 0, sizeof(double) * D); return; }
+  memset(var, 0, sizeof(double) * (size_t)D * (D + 1) / 2);
+  for (int64_t i = 0; i < D; ++i) var[(size_t)i * (i + 1) / 2 + i] = 1.0; /* L = I */
+}
+static int advi_run(bvgo_ctx *c, const double *th0, const bvgo_advi_cfg *cfg, int fullrank, double *mu, double *om,
+                    bvgo_advi_result *res, double *trace, int trace_cap) {
+  const int64_t D = c->L.D;
+  const size_t nh = fullrank ? (size_t)D + (size_t)D * (D + 1) / 2 : 2 * (size_t)D;
+  double *hist = (double *)calloc(nh, sizeof(double));
+#define FAM_STEP(eta_, it_, t_) (fullrank ? bvgo_fr_step(c, mu, om, hist, eta_, it_, cfg->seed, t_) : bvgo_advi_step(c, mu, om, hist, eta_, it_, cfg->seed, t_))
+#define FAM_ELBO(t_) (fullrank ? bvgo_fr_elbo(c, mu, om, cfg->elbo_samples, cfg->seed, t_) : bvgo_elbo(c, mu, om, cfg->elbo_samples, cfg->seed, t_))
   uint32_t tg = 0, te = 0; /* running draw counters */
   int gevals = 0, eevals = 0;
   double eta = cfg->eta;
   memset(res, 0, sizeof(*res));
   if (eta <= 0) { /* adapt_eta */
     static const double seq[5] = {100, 10, 1, 0.1, 0.01};
-    memcpy(mu, th0, sizeof(double) * D);
-    memset(om, 0, sizeof(double) * D);
-    const double e0 = bvgo_elbo(c, mu, om, cfg->elbo_samples, cfg->seed, te);
+    fam_init(fullrank, D, th0, mu, om);
+    const double e0 = FAM_ELBO(te);
     te += cfg->elbo_samples; ++eevals;
     if (!isfinite(e0)) { free(hist); return -2; }
     double ebest = -INFINITY, e = -INFINITY, eta_best = 0;
     for (int q = 0;; ++q) {
-      memcpy(mu, th0, sizeof(double) * D);
-      memset(om, 0, sizeof(double) * D);
+      fam_init(fullrank, D, th0, mu, om);
       for (int it = 1; it <= cfg->adapt_iter; ++it) {
-        bvgo_advi_step(c, mu, om, hist, seq[q], it, cfg->seed, tg++);
+        FAM_STEP(seq[q], it, tg++);
         ++gevals;
       }
-      e = bvgo_elbo(c, mu, om, cfg->elbo_samples, cfg->seed, te);
+      e = FAM_ELBO(te);
       te += cfg->elbo_samples; ++eevals;
       if (isnan(e)) e = -INFINITY;
       if (e < ebest && ebest > e0) break; /* previous eta stands */
@@ -415,20 +479,19 @@ int bvgo_advi(bvgo_ctx *c, const double *th0, const bvgo_advi_cfg *cfg, double *
         free(hist);
         return -3; /* "All proposed step-sizes failed" */
       }
-      memset(hist, 0, sizeof(double) * 2 * D);
+      memset(hist, 0, sizeof(double) * nh);
     }
     eta = eta_best;
   }
   /* stochastic_gradient_ascent */
-  memcpy(mu, th0, sizeof(double) * D);
-  memset(om, 0, sizeof(double) * D);
-  memset(hist, 0, sizeof(double) * 2 * D);
+  fam_init(fullrank, D, th0, mu, om);
+  memset(hist, 0, sizeof(double) * nh);
   int cbn = (int)fmax(0.1 * cfg->iter / cfg->eval_elbo, 2.0);
   double *cb = (double *)malloc(sizeof(double) * 2 * cbn), *tmp = cb + cbn;
   int cbc = 0, cbh = 0, ntr = 0, conv = 0, it;
   double elbo = 0, elbo_prev;
   for (it = 1; it <= cfg->iter; ++it) {
-    if (bvgo_advi_step(c, mu, om, hist, eta, it, cfg->seed, tg++)) {
+    if (FAM_STEP(eta, it, tg++)) {
       /* main loop: a failing gradient is an error in Stan; report it */
       free(cb); free(hist);
       res->eta = eta; res->iters = it; res->grad_evals = gevals + it;
@@ -436,7 +499,7 @@ int bvgo_advi(bvgo_ctx *c, const double *th0, const bvgo_advi_cfg *cfg, double *
     }
     if (it % cfg->eval_elbo == 0) {
       elbo_prev = elbo;
-      elbo = bvgo_elbo(c, mu, om, cfg->elbo_samples, cfg->seed, te);
+      elbo = FAM_ELBO(te);
       te += cfg->elbo_samples; ++eevals;
       const double d = fabs((elbo - elbo_prev) / elbo);
       cb[cbh] = d; cbh = (cbh + 1) % cbn; if (cbc < cbn) ++cbc;
@@ -461,6 +524,17 @@ int bvgo_advi(bvgo_ctx *c, const double *th0, const bvgo_advi_cfg *cfg, double *
   free(cb);
   free(hist);
   return 0;
+}
+#undef FAM_STEP
+#undef FAM_ELBO
+int bvgo_advi(bvgo_ctx *c, const double *th0, const bvgo_advi_cfg *cfg, double *mu, double *om,
+              bvgo_advi_result *res, double *trace, int trace_cap) {
+  return advi_run(c, th0, cfg, 0, mu, om, res, trace, trace_cap);
+}
+/* algorithm = "fullrank" (:357-364 with algorithm = "fullrank"): Lc receives the packed Cholesky factor */
+int bvgo_advi_fullrank(bvgo_ctx *c, const double *th0, const bvgo_advi_cfg *cfg, double *mu, double *Lc,
+                       bvgo_advi_result *res, double *trace, int trace_cap) {
+  return advi_run(c, th0, cfg, 1, mu, Lc, res, trace, trace_cap);
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -664,6 +738,31 @@ static int cmp_rank(const void *a, const void *b) {
   if (x->v < y->v) return 1;
   return (x->i > y->i) - (x->i < y->i);
 }
+/* statistics of one gene's nd draws x (sorted in place; d = scratch of nd) -> out columns 0..6 */
+static double summarise_gene(double *x, double *d, int nd, int64_t G, int64_t g, double *out) {
+  double mean = 0;
+  for (int t = 0; t < nd; ++t) mean += x[t];
+  mean /= nd;
+  double ss = 0;
+  for (int t = 0; t < nd; ++t) ss += (x[t] - mean) * (x[t] - mean);
+  const double sd = sqrt(ss / (nd - 1));
+  qsort(x, nd, sizeof(double), cmp_d);
+  const double med = quantile7(x, nd, 0.5);
+  for (int t = 0; t < nd; ++t) d[t] = fabs(x[t] - med);
+  qsort(d, nd, sizeof(double), cmp_d);
+  out[0 * G + g] = mean;
+  out[1 * G + g] = med;
+  out[2 * G + g] = sd;
+  out[3 * G + g] = 1.4826 * quantile7(d, nd, 0.5);
+  out[4 * G + g] = quantile7(x, nd, 0.05);
+  out[5 * G + g] = quantile7(x, nd, 0.95);
+  out[6 * G + g] = sd * sd / mean;
+  return mean;
+}
+static void fill_ranks(rank_t *rk, int64_t G, double *out) {
+  qsort(rk, G, sizeof(rank_t), cmp_rank);
+  for (int64_t r = 0; r < G; ++r) out[7 * G + rk[r].i] = (double)(r + 1);
+}
 int bvgo_summary(int model, int64_t G, int k, const double *mu, const double *om, int nd,
                  uint64_t seed, int64_t gene_offset, int64_t G_total, double *out) {
   const layout_t L = make_layout(model, G, k), LG = make_layout(model, G_total, k);
@@ -672,33 +771,38 @@ int bvgo_summary(int model, int64_t G, int k, const double *mu, const double *om
   for (int64_t g = 0; g < G; ++g) {
     const double m = mu[L.amp + g], s = exp(om[L.amp + g]);
     const uint64_t gi = (uint64_t)(LG.amp + gene_offset + g); /* global index of amplitude[g] */
-    double mean = 0;
-    for (int t = 0; t < nd; ++t) {
-      x[t] = exp(m + s * bvgo_normal(seed, STREAM_DRAW, (uint32_t)t, gi));
-      mean += x[t];
-    }
-    mean /= nd;
-    double ss = 0;
-    for (int t = 0; t < nd; ++t) ss += (x[t] - mean) * (x[t] - mean);
-    const double sd = sqrt(ss / (nd - 1));
-    qsort(x, nd, sizeof(double), cmp_d);
-    const double med = quantile7(x, nd, 0.5);
-    for (int t = 0; t < nd; ++t) d[t] = fabs(x[t] - med);
-    qsort(d, nd, sizeof(double), cmp_d);
-    out[0 * G + g] = mean;
-    out[1 * G + g] = med;
-    out[2 * G + g] = sd;
-    out[3 * G + g] = 1.4826 * quantile7(d, nd, 0.5);
-    out[4 * G + g] = quantile7(x, nd, 0.05);
-    out[5 * G + g] = quantile7(x, nd, 0.95);
-    out[6 * G + g] = sd * sd / mean;
-    rk[g].v = mean;
+    for (int t = 0; t < nd; ++t) x[t] = exp(m + s * bvgo_normal(seed, STREAM_DRAW, (uint32_t)t, gi));
+    rk[g].v = summarise_gene(x, d, nd, G, g, out);
     rk[g].i = g;
   }
-  qsort(rk, G, sizeof(rank_t), cmp_rank);
-  for (int64_t r = 0; r < G; ++r) out[7 * G + rk[r].i] = (double)(r + 1);
+  fill_ranks(rk, G, out);
   free(rk);
   free(x);
+  return 0;
+}
+/* algorithm = "fullrank": amplitude[g] = exp(mu_u + sum_j L[u, j] eta_j), eta_j = normal(seed, stream 3, draw t, j) */
+int bvgo_summary_fullrank(int model, int64_t G, int k, const double *mu, const double *Lc, int nd, uint64_t seed,
+                          double *out) {
+  const layout_t L = make_layout(model, G, k);
+  const int64_t nrow = L.amp + G; /* rows of L needed: every row up to the last amplitude */
+  double *x = (double *)malloc(sizeof(double) * 2 * nd), *d = x + nd;
+  double *eta = (double *)malloc(sizeof(double) * (size_t)nd * nrow);
+  rank_t *rk = (rank_t *)malloc(sizeof(rank_t) * G);
+  for (int t = 0; t < nd; ++t)
+    for (int64_t j = 0; j < nrow; ++j) eta[(size_t)t * nrow + j] = bvgo_normal(seed, STREAM_DRAW, (uint32_t)t, (uint64_t)j);
+  for (int64_t g = 0; g < G; ++g) {
+    const int64_t i = L.amp + g;
+    const double *row = Lc + (size_t)i * (i + 1) / 2;
+    for (int t = 0; t < nd; ++t) {
+      double z = 0;
+      for (int64_t j = 0; j <= i; ++j) z += row[j] * eta[(size_t)t * nrow + j];
+      x[t] = exp(mu[i] + z);
+    }
+    rk[g].v = summarise_gene(x, d, nd, G, g, out);
+    rk[g].i = g;
+  }
+  fill_ranks(rk, G, out);
+  free(rk); free(eta); free(x);
   return 0;
 }
 

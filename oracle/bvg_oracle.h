@@ -78,6 +78,15 @@ double bvgo_elbo(bvgo_ctx *, const double *mu, const double *omega, int S, uint6
 int bvgo_advi_step(bvgo_ctx *, double *mu, double *omega, double *hist, double eta, int it,
                    uint64_t seed, uint32_t t);
 
+/* algorithm = "fullrank" [U: stan::variational::normal_fullrank]: q = N(mu, L L^T), L lower triangular, PACKED row-major
+ * (row i starts at i (i + 1) / 2; D (D + 1) / 2 entries), initialised to the identity.  hist = [D | D (D + 1) / 2]. */
+int bvgo_advi_fullrank(bvgo_ctx *, const double *theta_init, const bvgo_advi_cfg *, double *mu, double *L_packed,
+                       bvgo_advi_result *, double *trace, int trace_cap);
+double bvgo_fr_elbo(bvgo_ctx *, const double *mu, const double *L_packed, int S, uint64_t seed, uint32_t t0);
+int bvgo_fr_step(bvgo_ctx *, double *mu, double *L_packed, double *hist, double eta, int it, uint64_t seed, uint32_t t);
+int bvgo_summary_fullrank(int model, int64_t G, int k, const double *mu, const double *L_packed, int n_draws,
+                          uint64_t seed, double *out);
+
 typedef struct {
   int max_iter;      /* mle.iter = 1000 (:89) */
   int history;       /* 25 (:353) */

@@ -74,6 +74,11 @@ def lib():
         L.bvgo_lbfgs.argtypes = [C.c_void_p, _dp, C.POINTER(_LbfgsCfg), _dp, C.POINTER(_LbfgsRes)]
         L.bvgo_summary.argtypes = [C.c_int, C.c_int64, C.c_int, _dp, _dp, C.c_int, C.c_uint64, C.c_int64, C.c_int64, _dp]
         L.bvgo_basis.argtypes = [_dp, C.c_int64, _dp, C.c_int, C.c_double, C.c_int, C.c_double, C.c_double, _dp, _dp]
+        L.bvgo_fr_elbo.restype = C.c_double
+        L.bvgo_fr_elbo.argtypes = [C.c_void_p, _dp, _dp, C.c_int, C.c_uint64, C.c_uint32]
+        L.bvgo_fr_step.argtypes = [C.c_void_p, _dp, _dp, _dp, C.c_double, C.c_int, C.c_uint64, C.c_uint32]
+        L.bvgo_advi_fullrank.argtypes = L.bvgo_advi.argtypes
+        L.bvgo_summary_fullrank.argtypes = [C.c_int, C.c_int64, C.c_int, _dp, _dp, C.c_int, C.c_uint64, _dp]
         L.bvgo_kmeans.argtypes = [_dp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_uint64, _dp, _dp, C.POINTER(C.c_int32)]
         L.bvgo_digamma.restype = C.c_double
         L.bvgo_digamma.argtypes = [C.c_double]
@@ -141,6 +146,37 @@ class Oracle:
         info["trace"] = tr[: res.n_trace].copy()
         return mu, om, info
 
+    # ---- algorithm = "fullrank": L is the PACKED row-major lower-triangular Cholesky factor, D (D + 1) / 2 entries ----
+    def fr_elbo(self, mu, L, S=150, seed=312, t0=0):
+        mu, L = np.ascontiguousarray(mu, dtype=np.float64), np.ascontiguousarray(L, dtype=np.float64)
+        assert L.shape == (self.D * (self.D + 1) // 2,)
+        return lib().bvgo_fr_elbo(self._h, _p(mu), _p(L), S, seed, t0)
+
+    def fr_step(self, mu, L, hist, eta, it, seed, t):
+        """in-place on mu (D), L (packed) and hist (D + D (D + 1) / 2)"""
+        assert hist.shape == (self.D + self.D * (self.D + 1) // 2,)
+        return lib().bvgo_fr_step(self._h, _p(mu), _p(L), _p(hist), eta, it, seed, t)
+
+    def advi_fullrank(self, theta_init, iter=3000, elbo_samples=150, eval_elbo=100, adapt_iter=50,
+                      tol_rel_obj=0.01, eta=0.0, seed=312):
+        cfg = _AdviCfg(iter, elbo_samples, eval_elbo, adapt_iter, tol_rel_obj, eta, seed)
+        res = _AdviRes()
+        th = np.ascontiguousarray(theta_init, dtype=np.float64)
+        mu, L = np.empty(self.D), np.empty(self.D * (self.D + 1) // 2)
+        cap = iter // eval_elbo + 1
+        tr = np.zeros((cap, 4))
+        rc = lib().bvgo_advi_fullrank(self._h, _p(th), C.byref(cfg), _p(mu), _p(L), C.byref(res), _p(tr), cap)
+        info = {f: getattr(res, f) for f, _ in _AdviRes._fields_}
+        info["rc"] = rc
+        info["trace"] = tr[: res.n_trace].copy()
+        return mu, L, info
+
+    def summary_fullrank(self, mu, L, n_draws=1000, seed=312):
+        mu, L = np.ascontiguousarray(mu, dtype=np.float64), np.ascontiguousarray(L, dtype=np.float64)
+        out = np.empty((self.G, 8), order="F")
+        lib().bvgo_summary_fullrank(self.model, self.G, self.k, _p(mu), _p(L), n_draws, seed, _p(out))
+        return out
+
     def lbfgs(self, theta0=None, max_iter=1000, history=25):
         th0 = np.zeros(self.D) if theta0 is None else np.ascontiguousarray(theta0, dtype=np.float64)
         cfg = _LbfgsCfg(max_iter, history, 1e-3, 1e-12, 1e4, 1e-8, 1e7, 1e-8)
@@ -188,6 +224,18 @@ class Oracle:
                 c += G
             out[d, c:c + G] = th[L["amplitude"]:L["amplitude"] + G] ** 2
         return out
+
+
+def pack_tril(Lfull):
+    """dense lower-triangular D x D -> packed row-major (row i at i (i + 1) / 2)"""
+    D = Lfull.shape[0]
+    return np.ascontiguousarray(Lfull[np.tril_indices(D)])
+
+
+def unpack_tril(Lp, D):
+    out = np.zeros((D, D))
+    out[np.tril_indices(D)] = Lp
+    return out
 
 
 def normal(seed, stream, t, i):

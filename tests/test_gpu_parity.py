@@ -410,6 +410,83 @@ def test_full_fit_agrees_with_cpu_restatement(prec, eng):
     f.close()
 
 
+@pytest.mark.parametrize("lik", ["gaussian", "nb"])
+@pytest.mark.parametrize("prec,eng", ENGINES)
+def test_fullrank_trajectory_elbo_and_draws_match_oracle(lik, prec, eng):
+    """algorithm = "fullrank" (R/findSpatiallyVariableFeaturesBayes.R:108, :357-364): q = N(mu, L L^T) [U: normal_fullrank].
+    Same Philox draws on both sides: the iterates (mu, packed L), the ELBO estimate, the amplitude summaries and the
+    posterior matrix must agree with the CPU restatement."""
+    p = make_problem(120, 14, 5, lik, seed=21)
+    o = orc.Oracle(p["phi"], p["y"], lik, nthreads=2)
+    D = o.D
+    nL = D * (D + 1) // 2
+    rng = np.random.default_rng(4)
+    mu0 = rng.normal(0, 0.1, D)
+    f = _fit(p["phi"], p["y"], lik, prec, eng, algorithm="fullrank", seed=77, n_draws=64)
+    f.set_variational(mu0)                                     # L = I
+    assert np.array_equal(f.get_cholesky(), orc.pack_tril(np.eye(D)))
+    mu, L, hist = mu0.copy(), orc.pack_tril(np.eye(D)), np.zeros(D + nL)
+    tol = 1e-9 if prec == "fp64" else 2e-4
+    f.advi_steps(7, 0.1, reset=True)
+    for it in range(1, 8):
+        assert o.fr_step(mu, L, hist, 0.1, it, 77, it - 1) == 0
+    gm, _ = f.get_variational()
+    assert rel_err(gm, mu) <= tol and rel_err(f.get_cholesky(), L) <= tol
+    f.advi_steps(5, 0.1)                                        # continues: it = 8.., draws 7..
+    for it in range(8, 13):
+        o.fr_step(mu, L, hist, 0.1, it, 77, it - 1)
+    gm, gom = f.get_variational()
+    gL = f.get_cholesky()
+    assert rel_err(gm, mu) <= 3 * tol and rel_err(gL, L) <= 3 * tol
+    diag = orc.unpack_tril(gL, D).diagonal()
+    assert np.allclose(gom, np.log(np.abs(diag)), rtol=1e-12)     # get_variational reports omega = log |L_ii|
+    # ELBO / summaries / posterior at exactly the oracle's state
+    f.set_variational(mu)
+    f.set_cholesky(L)
+    e = f.elbo(23)[0]
+    assert e == pytest.approx(o.fr_elbo(mu, L, 23, 77, 0), rel=1e-10 if prec == "fp64" else 2e-6)
+    assert f.elbo(8)[0] == pytest.approx(o.fr_elbo(mu, L, 8, 77, 23), rel=1e-10 if prec == "fp64" else 2e-6)   # counter advanced
+    got, ref = f.summarize(), o.summary_fullrank(mu, L, 64, 77)
+    assert np.allclose(got[:, :7], ref[:, :7], rtol=1e-9) and np.array_equal(got[:, 7], ref[:, 7])
+    P = f.posterior(11)
+    cols = f.posterior_columns()
+    ia = cols.index("amplitude[1]")
+    assert P.shape == (11, len(cols)) and np.allclose(P[:, ia:ia + 14], f.draws()[:11], rtol=1e-12)
+    Lf = orc.unpack_tril(L, D)
+    eta = np.array([[orc.normal(77, 3, d, i) for i in range(D)] for d in range(11)])
+    zeta = mu[None] + eta @ Lf.T
+    assert np.allclose(P[:, 2], -0.5 * (eta ** 2).sum(1), rtol=1e-12)
+    lp_ref = np.array([o.log_prob(z, True, False, grad=False) for z in zeta])
+    assert np.allclose(P[:, 1], lp_ref, rtol=1e-10 if prec == "fp64" else 2e-5)
+    f.close()
+
+
+def test_fullrank_full_fit_and_errors():
+    """whole path with algorithm = "fullrank": L-BFGS init -> adapt -> SGA -> draws (fp64 engine reproduces the oracle's
+    decisions), plus the refusals: gene sharding, pathfinder"""
+    p = make_problem(150, 12, 4, "gaussian", seed=9)
+    o = orc.Oracle(p["phi"], p["y"], "gaussian", nthreads=2)
+    cfg = dict(n_iter=300, mle_iter=50, elbo_samples=20, n_draws=200, seed=312)
+    f = bvg.Fit(p["phi"], p["y"], "gaussian", "fp64", "simt", algorithm="fullrank", **cfg)
+    got = f.run()
+    st = f.stats()
+    th, _ = o.lbfgs(max_iter=50)
+    mu, L, info = o.advi_fullrank(th, iter=300, elbo_samples=20, seed=312)
+    assert info["rc"] == 0 and st["eta"] == info["eta"] and st["advi_iters"] == info["iters"] and st["converged"] == info["converged"]
+    assert st["elbo"] == pytest.approx(info["elbo"], rel=1e-6)
+    ref = o.summary_fullrank(mu, L, 200, 312)
+    assert np.allclose(got[:, :7], ref[:, :7], rtol=1e-5)
+    f.close()
+    with pytest.raises(bvg._lib.BvgError, match="gene-sharded"):
+        bvg.Fit(p["phi"], p["y"], "gaussian", "fast", "auto", algorithm="fullrank", world_size=2, rank=0, G_total=24, gene_offset=0)
+    with pytest.raises(ValueError, match="valid variational inference"):
+        bvg.Fit(p["phi"], p["y"], "gaussian", "fast", "auto", algorithm="pathfinder")
+    fm = bvg.Fit(p["phi"], p["y"], "gaussian", "fast", "auto")
+    with pytest.raises(bvg._lib.BvgError, match="fullrank"):
+        fm.get_cholesky()
+    fm.close()
+
+
 def test_divergent_fit_fails_like_the_reference_algorithm():
     """a problem on which eta adaptation picks 1.0 and stochastic gradient ascent then overflows:
     Stan raises, the oracle returns -4, the engine must return BVG_ERR_NUMERIC (not garbage)"""

@@ -32,7 +32,7 @@ def test_validation_messages_match_the_reference():
     with pytest.raises(ValueError, match="valid variational inference approximation algorithm"):
         f(o, ["gene1"], algorithm="hmc")
     # accepted by the reference, rejected clearly here (no fallback)
-    for kw in (dict(algorithm="fullrank"), dict(algorithm="pathfinder"), dict(opencl_params=[0, 0]),
+    for kw in (dict(algorithm="pathfinder"), dict(opencl_params=[0, 0]),
                dict(lscale_estimator="variogram")):
         with pytest.raises(NotImplementedError):
             f(o, ["gene1"], **kw)
@@ -133,8 +133,8 @@ def test_gene_depths_reach_the_fit_only_with_depth_adjust(monkeypatch):
     seen = {}
 
     class FakeFit:
-        def __init__(self, phi, Y, lik, prec, eng, gene_depths=None, **cfg):
-            seen["depths"], seen["shape"] = gene_depths, Y.shape
+        def __init__(self, phi, Y, lik, prec, eng, gene_depths=None, algorithm="meanfield", **cfg):
+            seen["depths"], seen["shape"], seen["algorithm"] = gene_depths, Y.shape, algorithm
 
         def run(self):
             t = np.ones((seen["shape"][1], 8))
@@ -154,8 +154,8 @@ def test_gene_depths_reach_the_fit_only_with_depth_adjust(monkeypatch):
     api.findSpatiallyVariableFeaturesBayes(o, genes, n_basis_fns=3, gene_depth_adjust=True, verbose=False)
     rows = [list(o.genes).index(g) for g in genes]
     assert np.allclose(seen["depths"], np.log(np.asarray(o.counts)[rows].sum(1)))
-    api.findSpatiallyVariableFeaturesBayes(o, genes, n_basis_fns=3, verbose=False)
-    assert seen["depths"] is None
+    api.findSpatiallyVariableFeaturesBayes(o, genes, n_basis_fns=3, verbose=False, algorithm="FullRank")
+    assert seen["depths"] is None and seen["algorithm"] == "fullrank"       # :107 tolower(algorithm)
 
 
 def test_variational_fit_object_mirrors_cmdstanvb(tmp_path):

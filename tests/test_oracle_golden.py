@@ -105,3 +105,41 @@ def test_summary_against_numpy():
         assert np.allclose(out[g, :7], ref, rtol=1e-12)
     assert sorted(out[:, 7]) == list(range(1, G + 1))
     assert np.all(np.diff(out[np.argsort(out[:, 7]), 0]) <= 0)
+
+
+def test_fullrank_family_restatement():
+    """algorithm = "fullrank" [U: stan::variational::normal_fullrank]: with a diagonal L the family IS meanfield (same ELBO
+    estimate from the same draws); the gradient of the reparameterised objective matches central differences; mu's step
+    equals the meanfield step"""
+    from tests.util import make_problem
+    p = make_problem(60, 6, 3, "gaussian", seed=2)
+    o = orc.Oracle(p["phi"], p["y"])
+    D = o.D
+    rng = np.random.default_rng(0)
+    mu, om = rng.normal(0, 0.2, D), rng.normal(-2, 0.2, D)
+    assert o.fr_elbo(mu, orc.pack_tril(np.diag(np.exp(om))), 20, 5, 3) == pytest.approx(o.elbo(mu, om, 20, 5, 3), rel=1e-13)
+    Lf = np.tril(rng.normal(0, 0.05, (D, D)))
+    Lf[np.diag_indices(D)] = np.exp(om)
+    L0 = orc.pack_tril(Lf)
+    assert np.array_equal(orc.unpack_tril(L0, D), Lf)
+    eta = np.array([orc.normal(9, 1, 4, i) for i in range(D)])
+
+    def obj(Lfull):   # log p(mu + L eta) + log |det L|: the one-draw ELBO estimate as a function of L
+        return o.log_prob(mu + Lfull @ eta, True, True, grad=False) + np.log(np.abs(np.diag(Lfull))).sum()
+
+    mu1, L1, hist = mu.copy(), L0.copy(), np.zeros(D + len(L0))
+    assert o.fr_step(mu1, L1, hist, 1e-3, 1, 9, 4) == 0
+    gabs = np.sqrt(hist)                      # iteration 1: the history IS the squared gradient
+    ii, jj = np.tril_indices(D)
+    for q in (0, 5, 100, 400, len(L0) - 1):
+        Lp, Lm = Lf.copy(), Lf.copy()
+        Lp[ii[q], jj[q]] += 1e-6
+        Lm[ii[q], jj[q]] -= 1e-6
+        fd = (obj(Lp) - obj(Lm)) / 2e-6
+        assert abs(fd) == pytest.approx(gabs[D + q], rel=1e-6)
+        assert np.sign(L1[q] - L0[q]) == np.sign(fd)          # ascent direction
+    g = o.log_prob(mu + Lf @ eta, True, True)[1]
+    assert np.allclose(mu1 - mu, 1e-3 * g / (1 + np.abs(g)), rtol=1e-12)
+    # a short fit runs and its draws are finite
+    m, L, info = o.advi_fullrank(np.zeros(D), iter=200, elbo_samples=20, seed=3)
+    assert info["rc"] == 0 and np.isfinite(info["elbo"]) and np.all(np.isfinite(o.summary_fullrank(m, L, 50, 3)))
