@@ -724,6 +724,7 @@ extern "C" int bvg_fit_advi_steps(bvg_fit *f, int n, double eta, int reset_count
   if (n < 0 || !(eta > 0)) { bvg_set_error("n >= 0 and eta > 0 required"); return BVG_ERR_ARG; }
   Ctl h;
   BVG_TRY(ctl_get(f, &h));
+  if (is_fr(f)) h.t_grad = f->h_t_grad;   // full-rank steps count their gradient draws on the host
   if (reset_counters) {
     memset(&h, 0, sizeof(h)); h.it = 1;
     if (is_fr(f)) { BVG_TRY(fr_reset(f, nullptr, false)); fr_set_phase(f, eta); }   // keeps (mu, L), zeroes the step-size history

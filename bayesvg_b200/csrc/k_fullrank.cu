@@ -23,6 +23,7 @@
 
 #define FR_NB 10        // draws per pass over L
 #define FR_THREADS 256
+#define FR_U 4           // entries per thread and trip in the update pass
 
 struct FrState {
   double *L, *H;        // packed [D (D + 1) / 2]
@@ -67,35 +68,58 @@ __global__ void k_fr_normals(uint64_t seed, uint32_t stream, uint32_t t0, int nb
     out[q] = bvg_normal(seed, stream, t0 + (uint32_t)b, (uint64_t)i);
   }
 }
-// zb[b][i] = mu[i] + sum_{j <= i} L[i][j] etab[b][j] for rows r0 <= i < r1, b < nb <= FR_NB
-__global__ void __launch_bounds__(FR_THREADS) k_fr_gemv(const double *__restrict__ L, int64_t D, int64_t r0, int64_t r1,
-                                                        const double *__restrict__ mu, const double *__restrict__ etab,
-                                                        double *__restrict__ zb, int nb) {
-  __shared__ double red[FR_THREADS / 32][FR_NB];
-  for (int64_t i = r0 + blockIdx.x; i < r1; i += gridDim.x) {
-    const double *row = L + (size_t)i * (size_t)(i + 1) / 2;
-    double acc[FR_NB];
+// zb[b][i] = mu[i] + sum_{j <= i} L[i][j] etab[b][j] for rows r0 <= i < r1, b < nb <= FR_NB.
+// A CTA takes FR_R consecutive rows at a time: a thread loads the nb normals of its column j ONCE and uses them for
+// all FR_R rows (the first version, one row per CTA, re-read them per row: 80 bytes of L2 traffic per 8-byte entry of
+// L, 27 ms per pass at D = 66,045 where HBM allows 3); L is streamed past L2 (ld.global.cs).
+#define FR_R 4
+__global__ void __launch_bounds__(FR_THREADS, 2) k_fr_gemv(const double *__restrict__ L, int64_t D, int64_t r0, int64_t r1,
+                                                           const double *__restrict__ mu, const double *__restrict__ etab,
+                                                           double *__restrict__ zb, int nb) {
+  __shared__ double red[FR_THREADS / 32][FR_R][FR_NB];
+  for (int64_t ib = r0 + (int64_t)blockIdx.x * FR_R; ib < r1; ib += (int64_t)gridDim.x * FR_R) {
+    const int nrow = (int)(r1 - ib < FR_R ? r1 - ib : FR_R);
+    const int64_t imax = ib + nrow - 1;
+    const double *rowp[FR_R];
 #pragma unroll
-    for (int b = 0; b < FR_NB; ++b) acc[b] = 0.0;
-    for (int64_t j = threadIdx.x; j <= i; j += FR_THREADS) {
-      const double l = row[j];
+    for (int r = 0; r < FR_R; ++r) rowp[r] = L + (size_t)(ib + r) * (size_t)(ib + r + 1) / 2;
+    double acc[FR_R][FR_NB];
 #pragma unroll
-      for (int b = 0; b < FR_NB; ++b)
-        if (b < nb) acc[b] = fma(l, etab[(size_t)b * D + j], acc[b]);
+    for (int r = 0; r < FR_R; ++r)
+#pragma unroll
+      for (int b = 0; b < FR_NB; ++b) acc[r][b] = 0.0;
+    for (int64_t j = threadIdx.x; j <= imax; j += FR_THREADS) {
+      double l[FR_R];
+#pragma unroll
+      for (int r = 0; r < FR_R; ++r) l[r] = (r < nrow && j <= ib + r) ? __ldcs(rowp[r] + j) : 0.0;
+      double e[FR_NB];
+#pragma unroll
+      for (int b = 0; b < FR_NB; ++b) e[b] = b < nb ? etab[(size_t)b * D + j] : 0.0;
+#pragma unroll
+      for (int r = 0; r < FR_R; ++r)
+#pragma unroll
+        for (int b = 0; b < FR_NB; ++b) acc[r][b] = fma(l[r], e[b], acc[r][b]);
     }
 #pragma unroll
-    for (int b = 0; b < FR_NB; ++b) acc[b] = warp_sum(acc[b]);
+    for (int r = 0; r < FR_R; ++r)
+#pragma unroll
+      for (int b = 0; b < FR_NB; ++b) acc[r][b] = warp_sum(acc[r][b]);
     __syncthreads();
     if ((threadIdx.x & 31) == 0) {
 #pragma unroll
-      for (int b = 0; b < FR_NB; ++b) red[threadIdx.x >> 5][b] = acc[b];
+      for (int r = 0; r < FR_R; ++r)
+#pragma unroll
+        for (int b = 0; b < FR_NB; ++b) red[threadIdx.x >> 5][r][b] = acc[r][b];
     }
     __syncthreads();
-    if (threadIdx.x < nb) {
-      double s = 0;
+    if (threadIdx.x < FR_R * FR_NB) {
+      const int r = threadIdx.x / FR_NB, bb = threadIdx.x - r * FR_NB;
+      if (r < nrow && bb < nb) {
+        double s = 0;
 #pragma unroll
-      for (int w = 0; w < FR_THREADS / 32; ++w) s += red[w][threadIdx.x];
-      zb[(size_t)threadIdx.x * D + i] = mu[i] + s;
+        for (int w = 0; w < FR_THREADS / 32; ++w) s += red[w][r][bb];
+        zb[(size_t)bb * D + ib + r] = mu[ib + r] + s;
+      }
     }
   }
 }
@@ -126,14 +150,31 @@ __global__ void __launch_bounds__(FR_THREADS) k_fr_update(double *__restrict__ L
     __syncthreads();
     const double gi = ok ? g[i] : 0.0, dinv = s_dinv;
     double acc = 0.0;
-    for (int64_t j = threadIdx.x; j <= i; j += FR_THREADS) {
-      const double gl = ok ? gi * e0[j] + (j == i ? dinv : 0.0) : 0.0;
-      double h = hrow[j];
-      h = first ? h + gl * gl : 0.9 * h + 0.1 * gl * gl;
-      hrow[j] = h;
-      const double l = row[j] + es * gl / (1.0 + sqrt(h));
-      row[j] = l;
-      acc = fma(l, e1[j], acc);
+    // FR_U independent entries per thread and trip: enough loads in flight to cover the HBM latency (one entry per
+    // trip ran at 2.9 TB/s); L and H stream past L2 (ld/st.global.cs) so that Y and the draws stay resident there
+    for (int64_t jb = threadIdx.x; jb <= i; jb += FR_U * FR_THREADS) {
+      double hv[FR_U], lv[FR_U], a0[FR_U], a1[FR_U];
+#pragma unroll
+      for (int u = 0; u < FR_U; ++u) {
+        const int64_t j = jb + u * FR_THREADS;
+        const bool in = j <= i;
+        hv[u] = in ? __ldcs(hrow + j) : 0.0;
+        lv[u] = in ? __ldcs(row + j) : 0.0;
+        a0[u] = in ? e0[j] : 0.0;
+        a1[u] = in ? e1[j] : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < FR_U; ++u) {
+        const int64_t j = jb + u * FR_THREADS;
+        if (j <= i) {
+          const double gl = ok ? gi * a0[u] + (j == i ? dinv : 0.0) : 0.0;
+          const double h = first ? hv[u] + gl * gl : 0.9 * hv[u] + 0.1 * gl * gl;
+          __stcs(hrow + j, h);
+          const double l = lv[u] + es * gl / (1.0 + sqrt(h));
+          __stcs(row + j, l);
+          acc = fma(l, a1[u], acc);
+        }
+      }
     }
     acc = fr_block_sum(acc, red);
     if (threadIdx.x == 0) {
@@ -165,6 +206,19 @@ __global__ void k_fr_amp_draws(const double *__restrict__ zb, int64_t D, int64_t
 }
 
 static int fr_grid(int64_t rows) { return (int)std::min<int64_t>(rows, 148 * 4); }
+// persistent grid of the update pass: exactly the CTAs that are resident at once (rows are dealt round-robin, so a
+// partial second wave -- 592 CTAs on 444 slots in the first version -- leaves two thirds of the machine idle at the end)
+static int fr_grid_update(int64_t rows) {
+  static int per_sm = 0, nsm = 148;
+  if (!per_sm) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fr_update, FR_THREADS, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
+  }
+  return (int)std::min<int64_t>(rows, (int64_t)nsm * per_sm);
+}
+static int fr_grid_gemv(int64_t rows) { return (int)std::min<int64_t>((rows + FR_R - 1) / FR_R, 148 * 2); }
 
 int fr_setup(bvg_fit *f) {
   if (f->fr) return BVG_OK;
@@ -228,7 +282,7 @@ int fr_steps(bvg_fit *f, int n) {
   const int64_t D = f->m.L.D;
   if (n <= 0) return BVG_OK;
   k_fr_normals<<<148, 256, 0, f->stream>>>(f->m.seed, STREAM_GRAD, f->h_t_grad, 1, D, s->eta[0]);
-  k_fr_gemv<<<fr_grid(D), FR_THREADS, 0, f->stream>>>(s->L, D, 0, D, f->m.mu, s->eta[0], f->m.zeta, 1);
+  k_fr_gemv<<<fr_grid_gemv(D), FR_THREADS, 0, f->stream>>>(s->L, D, 0, D, f->m.mu, s->eta[0], f->m.zeta, 1);
   CUDA_TRY(cudaGetLastError());
   f->st.kernel_launches += 2;
   s->cur = 0;
@@ -237,7 +291,7 @@ int fr_steps(bvg_fit *f, int n) {
     k_fr_check<<<1, 1024, 0, f->stream>>>(f->m.grad, D, f->m.ctl, s->ok);
     f->h_t_grad += 1;
     k_fr_normals<<<148, 256, 0, f->stream>>>(f->m.seed, STREAM_GRAD, f->h_t_grad, 1, D, s->eta[s->cur ^ 1]);
-    k_fr_update<<<fr_grid(D), FR_THREADS, 0, f->stream>>>(s->L, s->H, D, f->m.grad, s->eta[s->cur], s->eta[s->cur ^ 1], f->m.mu,
+    k_fr_update<<<fr_grid_update(D), FR_THREADS, 0, f->stream>>>(s->L, s->H, D, f->m.grad, s->eta[s->cur], s->eta[s->cur ^ 1], f->m.mu,
                                                          f->m.hist, f->m.zeta, s->ok, s->it == 1 ? 1 : 0, s->step / sqrt((double)s->it));
     CUDA_TRY(cudaGetLastError());
     f->st.kernel_launches += 3;
@@ -269,7 +323,7 @@ static int fr_log_probs(bvg_fit *f, uint32_t stream, uint32_t t0, int S, std::ve
   for (int b0 = 0; b0 < S && rc == BVG_OK; b0 += FR_NB) {
     const int nb = std::min(FR_NB, S - b0);
     k_fr_normals<<<148 * 2, 256, 0, f->stream>>>(f->m.seed, stream, t0 + (uint32_t)b0, nb, D, s->etab);
-    k_fr_gemv<<<fr_grid(D), FR_THREADS, 0, f->stream>>>(s->L, D, 0, D, f->m.mu, s->etab, s->zb, nb);
+    k_fr_gemv<<<fr_grid_gemv(D), FR_THREADS, 0, f->stream>>>(s->L, D, 0, D, f->m.mu, s->etab, s->zb, nb);
     f->st.kernel_launches += 2;
     for (int b = 0; b < nb && rc == BVG_OK; ++b) {
       f->m.zeta = s->zb + (size_t)b * D;   // the launchers copy the model descriptor by value
@@ -328,7 +382,7 @@ int fr_amplitude_draws(bvg_fit *f) {
   for (int t0 = 0; t0 < nd; t0 += FR_NB) {
     const int nb = std::min(FR_NB, nd - t0);
     k_fr_normals<<<148 * 2, 256, 0, f->stream>>>(f->m.seed, STREAM_DRAW, (uint32_t)t0, nb, D, s->etab);
-    k_fr_gemv<<<fr_grid(G), FR_THREADS, 0, f->stream>>>(s->L, D, amp, amp + G, f->m.mu, s->etab, s->zb, nb);
+    k_fr_gemv<<<fr_grid_gemv(G), FR_THREADS, 0, f->stream>>>(s->L, D, amp, amp + G, f->m.mu, s->etab, s->zb, nb);
     k_fr_amp_draws<<<148, 256, 0, f->stream>>>(s->zb, D, amp, G, nd, t0, nb, f->draws);
     f->st.kernel_launches += 3;
   }
