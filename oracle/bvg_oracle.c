@@ -542,9 +542,9 @@ int bvgo_advi_fullrank(bvgo_ctx *c, const double *th0, const bvgo_advi_cfg *cfg,
  * R/findSpatiallyVariableFeaturesBayes.R:346-353 (init = 0, jacobian = FALSE, iter = mle.iter,
  * history_size = 25).  Minimises f = -log_prob<propto=false, jacobian=false>.
  * ---------------------------------------------------------------------------------------- */
-typedef struct { bvgo_ctx *c; int64_t D; int fevals; } fobj;
+typedef struct { bvgo_ctx *c; int64_t D; int fevals; int jac, propto; } fobj;
 static int feval(fobj *o, const double *x, double *f, double *g) {
-  const double lp = bvgo_log_prob(o->c, x, 0, 0, g);
+  const double lp = bvgo_log_prob(o->c, x, o->jac, o->propto, g);
   o->fevals++;
   *f = -lp;
   int ok = isfinite(lp);
@@ -633,11 +633,16 @@ static int wolfe_ls(fobj *o, double *alpha, double *x1, double *f1, double *g1, 
   }
 }
 
-int bvgo_lbfgs(bvgo_ctx *c, const double *th0, const bvgo_lbfgs_cfg *cfg, double *out,
-               bvgo_lbfgs_result *res) {
+typedef struct { double v; int64_t i; } rank_t;
+static double summarise_gene(double *x, double *d, int nd, int64_t G, int64_t g, double *out);
+static void fill_ranks(rank_t *rk, int64_t G, double *out);
+/* cb (optional): called with the initial point (it = 0) and after every accepted iterate; x, g = grad of f = -lp */
+typedef void (*lbfgs_cb)(void *user, int it, const double *x, const double *g, double f);
+static int lbfgs_core(bvgo_ctx *c, const double *th0, const bvgo_lbfgs_cfg *cfg, int jac, int propto, double *out,
+                      bvgo_lbfgs_result *res, lbfgs_cb cb, void *user) {
   const int64_t D = c->L.D;
   const int m = cfg->history;
-  fobj o = {c, D, 0};
+  fobj o = {c, D, 0, jac, propto};
   double *buf = (double *)malloc(sizeof(double) * D * (size_t)(8 + 2 * m));
   double *xk = buf, *gk = xk + D, *pk = gk + D, *xk1 = pk + D, *gk1 = xk1 + D, *pk1 = gk1 + D,
          *sk = pk1 + D, *yk = sk + D, *Sh = yk + D, *Yh = Sh + (size_t)m * D;
@@ -647,6 +652,7 @@ int bvgo_lbfgs(bvgo_ctx *c, const double *th0, const bvgo_lbfgs_cfg *cfg, double
   memcpy(xk, th0, sizeof(double) * D);
   int term = 0, it = 0;
   if (feval(&o, xk, &fk, gk)) { free(buf); free(rho); return -1; }
+  if (cb) cb(user, 0, xk, gk, fk);
   for (int64_t i = 0; i < D; ++i) pk[i] = -gk[i];
   const double eps = DBL_EPSILON;
   while (!term) {
@@ -670,6 +676,7 @@ int bvgo_lbfgs(bvgo_ctx *c, const double *th0, const bvgo_lbfgs_cfg *cfg, double
     { double t = fk; fk = fk1; fk1 = t; }
     { double *t; t = xk; xk = xk1; xk1 = t; t = gk; gk = gk1; gk1 = t; t = pk; pk = pk1; pk1 = t; }
     for (int64_t i = 0; i < D; ++i) { sk[i] = xk[i] - xk1[i]; yk[i] = gk[i] - gk1[i]; }
+    if (cb) cb(user, it, xk, gk, fk);
     const double gnorm = sqrt(dot(gk, gk, D)), snorm = sqrt(dot(sk, sk, D));
     const double skyk = dot(sk, yk, D), ykyk = dot(yk, yk, D);
     if (resetB) {
@@ -718,6 +725,396 @@ int bvgo_lbfgs(bvgo_ctx *c, const double *th0, const bvgo_lbfgs_cfg *cfg, double
   free(rho);
   return 0;
 }
+int bvgo_lbfgs(bvgo_ctx *c, const double *th0, const bvgo_lbfgs_cfg *cfg, double *out, bvgo_lbfgs_result *res) {
+  return lbfgs_core(c, th0, cfg, 0, 0, out, res, NULL, NULL);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Pathfinder [U: stan::services::pathfinder::pathfinder_lbfgs_single / _multi; Zhang, Carpenter, Gelman, Vehtari 2022],
+ * invoked by R/findSpatiallyVariableFeaturesBayes.R:366-375: init = 0.01, num_paths = n.cores, max_lbfgs_iters = 200,
+ * num_elbo_draws = elbo.samples (50), history_size = 25, draws = n.draws (PSIS draws); single-path draws 1000 [U].
+ * Along the L-BFGS path of f = -log_prob<propto, jacobian = true>, every iterate (x, g) gets a Gaussian approximation
+ * N(xc, Sigma) from the last <= J curvature pairs (S, Y) that pass check_curve and the recursively updated diagonal
+ * alpha (form_diag):  Sigma = diag(alpha) + [diag(alpha) Y | C'] [[0, I], [I, Y' diag(alpha) Y + Dk]] [...]',
+ * C = -R^{-1} S' (R = upper triangle of S'Y, Dk = its diagonal), xc = x - Sigma g.  Sampling goes through the thin
+ * factorisation W' = Q Rk of W = [Y diag(sqrt alpha); C diag(1 / sqrt alpha)] and La = chol(Rk Mk Rk' + I):
+ * phi = xc + sqrt(alpha) (Q La Q'u + u - Q Q'u), log q = -log|La| - 1/2 sum log alpha - 1/2 (u'u + D log 2 pi).
+ * The iterate with the largest ELBO estimate (num_elbo_draws draws) supplies the path's draws; several paths are
+ * combined by Pareto-smoothed importance resampling on lp - log q.
+ * Rk comes from a Cholesky factorisation of W W' here (Stan: Householder QR of W'): same Q up to column signs.
+ * ---------------------------------------------------------------------------------------- */
+double bvgo_uniform(uint64_t seed, uint32_t stream, uint32_t t, uint64_t i) {
+  uint32_t ctr[4] = {(uint32_t)i, (uint32_t)(i >> 32), t, stream};
+  uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)}, o[4];
+  bvgo_philox4x32_10(ctr, key, o);
+  return ((double)(((uint64_t)o[0] << 21) | (o[2] >> 11)) + 0.5) * (1.0 / 9007199254740992.0);
+}
+enum { STREAM_PF_INIT = 5, STREAM_PF_ELBO = 6, STREAM_PF_DRAW = 7, STREAM_PF_PSIS = 8 };
+static int chol_lower(double *A, int n) { /* in place, row-major; returns 1 if not positive definite */
+  for (int j = 0; j < n; ++j) {
+    double d = A[j * n + j];
+    for (int q = 0; q < j; ++q) d -= A[j * n + q] * A[j * n + q];
+    if (!(d > 0.0) || !isfinite(d)) return 1;
+    d = sqrt(d);
+    A[j * n + j] = d;
+    for (int i = j + 1; i < n; ++i) {
+      double v = A[i * n + j];
+      for (int q = 0; q < j; ++q) v -= A[i * n + q] * A[j * n + q];
+      A[i * n + j] = v / d;
+    }
+    for (int i = 0; i < j; ++i) A[i * n + j] = 0.0;
+  }
+  return 0;
+}
+typedef struct {
+  int n;                 /* curvature pairs in use */
+  double *W;             /* [2n][D] */
+  double *xc, *alpha;    /* [D] */
+  double Lc[50 * 50];    /* lower Cholesky factor of W W' (Rk = Lc') */
+  double La[50 * 50];    /* chol(Rk Mk Rk' + I), lower */
+  double logdet;         /* sum log La_ii + 1/2 sum log alpha */
+  int ok;
+} pf_approx;
+typedef struct {
+  bvgo_ctx *c; int64_t D; const bvgo_pf_cfg *cfg; int path;
+  double *alpha, *Sh, *Yh, *xprev, *gprev, *work; int nh, head;
+  pf_approx cur, best; double best_elbo; int best_iter; int n_iter;
+  double *elbos; int elbo_cap;
+} pf_state;
+static void pf_build(pf_state *st, const double *x, const double *g) {
+  const int64_t D = st->D;
+  const int J = st->cfg->history, n = st->nh, n2 = 2 * n;
+  pf_approx *a = &st->cur;
+  a->n = n; a->ok = 0;
+  memcpy(a->alpha, st->alpha, sizeof(double) * D);
+  const double *al = st->alpha;
+  /* history rows, oldest first */
+  const double *S[25], *Y[25];
+  for (int q = 0; q < n; ++q) { const int h = (st->head - n + q + 2 * J) % J; S[q] = st->Sh + (size_t)h * D; Y[q] = st->Yh + (size_t)h * D; }
+  double SY[25 * 25], YaY[25 * 25], Rinv[25 * 25];
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) {
+      double sy = 0, yy = 0;
+      for (int64_t d = 0; d < D; ++d) { sy += S[i][d] * Y[j][d]; yy += Y[i][d] * al[d] * Y[j][d]; }
+      SY[i * n + j] = sy; YaY[i * n + j] = yy;
+    }
+  /* Rinv: inverse of the upper triangle of SY (back substitution, column by column) */
+  for (int col = 0; col < n; ++col)
+    for (int i = n - 1; i >= 0; --i) {
+      double v = i == col ? 1.0 : 0.0;
+      for (int q = i + 1; q < n; ++q) v -= SY[i * n + q] * Rinv[q * n + col];
+      Rinv[i * n + col] = i > col ? 0.0 : v / SY[i * n + i];
+    }
+  /* W = [Y sqrt(alpha); C / sqrt(alpha)], C = -Rinv S */
+  double *W = a->W;
+  for (int i = 0; i < n; ++i)
+    for (int64_t d = 0; d < D; ++d) {
+      W[(size_t)i * D + d] = Y[i][d] * sqrt(al[d]);
+      double cv = 0;
+      for (int q = i; q < n; ++q) cv -= Rinv[i * n + q] * S[q][d];
+      W[(size_t)(n + i) * D + d] = cv / sqrt(al[d]);
+    }
+  /* Gram, Rk, Mk, La */
+  double *G = a->Lc, Mk[50 * 50], T[50 * 50], H[50 * 50];
+  for (int i = 0; i < n2; ++i)
+    for (int j = 0; j <= i; ++j) {
+      double v = 0;
+      for (int64_t d = 0; d < D; ++d) v += W[(size_t)i * D + d] * W[(size_t)j * D + d];
+      G[i * n2 + j] = G[j * n2 + i] = v;
+    }
+  if (n2 > 0 && chol_lower(G, n2)) return; /* linearly dependent history: no approximation at this iterate */
+  memset(Mk, 0, sizeof(Mk));
+  for (int i = 0; i < n; ++i) {
+    Mk[i * n2 + n + i] = Mk[(n + i) * n2 + i] = 1.0;
+    for (int j = 0; j < n; ++j) Mk[(n + i) * n2 + n + j] = YaY[i * n + j] + (i == j ? SY[i * n + i] : 0.0);
+  }
+  /* H = Rk Mk Rk' + I with Rk = Lc' :  H = Lc' Mk Lc + I */
+  for (int i = 0; i < n2; ++i)
+    for (int j = 0; j < n2; ++j) {
+      double v = 0;
+      for (int q = 0; q < n2; ++q) v += Mk[i * n2 + q] * G[q * n2 + j]; /* (Mk Lc)_ij */
+      T[i * n2 + j] = v;
+    }
+  for (int i = 0; i < n2; ++i)
+    for (int j = 0; j < n2; ++j) {
+      double v = i == j ? 1.0 : 0.0;
+      for (int q = 0; q < n2; ++q) v += G[q * n2 + i] * T[q * n2 + j]; /* (Lc' T)_ij */
+      H[i * n2 + j] = v;
+    }
+  for (int i = 0; i < n2; ++i) for (int j = 0; j < i; ++j) { const double v = 0.5 * (H[i * n2 + j] + H[j * n2 + i]); H[i * n2 + j] = H[j * n2 + i] = v; }
+  memcpy(a->La, H, sizeof(double) * n2 * n2);
+  if (n2 > 0 && chol_lower(a->La, n2)) return;
+  a->logdet = 0;
+  for (int i = 0; i < n2; ++i) a->logdet += log(a->La[i * n2 + i]);
+  double sl = 0;
+  for (int64_t d = 0; d < D; ++d) sl += log(al[d]);
+  a->logdet += 0.5 * sl;
+  /* xc = x - Sigma g:  t1 = C g, t2 = Y (alpha g), v = t2 + (YaY + Dk) t1; Sigma g = alpha g + alpha (Y' t1) + C' v */
+  double t1[25], t2[25], v[25];
+  for (int i = 0; i < n; ++i) {
+    double a1 = 0, a2 = 0;
+    for (int64_t d = 0; d < D; ++d) { a1 += W[(size_t)(n + i) * D + d] * sqrt(al[d]) * g[d]; a2 += Y[i][d] * al[d] * g[d]; }
+    t1[i] = a1; t2[i] = a2;
+  }
+  for (int i = 0; i < n; ++i) {
+    double s = t2[i];
+    for (int j = 0; j < n; ++j) s += (YaY[i * n + j] + (i == j ? SY[i * n + i] : 0.0)) * t1[j];
+    v[i] = s;
+  }
+  for (int64_t d = 0; d < D; ++d) {
+    double yt = 0, cv = 0;
+    for (int i = 0; i < n; ++i) { yt += Y[i][d] * t1[i]; cv += W[(size_t)(n + i) * D + d] * sqrt(al[d]) * v[i]; }
+    a->xc[d] = x[d] - (al[d] * g[d] + al[d] * yt + cv);
+  }
+  a->ok = 1;
+}
+/* one draw from an approximation: u given (length D) -> phi, returns log q */
+static double pf_draw(const pf_approx *a, int64_t D, const double *u, double *phi) {
+  const int n2 = 2 * a->n;
+  double wu[50], u1[50], z[50], cc[50];
+  double uu = 0;
+  for (int64_t d = 0; d < D; ++d) uu += u[d] * u[d];
+  for (int i = 0; i < n2; ++i) {
+    double s = 0;
+    for (int64_t d = 0; d < D; ++d) s += a->W[(size_t)i * D + d] * u[d];
+    wu[i] = s;
+  }
+  /* u1 = Rk^{-T} (W u) = Lc^{-1} (W u) */
+  for (int i = 0; i < n2; ++i) {
+    double s = wu[i];
+    for (int q = 0; q < i; ++q) s -= a->Lc[i * n2 + q] * u1[q];
+    u1[i] = s / a->Lc[i * n2 + i];
+  }
+  for (int i = 0; i < n2; ++i) { /* z = La u1 - u1 */
+    double s = -u1[i];
+    for (int q = 0; q <= i; ++q) s += a->La[i * n2 + q] * u1[q];
+    z[i] = s;
+  }
+  /* cc = Rk^{-1} z = Lc^{-T} z */
+  for (int i = n2 - 1; i >= 0; --i) {
+    double s = z[i];
+    for (int q = i + 1; q < n2; ++q) s -= a->Lc[q * n2 + i] * cc[q];
+    cc[i] = s / a->Lc[i * n2 + i];
+  }
+  for (int64_t d = 0; d < D; ++d) {
+    double s = u[d];
+    for (int i = 0; i < n2; ++i) s += a->W[(size_t)i * D + d] * cc[i];
+    phi[d] = a->xc[d] + sqrt(a->alpha[d]) * s;
+  }
+  return -a->logdet - 0.5 * (uu + (double)D * LOG_TWO_PI);
+}
+static void pf_copy(pf_approx *dst, const pf_approx *src, int64_t D) {
+  dst->n = src->n; dst->logdet = src->logdet; dst->ok = src->ok;
+  memcpy(dst->W, src->W, sizeof(double) * 2 * (size_t)src->n * D);
+  memcpy(dst->xc, src->xc, sizeof(double) * D);
+  memcpy(dst->alpha, src->alpha, sizeof(double) * D);
+  memcpy(dst->Lc, src->Lc, sizeof(src->Lc));
+  memcpy(dst->La, src->La, sizeof(src->La));
+}
+static void pf_cb(void *user, int it, const double *x, const double *g, double f) {
+  pf_state *st = (pf_state *)user;
+  const int64_t D = st->D;
+  const int J = st->cfg->history;
+  (void)f;
+  if (it > 0) {
+    double *s = st->work, *y = s + D;
+    double ys = 0, yy = 0;
+    for (int64_t d = 0; d < D; ++d) { s[d] = x[d] - st->xprev[d]; y[d] = g[d] - st->gprev[d]; ys += y[d] * s[d]; yy += y[d] * y[d]; }
+    if (ys > 0 && fabs(yy / ys) <= 1e12) { /* check_curve */
+      double yay = 0, sias = 0;
+      for (int64_t d = 0; d < D; ++d) { yay += y[d] * st->alpha[d] * y[d]; sias += s[d] * s[d] / st->alpha[d]; }
+      for (int64_t d = 0; d < D; ++d) { /* form_diag */
+        const double a = st->alpha[d], sa = s[d] / a;
+        st->alpha[d] = ys / (yay / a + y[d] * y[d] - (yay / sias) * sa * sa);
+      }
+      memcpy(st->Sh + (size_t)st->head * D, s, sizeof(double) * D);
+      memcpy(st->Yh + (size_t)st->head * D, y, sizeof(double) * D);
+      st->head = (st->head + 1) % J;
+      if (st->nh < J) ++st->nh;
+    }
+    pf_build(st, x, g);
+    double elbo = -INFINITY;
+    if (st->cur.ok) {
+      const int K = st->cfg->num_elbo_draws;
+      double *u = st->work, *phi = u + D, acc = 0;
+      int fin = 1;
+      for (int k = 0; k < K && fin; ++k) {
+        const uint32_t t = ((uint32_t)st->path << 24) | ((uint32_t)it << 12) | (uint32_t)k;
+        for (int64_t d = 0; d < D; ++d) u[d] = bvgo_normal(st->cfg->seed, STREAM_PF_ELBO, t, d);
+        const double lq = pf_draw(&st->cur, D, u, phi);
+        const double lp = bvgo_log_prob(st->c, phi, 1, 1, NULL);
+        if (!isfinite(lp) || !isfinite(lq)) fin = 0; else acc += lp - lq;
+      }
+      if (fin) elbo = acc / K;
+    }
+    if (it < st->elbo_cap) st->elbos[it] = elbo;
+    if (elbo > st->best_elbo) { st->best_elbo = elbo; st->best_iter = it; pf_copy(&st->best, &st->cur, D); }
+    st->n_iter = it;
+  }
+  memcpy(st->xprev, x, sizeof(double) * D);
+  memcpy(st->gprev, g, sizeof(double) * D);
+}
+static void pf_alloc(pf_approx *a, int64_t D, int J);
+/* test hook: the approximation built from given (alpha, S, Y [n][D] oldest first, x, g); nu draws u [nu][D] -> phi, log q */
+int bvgo_pf_approx_test(int64_t D, int n, const double *alpha, const double *S, const double *Y, const double *x,
+                        const double *g, int nu, const double *u, double *phi, double *logq, double *xc) {
+  bvgo_pf_cfg cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.history = n > 0 ? n : 1;
+  pf_state st;
+  memset(&st, 0, sizeof(st));
+  st.D = D; st.cfg = &cfg; st.nh = n; st.head = n % cfg.history;
+  st.alpha = (double *)alpha; st.Sh = (double *)S; st.Yh = (double *)Y;
+  pf_alloc(&st.cur, D, cfg.history);
+  pf_build(&st, x, g);
+  const int ok = st.cur.ok;
+  if (ok) {
+    memcpy(xc, st.cur.xc, sizeof(double) * D);
+    for (int k = 0; k < nu; ++k) logq[k] = pf_draw(&st.cur, D, u + (size_t)k * D, phi + (size_t)k * D);
+  }
+  free(st.cur.W); free(st.cur.xc);
+  return ok ? 0 : 1;
+}
+static void pf_alloc(pf_approx *a, int64_t D, int J) {
+  a->W = (double *)malloc(sizeof(double) * 2 * (size_t)J * D);
+  a->xc = (double *)malloc(sizeof(double) * 2 * D);
+  a->alpha = a->xc + D;
+  a->n = 0; a->ok = 0;
+}
+/* one path: amp [num_draws][G] (exp of the amplitude coordinates), lp_ratio [num_draws] = lp - log q;
+ * elbos (optional) [max_lbfgs_iters + 1]: the ELBO estimate at every iterate */
+int bvgo_pf_single(bvgo_ctx *c, const bvgo_pf_cfg *cfg, int path, double *amp, double *lp_ratio, bvgo_pf_info *info,
+                   double *elbos) {
+  const int64_t D = c->L.D, G = c->G;
+  const int J = cfg->history;
+  if (J < 1 || J > 25) return -1;
+  pf_state st;
+  memset(&st, 0, sizeof(st));
+  st.c = c; st.D = D; st.cfg = cfg; st.path = path;
+  st.alpha = (double *)malloc(sizeof(double) * ((size_t)D * (5 + 2 * (size_t)J)));
+  st.xprev = st.alpha + D; st.gprev = st.xprev + D; st.work = st.gprev + D; st.Sh = st.work + 2 * D; st.Yh = st.Sh + (size_t)J * D;
+  for (int64_t d = 0; d < D; ++d) st.alpha[d] = 1.0;
+  pf_alloc(&st.cur, D, J); pf_alloc(&st.best, D, J);
+  st.best_elbo = -INFINITY; st.best_iter = -1;
+  st.elbo_cap = cfg->max_lbfgs_iters + 1;
+  st.elbos = (double *)malloc(sizeof(double) * st.elbo_cap);
+  for (int i = 0; i < st.elbo_cap; ++i) st.elbos[i] = NAN;
+  double *th0 = (double *)malloc(sizeof(double) * 2 * D), *out = th0 + D;
+  for (int64_t d = 0; d < D; ++d) th0[d] = cfg->init_radius * (2.0 * bvgo_uniform(cfg->seed, STREAM_PF_INIT, (uint32_t)path, d) - 1.0);
+  bvgo_lbfgs_cfg lc = {cfg->max_lbfgs_iters, J, 1e-3, 1e-12, 1e4, 1e-8, 1e7, 1e-8};
+  bvgo_lbfgs_result lr;
+  memset(&lr, 0, sizeof(lr));
+  int rc = lbfgs_core(c, th0, &lc, 1, 1, out, &lr, pf_cb, &st);
+  if (rc == 0 && st.best_iter < 0) rc = -5; /* no iterate produced a finite ELBO */
+  if (rc == 0) {
+    double *u = st.work, *phi = u + D;
+    for (int k = 0; k < cfg->num_draws; ++k) {
+      const uint32_t t = ((uint32_t)path << 16) | (uint32_t)k;
+      for (int64_t d = 0; d < D; ++d) u[d] = bvgo_normal(cfg->seed, STREAM_PF_DRAW, t, d);
+      const double lq = pf_draw(&st.best, D, u, phi);
+      const double lp = bvgo_log_prob(c, phi, 1, 1, NULL);
+      lp_ratio[k] = isfinite(lp) ? lp - lq : -INFINITY;
+      for (int64_t g = 0; g < G; ++g) amp[(size_t)k * G + g] = exp(phi[c->L.amp + g]);
+    }
+  }
+  if (info) { info->lbfgs_iters = lr.iters; info->lbfgs_term = lr.term; info->best_iter = st.best_iter; info->best_elbo = st.best_elbo; info->n_pairs = st.best.n; }
+  if (elbos) memcpy(elbos, st.elbos, sizeof(double) * st.elbo_cap);
+  free(th0); free(st.elbos); free(st.cur.W); free(st.cur.xc); free(st.best.W); free(st.best.xc); free(st.alpha);
+  return rc;
+}
+/* Pareto-smoothed importance weights [U: stan::services::psis::psis_weights; Vehtari et al. 2015, Zhang & Stephens 2009] */
+typedef struct { double v; int i; } lr_t;
+static int cmp_lr(const void *a, const void *b) { const double x = ((const lr_t *)a)->v, y = ((const lr_t *)b)->v; return (x > y) - (x < y); }
+double bvgo_psis_weights(const double *lr_in, int S, double *w) {
+  double mx = -INFINITY, khat = NAN;
+  for (int i = 0; i < S; ++i) if (lr_in[i] > mx) mx = lr_in[i];
+  double *lr = (double *)malloc(sizeof(double) * S);
+  for (int i = 0; i < S; ++i) lr[i] = lr_in[i] - mx;
+  const int tail = (int)fmin(0.2 * S, 3.0 * sqrt((double)S));
+  if (tail >= 5) {
+    lr_t *srt = (lr_t *)malloc(sizeof(lr_t) * S);
+    for (int i = 0; i < S; ++i) { srt[i].v = lr[i]; srt[i].i = i; }
+    qsort(srt, S, sizeof(lr_t), cmp_lr);
+    const double cutoff = srt[S - tail - 1].v, ec = exp(cutoff);
+    const int n = tail;
+    double *x = (double *)malloc(sizeof(double) * n);
+    for (int i = 0; i < n; ++i) x[i] = exp(srt[S - tail + i].v) - ec; /* ascending */
+    if (x[n - 1] > 0 && isfinite(x[n - 1])) {
+      /* gpdfit */
+      const int M = 30 + (int)floor(sqrt((double)n));
+      const double xstar = x[(int)floor(n / 4.0 + 0.5) - 1], prior = 3.0;
+      double *th = (double *)malloc(sizeof(double) * 2 * M), *lt = th + M;
+      for (int j = 0; j < M; ++j) {
+        th[j] = 1.0 / x[n - 1] + (1.0 - sqrt((double)M / (j + 0.5))) / (prior * xstar);
+        double kk = 0;
+        for (int i = 0; i < n; ++i) kk += log1p(-th[j] * x[i]);
+        kk /= n;
+        lt[j] = n * (log(-th[j] / kk) - kk - 1.0);
+      }
+      double theta = 0;
+      for (int j = 0; j < M; ++j) {
+        double sw = 0;
+        for (int q = 0; q < M; ++q) sw += exp(lt[q] - lt[j]);
+        theta += th[j] / sw;
+      }
+      double k = 0;
+      for (int i = 0; i < n; ++i) k += log1p(-theta * x[i]);
+      k /= n;
+      const double sigma = -k / theta;
+      k = k * n / (n + 10.0) + 0.5 * 10.0 / (n + 10.0); /* weakly informative prior on k */
+      khat = k;
+      free(th);
+      if (isfinite(k) && isfinite(sigma)) {
+        for (int i = 0; i < n; ++i) {
+          const double pq = (i + 0.5) / n;
+          const double q = (fabs(k) < 1e-300 ? -sigma * log1p(-pq) : sigma * expm1(-k * log1p(-pq)) / k) + ec;
+          lr[srt[S - tail + i].i] = fmin(log(q), 0.0); /* truncated at the largest raw ratio */
+        }
+      }
+    }
+    free(x); free(srt);
+  }
+  double lse = 0;
+  for (int i = 0; i < S; ++i) lse += exp(lr[i]);
+  for (int i = 0; i < S; ++i) w[i] = exp(lr[i]) / lse;
+  free(lr);
+  return khat;
+}
+/* multi-path Pathfinder: summary G x 8 of the PSIS-resampled amplitude draws; idx (optional) [num_psis_draws] */
+int bvgo_pathfinder(bvgo_ctx *c, const bvgo_pf_cfg *cfg, double *summary, bvgo_pf_info *infos, int *idx_out, double *khat) {
+  const int64_t G = c->G;
+  const int P = cfg->num_paths, nd = cfg->num_draws, S = P * nd, ns = cfg->num_psis_draws;
+  double *amp = (double *)malloc(sizeof(double) * ((size_t)S * G + 2 * (size_t)S)), *lr = amp + (size_t)S * G, *w = lr + S;
+  int rc = 0;
+  for (int p = 0; p < P && rc == 0; ++p) rc = bvgo_pf_single(c, cfg, p, amp + (size_t)p * nd * G, lr + (size_t)p * nd, infos ? infos + p : NULL, NULL);
+  if (rc) { free(amp); return rc; }
+  int *idx = (int *)malloc(sizeof(int) * ns);
+  if (P > 1) {
+    const double kh = bvgo_psis_weights(lr, S, w);
+    if (khat) *khat = kh;
+    for (int r = 0; r < ns; ++r) { /* inverse-CDF resampling with replacement */
+      const double uu = bvgo_uniform(cfg->seed, STREAM_PF_PSIS, 0, (uint64_t)r);
+      double cs = 0;
+      int pick = S - 1;
+      for (int i = 0; i < S; ++i) { cs += w[i]; if (uu < cs) { pick = i; break; } }
+      idx[r] = pick;
+    }
+  } else {
+    if (khat) *khat = NAN;
+    for (int r = 0; r < ns; ++r) idx[r] = r % nd;
+  }
+  double *x = (double *)malloc(sizeof(double) * 2 * ns), *d = x + ns;
+  rank_t *rk = (rank_t *)malloc(sizeof(rank_t) * G);
+  for (int64_t g = 0; g < G; ++g) {
+    for (int r = 0; r < ns; ++r) x[r] = amp[(size_t)idx[r] * G + g];
+    rk[g].v = summarise_gene(x, d, ns, G, g, summary);
+    rk[g].i = g;
+  }
+  fill_ranks(rk, G, summary);
+  if (idx_out) memcpy(idx_out, idx, sizeof(int) * ns);
+  free(rk); free(x); free(idx); free(amp);
+  return 0;
+}
 
 /* ------------------------------------------------------------------------------------------
  * Posterior draws + amplitude summary.
@@ -731,7 +1128,6 @@ static double quantile7(const double *sorted, int n, double p) {
   const int hi = lo + 1 < n ? lo + 1 : lo;
   return sorted[lo] + (h - lo) * (sorted[hi] - sorted[lo]);
 }
-typedef struct { double v; int64_t i; } rank_t;
 static int cmp_rank(const void *a, const void *b) {
   const rank_t *x = (const rank_t *)a, *y = (const rank_t *)b;
   if (x->v > y->v) return -1;

@@ -97,6 +97,27 @@ typedef struct { int iters; int fevals; int term; double lp; } bvgo_lbfgs_result
 int bvgo_lbfgs(bvgo_ctx *, const double *theta0, const bvgo_lbfgs_cfg *, double *theta_out,
                bvgo_lbfgs_result *);
 
+/* algorithm = "pathfinder" (:366-375) [U: stan::services::pathfinder]; see bvg_oracle.c */
+typedef struct {
+  int max_lbfgs_iters;  /* 200 (:373) */
+  int history;          /* history_size = 25 (:375); <= 25 */
+  int num_elbo_draws;   /* elbo.samples = 50 for pathfinder (:111-112) */
+  int num_draws;        /* single-path draws, CmdStan default 1000 */
+  int num_paths;        /* n.cores (:372) */
+  int num_psis_draws;   /* draws = n.draws (:370) */
+  double init_radius;   /* init = 0.01 (:368) */
+  uint64_t seed;        /* random.seed */
+} bvgo_pf_cfg;
+typedef struct { int lbfgs_iters, lbfgs_term, best_iter, n_pairs; double best_elbo; } bvgo_pf_info;
+int bvgo_pf_single(bvgo_ctx *, const bvgo_pf_cfg *, int path, double *amp /*[num_draws][G]*/, double *lp_ratio /*[num_draws]*/,
+                   bvgo_pf_info *, double *elbos /* optional [max_lbfgs_iters + 1] */);
+double bvgo_psis_weights(const double *log_ratios, int S, double *weights); /* returns the Pareto k estimate */
+int bvgo_pathfinder(bvgo_ctx *, const bvgo_pf_cfg *, double *summary /*G x 8*/, bvgo_pf_info *infos /*[num_paths]*/,
+                    int *idx /* optional [num_psis_draws] */, double *khat);
+int bvgo_pf_approx_test(int64_t D, int n, const double *alpha, const double *S, const double *Y, const double *x,
+                        const double *g, int nu, const double *u, double *phi, double *logq, double *xc);
+double bvgo_uniform(uint64_t seed, uint32_t stream, uint32_t t, uint64_t i);
+
 /* amplitude summaries from n_draws draws of exp(mu_u + exp(omega_u) eps):
  * out G x 8 col-major: mean, median, sd, mad, q5, q95, dispersion, rank (1 = largest mean) */
 int bvgo_summary(int model, int64_t G, int k, const double *mu, const double *omega, int n_draws,

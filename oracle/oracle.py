@@ -35,6 +35,16 @@ class _AdviRes(C.Structure):
                 ("n_trace", C.c_int)]
 
 
+class _PfCfg(C.Structure):
+    _fields_ = [("max_lbfgs_iters", C.c_int), ("history", C.c_int), ("num_elbo_draws", C.c_int), ("num_draws", C.c_int),
+                ("num_paths", C.c_int), ("num_psis_draws", C.c_int), ("init_radius", C.c_double), ("seed", C.c_uint64)]
+
+
+class _PfInfo(C.Structure):
+    _fields_ = [("lbfgs_iters", C.c_int), ("lbfgs_term", C.c_int), ("best_iter", C.c_int), ("n_pairs", C.c_int),
+                ("best_elbo", C.c_double)]
+
+
 class _LbfgsCfg(C.Structure):
     _fields_ = [("max_iter", C.c_int), ("history", C.c_int), ("init_alpha", C.c_double),
                 ("tol_obj", C.c_double), ("tol_rel_obj", C.c_double), ("tol_grad", C.c_double),
@@ -79,6 +89,12 @@ def lib():
         L.bvgo_fr_step.argtypes = [C.c_void_p, _dp, _dp, _dp, C.c_double, C.c_int, C.c_uint64, C.c_uint32]
         L.bvgo_advi_fullrank.argtypes = L.bvgo_advi.argtypes
         L.bvgo_summary_fullrank.argtypes = [C.c_int, C.c_int64, C.c_int, _dp, _dp, C.c_int, C.c_uint64, _dp]
+        L.bvgo_pf_single.argtypes = [C.c_void_p, C.POINTER(_PfCfg), C.c_int, _dp, _dp, C.POINTER(_PfInfo), _dp]
+        L.bvgo_psis_weights.restype = C.c_double
+        L.bvgo_psis_weights.argtypes = [_dp, C.c_int, _dp]
+        L.bvgo_pathfinder.argtypes = [C.c_void_p, C.POINTER(_PfCfg), _dp, C.POINTER(_PfInfo), C.POINTER(C.c_int), C.POINTER(C.c_double)]
+        L.bvgo_uniform.restype = C.c_double
+        L.bvgo_uniform.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64]
         L.bvgo_kmeans.argtypes = [_dp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_uint64, _dp, _dp, C.POINTER(C.c_int32)]
         L.bvgo_digamma.restype = C.c_double
         L.bvgo_digamma.argtypes = [C.c_double]
@@ -177,6 +193,33 @@ class Oracle:
         lib().bvgo_summary_fullrank(self.model, self.G, self.k, _p(mu), _p(L), n_draws, seed, _p(out))
         return out
 
+    # ---- algorithm = "pathfinder" ----
+    @staticmethod
+    def _pf_cfg(max_lbfgs_iters=200, history=25, num_elbo_draws=50, num_draws=1000, num_paths=2, num_psis_draws=1000,
+                init_radius=0.01, seed=312):
+        return _PfCfg(max_lbfgs_iters, history, num_elbo_draws, num_draws, num_paths, num_psis_draws, init_radius, seed)
+
+    def pf_single(self, path=0, **kw):
+        cfg = self._pf_cfg(**kw)
+        amp = np.empty((cfg.num_draws, self.G))
+        lr = np.empty(cfg.num_draws)
+        elbos = np.empty(cfg.max_lbfgs_iters + 1)
+        info = _PfInfo()
+        rc = lib().bvgo_pf_single(self._h, C.byref(cfg), path, _p(amp), _p(lr), C.byref(info), _p(elbos))
+        d = {f: getattr(info, f) for f, _ in _PfInfo._fields_}
+        d.update(rc=rc, elbos=elbos)
+        return amp, lr, d
+
+    def pathfinder(self, **kw):
+        cfg = self._pf_cfg(**kw)
+        out = np.empty((self.G, 8), order="F")
+        infos = (_PfInfo * cfg.num_paths)()
+        idx = (C.c_int * cfg.num_psis_draws)()
+        kh = C.c_double()
+        rc = lib().bvgo_pathfinder(self._h, C.byref(cfg), _p(out), infos, idx, C.byref(kh))
+        return out, dict(rc=rc, khat=kh.value, idx=np.array(list(idx)),
+                         paths=[{f: getattr(i, f) for f, _ in _PfInfo._fields_} for i in infos])
+
     def lbfgs(self, theta0=None, max_iter=1000, history=25):
         th0 = np.zeros(self.D) if theta0 is None else np.ascontiguousarray(theta0, dtype=np.float64)
         cfg = _LbfgsCfg(max_iter, history, 1e-3, 1e-12, 1e4, 1e-8, 1e7, 1e-8)
@@ -236,6 +279,28 @@ def unpack_tril(Lp, D):
     out = np.zeros((D, D))
     out[np.tril_indices(D)] = Lp
     return out
+
+
+def pf_approx(alpha, S, Y, x, g, u):
+    """test hook: Pathfinder's Gaussian approximation from curvature pairs S, Y ([n][D], oldest first)"""
+    alpha, S, Y, x, g, u = (np.ascontiguousarray(a, dtype=np.float64) for a in (alpha, S, Y, x, g, u))
+    D, n, nu = len(alpha), S.shape[0], u.shape[0]
+    phi, lq, xc = np.empty((nu, D)), np.empty(nu), np.empty(D)
+    lib().bvgo_pf_approx_test.argtypes = [C.c_int64, C.c_int, _dp, _dp, _dp, _dp, _dp, C.c_int, _dp, _dp, _dp, _dp]
+    rc = lib().bvgo_pf_approx_test(D, n, _p(alpha), _p(S), _p(Y), _p(x), _p(g), nu, _p(u), _p(phi), _p(lq), _p(xc))
+    assert rc == 0
+    return phi, lq, xc
+
+
+def psis_weights(log_ratios):
+    lr = np.ascontiguousarray(log_ratios, dtype=np.float64)
+    w = np.empty(len(lr))
+    k = lib().bvgo_psis_weights(_p(lr), len(lr), _p(w))
+    return w, k
+
+
+def uniform(seed, stream, t, i):
+    return lib().bvgo_uniform(seed, stream, t, i)
 
 
 def normal(seed, stream, t, i):
