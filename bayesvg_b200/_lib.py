@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(_HERE, "libbayesvg_b200.so")
 
 ABI_VERSION = 2
-ALG_MEANFIELD, ALG_FULLRANK = 0, 1
+ALG_MEANFIELD, ALG_FULLRANK, ALG_PATHFINDER = 0, 1, 2
 GAUSSIAN, NB = 0, 1
 KERNELS = {"exp_quad": 0, "matern": 1, "periodic": 2}
 PREC_FP64, PREC_FAST = 0, 1
@@ -20,7 +20,7 @@ EXPORTS = [
     "bvg_version", "bvg_last_error", "bvg_device_count", "bvg_config_default", "bvg_basis_build", "bvg_kmeans",
     "bvg_fit_create", "bvg_fit_destroy", "bvg_fit_set_phi", "bvg_fit_set_y_f64", "bvg_fit_set_y_i32",
     "bvg_fit_dim", "bvg_fit_set_gene_depths", "bvg_comm_unique_id", "bvg_fit_comm_init", "bvg_fit_peer_handle", "bvg_fit_peer_init", "bvg_log_prob", "bvg_fit_run", "bvg_fit_mle",
-    "bvg_fit_advi", "bvg_fit_summarize", "bvg_fit_set_variational", "bvg_fit_get_variational", "bvg_fit_get_cholesky", "bvg_fit_set_cholesky",
+    "bvg_fit_advi", "bvg_fit_summarize", "bvg_fit_set_variational", "bvg_fit_get_variational", "bvg_fit_get_cholesky", "bvg_fit_set_cholesky", "bvg_fit_pathfinder_single",
     "bvg_fit_advi_steps", "bvg_fit_elbo", "bvg_fit_time_lik_kernel", "bvg_fit_flush_l2", "bvg_fit_get_summary",
     "bvg_fit_get_draws", "bvg_fit_posterior_ncol", "bvg_fit_get_posterior", "bvg_fit_get_trace", "bvg_fit_get_stats", "bvg_debug_stage_times", "bvg_debug_gene_trace", "bvg_debug_time_gene",
     "bvg_debug_tc_trace",
@@ -35,7 +35,8 @@ class Config(C.Structure):
         ("lbfgs_history", C.c_int32), ("verbose", C.c_int32), ("tol_rel_obj", C.c_double), ("eta", C.c_double),
         ("seed", C.c_uint64), ("rank", C.c_int32), ("world_size", C.c_int32), ("gene_offset", C.c_int64),
         ("G_total", C.c_int64), ("elbo_suffstat", C.c_int32), ("depth_adjust", C.c_int32),
-        ("algorithm", C.c_int32), ("reserved0", C.c_int32),
+        ("algorithm", C.c_int32), ("pf_num_paths", C.c_int32), ("pf_max_lbfgs_iters", C.c_int32),
+        ("pf_single_draws", C.c_int32), ("pf_init_radius", C.c_double),
     ]
 
 
@@ -104,6 +105,7 @@ def lib():
     L.bvg_debug_gene_trace.argtypes = [_vp, C.POINTER(C.c_longlong), C.c_int]
     L.bvg_fit_get_summary.argtypes = [_vp, _dp]
     L.bvg_fit_get_draws.argtypes = [_vp, _dp]
+    L.bvg_fit_pathfinder_single.argtypes = [_vp, C.c_int, _dp, _dp, _dp, _dp]
     L.bvg_fit_get_cholesky.argtypes = [_vp, _dp]
     L.bvg_fit_set_cholesky.argtypes = [_vp, _dp]
     L.bvg_kmeans.argtypes = [C.c_int, _dp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_uint64, _dp, _dp, C.POINTER(C.c_int32)]

@@ -207,10 +207,12 @@ def findSpatiallyVariableFeaturesBayes(sp_obj=None, naive_hvgs=None, likelihood=
     if elbo_samples is None:
         elbo_samples = 50 if algorithm == "pathfinder" else 150
     # accepted by the reference, rejected clearly here (north_star: no fallback)
-    if algorithm == "pathfinder":
-        raise NotImplementedError("algorithm = 'pathfinder' is not built in bayesvg_b200; 'meanfield' and 'fullrank' are.")
-    if algorithm == "fullrank" and shard is not None:
-        raise NotImplementedError("algorithm = 'fullrank' couples all parameters and cannot be gene-sharded.")
+    if mle_init and algorithm == "pathfinder" and verbose:   # :109
+        print("! Initialization at the regularized MLE is not supported when using the Pathfinder algorithm.")
+    if algorithm != "meanfield" and shard is not None:
+        raise NotImplementedError(f"algorithm = '{algorithm}' is not built for gene-sharded fits; use 'meanfield'.")
+    if algorithm == "pathfinder" and save_model:
+        raise NotImplementedError("save.model = TRUE is not built for algorithm = 'pathfinder'.")
     if opencl_params is not None:
         raise NotImplementedError("opencl.params is meaningless here: the fit always runs on the CUDA device.")
     if lscale_estimator != "kmeans":
@@ -253,6 +255,8 @@ def findSpatiallyVariableFeaturesBayes(sp_obj=None, naive_hvgs=None, likelihood=
     # fit (:337-413)
     cfg = dict(n_iter=int(n_iter), mle_init=int(bool(mle_init)), mle_iter=int(mle_iter), n_draws=int(n_draws),
                elbo_samples=int(elbo_samples), seed=int(random_seed), verbose=int(bool(verbose)), device=device)
+    if algorithm == "pathfinder":   # :366-375: num_paths = n.cores, max_lbfgs_iters = 200, history_size = 25, init = 0.01
+        cfg.update(pf_num_paths=int(n_cores), pf_max_lbfgs_iters=200, pf_init_radius=0.01, lbfgs_history=25)
     if shard is not None:
         from . import dist
         table, model = dist.fit_sharded(phi, Y, shard, likelihood, precision, engine, cfg, gene_depths=gene_depths)
@@ -267,7 +271,10 @@ def findSpatiallyVariableFeaturesBayes(sp_obj=None, naive_hvgs=None, likelihood=
         stats = fit.stats()
         fit.close()
         if verbose:
-            print(f"v ADVI ({algorithm}): eta = {stats['eta']}, {stats['advi_iters']} iterations, ELBO = {stats['elbo']:.6g}")
+            if algorithm == "pathfinder":
+                print(f"v Pathfinder: {n_cores} paths, {stats['advi_iters']} L-BFGS iterations, best ELBO = {stats['elbo']:.6g}, Pareto k = {stats['eta']:.3g}")
+            else:
+                print(f"v ADVI ({algorithm}): eta = {stats['eta']}, {stats['advi_iters']} iterations, ELBO = {stats['elbo']:.6g}")
     # summarise (:419-432)
     summ = pd.DataFrame(table[:, :7], columns=_SUMMARY_COLS[:7])
     summ.insert(0, "gene", list(naive_hvgs))

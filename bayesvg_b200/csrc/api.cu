@@ -55,9 +55,12 @@ extern "C" void bvg_config_default(bvg_config *c) {
   c->elbo_suffstat = 0;
   c->depth_adjust = 0;
   c->algorithm = BVG_ALG_MEANFIELD;
+  c->pf_num_paths = 2;        /* n.cores = 2 (:94) */
+  c->pf_max_lbfgs_iters = 200;
+  c->pf_single_draws = 1000;
+  c->pf_init_radius = 0.01;
 }
 
-int lbfgs_run(bvg_fit *f, const double *d_theta0, double *d_out);  // lbfgs.cu
 int basis_build_device(cudaStream_t st, const double *d_X, int64_t M, const double *d_C, int k, double ls, int kernel,
                        double nu, double period, double *d_Q, double *d_work);
 void comm_destroy(bvg_fit *f);
@@ -76,8 +79,9 @@ extern "C" int bvg_fit_create(const bvg_config *cfg, bvg_fit **out) {
   if (cfg->engine == BVG_ENGINE_TCGEN05 && cfg->precision != BVG_PREC_FAST) { bvg_set_error("the tcgen05 engine has no fp64 kind; use precision = FAST"); return BVG_ERR_ARG; }
   if (cfg->n_iter < 1 || cfg->elbo_samples < 1 || cfg->eval_elbo < 1 || cfg->adapt_iter < 1 || cfg->n_draws < 2) { bvg_set_error("iteration / sample counts must be positive"); return BVG_ERR_ARG; }
   if (cfg->world_size < 1 || cfg->rank < 0 || cfg->rank >= cfg->world_size) { bvg_set_error("bad rank/world_size"); return BVG_ERR_ARG; }
-  if (cfg->algorithm != BVG_ALG_MEANFIELD && cfg->algorithm != BVG_ALG_FULLRANK) { bvg_set_error("Please provide a valid variational inference approximation algorithm (meanfield and fullrank are built; pathfinder is not)."); return BVG_ERR_ARG; }
+  if (cfg->algorithm < BVG_ALG_MEANFIELD || cfg->algorithm > BVG_ALG_PATHFINDER) { bvg_set_error("Please provide a valid variational inference approximation algorithm."); return BVG_ERR_ARG; }
   if (cfg->algorithm == BVG_ALG_FULLRANK && cfg->world_size > 1) { bvg_set_error("algorithm = 'fullrank' couples all parameters and cannot be gene-sharded"); return BVG_ERR_ARG; }
+  if (cfg->algorithm == BVG_ALG_PATHFINDER && cfg->world_size > 1) { bvg_set_error("algorithm = 'pathfinder' is not built for gene-sharded fits"); return BVG_ERR_ARG; }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
     cudaGetLastError();
@@ -128,6 +132,7 @@ extern "C" void bvg_fit_destroy(bvg_fit *f) {
     for (int b = 0; b < 2; ++b) { cudaEventDestroy(f->ev_copied[b]); cudaEventDestroy(f->ev_staged[b]); }
   }
   delete[] f->h_theta_mle;
+  delete[] f->pf_idx;
   delete[] f->h_depths;
   cudaEventDestroy(f->ev0); cudaEventDestroy(f->ev1);
   cudaStreamDestroy(f->stream);
@@ -674,9 +679,35 @@ extern "C" int bvg_fit_summarize(bvg_fit *f) {
   return BVG_OK;
 }
 
+extern "C" int bvg_fit_pathfinder_single(bvg_fit *f, int path, double *amp, double *lp_ratio, double *info, double *elbos) {
+  BVG_TRY(need_ready(f));
+  if (f->cfg.algorithm != BVG_ALG_PATHFINDER || !amp || !lp_ratio || path < 0 || path > 255) { bvg_set_error("bvg_fit_pathfinder_single needs algorithm = pathfinder, 0 <= path <= 255 and output buffers"); return BVG_ERR_ARG; }
+  const size_t n = (size_t)f->cfg.pf_single_draws * f->m.G;
+  double *d_amp = nullptr;
+  CUDA_TRY(cudaMalloc(&d_amp, sizeof(double) * n));
+  int rc = pf_single(f, path, d_amp, 0, lp_ratio, info, elbos);
+  if (rc == BVG_OK && (cudaMemcpyAsync(amp, d_amp, sizeof(double) * n, cudaMemcpyDeviceToHost, f->stream) != cudaSuccess ||
+                       cudaStreamSynchronize(f->stream) != cudaSuccess)) { bvg_set_error("pathfinder: copy failed"); rc = BVG_ERR_CUDA; }
+  cudaFree(d_amp);
+  return rc;
+}
 extern "C" int bvg_fit_run(bvg_fit *f) {
   BVG_TRY(need_ready(f));
   const double t0 = now_s();
+  if (f->cfg.algorithm == BVG_ALG_PATHFINDER) {   // :366-375: no MLE initialisation (:109), no ADVI
+    f->have_mle = false;
+    f->st.grad_evals = 0; f->st.elbo_evals = 0;
+    const double t1 = now_s();
+    BVG_TRY(pf_run(f));
+    f->st.sec_sga = now_s() - t1;
+    const double t2 = now_s();
+    BVG_TRY(launch_summary(f, true));
+    CUDA_TRY(cudaStreamSynchronize(f->stream));
+    f->have_summary = true;
+    f->st.sec_draws = now_s() - t2;
+    f->st.sec_total = now_s() - t0 + f->st.sec_h2d;
+    return BVG_OK;
+  }
   if (f->cfg.mle_init) BVG_TRY(bvg_fit_mle(f, nullptr, nullptr));
   else f->have_mle = false;
   BVG_TRY(bvg_fit_advi(f, nullptr));

@@ -291,6 +291,7 @@ struct bvg_fit {
   NcclApi *nccl;
   void *comm;
   void *fr;            // full-rank ADVI state (k_fullrank.cu), allocated on first use
+  int *pf_idx;         // pathfinder: indices of the PSIS-resampled draws (host)
   int elbo_cap;        // capacity of m.elbo_lps
   void *peer_buf;      // this rank's exchange buffer (cudaMalloc, exported with cudaIpcGetMemHandle)
   void *peer_map[BVG_MAX_PEERS];  // peers' buffers opened with cudaIpcOpenMemHandle
@@ -340,6 +341,9 @@ int fr_posterior(bvg_fit *f, int n, double *d_out);
 int fr_get_cholesky(bvg_fit *f, double *L_out);
 int fr_set_cholesky(bvg_fit *f, const double *L_in);
 int fr_log_diag(bvg_fit *f);
+// Pathfinder (k_pathfinder.cu)
+int pf_single(bvg_fit *f, int path, double *d_amp, int64_t row0, double *h_lr, double *info, double *elbos);
+int pf_run(bvg_fit *f);
 int fr_store_draw(bvg_fit *f, int64_t n, int64_t d, double *d_out, const double *d_eta);  // api.cu: one row of the posterior matrix
 int launch_summary(bvg_fit *f, bool given = false);   // k_summary.cu; given: summarise the draws already in f->draws
 // MODE_POST_DRAW: log_p__ of a posterior draw (Philox stream 3, counter ctl->t_draw), stored in elbo_lps[t_draw]

@@ -6,6 +6,13 @@
 #define LBFGS_MAX_HISTORY 32
 struct LinCoef { double d[2 * LBFGS_MAX_HISTORY + 1]; };
 
+#include <functional>
+struct LbfgsOpt {
+  int jacobian = 0, propto = 0, max_iter = 0, history = 0;
+  std::function<int(int it, const double *d_x, const double *d_g, double fval)> on_iterate;
+};
+int lbfgs_run(bvg_fit *f, const double *d_theta0, double *d_out, const LbfgsOpt *opt = nullptr);  // lbfgs.cu
+
 template <typename SRC, typename DST>
 int stage_y(const SRC *src, DST *dst, int64_t M, int64_t ldY, int64_t ngenes, cudaStream_t st);
 template <typename SRC>

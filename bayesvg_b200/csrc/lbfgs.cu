@@ -91,13 +91,15 @@ int wolfe(const EvalFn &ev, double *alpha, double *f1, double *dg1, double f0, d
 
 }  // namespace
 
-int eval_log_prob_device(bvg_fit *f, int mode, int jac, int propto, bool backward);  // api.cu
 
 // d_theta0: device vector or NULL (= 0, the reference's init = 0).  Result left in d_out (device).
-int lbfgs_run(bvg_fit *f, const double *d_theta0, double *d_out) {
+// opt (optional): jacobian / propto of the objective, iteration cap, and a callback that sees the initial point (it = 0)
+// and every accepted iterate (device x, device gradient of f = -lp, f) -- Pathfinder builds its approximations there.
+int lbfgs_run(bvg_fit *f, const double *d_theta0, double *d_out, const LbfgsOpt *opt) {
   const DevModel &m = f->m;
   const int64_t D = m.L.D;
-  const int mh = std::min<int>(std::max(f->cfg.lbfgs_history, 1), LBFGS_MAX_HISTORY), nb = 2 * mh + 1;
+  const int jac = opt ? opt->jacobian : 0, propto = opt ? opt->propto : 0;
+  const int mh = std::min<int>(std::max(opt && opt->history > 0 ? opt->history : f->cfg.lbfgs_history, 1), LBFGS_MAX_HISTORY), nb = 2 * mh + 1;
   cudaStream_t st = f->stream;
   double *B = nullptr, *x0, *p, *w, *part, *dots, *scal;
   const size_t nd = (size_t)nb * D + 3 * (size_t)D + (size_t)nb * VEC_NCHUNK * 3 + (size_t)nb * 3 + 8;
@@ -116,7 +118,7 @@ int lbfgs_run(bvg_fit *f, const double *d_theta0, double *d_out) {
   // f(x0 + alpha p) and its directional derivative; leaves x in m.zeta and grad(lp) in m.grad
   EvalFn ev = [&](double alpha, double *fv, double *dg) -> int {
     if (vec_axpy_to(st, m.zeta, x0, alpha, p, D) != BVG_OK) return 2;
-    if (eval_log_prob_device(f, MODE_GRAD_OUT, 0, 0, true) != BVG_OK) return 2;
+    if (eval_log_prob_device(f, MODE_GRAD_OUT, jac, propto, true) != BVG_OK) return 2;
     if (vec_dot_sum(st, m.grad, p, w, D, scal) != BVG_OK) return 2;
     if (f->comm_mode && comm_allreduce(f, scal, 2) != BVG_OK) return 2;
     if (cudaMemcpyAsync(scal + 2, &m.ctl->lp, sizeof(double), cudaMemcpyDeviceToDevice, st) != cudaSuccess) return 2;
@@ -133,6 +135,7 @@ int lbfgs_run(bvg_fit *f, const double *d_theta0, double *d_out) {
   if (ev(0.0, &fk, &dg)) { bvg_set_error("L-BFGS: log density is not finite at the initial point"); return fail(BVG_ERR_NUMERIC); }
   // g0 = -grad, p = -g0 = grad
   if ((rc = vec_accept(st, nullptr, nullptr, x0, g0, m.zeta, m.grad, D)) != BVG_OK) return fail(rc);
+  if (opt && opt->on_iterate && (rc = opt->on_iterate(0, x0, g0, fk)) != BVG_OK) return fail(rc);
   CUDA_TRY(cudaMemcpyAsync(p, m.grad, D * sizeof(double), cudaMemcpyDeviceToDevice, st));
   if ((rc = vec_dot_sum(st, g0, g0, w, D, scal)) != BVG_OK) return fail(rc);
   if (f->comm_mode && (rc = comm_allreduce(f, scal, 2)) != BVG_OK) return fail(rc);
@@ -143,7 +146,7 @@ int lbfgs_run(bvg_fit *f, const double *d_theta0, double *d_out) {
   int nh = 0, head = 0, it = 0, term = 0;
   double fk1 = 0, alpha = 1e-3, alphak1 = 0, dfp_prev = 0, gamma = 1;
   const double eps = DBL_EPSILON, tol_obj = 1e-12, tol_rel_obj = 1e4, tol_grad = 1e-8, tol_rel_grad = 1e7, tol_param = 1e-8;
-  const int max_iter = f->cfg.mle_iter;
+  const int max_iter = opt && opt->max_iter > 0 ? opt->max_iter : f->cfg.mle_iter;
   while (!term && max_iter > 0) {
     ++it;
     int resetB = (it == 1) ? 1 : 0;
@@ -170,6 +173,7 @@ int lbfgs_run(bvg_fit *f, const double *d_theta0, double *d_out) {
     if ((rc = vec_accept(st, B + (size_t)head * D, B + (size_t)(mh + head) * D, x0, g0, m.zeta, m.grad, D)) != BVG_OK) return fail(rc);
     fk1 = fk; fk = f1;
     dfp_prev = dfp;
+    if (opt && opt->on_iterate && (rc = opt->on_iterate(it, x0, g0, fk)) != BVG_OK) return fail(rc);
     if (resetB) {  // history cleared before the push (LBFGSUpdate::update(reset = true))
       for (auto &v : Gm) v = 0.0;
       if (head != 0) {  // move the fresh pair to slot 0

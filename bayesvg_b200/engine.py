@@ -62,7 +62,7 @@ class Fit:
         lik = {"gaussian": B.GAUSSIAN, "nb": B.NB}.get(likelihood)
         if lik is None:
             raise ValueError("Please provide a valid likelihood.")
-        alg = {"meanfield": B.ALG_MEANFIELD, "fullrank": B.ALG_FULLRANK}.get(algorithm)
+        alg = {"meanfield": B.ALG_MEANFIELD, "fullrank": B.ALG_FULLRANK, "pathfinder": B.ALG_PATHFINDER}.get(algorithm)
         if alg is None:
             raise ValueError("Please provide a valid variational inference approximation algorithm.")
         self.cfg = default_config(algorithm=alg, likelihood=lik, precision={"fp64": B.PREC_FP64, "fast": B.PREC_FAST}[precision],
@@ -154,6 +154,14 @@ class Fit:
         mu, om = np.empty(self.D), np.empty(self.D)
         B.check(B.lib().bvg_fit_get_variational(self._h, _dp(mu), _dp(om)))
         return mu, om
+
+    def pathfinder_single(self, path=0):
+        """algorithm = "pathfinder": one path -> (amplitude draws [pf_single_draws][G], lp - log q per draw, info)"""
+        nd, it = self.cfg.pf_single_draws, self.cfg.pf_max_lbfgs_iters
+        amp, lr, info, elbos = np.empty((nd, self.G)), np.empty(nd), np.empty(5), np.empty(it + 1)
+        B.check(B.lib().bvg_fit_pathfinder_single(self._h, int(path), _dp(amp), _dp(lr), _dp(info), _dp(elbos)))
+        return amp, lr, dict(lbfgs_iters=int(info[0]), lbfgs_term=int(info[1]), best_iter=int(info[2]), n_pairs=int(info[3]),
+                             best_elbo=info[4], elbos=elbos)
 
     def get_cholesky(self):
         """algorithm = "fullrank": the packed row-major lower-triangular factor L of q = N(mu, L L^T)"""

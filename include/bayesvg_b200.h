@@ -81,14 +81,20 @@ typedef struct {
   /* gene.depth.adjust (:85): intercept beta0 + beta1 * gene_depths[g] (approxGP2/3.stan) instead of the
    * hierarchical per-gene intercept; needs bvg_fit_set_gene_depths */
   int32_t depth_adjust;
-  /* algorithm (:87, :108): BVG_ALG_MEANFIELD (default) or BVG_ALG_FULLRANK -- q = N(mu, L L^T) with the packed
+  /* algorithm (:87, :108): BVG_ALG_MEANFIELD (default); BVG_ALG_FULLRANK -- q = N(mu, L L^T) with the packed
    * lower-triangular L and its step-size history resident in HBM (D (D + 1) / 2 * 16 bytes: 35 GB at 3,000 genes,
-   * k = 20); single GPU only.  "pathfinder" is not built. */
+   * k = 20); BVG_ALG_PATHFINDER -- multi-path Pathfinder (:366-375).  The last two run on a single GPU only. */
   int32_t algorithm;
-  int32_t reserved0;
+  /* pathfinder (:366-375): num_paths = n.cores, max_lbfgs_iters = 200, single-path draws (CmdStan default 1000),
+   * init = 0.01; num_elbo_draws = elbo_samples (50 for pathfinder, :111-112; <= 50), history_size = lbfgs_history (<= 25),
+   * PSIS draws = n_draws.  mle_init does not apply (:109). */
+  int32_t pf_num_paths;
+  int32_t pf_max_lbfgs_iters;
+  int32_t pf_single_draws;
+  double pf_init_radius;
 } bvg_config;
 
-typedef enum { BVG_ALG_MEANFIELD = 0, BVG_ALG_FULLRANK = 1 } bvg_algorithm;
+typedef enum { BVG_ALG_MEANFIELD = 0, BVG_ALG_FULLRANK = 1, BVG_ALG_PATHFINDER = 2 } bvg_algorithm;
 
 typedef struct bvg_fit bvg_fit;
 
@@ -156,6 +162,13 @@ int bvg_fit_get_variational(bvg_fit *, double *mu, double *omega);
 /* algorithm = fullrank: the Cholesky factor of the approximation, PACKED lower-triangular row-major (row i starts at
  * i (i + 1) / 2; D (D + 1) / 2 doubles).  bvg_fit_set_variational installs (mu, L = I) [U: normal_fullrank's start];
  * bvg_fit_get_variational reports omega = log |L_ii|. */
+/* algorithm = pathfinder: ONE path (the parity hook next to the CPU restatement): amp [pf_single_draws][G] row-major
+ * amplitude draws of the path's best approximation, lp_ratio [pf_single_draws] = log p - log q of each draw,
+ * info[5] = {L-BFGS iterations, L-BFGS termination code, best iterate, curvature pairs in it, its ELBO estimate},
+ * elbos (may be NULL) [pf_max_lbfgs_iters + 1] the ELBO estimate at every iterate (NaN where none was made).
+ * bvg_fit_run runs pf_num_paths of them, Pareto-smoothed-importance resamples n_draws draws and summarises those;
+ * afterwards bvg_fit_get_trace rows are (path, best iterate, best ELBO, L-BFGS iterations) and stats.eta = Pareto k. */
+int bvg_fit_pathfinder_single(bvg_fit *, int path, double *amp, double *lp_ratio, double *info, double *elbos);
 int bvg_fit_get_cholesky(bvg_fit *, double *L_packed);
 int bvg_fit_set_cholesky(bvg_fit *, const double *L_packed);
 /* n stochastic-gradient steps (iteration counter continues from the last reset);

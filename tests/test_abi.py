@@ -35,7 +35,7 @@ def test_config_default_matches_reference_defaults():
     assert (cfg.n_iter, cfg.mle_init, cfg.mle_iter, cfg.n_draws, cfg.elbo_samples) == (3000, 1, 1000, 1000, 150)
     assert (cfg.eval_elbo, cfg.adapt_iter, cfg.lbfgs_history, cfg.seed) == (100, 50, 25, 312)
     assert cfg.tol_rel_obj == 0.01 and cfg.eta == 0.0 and cfg.world_size == 1
-    assert C.sizeof(_lib.Config) == 120  # layout of bvg_config (guards accidental ABI drift)
+    assert C.sizeof(_lib.Config) == 136  # layout of bvg_config (guards accidental ABI drift)
 
 
 def test_no_device_is_an_error_not_a_fallback():

@@ -480,11 +480,65 @@ def test_fullrank_full_fit_and_errors():
     with pytest.raises(bvg._lib.BvgError, match="gene-sharded"):
         bvg.Fit(p["phi"], p["y"], "gaussian", "fast", "auto", algorithm="fullrank", world_size=2, rank=0, G_total=24, gene_offset=0)
     with pytest.raises(ValueError, match="valid variational inference"):
-        bvg.Fit(p["phi"], p["y"], "gaussian", "fast", "auto", algorithm="pathfinder")
+        bvg.Fit(p["phi"], p["y"], "gaussian", "fast", "auto", algorithm="hmc")
     fm = bvg.Fit(p["phi"], p["y"], "gaussian", "fast", "auto")
     with pytest.raises(bvg._lib.BvgError, match="fullrank"):
         fm.get_cholesky()
     fm.close()
+
+
+@pytest.mark.parametrize("lik", ["gaussian", "nb"])
+@pytest.mark.parametrize("prec,eng", ENGINES)
+def test_pathfinder_single_path_matches_oracle(lik, prec, eng):
+    """algorithm = "pathfinder" (R/findSpatiallyVariableFeaturesBayes.R:366-375) [U: pathfinder_lbfgs_single]: over the first
+    L-BFGS iterates (before the two optimisers' round-off separates the paths) the per-iterate ELBO estimates, the chosen
+    iterate, its draws and their log p - log q must equal the CPU restatement's (same Philox draws)."""
+    p = make_problem(150, 12, 4, lik, seed=9)
+    o = orc.Oracle(p["phi"], p["y"], lik, nthreads=2)
+    kw = dict(max_lbfgs_iters=9, history=5, num_elbo_draws=12, num_draws=40, seed=21)
+    ramp, rlr, rinfo = o.pf_single(1, **kw)
+    f = _fit(p["phi"], p["y"], lik, prec, eng, algorithm="pathfinder", seed=21, elbo_samples=12, lbfgs_history=5,
+             pf_max_lbfgs_iters=9, pf_single_draws=40)
+    amp, lr, info = f.pathfinder_single(1)
+    assert rinfo["rc"] == 0 and info["lbfgs_iters"] == rinfo["lbfgs_iters"] == 9
+    tol = 1e-7 if prec == "fp64" else 2e-3
+    e, re = info["elbos"][1:10], rinfo["elbos"][1:10]
+    assert np.all(np.isfinite(e) == np.isfinite(re))
+    ok = np.isfinite(re)
+    assert np.allclose(e[ok], re[ok], rtol=tol)
+    if prec == "fp64":
+        assert info["best_iter"] == rinfo["best_iter"] and info["n_pairs"] == rinfo["n_pairs"]
+        assert np.allclose(amp, ramp, rtol=1e-6) and np.allclose(lr, rlr, rtol=1e-7, atol=1e-6)
+    f.close()
+
+
+def test_pathfinder_full_run_psis_and_summary():
+    """multi-path Pathfinder through bvg_fit_run: PSIS resampling + amplitude summaries; with few L-BFGS iterations the
+    fp64 engine reproduces the oracle's run exactly (paths, resampled indices, summary table)"""
+    p = make_problem(150, 12, 4, "gaussian", seed=9)
+    o = orc.Oracle(p["phi"], p["y"], "gaussian", nthreads=2)
+    kw = dict(max_lbfgs_iters=8, history=5, num_elbo_draws=10, num_draws=60, num_paths=3, num_psis_draws=90, seed=5)
+    ref, rinfo = o.pathfinder(**kw)
+    assert rinfo["rc"] == 0
+    f = bvg.Fit(p["phi"], p["y"], "gaussian", "fp64", "simt", algorithm="pathfinder", seed=5, elbo_samples=10, lbfgs_history=5,
+                pf_max_lbfgs_iters=8, pf_single_draws=60, pf_num_paths=3, n_draws=90)
+    got = f.run()
+    tr, st = f.trace(), f.stats()
+    assert len(tr) == 3 and [int(r[1]) for r in tr] == [q["best_iter"] for q in rinfo["paths"]]
+    assert np.allclose(tr[:, 2], [q["best_elbo"] for q in rinfo["paths"]], rtol=1e-7)
+    assert st["eta"] == pytest.approx(rinfo["khat"], rel=1e-5)          # Pareto k of the importance ratios
+    assert np.allclose(got[:, :7], ref[:, :7], rtol=1e-6) and np.array_equal(got[:, 7], ref[:, 7])
+    assert f.draws().shape == (90, 12)
+    f.close()
+    # a longer run on the fast engine: finite, positive, and the selected iterate is an interior one
+    f = bvg.Fit(p["phi"], p["y"], "gaussian", "fast", "auto", algorithm="pathfinder", seed=5, pf_max_lbfgs_iters=60, elbo_samples=20,
+                pf_single_draws=100, n_draws=150)
+    got = f.run()
+    tr = f.trace()
+    assert np.all(np.isfinite(got[:, :7])) and np.all(got[:, 0] > 0) and len(tr) == 2 and np.all(tr[:, 1] >= 1)
+    f.close()
+    with pytest.raises(bvg._lib.BvgError, match="gene-sharded"):
+        bvg.Fit(p["phi"], p["y"], "gaussian", "fast", "auto", algorithm="pathfinder", world_size=2, rank=0, G_total=24, gene_offset=0)
 
 
 def test_divergent_fit_fails_like_the_reference_algorithm():

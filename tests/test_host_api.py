@@ -32,7 +32,7 @@ def test_validation_messages_match_the_reference():
     with pytest.raises(ValueError, match="valid variational inference approximation algorithm"):
         f(o, ["gene1"], algorithm="hmc")
     # accepted by the reference, rejected clearly here (no fallback)
-    for kw in (dict(algorithm="pathfinder"), dict(opencl_params=[0, 0]),
+    for kw in (dict(opencl_params=[0, 0]),
                dict(lscale_estimator="variogram")):
         with pytest.raises(NotImplementedError):
             f(o, ["gene1"], **kw)

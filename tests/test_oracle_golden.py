@@ -143,3 +143,42 @@ def test_fullrank_family_restatement():
     # a short fit runs and its draws are finite
     m, L, info = o.advi_fullrank(np.zeros(D), iter=200, elbo_samples=20, seed=3)
     assert info["rc"] == 0 and np.isfinite(info["elbo"]) and np.all(np.isfinite(o.summary_fullrank(m, L, 50, 3)))
+
+
+def test_pathfinder_restatement():
+    """algorithm = "pathfinder" [U: stan pathfinder; Zhang et al. 2022]: the Gaussian approximation built from curvature
+    pairs equals the BFGS recursion started at diag(alpha) (mean, covariance, log density); PSIS weights behave; a whole
+    multi-path run produces finite summaries"""
+    from scipy.stats import multivariate_normal
+    from tests.util import make_problem
+    rng = np.random.default_rng(0)
+    D, n = 12, 4
+    A = rng.normal(size=(D, D))
+    Hs = A @ A.T + np.eye(D)
+    S = rng.normal(size=(n, D))
+    Y = S @ Hs                                          # exact curvature pairs of a quadratic: s'y > 0
+    alpha, x, g = np.exp(rng.normal(0, 0.3, D)), rng.normal(size=D), rng.normal(size=D)
+    u = np.vstack([np.eye(D), rng.normal(size=(3, D))])
+    phi, lq, xc = orc.pf_approx(alpha, S, Y, x, g, u)
+    H = np.diag(alpha)
+    for s, y in zip(S, Y):                              # BFGS inverse-Hessian recursion
+        rho = 1 / (y @ s)
+        V = np.eye(D) - rho * np.outer(s, y)
+        H = V @ H @ V.T + rho * np.outer(s, s)
+    assert np.allclose(xc, x - H @ g, rtol=1e-12, atol=1e-13)
+    Am = (phi[:D] - xc).T                               # phi - xc = A u with A A' = Sigma
+    assert np.allclose(Am @ Am.T, H, rtol=1e-11, atol=1e-13)
+    assert np.allclose(lq[D:], multivariate_normal(mean=xc, cov=H).logpdf(phi[D:]), rtol=1e-11)
+    # n = 0: the approximation is N(x - alpha g, diag(alpha))
+    phi0, lq0, xc0 = orc.pf_approx(alpha, np.zeros((0, D)), np.zeros((0, D)), x, g, u[D:])
+    assert np.allclose(xc0, x - alpha * g) and np.allclose(phi0, xc0 + np.sqrt(alpha) * u[D:])
+    assert np.allclose(lq0, multivariate_normal(mean=xc0, cov=np.diag(alpha)).logpdf(phi0), rtol=1e-12)
+    # PSIS: weights sum to one; light-tailed ratios give a small k, heavy-tailed ones a large k
+    w1, k1 = orc.psis_weights(rng.normal(0, 0.1, 2000))
+    w2, k2 = orc.psis_weights(3.0 * rng.standard_t(2, 2000))
+    assert w1.sum() == pytest.approx(1) and w2.sum() == pytest.approx(1) and k1 < 0.5 < k2 and w1.max() < 0.01
+    p = make_problem(100, 8, 3, "gaussian", seed=1)
+    o = orc.Oracle(p["phi"], p["y"])
+    out, info = o.pathfinder(max_lbfgs_iters=40, history=6, num_elbo_draws=15, num_draws=100, num_paths=2, num_psis_draws=120, seed=2)
+    assert info["rc"] == 0 and np.all(np.isfinite(out)) and all(q["best_iter"] >= 1 for q in info["paths"])
+    assert orc.uniform(1, 5, 0, 0) != orc.uniform(1, 5, 1, 0) and 0 < orc.uniform(1, 5, 0, 0) < 1
