@@ -325,6 +325,35 @@ def run_ours(args, rank, world, local_rank):
                           "algorithmic_bytes_per_launch": bl, "ms_per_elbo_grad_eval": ms_eval_l}
         fl.close()
 
+    # ---- the large-basis kernels (BASELINE config 5: k ~ 400) against the TENSOR roofline: two tcgen05 GEMM kernels,
+    # BF16x3 (every product is 3 bf16 MMAs), 50,000 spots x 1,280 genes = a quarter of a config-5 shard ----
+    roofline_kbig = None
+    if world == 1 and not args.skip_large and not cfg4:
+        from bayesvg_b200 import synth
+        Mb, Gb, kb = 50000, 1280, 400
+        Xb = synth.scale_coords(synth.random_points(Mb, 2))
+        Cb = bvg.kmeans_centers(Xb, kb, 30, 1, rng=312, device=local_rank)
+        from bayesvg_b200.api import length_scale_kmeans
+        phib = bvg.basis_build(Xb, Cb, length_scale_kmeans(Cb), "matern", 1.5, device=local_rank)
+        rngb = np.random.default_rng(312)
+        Yb = np.asfortranarray((phib @ rngb.normal(size=(kb, Gb))) * np.sqrt(Mb / kb) * 0.3 + rngb.normal(size=(Mb, Gb)))
+        Yb = (Yb - Yb.mean()) / Yb.std(ddof=1)
+        fb = bvg.Fit(phib, Yb, "gaussian", "fast", args.engine, **cfg)
+        fb.set_variational(np.zeros(fb.D), None)
+        fb.advi_steps(3, 0.1, reset=True)
+        ms_b = fb.time_lik_kernel(20, False, True)
+        ms_eval_b = fb.advi_steps(20, 0.1) / 20
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+        tpeak = float(peaks.get("bf16_tflops_sustained", 1418.0))
+        executed = 3 * 4.0 * (kb + 1) * Mb * Gb / (ms_b * 1e-3) / 1e12
+        roofline_kbig = {"workload": "50,000 spots x 1,280 genes, k = 400 (quarter of a config-5 shard), gaussian", "bound": "tensor",
+                         "kernel": "k_tcbig<FWD> + k_tcbig<BWD> (BF16x3 tcgen05 GEMMs)", "achieved": executed, "peak": tpeak,
+                         "unit": "TFLOP/s", "frac": executed / tpeak, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained",
+                         "algorithmic_tflops": (4.0 * kb * Mb * Gb + 12.0 * Mb * Gb) / (ms_b * 1e-3) / 1e12,
+                         "ms_per_pass": ms_b, "ms_per_elbo_grad_eval": ms_eval_b,
+                         "what": "achieved = executed bf16 MMA flops (3 MMAs per product x 2 GEMMs x 2 flop); algorithmic = 4 k M G + 12 M G per pass"}
+        fb.close()
+
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu and not cfg4:
         nthreads = os.cpu_count() or 1
@@ -348,7 +377,7 @@ def run_ours(args, rank, world, local_rank):
                                     ("2k+10 fp64 sums per eval, all-reduced inside k_gene's last CTA over CUDA-IPC peer memory (NVLink)"
                                      if args.comm == "peer" else "2k+10 fp64 sums per eval, ncclAllReduce between k_gene and k_finish"))},
             "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-            "roofline_input_larger_than_l2": roofline_large, "cpu_baseline": cpu, "fit": fit_info,
+            "roofline_input_larger_than_l2": roofline_large, "roofline_large_basis": roofline_kbig, "cpu_baseline": cpu, "fit": fit_info,
         }))
     if world > 1:
         import torch.distributed as td
