@@ -360,6 +360,10 @@ def run_ours(args, rank, world, local_rank):
         n, dt = cpu_evals(phi, Y, args.cpu_seconds, 3, nthreads)
         cpu = {"value": n / dt, "unit": "evals/s", "cores": nthreads, "kind": "port",
                "sample": f"{n} ELBO-gradient evals of the full 4,992 x 3,000 workload in {dt:.1f} s (fp64 C restatement, OpenMP)"}
+        # the reference's meanfield fit is single-threaded (stan_threads = FALSE, findSpatiallyVariableFeaturesBayes.R:123-129)
+        n1, dt1 = cpu_evals(phi, Y, 3.0, 3, 1)
+        cpu["single_thread"] = {"value": n1 / dt1, "unit": "evals/s", "cores": 1,
+                                "sample": f"{n1} evals in {dt1:.1f} s on one thread (what stan_threads = FALSE gives the reference)"}
     fit.close()
     if rank == 0:
         print(json.dumps({

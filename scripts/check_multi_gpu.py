@@ -27,7 +27,9 @@ def main():
                                          ("nb", "fast", "tcgen05", "nccl", 12, False),
                                          ("gaussian", "fp64", "simt", "peer", 12, True),      # depth-adjusted (approxGP2)
                                          ("nb", "fast", "tcgen05", "peer", 12, True),         # depth-adjusted (approxGP3)
-                                         ("gaussian", "fp64", "auto", "peer", 40, False)):    # large basis: split exchange path
+                                         ("gaussian", "fp64", "auto", "peer", 40, False),     # large basis: split exchange path
+                                         ("gaussian", "fast", "auto", "peer", 40, False),     # large basis on the tcgen05 GEMM kernels
+                                         ("nb", "fast", "auto", "nccl", 40, False)):
         M, G = 400, 301
         p = make_problem(M, G, k, lik, seed=3)
         depths = np.log(np.random.default_rng(8).integers(300, 90000, G).astype(np.float64)) if dep else None
