@@ -72,7 +72,7 @@ def main():
         out = dict(workload=f"config 5: {M} spots x {Gt} genes, k = {k}, periodic, gaussian, meanfield", n_gpus=world, genes_per_gpu=G,
                    ms_per_elbo_grad_eval=ms, evals_per_s=1e3 / ms, algorithmic_tflops=(4.0 * k * M * Gt + 12.0 * M * Gt) / (ms * 1e-3) / 1e12,
                    fit_wall_s=wall, advi_iters=st["advi_iters"], grad_evals=st["grad_evals"], elbo_evals=st["elbo_evals"], eta=st["eta"],
-                   mle_iters=st["mle_iters"], sec_mle=st["sec_mle"], sec_adapt=st["sec_adapt"], sec_sga=st["sec_sga"],
+                   mle_iters=st["mle_iters"], mle_term=st["mle_term"], mle_lp=st["mle_lp"], mle_fevals=st["mle_fevals"], converged=st["converged"], elbo=st["elbo"], sec_mle=st["sec_mle"], sec_adapt=st["sec_adapt"], sec_sga=st["sec_sga"],
                    spearman_amplitude_vs_truth_rank0_shard=rho)
         print(json.dumps(out))
         json.dump(out, open(f"gpurun_out/r1b_cfg5_n{world}.json", "w"), indent=1)
