@@ -65,6 +65,7 @@ int basis_build_device(cudaStream_t st, const double *d_X, int64_t M, const doub
                        double nu, double period, double *d_Q, double *d_work);
 void comm_destroy(bvg_fit *f);
 
+static int g_no_elbo_batch = 0;   // diagnostics: BVG_NO_ELBO_BATCH=1 keeps one k_prep launch per ELBO draw
 static double now_s() {
   return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
@@ -92,6 +93,7 @@ extern "C" int bvg_fit_create(const bvg_config *cfg, bvg_fit **out) {
   CUDA_TRY(cudaSetDevice(cfg->device));
   bvg_fit *f = new bvg_fit();
   memset(f, 0, sizeof(*f));
+  { const char *e = getenv("BVG_NO_ELBO_BATCH"); g_no_elbo_batch = e && e[0] == '1'; }
   f->cfg = *cfg;
   CUDA_TRY(cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking));
   CUDA_TRY(cudaEventCreate(&f->ev0));
@@ -102,6 +104,8 @@ extern "C" int bvg_fit_create(const bvg_config *cfg, bvg_fit **out) {
 
 static void free_model(bvg_fit *f) {
   fr_destroy(f);
+  cudaFree(f->eb_d);
+  f->eb_d = nullptr; f->eb_cap = 0;
   tc_destroy(f);
   tcbig_destroy(f);
   suff_destroy(f);
@@ -522,7 +526,37 @@ static int advi_elbo(bvg_fit *f, int S, double *out) {
     if (std::isnan(*out)) *out = -INFINITY;
     return BVG_OK;
   }
-  for (int s = 0; s < S; ++s) BVG_TRY(eval_log_prob_device(f, MODE_ELBO_DRAW, 1, 0, false));
+  if (f->engine == BVG_ENGINE_TCGEN05 && !f->big_tc && f->m.k <= BVG_SMALL_K && !g_no_elbo_batch) {
+    // fused tcgen05 engine: mu / omega do not change between the S draws, so ONE batched k_prep launch makes all of them
+    // (throughput-bound: ~0.2 ms for 150 x 66,045 Philox / Box-Muller / exp chains) instead of S latency-bound launches of
+    // ~11 us each; every draw is then two launches (forward-only likelihood pass, per-gene kernel + finish)
+    const int k = f->m.k;
+    const size_t nd = (size_t)D + 4 + k + (size_t)f->m.G, nf = (size_t)f->m.Gpad * 32 + 96;
+    if (f->eb_cap < S) {
+      cudaFree(f->eb_d);
+      f->eb_d = nullptr; f->eb_cap = 0;
+      CUDA_TRY(cudaMalloc(&f->eb_d, (size_t)S * (nd * sizeof(double) + nf * sizeof(float))));
+      CUDA_TRY(cudaMemsetAsync(f->eb_d, 0, (size_t)S * (nd * sizeof(double) + nf * sizeof(float)), f->stream));  // W pads stay zero
+      f->eb_cap = S;
+    }
+    double *bz = f->eb_d, *bs = bz + (size_t)f->eb_cap * D, *ba = bs + (size_t)f->eb_cap * (4 + k);
+    float *bw = (float *)(ba + (size_t)f->eb_cap * f->m.G), *bu = bw + (size_t)f->eb_cap * f->m.Gpad * 32;
+    DevModel &m = f->m;
+    double *z0 = m.zeta, *s0 = m.shx, *a0 = m.Aexp;
+    float *w0 = m.W, *u0 = m.U;
+    m.zeta = bz; m.shx = bs; m.Aexp = ba; m.W = bw; m.U = bu;
+    int rc = launch_prep_batch(f, PREP_ELBO, S);
+    for (int s = 0; s < S && rc == BVG_OK; ++s) {
+      m.zeta = bz + (size_t)s * D; m.shx = bs + (size_t)s * (4 + k); m.Aexp = ba + (size_t)s * m.G;
+      m.W = bw + (size_t)s * m.Gpad * 32; m.U = bu + (size_t)s * 96;
+      rc = launch_lik(f, false);
+      if (rc == BVG_OK) rc = launch_gene_finish(f, MODE_ELBO_DRAW, 1, 0);
+    }
+    m.zeta = z0; m.shx = s0; m.Aexp = a0; m.W = w0; m.U = u0;
+    BVG_TRY(rc);
+  } else {
+    for (int s = 0; s < S; ++s) BVG_TRY(eval_log_prob_device(f, MODE_ELBO_DRAW, 1, 0, false));
+  }
   BVG_TRY(vec_dot_sum(f->stream, f->m.omega, nullptr, f->scratch + D, D, f->m.tot));
   BVG_TRY(comm_allreduce(f, f->m.tot, 2));
   double hs[2];

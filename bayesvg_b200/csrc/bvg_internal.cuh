@@ -292,6 +292,8 @@ struct bvg_fit {
   void *comm;
   void *fr;            // full-rank ADVI state (k_fullrank.cu), allocated on first use
   int *pf_idx;         // pathfinder: indices of the PSIS-resampled draws (host)
+  double *eb_d;        // batched ELBO draws: [cap][D | 4 + k | G] doubles, then [cap][Gpad * 32 | 96] floats
+  int eb_cap;
   int elbo_cap;        // capacity of m.elbo_lps
   void *peer_buf;      // this rank's exchange buffer (cudaMalloc, exported with cudaIpcGetMemHandle)
   void *peer_map[BVG_MAX_PEERS];  // peers' buffers opened with cudaIpcOpenMemHandle
@@ -314,6 +316,7 @@ void bvg_set_error(const char *fmt, ...);
 
 // launchers (one per translation unit)
 int launch_prep(bvg_fit *f, int mode);                       // k_model.cu: draw + transform -> C
+int launch_prep_batch(bvg_fit *f, int mode, int B);          // k_model.cu: B draws in one launch (fused tcgen05 engine)
 int launch_lik(bvg_fit *f, bool backward);                   // k_lik_simt.cu / k_lik_tc.cu dispatch
 int launch_lik_simt(bvg_fit *f, bool backward);
 int launch_lik_tc(bvg_fit *f, bool backward);

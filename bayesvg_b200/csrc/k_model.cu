@@ -24,7 +24,13 @@ __global__ void __launch_bounds__(256) k_prep(DevModel m, int mode, int tc, int 
   const int k = m.k, nsh = 2 * k + 5, npg = k + 2, tid = threadIdx.x;
   double *sal = sh + nsh, *zg = sal + k, *Ag = zg + gpb * npg;
   const uint32_t stream = mode == PREP_GRAD ? STREAM_GRAD : (mode == PREP_DRAW ? STREAM_DRAW : STREAM_ELBO);
-  const uint32_t t = mode == PREP_GRAD ? m.ctl->t_grad : (mode == PREP_DRAW ? m.ctl->t_draw : m.ctl->t_elbo);
+  // batched form (gridDim.y = B draws, tcgen05 engine): draw b of the batch uses counter t + b and leaves its zeta / shx /
+  // Aexp / W / U in slice b of the batch buffers the model descriptor points at (advi_elbo: all draws of an ELBO estimate in
+  // one throughput-bound launch instead of one latency-bound launch per draw)
+  const uint32_t bb = blockIdx.y;
+  const uint32_t t = (mode == PREP_GRAD ? m.ctl->t_grad : (mode == PREP_DRAW ? m.ctl->t_draw : m.ctl->t_elbo)) + bb;
+  double *const zeta_o = m.zeta + (size_t)bb * m.L.D, *const shx_o = m.shx + (size_t)bb * (4 + k), *const Aexp_o = m.Aexp + (size_t)bb * m.G;
+  float *const W_o = m.W + (size_t)bb * m.Gpad * 32, *const U_o = m.U + (size_t)bb * 96;
   // ---- phase 1: every parameter's zeta ----
   const int t2 = tid - nsh, gl = t2 >= 0 ? t2 / npg : -1, j = t2 >= 0 ? t2 - gl * npg : 0;
   const int64_t g = (int64_t)blockIdx.x * gpb + gl;
@@ -43,7 +49,7 @@ __global__ void __launch_bounds__(256) k_prep(DevModel m, int mode, int tc, int 
     double z;
     if (mode != PREP_NONE) {
       z = m.mu[li] + exp(m.omega[li]) * bvg_normal(m.seed, stream, t, (uint64_t)gi);
-      if (is_gene || blockIdx.x == 0) m.zeta[li] = z;
+      if (is_gene || blockIdx.x == 0) zeta_o[li] = z;
     } else {
       z = m.zeta[li];
     }
@@ -52,25 +58,25 @@ __global__ void __launch_bounds__(256) k_prep(DevModel m, int mode, int tc, int 
   __syncthreads();
   // ---- phase 2: the exponentials (sigma_alpha, sigma_beta0 in place, A_g = amplitude^2) ----
   // (also published for k_gene / finish_body: shx = [sigma_beta0, sigma_amplitude, tail, sigma_alpha[k]], Aexp[g])
-  if (tid < k) { const double e = exp(sh[5 + k + tid]); sal[tid] = e; if (blockIdx.x == 0) m.shx[3 + tid] = e; }
-  else if (tid == k) { const double e = m.depth ? sh[1] : exp(sh[1]); sh[1] = e; if (blockIdx.x == 0) m.shx[0] = e; }  // sigma_beta0 | beta1
+  if (tid < k) { const double e = exp(sh[5 + k + tid]); sal[tid] = e; if (blockIdx.x == 0) shx_o[3 + tid] = e; }
+  else if (tid == k) { const double e = m.depth ? sh[1] : exp(sh[1]); sh[1] = e; if (blockIdx.x == 0) shx_o[0] = e; }  // sigma_beta0 | beta1
   else if (tid > k && tid <= k + gpb) {
     const int q = tid - k - 1;
     const double e = exp(2.0 * zg[q * npg + k + 1]);  // approxGP.stan:27
     Ag[q] = e;
-    if ((int64_t)blockIdx.x * gpb + q < m.G) m.Aexp[(int64_t)blockIdx.x * gpb + q] = e;
-  } else if (blockIdx.x == 0 && tid == k + gpb + 1) m.shx[1] = exp(sh[3]);
+    if ((int64_t)blockIdx.x * gpb + q < m.G) Aexp_o[(int64_t)blockIdx.x * gpb + q] = e;
+  } else if (blockIdx.x == 0 && tid == k + gpb + 1) shx_o[1] = exp(sh[3]);
   else if (blockIdx.x == 0 && tid == k + gpb + 2) {
     const double e = exp(sh[4]);
-    m.shx[2] = e;
-    m.shx[3 + k] = m.lik == BVG_GAUSSIAN ? 1.0 / (e * e) : 1.0;
+    shx_o[2] = e;
+    shx_o[3 + k] = m.lik == BVG_GAUSSIAN ? 1.0 / (e * e) : 1.0;
   }
   __syncthreads();
   // ---- phase 3: coefficient rows c'_g = (A_g alpha_t[,g], beta0_g) ----
   if (tc) {  // tcgen05 engine: publish the draw in fp32 (W rows, U vector); the likelihood kernel forms c'_g itself
-    if (is_gene) m.W[g * 32 + j] = (float)(j == k + 1 ? Ag[gl] : zg[gl * npg + j]);
-    if (blockIdx.x == 0 && tid < k) { m.U[tid] = (float)sh[5 + tid]; m.U[32 + tid] = (float)sal[tid]; }
-    if (blockIdx.x == 0 && tid == k) { m.U[64] = (float)sh[0]; m.U[65] = (float)sh[1]; }
+    if (is_gene) W_o[g * 32 + j] = (float)(j == k + 1 ? Ag[gl] : zg[gl * npg + j]);
+    if (blockIdx.x == 0 && tid < k) { U_o[tid] = (float)sh[5 + tid]; U_o[32 + tid] = (float)sal[tid]; }
+    if (blockIdx.x == 0 && tid == k) { U_o[64] = (float)sh[0]; U_o[65] = (float)sh[1]; }
     return;
   }
   if (!is_gene || j == k + 1) return;
@@ -159,6 +165,19 @@ int launch_prep(bvg_fit *f, int mode) {
   const size_t sh = sizeof(double) * (3 * k + 5 + gpb * (k + 3));
   if (f->cfg.precision == BVG_PREC_FP64) CUDA_TRY(launch_pdl(k_prep<double>, dim3(grid), dim3(256), sh, f->stream, f->m, mode, 0, gpb));
   else CUDA_TRY(launch_pdl(k_prep<float>, dim3(grid), dim3(256), sh, f->stream, f->m, mode, (int)(f->engine == BVG_ENGINE_TCGEN05 && !f->big_tc), gpb));
+  f->st.kernel_launches++;
+  return BVG_OK;
+}
+
+// B draws of one stream in ONE launch (tcgen05 engine, k <= BVG_SMALL_K): slice b of the buffers f->m.{zeta, shx, Aexp, W, U}
+// currently point at receives draw (counter + b).  The caller points the descriptor at batch buffers first.
+int launch_prep_batch(bvg_fit *f, int mode, int B) {
+  const int k = f->m.k;
+  if (k > BVG_SMALL_K || f->cfg.precision == BVG_PREC_FP64 || f->engine != BVG_ENGINE_TCGEN05 || f->big_tc) { bvg_set_error("batched draws need the fused tcgen05 engine"); return BVG_ERR_STATE; }
+  const int gpb = (256 - (2 * k + 5)) / (k + 2);
+  const int grid = (int)((f->m.G + gpb - 1) / gpb);
+  const size_t sh = sizeof(double) * (3 * k + 5 + gpb * (k + 3));
+  CUDA_TRY(launch_pdl(k_prep<float>, dim3(grid, B), dim3(256), sh, f->stream, f->m, mode, 1, gpb));
   f->st.kernel_launches++;
   return BVG_OK;
 }

@@ -11,7 +11,8 @@
 #                     gene_depths (:303, log(rowSums(counts[naive.hvgs, ]))) when gene.depth.adjust = TRUE, else NULL
 bvg_fit_backend <- function(spatial_mtx, kmeans_centers, lscale, expr_df, gene_mapping, likelihood, kernel,
                             kernel.smoothness, kernel.period, n.iter, mle.init, mle.iter, n.draws,
-                            elbo.samples, random.seed, verbose, gene_depths = NULL, device = 0L, save.model = FALSE) {
+                            elbo.samples, random.seed, verbose, gene_depths = NULL, device = 0L, save.model = FALSE,
+                            algorithm = "meanfield", n.cores = 2L) {
   M <- nrow(spatial_mtx)
   G <- length(unique(expr_df$gene))
   kernel_id <- match(kernel, c("exp_quad", "matern", "periodic")) - 1L
@@ -27,6 +28,8 @@ bvg_fit_backend <- function(spatial_mtx, kmeans_centers, lscale, expr_df, gene_m
                                         n_draws = as.integer(n.draws), elbo_samples = as.integer(elbo.samples),
                                         seed = as.integer(random.seed), verbose = as.integer(verbose),
                                         depth_adjust = as.integer(!is.null(gene_depths)),  # approxGP2 / approxGP3 (:293-318)
+                                        algorithm = match(algorithm, c("meanfield", "fullrank", "pathfinder")) - 1L,  # :357-375
+                                        pf_num_paths = as.integer(n.cores),                # num_paths = n.cores (:372)
                                         device = as.integer(device)))
   on.exit(.Call("R_bvg_fit_destroy", fit), add = TRUE)
   .Call("R_bvg_fit_set_phi", fit, phi_ortho)

@@ -53,6 +53,9 @@ SEXP R_bvg_fit_create(SEXP opts) {
   cfg.elbo_samples = geti(opts, "elbo_samples", cfg.elbo_samples);
   cfg.verbose = geti(opts, "verbose", cfg.verbose);
   cfg.depth_adjust = geti(opts, "depth_adjust", cfg.depth_adjust);
+  cfg.algorithm = geti(opts, "algorithm", cfg.algorithm);            /* 0 meanfield, 1 fullrank, 2 pathfinder (:108) */
+  cfg.pf_num_paths = geti(opts, "pf_num_paths", cfg.pf_num_paths);   /* num_paths = n.cores (:372) */
+  cfg.lbfgs_history = geti(opts, "lbfgs_history", cfg.lbfgs_history);
   cfg.seed = (uint64_t)geti(opts, "seed", (int)cfg.seed);
   bvg_fit *f = NULL;
   chk(bvg_fit_create(&cfg, &f));
