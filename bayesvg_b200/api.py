@@ -215,8 +215,10 @@ def findSpatiallyVariableFeaturesBayes(sp_obj=None, naive_hvgs=None, likelihood=
         raise NotImplementedError("save.model = TRUE is not built for algorithm = 'pathfinder'.")
     if opencl_params is not None:
         raise NotImplementedError("opencl.params is meaningless here: the fit always runs on the CUDA device.")
-    if lscale_estimator != "kmeans":
-        raise NotImplementedError("lscale.estimator = 'variogram' is not built in bayesvg_b200; use 'kmeans'.")
+    if lscale_estimator not in ("kmeans", "variogram"):
+        _abort("Please provide a valid length-scale estimator.")
+    if lscale_estimator == "variogram" and kernel_smoothness not in (0.5, 1.5, 2.5):
+        raise NotImplementedError("lscale.estimator = 'variogram' is built for kernel.smoothness in {0.5, 1.5, 2.5} only.")
     t_start = time.time()
     # coordinates (:154-161)
     X = scale_coords(sp_obj.coords)
@@ -248,7 +250,10 @@ def findSpatiallyVariableFeaturesBayes(sp_obj=None, naive_hvgs=None, likelihood=
     centers = np.asarray(centers, dtype=np.float64)
     if centers.shape != (n_basis_fns, 2):
         _abort("centers must be n.basis.fns x 2")
-    lscale = length_scale_kmeans(centers)
+    if lscale_estimator == "kmeans":
+        lscale = length_scale_kmeans(centers)
+    else:   # :208-260: median fitted Matern range of the per-gene empirical variograms (expr_mtx rows, not the z-scored vector)
+        lscale = E.variogram_lscale(X, np.asarray(expr, dtype=np.float64), kernel_smoothness, device)
     if verbose:
         print(f"i Estimated length-scale: {round(lscale, 4)}")
     phi = E.basis_build(X, centers, lscale, kernel, kernel_smoothness, float(kernel_period), device)

@@ -53,6 +53,19 @@ def kmeans(coords, k, iter_max=100, nstart=10, seed=312, device=0, return_info=F
     return out
 
 
+def variogram_lscale(coords, expr, kappa=1.5, device=0, return_ranges=False):
+    """lscale.estimator = "variogram" (findSpatiallyVariableFeaturesBayes.R:208-260) on the GPU: median over genes of the range of
+    a Matern variogram model fitted to each gene's empirical semivariogram.  coords M x 2 (scaled), expr G x M (genes x spots)."""
+    X = np.asfortranarray(coords, dtype=np.float64)
+    Z = np.asfortranarray(expr, dtype=np.float64)
+    if X.ndim != 2 or X.shape[1] != 2 or Z.ndim != 2 or Z.shape[1] != X.shape[0]:
+        raise ValueError("coords must be M x 2 and expr G x M")
+    ranges = np.empty(Z.shape[0])
+    ls = C.c_double()
+    B.check(B.lib().bvg_variogram_lscale(device, _dp(X), X.shape[0], _dp(Z), Z.shape[0], float(kappa), _dp(ranges), C.byref(ls)))
+    return (ls.value, ranges) if return_ranges else ls.value
+
+
 class Fit:
     """gene_depths (length G, log of each gene's total count) selects the depth-adjusted programs
     inst/approxGP2.stan / approxGP3.stan (gene.depth.adjust = TRUE in the reference)."""

@@ -117,6 +117,14 @@ int bvg_basis_build(int device, const double *coords, int64_t M, const double *c
 int bvg_kmeans(int device, const double *coords, int64_t M, int k, int iter_max, int nstart, uint64_t seed,
                double *centers_out, double *tot_withinss, int32_t *info);
 
+/* lscale.estimator = "variogram" (:208-260): per gene, gstat::variogram(z ~ 1) (cutoff = bounding-box diagonal / 3, 15 distance
+ * classes) and gstat::fit.variogram of vgm(0.8 var, "Mat", median(dist), 0.2 var, kappa = kernel.smoothness) by weighted least
+ * squares (weights N_h / h^2) [U]; *lscale_out = median of the fitted ranges, NaN ranges (failed fits, constant genes) dropped.
+ * coords M x 2 col-major, scaled (:209-211); expr G x M col-major = R's expr_mtx[naive.hvgs, ] (:174); kappa in {0.5, 1.5, 2.5};
+ * ranges_out (G) may be NULL. */
+int bvg_variogram_lscale(int device, const double *coords, int64_t M, const double *expr, int64_t G, double kappa,
+                         double *ranges_out, double *lscale_out);
+
 int bvg_fit_create(const bvg_config *cfg, bvg_fit **out);
 void bvg_fit_destroy(bvg_fit *);
 

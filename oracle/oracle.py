@@ -281,6 +281,43 @@ def unpack_tril(Lp, D):
     return out
 
 
+def variogram(coords, expr, kappa=1.5):
+    """lscale.estimator = "variogram" (findSpatiallyVariableFeaturesBayes.R:208-260), numpy / scipy restatement for small cases:
+    gstat::variogram(z ~ 1) defaults [U] (cutoff = bounding-box diagonal / 3, 15 classes of width cutoff / 15, gamma = sum (z_i -
+    z_j)^2 / (2 N_h), dist = mean pair distance) and gstat::fit.variogram of nugget + Matern(kappa) by weighted least squares with
+    weights N_h / h^2 [U], started at vgm(0.8 var, "Mat", median(dist), 0.2 var) (:241-245).  Returns (median range, ranges, table)."""
+    from scipy.optimize import least_squares
+    X, Z = np.asarray(coords, dtype=np.float64), np.asarray(expr, dtype=np.float64)
+    M, G = X.shape[0], Z.shape[0]
+    cutoff = np.sqrt(((X.max(0) - X.min(0)) ** 2).sum()) / 3.0
+    width = cutoff / 15
+    iu, ju = np.triu_indices(M, 1)
+    dx, dy = X[iu, 0] - X[ju, 0], X[iu, 1] - X[ju, 1]
+    h = np.sqrt(dx * dx + dy * dy)
+    keep = (h > 0) & (h <= cutoff)
+    iu, ju, h = iu[keep], ju[keep], h[keep]
+    b = np.minimum(np.floor(h / width).astype(int), 14)
+    npairs = np.bincount(b, minlength=15).astype(np.float64)
+    dist = np.bincount(b, weights=h, minlength=15) / np.maximum(npairs, 1)
+    use = npairs > 0
+    rho = {0.5: lambda x: np.exp(-x), 1.5: lambda x: (1 + x) * np.exp(-x), 2.5: lambda x: (1 + x + x * x / 3) * np.exp(-x)}[kappa]
+    ranges, gam_all = np.full(G, np.nan), np.zeros((G, 15))
+    for g in range(G):
+        d2 = (Z[g, iu] - Z[g, ju]) ** 2
+        gam = np.bincount(b, weights=d2, minlength=15) / (2 * np.maximum(npairs, 1))
+        gam_all[g] = gam
+        var = Z[g].var(ddof=1)
+        if not var > 0 or use.sum() < 3:
+            continue
+        hh, gg, ww = dist[use], gam[use], np.sqrt(npairs[use] / dist[use] ** 2)
+        p0 = np.array([0.2 * var, 0.8 * var, np.median(hh)])
+        res = least_squares(lambda p: ww * (gg - (p[0] + p[1] * (1 - rho(hh / p[2])))) if p[2] > 0 else np.full(len(hh), 1e150), p0,
+                            method="lm", xtol=1e-14, ftol=1e-14, gtol=1e-14, max_nfev=2000)
+        if np.isfinite(res.x[2]) and res.x[2] > 0:
+            ranges[g] = res.x[2]
+    return float(np.nanmedian(ranges)), ranges, dict(np=npairs, dist=dist, gamma=gam_all, cutoff=cutoff)
+
+
 def pf_approx(alpha, S, Y, x, g, u):
     """test hook: Pathfinder's Gaussian approximation from curvature pairs S, Y ([n][D], oldest first)"""
     alpha, S, Y, x, g, u = (np.ascontiguousarray(a, dtype=np.float64) for a in (alpha, S, Y, x, g, u))

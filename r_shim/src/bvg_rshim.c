@@ -31,6 +31,29 @@ SEXP R_bvg_basis_build(SEXP coords, SEXP centers, SEXP lscale, SEXP kernel, SEXP
   return out;
 }
 
+/* .Call("R_bvg_variogram_lscale", spatial_mtx (M x 2, scaled), expr_mtx[naive.hvgs, ] (G x M), kernel.smoothness, device)
+ * -> list(lscale =, ranges =): replaces the foreach / gstat loop of :208-260 */
+SEXP R_bvg_variogram_lscale(SEXP coords, SEXP expr, SEXP kappa, SEXP device) {
+  const int64_t M = Rf_nrows(coords), G = Rf_nrows(expr);
+  SEXP ranges = PROTECT(Rf_allocVector(REALSXP, G));
+  double ls = 0;
+  chk(bvg_variogram_lscale(Rf_asInteger(device), REAL(coords), M, REAL(expr), G, Rf_asReal(kappa), REAL(ranges), &ls));
+  SEXP out = PROTECT(Rf_allocVector(VECSXP, 2));
+  SET_VECTOR_ELT(out, 0, Rf_ScalarReal(ls));
+  SET_VECTOR_ELT(out, 1, ranges);
+  UNPROTECT(2);
+  return out;
+}
+/* .Call("R_bvg_kmeans", spatial_mtx, k, iter.max, nstart, seed, device) -> k x 2 centres (:200-204) */
+SEXP R_bvg_kmeans(SEXP coords, SEXP k, SEXP iter_max, SEXP nstart, SEXP seed, SEXP device) {
+  const int kk = Rf_asInteger(k);
+  SEXP out = PROTECT(Rf_allocMatrix(REALSXP, kk, 2));
+  chk(bvg_kmeans(Rf_asInteger(device), REAL(coords), (int64_t)Rf_nrows(coords), kk, Rf_asInteger(iter_max), Rf_asInteger(nstart),
+                 (uint64_t)Rf_asInteger(seed), REAL(out), NULL, NULL));
+  UNPROTECT(1);
+  return out;
+}
+
 /* .Call("R_bvg_fit_create", list(likelihood=, precision=, n_iter=, mle_init=, mle_iter=, n_draws=,
  *        elbo_samples=, seed=, verbose=, device=, depth_adjust=)) -> external pointer */
 static int geti(SEXP lst, const char *name, int dflt) {
@@ -124,6 +147,7 @@ static const R_CallMethodDef calls[] = {
   {"R_bvg_log_prob", (DL_FUNC)&R_bvg_log_prob, 4},       {"R_bvg_fit_variational", (DL_FUNC)&R_bvg_fit_variational, 2},
   {"R_bvg_fit_destroy", (DL_FUNC)&R_bvg_fit_destroy, 1}, {"R_bvg_fit_set_gene_depths", (DL_FUNC)&R_bvg_fit_set_gene_depths, 2},
   {"R_bvg_fit_posterior", (DL_FUNC)&R_bvg_fit_posterior, 2},
+  {"R_bvg_variogram_lscale", (DL_FUNC)&R_bvg_variogram_lscale, 4}, {"R_bvg_kmeans", (DL_FUNC)&R_bvg_kmeans, 6},
   {NULL, NULL, 0}};
 void R_init_bayesVGb200(DllInfo *dll) {
   R_registerRoutines(dll, NULL, calls, NULL, NULL);

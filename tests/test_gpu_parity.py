@@ -371,6 +371,30 @@ def test_kmeans_centroids_equal_the_cpu_restatement(M, k, nstart, iter_max):
         bvg.engine.kmeans(X * 1e4, k)
 
 
+@pytest.mark.parametrize("kappa", [0.5, 1.5, 2.5])
+def test_variogram_length_scale_matches_the_cpu_restatement(kappa):
+    """lscale.estimator = "variogram" (R/findSpatiallyVariableFeaturesBayes.R:208-260): per-gene empirical semivariograms and
+    Matern variogram fits on the device against the numpy / scipy restatement (same classes, same weights, same start)"""
+    rng = np.random.default_rng(7)
+    M, G = 300, 37
+    X = bvg.scale_coords(rng.uniform(0, 100, (M, 2)))
+    d = np.sqrt(((X[:, None] - X[None]) ** 2).sum(-1))
+    K = (1 + d / 0.25) * np.exp(-d / 0.25) + 0.15 * np.eye(M)
+    Z = (np.linalg.cholesky(K) @ rng.normal(size=(M, G))).T * rng.uniform(0.5, 2, G)[:, None] + rng.normal(size=(G, 1))
+    Z[5] = 3.0                                                  # a constant gene: no variogram, NA in the reference
+    ls, ranges = bvg.engine.variogram_lscale(X, Z, kappa, return_ranges=True)
+    rls, rranges, _ = orc.variogram(X, Z, kappa)
+    assert np.isnan(ranges[5]) and np.isnan(rranges[5])
+    both = np.isfinite(ranges) & np.isfinite(rranges)
+    assert both.sum() >= G - 4
+    close = np.isclose(ranges[both], rranges[both], rtol=1e-4)
+    assert close.mean() >= 0.9, (ranges[both][~close], rranges[both][~close])    # the two optimisers may part on a flat objective
+    assert ls == pytest.approx(rls, rel=1e-3)
+    assert ls == bvg.engine.variogram_lscale(X, Z, kappa)                        # deterministic
+    with pytest.raises(bvg._lib.BvgError, match="smoothness"):
+        bvg.engine.variogram_lscale(X, Z, 2.0)
+
+
 def test_basis_visium_shape():
     from bayesvg_b200 import synth
     X = bvg.scale_coords(synth.visium_grid())

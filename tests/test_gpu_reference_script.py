@@ -92,5 +92,9 @@ def test_other_algorithms_of_the_same_call(brain):
         st = bvg.getBayesianGeneStats(o)
         assert st.shape[0] == len(hv) and np.all(np.isfinite(st["amplitude_mean"])) and np.all(st["amplitude_mean"] > 0)
     hv = brain[3][:40]
-    with pytest.raises(NotImplementedError):
-        bvg.findSpatiallyVariableFeaturesBayes(obj, naive_hvgs=hv, lscale_estimator="variogram", verbose=False)
+    # test_bayesVG.R:59-66: the Seurat call of the reference's script estimates the length-scale from per-gene variograms
+    o = bvg.findSpatiallyVariableFeaturesBayes(obj, naive_hvgs=hv, lscale_estimator="variogram", kernel="matern", kernel_smoothness=1.5,
+                                               n_cores=1, n_iter=300, n_draws=200, verbose=False, kmeans_rng=312)
+    assert bvg.getBayesianGeneStats(o).shape[0] == 40
+    with pytest.raises(ValueError, match="length-scale estimator"):
+        bvg.findSpatiallyVariableFeaturesBayes(obj, naive_hvgs=hv, lscale_estimator="idw", verbose=False)

@@ -32,8 +32,7 @@ def test_validation_messages_match_the_reference():
     with pytest.raises(ValueError, match="valid variational inference approximation algorithm"):
         f(o, ["gene1"], algorithm="hmc")
     # accepted by the reference, rejected clearly here (no fallback)
-    for kw in (dict(opencl_params=[0, 0]),
-               dict(lscale_estimator="variogram")):
+    for kw in (dict(opencl_params=[0, 0]),):
         with pytest.raises(NotImplementedError):
             f(o, ["gene1"], **kw)
     with pytest.raises(KeyError):

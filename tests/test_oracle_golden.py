@@ -182,3 +182,33 @@ def test_pathfinder_restatement():
     out, info = o.pathfinder(max_lbfgs_iters=40, history=6, num_elbo_draws=15, num_draws=100, num_paths=2, num_psis_draws=120, seed=2)
     assert info["rc"] == 0 and np.all(np.isfinite(out)) and all(q["best_iter"] >= 1 for q in info["paths"])
     assert orc.uniform(1, 5, 0, 0) != orc.uniform(1, 5, 1, 0) and 0 < orc.uniform(1, 5, 0, 0) < 1
+
+
+def test_variogram_restatement():
+    """lscale.estimator = "variogram" (:208-260): the empirical semivariogram against a brute-force double loop, and the fit
+    recovers the range of data simulated from the model it fits"""
+    rng = np.random.default_rng(3)
+    M = 60
+    X = rng.uniform(-1.7, 1.7, (M, 2))
+    Z = rng.normal(size=(2, M))
+    ls, ranges, tab = orc.variogram(X, Z, 1.5)
+    cutoff = np.sqrt(((X.max(0) - X.min(0)) ** 2).sum()) / 3
+    num, cnt, hs = np.zeros(15), np.zeros(15), np.zeros(15)
+    for i in range(M):
+        for j in range(i + 1, M):
+            h = np.hypot(*(X[i] - X[j]))
+            if 0 < h <= cutoff:
+                b = min(int(h // (cutoff / 15)), 14)
+                num[b] += (Z[0, i] - Z[0, j]) ** 2
+                cnt[b] += 1
+                hs[b] += h
+    assert np.array_equal(cnt, tab["np"]) and np.allclose(hs / np.maximum(cnt, 1), tab["dist"])
+    assert np.allclose(num / (2 * np.maximum(cnt, 1)), tab["gamma"][0])
+    # data from a Matern-1.5 field with range 0.3 (gstat "Mat": rho(h / a)), plus a nugget
+    M = 350
+    X = rng.uniform(-1.7, 1.7, (M, 2))
+    d = np.sqrt(((X[:, None] - X[None]) ** 2).sum(-1))
+    K = (1 + d / 0.3) * np.exp(-d / 0.3) + 0.1 * np.eye(M)
+    Z = (np.linalg.cholesky(K) @ rng.normal(size=(M, 40))).T
+    ls, ranges, _ = orc.variogram(X, Z, 1.5)
+    assert np.isfinite(ranges).sum() >= 35 and 0.15 < ls < 0.6
