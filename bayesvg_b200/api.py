@@ -327,3 +327,52 @@ def classifySVGs(obj, selection_method="rank", n_SVG=1000, quantile_SVG=0.75, cu
     order = df.loc[sel.fillna(False)].sort_values("amplitude_mean_rank").index
     obj.variable_features = list(order)
     return obj
+
+
+def clusterSVGsBayes(sp_obj=None, svgs=None, n_clust=5, n_PCs=30, algorithm="fullrank", n_iter=30000, n_draws=1000,
+                     elbo_samples=None, opencl_params=None, n_cores=2, random_seed=312, verbose=True, *, device=0):
+    """Drop-in for R/clusterSVGsBayes.R:63-319: scale the SVGs' expression, PCA, fit the Bayesian Gaussian mixture of
+    inst/clusterSVGs.stan by ADVI on the GPU, soft / hard cluster assignments, log-likelihood and BIC."""
+    if sp_obj is None or svgs is None:
+        _abort("All arguments to clusterSVGsBayes() must be supplied.")
+    if not isinstance(sp_obj, SpatialData):
+        _abort("Please provide an object of class Seurat or SpatialExperiment.")
+    if n_clust <= 1:
+        _abort("Please provide a valid number of clusters.")
+    algorithm = algorithm.lower()
+    if algorithm not in ("meanfield", "fullrank", "pathfinder"):
+        _abort("Please provide a valid variational inference approximation algorithm.")
+    if algorithm == "pathfinder":
+        raise NotImplementedError("algorithm = 'pathfinder' is not built for clusterSVGsBayes(); use 'fullrank' (the default) or 'meanfield'.")
+    if opencl_params is not None:
+        raise NotImplementedError("opencl.params is meaningless here: the fit always runs on the CUDA device.")
+    if algorithm == "meanfield" and verbose:
+        print("! The meanfield VI algorithm often does not perform well on clustering problems do to multi-modality and high "
+              "correlation of the posterior. Use caution and consider utilizing the default fullrank VI algorithm instead.")
+    if elbo_samples is None:
+        elbo_samples = 300
+    t_start = time.time()
+    gidx = {g: i for i, g in enumerate(sp_obj.genes)}
+    rows = [gidx[g] for g in svgs]
+    expr = np.asarray(sp_obj.data, dtype=np.float64)[rows, :]                                  # :125-132 layer "data", svgs x spots
+    expr = (expr - expr.mean(1, keepdims=True)) / expr.std(1, ddof=1, keepdims=True)           # t(coop::scaler(t(expr_mtx)))
+    # irlba::prcomp_irlba(expr_mtx, n = n.PCs, center = FALSE, scale. = FALSE)$x = U S of the leading singular triplets (:134-137)
+    U, S, _ = np.linalg.svd(expr, full_matrices=False)
+    n_pc = min(int(n_PCs), len(S))
+    emb = U[:, :n_pc] * S[:n_pc]
+    res = E.gmm_fit(emb, n_clust, algorithm, n_iter, n_draws, elbo_samples, random_seed, device=device)
+    soft = res["soft"]
+    K, D, N = int(n_clust), n_pc, emb.shape[0]
+    cluster_df = pd.DataFrame(soft, columns=[f"prob_cluster_{j + 1}" for j in range(K)])
+    cluster_df.insert(0, "gene", list(svgs))
+    cluster_df["assigned_cluster"] = soft.argmax(1) + 1                                          # :262-266 which.max
+    ll = res["info"]["log_likelihood"]                                                           # :281-284
+    p = (K - 1) + 2 * K * D                                                                      # :286
+    cols = ([f"theta[{j + 1}]" for j in range(K)] + [f"mu[{j + 1},{d + 1}]" for d in range(D) for j in range(K)]
+            + [f"sigma[{j + 1},{d + 1}]" for j in range(K) for d in range(D)])
+    model_fit = VariationalFit(cols, res["draws"], trace=None, stats=res["info"], mu_unconstrained=res["mu"], var=res["var"])
+    if verbose:
+        i = res["info"]
+        print(f"v ADVI ({algorithm}): eta = {i['eta']}, {i['iters']} iterations, ELBO = {i['elbo']:.6g}")
+        print(f"v bayesVG clustering of {len(svgs)} SVGs completed in {round(time.time() - t_start, 3)} seconds.")
+    return dict(pca_embedding=emb, cluster_df=cluster_df, model_fit=model_fit, log_likelihood=ll, BIC=-2 * ll + p * np.log(N))

@@ -66,6 +66,40 @@ def variogram_lscale(coords, expr, kappa=1.5, device=0, return_ranges=False):
     return (ls.value, ranges) if return_ranges else ls.value
 
 
+def gmm_log_prob(X, K, theta, jacobian=True, propto=False, grad=True, device=0):
+    """log density (and gradient) of inst/clusterSVGs.stan at an unconstrained vector; X: N x D PCA embedding"""
+    Xf = np.asfortranarray(X, dtype=np.float64)
+    N, D = Xf.shape
+    th = np.ascontiguousarray(theta, dtype=np.float64)
+    if th.shape != (K - 1 + 2 * K * D,):
+        raise ValueError("theta must have K - 1 + 2 K D entries")
+    lp = C.c_double()
+    g = np.empty_like(th) if grad else None
+    B.check(B.lib().bvg_gmm_log_prob(device, _dp(Xf), N, D, int(K), _dp(th), int(jacobian), int(propto), C.byref(lp), _dp(g) if grad else None))
+    return (lp.value, g) if grad else lp.value
+
+
+def gmm_fit(X, K, algorithm="fullrank", n_iter=30000, n_draws=1000, elbo_samples=300, seed=312, eval_elbo=100, adapt_iter=50, eta=0.0,
+            tol_rel_obj=0.01, device=0, return_draws=True):
+    """mod$variational(...) on inst/clusterSVGs.stan + the posterior pass (R/clusterSVGsBayes.R:153-291) on the GPU"""
+    if algorithm not in ("meanfield", "fullrank"):
+        raise ValueError("Please provide a valid variational inference approximation algorithm.")
+    Xf = np.asfortranarray(X, dtype=np.float64)
+    N, D = Xf.shape
+    K = int(K)
+    P = K - 1 + 2 * K * D
+    fr = algorithm == "fullrank"
+    opts = np.array([n_iter, n_draws, elbo_samples, eval_elbo, adapt_iter, eta, tol_rel_obj], dtype=np.float64)
+    mu, var = np.empty(P), np.empty(P * (P + 1) // 2 if fr else P)
+    draws = np.empty((n_draws, K + 2 * K * D)) if return_draws else None
+    soft, stats = np.empty((N, K)), np.empty(8)
+    B.check(B.lib().bvg_gmm_fit(device, _dp(Xf), N, D, K, int(fr), int(seed), _dp(opts), _dp(mu), _dp(var),
+                                _dp(draws) if return_draws else None, _dp(soft), _dp(stats)))
+    info = dict(eta=stats[0], iters=int(stats[1]), converged=int(stats[2]), elbo=stats[3], log_likelihood=stats[4], seconds=stats[5],
+                grad_evals=int(stats[6]), elbo_evals=int(stats[7]))
+    return dict(mu=mu, var=var, draws=draws, soft=soft, info=info)
+
+
 class Fit:
     """gene_depths (length G, log of each gene's total count) selects the depth-adjusted programs
     inst/approxGP2.stan / approxGP3.stan (gene.depth.adjust = TRUE in the reference)."""

@@ -125,6 +125,22 @@ int bvg_kmeans(int device, const double *coords, int64_t M, int k, int iter_max,
 int bvg_variogram_lscale(int device, const double *coords, int64_t M, const double *expr, int64_t G, double kappa,
                          double *ranges_out, double *lscale_out);
 
+/* The step after the fit: clusterSVGsBayes() (R/clusterSVGsBayes.R:63-319) = ADVI on inst/clusterSVGs.stan, a diagonal-covariance
+ * Gaussian mixture over the PCA embedding X of the SVGs (N x D COLUMN-major, as R holds svg_mtx_pca$x), K = n.clust clusters.
+ * Unconstrained vector (declaration order, :8-12): simplex[K] theta (K - 1 stick-breaking coordinates [U]), matrix[K, D] mu
+ * (column-major), array[K] vector<lower=0>[D] sigma (log); P = K - 1 + 2 K D.
+ * bvg_gmm_log_prob: the parity hook (log_prob / grad_log_prob of that program).
+ * bvg_gmm_fit: mod$variational(init = 0, algorithm = "meanfield" | "fullrank", iter, draws, elbo_samples) (:153-160) followed by
+ * the posterior pass of :201-291.  opts[7] = {n_iter (30000), n_draws (1000), elbo_samples (300), eval_elbo (100), adapt_iter (50),
+ * eta (<= 0: adapt), tol_rel_obj (0.01)}; mu_out [P]; var_out [P] (omega) or [P (P + 1) / 2] (packed row-major Cholesky factor);
+ * draws_out [n_draws][K + 2 K D] row-major (theta | mu column-major | sigma) or NULL; soft_out [N][K] row-major = the soft
+ * cluster assignment probabilities (:215-239); stats_out[8] = {eta, iterations, converged, last ELBO, log-likelihood (:281-284),
+ * seconds, gradient evaluations, ELBO estimates}.  One CTA runs every stretch of iterations without returning to the host. */
+int bvg_gmm_log_prob(int device, const double *X, int64_t N, int D, int K, const double *theta, int jacobian, int propto,
+                     double *lp, double *grad);
+int bvg_gmm_fit(int device, const double *X, int64_t N, int D, int K, int fullrank, uint64_t seed, const double *opts,
+                double *mu_out, double *var_out, double *draws_out, double *soft_out, double *stats_out);
+
 int bvg_fit_create(const bvg_config *cfg, bvg_fit **out);
 void bvg_fit_destroy(bvg_fit *);
 

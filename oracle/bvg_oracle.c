@@ -81,6 +81,10 @@ struct bvgo_ctx {
   const double *depths; /* gene_depths[G] of approxGP2/3.stan:9 (NULL for the hierarchical-intercept models) */
   int nthreads;
   layout_t L;
+  /* model == BVGO_GMM (inst/clusterSVGs.stan): X [N][Dx] row-major, K clusters; L.D = K - 1 + 2 K Dx */
+  int64_t gN;
+  int gD, gK;
+  const double *gX;
 };
 void bvgo_set_depths(bvgo_ctx *c, const double *gene_depths) { c->depths = gene_depths; }
 
@@ -135,7 +139,9 @@ static inline double inv_logit(double a) {
  * ---------------------------------------------------------------------------------------- */
 #define SB 256 /* spot block kept in L1 */
 
+static double gmm_log_prob(bvgo_ctx *c, const double *th, int jac, int propto, double *grad);
 double bvgo_log_prob(bvgo_ctx *c, const double *th, int jac, int propto, double *grad) {
+  if (c->model == BVGO_GMM) return gmm_log_prob(c, th, jac, propto, grad);
   const layout_t L = c->L;
   const int64_t M = c->M, G = c->G;
   const int k = c->k;
@@ -1199,6 +1205,149 @@ int bvgo_summary_fullrank(int model, int64_t G, int k, const double *mu, const d
   }
   fill_ranks(rk, G, out);
   free(rk); free(eta); free(x);
+  return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * inst/clusterSVGs.stan (R/clusterSVGsBayes.R:139-160): diagonal-covariance Gaussian mixture over the PCA embedding of the
+ * SVGs.  Parameters in declaration order (:8-12): simplex[K] theta (K - 1 unconstrained, stick-breaking [U:
+ * stan::math::simplex_constrain]), matrix[K, D] mu (column-major), array[K] vector<lower=0>[D] sigma (log).
+ *   to_vector(mu) ~ normal(0, 7); sigma[i] ~ normal(0, 3); theta ~ dirichlet(2);                      (:15-19)
+ *   target += log_sum_exp_j(log theta_j - 0.5 (D log 2 pi + 2 sum log sigma_j) - 0.5 |(x_i - mu_j) / sigma_j|^2)   (:20-31)
+ * ---------------------------------------------------------------------------------------- */
+bvgo_ctx *bvgo_gmm_create(const double *X, int64_t N, int D, int K) {
+  bvgo_ctx *c = (bvgo_ctx *)calloc(1, sizeof(*c));
+  c->model = BVGO_GMM;
+  c->gX = X; c->gN = N; c->gD = D; c->gK = K;
+  c->nthreads = 1;
+  c->G = K; /* unused by the drivers */
+  c->L.D = (int64_t)K - 1 + 2 * (int64_t)K * D;
+  return c;
+}
+/* constrained parameters from the unconstrained vector; returns the log-Jacobian; zk / stick kept for the backward pass */
+static double gmm_constrain(const double *th, int K, int D, double *theta, double *mu, double *sigma, double *zk, double *stick) {
+  double lj = 0, st = 1.0;
+  for (int q = 0; q < K - 1; ++q) {
+    const double a = th[q] - log((double)(K - 1 - q)), z = inv_logit(a);
+    if (zk) { zk[q] = z; stick[q] = st; }
+    theta[q] = st * z;
+    lj += log(st) - log1p_exp(-a) - log1p_exp(a);
+    st -= theta[q];
+  }
+  theta[K - 1] = st;
+  const double *um = th + K - 1, *us = um + (size_t)K * D;
+  for (int d = 0; d < D; ++d)
+    for (int j = 0; j < K; ++j) mu[j * D + d] = um[j + K * d]; /* matrix[K, D] column-major -> mu[j][d] */
+  for (int j = 0; j < K; ++j)
+    for (int d = 0; d < D; ++d) { sigma[j * D + d] = exp(us[j * D + d]); lj += us[j * D + d]; }
+  return lj;
+}
+static double gmm_log_prob(bvgo_ctx *c, const double *th, int jac, int propto, double *grad) {
+  const int K = c->gK, D = c->gD;
+  const int64_t N = c->gN;
+  double theta[64], zk[64], stick[64];
+  double *mu = (double *)malloc(sizeof(double) * (4 * (size_t)K * D + 3 * K)), *sigma = mu + K * D, *gmu = sigma + K * D, *gsg = gmu + K * D;
+  double *lc = gsg + K * D, *R = lc + K, *lconst = R + K;
+  const double lj = gmm_constrain(th, K, D, theta, mu, sigma, zk, stick);
+  double lp = 0;
+  for (int q = 0; q < K * D; ++q) {
+    lp += -0.5 * mu[q] * mu[q] / 49.0 - 0.5 * sigma[q] * sigma[q] / 9.0;
+    gmu[q] = -mu[q] / 49.0; gsg[q] = -sigma[q] / 9.0;
+  }
+  if (!propto) lp += K * D * (-0.5 * LOG_TWO_PI - log(7.0)) + K * D * (-0.5 * LOG_TWO_PI - log(3.0)) + lgam(2.0 * K);
+  for (int j = 0; j < K; ++j) {
+    lp += log(theta[j]); /* dirichlet(2): (alpha - 1) log theta */
+    double sl = 0;
+    for (int d = 0; d < D; ++d) sl += log(sigma[j * D + d]);
+    lconst[j] = log(theta[j]) - 0.5 * (D * LOG_TWO_PI + 2.0 * sl);
+    R[j] = 0;
+  }
+  for (int64_t i = 0; i < N; ++i) {
+    const double *x = c->gX + (size_t)i * D;
+    double mx = -INFINITY;
+    for (int j = 0; j < K; ++j) {
+      double ss = 0;
+      for (int d = 0; d < D; ++d) { const double u = (x[d] - mu[j * D + d]) / sigma[j * D + d]; ss += u * u; }
+      lc[j] = lconst[j] - 0.5 * ss;
+      if (lc[j] > mx) mx = lc[j];
+    }
+    double se = 0;
+    for (int j = 0; j < K; ++j) se += exp(lc[j] - mx);
+    lp += mx + log(se);
+    if (grad)
+      for (int j = 0; j < K; ++j) {
+        const double r = exp(lc[j] - mx) / se;
+        R[j] += r;
+        for (int d = 0; d < D; ++d) {
+          const double df = x[d] - mu[j * D + d], sg = sigma[j * D + d];
+          gmu[j * D + d] += r * df / (sg * sg);
+          gsg[j * D + d] += r * (df * df / (sg * sg * sg) - 1.0 / sg);
+        }
+      }
+  }
+  if (jac) lp += lj;
+  if (grad) {
+    const double j1 = jac ? 1.0 : 0.0;
+    double gx[64];
+    for (int j = 0; j < K; ++j) gx[j] = (R[j] + 1.0) / theta[j];
+    double gst = gx[K - 1]; /* reverse pass through the stick-breaking transform */
+    for (int q = K - 2; q >= 0; --q) {
+      const double z = zk[q], st = stick[q];
+      const double gz = gx[q] * st - gst * st + j1 * (1.0 / z - 1.0 / (1.0 - z));
+      gst = gx[q] * z + gst * (1.0 - z) + j1 / st;
+      grad[q] = gz * z * (1.0 - z);
+    }
+    double *gm = grad + K - 1, *gs = gm + (size_t)K * D;
+    for (int d = 0; d < D; ++d)
+      for (int j = 0; j < K; ++j) gm[j + K * d] = gmu[j * D + d];
+    for (int q = 0; q < K * D; ++q) gs[q] = gsg[q] * sigma[q] + j1;
+  }
+  free(mu);
+  return lp;
+}
+/* posterior pieces of R/clusterSVGsBayes.R:201-291 from n_draws draws of the approximation (Philox stream 3, draw t):
+ * draws [n_draws][K + 2 K D] constrained (theta | mu column-major | sigma), soft [N][K] = mean over draws of the per-draw
+ * responsibilities (:215-239), *loglik = mean over draws of sum_i log_lik_i (:281-284) */
+int bvgo_gmm_post(bvgo_ctx *c, const double *mu_v, const double *var, int fullrank, int nd, uint64_t seed, double *draws,
+                  double *soft, double *loglik) {
+  const int K = c->gK, D = c->gD;
+  const int64_t N = c->gN, P = c->L.D;
+  double *eta = (double *)malloc(sizeof(double) * (2 * (size_t)P + 2 * (size_t)K * D + 3 * K)), *zeta = eta + P, *mu = zeta + P, *sigma = mu + K * D;
+  double *lc = sigma + K * D, *lconst = lc + K, theta[64];
+  memset(soft, 0, sizeof(double) * (size_t)N * K);
+  double ll = 0;
+  for (int t = 0; t < nd; ++t) {
+    for (int64_t i = 0; i < P; ++i) eta[i] = bvgo_normal(seed, STREAM_DRAW, (uint32_t)t, (uint64_t)i);
+    if (fullrank) fr_transform(P, mu_v, var, eta, zeta);
+    else for (int64_t i = 0; i < P; ++i) zeta[i] = mu_v[i] + exp(var[i]) * eta[i];
+    gmm_constrain(zeta, K, D, theta, mu, sigma, NULL, NULL);
+    if (draws) {
+      double *o = draws + (size_t)t * (K + 2 * K * D);
+      for (int j = 0; j < K; ++j) o[j] = theta[j];
+      for (int d = 0; d < D; ++d) for (int j = 0; j < K; ++j) o[K + j + K * d] = mu[j * D + d];
+      for (int q = 0; q < K * D; ++q) o[K + K * D + q] = sigma[q];
+    }
+    for (int j = 0; j < K; ++j) {
+      double sl = 0;
+      for (int d = 0; d < D; ++d) sl += log(sigma[j * D + d]);
+      lconst[j] = log(theta[j]) - 0.5 * (D * LOG_TWO_PI + 2.0 * sl);
+    }
+    for (int64_t i = 0; i < N; ++i) {
+      const double *x = c->gX + (size_t)i * D;
+      double mx = -INFINITY, se = 0;
+      for (int j = 0; j < K; ++j) {
+        double ss = 0;
+        for (int d = 0; d < D; ++d) { const double u = (x[d] - mu[j * D + d]) / sigma[j * D + d]; ss += u * u; }
+        lc[j] = lconst[j] - 0.5 * ss;
+        if (lc[j] > mx) mx = lc[j];
+      }
+      for (int j = 0; j < K; ++j) se += exp(lc[j] - mx);
+      ll += mx + log(se);
+      for (int j = 0; j < K; ++j) soft[(size_t)i * K + j] += exp(lc[j] - mx) / se / nd;
+    }
+  }
+  *loglik = ll / nd;
+  free(eta);
   return 0;
 }
 

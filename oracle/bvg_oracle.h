@@ -21,7 +21,8 @@ extern "C" {
 
 enum {
   BVGO_GAUSSIAN = 0 /* inst/approxGP.stan */, BVGO_NB = 1 /* inst/approxGP4.stan */,
-  BVGO_GAUSSIAN_DEPTH = 2 /* inst/approxGP2.stan */, BVGO_NB_DEPTH = 3 /* inst/approxGP3.stan */
+  BVGO_GAUSSIAN_DEPTH = 2 /* inst/approxGP2.stan */, BVGO_NB_DEPTH = 3 /* inst/approxGP3.stan */,
+  BVGO_GMM = 4 /* inst/clusterSVGs.stan (bvgo_gmm_create) */
 };
 enum { BVGO_KERNEL_EXP_QUAD = 0, BVGO_KERNEL_MATERN = 1, BVGO_KERNEL_PERIODIC = 2 };
 
@@ -117,6 +118,12 @@ int bvgo_pathfinder(bvgo_ctx *, const bvgo_pf_cfg *, double *summary /*G x 8*/, 
 int bvgo_pf_approx_test(int64_t D, int n, const double *alpha, const double *S, const double *Y, const double *x,
                         const double *g, int nu, const double *u, double *phi, double *logq, double *xc);
 double bvgo_uniform(uint64_t seed, uint32_t stream, uint32_t t, uint64_t i);
+
+/* inst/clusterSVGs.stan (R/clusterSVGsBayes.R:139-291): the mixture model over the PCA embedding X [N][D] row-major.  The
+ * returned context works with bvgo_log_prob / bvgo_advi / bvgo_advi_fullrank (dimension K - 1 + 2 K D). */
+bvgo_ctx *bvgo_gmm_create(const double *X, int64_t N, int D, int K);
+int bvgo_gmm_post(bvgo_ctx *, const double *mu, const double *var /* omega or packed L */, int fullrank, int n_draws,
+                  uint64_t seed, double *draws /* [n_draws][K + 2 K D] or NULL */, double *soft /* [N][K] */, double *loglik);
 
 /* amplitude summaries from n_draws draws of exp(mu_u + exp(omega_u) eps):
  * out G x 8 col-major: mean, median, sd, mad, q5, q95, dispersion, rank (1 = largest mean) */

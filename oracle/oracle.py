@@ -281,6 +281,29 @@ def unpack_tril(Lp, D):
     return out
 
 
+class GmmOracle(Oracle):
+    """inst/clusterSVGs.stan on the PCA embedding X (N x D): log_prob / advi / advi_fullrank are inherited"""
+
+    def __init__(self, X, K):
+        self.X = np.ascontiguousarray(X, dtype=np.float64)   # row-major [N][D]
+        self.N, self.Dx = self.X.shape
+        self.K = int(K)
+        self.G, self.k, self.model = self.K, 0, 4
+        lib().bvgo_gmm_create.restype = C.c_void_p
+        lib().bvgo_gmm_create.argtypes = [_dp, C.c_int64, C.c_int, C.c_int]
+        lib().bvgo_gmm_post.argtypes = [C.c_void_p, _dp, _dp, C.c_int, C.c_int, C.c_uint64, _dp, _dp, C.POINTER(C.c_double)]
+        self._h = lib().bvgo_gmm_create(_p(self.X), self.N, self.Dx, self.K)
+        self.D = self.K - 1 + 2 * self.K * self.Dx
+
+    def post(self, mu, var, fullrank, n_draws=1000, seed=312):
+        mu, var = np.ascontiguousarray(mu, dtype=np.float64), np.ascontiguousarray(var, dtype=np.float64)
+        draws = np.empty((n_draws, self.K + 2 * self.K * self.Dx))
+        soft = np.empty((self.N, self.K))
+        ll = C.c_double()
+        lib().bvgo_gmm_post(self._h, _p(mu), _p(var), int(fullrank), n_draws, seed, _p(draws), _p(soft), C.byref(ll))
+        return draws, soft, ll.value
+
+
 def variogram(coords, expr, kappa=1.5):
     """lscale.estimator = "variogram" (findSpatiallyVariableFeaturesBayes.R:208-260), numpy / scipy restatement for small cases:
     gstat::variogram(z ~ 1) defaults [U] (cutoff = bounding-box diagonal / 3, 15 classes of width cutoff / 15, gamma = sum (z_i -

@@ -640,3 +640,74 @@ def test_full_size_properties_cfg2():
         else:
             assert rel_err(g, g64) <= 2e-4
         f.close()
+
+
+def _gmm_data(N=150, D=4, K=3, seed=0):
+    rng = np.random.default_rng(seed)
+    cent = rng.normal(0, 3, (K, D))
+    lab = rng.integers(0, K, N)
+    return cent[lab] + rng.normal(0, 0.7, (N, D)), lab
+
+
+def test_gmm_log_prob_matches_oracle():
+    """inst/clusterSVGs.stan (the program behind clusterSVGsBayes, R/clusterSVGsBayes.R:139-160): log density and gradient at
+    unconstrained vectors, all (jacobian, propto) combinations, against the CPU restatement"""
+    for (N, D, K) in ((150, 4, 3), (97, 30, 5), (40, 2, 2), (500, 7, 16)):
+        X, _ = _gmm_data(N, D, K, seed=N)
+        o = orc.GmmOracle(X, K)
+        rng = np.random.default_rng(1)
+        for scale in (0.0, 0.3, 1.0):
+            th = rng.normal(0, 1, o.D) * scale
+            for jac in (0, 1):
+                for pro in (0, 1):
+                    lp, g = bvg.engine.gmm_log_prob(X, K, th, jac, pro)
+                    rlp, rg = o.log_prob(th, jac, pro)
+                    assert lp == pytest.approx(rlp, rel=1e-11) and rel_err(g, rg) <= 1e-11, (N, D, K, scale, jac, pro)
+                    assert bvg.engine.gmm_log_prob(X, K, th, jac, pro, grad=False) == pytest.approx(rlp, rel=1e-11)
+
+
+@pytest.mark.parametrize("algorithm", ["meanfield", "fullrank"])
+def test_gmm_fit_matches_oracle(algorithm):
+    """the whole clusterSVGsBayes() fit (eta adaptation, SGA, ELBO test, draws, soft assignments, log-likelihood) on the device
+    against the oracle driving the same algorithm with the same Philox streams"""
+    X, _ = _gmm_data(150, 4, 3, seed=2)
+    o = orc.GmmOracle(X, 3)
+    kw = dict(iter=400, elbo_samples=40, seed=17)
+    fr = algorithm == "fullrank"
+    mu, var, info = (o.advi_fullrank if fr else o.advi)(np.zeros(o.D), **kw)
+    assert info["rc"] == 0
+    res = bvg.engine.gmm_fit(X, 3, algorithm, n_iter=400, n_draws=64, elbo_samples=40, seed=17)
+    i = res["info"]
+    assert (i["eta"], i["iters"], i["converged"]) == (info["eta"], info["iters"], info["converged"])
+    assert i["elbo"] == pytest.approx(info["elbo"], rel=1e-7)
+    assert rel_err(res["mu"], mu) <= 1e-7 and rel_err(res["var"], var) <= 1e-7
+    draws, soft, ll = o.post(mu, var, fr, 64, 17)
+    assert np.allclose(res["draws"], draws, rtol=1e-6, atol=1e-9) and np.allclose(res["soft"], soft, atol=1e-7)
+    assert i["log_likelihood"] == pytest.approx(ll, rel=1e-7)
+    assert np.allclose(res["soft"].sum(1), 1.0) and np.allclose(res["draws"][:, :3].sum(1), 1.0)     # simplex draws
+
+
+def test_cluster_svgs_bayes_host_mirror():
+    """clusterSVGsBayes() (R/clusterSVGsBayes.R:63-319; test_bayesVG.R:114-118, :188-192): list with cluster_df, pca_embedding,
+    model_fit, log_likelihood, BIC; planted gene modules are recovered up to a relabelling"""
+    rng = np.random.default_rng(5)
+    M, n_per, K = 400, 40, 3
+    patterns = rng.normal(size=(K, M))
+    lab = np.repeat(np.arange(K), n_per)
+    data = patterns[lab] * rng.uniform(0.8, 1.5, (K * n_per, 1)) + 0.4 * rng.normal(size=(K * n_per, M))
+    genes = [f"g{i}" for i in range(K * n_per)]
+    obj = bvg.SpatialData(rng.uniform(0, 10, (M, 2)), data=data, genes=genes)
+    res = bvg.clusterSVGsBayes(obj, svgs=genes, n_clust=K, n_PCs=5, n_iter=3000, n_draws=200, verbose=False)
+    assert set(res) == {"pca_embedding", "cluster_df", "model_fit", "log_likelihood", "BIC"}
+    cdf = res["cluster_df"]
+    assert list(cdf.columns) == ["gene"] + [f"prob_cluster_{j}" for j in (1, 2, 3)] + ["assigned_cluster"] and len(cdf) == K * n_per
+    assert res["pca_embedding"].shape == (K * n_per, 5) and isinstance(res["model_fit"], bvg.VariationalFit)
+    assert np.isfinite(res["log_likelihood"]) and res["BIC"] == pytest.approx(-2 * res["log_likelihood"] + (K - 1 + 2 * K * 5) * np.log(K * n_per))
+    got = cdf["assigned_cluster"].to_numpy()
+    purity = sum(np.bincount(got[lab == j], minlength=K + 1).max() for j in range(K)) / len(lab)
+    assert purity >= 0.9, purity
+    assert list(res["model_fit"].draws("theta").columns) == ["theta[1]", "theta[2]", "theta[3]"]
+    with pytest.raises(ValueError, match="valid number of clusters"):
+        bvg.clusterSVGsBayes(obj, svgs=genes, n_clust=1)
+    with pytest.raises(ValueError, match="must be supplied"):
+        bvg.clusterSVGsBayes(obj)

@@ -212,3 +212,42 @@ def test_variogram_restatement():
     Z = (np.linalg.cholesky(K) @ rng.normal(size=(M, 40))).T
     ls, ranges, _ = orc.variogram(X, Z, 1.5)
     assert np.isfinite(ranges).sum() >= 35 and 0.15 < ls < 0.6
+
+
+def test_gmm_restatement_matches_a_literal_transcription():
+    """inst/clusterSVGs.stan statement by statement with scipy.stats densities (stick-breaking simplex transform with its
+    Jacobian [U], lower = 0 transforms), and the analytic gradient against central differences"""
+    from scipy.special import expit, logsumexp
+    from scipy.stats import dirichlet, norm
+    rng = np.random.default_rng(0)
+    N, D, K = 60, 3, 4
+    X = rng.normal(0, 2, (N, D))
+    o = orc.GmmOracle(X, K)
+    assert o.D == K - 1 + 2 * K * D
+
+    def stan_lp(th):
+        y, theta, st, lj = th[:K - 1], np.zeros(K), 1.0, 0.0
+        for q in range(K - 1):
+            z = expit(y[q] - np.log(K - 1 - q))
+            theta[q] = st * z
+            lj += np.log(st) + np.log(z) + np.log(1 - z)
+            st -= theta[q]
+        theta[K - 1] = st
+        mu = th[K - 1:K - 1 + K * D].reshape(D, K).T                # matrix[K, D], column-major
+        sig = np.exp(th[K - 1 + K * D:].reshape(K, D))              # array[K] vector[D]
+        lj += th[K - 1 + K * D:].sum()
+        lp = norm.logpdf(mu, 0, 7).sum() + norm.logpdf(sig, 0, 3).sum() + dirichlet.logpdf(theta, np.full(K, 2.0))
+        for i in range(N):
+            lp += logsumexp([np.log(theta[j]) + norm.logpdf(X[i], mu[j], sig[j]).sum() for j in range(K)])
+        return lp, lj
+
+    for scale in (0.0, 0.4, 1.2):
+        th = rng.normal(0, 1, o.D) * scale
+        lp, lj = stan_lp(th)
+        assert o.log_prob(th, True, False, grad=False) == pytest.approx(lp + lj, rel=1e-12)
+        assert o.log_prob(th, False, False, grad=False) == pytest.approx(lp, rel=1e-12)
+        for jac in (False, True):
+            g = o.log_prob(th, jac, True)[1]
+            fd = np.array([(o.log_prob(th + 1e-6 * e, jac, True, grad=False) - o.log_prob(th - 1e-6 * e, jac, True, grad=False)) / 2e-6
+                           for e in np.eye(o.D)])
+            assert np.abs(fd - g).max() <= 1e-6 * max(1.0, np.abs(g).max())
