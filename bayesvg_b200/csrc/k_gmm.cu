@@ -27,6 +27,8 @@ struct GmmDev {
   double *mu, *var, *hmu, *hvar, *zeta, *grad, *eta, *r;   // var: omega [P] or packed L; r: [N][K] responsibilities
   double *scal;         // [0] lp of the last evaluation, [1] ELBO sum, [2] ELBO finite count, [3] bad evaluations, [4] loglik sum
   uint64_t seed;
+  double lpconst;       // the parameter-free terms of log_prob<propto = false>: normal / dirichlet normalising constants (host-computed:
+                        // an lgamma evaluated by all 1,024 threads of the CTA cost 5 us of its one SM's fp64 pipe per evaluation)
 };
 
 __device__ inline double gmm_inv_logit(double a) {
@@ -36,12 +38,15 @@ __device__ inline double gmm_inv_logit(double a) {
 }
 __device__ inline double gmm_log1p_exp(double a) { return a > 0 ? a + log1p(exp(-a)) : log1p(exp(a)); }
 
-// shared-memory layout of one evaluation: theta[K] | zk[K] | stick[K] | lconst[K] | R[K] | mu[K D] | sigma[K D] | red[64] | part[...]
+// shared-memory layout of one evaluation: (mu, 1/sigma)[K D] | theta[K] | zk[K] | stick[K] | lconst[K] | R[K] | mu[K D] | sigma[K D] | red[64] | part[...]
 struct GmmSh {
   double *theta, *zk, *stick, *lconst, *R, *mu, *sigma, *red, *part;
+  double2 *mi;   // (mu, 1 / sigma) per (cluster, PC)
 };
 __device__ inline GmmSh gmm_sh(double *base, int K, int D) {
   GmmSh s;
+  s.mi = reinterpret_cast<double2 *>(base);   // first, 16-byte aligned
+  base += 2 * K * D;
   s.theta = base; s.zk = s.theta + K; s.stick = s.zk + K; s.lconst = s.stick + K; s.R = s.lconst + K;
   s.mu = s.R + K; s.sigma = s.mu + K * D; s.red = s.sigma + K * D; s.part = s.red + 64;
   return s;
@@ -76,6 +81,7 @@ __device__ inline double gmm_constrain(const GmmDev &m, const GmmSh &s, const do
     const int j = q / D, d = q - j * D;
     s.mu[q] = um[j + K * d];          // matrix[K, D] is column-major in the unconstrained vector
     s.sigma[q] = exp(us[q]);
+    s.mi[q] = make_double2(um[j + K * d], exp(-us[q]));
   }
   __syncthreads();
   double ls = 0;
@@ -84,35 +90,54 @@ __device__ inline double gmm_constrain(const GmmDev &m, const GmmSh &s, const do
   ls = gmm_block_sum(ls, s.red);
   if (tid < K) {
     double sl = 0;
-    for (int d = 0; d < D; ++d) sl += log(s.sigma[tid * D + d]);
+    for (int d = 0; d < D; ++d) sl += us[tid * D + d];   // log sigma is the unconstrained coordinate itself
     s.lconst[tid] = log(s.theta[tid]) - 0.5 * (D * BVG_LOG_TWO_PI + 2.0 * sl);
   }
   __syncthreads();
   return lj + ls;
 }
-// sum_i log_sum_exp_j(...) with the responsibilities left in m.r (and, if soft, accumulated into soft[i][j] with weight wsoft)
-__device__ inline double gmm_mixture(const GmmDev &m, const GmmSh &s, bool store_r, double *soft, double wsoft) {
+// sum_i log_sum_exp_j(...) with the responsibilities left in m.r (and, if soft, accumulated into soft[i][j] with weight wsoft).
+// KT = K rounded up to 4 / 8 / 16: the per-cluster accumulators are fully unrolled into registers, and (mu, 1 / sigma) of a
+// (cluster, PC) pair come in ONE 16-byte shared-memory read.  ncu of the first version (runtime K: accumulators in local
+// memory, two 8-byte reads per term): 116 k warp instructions per evaluation, mio_throttle + short_scoreboard on top.
+template <int KT>
+__device__ inline double gmm_mixture_t(const GmmDev &m, const GmmSh &s, bool store_r, double *soft, double wsoft) {
   const int K = m.K, D = m.D;
   double acc = 0;
   for (int64_t i = threadIdx.x; i < m.N; i += GMM_THREADS) {
-    double lc[GMM_MAXK];
+    double lc[KT];
+#pragma unroll
+    for (int j = 0; j < KT; ++j) lc[j] = 0.0;
+    for (int d = 0; d < D; ++d) {
+      const double x = m.XT[(size_t)d * m.N + i];   // coalesced over the genes of a warp; read once for all clusters
+#pragma unroll
+      for (int j = 0; j < KT; ++j)
+        if (j < K) { const double2 v = s.mi[j * D + d]; const double u = (x - v.x) * v.y; lc[j] = fma(u, u, lc[j]); }
+    }
     double mx = -INFINITY;
-    for (int j = 0; j < K; ++j) {
-      double ss = 0;
-      for (int d = 0; d < D; ++d) { const double u = (m.XT[(size_t)d * m.N + i] - s.mu[j * D + d]) / s.sigma[j * D + d]; ss = fma(u, u, ss); }
-      lc[j] = s.lconst[j] - 0.5 * ss;
-      mx = lc[j] > mx ? lc[j] : mx;
-    }
+#pragma unroll
+    for (int j = 0; j < KT; ++j)
+      if (j < K) { lc[j] = s.lconst[j] - 0.5 * lc[j]; mx = lc[j] > mx ? lc[j] : mx; }
     double se = 0;
-    for (int j = 0; j < K; ++j) { lc[j] = exp(lc[j] - mx); se += lc[j]; }
+#pragma unroll
+    for (int j = 0; j < KT; ++j)
+      if (j < K) { lc[j] = exp(lc[j] - mx); se += lc[j]; }
     acc += mx + log(se);
-    for (int j = 0; j < K; ++j) {
-      const double r = lc[j] / se;
-      if (store_r) m.r[(size_t)i * K + j] = r;
-      if (soft) soft[(size_t)i * K + j] += wsoft * r;
-    }
+    const double ise = 1.0 / se;
+#pragma unroll
+    for (int j = 0; j < KT; ++j)
+      if (j < K) {
+        const double r = lc[j] * ise;
+        if (store_r) m.r[(size_t)i * K + j] = r;
+        if (soft) soft[(size_t)i * K + j] += wsoft * r;
+      }
   }
   return gmm_block_sum(acc, s.red);
+}
+__device__ inline double gmm_mixture(const GmmDev &m, const GmmSh &s, bool store_r, double *soft, double wsoft) {
+  if (m.K <= 4) return gmm_mixture_t<4>(m, s, store_r, soft, wsoft);
+  if (m.K <= 8) return gmm_mixture_t<8>(m, s, store_r, soft, wsoft);
+  return gmm_mixture_t<16>(m, s, store_r, soft, wsoft);
 }
 // one evaluation of log_prob<propto, jacobian> (+ gradient into m.grad) at zeta
 __device__ inline double gmm_eval(const GmmDev &m, const GmmSh &s, const double *zeta, int jac, int propto, bool want_grad) {
@@ -123,7 +148,7 @@ __device__ inline double gmm_eval(const GmmDev &m, const GmmSh &s, const double 
   if (tid < K) pr += log(s.theta[tid]);
   pr = gmm_block_sum(pr, s.red);
   double lp = pr + gmm_mixture(m, s, want_grad, nullptr, 0.0);
-  if (!propto) lp += KD * (-0.5 * BVG_LOG_TWO_PI - log(7.0)) + KD * (-0.5 * BVG_LOG_TWO_PI - log(3.0)) + lgamma(2.0 * K);
+  if (!propto) lp += m.lpconst;
   if (jac) lp += lj;
   if (!want_grad) return lp;
   // gradient sums over the genes: segments of the gene range per (j, d) pair, combined in a fixed order
@@ -194,7 +219,7 @@ __device__ inline void gmm_transform(const GmmDev &m, uint32_t stream, uint32_t 
   }
   __syncthreads();
 }
-extern __shared__ double gmm_smem[];
+extern __shared__ __align__(16) double gmm_smem[];
 
 __global__ void __launch_bounds__(GMM_THREADS) k_gmm_logprob(GmmDev m, int jac, int propto, int want_grad) {
   const GmmSh s = gmm_sh(gmm_smem, m.K, m.D);
@@ -322,6 +347,7 @@ int gmm_setup(GmmHost &h, int device, const double *X, int64_t N, int D, int K, 
   double *p = (double *)h.base;
   GmmDev &m = h.m;
   m.N = N; m.D = D; m.K = K; m.P = P; m.fullrank = fullrank; m.seed = seed;
+  m.lpconst = KD * (-0.5 * BVG_LOG_TWO_PI - std::log(7.0)) + KD * (-0.5 * BVG_LOG_TWO_PI - std::log(3.0)) + std::lgamma(2.0 * K);
   double *XT = p; p += (size_t)D * N;
   m.XT = XT;
   m.mu = p; p += P; m.hmu = p; p += P; m.zeta = p; p += P; m.grad = p; p += P; m.eta = p; p += P;
@@ -329,7 +355,7 @@ int gmm_setup(GmmHost &h, int device, const double *X, int64_t N, int D, int K, 
   // X is N x D column-major (an R matrix) = [D][N]: already the transposed layout the kernels want
   CUDA_TRY(cudaMemcpyAsync(XT, X, sizeof(double) * (size_t)D * N, cudaMemcpyHostToDevice, h.st));
   const int nseg = std::max(1, std::min(GMM_THREADS / KD, 32));
-  h.smem = sizeof(double) * (5 * (size_t)K + 2 * (size_t)KD + 64 + (size_t)2 * nseg * KD + (size_t)nseg * K);
+  h.smem = sizeof(double) * (5 * (size_t)K + 4 * (size_t)KD + 64 + (size_t)2 * nseg * KD + (size_t)nseg * K);
   if (h.smem > 200 * 1024) { bvg_set_error("gmm: K * D too large for one CTA's shared memory"); return BVG_ERR_ARG; }
   CUDA_TRY(cudaFuncSetAttribute(k_gmm_logprob, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h.smem));
   CUDA_TRY(cudaFuncSetAttribute(k_gmm_steps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h.smem));
