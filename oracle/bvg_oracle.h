@@ -5,9 +5,11 @@
  * (un-vendored, version-unpinned: DESCRIPTION:58 "SystemRequirements: CmdStan") and the
  * reference's own tests hold no numeric golden vectors (tests/testthat/test_bayesVG.R:144-219
  * assert classes and shapes only).  Neither R nor CmdStan exists in this image, so this file is a
- * restatement of inst/approxGP.stan / inst/approxGP4.stan and of the published Stan algorithms
- * (meanfield ADVI, L-BFGS), pinned only against an independent literal transcription of the Stan
- * programs (tests/golden/make_golden.py: scipy.stats log-densities + torch-autograd fp64).
+ * restatement of inst/approxGP{,2,3,4}.stan and inst/clusterSVGs.stan and of the published Stan algorithms
+ * (meanfield and fullrank ADVI, L-BFGS, Pathfinder with PSIS resampling), pinned only against independent
+ * literal transcriptions of the Stan programs (tests/golden/make_golden.py, tests/test_oracle_golden.py:
+ * scipy.stats log-densities + torch-autograd fp64 / central differences), the BFGS recursion (Pathfinder's
+ * approximations) and brute-force loops (k-means fixed points, empirical variograms in oracle.py).
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
  * load this library.  The product (bayesvg_b200/) never does.
