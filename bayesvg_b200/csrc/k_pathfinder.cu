@@ -29,7 +29,7 @@ struct PfApprox {           // host part of an approximation; the D-length parts
 struct PfState {
   double *alpha, *Sh, *Yh, *xprev, *gprev, *s, *y, *W, *xc, *Wb, *xcb, *alphab, *U, *PHI, *part, *out, *coef;
   double *base;
-  int nh = 0, head = 0, K = 0;
+  int nh = 0, head = 0;
   PfApprox cur, best;
   double best_elbo = -INFINITY;
   int best_iter = -1, n_iter = 0;
@@ -448,8 +448,7 @@ int pf_single(bvg_fit *f, int path, double *d_amp, int64_t row0, double *h_lr, d
   st.Sh = p; p += (size_t)J * D; st.Yh = p; p += (size_t)J * D; st.W = p; p += 2 * (size_t)J * D; st.Wb = p; p += 2 * (size_t)J * D;
   st.U = p; p += (size_t)KB * D; st.PHI = p; p += (size_t)KB * D;
   st.part = p; p += (size_t)PF_NCH * 2560; st.out = p; p += 2560; st.coef = p;
-  st.alphab = st.s;   // s / y are only live inside one callback; the best alpha is parked in a dedicated row below
-  double *alphab = nullptr;
+  double *alphab = nullptr;   // the best iterate's alpha
   auto fail = [&](int code) { cudaFree(st.base); cudaFree(alphab); return code; };
   if (cudaMalloc(&alphab, sizeof(double) * D) != cudaSuccess) { cudaGetLastError(); bvg_set_error("out of device memory"); return fail(BVG_ERR_CUDA); }
   st.alphab = alphab;
