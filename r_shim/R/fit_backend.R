@@ -54,3 +54,22 @@ bvg_fit_backend <- function(spatial_mtx, kmeans_centers, lscale, expr_df, gene_m
   if (save.model) attr(amplitude_summary, "draws") <- .Call("R_bvg_fit_posterior", fit, as.integer(n.draws))
   amplitude_summary
 }
+
+
+# What replaces lines 139-291 of R/clusterSVGsBayes.R (compile, $variational, the foreach responsibility loop, the log_lik summary).
+# in scope at :139 : svg_mtx_pca (irlba::prcomp_irlba result), svgs, n.clust, algorithm, n.iter, n.draws, elbo.samples, random.seed
+bvg_cluster_backend <- function(svg_mtx_pca, svgs, n.clust, algorithm, n.iter, n.draws, elbo.samples, random.seed, device = 0L) {
+  X <- svg_mtx_pca$x
+  N <- nrow(X); D <- ncol(X); K <- as.integer(n.clust)
+  opts <- as.double(c(n.iter, n.draws, elbo.samples, 100, 50, 0, 0.01))       # eval_elbo, adapt_iter, eta (adaptive), tol_rel_obj: CmdStan defaults
+  res <- .Call("R_bvg_gmm_fit", X, K, algorithm == "fullrank", as.integer(random.seed), opts, as.integer(device))
+  soft_assignments <- t(res[[1]])                                              # :241-254
+  cluster_df <- as.data.frame(soft_assignments)
+  colnames(cluster_df) <- paste0("prob_cluster_", seq(K))
+  cluster_df <- dplyr::mutate(cluster_df, gene = svgs, .before = 1)
+  cluster_df$assigned_cluster <- max.col(soft_assignments, ties.method = "first")  # :262-266 which.max
+  log_likelihood <- res[[3]][5]                                                # :281-284
+  p <- (K - 1) + 2 * K * D                                                     # :286
+  list(pca_embedding = X, cluster_df = cluster_df, model_fit = t(res[[2]]), log_likelihood = log_likelihood,
+       BIC = -2 * log_likelihood + p * log(N))
+}

@@ -44,6 +44,23 @@ SEXP R_bvg_variogram_lscale(SEXP coords, SEXP expr, SEXP kappa, SEXP device) {
   UNPROTECT(2);
   return out;
 }
+/* .Call("R_bvg_gmm_fit", svg_mtx_pca$x (N x D), K, fullrank, seed, opts (7 doubles), device)
+ * -> list(soft = N x K, draws = n_draws x (K + 2 K D), stats = 8 doubles): replaces R/clusterSVGsBayes.R:139-291 */
+SEXP R_bvg_gmm_fit(SEXP X, SEXP K, SEXP fullrank, SEXP seed, SEXP opts, SEXP device) {
+  const int64_t N = Rf_nrows(X);
+  const int D = Rf_ncols(X), k = Rf_asInteger(K), nd = (int)REAL(opts)[1];
+  SEXP softT = PROTECT(Rf_allocMatrix(REALSXP, k, (int)N));                 /* the ABI writes [N][K] row-major = K x N column-major */
+  SEXP drawsT = PROTECT(Rf_allocMatrix(REALSXP, k + 2 * k * D, nd));
+  SEXP stats = PROTECT(Rf_allocVector(REALSXP, 8));
+  chk(bvg_gmm_fit(Rf_asInteger(device), REAL(X), N, D, k, Rf_asLogical(fullrank), (uint64_t)Rf_asInteger(seed), REAL(opts), NULL, NULL,
+                  REAL(drawsT), REAL(softT), REAL(stats)));
+  SEXP out = PROTECT(Rf_allocVector(VECSXP, 3));
+  SET_VECTOR_ELT(out, 0, softT);    /* t() on the R side */
+  SET_VECTOR_ELT(out, 1, drawsT);
+  SET_VECTOR_ELT(out, 2, stats);
+  UNPROTECT(4);
+  return out;
+}
 /* .Call("R_bvg_kmeans", spatial_mtx, k, iter.max, nstart, seed, device) -> k x 2 centres (:200-204) */
 SEXP R_bvg_kmeans(SEXP coords, SEXP k, SEXP iter_max, SEXP nstart, SEXP seed, SEXP device) {
   const int kk = Rf_asInteger(k);
@@ -148,6 +165,7 @@ static const R_CallMethodDef calls[] = {
   {"R_bvg_fit_destroy", (DL_FUNC)&R_bvg_fit_destroy, 1}, {"R_bvg_fit_set_gene_depths", (DL_FUNC)&R_bvg_fit_set_gene_depths, 2},
   {"R_bvg_fit_posterior", (DL_FUNC)&R_bvg_fit_posterior, 2},
   {"R_bvg_variogram_lscale", (DL_FUNC)&R_bvg_variogram_lscale, 4}, {"R_bvg_kmeans", (DL_FUNC)&R_bvg_kmeans, 6},
+  {"R_bvg_gmm_fit", (DL_FUNC)&R_bvg_gmm_fit, 6},
   {NULL, NULL, 0}};
 void R_init_bayesVGb200(DllInfo *dll) {
   R_registerRoutines(dll, NULL, calls, NULL, NULL);

@@ -666,6 +666,19 @@ def test_gmm_log_prob_matches_oracle():
                     assert bvg.engine.gmm_log_prob(X, K, th, jac, pro, grad=False) == pytest.approx(rlp, rel=1e-11)
 
 
+@pytest.mark.parametrize("name", ["gmm_small", "gmm_default_shape"])
+def test_gmm_log_prob_golden(golden_dir, name):
+    """the device evaluation of inst/clusterSVGs.stan against the committed torch-autograd transcription"""
+    z = np.load(os.path.join(golden_dir, name + ".npz"))
+    X, K = z["X"], int(z["K"])
+    for jac in (0, 1):
+        for pro in (0, 1):
+            for t, th in enumerate(z["thetas"]):
+                lp, g = bvg.engine.gmm_log_prob(X, K, th, jac, pro)
+                assert lp == pytest.approx(z[f"lp_j{jac}_p{pro}"][t], rel=1e-11), (jac, pro, t)
+                assert rel_err(g, z[f"grad_j{jac}_p{pro}"][t]) <= 1e-10, (jac, pro, t)
+
+
 @pytest.mark.parametrize("algorithm", ["meanfield", "fullrank"])
 def test_gmm_fit_matches_oracle(algorithm):
     """the whole clusterSVGsBayes() fit (eta adaptation, SGA, ELBO test, draws, soft assignments, log-likelihood) on the device

@@ -251,3 +251,17 @@ def test_gmm_restatement_matches_a_literal_transcription():
             fd = np.array([(o.log_prob(th + 1e-6 * e, jac, True, grad=False) - o.log_prob(th - 1e-6 * e, jac, True, grad=False)) / 2e-6
                            for e in np.eye(o.D)])
             assert np.abs(fd - g).max() <= 1e-6 * max(1.0, np.abs(g).max())
+
+
+@pytest.mark.parametrize("name", ["gmm_small", "gmm_default_shape"])
+def test_gmm_oracle_matches_golden(golden_dir, name):
+    """oracle (analytic gradient, hand-written reverse pass through the simplex transform) against the committed torch-autograd
+    transcription of inst/clusterSVGs.stan (tests/golden/make_golden_gmm.py)"""
+    z = np.load(os.path.join(golden_dir, name + ".npz"))
+    o = orc.GmmOracle(z["X"], int(z["K"]))
+    for jac in (0, 1):
+        for pro in (0, 1):
+            for t, th in enumerate(z["thetas"]):
+                lp, g = o.log_prob(th, jac, pro)
+                assert lp == pytest.approx(z[f"lp_j{jac}_p{pro}"][t], rel=1e-12), (jac, pro, t)
+                assert np.linalg.norm(g - z[f"grad_j{jac}_p{pro}"][t]) <= 1e-11 * np.linalg.norm(g), (jac, pro, t)
