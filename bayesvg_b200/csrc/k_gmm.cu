@@ -23,6 +23,7 @@
 struct GmmDev {
   int64_t N;
   int D, K, P, fullrank;
+  int r_smem;           // 1: the responsibilities of an evaluation fit in shared memory (N K doubles <= 96 KB), else they go through m.r
   const double *XT;     // [D][N]
   double *mu, *var, *hmu, *hvar, *zeta, *grad, *eta, *r;   // var: omega [P] or packed L; r: [N][K] responsibilities
   double *scal;         // [0] lp of the last evaluation, [1] ELBO sum, [2] ELBO finite count, [3] bad evaluations, [4] loglik sum
@@ -42,14 +43,20 @@ __device__ inline double gmm_log1p_exp(double a) { return a > 0 ? a + log1p(exp(
 struct GmmSh {
   double *theta, *zk, *stick, *lconst, *R, *mu, *sigma, *red, *part;
   double2 *mi;   // (mu, 1 / sigma) per (cluster, PC)
+  double *rs;    // responsibilities [N][K] (shared memory when they fit, else global)
 };
-__device__ inline GmmSh gmm_sh(double *base, int K, int D) {
+__device__ inline GmmSh gmm_sh(double *base, int K, int D, int nseg_part = 0, double *r_global = nullptr, int r_smem = 0) {
   GmmSh s;
   s.mi = reinterpret_cast<double2 *>(base);   // first, 16-byte aligned
   base += 2 * K * D;
   s.theta = base; s.zk = s.theta + K; s.stick = s.zk + K; s.lconst = s.stick + K; s.R = s.lconst + K;
   s.mu = s.R + K; s.sigma = s.mu + K * D; s.red = s.sigma + K * D; s.part = s.red + 64;
+  s.rs = r_smem ? s.part + nseg_part : r_global;
   return s;
+}
+__host__ __device__ inline int gmm_part_doubles(int K, int D) {
+  const int KD = K * D, a = GMM_THREADS / KD, nseg = a < 1 ? 1 : (a > 32 ? 32 : a);
+  return 2 * nseg * KD + nseg * K;
 }
 __device__ inline double gmm_block_sum(double v, double *red) {   // fixed tree: deterministic
   v = warp_sum(v);
@@ -128,7 +135,7 @@ __device__ inline double gmm_mixture_t(const GmmDev &m, const GmmSh &s, bool sto
     for (int j = 0; j < KT; ++j)
       if (j < K) {
         const double r = lc[j] * ise;
-        if (store_r) m.r[(size_t)i * K + j] = r;
+        if (store_r) s.rs[(size_t)i * K + j] = r;
         if (soft) soft[(size_t)i * K + j] += wsoft * r;
       }
   }
@@ -159,8 +166,9 @@ __device__ inline double gmm_eval(const GmmDev &m, const GmmSh &s, const double 
     const int64_t i0 = (int64_t)sg * per, i1 = i0 + per < m.N ? i0 + per : m.N;
     const double muq = s.mu[q];
     double a = 0, b = 0, rs = 0;
+#pragma unroll 4
     for (int64_t i = i0; i < i1; ++i) {
-      const double r = m.r[(size_t)i * K + j], df = m.XT[(size_t)d * m.N + i] - muq;
+      const double r = s.rs[(size_t)i * K + j], df = m.XT[(size_t)d * m.N + i] - muq;
       a = fma(r, df, a);
       b = fma(r * df, df, b);
       rs += r;
@@ -222,13 +230,13 @@ __device__ inline void gmm_transform(const GmmDev &m, uint32_t stream, uint32_t 
 extern __shared__ __align__(16) double gmm_smem[];
 
 __global__ void __launch_bounds__(GMM_THREADS) k_gmm_logprob(GmmDev m, int jac, int propto, int want_grad) {
-  const GmmSh s = gmm_sh(gmm_smem, m.K, m.D);
+  const GmmSh s = gmm_sh(gmm_smem, m.K, m.D, gmm_part_doubles(m.K, m.D), m.r, m.r_smem);
   const double lp = gmm_eval(m, s, m.zeta, jac, propto, want_grad != 0);
   if (threadIdx.x == 0) m.scal[0] = lp;
 }
 // n iterations of stochastic gradient ascent: iteration counter it0.., gradient draws t0..
 __global__ void __launch_bounds__(GMM_THREADS) k_gmm_steps(GmmDev m, int n, int it0, uint32_t t0, double eta_s) {
-  const GmmSh s = gmm_sh(gmm_smem, m.K, m.D);
+  const GmmSh s = gmm_sh(gmm_smem, m.K, m.D, gmm_part_doubles(m.K, m.D), m.r, m.r_smem);
   const int P = m.P, tid = threadIdx.x;
   for (int q = 0; q < n; ++q) {
     const int it = it0 + q;
@@ -368,6 +376,8 @@ int gmm_setup(GmmHost &h, int device, const double *X, int64_t N, int D, int K, 
   CUDA_TRY(cudaMemcpyAsync(XT, X, sizeof(double) * (size_t)D * N, cudaMemcpyHostToDevice, h.st));
   const int nseg = std::max(1, std::min(GMM_THREADS / KD, 32));
   h.smem = sizeof(double) * (5 * (size_t)K + 4 * (size_t)KD + 64 + (size_t)2 * nseg * KD + (size_t)nseg * K);
+  m.r_smem = sizeof(double) * (size_t)N * K <= 96 * 1024 ? 1 : 0;   // then the gradient sums read them at shared-memory latency
+  if (m.r_smem) h.smem += sizeof(double) * (size_t)N * K;
   if (h.smem > 200 * 1024) { bvg_set_error("gmm: K * D too large for one CTA's shared memory"); return BVG_ERR_ARG; }
   CUDA_TRY(cudaFuncSetAttribute(k_gmm_logprob, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h.smem));
   CUDA_TRY(cudaFuncSetAttribute(k_gmm_steps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h.smem));
