@@ -10,6 +10,13 @@
  *     fit_vi$summary("amplitude")        :419-432   -> bvg_fit_summarize + bvg_fit_get_summary
  *     fit$log_prob / fit$grad_log_prob   (cmdstanr) -> bvg_log_prob           (the parity hook)
  *     phi <- kernel(...); qr.Q(qr(phi))  :265-288   -> bvg_basis_build
+ * and, for the rows either side of and next to that path:
+ *     stats::kmeans(centers = k, ...)    :200-204   -> bvg_kmeans
+ *     lscale.estimator = "variogram"     :208-260   -> bvg_variogram_lscale
+ *     mod$variational("fullrank")        :357-364   -> cfg.algorithm = BVG_ALG_FULLRANK   (same bvg_fit_run)
+ *     mod$pathfinder(...)                :366-375   -> cfg.algorithm = BVG_ALG_PATHFINDER (same bvg_fit_run)
+ *     save.model = TRUE / extractModel() :483-489   -> bvg_fit_get_posterior
+ *     clusterSVGsBayes()   R/clusterSVGsBayes.R:139-291 -> bvg_gmm_fit, bvg_gmm_log_prob
  * An R package binds these through a logic-free .Call shim.
  *
  * Conventions: every matrix is COLUMN-MAJOR like R.  All pointers are HOST pointers owned by the
