@@ -211,3 +211,47 @@ def test_variational_fit_object_mirrors_cmdstanvb(tmp_path):
         Lx = orc.layout("nb" if lik else "gaussian", 5, 3, bool(depth))
         assert c[3 + Lx["amplitude"]] == "amplitude[1]" and c[3 + Lx["mu_alpha"]] == "mu_alpha[1]"
         assert c[3 + Lx["phi_nb" if lik else "sigma_y"]] == ("phi_nb" if lik else "sigma_y")
+
+
+def test_cluster_svgs_bayes_host_logic(monkeypatch):
+    """clusterSVGsBayes() (R/clusterSVGsBayes.R:63-137, :255-291): argument checks with the reference's messages, per-gene scaling +
+    PCA, the cluster table, log-likelihood and BIC -- with the device fit faked (host logic only)"""
+    import bayesvg_b200.api as api
+    o = _obj(G=12, M=30, seed=4)
+    f = bvg.clusterSVGsBayes
+    with pytest.raises(ValueError, match="All arguments to clusterSVGsBayes"):
+        f(o, None)
+    with pytest.raises(ValueError, match="Please provide an object of class"):
+        f(object(), ["gene1"])
+    with pytest.raises(ValueError, match="Please provide a valid number of clusters."):
+        f(o, ["gene1", "gene2"], n_clust=1)
+    with pytest.raises(ValueError, match="valid variational inference approximation algorithm"):
+        f(o, ["gene1", "gene2"], algorithm="hmc")
+    for kw in (dict(algorithm="pathfinder"), dict(opencl_params=[0, 0])):
+        with pytest.raises(NotImplementedError):
+            f(o, ["gene1", "gene2"], **kw)
+    seen = {}
+
+    def fake_fit(X, K, algorithm, n_iter, n_draws, elbo_samples, seed, device=0):
+        seen.update(X=X, K=K, algorithm=algorithm, n_iter=n_iter, n_draws=n_draws, elbo_samples=elbo_samples, seed=seed)
+        N, D = X.shape
+        soft = np.full((N, K), 0.1 / (K - 1))
+        soft[np.arange(N), np.arange(N) % K] = 0.9
+        return dict(mu=np.zeros(K - 1 + 2 * K * D), var=np.zeros(3), draws=np.ones((n_draws, K + 2 * K * D)), soft=soft,
+                    info=dict(eta=0.1, iters=n_iter, converged=0, elbo=-1.0, log_likelihood=-50.0, seconds=0.0, grad_evals=0, elbo_evals=0))
+
+    monkeypatch.setattr(api.E, "gmm_fit", fake_fit)
+    svgs = [f"gene{i}" for i in (3, 1, 7, 9, 10, 12, 5)]
+    res = f(o, svgs, n_clust=3, n_PCs=4, n_iter=500, n_draws=20, verbose=False)
+    assert seen["K"] == 3 and seen["algorithm"] == "fullrank" and seen["elbo_samples"] == 300 and seen["seed"] == 312   # defaults (:67-76, :85-91)
+    X = seen["X"]
+    assert X.shape == (7, 4) and np.allclose(res["pca_embedding"], X)
+    rows = [o.genes.index(g) for g in svgs]
+    expr = np.asarray(o.data, dtype=np.float64)[rows]
+    z = (expr - expr.mean(1, keepdims=True)) / expr.std(1, ddof=1, keepdims=True)          # t(coop::scaler(t(expr_mtx))) (:132)
+    assert np.allclose(np.abs(X), np.abs(np.linalg.svd(z, full_matrices=False)[0][:, :4] * np.linalg.svd(z, compute_uv=False)[:4]))
+    cdf = res["cluster_df"]
+    assert list(cdf["gene"]) == svgs and list(cdf["assigned_cluster"]) == [1, 2, 3, 1, 2, 3, 1]       # which.max (:262-266), 1-based
+    assert res["log_likelihood"] == -50.0 and res["BIC"] == pytest.approx(100.0 + (2 + 2 * 3 * 4) * np.log(7))   # :286-291
+    fit = res["model_fit"]
+    assert fit.columns[:3] == ["theta[1]", "theta[2]", "theta[3]"] and fit.columns[3] == "mu[1,1]" and fit.columns[-1] == "sigma[3,4]"
