@@ -1211,7 +1211,9 @@ int bvgo_summary_fullrank(int model, int64_t G, int k, const double *mu, const d
 /* ------------------------------------------------------------------------------------------
  * inst/clusterSVGs.stan (R/clusterSVGsBayes.R:139-160): diagonal-covariance Gaussian mixture over the PCA embedding of the
  * SVGs.  Parameters in declaration order (:8-12): simplex[K] theta (K - 1 unconstrained, stick-breaking [U:
- * stan::math::simplex_constrain]), matrix[K, D] mu (column-major), array[K] vector<lower=0>[D] sigma (log).
+ * stan::math::simplex_constrain as published in the Stan reference manual; the reference pins no CmdStan version and recent
+ * releases may map the simplex differently -- that changes the shape of the variational family, not the model]),
+ * matrix[K, D] mu (column-major), array[K] vector<lower=0>[D] sigma (log).
  *   to_vector(mu) ~ normal(0, 7); sigma[i] ~ normal(0, 3); theta ~ dirichlet(2);                      (:15-19)
  *   target += log_sum_exp_j(log theta_j - 0.5 (D log 2 pi + 2 sum log sigma_j) - 0.5 |(x_i - mu_j) / sigma_j|^2)   (:20-31)
  * ---------------------------------------------------------------------------------------- */
