@@ -19,7 +19,7 @@ ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05 = 0, 1, 2
 EXPORTS = [
     "bvg_version", "bvg_last_error", "bvg_device_count", "bvg_config_default", "bvg_basis_build", "bvg_kmeans", "bvg_variogram_lscale", "bvg_gmm_log_prob", "bvg_gmm_fit",
     "bvg_fit_create", "bvg_fit_destroy", "bvg_fit_set_phi", "bvg_fit_set_y_f64", "bvg_fit_set_y_i32",
-    "bvg_fit_dim", "bvg_fit_set_gene_depths", "bvg_comm_unique_id", "bvg_fit_comm_init", "bvg_fit_peer_handle", "bvg_fit_peer_init", "bvg_log_prob", "bvg_fit_run", "bvg_fit_mle",
+    "bvg_fit_dim", "bvg_fit_shape", "bvg_fit_set_gene_depths", "bvg_comm_unique_id", "bvg_fit_comm_init", "bvg_fit_peer_handle", "bvg_fit_peer_init", "bvg_log_prob", "bvg_fit_run", "bvg_fit_mle",
     "bvg_fit_advi", "bvg_fit_summarize", "bvg_fit_set_variational", "bvg_fit_get_variational", "bvg_fit_get_cholesky", "bvg_fit_set_cholesky", "bvg_fit_pathfinder_single",
     "bvg_fit_advi_steps", "bvg_fit_elbo", "bvg_fit_time_lik_kernel", "bvg_fit_flush_l2", "bvg_fit_get_summary",
     "bvg_fit_get_draws", "bvg_fit_posterior_ncol", "bvg_fit_get_posterior", "bvg_fit_get_trace", "bvg_fit_get_stats", "bvg_debug_stage_times", "bvg_debug_gene_trace", "bvg_debug_time_gene",
@@ -83,6 +83,7 @@ def lib():
     L.bvg_fit_set_y_f64.argtypes = [_vp, _dp, C.c_int64, C.c_int64]
     L.bvg_fit_set_y_i32.argtypes = [_vp, C.POINTER(C.c_int32), C.c_int64, C.c_int64]
     L.bvg_fit_dim.argtypes = [_vp, C.POINTER(C.c_int64)]
+    L.bvg_fit_shape.argtypes = [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int), C.POINTER(C.c_int64)]
     L.bvg_fit_set_gene_depths.argtypes = [_vp, _dp, C.c_int64]
     L.bvg_comm_unique_id.argtypes = [_vp, C.c_size_t, C.POINTER(C.c_size_t)]
     L.bvg_fit_comm_init.argtypes = [_vp, _vp, C.c_size_t]

@@ -213,6 +213,10 @@ def findSpatiallyVariableFeaturesBayes(sp_obj=None, naive_hvgs=None, likelihood=
         raise NotImplementedError(f"algorithm = '{algorithm}' is not built for gene-sharded fits; use 'meanfield'.")
     if algorithm == "pathfinder" and save_model:
         raise NotImplementedError("save.model = TRUE is not built for algorithm = 'pathfinder'.")
+    if shard is not None and device == 0:
+        # one process per GPU (torchrun): the default device of a sharded fit is this rank's GPU, not GPU 0 for everyone
+        import os
+        device = int(os.environ.get("LOCAL_RANK", shard.rank))
     if opencl_params is not None:
         raise NotImplementedError("opencl.params is meaningless here: the fit always runs on the CUDA device.")
     if lscale_estimator not in ("kmeans", "variogram"):
@@ -264,7 +268,9 @@ def findSpatiallyVariableFeaturesBayes(sp_obj=None, naive_hvgs=None, likelihood=
         cfg.update(pf_num_paths=int(n_cores), pf_max_lbfgs_iters=200, pf_init_radius=0.01, lbfgs_history=25)
     if shard is not None:
         from . import dist
-        table, model = dist.fit_sharded(phi, Y, shard, likelihood, precision, engine, cfg, gene_depths=gene_depths)
+        table, model = dist.fit_sharded(phi, Y, shard, likelihood, precision, engine, cfg, gene_depths=gene_depths,
+                                        save_model=bool(save_model), n_draws=int(n_draws), genes=list(naive_hvgs),
+                                        extra=dict(phi=phi, lscale=lscale, centers=centers))
     else:
         fit = E.Fit(phi, Y, likelihood, precision, engine, gene_depths=gene_depths, algorithm=algorithm, **cfg)
         table = fit.run()

@@ -70,6 +70,7 @@ static double now_s() {
   return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 static int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+static int comm_failed(const Ctl &h);
 
 // ---- lifecycle ----------------------------------------------------------------------------------
 extern "C" int bvg_fit_create(const bvg_config *cfg, bvg_fit **out) {
@@ -208,13 +209,14 @@ static int finalize_model(bvg_fit *f) {
   CUDA_TRY(cudaMalloc(&m.C, c_bytes));
   CUDA_TRY(cudaMemsetAsync(m.C, 0, c_bytes, f->stream));
   CUDA_TRY(cudaMalloc(&m.Ppart, ts * (size_t)m.nsplit * m.Gpad * m.KP));
-  CUDA_TRY(cudaMalloc(&m.Spart, ts * (size_t)m.nsplit * m.Gpad * 2));
+  CUDA_TRY(cudaMalloc(&m.Spart, sizeof(double) * (size_t)m.nsplit * m.Gpad * 2));  // always fp64
   CUDA_TRY(cudaMemsetAsync(m.Ppart, 0, ts * (size_t)m.nsplit * m.Gpad * m.KP, f->stream));
-  CUDA_TRY(cudaMemsetAsync(m.Spart, 0, ts * (size_t)m.nsplit * m.Gpad * 2, f->stream));
+  CUDA_TRY(cudaMemsetAsync(m.Spart, 0, sizeof(double) * (size_t)m.nsplit * m.Gpad * 2, f->stream));
   // one gene per warp, at most one CTA per SM: 16 warps per CTA, or 21 when that lets every gene be served in a
   // single pass (a warp that owns two genes runs two dependent latency chains back to back)
   f->gene_wpb = (m.G > (int64_t)16 * nsm && m.G <= (int64_t)(BVG_GENE_MAX_THREADS / 32) * nsm) ? BVG_GENE_MAX_THREADS / 32 : 16;
   if (m.k > BVG_SMALL_K) f->gene_wpb = 16;  // k_gene_big
+  if (m.k > BVG_SMALL_K) BVG_TRY(gene_big_setup());
   m.nblk_gene = (int)std::min<int64_t>((m.G + f->gene_wpb - 1) / f->gene_wpb, nsm);
   f->h_t_grad = 0;
   const int NS = bvg_ns(m.k);
@@ -226,6 +228,7 @@ static int finalize_model(bvg_fit *f) {
   m.W = (float *)m.C;             // tcgen05 engine: the coefficient-row allocation holds the fp32 draw rows instead
   CUDA_TRY(cudaMalloc(&m.ctl, sizeof(Ctl)));
   CUDA_TRY(cudaMemsetAsync(m.ctl, 0, sizeof(Ctl), f->stream));
+  if (m.peer.world > 1) m.peer.fail = &m.ctl->comm_fail;  // a model re-staged after bvg_fit_peer_init
   CUDA_TRY(cudaMalloc(&f->summary, sizeof(double) * 8 * m.G));
   CUDA_TRY(cudaMalloc(&f->draws, sizeof(double) * m.G * f->cfg.n_draws));
   // Phi' in the compute type
@@ -405,6 +408,15 @@ extern "C" int bvg_fit_dim(bvg_fit *f, int64_t *D) {
   return BVG_OK;
 }
 
+extern "C" int bvg_fit_shape(bvg_fit *f, int64_t *M, int64_t *G, int *k, int64_t *D) {
+  BVG_TRY(need_ready(f, false));
+  if (M) *M = f->m.M;
+  if (G) *G = f->m.G;
+  if (k) *k = f->m.k;
+  if (D) *D = f->m.L.D;
+  return BVG_OK;
+}
+
 // ---- one evaluation -----------------------------------------------------------------------------
 int launch_lik(bvg_fit *f, bool backward) {
   if (f->big_tc) return launch_lik_tcbig(f, backward);
@@ -429,6 +441,7 @@ extern "C" int bvg_log_prob(bvg_fit *f, const double *theta, int jacobian, int p
   CUDA_TRY(cudaMemcpyAsync(&h, f->m.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, f->stream));
   if (grad) CUDA_TRY(cudaMemcpyAsync(grad, f->m.grad, sizeof(double) * D, cudaMemcpyDeviceToHost, f->stream));
   CUDA_TRY(cudaStreamSynchronize(f->stream));
+  BVG_TRY(comm_failed(h));
   *lp = h.lp;
   return BVG_OK;
 }
@@ -449,10 +462,15 @@ static int ctl_set(bvg_fit *f, const Ctl &h0) {
   CUDA_TRY(cudaStreamSynchronize(f->stream));  // h lives on the caller's stack
   return BVG_OK;
 }
+static int comm_failed(const Ctl &h) {
+  if (!h.comm_fail) return BVG_OK;
+  bvg_set_error("multi-GPU exchange timed out: a peer rank never delivered its sums (BVG_PEER_TIMEOUT_S raises the limit)");
+  return BVG_ERR_COMM;
+}
 static int ctl_get(bvg_fit *f, Ctl *h) {
   CUDA_TRY(cudaMemcpyAsync(h, f->m.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, f->stream));
   CUDA_TRY(cudaStreamSynchronize(f->stream));
-  return BVG_OK;
+  return comm_failed(*h);
 }
 // n consecutive ELBO-gradient evaluations.  tcgen05 engine: only the first one launches k_prep; every
 // k_gene draws the next evaluation's zeta itself ("draw-ahead"), and the likelihood kernel builds its
@@ -958,7 +976,13 @@ extern "C" int bvg_fit_get_summary(bvg_fit *f, double *out) {
   // amplitude_mean_rank: arrange(desc(amplitude_mean)) then row_number()  (:429-430); within a shard
   std::vector<int64_t> idx(G);
   for (int64_t g = 0; g < G; ++g) idx[g] = g;
-  std::stable_sort(idx.begin(), idx.end(), [&](int64_t a, int64_t b) { return out[a] > out[b]; });
+  // descending, NaN last (dplyr::arrange(desc()) puts NA at the end): a strict weak ordering also when a mean is NaN
+  std::stable_sort(idx.begin(), idx.end(), [&](int64_t a, int64_t b) {
+    const double x = out[a], y = out[b];
+    const bool nx = std::isnan(x), ny = std::isnan(y);
+    if (nx || ny) return !nx && ny;
+    return x > y;
+  });
   for (int64_t r = 0; r < G; ++r) out[7 * G + idx[r]] = (double)(r + 1);
   return BVG_OK;
 }
@@ -981,7 +1005,8 @@ extern "C" int bvg_fit_posterior_ncol(bvg_fit *f, int64_t *ncol) {
 }
 // one draw: constrain zeta into column-major out[col][d]; per-block partial sums of eps^2 for log_g__
 __global__ void __launch_bounds__(256) k_store_draw(DevModel m, int64_t n, int64_t d, double *__restrict__ out, double *__restrict__ part,
-                                                    const double *__restrict__ eta /* full-rank family: the draw's standard normals */) {
+                                                    const double *__restrict__ eta /* full-rank family: the draw's standard normals */,
+                                                    const double *__restrict__ wgt /* gene-sharded fit: 0 for the replicated gene-shared parameters on ranks > 0 */) {
   __shared__ double red[8];
   const Layout &L = m.L;
   const int64_t D = L.D, G = m.G, ntp = (m.depth ? 1 : 2) * G;
@@ -994,7 +1019,7 @@ __global__ void __launch_bounds__(256) k_store_draw(DevModel m, int64_t n, int64
                        (i >= L.sigma_alpha && i < L.sigma_alpha + m.k) || i == L.tail;
       v = pos ? exp(z) : z;
       const double e = eta ? eta[i] : (z - m.mu[i]) * exp(-m.omega[i]);
-      acc += e * e;
+      acc += (wgt ? wgt[i] : 1.0) * e * e;
     } else if (!m.depth && i < D + G) {
       v = m.zeta[L.mu_beta0] + exp(m.zeta[L.sigma_beta0]) * m.zeta[L.z_beta0 + (i - D)];   // beta0[g], approxGP.stan:26
     } else {
@@ -1022,7 +1047,7 @@ __global__ void k_store_draw_finish(const double *__restrict__ part, int nblk, c
 static const int kStoreBlocks = 148 * 2;
 int fr_store_draw(bvg_fit *f, int64_t n, int64_t d, double *d_out, const double *d_eta) {
   double *d_part = d_out + (size_t)posterior_ncol(f) * n;
-  k_store_draw<<<kStoreBlocks, 256, 0, f->stream>>>(f->m, n, d, d_out, d_part, d_eta);
+  k_store_draw<<<kStoreBlocks, 256, 0, f->stream>>>(f->m, n, d, d_out, d_part, d_eta, nullptr);
   k_store_draw_finish<<<1, 1, 0, f->stream>>>(d_part, kStoreBlocks, f->m.elbo_lps, n, d, d_out);
   f->st.kernel_launches += 2;
   CUDA_TRY(cudaGetLastError());
@@ -1032,7 +1057,10 @@ extern "C" int bvg_fit_get_posterior(bvg_fit *f, int n, double *out) {
   BVG_TRY(need_ready(f));
   if (!f->have_vi) { bvg_set_error("no variational fit to draw from"); return BVG_ERR_STATE; }
   if (n < 1 || !out) { bvg_set_error("bad argument"); return BVG_ERR_ARG; }
-  if (f->comm_mode) { bvg_set_error("posterior draws of a gene-sharded fit are not built; use bvg_fit_get_draws per shard"); return BVG_ERR_ARG; }
+  // gene-sharded fit: this rank's columns (its slice of the unconstrained vector, beta0 / amplitude_sq of its genes).
+  // log_p__ and log_g__ are sums over ALL parameters: every rank forms its local share per draw (the replicated
+  // gene-shared parameters count on rank 0 only) and ONE all-reduce of the 2 n scalars follows the n draws.
+  const bool sharded = f->comm_mode != 0;
   const int64_t ncol = posterior_ncol(f);
   double *d_out = nullptr, *d_part = nullptr;
   const int nblk = kStoreBlocks;
@@ -1049,13 +1077,16 @@ extern "C" int bvg_fit_get_posterior(bvg_fit *f, int n, double *out) {
   h.t_draw = 0;
   if (rc == BVG_OK) rc = ctl_set(f, h);
   if (rc == BVG_OK && is_fr(f)) rc = fr_posterior(f, n, d_out);   // zeta = mu + L eta, ten draws per pass over L
+  if (sharded) { f->m.elbo_local = 1; f->m.rank_id = f->cfg.rank; }
   for (int d = 0; d < n && rc == BVG_OK && !is_fr(f); ++d) {
     rc = eval_log_prob_device(f, MODE_POST_DRAW, 1, 0, false);
     if (rc != BVG_OK) break;
-    k_store_draw<<<nblk, 256, 0, f->stream>>>(f->m, n, d, d_out, d_part, nullptr);
+    k_store_draw<<<nblk, 256, 0, f->stream>>>(f->m, n, d, d_out, d_part, nullptr, sharded ? f->scratch + f->m.L.D : nullptr);
     k_store_draw_finish<<<1, 1, 0, f->stream>>>(d_part, nblk, f->m.elbo_lps, n, d, d_out);
     f->st.kernel_launches += 2;
   }
+  f->m.elbo_local = 0;
+  if (rc == BVG_OK && sharded) rc = comm_allreduce(f, d_out + n, 2 * n);   // columns log_p__ | log_g__ are contiguous
   if (rc == BVG_OK && (cudaGetLastError() != cudaSuccess ||
                        cudaMemcpyAsync(out, d_out, sizeof(double) * (size_t)ncol * n, cudaMemcpyDeviceToHost, f->stream) != cudaSuccess ||
                        cudaStreamSynchronize(f->stream) != cudaSuccess)) {

@@ -83,7 +83,7 @@ struct Ctl {
   uint32_t ticket;   // last-block-done counter of k_gene (fused finish)
   double es;         // eta / sqrt(it): kept next to `it` so that k_gene starts without a sqrt + divide chain
   uint32_t t_draw;   // running counter of posterior draws (stream 3; bvg_fit_get_posterior)
-  uint32_t pad1;
+  uint32_t comm_fail; // set by a peer exchange (or the persistent ADVI kernel) whose partner never arrived: BVG_ERR_COMM on the host
 };
 
 // ---- peer-memory exchange (multi-GPU) ------------------------------------------
@@ -97,6 +97,8 @@ struct PeerCtx {
   int world, rank;
   uint32_t *seq;                 // exchanges completed so far (advances in lockstep on every rank)
   uint2 *cells[BVG_MAX_PEERS];   // cells[r] = rank r's exchange buffer as mapped here (cells[rank] is local)
+  long long timeout;             // SM cycles a poll may wait for a peer (BVG_PEER_TIMEOUT_S, default 120 s) before it gives up
+  uint32_t *fail;                // -> Ctl::comm_fail of this rank
 };
 
 struct DevModel {
@@ -110,7 +112,7 @@ struct DevModel {
   Ctl *ctl;
   void *C;       // [Gpad][KP]
   void *Ppart;   // [nsplit][Gpad][KP]
-  void *Spart;   // [nsplit][Gpad][2]
+  void *Spart;   // [nsplit][Gpad][2], always fp64
   double *blk;   // [nblk_gene][NS]
   double *tot;   // [NS]
   double *shx;   // [4+k] exp of the shared log-scales of the current draw: sigma_beta0, sigma_amplitude, tail, sigma_alpha[k];
@@ -145,13 +147,19 @@ struct DevModel {
 // runs in rank order on every rank, so all ranks end with bit-identical results (the replicated
 // gene-shared parameters stay identical without a broadcast).  Parity double-buffering is enough: a
 // rank can only be one exchange ahead of a peer it is waiting for.
-__device__ inline double peer_poll(const uint2 *src, uint32_t seq, long long t0) {
+// A peer that never arrives (crashed rank, a rank stuck in host code for longer than the time-out) must not hang
+// the GPU: the poll gives up, raises Ctl::comm_fail (the host turns it into BVG_ERR_COMM at its next read of the
+// control block) and returns NaN so that nothing downstream looks like a result.
+__device__ inline double peer_poll(const PeerCtx &p, const uint2 *src, uint32_t seq, long long t0) {
   uint32_t lo, fl, hi, fh;
   for (;;) {
     asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(fl) : "l"(src) : "memory");
     asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(hi), "=r"(fh) : "l"(src + 1) : "memory");
     if (fl == seq && fh == seq) break;
-    if (clock64() - t0 > 40000000000LL) __trap();  // ~20 s: a peer never arrived -> fail instead of hanging the GPU
+    if (clock64() - t0 > p.timeout) {
+      if (p.fail) *(volatile uint32_t *)p.fail = 1u;
+      return __longlong_as_double(0x7ff8000000000000LL);
+    }
   }
   return __hiloint2double((int)hi, (int)lo);
 }
@@ -180,13 +188,13 @@ __device__ inline void peer_allreduce_cta(const PeerCtx &p, double *vals, int n,
   if (scratch) {
     for (int t = threadIdx.x; t < n * (p.world - 1); t += blockDim.x) {
       const int ri = t / n, cc = t - ri * n, r = ri < p.rank ? ri : ri + 1;
-      scratch[t] = peer_poll(mine + (size_t)r * per_rank + 2 * cc, seq, t0);
+      scratch[t] = peer_poll(p, mine + (size_t)r * per_rank + 2 * cc, seq, t0);
     }
     __syncthreads();
     if (c < n)
       for (int r = 0; r < p.world; ++r) s += r == p.rank ? vals[c] : scratch[(r < p.rank ? r : r - 1) * n + c];  // rank order
   } else if (c < n) {
-    for (int r = 0; r < p.world; ++r) s += r == p.rank ? vals[c] : peer_poll(mine + (size_t)r * per_rank + 2 * c, seq, t0);
+    for (int r = 0; r < p.world; ++r) s += r == p.rank ? vals[c] : peer_poll(p, mine + (size_t)r * per_rank + 2 * c, seq, t0);
   }
   __syncthreads();  // every push has read vals[] before it is overwritten
   if (c < n) vals[c] = s;
@@ -326,6 +334,7 @@ void tcbig_destroy(bvg_fit *f);
 bool tc_available();                                         // false until the tcgen05 kernel is linked in
 int tc_setup(bvg_fit *f);                                    // build TMA descriptors etc.
 void tc_destroy(bvg_fit *f);
+int gene_big_setup();                                        // k_model.cu: per-device function attributes of k_gene_big
 int launch_gene_finish(bvg_fit *f, int mode, int jacobian, int propto, int ahead = 0);  // per-gene backward (+ update, + next draw) + cross-gene finish
 int comm_allreduce(bvg_fit *f, double *buf, int n);          // comm.cu
 int suff_elbo(bvg_fit *f, int S, double *lps_host);          // k_suff.cu: S log densities from sufficient statistics

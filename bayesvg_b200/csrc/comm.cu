@@ -8,6 +8,7 @@
 // NCCL is resolved at run time with dlopen so the C-ABI library has no link-time dependency on it
 // (an R session loads it the same way a torch process does).
 #include <dlfcn.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "bvg_internal.cuh"
@@ -129,6 +130,14 @@ extern "C" int bvg_fit_peer_init(bvg_fit *f, const void *handles, size_t len) {
   p.seq = (uint32_t *)((char *)f->peer_buf + (size_t)2 * W * 2 * BVG_PEER_CAP * sizeof(uint2));
   p.world = W;
   p.rank = f->cfg.rank;
+  {  // how long a poll waits for a peer: legitimate host-side skew (module load, cudaMalloc, a paused rank) can be seconds
+    double sec = 120.0;
+    if (const char *e = getenv("BVG_PEER_TIMEOUT_S")) { const double v = atof(e); if (v > 0) sec = v; }
+    int khz = 2000000;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, f->cfg.device);
+    p.timeout = (long long)(sec * 1e3 * (double)khz);
+  }
+  p.fail = f->m.ctl ? &f->m.ctl->comm_fail : nullptr;
   f->comm_mode = 2;
   return BVG_OK;
 }

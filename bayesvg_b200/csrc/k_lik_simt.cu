@@ -23,7 +23,7 @@ template <> __device__ inline double t_log1p<double>(double x) { return log1p(x)
 template <typename T, int KP, int LIK, bool BWD>
 __global__ void __launch_bounds__(BVG_GENE_TILE) k_lik_simt(const T *__restrict__ Y, int64_t ldY,
                                                             const T *__restrict__ Phi, const T *__restrict__ C,
-                                                            T *__restrict__ Ppart, T *__restrict__ Spart, int64_t M,
+                                                            T *__restrict__ Ppart, double *__restrict__ Spart, int64_t M,
                                                             int64_t G, int64_t Gpad, int chunks_per_split,
                                                             const double *__restrict__ zeta, int64_t tail_idx) {
   griddep_wait();    // the coefficient rows C come from k_prep
@@ -86,8 +86,8 @@ __global__ void __launch_bounds__(BVG_GENE_TILE) k_lik_simt(const T *__restrict_
 #pragma unroll
     for (int j = 0; j < KP; ++j) Ppart[row * KP + j] = P[j];
   }
-  Spart[row * 2 + 0] = acc0;
-  Spart[row * 2 + 1] = acc1;
+  Spart[row * 2 + 0] = (double)acc0;
+  Spart[row * 2 + 1] = (double)acc1;
 }
 
 template <typename T, int KP>
@@ -99,7 +99,7 @@ static int launch_t(bvg_fit *f, bool bwd) {
   dim3 grid(ntiles, m.nsplit);
 #define LAUNCH(LIK, BWD)                                                                                      \
   CUDA_TRY(launch_pdl(k_lik_simt<T, KP, LIK, BWD>, grid, dim3(BVG_GENE_TILE), 0, f->stream, (const T *)f->Y, f->ldY, \
-                      (const T *)f->Phi, (const T *)m.C, (T *)m.Ppart, (T *)m.Spart, m.M, m.G, m.Gpad, cps,     \
+                      (const T *)f->Phi, (const T *)m.C, (T *)m.Ppart, (double *)m.Spart, m.M, m.G, m.Gpad, cps,     \
                       (const double *)m.zeta, m.L.tail))
   if (m.lik == BVG_GAUSSIAN) { if (bwd) LAUNCH(BVG_GAUSSIAN, true); else LAUNCH(BVG_GAUSSIAN, false); }
   else { if (bwd) LAUNCH(BVG_NB, true); else LAUNCH(BVG_NB, false); }
@@ -121,7 +121,7 @@ static int launch_t(bvg_fit *f, bool bwd) {
 // It is the fp64 parity path and the fp32 fallback for k > 23; the tcgen05 kernel covers k <= 23.
 template <typename T, int NKB, int LIK, bool BWD>
 __global__ void __launch_bounds__(256) k_lik_gen(const T *__restrict__ Y, int64_t ldY, const T *__restrict__ Phi,
-                                                 const T *__restrict__ C, T *__restrict__ Ppart, T *__restrict__ Spart,
+                                                 const T *__restrict__ C, T *__restrict__ Ppart, double *__restrict__ Spart,
                                                  int64_t M, int64_t G, int64_t Gpad, int KP, int chunks_per_split,
                                                  const double *__restrict__ zeta, int64_t tail_idx) {
   griddep_wait();
@@ -224,8 +224,8 @@ __global__ void __launch_bounds__(256) k_lik_gen(const T *__restrict__ Y, int64_
   if (grp == 0) {
     T a = 0, b = 0;
     for (int q = 0; q < 8; ++q) { a += red[0][q][gt]; b += red[1][q][gt]; }  // fixed order
-    Spart[row * 2 + 0] = a;
-    Spart[row * 2 + 1] = b;
+    Spart[row * 2 + 0] = (double)a;
+    Spart[row * 2 + 1] = (double)b;
   }
 }
 
@@ -237,7 +237,7 @@ static int launch_gen(bvg_fit *f, bool bwd) {
   dim3 grid((unsigned)(m.Gpad / 32), (unsigned)m.nsplit);
 #define LAUNCHG(LIK, BWD)                                                                                          \
   CUDA_TRY(launch_pdl(k_lik_gen<T, NKB, LIK, BWD>, grid, dim3(256), 0, f->stream, (const T *)f->Y, f->ldY, (const T *)f->Phi, \
-                      (const T *)m.C, (T *)m.Ppart, (T *)m.Spart, m.M, m.G, m.Gpad, m.KP, cps, (const double *)m.zeta, m.L.tail))
+                      (const T *)m.C, (T *)m.Ppart, (double *)m.Spart, m.M, m.G, m.Gpad, m.KP, cps, (const double *)m.zeta, m.L.tail))
   if (m.lik == BVG_GAUSSIAN) { if (bwd) LAUNCHG(BVG_GAUSSIAN, true); else LAUNCHG(BVG_GAUSSIAN, false); }
   else { if (bwd) LAUNCHG(BVG_NB, true); else LAUNCHG(BVG_NB, false); }
 #undef LAUNCHG

@@ -53,7 +53,8 @@
 #define TM_COLS 512
 
 struct TcArgs {
-  float *Ppart, *Spart;
+  float *Ppart;
+  double *Spart;   // fp64: a float store of the fp64 running sums cost ~1e-8 of the log density (L-BFGS noise floor)
   // coefficient rows c'_g = (A_g alpha_t[,g], beta0_g) are built here from the current draw (approxGP.stan:26-27, :32),
   // published in fp32 by k_prep / k_gene: W[g] = (z_alpha_t[,g], z_beta0[g], A_g), U = (mu_alpha | sigma_alpha | mu_beta0, sigma_beta0)
   const float *W, *U;
@@ -365,8 +366,8 @@ k_lik_tc(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtens
     if (h == 1) { s_half[0][r] = sum0; s_half[1][r] = sum1; }
     asm volatile("bar.sync 1, 256;" ::: "memory");
     if (h == 0) {
-      a.Spart[row * 2 + 0] = (float)(sum0 + s_half[0][r]);
-      a.Spart[row * 2 + 1] = (float)(sum1 + s_half[1][r]);
+      a.Spart[row * 2 + 0] = sum0 + s_half[0][r];
+      a.Spart[row * 2 + 1] = sum1 + s_half[1][r];
     }
   }
   if (tr0) a.trace[8 * 30 + 2] = clock64();
@@ -482,7 +483,7 @@ int launch_lik_tc(bvg_fit *f, bool bwd) {
   TcState *t = (TcState *)f->tc;
   TcArgs a;
   memset(&a, 0, sizeof(a));  // padding bytes take part in the change check below
-  a.Ppart = (float *)m.Ppart; a.Spart = (float *)m.Spart;
+  a.Ppart = (float *)m.Ppart; a.Spart = (double *)m.Spart;
   a.W = m.W; a.U = m.U; a.k = m.k;
   a.hist_val = m.hist_val; a.hist_cnt = m.hist_cnt; a.nhist = m.nhist;
   a.hterm = m.lik == BVG_NB ? m.hterm : nullptr;  // allocated only when every distinct count gets a lane (api.cu)

@@ -29,7 +29,7 @@ struct TbArgs {
   const float *Y;           // [G][ldY] fp32
   int64_t ldY, M, G, Gpad, Mpad;
   __nv_bfloat16 *R1, *R2;   // [Gpad][Mpad]
-  float *Spart;             // [nsplit][Gpad][2]
+  double *Spart;            // [nsplit][Gpad][2] fp64: the per-(split, gene) sums are accumulated in fp64 and stay fp64
   // backward
   float *Ppart;             // [nsplit][Gpad][KP]
   int KP, k1;               // padded row width of Ppart, k + 1
@@ -269,8 +269,8 @@ k_tcbig(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtens
         double o0, o1;
         ld_shared_f64x2(sred, o0, o1);
         const int64_t row = (int64_t)split * a.Gpad + g;
-        a.Spart[row * 2 + 0] = (float)(sum0 + o0);
-        a.Spart[row * 2 + 1] = (float)(sum1 + o1);
+        a.Spart[row * 2 + 0] = sum0 + o0;
+        a.Spart[row * 2 + 1] = sum1 + o1;
       }
     } else {
       const int j = jb * 128 + r;  // basis index of this row
@@ -377,7 +377,7 @@ int launch_lik_tcbig(bvg_fit *f, bool bwd) {
   TbArgs a;
   memset(&a, 0, sizeof(a));
   a.Y = (const float *)f->Y; a.ldY = f->ldY; a.M = m.M; a.G = m.G; a.Gpad = m.Gpad; a.Mpad = f->Mpad;
-  a.R1 = t->R1; a.R2 = t->R2; a.Spart = (float *)m.Spart; a.Ppart = (float *)m.Ppart; a.KP = m.KP; a.k1 = m.k + 1;
+  a.R1 = t->R1; a.R2 = t->R2; a.Spart = (double *)m.Spart; a.Ppart = (float *)m.Ppart; a.KP = m.KP; a.k1 = m.k + 1;
   a.nkb = t->Kp / 64;
   a.ntiles_m = (int)(f->Mpad / 128);
   a.tiles_per_split = (a.ntiles_m + m.nsplit - 1) / m.nsplit;

@@ -297,7 +297,7 @@ __device__ void finish_body(const DevModel &m, int mode, int jac, int propto, in
   if (!(phase & 2)) return;
   // multi-GPU, fused: the cross-gene sums of every gene shard meet here, inside the kernel that produced
   // them -- stores into the peers' exchange buffers over NVLink, no extra launch (bvg_internal.cuh)
-  const bool loc = m.elbo_local && mode == MODE_ELBO_DRAW;  // local share of a sharded ELBO draw: no exchange
+  const bool loc = m.elbo_local && (mode == MODE_ELBO_DRAW || mode == MODE_POST_DRAW);  // local share of a sharded ELBO / posterior draw: no exchange
   if ((phase & 1) && m.peer.world > 1 && !loc) peer_allreduce_cta(m.peer, m.tot, NS, scratch);
   const double shw = (loc && m.rank_id != 0) ? 0.0 : 1.0;   // weight of the terms that involve gene-shared parameters only
   const double *tot = m.tot;
@@ -480,7 +480,8 @@ __global__ void __launch_bounds__(BVG_GENE_MAX_THREADS) k_gene(DevModel m, int m
   const bool upd = mode == MODE_ADVI_UPDATE;
   DBG0(0);
   double aR = 0, aRz = 0, aDu = 0, aDu2 = 0, aS0 = 0, aS1 = 0, aZ2 = 0, aU = 0, aAP = 0, aAPz = 0;
-  const T *Pp = (const T *)m.Ppart, *Sp = (const T *)m.Spart;
+  const T *Pp = (const T *)m.Ppart;
+  const double *Sp = (const double *)m.Spart;
   for (int64_t g = (int64_t)blockIdx.x * nw + warp; g < m.G; g += (int64_t)gridDim.x * nw) {
     const int64_t li = lane < k ? L.z_alpha + g * k + lane : (lane == k ? L.z_beta0 + g : L.amp + g);
     const double zi = has ? zt[li] : ((dep && lane == k) ? m.depths[g] : 0.0);  // this lane's own parameter value
@@ -491,7 +492,8 @@ __global__ void __launch_bounds__(BVG_GENE_MAX_THREADS) k_gene(DevModel m, int m
     for (int sp0 = 0; sp0 < m.nsplit; sp0 += 8) {  // fixed order -> deterministic
       // unconditional loads from clamped (always valid) addresses: all 16 go out in one round trip; the
       // predicated form was compiled into several dependent load -> convert rounds
-      T pv[8], sv[8];
+      T pv[8];
+      double sv[8];
       const int lp = lane < KP ? lane : KP - 1, ls = lane & 1;
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
@@ -504,7 +506,7 @@ __global__ void __launch_bounds__(BVG_GENE_MAX_THREADS) k_gene(DevModel m, int m
       for (int q = 0; q < 8; ++q) {
         const bool ok = sp0 + q < m.nsplit;
         Pj += (ok && lane < KP) ? (double)pv[q] : 0.0;
-        s0 += (ok && lane < 2) ? (double)sv[q] : 0.0;
+        s0 += (ok && lane < 2) ? sv[q] : 0.0;
       }
     }
     const double s1 = __shfl_sync(0xffffffffu, s0, 1);
@@ -613,7 +615,8 @@ __global__ void __launch_bounds__(512) k_gene_big(DevModel m, int mode, int jac,
   for (int c = lane; c < NS; c += 32) row[c] = 0.0;
   __syncwarp();
   double aR = 0, aRz = 0, aDu = 0, aDu2 = 0, aS0 = 0, aS1 = 0, aZ2 = 0, aU = 0;
-  const T *Pp = (const T *)m.Ppart, *Sp = (const T *)m.Spart;
+  const T *Pp = (const T *)m.Ppart;
+  const double *Sp = (const double *)m.Spart;
   for (int64_t g = (int64_t)blockIdx.x * nw + warp; g < m.G; g += (int64_t)gridDim.x * nw) {
     const double A = m.Aexp[g];
     double s0 = 0, s1 = 0;
@@ -703,6 +706,13 @@ __global__ void __launch_bounds__(512) k_gene_big(DevModel m, int mode, int jac,
   finish_body(m, mode, jac, propto, fuse, 0);
 }
 
+// function attributes are per device: called from finalize_model (after cudaSetDevice) for every large-basis model
+int gene_big_setup() {
+  CUDA_TRY(cudaFuncSetAttribute(k_gene_big<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  CUDA_TRY(cudaFuncSetAttribute(k_gene_big<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  return BVG_OK;
+}
+
 int g_gene_fuse_override = -1;  // diagnostics (bvg_debug_time_gene): force the fuse argument
 int launch_gene_finish(bvg_fit *f, int mode, int jac, int propto, int ahead) {
   const int wpb = f->gene_wpb;
@@ -717,17 +727,11 @@ int launch_gene_finish(bvg_fit *f, int mode, int jac, int propto, int ahead) {
     const size_t shb = sizeof(double) * wb * bvg_ns(f->m.k);
     const bool splitb = f->comm_mode != 0;  // 2k+10 sums exceed one CTA's exchange width: reduce, all-reduce, finish
     const int fuseb = g_gene_fuse_override >= 0 ? g_gene_fuse_override : (splitb ? 1 : 3);
-    static bool attr_set = false;
-    if (!attr_set) {
-      CUDA_TRY(cudaFuncSetAttribute(k_gene_big<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-      CUDA_TRY(cudaFuncSetAttribute(k_gene_big<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-      attr_set = true;
-    }
     if (f->cfg.precision == BVG_PREC_FP64) CUDA_TRY(launch_pdl(k_gene_big<double>, dim3(f->m.nblk_gene), dim3(wb * 32), shb, f->stream, f->m, mode, jac, propto, fuseb));
     else CUDA_TRY(launch_pdl(k_gene_big<float>, dim3(f->m.nblk_gene), dim3(wb * 32), shb, f->stream, f->m, mode, jac, propto, fuseb));
     f->st.kernel_launches++;
     if (fuseb == 1) {
-      if (!(f->m.elbo_local && mode == MODE_ELBO_DRAW)) BVG_TRY(comm_allreduce(f, f->m.tot, bvg_ns(f->m.k)));
+      if (!(f->m.elbo_local && (mode == MODE_ELBO_DRAW || mode == MODE_POST_DRAW))) BVG_TRY(comm_allreduce(f, f->m.tot, bvg_ns(f->m.k)));
       k_finish<<<1, 512, 0, f->stream>>>(f->m, mode, jac, propto, 2, 0);
       f->st.kernel_launches += 1;
       CUDA_TRY(cudaGetLastError());
@@ -745,7 +749,7 @@ int launch_gene_finish(bvg_fit *f, int mode, int jac, int propto, int ahead) {
   }
   f->st.kernel_launches++;
   if (fuse == 1) {
-    if (!(f->m.elbo_local && mode == MODE_ELBO_DRAW)) BVG_TRY(comm_allreduce(f, f->m.tot, bvg_ns(f->m.k)));
+    if (!(f->m.elbo_local && (mode == MODE_ELBO_DRAW || mode == MODE_POST_DRAW))) BVG_TRY(comm_allreduce(f, f->m.tot, bvg_ns(f->m.k)));
     k_finish<<<1, 512, 0, f->stream>>>(f->m, mode, jac, propto, 2, ahead);
     f->st.kernel_launches += 1;
     CUDA_TRY(cudaGetLastError());

@@ -44,16 +44,24 @@ __global__ void __launch_bounds__(256) k_summary(DevModel m, int nd, int npad, d
   const int64_t g = blockIdx.x, li = m.L.amp + g;
   const uint64_t gi = (uint64_t)(m.LG.amp + m.gene_offset + g);
   const double mu = m.mu[li], sd_u = exp(m.omega[li]);
-  double acc = 0;
+  double acc = 0, nbad = 0;
   for (int t = threadIdx.x; t < npad; t += blockDim.x) {
     double v = INFINITY;
     if (t < nd) {
       v = given ? draws[g * nd + t]   // full-rank family: the draws were made by k_fullrank.cu
                 : exp(mu + sd_u * bvg_normal(m.seed, STREAM_DRAW, (uint32_t)t, gi));
       acc += v;
+      if (!isfinite(v)) nbad += 1.0;
       if (draws && !given) draws[g * nd + t] = v;
     }
     x[t] = v;
+  }
+  // a non-finite draw (overflowing exp, NaN mu / omega) would collide with the +inf padding and break the
+  // comparisons of the sorting network: such a gene gets NaN statistics instead of silently wrong quantiles
+  if (block_sum(nbad, red) > 0.0) {
+    if (threadIdx.x < 7) out[threadIdx.x * m.G + g] = NAN;
+    if (threadIdx.x == 7) out[7 * m.G + g] = 0.0;
+    return;
   }
   const double mean = block_sum(acc, red) / nd;
   acc = 0;

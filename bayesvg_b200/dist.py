@@ -62,11 +62,18 @@ def make_sharded_fit(phi, Y_local, shard, G_total, gene_offset, likelihood, prec
     else:
         uid = E.comm_unique_id() if shard.rank == 0 else b""
         fit.comm_init(_bcast_bytes(uid)[:128])
+    # every rank has mapped every peer's exchange buffer before anyone's first exchange can start
+    import torch.distributed as td
+    td.barrier()
     return fit
 
 
-def fit_sharded(phi, Y, shard, likelihood, precision, engine, cfg, comm="peer", gene_depths=None):
-    """Y: full M x G on every rank (each keeps its slice).  Returns the gathered G x 8 table."""
+def fit_sharded(phi, Y, shard, likelihood, precision, engine, cfg, comm="peer", gene_depths=None, save_model=False,
+                n_draws=None, genes=None, extra=None):
+    """Y: full M x G on every rank (each keeps its slice).  Returns (gathered G x 8 table, model).
+    save_model (save.model = TRUE, R/findSpatiallyVariableFeaturesBayes.R:483-489): every rank draws its columns of
+    the posterior matrix (bvg_fit_get_posterior on a sharded fit), the columns are gathered and put into the
+    declaration order of the UNSHARDED model, and every rank returns the same api.VariationalFit."""
     import torch
     import torch.distributed as td
     G = Y.shape[1]
@@ -74,13 +81,70 @@ def fit_sharded(phi, Y, shard, likelihood, precision, engine, cfg, comm="peer", 
     fit = make_sharded_fit(phi, np.asfortranarray(Y[:, g0:g1]), shard, G, g0, likelihood, precision, engine, cfg, comm,
                            None if gene_depths is None else np.asarray(gene_depths)[g0:g1])
     local = fit.run()
-    fit.close()
     dev = "cuda" if td.get_backend() == "nccl" else "cpu"
+    model = None
+    if save_model:
+        model = _gather_model(fit, shard, likelihood, G, g0, g1, gene_depths is not None, n_draws, genes, extra or {}, dev)
+    fit.close()
     sizes = [b - a for a, b in gene_ranges(G, shard.world_size)]
     bufs = [torch.zeros(s, 8, dtype=torch.float64, device=dev) for s in sizes]
     td.all_gather(bufs, torch.tensor(np.ascontiguousarray(local), device=dev)) if len(set(sizes)) == 1 else _gather_ragged(bufs, local, dev, sizes)
     table = np.concatenate([b.cpu().numpy() for b in bufs], 0)
-    return table, None
+    return table, model
+
+
+def assemble_posterior(parts, likelihood, G, k, ranges, depth=False):
+    """parts[r] = (n x (3 + D_r + ntp G_r)) posterior matrix of the shard holding genes ranges[r] (local declaration
+    order, then beta0[G_r] (hierarchical intercept only), amplitude_sq[G_r]) -> the n x (3 + D + ntp G) matrix of the
+    unsharded model.  lp__/log_p__/log_g__ and the replicated gene-shared columns are identical on every shard."""
+    LG = layout(likelihood, G, k, depth)
+    D, ntp = LG["D"], (1 if depth else 2)
+    n = parts[0].shape[0]
+    out = np.empty((n, 3 + D + ntp * G), order="F")
+    out[:, :3] = parts[0][:, :3]
+    for (g0, g1), P in zip(ranges, parts):
+        Gl = g1 - g0
+        Dl = layout(likelihood, Gl, k, depth)["D"]
+        if P.shape != (n, 3 + Dl + ntp * Gl):
+            raise ValueError("shard matrix has the wrong shape")
+        out[:, 3 + shard_index(likelihood, G, k, g0, g1, depth)] = P[:, 3:3 + Dl]
+        for t in range(ntp):   # beta0[G] (if any), then amplitude_sq[G]
+            out[:, 3 + D + t * G + g0:3 + D + t * G + g1] = P[:, 3 + Dl + t * Gl:3 + Dl + (t + 1) * Gl]
+    return out
+
+
+def _gather_model(fit, shard, likelihood, G, g0, g1, depth, n_draws, genes, extra, dev):
+    import torch
+    import torch.distributed as td
+    from . import engine as E
+    from .api import VariationalFit
+    n = int(fit.cfg.n_draws if n_draws is None else n_draws)
+    k = fit.k
+    local = np.ascontiguousarray(fit.posterior(n))
+    mu, om = fit.get_variational()
+    ranges = gene_ranges(G, shard.world_size)
+    widths = [3 + layout(likelihood, b - a, k, depth)["D"] + (1 if depth else 2) * (b - a) for a, b in ranges]
+    wmax = max(widths)
+
+    def gather(mat):   # ragged in the column count: pad to the widest shard
+        pad = torch.zeros(mat.shape[0], wmax, dtype=torch.float64, device=dev)
+        pad[:, :mat.shape[1]] = torch.tensor(mat, device=dev)
+        outs = [torch.zeros_like(pad) for _ in ranges]
+        td.all_gather(outs, pad)
+        return [o.cpu().numpy() for o in outs]
+
+    parts = [p[:, :w] for p, w in zip(gather(local), widths)]
+    draws = assemble_posterior(parts, likelihood, G, k, ranges, depth)
+    mo = gather(np.stack([np.concatenate([np.zeros(3), mu]), np.concatenate([np.zeros(3), om])]))
+    LGD = layout(likelihood, G, k, depth)["D"]
+    mu_g, om_g = np.empty(LGD), np.empty(LGD)
+    for (a, b), m2 in zip(ranges, mo):
+        Dl = layout(likelihood, b - a, k, depth)["D"]
+        idx = shard_index(likelihood, G, k, a, b, depth)
+        mu_g[idx], om_g[idx] = m2[0, 3:3 + Dl], m2[1, 3:3 + Dl]
+    # column names of the unsharded model: ask a name-only helper with the global G
+    cols = E.posterior_column_names(likelihood == "nb", depth, G, k)
+    return VariationalFit(cols, draws, mu=mu_g, omega=om_g, trace=fit.trace(), stats=fit.stats(), genes=genes, **extra)
 
 
 def _gather_ragged(bufs, local, dev, sizes):

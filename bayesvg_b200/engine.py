@@ -100,6 +100,23 @@ def gmm_fit(X, K, algorithm="fullrank", n_iter=30000, n_draws=1000, elbo_samples
     return dict(mu=mu, var=var, draws=draws, soft=soft, info=info)
 
 
+def posterior_column_names(nb, depth, G, k):
+    """header of CmdStan's variational output CSV for approxGP (gaussian) / approxGP4 (nb) / approxGP2-3 (depth)"""
+    vec = lambda name, n: [f"{name}[{i + 1}]" for i in range(n)]  # noqa: E731
+    z = [f"z_alpha_t[{j + 1},{g + 1}]" for g in range(G) for j in range(k)]  # column-major
+    hyper = ["mu_amplitude", "sigma_amplitude"]
+    alpha = vec("mu_alpha", k) + vec("sigma_alpha", k) + z
+    tail = "phi_nb" if nb else "sigma_y"
+    if depth:      # approxGP2.stan:13-23 / approxGP3.stan:13-23
+        cols = ["beta0", "beta1", tail] + vec("amplitude", G) + hyper + alpha
+    elif nb:       # approxGP4.stan:12-23
+        cols = ["mu_beta0", "sigma_beta0"] + vec("z_beta0", G) + [tail] + vec("amplitude", G) + hyper + alpha
+    else:          # approxGP.stan:12-23
+        cols = ["mu_beta0", "sigma_beta0"] + vec("z_beta0", G) + hyper + vec("amplitude", G) + alpha + [tail]
+    tp = ([] if depth else vec("beta0", G)) + vec("amplitude_sq", G)
+    return ["lp__", "log_p__", "log_g__"] + cols + tp
+
+
 class Fit:
     """gene_depths (length G, log of each gene's total count) selects the depth-adjusted programs
     inst/approxGP2.stan / approxGP3.stan (gene.depth.adjust = TRUE in the reference)."""
@@ -283,21 +300,9 @@ class Fit:
     def posterior_columns(self):
         """CmdStan's variational CSV header for this model: lp__, log_p__, log_g__, the parameters in declaration
         order (inst/approxGP*.stan `parameters`), then the transformed parameters (approxGP.stan:25-28)."""
-        G, k, nb, depth = self.G, self.k, self.cfg.likelihood == B.NB, bool(self.cfg.depth_adjust)
-        vec = lambda name, n: [f"{name}[{i + 1}]" for i in range(n)]  # noqa: E731
-        z = [f"z_alpha_t[{j + 1},{g + 1}]" for g in range(G) for j in range(k)]  # column-major
-        hyper = ["mu_amplitude", "sigma_amplitude"]
-        alpha = vec("mu_alpha", k) + vec("sigma_alpha", k) + z
-        tail = "phi_nb" if nb else "sigma_y"
-        if depth:      # approxGP2.stan:13-23 / approxGP3.stan:13-23
-            cols = ["beta0", "beta1", tail] + vec("amplitude", G) + hyper + alpha
-        elif nb:       # approxGP4.stan:12-23
-            cols = ["mu_beta0", "sigma_beta0"] + vec("z_beta0", G) + [tail] + vec("amplitude", G) + hyper + alpha
-        else:          # approxGP.stan:12-23
-            cols = ["mu_beta0", "sigma_beta0"] + vec("z_beta0", G) + hyper + vec("amplitude", G) + alpha + [tail]
-        assert len(cols) == self.D
-        tp = ([] if depth else vec("beta0", G)) + vec("amplitude_sq", G)
-        return ["lp__", "log_p__", "log_g__"] + cols + tp
+        cols = posterior_column_names(self.cfg.likelihood == B.NB, bool(self.cfg.depth_adjust), self.G, self.k)
+        assert len(cols) == 3 + self.D + (1 if self.cfg.depth_adjust else 2) * self.G
+        return cols
 
     def posterior(self, n=None):
         """n x ncol draws of the whole model (what cmdstanr's `fit_vi$draws()` holds; save.model = TRUE, :483-489)."""

@@ -160,6 +160,9 @@ int bvg_fit_set_y_i32(bvg_fit *, const int32_t *y, int64_t M, int64_t G);
  * May be called before or after bvg_fit_set_y; must be set before any evaluation. */
 int bvg_fit_set_gene_depths(bvg_fit *, const double *gene_depths, int64_t G);
 int bvg_fit_dim(bvg_fit *, int64_t *D);
+/* shape of the staged model: M spots, G (local) genes, k basis functions, D unconstrained parameters; any pointer may
+ * be NULL.  Lets a binding size and validate its buffers from the handle instead of trusting caller-supplied sizes. */
+int bvg_fit_shape(bvg_fit *, int64_t *M, int64_t *G, int *k, int64_t *D);
 
 /* multi-GPU (one process per GPU of one node; the reference has no counterpart -- its fit is one
  * CPU thread, R/findSpatiallyVariableFeaturesBayes.R:123-129).  Two transports for the one exchange
