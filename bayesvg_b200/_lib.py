@@ -23,7 +23,7 @@ EXPORTS = [
     "bvg_fit_advi", "bvg_fit_summarize", "bvg_fit_set_variational", "bvg_fit_get_variational", "bvg_fit_get_cholesky", "bvg_fit_set_cholesky", "bvg_fit_pathfinder_single",
     "bvg_fit_advi_steps", "bvg_fit_elbo", "bvg_fit_time_lik_kernel", "bvg_fit_flush_l2", "bvg_fit_get_summary",
     "bvg_fit_get_draws", "bvg_fit_posterior_ncol", "bvg_fit_get_posterior", "bvg_fit_get_trace", "bvg_fit_get_stats", "bvg_debug_stage_times", "bvg_debug_gene_trace", "bvg_debug_time_gene",
-    "bvg_debug_tc_trace",
+    "bvg_debug_tc_trace", "bvg_debug_persist_trace",
 ]
 
 
@@ -104,6 +104,7 @@ def lib():
     L.bvg_debug_time_gene.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _fp]
     L.bvg_debug_tc_trace.argtypes = [_vp, C.POINTER(C.c_longlong), C.c_int]
     L.bvg_debug_gene_trace.argtypes = [_vp, C.POINTER(C.c_longlong), C.c_int]
+    L.bvg_debug_persist_trace.argtypes = [_vp, C.c_int, C.POINTER(C.c_longlong), C.c_int]
     L.bvg_fit_get_summary.argtypes = [_vp, _dp]
     L.bvg_fit_get_draws.argtypes = [_vp, _dp]
     L.bvg_gmm_log_prob.argtypes = [C.c_int, _dp, C.c_int64, C.c_int, C.c_int, _dp, C.c_int, C.c_int, C.POINTER(C.c_double), _dp]

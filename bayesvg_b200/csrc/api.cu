@@ -95,6 +95,7 @@ extern "C" int bvg_fit_create(const bvg_config *cfg, bvg_fit **out) {
   bvg_fit *f = new bvg_fit();
   memset(f, 0, sizeof(*f));
   { const char *e = getenv("BVG_NO_ELBO_BATCH"); g_no_elbo_batch = e && e[0] == '1'; }
+  { const char *e = getenv("BVG_NO_PERSIST"); f->no_persist = e && e[0] == '1'; }
   f->cfg = *cfg;
   CUDA_TRY(cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking));
   CUDA_TRY(cudaEventCreate(&f->ev0));
@@ -477,6 +478,14 @@ static int ctl_get(bvg_fit *f, Ctl *h) {
 // coefficient rows from zeta, so an evaluation is two launches.
 static int advi_steps(bvg_fit *f, int n) {
   const bool ahead = f->engine == BVG_ENGINE_TCGEN05 && !f->big_tc && f->m.k <= BVG_SMALL_K;
+  if (n > 0 && persist_ok(f)) {
+    // the whole stretch in one cooperative launch (k_advi_persist.cu): no host involvement between evaluations
+    BVG_TRY(launch_prep(f, PREP_GRAD));
+    BVG_TRY(launch_advi_persist(f, n));
+    f->h_t_grad += (uint32_t)n;
+    f->st.grad_evals += n;
+    return BVG_OK;
+  }
   for (int i = 0; i < n; ++i) {
     if (!ahead || i == 0) BVG_TRY(launch_prep(f, PREP_GRAD));
     BVG_TRY(launch_lik(f, true));

@@ -305,6 +305,7 @@ struct bvg_fit {
   int elbo_cap;        // capacity of m.elbo_lps
   void *peer_buf;      // this rank's exchange buffer (cudaMalloc, exported with cudaIpcGetMemHandle)
   void *peer_map[BVG_MAX_PEERS];  // peers' buffers opened with cudaIpcOpenMemHandle
+  bool no_persist;     // diagnostics / tests (BVG_NO_PERSIST=1): keep the two-launch evaluation chain instead of k_advi_persist
 };
 
 void bvg_set_error(const char *fmt, ...);
@@ -334,6 +335,9 @@ void tcbig_destroy(bvg_fit *f);
 bool tc_available();                                         // false until the tcgen05 kernel is linked in
 int tc_setup(bvg_fit *f);                                    // build TMA descriptors etc.
 void tc_destroy(bvg_fit *f);
+bool persist_ok(bvg_fit *f);                                 // k_advi_persist.cu: a stretch of ADVI iterations in one cooperative launch
+int launch_advi_persist(bvg_fit *f, int n_iter);             //   (the current draw must be in place: launch_prep(PREP_GRAD) first)
+void persist_destroy(bvg_fit *f);
 int gene_big_setup();                                        // k_model.cu: per-device function attributes of k_gene_big
 int launch_gene_finish(bvg_fit *f, int mode, int jacobian, int propto, int ahead = 0);  // per-gene backward (+ update, + next draw) + cross-gene finish
 int comm_allreduce(bvg_fit *f, double *buf, int n);          // comm.cu

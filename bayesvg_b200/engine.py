@@ -270,6 +270,18 @@ class Fit:
         B.check(B.lib().bvg_debug_tc_trace(self._h, out, nchunk))
         return np.array(list(out), dtype=np.int64).reshape(nchunk, 8)
 
+    def persist_trace(self, n_iter=20):
+        """diagnostics: clock64 stamps of CTA 0 of one k_advi_persist stretch, [iteration][8]: 0 iteration start, 1 passes done
+        (partials published), 2 gene phases done, 3 grid barrier passed, 4 sums reduced (+ exchanged), 5 shared update done,
+        6 state loaded (before the tile wait), 7 tile counter reached, 8-15 finer stamps of the gene phase / block row.  Second
+        array: per-chunk stamps of the pass of iteration 8 (layout of tc_trace); row 31: coefficient rows stored, chunk loop
+        done, D2 read, partials written."""
+        out = (C.c_longlong * (32 * 16 + 32 * 8 + 32 * 4))()
+        B.check(B.lib().bvg_debug_persist_trace(self._h, int(n_iter), out, 64))
+        v = np.array(list(out), dtype=np.int64)
+        self.last_latency_probe = v[768:].reshape(32, 4)
+        return v[:512].reshape(32, 16), v[512:768].reshape(32, 8)
+
     def time_gene(self, n=100, mode=1, fuse=3, ahead=0):
         """diagnostics: average device ms of n back-to-back k_gene launches"""
         ms = C.c_float()

@@ -243,6 +243,7 @@ int bvg_debug_stage_times(bvg_fit *, int n, float *out4 /* ms: prep, likelihood,
 int bvg_debug_gene_trace(bvg_fit *, long long *out16 /* %globaltimer ns stamps inside k_gene */, int ahead);
 int bvg_debug_time_gene(bvg_fit *, int n, int mode /* 0 grad out, 1 advi update, 3 lp only */, int fuse /* 0 | 3 */, int ahead, float *ms_avg);
 int bvg_debug_tc_trace(bvg_fit *, long long *out /* [chunk][8] clock64 stamps of CTA (0,0) */, int nchunk_cap);
+int bvg_debug_persist_trace(bvg_fit *, int n_iter, long long *out /* [iteration][8] clock64 stamps of CTA 0 of k_advi_persist */, int cap_iters);
 
 #ifdef __cplusplus
 }

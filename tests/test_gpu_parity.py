@@ -277,6 +277,54 @@ def test_draw_ahead_batches_are_bitwise_identical(lik):
     assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
 
 
+def _advi_run(p, lik, steps, no_persist, depths=None, seed=11, eta=0.05):
+    """(mu, omega, kernel launches) after `steps` mean-field iterations on the fused tcgen05 engine"""
+    old = os.environ.get("BVG_NO_PERSIST")
+    os.environ["BVG_NO_PERSIST"] = "1" if no_persist else "0"
+    try:
+        f = _fit(p["phi"], p["y"], lik, "fast", "tcgen05", seed=seed, gene_depths=depths)
+    finally:
+        if old is None:
+            del os.environ["BVG_NO_PERSIST"]
+        else:
+            os.environ["BVG_NO_PERSIST"] = old
+    f.set_variational(np.zeros(f.D), None)
+    f.advi_steps(0, eta, reset=True)
+    n0 = f.stats()["kernel_launches"]
+    for n in steps:
+        f.advi_steps(n, eta)
+    out = f.get_variational() + (f.stats()["kernel_launches"] - n0,)
+    f.close()
+    return out
+
+
+@pytest.mark.parametrize("lik,depth", [("gaussian", False), ("nb", False), ("gaussian", True), ("nb", True)])
+@pytest.mark.parametrize("M,G,k", [(1000, 257, 20), (300, 200, 17), (97, 130, 7), (260, 1, 1), (4000, 700, 23)])
+def test_persistent_advi_kernel_equals_the_two_launch_chain(lik, depth, M, G, k):
+    """k_advi_persist (one cooperative launch per stretch: passes, tile / grid arrival counters, replicated finish) against
+    k_lik_tc -> k_gene per evaluation: same Philox draws, same per-gene arithmetic; only the cross-gene sums are added in a
+    different fixed order, so 25 iterations agree to rounding.  Also: the stretch really is 2 launches (k_prep + persistent)."""
+    p = make_problem(M, G, k, lik, seed=21)
+    depths = np.log(np.maximum(p["y"].sum(0), 1.0)) - 5.0 if depth else None
+    mu_a, om_a, la = _advi_run(p, lik, (25,), False, depths)
+    mu_b, om_b, lb = _advi_run(p, lik, (25,), True, depths)
+    assert la == 2 and lb >= 50
+    assert np.all(np.isfinite(mu_a)) and rel_err(mu_a, mu_b) < 1e-9 and rel_err(om_a, om_b) < 1e-9
+    # stretch boundaries re-draw with k_prep: 25 == 7 + 1 + 17, bit for bit
+    mu_c, om_c, _ = _advi_run(p, lik, (7, 1, 17), False, depths)
+    assert np.array_equal(mu_a, mu_c) and np.array_equal(om_a, om_c)
+
+
+@pytest.mark.parametrize("lik", ["gaussian", "nb"])
+def test_persistent_advi_kernel_with_more_work_items_than_sms(lik):
+    """157 gene tiles (x spot splits) on 148 SMs: a CTA of the persistent kernel walks several (tile, split) items per iteration"""
+    p = make_problem(700, 20000, 5, lik, seed=3)
+    mu_a, om_a, la = _advi_run(p, lik, (12,), False)
+    mu_b, om_b, _ = _advi_run(p, lik, (12,), True)
+    assert la == 2
+    assert np.all(np.isfinite(mu_a)) and rel_err(mu_a, mu_b) < 1e-9 and rel_err(om_a, om_b) < 1e-9
+
+
 @pytest.mark.parametrize("iters,tol_lp,tol_th", [(8, 1e-10, 1e-7), (60, 1e-5, 5e-2)])
 def test_lbfgs_matches_oracle_fp64(iters, tol_lp, tol_th):
     """same algorithm (two-loop vs its vector-free Gram form): identical iterates early on, the same
