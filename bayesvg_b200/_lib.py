@@ -46,7 +46,7 @@ class Stats(C.Structure):
         ("converged", C.c_int32), ("mle_iters", C.c_int32), ("mle_fevals", C.c_int32), ("mle_term", C.c_int32),
         ("mle_lp", C.c_double), ("elbo", C.c_double), ("sec_h2d", C.c_double), ("sec_mle", C.c_double),
         ("sec_adapt", C.c_double), ("sec_sga", C.c_double), ("sec_draws", C.c_double), ("sec_total", C.c_double),
-        ("kernel_launches", C.c_int64), ("engine_used", C.c_int32), ("pad", C.c_int32),
+        ("kernel_launches", C.c_int64), ("engine_used", C.c_int32), ("mle_fp64_from", C.c_int32),
     ]
 
 

@@ -96,6 +96,7 @@ extern "C" int bvg_fit_create(const bvg_config *cfg, bvg_fit **out) {
   memset(f, 0, sizeof(*f));
   { const char *e = getenv("BVG_NO_ELBO_BATCH"); g_no_elbo_batch = e && e[0] == '1'; }
   { const char *e = getenv("BVG_NO_PERSIST"); f->no_persist = e && e[0] == '1'; }
+  { const char *e = getenv("BVG_NO_MLE_FP64"); f->no_mle_fp64 = e && e[0] == '1'; }
   f->cfg = *cfg;
   CUDA_TRY(cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking));
   CUDA_TRY(cudaEventCreate(&f->ev0));
@@ -105,6 +106,7 @@ extern "C" int bvg_fit_create(const bvg_config *cfg, bvg_fit **out) {
 }
 
 static void free_model(bvg_fit *f) {
+  shadow_destroy(f);
   fr_destroy(f);
   cudaFree(f->eb_d);
   f->eb_d = nullptr; f->eb_cap = 0;
@@ -302,6 +304,7 @@ static int set_y_impl(bvg_fit *f, const SRC *y, int64_t M, int64_t G) {
   // same shape as the resident model (a refit on new expression values): keep every allocation, the staged
   // basis and the tensor maps; only Y is restaged
   const bool reuse = f->have_y && f->m.G == G && f->Y != nullptr;
+  shadow_destroy(f);   // the fp64 copy of Y belongs to the previous data
   if (f->have_y && !reuse) free_model(f);
   f->have_y = f->have_mle = f->have_vi = f->have_summary = false;
   const bool fp64 = f->cfg.precision == BVG_PREC_FP64;
@@ -518,9 +521,59 @@ static int advi_elbo(bvg_fit *f, int S, double *out) {
     if (std::isnan(*out)) *out = -INFINITY;
     return BVG_OK;
   }
+  const int64_t D = f->m.L.D;
+  if (persist_ok(f) && !g_no_elbo_batch) {
+    // fused tcgen05 engine: ONE batched k_prep launch draws all S points (mu / omega do not change between them), ONE
+    // cooperative launch (k_elbo_persist) streams the S forward-only passes with no barrier between draws and leaves the S
+    // log densities -- local shares on a gene-sharded fit, all-reduced once below
+    const int k = f->m.k;
+    const size_t nd = (size_t)D + 4 + k + (size_t)f->m.G, nf = (size_t)f->m.Gpad * 32 + 96;
+    if (f->eb_cap < S) {
+      cudaFree(f->eb_d);
+      f->eb_d = nullptr; f->eb_cap = 0;
+      CUDA_TRY(cudaMalloc(&f->eb_d, (size_t)S * (nd * sizeof(double) + nf * sizeof(float))));
+      CUDA_TRY(cudaMemsetAsync(f->eb_d, 0, (size_t)S * (nd * sizeof(double) + nf * sizeof(float)), f->stream));  // W pads stay zero
+      f->eb_cap = S;
+    }
+    if (f->elbo_cap < S) {
+      cudaFree(f->m.elbo_lps);
+      f->m.elbo_lps = nullptr; f->elbo_cap = 0;
+      CUDA_TRY(cudaMalloc(&f->m.elbo_lps, sizeof(double) * S));
+      f->elbo_cap = S;
+    }
+    double *bz = f->eb_d, *bs = bz + (size_t)f->eb_cap * D, *ba = bs + (size_t)f->eb_cap * (4 + k);
+    float *bw = (float *)(ba + (size_t)f->eb_cap * f->m.G), *bu = bw + (size_t)f->eb_cap * f->m.Gpad * 32;
+    DevModel &m = f->m;
+    double *z0 = m.zeta, *s0 = m.shx, *a0 = m.Aexp;
+    float *w0 = m.W, *u0 = m.U;
+    m.zeta = bz; m.shx = bs; m.Aexp = ba; m.W = bw; m.U = bu;
+    m.elbo_local = f->comm_mode ? 1 : 0;
+    m.rank_id = f->cfg.rank;
+    int rc = launch_prep_batch(f, PREP_ELBO, S);
+    if (rc == BVG_OK) rc = launch_elbo_persist(f, S, m.elbo_lps);
+    m.zeta = z0; m.shx = s0; m.Aexp = a0; m.W = w0; m.U = u0;
+    m.elbo_local = 0;
+    BVG_TRY(rc);
+    if (f->comm_mode) BVG_TRY(comm_allreduce(f, f->m.elbo_lps, S));
+    std::vector<double> lps(S);
+    CUDA_TRY(cudaMemcpyAsync(lps.data(), f->m.elbo_lps, sizeof(double) * S, cudaMemcpyDeviceToHost, f->stream));
+    BVG_TRY(vec_dot_sum(f->stream, f->m.omega, nullptr, f->scratch + D, D, f->m.tot));
+    BVG_TRY(comm_allreduce(f, f->m.tot, 2));
+    double hs[2];
+    CUDA_TRY(cudaMemcpyAsync(hs, f->m.tot, sizeof(hs), cudaMemcpyDeviceToHost, f->stream));
+    h.t_elbo += (uint32_t)S;
+    BVG_TRY(ctl_set(f, h));   // synchronises the stream
+    f->st.elbo_evals++;
+    double acc = 0;
+    int ok = 0;
+    for (double v : lps) if (std::isfinite(v)) { acc += v; ++ok; }
+    if (!ok) { *out = -INFINITY; return BVG_OK; }
+    *out = acc / ok + 0.5 * (double)f->m.LG.D * (1.0 + BVG_LOG_TWO_PI) + hs[1];
+    if (std::isnan(*out)) *out = -INFINITY;
+    return BVG_OK;
+  }
   h.elbo_acc = 0; h.elbo_ok = 0;
   BVG_TRY(ctl_set(f, h));
-  const int64_t D = f->m.L.D;
   if (f->comm_mode) {
     // gene-sharded: every draw leaves its LOCAL share of the log density in elbo_lps[draw] with no exchange; one
     // all-reduce of the S scalars (and of the entropy sum) follows

@@ -256,6 +256,57 @@ __device__ inline double warp_sum(double v) {
   return v;
 }
 
+// Log density from the cross-gene sums tot[] and the gene-shared entries of the point zt (full unconstrained layout) with their
+// exponentials shx (DevModel::shx): the last-warp job of finish_body, and the ELBO mode of the persistent kernel.
+// inst/approxGP.stan:37-49 / approxGP4.stan:37-49 / approxGP2-3.stan:36-48 of the reference.  Warp-collective (all 32 lanes of
+// one warp call it); the value is valid on lane 0.  loc: local share of a gene-sharded draw (gene counts of this shard only,
+// terms of the gene-shared parameters weighted by shw = 1 on rank 0, 0 elsewhere).
+__device__ inline double bvg_lp_from_sums(const DevModel &m, const double *tot, const double *zt, const double *shx, int jac,
+                                          int propto, bool loc, double shw, int lane) {
+  const int k = m.k;
+  const Layout &L = m.L;
+  const double mb = zt[L.mu_beta0], lsb = zt[L.sigma_beta0], sb = shx[0];
+  const double ma = zt[L.mu_amp], lsa = zt[L.sigma_amp], sa = shx[1];
+  const double lt = zt[L.tail], tl = shx[2];
+  const double Gt = loc ? (double)m.G : (double)m.G_total, N = (double)m.M * Gt;
+  const double j1 = jac ? 1.0 : 0.0;
+  double pa = 0;  // prior terms of mu_alpha, sigma_alpha + jacobian of sigma_alpha
+  for (int j = lane; j < k; j += 32) {
+    const double a = zt[L.mu_alpha + j], ls = zt[L.sigma_alpha + j], s = shx[3 + j];
+    pa += -a * a / 8.0 - 0.5 * s * s + j1 * ls;
+  }
+  pa = warp_sum(pa);
+  double lp, lsh;  // lp: terms carrying cross-gene sums or gene counts; lsh: gene-shared parameters only
+  if (m.lik == BVG_GAUSSIAN) { lp = -N * lt - 0.5 * tot[S_SSE] / (tl * tl); lsh = -0.5 * tl * tl; }
+  else { lp = tot[S_SSE] + tot[S_LG]; lsh = -log1p(tl * tl / 4.0); }
+  if (m.depth && m.lik == BVG_GAUSSIAN) lsh += 0.5 * tl * tl - tl * tl / 8.0;  // sigma_y ~ normal(0, 2) (approxGP2.stan:44)
+  lp += -0.5 * tot[S_Z2];
+  lsh += -mb * mb / 8.0 - (m.depth ? sb * sb / 8.0 : 0.5 * sb * sb) - ma * ma / 8.0 - 0.5 * sa * sa;
+  lp += -Gt * lsa - tot[S_U] - 0.5 * tot[S_DU2] / (sa * sa);
+  lsh += pa;
+  if (jac) { lp += tot[S_U]; lsh += (m.depth ? 0.0 : lsb) + lsa + lt; }
+  if (!propto) {
+    if (!m.depth) {
+      if (m.lik == BVG_GAUSSIAN) {
+        lp += -0.5 * BVG_LOG_TWO_PI * (N + (double)k * Gt + 2.0 * Gt);
+        lsh += -0.5 * BVG_LOG_TWO_PI * (2.0 * k + 5.0) - (k + 2.0) * BVG_LOG_TWO;
+      } else {
+        lp += -0.5 * BVG_LOG_TWO_PI * ((double)k * Gt + 2.0 * Gt);
+        lsh += -0.5 * BVG_LOG_TWO_PI * (2.0 * k + 4.0) - (k + 2.0) * BVG_LOG_TWO - BVG_LOG_PI;
+      }
+    } else {  // approxGP2/3: no z_beta0 terms; normal(0, 2) on beta0, beta1, mu_amplitude, mu_alpha[k] (and sigma_y)
+      if (m.lik == BVG_GAUSSIAN) {
+        lp += -0.5 * BVG_LOG_TWO_PI * (N + (double)k * Gt + Gt);
+        lsh += -0.5 * BVG_LOG_TWO_PI * (2.0 * k + 5.0) - (k + 4.0) * BVG_LOG_TWO;
+      } else {
+        lp += -0.5 * BVG_LOG_TWO_PI * ((double)k * Gt + Gt);
+        lsh += -0.5 * BVG_LOG_TWO_PI * (2.0 * k + 4.0) - (k + 3.0) * BVG_LOG_TWO - BVG_LOG_PI;
+      }
+    }
+  }
+  return lp + shw * lsh;
+}
+
 // ---- host-side fit object ---------------------------------------------------------------------
 struct NcclApi;
 struct bvg_fit {
@@ -306,6 +357,8 @@ struct bvg_fit {
   void *peer_buf;      // this rank's exchange buffer (cudaMalloc, exported with cudaIpcGetMemHandle)
   void *peer_map[BVG_MAX_PEERS];  // peers' buffers opened with cudaIpcOpenMemHandle
   bool no_persist;     // diagnostics / tests (BVG_NO_PERSIST=1): keep the two-launch evaluation chain instead of k_advi_persist
+  void *shadow;        // fp64 evaluator of a fast-precision fit (fp64_shadow.cu), built when the L-BFGS line search hits the fast engines' noise floor
+  bool no_mle_fp64;    // diagnostics (BVG_NO_MLE_FP64=1): let the fast path's L-BFGS end with TERM_LSFAIL as in round 1
 };
 
 void bvg_set_error(const char *fmt, ...);
@@ -337,7 +390,12 @@ int tc_setup(bvg_fit *f);                                    // build TMA descri
 void tc_destroy(bvg_fit *f);
 bool persist_ok(bvg_fit *f);                                 // k_advi_persist.cu: a stretch of ADVI iterations in one cooperative launch
 int launch_advi_persist(bvg_fit *f, int n_iter);             //   (the current draw must be in place: launch_prep(PREP_GRAD) first)
+int launch_elbo_persist(bvg_fit *f, int S, double *d_lps);   //   all S forward-only draws of an ELBO estimate in one cooperative launch
 void persist_destroy(bvg_fit *f);
+int shadow_enter(bvg_fit *f);                                // fp64_shadow.cu: evaluate in fp64 (SIMT kernels, Y widened on the device) until shadow_leave
+void shadow_leave(bvg_fit *f);
+void shadow_destroy(bvg_fit *f);
+bool shadow_active(const bvg_fit *f);
 int gene_big_setup();                                        // k_model.cu: per-device function attributes of k_gene_big
 int launch_gene_finish(bvg_fit *f, int mode, int jacobian, int propto, int ahead = 0);  // per-gene backward (+ update, + next draw) + cross-gene finish
 int comm_allreduce(bvg_fit *f, double *buf, int n);          // comm.cu

@@ -43,9 +43,12 @@ struct PersistArgs {
   DevModel m;
   int n_iter, nitems, nsplit, gs;   // gs = genes of a tile owned by each of its splits in the gene phase
   int pre_y, pre_b;                 // stages the producers run ahead into the next pass (<= TC_NY, <= TC_NB - 1)
+  int xchg_all;                     // multi-GPU: 1 = every CTA polls the exchange buffer itself, 0 = CTA 0 polls and publishes the totals
   uint32_t *tile_cnt;               // [ntiles] arrival counters (zeroed before the launch; monotonic inside it)
   uint32_t *grid_cnt;               // [1]
   double *rows;                     // [2 parities][gridDim.x][PS_GROW] block rows of the cross-gene sums
+  double *xtot;                     // [2 parities][PS_GROW] multi-GPU: the exchanged totals, published by CTA 0
+  uint32_t *xflag;                  // [1] multi-GPU: iterations whose totals CTA 0 has published
   long long timeout;                // SM cycles any intra-GPU wait may last before the kernel traps
   long long *trace;                 // optional [32 iterations][8] clock64 stamps of CTA 0, then [32 chunks][8] of the pass of iteration 8 (diagnostics)
 };
@@ -138,7 +141,8 @@ k_advi_persist(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ 
   if (nmy > 0) item_geom(0, tile0, split0, cb0, n0_);
   const int r_lo0 = split0 * p.gs;
   const int r_hi0 = (r_lo0 + p.gs < BVG_GENE_TILE) ? r_lo0 + p.gs : BVG_GENE_TILE;
-  const int nslot0 = nmy > 0 ? ((r_hi0 - r_lo0) < PS_NPRE ? (r_hi0 - r_lo0) : PS_NPRE) : 0;
+  // (with nsplit * gs > 128 the last splits of a tile own no genes: r_lo0 >= r_hi0)
+  const int nslot0 = (nmy > 0 && r_hi0 > r_lo0) ? ((r_hi0 - r_lo0) < PS_NPRE ? (r_hi0 - r_lo0) : PS_NPRE) : 0;
   // normals of draw `t` for the ahead slots and (buffer sb) for the gene-shared parameters; nl = this thread's index among
   // the nthr threads doing it
   auto draw_normals = [&](uint32_t t, int sb, int nl, int nthr) {
@@ -433,27 +437,26 @@ k_advi_persist(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ 
       for (int q = 0; q < 4; ++q) wpre[q] = __ldcg(pw + q);
       wAg = __ldcg(a.W + g * TC_KW + k + 1);
     }
-    {
+    const bool reducer = m.peer.world <= 1 || cta == 0 || p.xchg_all;  // multi-GPU: only CTA 0 needs the local sums (it exchanges and publishes the totals)
+    if (reducer) {
       // 6 groups of 64 threads: group q sums rows q, q + 6, ... (all loads of a thread in flight at once), then a fixed
       // six-term sum per column
       const int c = tid & 63, grp = tid >> 6;
       double acc = 0;
       if (c < NS) {
-        for (int b0 = grp; b0 < ncta; b0 += 6 * 13) {
-          double v[13];
+        double v[25];   // ncta <= 148: at most 25 rows per group, all in flight at once
 #pragma unroll
-          for (int q = 0; q < 13; ++q) {
-            const int b = b0 + 6 * q;
-            v[q] = __ldcg(grow + (size_t)(b < ncta ? b : cta) * PS_GROW + c);
-          }
-#pragma unroll
-          for (int q = 0; q < 13; ++q) acc += b0 + 6 * q < ncta ? v[q] : 0.0;
+        for (int q = 0; q < 25; ++q) {
+          const int b = grp + 6 * q;
+          v[q] = __ldcg(grow + (size_t)(b < ncta ? b : cta) * PS_GROW + c);
         }
+#pragma unroll
+        for (int q = 0; q < 25; ++q) acc += grp + 6 * q < ncta ? v[q] : 0.0;
         SC->wrow[grp][c] = acc;
       }
     }
     __syncthreads();
-    if (tid < NS) {
+    if (reducer && tid < NS) {
       double t = 0;
 #pragma unroll
       for (int q = 0; q < 6; ++q) t += SC->wrow[q][tid];
@@ -462,36 +465,48 @@ k_advi_persist(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ 
     }
     __syncthreads();
     if (m.peer.world > 1) {
-      // multi-GPU: the local sums of every gene shard meet here (bvg_internal.cuh: 8-byte cells {32 data bits, sequence number})
-      const PeerCtx &pc = m.peer;
-      ++xseq;
-      const size_t per_rank = 2 * BVG_PEER_CAP, slot = (size_t)(xseq & 1u) * pc.world * per_rank;
-      if (cta == 0) {
-        for (int q = tid; q < 2 * NS; q += TC_THREADS) {
-          const double v = S.tot[q >> 1];
-          const uint32_t hv = (q & 1) ? (uint32_t)__double2hiint(v) : (uint32_t)__double2loint(v);
-          for (int r = 0; r < pc.world; ++r) {
-            if (r == pc.rank) continue;
-            uint2 *dst = pc.cells[r] + slot + (size_t)pc.rank * per_rank + q;
+      // multi-GPU: the local sums of every gene shard meet here (bvg_internal.cuh: 8-byte cells {32 data bits, sequence
+      // number}).  ONE CTA talks to the peers: it pushes this rank's sums, polls the local exchange buffer, sums in rank
+      // order (bit-identical totals on every rank) and publishes them to the other CTAs behind a flag.  (All 144 CTAs polling
+      // the 700 cells themselves cost ~10 us per evaluation at 8 GPUs: the polling storm sat on the very L2 lines the
+      // NVLink writes had to land in.)
+      double *const xt = p.xtot + (size_t)(i & 1) * PS_GROW;
+      if (cta == 0 || p.xchg_all) {
+        const PeerCtx &pc = m.peer;
+        ++xseq;
+        const size_t per_rank = 2 * BVG_PEER_CAP, slot = (size_t)(xseq & 1u) * pc.world * per_rank;
+        if (cta == 0) {
+          // one thread per (peer, cell): all remote stores of the exchange leave in one instruction per thread
+          for (int q = tid; q < 2 * NS * (pc.world - 1); q += TC_THREADS) {
+            const int ri = q / (2 * NS), cq = q - ri * 2 * NS, r = ri < pc.rank ? ri : ri + 1;
+            const double v = S.tot[cq >> 1];
+            const uint32_t hv = (cq & 1) ? (uint32_t)__double2hiint(v) : (uint32_t)__double2loint(v);
+            uint2 *dst = pc.cells[r] + slot + (size_t)pc.rank * per_rank + cq;
             asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(hv), "r"(xseq) : "memory");
           }
         }
+        double *scratch = &SC->wrow[0][0];  // (world - 1) * NS <= 7 * 56 doubles
+        const uint2 *mine = pc.cells[pc.rank] + slot;
+        const long long t0 = clock64();
+        for (int t = tid; t < NS * (pc.world - 1); t += TC_THREADS) {
+          const int ri = t / NS, cc = t - ri * NS, r = ri < pc.rank ? ri : ri + 1;
+          scratch[t] = peer_dead ? __longlong_as_double(0x7ff8000000000000LL) : peer_poll(pc, mine + (size_t)r * per_rank + 2 * cc, xseq, t0);
+        }
+        __syncthreads();
+        double sx = 0;
+        if (tid < NS)
+          for (int r = 0; r < pc.world; ++r) sx += r == pc.rank ? S.tot[tid] : scratch[(r < pc.rank ? r : r - 1) * NS + tid];  // rank order
+        if (!peer_dead && *(volatile uint32_t *)pc.fail) peer_dead = true;  // a peer never arrived: stop polling, finish with NaN
+        __syncthreads();
+        if (tid < NS) { S.tot[tid] = sx; if (!p.xchg_all) xt[tid] = sx; }
+        __syncthreads();
+        if (tid == 0 && !p.xchg_all) red_release_add(p.xflag, 1u);
+      } else {
+        if (tid == 0) wait_counter(p.xflag, (uint32_t)(i + 1), p.timeout);
+        __syncthreads();
+        if (tid < NS) S.tot[tid] = __ldcg(xt + tid);
+        __syncthreads();
       }
-      double *scratch = &SC->wrow[0][0];  // (world - 1) * NS <= 7 * 56 doubles
-      const uint2 *mine = pc.cells[pc.rank] + slot;
-      const long long t0 = clock64();
-      for (int t = tid; t < NS * (pc.world - 1); t += TC_THREADS) {
-        const int ri = t / NS, cc = t - ri * NS, r = ri < pc.rank ? ri : ri + 1;
-        scratch[t] = peer_dead ? __longlong_as_double(0x7ff8000000000000LL) : peer_poll(pc, mine + (size_t)r * per_rank + 2 * cc, xseq, t0);
-      }
-      __syncthreads();
-      double s = 0;
-      if (tid < NS)
-        for (int r = 0; r < pc.world; ++r) s += r == pc.rank ? S.tot[tid] : scratch[(r < pc.rank ? r : r - 1) * NS + tid];  // rank order
-      if (!peer_dead && *(volatile uint32_t *)pc.fail) peer_dead = true;  // a peer never arrived: stop polling, finish with NaN
-      __syncthreads();
-      if (tid < NS) S.tot[tid] = s;
-      __syncthreads();
     }
     if (tr && i < 32) p.trace[i * 16 + 4] = clock64();
     // warps 2, 11: gradient and mean-field update of the 2k+5 gene-shared parameters (finish_body of k_model.cu, jacobian on);
@@ -567,12 +582,191 @@ k_advi_persist(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------------------------------------
+// k_elbo_persist: all S forward-only draws of ONE ELBO estimate (stan::variational::advi::calc_ELBO [U]: the mean of
+// log_prob<propto = false, jacobian = true> over S draws of q) in one cooperative launch -- SURVEY.md 2.1's "K5".
+// The draws do not depend on each other, so there is NO barrier between them: a CTA streams its (gene tile, spot range)
+// item(s) through the forward-only pass once per draw -- rings, barriers and TMEM keep turning -- and leaves one row of
+// partial sums per draw; the only grid-wide synchronisation is the one at the end, after which one warp per draw adds the
+// rows in a fixed order and forms the draw's log density.  The draws themselves (zeta, exponentials, fp32 rows W / U of all
+// S draws) come from ONE batched k_prep launch.  While the epilogue warps work, the otherwise idle backward-MMA warp adds
+// the prior terms of the CTA's own genes, and (nb) the basis producer's idle lanes the lgamma terms of their distinct counts.
+struct ElboArgs {
+  TcArgs a;
+  DevModel m;                 // zeta / shx / Aexp / W / U point at slice 0 of the batch buffers
+  int S, nitems, nsplit, gs;
+  int loc, rank_id;           // gene-sharded: local share of every draw (the host all-reduces the S values)
+  int pre_y, pre_b;
+  uint32_t *grid_cnt;         // [1], zeroed before the launch
+  double *erows;              // [S][gridDim.x][8]: SSE | sum L | sum z^2 | sum u | sum (u - mu_amplitude)^2 | lgamma terms | - | -
+  double *lps;                // [S] out
+  long long timeout;
+};
+
+template <int LIK>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_elbo_persist(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmF1,
+               const __grid_constant__ CUtensorMap tmF2, const __grid_constant__ CUtensorMap tmT1,
+               const __grid_constant__ CUtensorMap tmT2, const __grid_constant__ ElboArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ double s_wsum[2][8][2];   // [draw parity][epilogue warp][SSE | L]
+  __shared__ double s_tot[PS_NW][PS_ROW];
+  const TcArgs &a = p.a;
+  const DevModel &m = p.m;
+  TcCtx x = tc_ctx_make(smem_raw, p.timeout);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int cta = blockIdx.x, ncta = gridDim.x;
+  const int k = m.k;
+  const bool dep = m.depth != 0;
+  const Layout &L = m.L;
+  const int64_t D = L.D;
+  tc_setup_cta(x);
+  const int nmy = cta < p.nitems ? (p.nitems - cta + ncta - 1) / ncta : 0;
+  auto item_geom = [&](int j, int &tile, int &split, int &c_begin, int &n) {
+    const int id = cta + j * ncta;
+    tile = id / p.nsplit;
+    split = id - tile * p.nsplit;
+    c_begin = split * a.cps;
+    n = a.nchunks - c_begin;
+    n = n < a.cps ? n : a.cps;
+    if (n < 0) n = 0;
+  };
+  uint32_t q0 = 0, pass = 0;
+  int preY = 0, preB = 0;
+  for (int s = 0; s < p.S; ++s) {
+    const double *zt = m.zeta + (size_t)s * D, *shx = m.shx + (size_t)s * (4 + k);
+    const float *Ws = m.W + (size_t)s * m.Gpad * 32, *Us = m.U + (size_t)s * 96;
+    double *erow = p.erows + ((size_t)s * ncta + cta) * 8;
+    double t0 = 0.0, t1 = 0.0;                 // epilogue threads: this draw's sums over the CTA's items
+    double aZ2 = 0, aU = 0, aDU2 = 0;          // warp 2: prior terms of the CTA's own genes
+    double hlg = 0.0;
+    for (int j = 0; j < nmy; ++j) {
+      int tile, split, c_begin, n;
+      item_geom(j, tile, split, c_begin, n);
+      const bool has_next = j + 1 < nmy || s + 1 < p.S;
+      int ntile = 0, nsplit_ = 0, nc_begin = 0, nn = 0;
+      if (has_next) item_geom(j + 1 < nmy ? j + 1 : 0, ntile, nsplit_, nc_begin, nn);
+      if (warp == TC_WARP_Y) {
+        const int pre = has_next ? (nn < p.pre_y ? nn : p.pre_y) : 0;
+        if (lane == 0) {
+          tc_role_produce_y(x, &tmY, tile, a.nch32, c_begin, preY, n, q0);
+          tc_role_produce_y(x, &tmY, ntile, a.nch32, nc_begin, 0, pre, q0 + (uint32_t)n);
+        }
+        preY = pre;
+        __syncwarp();
+      } else if (warp == TC_WARP_BASIS) {
+        const int pre = has_next ? (nn < p.pre_b ? nn : p.pre_b) : 0;
+        if (lane == 0) {
+          tc_role_produce_basis<false>(x, &tmF1, &tmF2, &tmT1, &tmT2, c_begin, preB, n, q0);
+          tc_role_produce_basis<false>(x, &tmF1, &tmF2, &tmT1, &tmT2, nc_begin, 0, pre, q0 + (uint32_t)n);
+        }
+        preB = pre;
+        double lg = 0.0;
+        if (LIK == BVG_NB && j == 0 && lane > 0) {
+          const double phi = shx[2], lg0 = lgamma(phi);
+          for (int e = cta * 31 + lane - 1; e < a.nhist; e += ncta * 31) lg += a.hist_cnt[e] * (lgamma(a.hist_val[e] + phi) - lg0);
+        }
+        __syncwarp();
+        if (LIK == BVG_NB && j == 0) hlg = warp_sum(lg);
+      } else if (warp == TC_WARP_MMA1) {
+        tc_role_mma1<false>(x, n, a.nk1, q0, pass, nullptr);
+      } else if (warp == TC_WARP_MMA2) {
+        // no backward MMA in a forward-only pass: this warp adds the prior terms of the genes this CTA owns
+        const int r_lo = split * p.gs, r_hi = (r_lo + p.gs < BVG_GENE_TILE) ? r_lo + p.gs : BVG_GENE_TILE;
+        const double ma = zt[L.mu_amp];
+        for (int rr = r_lo; rr < r_hi; ++rr) {
+          const int64_t g = (int64_t)tile * BVG_GENE_TILE + rr;
+          if (g >= m.G) break;
+          const double zj = lane < k ? zt[L.z_alpha + g * k + lane] : 0.0;
+          const double zb = dep ? 0.0 : zt[L.z_beta0 + g], u = zt[L.amp + g];
+          const double z2 = warp_sum(zj * zj) + (dep ? 0.0 : zb * zb);
+          const double du = u - ma;
+          aZ2 += z2; aU += u; aDU2 += du * du;
+        }
+      } else {
+        const int e = warp - TC_WARP_EPI0, qd = warp & 3, h = e >> 2;
+        const int r = 32 * qd + lane;
+        const uint32_t trow = x.tmem + ((uint32_t)(32 * qd) << 16);
+        const int64_t g = (int64_t)tile * BVG_GENE_TILE + r;
+        {
+          float cv[16];
+          const float4 *pw = reinterpret_cast<const float4 *>(Ws + g * TC_KW + 16 * h);
+          const float4 *pm = reinterpret_cast<const float4 *>(Us + 16 * h), *ps = reinterpret_cast<const float4 *>(Us + 32 + 16 * h);
+          const float Ag = __ldg(Ws + g * TC_KW + k + 1), mb = __ldg(Us + 64), sb = __ldg(Us + 65);
+          float w[16], um[16], us[16];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 xx = __ldg(pw + i), y = __ldg(pm + i), z = __ldg(ps + i);
+            w[4 * i] = xx.x; w[4 * i + 1] = xx.y; w[4 * i + 2] = xx.z; w[4 * i + 3] = xx.w;
+            um[4 * i] = y.x; um[4 * i + 1] = y.y; um[4 * i + 2] = y.z; um[4 * i + 3] = y.w;
+            us[4 * i] = z.x; us[4 * i + 1] = z.y; us[4 * i + 2] = z.z; us[4 * i + 3] = z.w;
+          }
+          tc_epi_form_coeff(k, h, g < a.G, Ag, mb, sb, w, um, us, cv);
+          tc_epi_store_coeff(x, trow, h, cv);
+        }
+        double sum0 = 0.0, sum1 = 0.0;
+        float lt = 0.f, phi = 0.f;
+        if (LIK == BVG_NB) { lt = (float)zt[L.tail]; phi = __expf(lt); }
+        tc_role_epilogue<LIK, false>(x, trow, r, h, c_begin, n, q0, a.M, lt, phi, sum0, sum1, nullptr);
+        if (g < a.G) { t0 += sum0; t1 += sum1; }
+      }
+      q0 += (uint32_t)n;
+      ++pass;
+    }
+    // ---- this CTA's row of the draw (no CTA-wide barrier: only the eight epilogue warps meet) ----
+    if (warp >= TC_WARP_EPI0 && warp < TC_WARP_EPI0 + 8) {
+      const int e = warp - TC_WARP_EPI0;
+      t0 = warp_sum(t0);
+      if (LIK == BVG_NB) t1 = warp_sum(t1);
+      if (lane == 0) { s_wsum[s & 1][e][0] = t0; s_wsum[s & 1][e][1] = t1; }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (e == 0 && lane == 0) {
+        double b0 = 0, b1 = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { b0 += s_wsum[s & 1][w][0]; b1 += s_wsum[s & 1][w][1]; }
+        erow[0] = b0; erow[1] = b1;
+      }
+    } else if (warp == TC_WARP_MMA2) {
+      if (lane == 0) { erow[2] = aZ2; erow[3] = aU; erow[4] = aDU2; erow[6] = 0.0; erow[7] = 0.0; }
+    } else if (warp == TC_WARP_BASIS) {
+      if (lane == 0) erow[5] = hlg;
+    }
+  }
+  // ---- the one grid-wide meeting, then one warp per draw: rows -> sums -> log density ----
+  __syncthreads();
+  if (tid == 0) {
+    red_release_add(p.grid_cnt, 1u);
+    wait_counter(p.grid_cnt, (uint32_t)ncta, p.timeout);
+  }
+  __syncthreads();
+  for (int s = cta * PS_NW + warp; s < p.S; s += ncta * PS_NW) {
+    const int c = lane & 7, rg = lane >> 3;   // 8 columns x 4 row groups
+    double acc = 0;
+    for (int b = rg; b < ncta; b += 4) acc += __ldcg(p.erows + ((size_t)s * ncta + b) * 8 + c);
+    const double a1 = __shfl_sync(0xffffffffu, acc, c + 8), a2 = __shfl_sync(0xffffffffu, acc, c + 16), a3 = __shfl_sync(0xffffffffu, acc, c + 24);
+    acc = ((acc + a1) + a2) + a3;   // fixed order
+    double *tot = s_tot[warp];
+    if (lane < 8) {
+      const int slot = lane == 0 ? S_SSE : lane == 1 ? S_L : lane == 2 ? S_Z2 : lane == 3 ? S_U : lane == 4 ? S_DU2 : lane == 5 ? S_LG : -1;
+      if (slot >= 0) tot[slot] = (LIK == BVG_NB && slot == S_LG) ? acc - m.lgam_y1 : acc;
+    }
+    __syncwarp();
+    const double lp = bvg_lp_from_sums(m, tot, m.zeta + (size_t)s * D, m.shx + (size_t)s * (4 + k), 1, 0, p.loc != 0,
+                                       (p.loc && p.rank_id != 0) ? 0.0 : 1.0, lane);
+    if (lane == 0) p.lps[s] = lp;
+    __syncwarp();
+  }
+  tc_teardown_cta(x);
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 struct PersistBuf {
-  uint32_t *cnt;    // [ntiles + 1]
-  double *rows;     // [2][ncta][PS_GROW]
+  uint32_t *cnt;    // [ntiles] tile counters, grid counter, exchange flag
+  double *rows;     // [2][ncta][PS_GROW] block rows, then [2][PS_GROW] exchanged totals
   long long *trace; // [32][8]
+  double *erows;    // ELBO mode: [S][ncta][8]
+  int erows_cap;
   int ntiles, ncta;
   bool attr_set;
 };
@@ -586,6 +780,7 @@ void persist_destroy(bvg_fit *f) {
   cudaFree(b->cnt);
   cudaFree(b->rows);
   cudaFree(b->trace);
+  cudaFree(b->erows);
   delete b;
   t->persist = nullptr;
 }
@@ -615,17 +810,20 @@ int launch_advi_persist(bvg_fit *f, int n_iter) {
     memset(b, 0, sizeof(*b));
     t->persist = b;
     b->ntiles = ntiles; b->ncta = ncta;
-    CUDA_TRY(cudaMalloc(&b->cnt, sizeof(uint32_t) * (ntiles + 1)));
-    CUDA_TRY(cudaMalloc(&b->rows, sizeof(double) * 2 * ncta * PS_GROW));
+    CUDA_TRY(cudaMalloc(&b->cnt, sizeof(uint32_t) * (ntiles + 2)));
+    CUDA_TRY(cudaMalloc(&b->rows, sizeof(double) * 2 * (ncta + 1) * PS_GROW));
     CUDA_TRY(cudaMalloc(&b->trace, sizeof(long long) * (32 * 16 + 32 * 8 + 32 * 4)));
     CUDA_TRY(cudaFuncSetAttribute(k_advi_persist<BVG_GAUSSIAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
     CUDA_TRY(cudaFuncSetAttribute(k_advi_persist<BVG_NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(k_elbo_persist<BVG_GAUSSIAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(k_elbo_persist<BVG_NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    b->attr_set = true;
     int occ = 0;
     if (m.lik == BVG_GAUSSIAN) CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_advi_persist<BVG_GAUSSIAN>, TC_THREADS, TC_SMEM_BYTES));
     else CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_advi_persist<BVG_NB>, TC_THREADS, TC_SMEM_BYTES));
     if (occ < 1) { bvg_set_error("persistent ADVI kernel does not fit an SM"); return BVG_ERR_STATE; }
   }
-  CUDA_TRY(cudaMemsetAsync(b->cnt, 0, sizeof(uint32_t) * (ntiles + 1), f->stream));
+  CUDA_TRY(cudaMemsetAsync(b->cnt, 0, sizeof(uint32_t) * (ntiles + 2), f->stream));
   PersistArgs p;
   memset(&p, 0, sizeof(p));
   TcArgs &a = p.a;
@@ -644,8 +842,11 @@ int launch_advi_persist(bvg_fit *f, int n_iter) {
   p.gs = (BVG_GENE_TILE + m.nsplit - 1) / m.nsplit;
   p.pre_y = TC_NY; p.pre_b = TC_NB - 1;
   if (const char *e = getenv("BVG_PERSIST_PRE")) { int y = 0, bb = 0; if (sscanf(e, "%d,%d", &y, &bb) == 2) { p.pre_y = std::max(0, std::min(y, TC_NY)); p.pre_b = std::max(0, std::min(bb, TC_NB - 1)); } }
+  { const char *e = getenv("BVG_XCHG_ALL"); p.xchg_all = !(e && e[0] == '0'); }   // measured at 8 GPUs (profiles/README.md): every CTA polling is the faster form
   p.tile_cnt = b->cnt; p.grid_cnt = b->cnt + ntiles;
   p.rows = b->rows;
+  p.xtot = b->rows + (size_t)2 * ncta * PS_GROW;
+  p.xflag = b->cnt + ntiles + 1;
   p.timeout = 8000000000LL;  // ~4 s: longer than any legitimate wait inside one GPU
   if (m.peer.world > 1 && m.peer.timeout > p.timeout) p.timeout = 2 * m.peer.timeout;  // the rings idle while a peer is awaited
   p.trace = g_persist_trace ? b->trace : nullptr;
@@ -657,6 +858,74 @@ int launch_advi_persist(bvg_fit *f, int n_iter) {
   cfg.attrs = at; cfg.numAttrs = 1;
   if (m.lik == BVG_GAUSSIAN) CUDA_TRY(cudaLaunchKernelEx(&cfg, k_advi_persist<BVG_GAUSSIAN>, t->tmY, t->tmF1, t->tmF2, t->tmT1, t->tmT2, p));
   else CUDA_TRY(cudaLaunchKernelEx(&cfg, k_advi_persist<BVG_NB>, t->tmY, t->tmF1, t->tmF2, t->tmT1, t->tmT2, p));
+  f->st.kernel_launches++;
+  return BVG_OK;
+}
+
+// All S draws of an ELBO estimate in one cooperative launch.  The model descriptor's zeta / shx / Aexp / W / U must point at
+// slice 0 of the batch buffers filled by launch_prep_batch(PREP_ELBO, S); d_lps receives S log densities (local shares when
+// the fit is gene-sharded and m.elbo_local is set).
+int launch_elbo_persist(bvg_fit *f, int S, double *d_lps) {
+  const DevModel &m = f->m;
+  TcState *t = (TcState *)f->tc;
+  int nsm = 148, coop = 0;
+  CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, f->cfg.device));
+  CUDA_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, f->cfg.device));
+  if (!coop) { bvg_set_error("device does not support cooperative launches"); return BVG_ERR_STATE; }
+  const int ntiles = (int)(m.Gpad / BVG_GENE_TILE), nitems = ntiles * m.nsplit;
+  const int ncta = std::min(nitems, nsm);
+  PersistBuf *b = (PersistBuf *)t->persist;
+  if (b && (b->ntiles != ntiles || b->ncta != ncta)) { persist_destroy(f); b = nullptr; }
+  if (!b) {
+    b = new PersistBuf();
+    memset(b, 0, sizeof(*b));
+    t->persist = b;
+    b->ntiles = ntiles; b->ncta = ncta;
+    CUDA_TRY(cudaMalloc(&b->cnt, sizeof(uint32_t) * (ntiles + 2)));
+    CUDA_TRY(cudaMalloc(&b->rows, sizeof(double) * 2 * (ncta + 1) * PS_GROW));
+    CUDA_TRY(cudaMalloc(&b->trace, sizeof(long long) * (32 * 16 + 32 * 8 + 32 * 4)));
+  }
+  if (!b->attr_set) {
+    CUDA_TRY(cudaFuncSetAttribute(k_advi_persist<BVG_GAUSSIAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(k_advi_persist<BVG_NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(k_elbo_persist<BVG_GAUSSIAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(k_elbo_persist<BVG_NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    b->attr_set = true;
+  }
+  if (b->erows_cap < S) {
+    cudaFree(b->erows);
+    b->erows = nullptr; b->erows_cap = 0;
+    CUDA_TRY(cudaMalloc(&b->erows, sizeof(double) * (size_t)S * ncta * 8));
+    b->erows_cap = S;
+  }
+  CUDA_TRY(cudaMemsetAsync(b->cnt, 0, sizeof(uint32_t) * (ntiles + 2), f->stream));
+  ElboArgs p;
+  memset(&p, 0, sizeof(p));
+  TcArgs &a = p.a;
+  a.k = m.k;
+  a.hist_val = m.hist_val; a.hist_cnt = m.hist_cnt; a.nhist = m.nhist;
+  a.nk1 = (m.k + 1 + 15) / 16;
+  a.nch32 = (int)(f->ldY / 32);
+  a.M = m.M; a.G = m.G; a.Gpad = m.Gpad; a.KP = m.KP;
+  a.nchunks = (int)((m.M + TC_CHUNK - 1) / TC_CHUNK);
+  a.cps = (a.nchunks + m.nsplit - 1) / m.nsplit;
+  p.m = m;
+  p.S = S; p.nitems = nitems; p.nsplit = m.nsplit;
+  p.gs = (BVG_GENE_TILE + m.nsplit - 1) / m.nsplit;
+  p.loc = m.elbo_local; p.rank_id = m.rank_id;
+  p.pre_y = TC_NY; p.pre_b = TC_NB;
+  p.grid_cnt = b->cnt + ntiles;
+  p.erows = b->erows;
+  p.lps = d_lps;
+  p.timeout = 8000000000LL;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)ncta); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = TC_SMEM_BYTES; cfg.stream = f->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeCooperative;
+  at[0].val.cooperative = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  if (m.lik == BVG_GAUSSIAN) CUDA_TRY(cudaLaunchKernelEx(&cfg, k_elbo_persist<BVG_GAUSSIAN>, t->tmY, t->tmF1, t->tmF2, t->tmT1, t->tmT2, p));
+  else CUDA_TRY(cudaLaunchKernelEx(&cfg, k_elbo_persist<BVG_NB>, t->tmY, t->tmF1, t->tmF2, t->tmT1, t->tmT2, p));
   f->st.kernel_launches++;
   return BVG_OK;
 }

@@ -308,44 +308,8 @@ __device__ void finish_body(const DevModel &m, int mode, int jac, int propto, in
   const double j1 = jac ? 1.0 : 0.0;
   const int it = m.ctl->it;
   if (warp == (blockDim.x >> 5) - 1) {  // log density (last warp, concurrently with the gradient threads below)
-    double pa = 0;  // prior terms of mu_alpha, sigma_alpha + jacobian of sigma_alpha
-    for (int j = lane; j < k; j += 32) {
-      const double a = zt[L.mu_alpha + j], ls = zt[L.sigma_alpha + j], s = m.shx[3 + j];
-      pa += -a * a / 8.0 - 0.5 * s * s + j1 * ls;
-    }
-    pa = warp_sum(pa);
-    if (lane == 0) {
-      double lp, lsh;  // lp: terms carrying cross-gene sums or gene counts; lsh: gene-shared parameters only
-      if (m.lik == BVG_GAUSSIAN) { lp = -N * lt - 0.5 * tot[S_SSE] / (tl * tl); lsh = -0.5 * tl * tl; }
-      else { lp = tot[S_SSE] + tot[S_LG]; lsh = -log1p(tl * tl / 4.0); }
-      if (m.depth && m.lik == BVG_GAUSSIAN) lsh += 0.5 * tl * tl - tl * tl / 8.0;  // sigma_y ~ normal(0, 2) (approxGP2.stan:44)
-      lp += -0.5 * tot[S_Z2];
-      lsh += -mb * mb / 8.0 - (m.depth ? sb * sb / 8.0 : 0.5 * sb * sb) - ma * ma / 8.0 - 0.5 * sa * sa;
-      lp += -Gt * lsa - tot[S_U] - 0.5 * tot[S_DU2] / (sa * sa);
-      lsh += pa;
-      if (jac) { lp += tot[S_U]; lsh += (m.depth ? 0.0 : lsb) + lsa + lt; }
-      if (!propto) {
-        if (!m.depth) {
-          if (m.lik == BVG_GAUSSIAN) {
-            lp += -0.5 * BVG_LOG_TWO_PI * (N + (double)k * Gt + 2.0 * Gt);
-            lsh += -0.5 * BVG_LOG_TWO_PI * (2.0 * k + 5.0) - (k + 2.0) * BVG_LOG_TWO;
-          } else {
-            lp += -0.5 * BVG_LOG_TWO_PI * ((double)k * Gt + 2.0 * Gt);
-            lsh += -0.5 * BVG_LOG_TWO_PI * (2.0 * k + 4.0) - (k + 2.0) * BVG_LOG_TWO - BVG_LOG_PI;
-          }
-        } else {  // approxGP2/3: no z_beta0 terms; normal(0, 2) on beta0, beta1, mu_amplitude, mu_alpha[k] (and sigma_y)
-          if (m.lik == BVG_GAUSSIAN) {
-            lp += -0.5 * BVG_LOG_TWO_PI * (N + (double)k * Gt + Gt);
-            lsh += -0.5 * BVG_LOG_TWO_PI * (2.0 * k + 5.0) - (k + 4.0) * BVG_LOG_TWO;
-          } else {
-            lp += -0.5 * BVG_LOG_TWO_PI * ((double)k * Gt + Gt);
-            lsh += -0.5 * BVG_LOG_TWO_PI * (2.0 * k + 4.0) - (k + 3.0) * BVG_LOG_TWO - BVG_LOG_PI;
-          }
-        }
-      }
-      lp += shw * lsh;
-      s_lp = lp;
-    }
+    const double lp = bvg_lp_from_sums(m, tot, zt, m.shx, jac, propto, loc, shw, lane);
+    if (lane == 0) s_lp = lp;
   } else if (big && (mode == MODE_GRAD_OUT || mode == MODE_ADVI_UPDATE)) {
     const double es = m.ctl->es;
     for (int i = tid; i < 2 * k + 5; i += blockDim.x - 32) {  // every warp but the last (which forms the log density)

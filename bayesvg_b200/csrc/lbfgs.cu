@@ -109,7 +109,7 @@ int lbfgs_run(bvg_fit *f, const double *d_theta0, double *d_out, const LbfgsOpt 
   double *g0 = B + (size_t)(2 * mh) * D;  // the gradient row of the basis
   int rc = BVG_OK;
   double *h_scal = nullptr;  // pinned: [0] grad.p, [1] sum grad, [2] lp  -- one small D2H per evaluation
-  auto fail = [&](int code) { cudaFree(B); cudaFreeHost(h_scal); return code; };
+  auto fail = [&](int code) { shadow_leave(f); cudaFree(B); cudaFreeHost(h_scal); return code; };
   if (cudaMallocHost(&h_scal, 4 * sizeof(double)) != cudaSuccess) { bvg_set_error("cudaMallocHost failed"); return fail(BVG_ERR_CUDA); }
   if ((rc = vec_make_weights(st, w, m, f->cfg.rank)) != BVG_OK) return fail(rc);
   if (d_theta0) CUDA_TRY(cudaMemcpyAsync(x0, d_theta0, D * sizeof(double), cudaMemcpyDeviceToDevice, st));
@@ -143,7 +143,7 @@ int lbfgs_run(bvg_fit *f, const double *d_theta0, double *d_out, const LbfgsOpt 
   CUDA_TRY(cudaStreamSynchronize(st));
   double gg = h_scal[0];   // g.g
   double dfp = -gg;        // g.p for p = -g
-  int nh = 0, head = 0, it = 0, term = 0;
+  int nh = 0, head = 0, it = 0, term = 0, switch_iter = 0;
   double fk1 = 0, alpha = 1e-3, alphak1 = 0, dfp_prev = 0, gamma = 1;
   const double eps = DBL_EPSILON, tol_obj = 1e-12, tol_rel_obj = 1e4, tol_grad = 1e-8, tol_rel_grad = 1e7, tol_param = 1e-8;
   const int max_iter = opt && opt->max_iter > 0 ? opt->max_iter : f->cfg.mle_iter;
@@ -162,7 +162,25 @@ int lbfgs_run(bvg_fit *f, const double *d_theta0, double *d_out, const LbfgsOpt 
       else alpha = 1e-3;
       const int ls = wolfe(ev, &alpha, &f1, &dg1, fk, dfp);
       if (ls) {
-        if (resetB) { term = -1; break; }
+        if (resetB) {
+          // even steepest descent finds no acceptable step.  Fast precision: the search is comparing the evaluator's noise
+          // (fp64_shadow.cu) -- continue from this very point with fp64 evaluations, fresh curvature history
+          if (f->cfg.precision == BVG_PREC_FAST && !opt && !f->no_mle_fp64) {
+            if ((rc = shadow_enter(f)) != BVG_OK) return fail(rc);
+            switch_iter = it;
+            if (ev(0.0, &fk, &dg1)) { bvg_set_error("L-BFGS: log density is not finite where the fp64 evaluator takes over"); return fail(BVG_ERR_NUMERIC); }
+            if ((rc = vec_accept(st, nullptr, nullptr, x0, g0, m.zeta, m.grad, D)) != BVG_OK) return fail(rc);
+            if ((rc = vec_dot_sum(st, g0, g0, w, D, scal)) != BVG_OK) return fail(rc);
+            if (f->comm_mode && (rc = comm_allreduce(f, scal, 2)) != BVG_OK) return fail(rc);
+            CUDA_TRY(cudaMemcpyAsync(h_scal, scal, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            gg = h_scal[0];
+            resetB = 2;   // steepest descent from the re-evaluated point, initial step as after any failed search
+            continue;
+          }
+          term = -1;
+          break;
+        }
         resetB = 2;
         continue;
       }
@@ -239,6 +257,8 @@ int lbfgs_run(bvg_fit *f, const double *d_theta0, double *d_out, const LbfgsOpt 
   f->st.mle_iters = it;
   f->st.mle_fevals = fevals;
   f->st.mle_term = term;
+  f->st.mle_fp64_from = switch_iter;
+  shadow_leave(f);
   f->st.mle_lp = -fk;
   cudaFree(B);
   cudaFreeHost(h_scal);

@@ -14,6 +14,12 @@ N > 1 (torchrun, one rank per GPU): weak scaling -- every rank holds its own 3,0
 per-gene kernel over peer memory; --comm nccl: ncclAllReduce between kernels), and `value` counts
 3,000-gene evaluations (N per global evaluation).
 
+Every line also carries `strong_cfg4` (BASELINE.json configs[3], the split north_star names: 50,000 spots x 10,000 genes in
+total, gene-sharded over the N ranks -- STRONG scaling: value = evaluations of the whole problem per second, plus the wall of
+the whole default fit), so the driver's 1/2/4/8-GPU run records it next to the weak-scaling line; for N > 1 also
+`parity_check` (a gene-sharded problem against its unsharded twin on the same GPUs, before anything is timed).  At N = 1 the
+line further carries `cfg3_nb` (configs[2]), `fp64_engine`, and `cfg1_fit` (the stand-in for configs[0] with a bounded CPU leg).
+
 --impl reference times the reference's CPU path.  The reference is R + CmdStan, neither of which
 exists in this image, so that arm is the fp64 C restatement in oracle/ ("port") running
 the same evaluation with all host threads.
@@ -155,6 +161,205 @@ def run_reference(args, rank, world):
     }))
 
 
+def _max_over_ranks(x, world):
+    if world == 1:
+        return float(x)
+    import torch
+    import torch.distributed as td
+    t = torch.tensor([x], device="cuda", dtype=torch.float64)
+    td.all_reduce(t, op=td.ReduceOp.MAX)
+    return float(t.item())
+
+
+def parity_check(rank, world, local_rank, engine, comm):
+    """N > 1: a gene-sharded problem on the N ranks against its unsharded twin (every rank holds both): log density,
+    gradient, a 25-step ADVI trajectory through the persistent kernel's in-kernel exchange, and an ELBO estimate."""
+    import torch
+    import torch.distributed as td
+
+    import bayesvg_b200 as bvg
+    from bayesvg_b200 import dist as bdist
+    from bayesvg_b200 import synth
+    from bayesvg_b200.api import length_scale_kmeans
+    M, G, k, lik = 1500, 128 * world + 37, 20, "gaussian"
+    X = synth.scale_coords(synth.random_points(M, 7))
+    C = synth.det_kmeans(X, k, 312, iters=30)
+    phi = bvg.basis_build(X, C, length_scale_kmeans(C), "matern", 2.5, device=local_rank)
+    Y, _ = synth.expression(phi, G, lik, 99)
+    sh = bdist.Shard(rank, world)
+    g0, g1 = sh.gene_range(G)
+    idx = bdist.shard_index(lik, G, k, g0, g1)
+    cfg = dict(device=local_rank, seed=312)
+    fs = bdist.make_sharded_fit(phi, np.asfortranarray(Y[:, g0:g1]), sh, G, g0, lik, "fast", engine, cfg, comm)
+    ff = bvg.Fit(phi, Y, lik, "fast", engine, **cfg)
+    theta = np.random.default_rng(1).normal(0, 0.3, ff.D)
+    lp_s, g_s = fs.log_prob(theta[idx], True, False)
+    lp_f, g_f = ff.log_prob(theta, True, False)
+    e_lp = abs(lp_s - lp_f) / abs(lp_f)
+    e_g = float(np.linalg.norm(g_s - g_f[idx]) / np.linalg.norm(g_f[idx]))
+    for f, th in ((fs, theta[idx]), (ff, theta)):
+        f.set_variational(0.1 * th)
+        f.advi_steps(0, 0.1, reset=True)
+        f.advi_steps(25, 0.1)
+    mu_s, om_s = fs.get_variational()
+    mu_f, om_f = ff.get_variational()
+    e_t = float(max(np.linalg.norm(mu_s - mu_f[idx]) / np.linalg.norm(mu_f[idx]), np.linalg.norm(om_s - om_f[idx]) / np.linalg.norm(om_f[idx])))
+    el_s, el_f = fs.elbo(20)[0], ff.elbo(20)[0]
+    e_e = abs(el_s - el_f) / abs(el_f)
+    fs.close()
+    ff.close()
+    worst = torch.tensor([e_lp, e_g, e_t, e_e], device="cuda", dtype=torch.float64)
+    td.all_reduce(worst, op=td.ReduceOp.MAX)
+    e_lp, e_g, e_t, e_e = (float(v) for v in worst.tolist())
+    # fast path (BF16x3): the shards sum the same products in a different order; gates as tests/test_gpu_multi.py
+    return {"what": f"{M} spots x {G} genes, k={k}, gaussian, fast/{engine}, gene-sharded over {world} ranks vs unsharded on every rank",
+            "log_prob_rel": e_lp, "grad_rel": e_g, "advi_25_steps_rel": e_t, "elbo_rel": e_e,
+            "ok": bool(e_lp < 2e-5 and e_g < 2e-5 and e_t < 2e-2 and e_e < 2e-5)}
+
+
+def strong_cfg4(args, rank, world, local_rank, barrier):
+    """BASELINE.json configs[3]: 50,000 spots x 10,000 genes, Matern-1.5, the genes split over the ranks (strong scaling)."""
+    import bayesvg_b200 as bvg
+    from bayesvg_b200 import dist as bdist
+    g_lo, g_hi = bdist.Shard(rank, world).gene_range(CFG4_G)
+    t0 = time.perf_counter()
+    phi, Y = make_dataset(lambda X, C, ls: bvg.basis_build(X, C, ls, "matern", 1.5, device=local_rank), 312 + rank, "cfg4", g_hi - g_lo)
+    t_data = time.perf_counter() - t0
+    cfg = dict(device=local_rank, seed=312)
+
+    def make():
+        if world > 1:
+            return bdist.make_sharded_fit(phi, Y, bdist.Shard(rank, world), CFG4_G, g_lo, "gaussian", "fast", args.engine, cfg, args.comm)
+        return bvg.Fit(phi, Y, "gaussian", "fast", args.engine, **cfg)
+
+    fit = make()
+    E = args.evals_per_step
+    fit.set_variational(np.zeros(fit.D), None)
+    fit.advi_steps(0, 0.1, reset=True)
+    for _ in range(3):
+        fit.advi_steps(E, 0.1)
+    steps = max(2, min(args.steps, 5))
+    barrier()
+    ms = 0.0
+    for _ in range(steps):
+        ms += fit.advi_steps(E, 0.1)   # Y of a shard (>= 250 MB) exceeds L2: every evaluation streams it from HBM
+    barrier()
+    ms = _max_over_ranks(ms, world)
+    ms_lik = fit.time_lik_kernel(10, False, True)
+    fit.close()
+    barrier()
+    t0 = time.perf_counter()
+    f3 = make()
+    f3.run()
+    barrier()
+    wall = _max_over_ranks(time.perf_counter() - t0, world)
+    s3 = f3.stats()
+    f3.close()
+    peak, _ = load_peaks()
+    Gl = g_hi - g_lo
+    bl = 4 * CFG4_M * Gl + 4 * CFG4_M * K_BASIS + 8 * K_BASIS * Gl
+    return {"workload": "cfg4: 50,000 spots x 10,000 genes in total, k=20 Matern-1.5, gaussian, meanfield ADVI; genes split over the ranks",
+            "scaling": "strong", "value": steps * E / (ms * 1e-3), "unit": "evals/s (whole 10,000-gene problem)", "n_gpus": world,
+            "us_per_eval": 1e3 * ms / (steps * E), "steps": steps, "evals_per_step": E, "genes_per_gpu": Gl,
+            "likelihood_kernel_us": 1e3 * ms_lik, "likelihood_kernel_hbm_frac": bl / (ms_lik * 1e-3) / 1e9 / peak,
+            "fit": {"wall_s": wall, "grad_evals": s3["grad_evals"], "elbo_evals": s3["elbo_evals"], "advi_iters": s3["advi_iters"],
+                    "mle_iters": s3["mle_iters"], "mle_term": s3["mle_term"], "sec_mle": s3["sec_mle"], "sec_adapt": s3["sec_adapt"],
+                    "sec_sga": s3["sec_sga"], "sec_draws": s3["sec_draws"], "converged": s3["converged"], "elbo": s3["elbo"]},
+            "synthetic_data_seconds": t_data}
+
+
+def extra_blocks_n1(args, local_rank, phi_cfg2, Y_cfg2):
+    """N = 1 only: BASELINE configs[2] (nb, exp_quad), the fp64 engine on configs[1], and the configs[0] stand-in fit with a
+    bounded CPU leg, so that those numbers are in the driver's record and not only in profiles/."""
+    import bayesvg_b200 as bvg
+    from bayesvg_b200 import synth
+    from bayesvg_b200.api import kmeans_centers, length_scale_kmeans
+    peak, _ = load_peaks()
+    cfg = dict(device=local_rank, seed=312)
+    out = {}
+    # ---- cfg3: counts, nb likelihood, exp_quad kernel
+    X = synth.scale_coords(synth.visium_grid())
+    C = synth.det_kmeans(X, K_BASIS, 312)
+    phi3 = bvg.basis_build(X, C, length_scale_kmeans(C), "exp_quad", 0.0, device=local_rank)
+    Y3, _ = synth.expression(phi3, G_GENES, "nb", 312)
+    Y3 = np.asfortranarray(Y3.astype(np.int32))
+    f = bvg.Fit(phi3, Y3, "nb", "fast", args.engine, **cfg)
+    f.set_variational(np.zeros(f.D), None)
+    f.advi_steps(0, 0.1, reset=True)
+    for _ in range(3):
+        f.advi_steps(100, 0.1)
+    ms = sum(f.advi_steps(100, 0.1) for _ in range(5))
+    ms_c, ms_w = f.time_lik_kernel(20, True, True), f.time_lik_kernel(50, False, True)
+    bl = 4 * M_SPOTS * G_GENES + 4 * M_SPOTS * K_BASIS + 8 * K_BASIS * G_GENES
+    t0 = time.perf_counter()
+    f.close()
+    f = bvg.Fit(phi3, Y3, "nb", "fast", args.engine, **cfg)
+    f.run()
+    s = f.stats()
+    out["cfg3_nb"] = {"workload": "cfg3: 4,992 spots x 3,000 genes, k=20 exp_quad, negative-binomial counts, meanfield ADVI",
+                      "value": 500 / (ms * 1e-3), "unit": "evals/s", "us_per_eval": 2.0 * ms,
+                      "likelihood_kernel_us_cold_l2": 1e3 * ms_c, "likelihood_kernel_us_l2_resident": 1e3 * ms_w,
+                      "roofline_frac_cold": bl / (ms_c * 1e-3) / 1e9 / peak,
+                      "fit": {"wall_s": time.perf_counter() - t0, "advi_iters": s["advi_iters"], "mle_iters": s["mle_iters"], "mle_term": s["mle_term"],
+                              "mle_fp64_from": s["mle_fp64_from"], "sec_mle": s["sec_mle"], "sec_adapt": s["sec_adapt"], "sec_sga": s["sec_sga"], "converged": s["converged"], "elbo": s["elbo"]}}
+    f.close()
+    # ---- fp64 engine on cfg2 (north_star's <= 1e-6 path)
+    f = bvg.Fit(phi_cfg2, Y_cfg2, "gaussian", "fp64", "simt", **cfg)
+    f.set_variational(np.zeros(f.D), None)
+    f.advi_steps(0, 0.1, reset=True)
+    f.advi_steps(20, 0.1)
+    ms = sum(f.advi_steps(50, 0.1) for _ in range(2))
+    f.close()
+    out["fp64_engine"] = {"workload": "cfg2, precision = fp64 (SIMT engine, fp64 FMA: the tcgen05 path has no fp64 kind)",
+                          "value": 100 / (ms * 1e-3), "unit": "evals/s", "us_per_eval": 10.0 * ms}
+    # ---- cfg1 stand-in (seu_brain: 2,444 in-tissue spots x 3,000 HVGs): coordinates -> k-means -> basis -> whole default fit
+    X1 = synth.scale_coords(synth.masked_blob(synth.visium_grid(), 2444))
+    t0 = time.perf_counter()
+    C1 = kmeans_centers(X1, K_BASIS, 100, 10, rng=312, device=local_rank)
+    phi1 = bvg.basis_build(X1, C1, length_scale_kmeans(C1), "matern", 2.5, device=local_rank)
+    t_basis = time.perf_counter() - t0
+    Y1, amp1 = synth.expression(phi1, G_GENES, "gaussian", 312)
+    t0 = time.perf_counter()
+    f = bvg.Fit(phi1, Y1, "gaussian", "fast", args.engine, **cfg)
+    tab = f.run()
+    wall = time.perf_counter() - t0 + t_basis
+    s = f.stats()
+    f.close()
+    blk = {"workload": "stand-in for cfg1 (seu_brain): 2,444 spots x 3,000 genes, k=20 Matern-2.5, gaussian; k-means + basis build + L-BFGS + ADVI + draws",
+           "gpu": {"wall_s": wall, "sec_kmeans_basis": t_basis, "sec_h2d": s["sec_h2d"], "sec_mle": s["sec_mle"], "sec_adapt": s["sec_adapt"], "sec_sga": s["sec_sga"],
+                   "sec_draws": s["sec_draws"], "advi_iters": s["advi_iters"], "mle_iters": s["mle_iters"], "elbo": s["elbo"], "converged": s["converged"]}}
+    if not args.skip_cpu:
+        # bounded CPU leg: the SAME pipeline of the fp64 C restatement (all host threads) on the first `gs` genes
+        from scipy.stats import spearmanr
+
+        from oracle import oracle as orc
+        gs = args.cpu_fit_genes
+        nthreads = os.cpu_count() or 1
+        t0 = time.perf_counter()
+        o = orc.Oracle(phi1, np.asfortranarray(Y1[:, :gs]), "gaussian", nthreads=nthreads)
+        th, _ = o.lbfgs(max_iter=1000)
+        mu, om, info = o.advi(th, iter=3000, elbo_samples=150, seed=312)
+        ref = o.summary(mu, om, 1000, 312)
+        cw = time.perf_counter() - t0
+        f = bvg.Fit(phi1, np.asfortranarray(Y1[:, :gs]), "gaussian", "fast", args.engine, **cfg)
+        t0 = time.perf_counter()
+        tg = f.run()
+        gw = time.perf_counter() - t0
+        f.close()
+        top = gs // 3
+        blk["cpu_port_sample"] = {"genes": gs, "wall_s": cw, "threads": nthreads, "advi_iters": info["iters"], "eta": info["eta"],
+                                  "gpu_wall_s_same_sample": gw,
+                                  "spearman_amplitude_mean": float(spearmanr(tg[:, 0], ref[:, 0]).correlation),
+                                  "top_third_overlap": len(set(np.argsort(-tg[:, 0])[:top]) & set(np.argsort(-ref[:, 0])[:top])) / top,
+                                  "full_problem_extrapolated_wall_s": cw * G_GENES / gs,
+                                  "note": "the CPU port's cost per iteration is linear in the gene count; the full 3,000-gene CPU fit was measured once at "
+                                          "68.9 s on 16 threads (profiles/r1_fit_agreement_cfg1.json)"}
+        blk["speedup_vs_cpu_port_extrapolated"] = blk["cpu_port_sample"]["full_problem_extrapolated_wall_s"] / wall
+    blk["spearman_vs_planted_amplitude"] = float(__import__("scipy.stats", fromlist=["spearmanr"]).spearmanr(tab[:, 0], amp1).correlation)
+    out["cfg1_fit"] = blk
+    return out
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
 
@@ -167,6 +372,11 @@ def run_ours(args, rank, world, local_rank):
         if os.environ.get("NCCL_DEBUG", "VERSION") == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner out of stdout: rank 0 prints ONE JSON line
         td.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    parity = None
+    if world > 1 and not args.skip_parity:
+        parity = parity_check(rank, world, local_rank, args.engine, args.comm)
+        if not parity["ok"]:
+            raise SystemExit(f"parity check failed: {parity}")
     cfg4 = args.workload == "cfg4"
     if cfg4:   # strong scaling: this rank's contiguous share of the 10,000 genes
         g_lo, g_hi = bdist.Shard(rank, world).gene_range(CFG4_G)
@@ -203,6 +413,8 @@ def run_ours(args, rank, world, local_rank):
     for _ in range(args.steps):
         if not args.no_flush:
             fit.flush_l2()
+            if world > 1:
+                barrier()   # the flush is a measurement device, not work: without this the first exchange of a step also times the other ranks' flushes
         ms_total += fit.advi_steps(E, 0.1)  # CUDA events on the engine's stream
     barrier()
     sampler.stop_flag = True
@@ -231,7 +443,8 @@ def run_ours(args, rank, world, local_rank):
         traffic = json.load(open(tpath)).get(eng_name)
     roofline = {"bound": "hbm", "kernel": f"k_lik_{eng_name} (forward+backward, cold L2)",
                 "achieved": bytes_launch / (ms_cold * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                "frac": bytes_launch / (ms_cold * 1e-3) / 1e9 / peak, "traffic": traffic, "peak_source": peak_src,
+                "frac": bytes_launch / (ms_cold * 1e-3) / 1e9 / peak, "traffic": traffic,
+                "traffic_source": (json.load(open(tpath)).get("source") if os.path.exists(tpath) else None), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bytes_launch, "ms_per_launch_cold_l2": ms_cold,
                 "ms_per_launch_l2_resident": ms_warm,
                 "l2_resident_equiv_gbs": bytes_launch / (ms_warm * 1e-3) / 1e9}
@@ -283,18 +496,29 @@ def run_ours(args, rank, world, local_rank):
                     "converged": s3["converged"], "elbo": s3["elbo"]}
         f3.close()
     if world == 1 and not args.skip_fit and not cfg4:
+        # the fit's wall-clock starts at the scaled coordinates: k-means centroids (10 starts) and the basis build
+        # (kernel matrix + pivoted QR) on the device, H2D + staging of Y, L-BFGS, eta adaptation, SGA, draws + summaries
+        from bayesvg_b200 import synth
+        from bayesvg_b200.api import kmeans_centers, length_scale_kmeans
+        Xf = synth.scale_coords(synth.visium_grid())
         t0 = time.perf_counter()
-        f3 = bvg.Fit(phi, Y, "gaussian", "fast", args.engine, **cfg)
+        Cf = kmeans_centers(Xf, K_BASIS, 100, 10, rng=312, device=local_rank)
+        phif = bvg.basis_build(Xf, Cf, length_scale_kmeans(Cf), "matern", 2.5, device=local_rank)
+        t_kb = time.perf_counter() - t0
+        Yf, _ = synth.expression(phif, G_GENES, "gaussian", 312)
+        t0 = time.perf_counter()
+        f3 = bvg.Fit(phif, Yf, "gaussian", "fast", args.engine, **cfg)
         f3.run()
         s3 = f3.stats()
-        fit_info = {"wall_s": time.perf_counter() - t0, "grad_evals": s3["grad_evals"], "elbo_evals": s3["elbo_evals"],
-                    "advi_iters": s3["advi_iters"], "eta": s3["eta"], "mle_iters": s3["mle_iters"],
-                    "mle_fevals": s3["mle_fevals"], "sec_mle": s3["sec_mle"], "sec_adapt": s3["sec_adapt"],
-                    "sec_sga": s3["sec_sga"], "sec_draws": s3["sec_draws"], "converged": s3["converged"]}
+        fit_info = {"wall_s": time.perf_counter() - t0 + t_kb, "sec_kmeans_basis": t_kb, "sec_h2d": s3["sec_h2d"], "grad_evals": s3["grad_evals"],
+                    "elbo_evals": s3["elbo_evals"], "advi_iters": s3["advi_iters"], "eta": s3["eta"], "mle_iters": s3["mle_iters"],
+                    "mle_fevals": s3["mle_fevals"], "mle_term": s3["mle_term"], "sec_mle": s3["sec_mle"], "sec_adapt": s3["sec_adapt"],
+                    "sec_sga": s3["sec_sga"], "sec_draws": s3["sec_draws"], "converged": s3["converged"], "elbo": s3["elbo"],
+                    "includes": "k-means (10 starts) + basis build + H2D + L-BFGS + eta adaptation + SGA + 1,000 draws + summaries"}
         f3.close()
         # separately reported fast path: forward-only ELBO estimates from sufficient statistics (gaussian)
         t0 = time.perf_counter()
-        f4 = bvg.Fit(phi, Y, "gaussian", "fast", args.engine, elbo_suffstat=1, **cfg)
+        f4 = bvg.Fit(phif, Yf, "gaussian", "fast", args.engine, elbo_suffstat=1, **cfg)
         f4.run()
         s4 = f4.stats()
         fit_info["suffstat_elbo"] = {"wall_s": time.perf_counter() - t0, "sec_mle": s4["sec_mle"], "sec_adapt": s4["sec_adapt"],
@@ -364,7 +588,14 @@ def run_ours(args, rank, world, local_rank):
         n1, dt1 = cpu_evals(phi, Y, 3.0, 3, 1)
         cpu["single_thread"] = {"value": n1 / dt1, "unit": "evals/s", "cores": 1,
                                 "sample": f"{n1} evals in {dt1:.1f} s on one thread (what stan_threads = FALSE gives the reference)"}
+    extra = {}
+    if rank == 0 and world == 1 and not cfg4 and not args.skip_extra:
+        extra = extra_blocks_n1(args, local_rank, phi, Y)
     fit.close()
+    strong = None
+    if not cfg4 and not args.skip_strong:
+        del Y
+        strong = strong_cfg4(args, rank, world, local_rank, barrier)
     if rank == 0:
         print(json.dumps({
             "metric": "elbo_grad_evals_per_sec", "value": value, "unit": "evals/s", "n_gpus": world,
@@ -378,10 +609,13 @@ def run_ours(args, rank, world, local_rank):
                               "the 60 MB Y as the real fit does" if not args.no_flush else "no flush"),
                        "genes_total": G_total,
                        "exchange": (None if world == 1 else
-                                    ("2k+10 fp64 sums per eval, all-reduced inside k_gene's last CTA over CUDA-IPC peer memory (NVLink)"
+                                    ("2k+10 fp64 sums per eval, exchanged inside the persistent ADVI kernel over CUDA-IPC peer memory (NVLink): CTA 0 pushes, every CTA polls and sums in rank order"
                                      if args.comm == "peer" else "2k+10 fp64 sums per eval, ncclAllReduce between k_gene and k_finish"))},
-            "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+            "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(launches),
+            "gpu_launches_note": "kernel launches inside the timed region: k_prep + k_advi_persist (one cooperative launch = the whole stretch of evals_per_step evaluations) per step",
+            "roofline": roofline,
             "roofline_input_larger_than_l2": roofline_large, "roofline_large_basis": roofline_kbig, "cpu_baseline": cpu, "fit": fit_info,
+            "strong_cfg4": strong, "parity_check": parity, **extra,
         }))
     if world > 1:
         import torch.distributed as td
@@ -405,6 +639,10 @@ def main():
     ap.add_argument("--skip-fit", action="store_true")
     ap.add_argument("--skip-large", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--cpu-fit-genes", type=int, default=192, help="genes of the bounded CPU fit leg of cfg1_fit")
+    ap.add_argument("--skip-strong", action="store_true", help="no strong_cfg4 block")
+    ap.add_argument("--skip-extra", action="store_true", help="no cfg3_nb / fp64_engine / cfg1_fit blocks (N = 1)")
+    ap.add_argument("--skip-parity", action="store_true", help="no sharded-vs-unsharded pre-flight (N > 1)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -234,7 +234,7 @@ typedef struct {
   double sec_h2d, sec_mle, sec_adapt, sec_sga, sec_draws, sec_total;
   int64_t kernel_launches;
   int32_t engine_used; /* bvg_engine actually running the likelihood */
-  int32_t pad;
+  int32_t mle_fp64_from; /* fast precision: L-BFGS iteration from which the fp64 evaluator took over (0 = never) */
 } bvg_fit_stats;
 int bvg_fit_get_stats(bvg_fit *, bvg_fit_stats *out);
 

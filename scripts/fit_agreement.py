@@ -26,24 +26,42 @@ def main():
     out = dict(workload=f"{name}: {M} spots x {G} genes, k={ds['k']}, {ds['kernel']} {ds['nu']}, {lik}", n_draws=1000,
                n_iter=3000, elbo_samples=150, seed=312)
     res = {}
-    for prec, eng in (("fast", "auto"), ("fp64", "simt")):
+    nseeds = int(os.environ.get("FIT_SEEDS", "3"))
+    # ONE estimator for every fitted (mu, omega): the fp64 engine, 1,000 fresh draws of a fixed Philox key -- separates
+    # "the fast engine estimates the ELBO differently" from "the two optimisations ended somewhere else"
+    judge = bvg.Fit(phi, Y, lik, "fp64", "simt", seed=99991)
+    out["elbo_by_common_fp64_estimator_1000_draws"] = {}
+    for seed in [312 + 1000 * i for i in range(nseeds)]:
+        for prec, eng in (("fast", "auto"), ("fp64", "simt")):
+            t0 = time.perf_counter()
+            f = bvg.Fit(phi, Y, lik, prec, eng, seed=seed)
+            tab = f.run()
+            st = f.stats()
+            mu_v, om_v = f.get_variational()
+            judge.set_variational(mu_v, om_v)
+            judge.advi_steps(0, 0.1, reset=True)
+            e_common = judge.elbo(1000)[0]
+            rec = dict(wall_s=time.perf_counter() - t0, eta=st["eta"], advi_iters=st["advi_iters"], converged=st["converged"],
+                       elbo=st["elbo"], elbo_common=e_common, mle_iters=st["mle_iters"], mle_term=st["mle_term"], mle_lp=st["mle_lp"], mle_fp64_from=st["mle_fp64_from"],
+                       sec_mle=st["sec_mle"], sec_adapt=st["sec_adapt"], sec_sga=st["sec_sga"], engine=st["engine_used"])
+            out["elbo_by_common_fp64_estimator_1000_draws"].setdefault(prec, []).append(dict(seed=seed, elbo_own_150_draws=st["elbo"], elbo_common=e_common,
+                                                                                             mle_iters=st["mle_iters"], mle_term=st["mle_term"], mle_lp=st["mle_lp"]))
+            if seed == 312:
+                res[prec] = tab
+                out[f"gpu_{prec}"] = rec
+            f.close()
+    judge.close()
+    skip_cpu = os.environ.get("FIT_SKIP_CPU") == "1"   # GPU fast vs GPU fp64 only (the fp64 engine reproduces the CPU fit: Spearman 0.999)
+    ref = res["fp64"]
+    if not skip_cpu:
         t0 = time.perf_counter()
-        f = bvg.Fit(phi, Y, lik, prec, eng, seed=312)
-        tab = f.run()
-        st = f.stats()
-        res[prec] = tab
-        out[f"gpu_{prec}"] = dict(wall_s=time.perf_counter() - t0, eta=st["eta"], advi_iters=st["advi_iters"], converged=st["converged"],
-                                  elbo=st["elbo"], mle_iters=st["mle_iters"], sec_mle=st["sec_mle"], sec_adapt=st["sec_adapt"],
-                                  sec_sga=st["sec_sga"], engine=st["engine_used"])
-        f.close()
-    t0 = time.perf_counter()
-    o = orc.Oracle(phi, Y, lik, nthreads=nthreads)
-    th, li = o.lbfgs(max_iter=1000)
-    t1 = time.perf_counter()
-    mu, om, info = o.advi(th, iter=3000, elbo_samples=150, seed=312)
-    ref = o.summary(mu, om, 1000, 312)
-    out["cpu_port"] = dict(wall_s=time.perf_counter() - t0, sec_mle=t1 - t0, threads=nthreads, eta=info["eta"], advi_iters=info["iters"],
-                           converged=info["converged"], elbo=info.get("elbo"), mle_iters=li.get("iters") if isinstance(li, dict) else None)
+        o = orc.Oracle(phi, Y, lik, nthreads=nthreads)
+        th, li = o.lbfgs(max_iter=1000)
+        t1 = time.perf_counter()
+        mu, om, info = o.advi(th, iter=3000, elbo_samples=150, seed=312)
+        ref = o.summary(mu, om, 1000, 312)
+        out["cpu_port"] = dict(wall_s=time.perf_counter() - t0, sec_mle=t1 - t0, threads=nthreads, eta=info["eta"], advi_iters=info["iters"],
+                               converged=info["converged"], elbo=info.get("elbo"), mle_iters=li.get("iters") if isinstance(li, dict) else None)
     top = min(1000, G // 3)
 
     def agree(a, b):
@@ -51,14 +69,16 @@ def main():
         return dict(spearman=float(spearmanr(a, b).correlation), top_k=top, top_k_overlap=ov,
                     max_rel_diff=float(np.max(np.abs(a - b) / np.abs(b))))
 
-    out["fast_vs_cpu"] = agree(res["fast"][:, 0], ref[:, 0])
-    out["fp64_vs_cpu"] = agree(res["fp64"][:, 0], ref[:, 0])
+    if not skip_cpu:
+        out["fast_vs_cpu"] = agree(res["fast"][:, 0], ref[:, 0])
+        out["fp64_vs_cpu"] = agree(res["fp64"][:, 0], ref[:, 0])
     out["fast_vs_fp64_gpu"] = agree(res["fast"][:, 0], res["fp64"][:, 0])
     amp = ds["amp"]
     out["vs_planted_amplitude"] = dict(gpu_fast=float(spearmanr(res["fast"][:, 0], amp).correlation),
                                        gpu_fp64=float(spearmanr(res["fp64"][:, 0], amp).correlation),
-                                       cpu_port=float(spearmanr(ref[:, 0], amp).correlation))
-    out["speedup_fast_vs_cpu_port"] = out["cpu_port"]["wall_s"] / out["gpu_fast"]["wall_s"]
+                                       cpu_port=None if skip_cpu else float(spearmanr(ref[:, 0], amp).correlation))
+    if not skip_cpu:
+        out["speedup_fast_vs_cpu_port"] = out["cpu_port"]["wall_s"] / out["gpu_fast"]["wall_s"]
     print(json.dumps(out))
 
 

@@ -299,11 +299,12 @@ def _advi_run(p, lik, steps, no_persist, depths=None, seed=11, eta=0.05):
 
 
 @pytest.mark.parametrize("lik,depth", [("gaussian", False), ("nb", False), ("gaussian", True), ("nb", True)])
-@pytest.mark.parametrize("M,G,k", [(1000, 257, 20), (300, 200, 17), (97, 130, 7), (260, 1, 1), (4000, 700, 23)])
+@pytest.mark.parametrize("M,G,k", [(1000, 257, 20), (300, 200, 17), (97, 130, 7), (260, 1, 1), (4000, 700, 23), (9000, 300, 12)])
 def test_persistent_advi_kernel_equals_the_two_launch_chain(lik, depth, M, G, k):
     """k_advi_persist (one cooperative launch per stretch: passes, tile / grid arrival counters, replicated finish) against
     k_lik_tc -> k_gene per evaluation: same Philox draws, same per-gene arithmetic; only the cross-gene sums are added in a
-    different fixed order, so 25 iterations agree to rounding.  Also: the stretch really is 2 launches (k_prep + persistent)."""
+    different fixed order, so 25 iterations agree to rounding.  Also: the stretch really is 2 launches (k_prep + persistent).
+    (9000, 300, 12): 3 tiles x 47 spot splits -- more splits than a tile has genes to hand out, so some CTAs own no genes."""
     p = make_problem(M, G, k, lik, seed=21)
     depths = np.log(np.maximum(p["y"].sum(0), 1.0)) - 5.0 if depth else None
     mu_a, om_a, la = _advi_run(p, lik, (25,), False, depths)
@@ -688,6 +689,101 @@ def test_full_size_properties_cfg2():
         else:
             assert rel_err(g, g64) <= 2e-4
         f.close()
+
+
+@pytest.mark.parametrize("name,M,G,k,lik,kern,nu", [
+    ("cfg2", 4992, 3000, 20, "gaussian", "matern", 2.5),      # BASELINE.json configs[1]: the shape the metric is quoted on
+    ("cfg3", 4992, 3000, 20, "nb", "exp_quad", 0.0),          # configs[2]: counts, negative-binomial, exp_quad
+    ("cfg4_shard", 50000, 1250, 20, "gaussian", "matern", 1.5),  # configs[3]: what each of 8 GPUs holds at 50k x 10k
+    ("k400", 20000, 256, 400, "gaussian", "matern", 1.5),     # configs[4]'s basis size on the large-basis tcgen05 kernels
+])
+def test_full_size_log_prob_and_gradient_against_the_oracle(name, M, G, k, lik, kern, nu):
+    """The engines the bench quotes, at the shapes it quotes them on, against the CPU ORACLE (not against each other):
+    log density and full gradient at a random unconstrained vector.  north_star gates: <= 1e-6 (fp64), <= 1e-3 (fast path);
+    asserted tighter."""
+    from bayesvg_b200 import synth
+    from bayesvg_b200.api import length_scale_kmeans
+    X = synth.scale_coords(synth.visium_grid() if M == 4992 else synth.random_points(M, 1))
+    C = synth.det_kmeans(X, k, 312, iters=30) if k <= 30 else bvg.kmeans_centers(X, k, 30, 1, rng=312)
+    phi = bvg.basis_build(X, C, length_scale_kmeans(C), kern, nu)
+    Y, _ = synth.expression(phi, G, lik, 312)
+    if lik == "nb":
+        Y = np.asfortranarray(Y.astype(np.int32))
+    o = orc.Oracle(phi, np.asfortranarray(Y, dtype=np.float64), lik, nthreads=os.cpu_count() or 4)
+    th = np.random.default_rng(5).normal(0, 0.2, o.D)
+    rlp, rg = o.log_prob(th, True, True)
+    engines = [("fast", "tcgen05", 2e-5, 2e-4)]
+    if name in ("cfg2", "cfg3"):
+        engines.append(("fp64", "simt", 1e-10, 1e-9))
+    for prec, eng, tol_lp, tol_g in engines:
+        f = bvg.Fit(phi, Y, lik, prec, eng)
+        assert f.stats()["engine_used"] == (2 if eng == "tcgen05" else 1)
+        lp, g = f.log_prob(th, True, True)
+        assert abs(lp - rlp) <= tol_lp * abs(rlp), (name, prec, lp, rlp)
+        assert rel_err(g, rg) <= tol_g, (name, prec, rel_err(g, rg))
+        if prec == "fast" and k <= 23:
+            # ... and ten ADVI iterations through the persistent kernel against the oracle's fp64 loop (same Philox draws)
+            mu, om, hist = np.zeros(o.D), np.zeros(o.D), np.zeros(2 * o.D)
+            f.set_variational(mu, None)
+            f.advi_steps(0, 0.1, reset=True)
+            for it in range(1, 11):
+                o.advi_step(mu, om, hist, 0.1, it, 312, it - 1)
+            f.advi_steps(10, 0.1)
+            gmu, gom = f.get_variational()
+            assert rel_err(gmu, mu) < 1e-3 and rel_err(gom, om) < 1e-3, (name, rel_err(gmu, mu), rel_err(gom, om))
+        f.close()
+
+
+def test_fast_lbfgs_hands_over_to_the_fp64_evaluator_at_its_noise_floor():
+    """BASELINE configs[2] (nb, exp_quad, 4,992 x 3,000): the fast path's line search fails after ~350 of the 1,000 L-BFGS
+    iterations (its evaluator's noise, scripts/lsfail_probe.py); lbfgs_run then continues from that point with the fp64
+    evaluator (fp64_shadow.cu) and must end like the all-fp64 run: same termination after the same 1,000 iterations, a log
+    density no worse than the all-fp64 run's (both stop at the iteration cap, on slightly different paths), and the fast engine
+    back in place afterwards."""
+    from bayesvg_b200 import synth
+    ds = synth.dataset("cfg3", lambda X, C, ls, kern, nu: bvg.basis_build(X, C, ls, kern, nu))
+    f = bvg.Fit(ds["phi"], ds["Y"], "nb", "fast", "tcgen05", seed=312)
+    th = f.mle()
+    st = f.stats()
+    fd = bvg.Fit(ds["phi"], ds["Y"], "nb", "fp64", "simt", seed=312)
+    fd.mle()
+    sd = fd.stats()
+    assert st["mle_fp64_from"] > 0 and st["mle_term"] == sd["mle_term"] and st["mle_iters"] == sd["mle_iters"] == 1000
+    assert st["mle_lp"] >= sd["mle_lp"] - 2e-5 * abs(sd["mle_lp"])   # round 1 (no hand-over): 1,489 = 9.4e-5 below
+    assert st["engine_used"] == 2
+    lp_fast = f.log_prob(th, False, False, grad=False)          # evaluated by the tcgen05 engine again
+    lp_64 = fd.log_prob(th, False, False, grad=False)
+    assert lp_fast == pytest.approx(lp_64, rel=1e-6)
+    assert f.advi_steps(10, 0.1, reset=True) > 0                 # ... and the persistent kernel runs on the restored buffers
+    f.close()
+    fd.close()
+
+
+def test_cfg1_fit_agrees_with_the_oracle_fit_fixture(golden_dir):
+    """north_star's second check at the scale it names: the posterior amplitude summaries of the whole default fit (L-BFGS
+    init -> eta adaptation -> 3,000 SGA iterations -> 1,000 draws) on the stand-in for configs[0] (2,444 spots x 3,000 HVGs,
+    Matern-2.5, gaussian) against the CPU oracle's fit of the same data with the same Philox streams, stored in
+    tests/golden/cfg1_fit.npz (tests/golden/make_cfg1_fit_fixture.py).  Stated Monte Carlo tolerance: Spearman >= 0.99 and
+    top-1,000 overlap >= 0.98 for the fast path (>= 0.999 / 0.99 in fp64)."""
+    from scipy.stats import spearmanr
+
+    from bayesvg_b200 import synth
+    fx = np.load(os.path.join(golden_dir, "cfg1_fit.npz"))
+    ds = synth.dataset("cfg1", lambda X, C, ls, kern, nu: bvg.basis_build(X, C, ls, kern, nu))
+    assert float(np.abs(ds["Y"]).sum()) == pytest.approx(float(fx["y_checksum"]), rel=1e-9)     # same data as the fixture's
+    assert float(np.abs(ds["phi"]).sum()) == pytest.approx(float(fx["phi_checksum"]), rel=1e-8)
+    ref = fx["amplitude_mean"]
+    for prec, eng, rho_min, top_min in (("fast", "tcgen05", 0.99, 0.98), ("fp64", "simt", 0.999, 0.99)):
+        f = bvg.Fit(ds["phi"], ds["Y"], "gaussian", prec, eng, seed=312)
+        tab = f.run()
+        st = f.stats()
+        f.close()
+        assert st["eta"] == float(fx["eta"]) and st["advi_iters"] == int(fx["advi_iters"])
+        rho = float(spearmanr(tab[:, 0], ref).correlation)
+        top = len(set(np.argsort(-tab[:, 0])[:1000]) & set(np.argsort(-ref)[:1000])) / 1000
+        assert rho >= rho_min and top >= top_min, (prec, rho, top)
+        if prec == "fast":
+            assert st["mle_iters"] == 1000 and st["mle_term"] == 5   # the fast path's L-BFGS runs its 1,000 iterations like the fp64 one
 
 
 def _gmm_data(N=150, D=4, K=3, seed=0):
