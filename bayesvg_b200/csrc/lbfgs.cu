@@ -9,6 +9,7 @@
 // the (2m+1)^2 Gram matrix; each iteration adds three rows to that matrix with ONE fused kernel and
 // forms the direction with one more, instead of 4m dependent dot/axpy launches.
 #include <float.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <cmath>
@@ -144,6 +145,8 @@ int lbfgs_run(bvg_fit *f, const double *d_theta0, double *d_out, const LbfgsOpt 
   double gg = h_scal[0];   // g.g
   double dfp = -gg;        // g.p for p = -g
   int nh = 0, head = 0, it = 0, term = 0, switch_iter = 0;
+  int force_at = 0;
+  if (const char *e = getenv("BVG_MLE_FP64_AT")) force_at = atoi(e);
   double fk1 = 0, alpha = 1e-3, alphak1 = 0, dfp_prev = 0, gamma = 1;
   const double eps = DBL_EPSILON, tol_obj = 1e-12, tol_rel_obj = 1e4, tol_grad = 1e-8, tol_rel_grad = 1e7, tol_param = 1e-8;
   const int max_iter = opt && opt->max_iter > 0 ? opt->max_iter : f->cfg.mle_iter;
@@ -160,7 +163,8 @@ int lbfgs_run(bvg_fit *f, const double *d_theta0, double *d_out, const LbfgsOpt 
       }
       if (it > 1 && resetB != 2) alpha = std::min(1.0, 1.01 * cubic_interp(dfp_prev, alphak1, fk - fk1, dfp, 1e-12, 1.0));
       else alpha = 1e-3;
-      const int ls = wolfe(ev, &alpha, &f1, &dg1, fk, dfp);
+      int ls = wolfe(ev, &alpha, &f1, &dg1, fk, dfp);
+      if (force_at > 0 && it == force_at && !shadow_active(f)) { ls = 1; resetB = resetB ? resetB : 2; }  // tests: hand over at a chosen iteration
       if (ls) {
         if (resetB) {
           // even steepest descent finds no acceptable step.  Fast precision: the search is comparing the evaluator's noise

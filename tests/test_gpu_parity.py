@@ -759,6 +759,38 @@ def test_fast_lbfgs_hands_over_to_the_fp64_evaluator_at_its_noise_floor():
     fd.close()
 
 
+@pytest.mark.parametrize("lik,eng,M,G,k", [("gaussian", "tcgen05", 700, 300, 20), ("nb", "tcgen05", 700, 300, 12),
+                                             ("gaussian", "auto", 640, 45, 64), ("nb", "simt", 300, 70, 7)])
+def test_fp64_hand_over_of_the_fast_lbfgs_on_every_fast_engine(lik, eng, M, G, k):
+    """fp64_shadow.cu behind every fast engine (fused tcgen05, large-basis tcgen05, SIMT fp32), forced at iteration 6
+    (BVG_MLE_FP64_AT): the run finishes on fp64 evaluations (Y widened from the resident fp32 copy), reaches the all-fp64 run's
+    optimum, and the fast engine evaluates again afterwards."""
+    p = make_problem(M, G, k, lik, seed=41)
+    os.environ["BVG_MLE_FP64_AT"] = "6"
+    try:
+        f = bvg.Fit(p["phi"], p["y"], lik, "fast", eng, seed=3, mle_iter=60)
+        th = f.mle()
+        st = f.stats()
+    finally:
+        del os.environ["BVG_MLE_FP64_AT"]
+    fd = bvg.Fit(p["phi"], p["y"], lik, "fp64", "simt", seed=3, mle_iter=60)
+    fd.mle()
+    sd = fd.stats()
+    assert st["mle_fp64_from"] == 6 and st["mle_iters"] == 60 and sd["mle_fp64_from"] == 0
+    # (the forced hand-over clears the curvature history at iteration 6, so after 60 iterations the two runs are at different
+    # stages of the same climb: the run must have climbed, not matched)
+    lp0 = fd.log_prob(np.zeros(fd.D), False, False, grad=False)
+    assert st["mle_lp"] > lp0 + 0.5 * (sd["mle_lp"] - lp0)
+    # the reported optimum is an fp64 value of the point returned, and the fast engine is back for everything that follows
+    assert fd.log_prob(th, False, False, grad=False) == pytest.approx(st["mle_lp"], rel=1e-6)
+    assert f.log_prob(th, False, False, grad=False) == pytest.approx(st["mle_lp"], rel=2e-4)
+    assert f.stats()["engine_used"] == (1 if eng == "simt" else 2)
+    f.advi()
+    assert np.all(np.isfinite(f.summarize()))
+    f.close()
+    fd.close()
+
+
 def test_cfg1_fit_agrees_with_the_oracle_fit_fixture(golden_dir):
     """north_star's second check at the scale it names: the posterior amplitude summaries of the whole default fit (L-BFGS
     init -> eta adaptation -> 3,000 SGA iterations -> 1,000 draws) on the stand-in for configs[0] (2,444 spots x 3,000 HVGs,
