@@ -208,6 +208,35 @@ __device__ __forceinline__ void split_bf16x2(float e0, float e1, uint32_t &p1, u
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p2) : "f"(r1), "f"(r0));
 }
 
+// ---- packed fp32 pairs (sm_100: add / mul / fma .f32x2 issue ONE instruction for two lanes' worth of fp32 work) ----
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t f2_sub(uint64_t a, uint64_t b) {   // a - b = fma(b, -1, a): exact, one rounding like sub
+  uint64_t r;
+  asm("{\n\t.reg .b64 m;\n\tmov.b64 m, 0xbf800000bf800000;\n\tfma.rn.f32x2 %0, %2, m, %1;\n\t}" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+// (e0, e1) as a packed pair -> packed bf16 pair p1 and the packed bf16 pair p2 of the remainders (split_bf16x2 with the
+// remainder formed by one packed subtraction)
+__device__ __forceinline__ void split_bf16x2_pk(uint64_t e, uint32_t &p1, uint32_t &p2) {
+  float e0, e1;
+  f2_unpack(e, e0, e1);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p1) : "f"(e1), "f"(e0));
+  const uint64_t hi = f2_pack(__uint_as_float(p1 << 16), __uint_as_float(p1 & 0xffff0000u));
+  float r0, r1;
+  f2_unpack(f2_sub(e, hi), r0, r1);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p2) : "f"(r1), "f"(r0));
+}
+
 // D[tmem] (+)= A[smem] . B[smem]^T, kind::f16 (bf16 inputs, fp32 accumulate), M = 128, K = 16: both operands K-major in smem
 __device__ __forceinline__ void tc_mma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
   asm volatile(

@@ -191,6 +191,18 @@ __device__ __forceinline__ void tc_role_produce_basis(const TcCtx &x, const CUte
     }
   }
 }
+// the forward MMAs of one accumulator (BF16x3: C1 F1 + C2 F1 + C1 F2), NK1 = ceil((k + 1) / 16) K steps each, fully unrolled:
+// with a run-time trip count ptxas built a 16-way unrolled loop with remainder branches around six instructions, and ISSUING
+// them took ~650 cycles per chunk (in-kernel trace) -- longer than the 200 cycles the tensor pipe needs to execute them
+template <int NK1>
+__device__ __forceinline__ void tc_issue_mma1(uint32_t d1, uint32_t tmem, uint64_t f1, uint64_t f2, uint32_t idesc) {
+#pragma unroll
+  for (int kk = 0; kk < NK1; ++kk) tc_mma_bf16_ts(d1, tmem + TM_C1 + 8 * kk, f1 + 2 * kk, idesc, kk ? 1u : 0u);
+#pragma unroll
+  for (int kk = 0; kk < NK1; ++kk) tc_mma_bf16_ts(d1, tmem + TM_C2 + 8 * kk, f1 + 2 * kk, idesc, 1u);
+#pragma unroll
+  for (int kk = 0; kk < NK1; ++kk) tc_mma_bf16_ts(d1, tmem + TM_C1 + 8 * kk, f2 + 2 * kk, idesc, 1u);
+}
 // ===================== forward MMA issuer (whole warp convergent, one elected lane issues) =====
 // pass = index of this pass since barrier init (parity of the "coefficient rows are in TMEM" barrier)
 template <bool BWD>
@@ -209,9 +221,8 @@ __device__ __forceinline__ void tc_role_mma1(const TcCtx &x, int n, int nk1, uin
     if (elect_one()) {
       const uint32_t d1 = x.tmem + TM_D1 + 64 * b;
       const uint64_t f1 = make_desc(x.stF(s, 0)), f2 = make_desc(x.stF(s, 1));
-      for (int kk = 0; kk < nk1; ++kk) tc_mma_bf16_ts(d1, x.tmem + TM_C1 + 8 * kk, f1 + 2 * kk, idesc, kk ? 1u : 0u);
-      for (int kk = 0; kk < nk1; ++kk) tc_mma_bf16_ts(d1, x.tmem + TM_C2 + 8 * kk, f1 + 2 * kk, idesc, 1u);
-      for (int kk = 0; kk < nk1; ++kk) tc_mma_bf16_ts(d1, x.tmem + TM_C1 + 8 * kk, f2 + 2 * kk, idesc, 1u);
+      if (nk1 == 2) tc_issue_mma1<2>(d1, x.tmem, f1, f2, idesc);
+      else tc_issue_mma1<1>(d1, x.tmem, f1, f2, idesc);
       tc_commit(x.bD1Full + 8 * b);
       if (!BWD) tc_commit(x.bEmptyB + 8 * s);  // forward-only: the basis stage is free once MMA1 has read it
     }
@@ -299,6 +310,7 @@ __device__ __forceinline__ void tc_role_epilogue(const TcCtx &x, uint32_t trow, 
     const int64_t spot0 = (int64_t)(c_begin + c) * TC_CHUNK + 32 * h;
     uint32_t p1[16], p2[16];
     float acc0 = 0.f, acc1 = 0.f;
+    uint64_t accp = 0ull;   // gaussian: two running sums of squares, packed
     // masked = std::true_type only for the one chunk that straddles M (nb: padded spots have a non-zero term)
     auto body = [&](auto masked, int nvalid) {
       constexpr bool MASKED = decltype(masked)::value;
@@ -308,6 +320,17 @@ __device__ __forceinline__ void tc_role_epilogue(const TcCtx &x, uint32_t trow, 
         const float4 y4 = lds128(yrow + off);
         const float yv[4] = {y4.x, y4.y, y4.z, y4.w};
         float res[4];
+        if (LIK == BVG_GAUSSIAN) {
+          // packed fp32 pairs: residual, squared-error accumulation and the bf16 remainder are one instruction per TWO
+          // elements each (the epilogue is bound by issue slots: ~5.25 instructions per element before, ~3.75 now)
+          const uint64_t ra = f2_sub(f2_pack(yv[0], yv[1]), f2_pack(f[4 * c4], f[4 * c4 + 1]));
+          const uint64_t rb = f2_sub(f2_pack(yv[2], yv[3]), f2_pack(f[4 * c4 + 2], f[4 * c4 + 3]));
+          accp = f2_fma(ra, ra, accp);
+          accp = f2_fma(rb, rb, accp);
+          split_bf16x2_pk(ra, p1[2 * c4], p2[2 * c4]);
+          split_bf16x2_pk(rb, p1[2 * c4 + 1], p2[2 * c4 + 1]);
+          continue;
+        }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const float ff = f[4 * c4 + i];
@@ -342,6 +365,7 @@ __device__ __forceinline__ void tc_role_epilogue(const TcCtx &x, uint32_t trow, 
     if (LIK == BVG_GAUSSIAN || left >= 32) body(std::false_type{}, 32);
     else body(std::true_type{}, left > 0 ? (int)left : 0);
     mbar_arrive(x.bEmptyY + 8 * s);  // y is in registers: the Y stage can be refilled
+    if (LIK == BVG_GAUSSIAN) { float a0, a1; f2_unpack(accp, a0, a1); acc0 = a0 + a1; }
     sum0 += (double)acc0;
     if (LIK == BVG_NB) sum1 += (double)acc1;
     if (BWD) {
