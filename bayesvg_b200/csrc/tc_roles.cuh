@@ -310,7 +310,7 @@ __device__ __forceinline__ void tc_role_epilogue(const TcCtx &x, uint32_t trow, 
     const int64_t spot0 = (int64_t)(c_begin + c) * TC_CHUNK + 32 * h;
     uint32_t p1[16], p2[16];
     float acc0 = 0.f, acc1 = 0.f;
-    uint64_t accp = 0ull;   // gaussian: two running sums of squares, packed
+    uint64_t accp = 0ull, accq = 0ull;   // packed pairs of running sums (gaussian: squares; nb: log-lik terms, log1p_exp terms)
     // masked = std::true_type only for the one chunk that straddles M (nb: padded spots have a non-zero term)
     auto body = [&](auto masked, int nvalid) {
       constexpr bool MASKED = decltype(masked)::value;
@@ -329,6 +329,45 @@ __device__ __forceinline__ void tc_role_epilogue(const TcCtx &x, uint32_t trow, 
           accp = f2_fma(rb, rb, accp);
           split_bf16x2_pk(ra, p1[2 * c4], p2[2 * c4]);
           split_bf16x2_pk(rb, p1[2 * c4 + 1], p2[2 * c4 + 1]);
+          continue;
+        }
+        if (LIK == BVG_NB && !MASKED) {
+          // negative binomial, packed: per element TWO MUFU operations (ex2, rcp) instead of three -- log1p(e^{-|d|}) comes
+          // from a degree-8 polynomial in u = e^{-|d|} in (0, 1] on the FMA pipe (fp32 Horner error 1.2e-7 absolute, the same
+          // as lg2.approx x ln 2 had) -- and everything that is an add / multiply / fma is one instruction per two elements.
+          // The round-1 form (3 MUFU + ~17 scalar instructions per element) was bound by the MUFU pipe: 1,536 cycles per
+          // chunk and scheduler against 950 for the gaussian epilogue.
+          //   ll_sg = y d - (y + phi) L,  d = eta - log phi,  L = log1p_exp(d)   (approxGP4.stan:48)
+          const uint64_t one2 = f2_pack(1.f, 1.f), mone2 = f2_pack(-1.f, -1.f), lt2 = f2_pack(lt, lt), nphi2 = f2_pack(-phi, -phi);
+#pragma unroll
+          for (int hp = 0; hp < 2; ++hp) {
+            const uint64_t y2 = f2_pack(yv[2 * hp], yv[2 * hp + 1]);
+            const uint64_t d2 = f2_sub(f2_pack(f[4 * c4 + 2 * hp], f[4 * c4 + 2 * hp + 1]), lt2);
+            float d0, d1;
+            f2_unpack(d2, d0, d1);
+            const float e0 = ex2_approx(-fabsf(d0) * 1.4426950408889634f), e1 = ex2_approx(-fabsf(d1) * 1.4426950408889634f);
+            const uint64_t u2 = f2_pack(e0, e1);
+            float t0, t1;
+            f2_unpack(f2_fma(u2, one2, one2), t0, t1);
+            const uint64_t rt2 = f2_pack(rcp_approx(t0), rcp_approx(t1));
+            uint64_t L2 = f2_pack(-0.006006604991853237f, -0.006006604991853237f);
+            L2 = f2_fma(L2, u2, f2_pack(0.03426460176706314f, 0.03426460176706314f));
+            L2 = f2_fma(L2, u2, f2_pack(-0.09229041635990143f, -0.09229041635990143f));
+            L2 = f2_fma(L2, u2, f2_pack(0.1649981290102005f, 0.1649981290102005f));
+            L2 = f2_fma(L2, u2, f2_pack(-0.2394333779811859f, -0.2394333779811859f));
+            L2 = f2_fma(L2, u2, f2_pack(0.33144664764404297f, 0.33144664764404297f));
+            L2 = f2_fma(L2, u2, f2_pack(-0.49982550740242004f, -0.49982550740242004f));
+            L2 = f2_fma(L2, u2, f2_pack(0.999993622303009f, 0.999993622303009f));
+            L2 = f2_fma(L2, u2, f2_pack(3.910905377324525e-08f, 3.910905377324525e-08f));   // log1p(u)
+            const uint64_t Lq2 = f2_fma(L2, one2, f2_pack(fmaxf(d0, 0.f), fmaxf(d1, 0.f)));      // + max(d, 0) = log1p_exp(d)
+            const uint64_t sg2 = f2_fma(f2_pack(d0 >= 0.f ? 1.f : e0, d1 >= 0.f ? 1.f : e1), rt2, 0ull);   // sigmoid(d)
+            const uint64_t nyp2 = f2_fma(y2, mone2, nphi2);                                     // -(y + phi)
+            const uint64_t r2 = f2_fma(nyp2, sg2, y2);                                          // y - (y + phi) sigmoid(d)
+            accp = f2_fma(y2, d2, accp);
+            accp = f2_fma(nyp2, Lq2, accp);
+            accq = f2_fma(Lq2, one2, accq);
+            split_bf16x2_pk(r2, p1[2 * c4 + hp], p2[2 * c4 + hp]);
+          }
           continue;
         }
 #pragma unroll
@@ -366,6 +405,7 @@ __device__ __forceinline__ void tc_role_epilogue(const TcCtx &x, uint32_t trow, 
     else body(std::true_type{}, left > 0 ? (int)left : 0);
     mbar_arrive(x.bEmptyY + 8 * s);  // y is in registers: the Y stage can be refilled
     if (LIK == BVG_GAUSSIAN) { float a0, a1; f2_unpack(accp, a0, a1); acc0 = a0 + a1; }
+    else { float a0, a1, b0, b1; f2_unpack(accp, a0, a1); f2_unpack(accq, b0, b1); acc0 += a0 + a1; acc1 += b0 + b1; }
     sum0 += (double)acc0;
     if (LIK == BVG_NB) sum1 += (double)acc1;
     if (BWD) {
