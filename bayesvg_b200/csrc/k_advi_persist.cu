@@ -33,6 +33,7 @@
 #define PS_NW (TC_THREADS / 32)  // 12 warps
 #define PS_ROW 56                // 2k+10 <= 56 (k <= 23)
 #define PS_GROW 64               // row pitch of the block rows in global memory
+#define PS_NROWS 150             // rows per parity: gridDim.x <= 148 block rows, the rest stay zero (6 groups x 25 rows)
 #define PS_NSH 52                // 2k+5 <= 51
 #define PS_NPRE 24               // gene slots of a CTA's first item whose next normals are drawn ahead of the gene phase
 #define PS_KW 25                 // k + 2 <= 25 parameters per gene
@@ -308,28 +309,35 @@ k_advi_persist(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ 
             if (ahead && has) s.eps = (j == 0 && slot < PS_NPRE) ? S.nrm[slot * PS_KW + lane] : bvg_normal(m.seed, STREAM_GRAD, tg_next, global_index(g, lane));
           }
         };
-        auto process = [&](const GS &s) {
+        // the splits' partials of a gene (fixed order -> deterministic, k_gene's order): one pointer per array, bumped by a
+        // constant stride (the indexed form spent ~40 % of the gene phase's instructions on 64-bit address arithmetic)
+        auto fetch = [&](const GS &s, double &Pj, double &s0) {
+          Pj = 0; s0 = 0;
           if (s.g >= m.G) return;  // warp-uniform
           const int64_t g = s.g;
-          double Pj = 0, s0 = 0;
-          for (int sp0 = 0; sp0 < p.nsplit; sp0 += 8) {  // fixed order -> deterministic (k_gene's order)
+          const float *pp = Pp + g * KP + (lane < KP ? lane : KP - 1);
+          const double *sp_ = Sp + g * 2 + (lane & 1);
+          const int64_t pstride = m.Gpad * KP, sstride = m.Gpad * 2;
+          for (int sp0 = 0; sp0 < p.nsplit; sp0 += 8) {
             float pv[8];
             double sv[8];
-            const int lp = lane < KP ? lane : KP - 1, ls = lane & 1;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const int sp = sp0 + q < p.nsplit ? sp0 + q : p.nsplit - 1;
-              const int64_t row = (int64_t)sp * m.Gpad + g;
-              pv[q] = __ldcg(Pp + row * KP + lp);
-              sv[q] = __ldcg(Sp + row * 2 + ls);
-            }
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
               const bool ok = sp0 + q < p.nsplit;
-              Pj += (ok && lane < KP) ? (double)pv[q] : 0.0;
-              s0 += (ok && lane < 2) ? sv[q] : 0.0;
+              pv[q] = ok ? __ldcg(pp) : 0.f;
+              sv[q] = (ok && lane < 2) ? __ldcg(sp_) : 0.0;
+              if (ok) { pp += pstride; sp_ += sstride; }
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              Pj += lane < KP ? (double)pv[q] : 0.0;
+              s0 += sv[q];
             }
           }
+        };
+        auto process = [&](const GS &s, double Pj, double s0) {
+          if (s.g >= m.G) return;  // warp-uniform
+          const int64_t g = s.g;
           const double s1 = __shfl_sync(0xffffffffu, s0, 1);
           s0 = __shfl_sync(0xffffffffu, s0, 0);
           Pj *= inv_s2;
@@ -382,14 +390,19 @@ k_advi_persist(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ 
         if (lane == 0) wait_counter(p.tile_cnt + tile, target, p.timeout);
         __syncwarp();
         if (tr && i < 32 && j == 0) p.trace[i * 16 + 7] = clock64();
-        process(s0);
+        double P0, P1, q0s, q1s;
+        fetch(s0, P0, q0s);   // both genes' partials are in flight before either gene's arithmetic starts
+        fetch(s1, P1, q1s);
+        process(s0, P0, q0s);
         if (tr && i < 32 && j == 0) p.trace[i * 16 + 10] = clock64();
-        process(s1);
+        process(s1, P1, q1s);
         if (tr && i < 32 && j == 0) p.trace[i * 16 + 11] = clock64();
         for (int slot = warp + 2 * PS_NW; r_lo + slot < r_hi; slot += PS_NW) {
           GS s2;
+          double P2, q2s;
           load(slot, s2);
-          process(s2);
+          fetch(s2, P2, q2s);
+          process(s2, P2, q2s);
         }
       }
     }
@@ -409,7 +422,7 @@ k_advi_persist(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ 
     if (tr && i < 32) p.trace[i * 16 + 12] = clock64();
     __syncthreads();
     if (tr && i < 32) p.trace[i * 16 + 13] = clock64();
-    double *const grow = p.rows + (size_t)(i & 1) * ncta * PS_GROW;
+    double *const grow = p.rows + (size_t)(i & 1) * PS_NROWS * PS_GROW;
     if (tid < NS) {
       double s = 0;
 #pragma unroll
@@ -444,14 +457,13 @@ k_advi_persist(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ 
       const int c = tid & 63, grp = tid >> 6;
       double acc = 0;
       if (c < NS) {
-        double v[25];   // ncta <= 148: at most 25 rows per group, all in flight at once
+        // rows [ncta, 150) of the buffer are zero (set once): 25 rows per group at compile-time offsets, all loads in flight
+        const double *gp = grow + (size_t)grp * PS_GROW + c;
+        double v[25];
 #pragma unroll
-        for (int q = 0; q < 25; ++q) {
-          const int b = grp + 6 * q;
-          v[q] = __ldcg(grow + (size_t)(b < ncta ? b : cta) * PS_GROW + c);
-        }
+        for (int q = 0; q < 25; ++q) v[q] = __ldcg(gp + (size_t)q * 6 * PS_GROW);
 #pragma unroll
-        for (int q = 0; q < 25; ++q) acc += grp + 6 * q < ncta ? v[q] : 0.0;
+        for (int q = 0; q < 25; ++q) acc += v[q];
         SC->wrow[grp][c] = acc;
       }
     }
@@ -826,7 +838,7 @@ int launch_advi_persist(bvg_fit *f, int n_iter) {
   CUDA_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, f->cfg.device));
   if (!coop) { bvg_set_error("device does not support cooperative launches"); return BVG_ERR_STATE; }
   const int ntiles = (int)(m.Gpad / BVG_GENE_TILE), nitems = ntiles * m.nsplit;
-  const int ncta = std::min(nitems, nsm);
+  const int ncta = std::min(nitems, std::min(nsm, 148));   // PS_NROWS block rows per parity
   PersistBuf *b = (PersistBuf *)t->persist;
   if (b && (b->ntiles != ntiles || b->ncta != ncta)) { persist_destroy(f); b = nullptr; }
   if (!b) {
@@ -835,7 +847,8 @@ int launch_advi_persist(bvg_fit *f, int n_iter) {
     t->persist = b;
     b->ntiles = ntiles; b->ncta = ncta;
     CUDA_TRY(cudaMalloc(&b->cnt, sizeof(uint32_t) * (ntiles + 2)));
-    CUDA_TRY(cudaMalloc(&b->rows, sizeof(double) * 2 * (ncta + 1) * PS_GROW));
+    CUDA_TRY(cudaMalloc(&b->rows, sizeof(double) * 2 * (PS_NROWS + 1) * PS_GROW));
+    CUDA_TRY(cudaMemsetAsync(b->rows, 0, sizeof(double) * 2 * (PS_NROWS + 1) * PS_GROW, f->stream));
     CUDA_TRY(cudaMalloc(&b->trace, sizeof(long long) * (32 * 16 + 32 * 8 + 32 * 4)));
     CUDA_TRY(cudaFuncSetAttribute(k_advi_persist<BVG_GAUSSIAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
     CUDA_TRY(cudaFuncSetAttribute(k_advi_persist<BVG_NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
@@ -869,7 +882,7 @@ int launch_advi_persist(bvg_fit *f, int n_iter) {
   { const char *e = getenv("BVG_XCHG_ALL"); p.xchg_all = !(e && e[0] == '0'); }   // measured at 8 GPUs (profiles/README.md): every CTA polling is the faster form
   p.tile_cnt = b->cnt; p.grid_cnt = b->cnt + ntiles;
   p.rows = b->rows;
-  p.xtot = b->rows + (size_t)2 * ncta * PS_GROW;
+  p.xtot = b->rows + (size_t)2 * PS_NROWS * PS_GROW;
   p.xflag = b->cnt + ntiles + 1;
   p.timeout = 8000000000LL;  // ~4 s: longer than any legitimate wait inside one GPU
   if (m.peer.world > 1 && m.peer.timeout > p.timeout) p.timeout = 2 * m.peer.timeout;  // the rings idle while a peer is awaited
@@ -897,7 +910,7 @@ int launch_elbo_persist(bvg_fit *f, int S, double *d_lps) {
   CUDA_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, f->cfg.device));
   if (!coop) { bvg_set_error("device does not support cooperative launches"); return BVG_ERR_STATE; }
   const int ntiles = (int)(m.Gpad / BVG_GENE_TILE), nitems = ntiles * m.nsplit;
-  const int ncta = std::min(nitems, nsm);
+  const int ncta = std::min(nitems, std::min(nsm, 148));   // PS_NROWS block rows per parity
   PersistBuf *b = (PersistBuf *)t->persist;
   if (b && (b->ntiles != ntiles || b->ncta != ncta)) { persist_destroy(f); b = nullptr; }
   if (!b) {
@@ -906,7 +919,8 @@ int launch_elbo_persist(bvg_fit *f, int S, double *d_lps) {
     t->persist = b;
     b->ntiles = ntiles; b->ncta = ncta;
     CUDA_TRY(cudaMalloc(&b->cnt, sizeof(uint32_t) * (ntiles + 2)));
-    CUDA_TRY(cudaMalloc(&b->rows, sizeof(double) * 2 * (ncta + 1) * PS_GROW));
+    CUDA_TRY(cudaMalloc(&b->rows, sizeof(double) * 2 * (PS_NROWS + 1) * PS_GROW));
+    CUDA_TRY(cudaMemsetAsync(b->rows, 0, sizeof(double) * 2 * (PS_NROWS + 1) * PS_GROW, f->stream));
     CUDA_TRY(cudaMalloc(&b->trace, sizeof(long long) * (32 * 16 + 32 * 8 + 32 * 4)));
   }
   if (!b->attr_set) {
