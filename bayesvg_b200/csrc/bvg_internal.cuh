@@ -307,6 +307,9 @@ __device__ inline double bvg_lp_from_sums(const DevModel &m, const double *tot, 
   return lp + shw * lsh;
 }
 
+// trial point of the device-resident L-BFGS line search (lbfgs_dev.cu): k_prep forms zeta = x0 + *a * p itself when x0 != NULL
+struct LsPoint { const double *x0, *p, *a; };
+
 // ---- host-side fit object ---------------------------------------------------------------------
 struct NcclApi;
 struct bvg_fit {
@@ -358,6 +361,7 @@ struct bvg_fit {
   void *peer_map[BVG_MAX_PEERS];  // peers' buffers opened with cudaIpcOpenMemHandle
   bool no_persist;     // diagnostics / tests (BVG_NO_PERSIST=1): keep the two-launch evaluation chain instead of k_advi_persist
   void *shadow;        // fp64 evaluator of a fast-precision fit (fp64_shadow.cu), built when the L-BFGS line search hits the fast engines' noise floor
+  LsPoint ls;          // non-NULL x0 only while lbfgs_run_device() is enqueueing evaluations
   bool no_mle_fp64;    // diagnostics (BVG_NO_MLE_FP64=1): let the fast path's L-BFGS end with TERM_LSFAIL as in round 1
 };
 

@@ -11,7 +11,9 @@ struct LbfgsOpt {
   int jacobian = 0, propto = 0, max_iter = 0, history = 0;
   std::function<int(int it, const double *d_x, const double *d_g, double fval)> on_iterate;
 };
-int lbfgs_run(bvg_fit *f, const double *d_theta0, double *d_out, const LbfgsOpt *opt = nullptr);  // lbfgs.cu
+int lbfgs_run(bvg_fit *f, const double *d_theta0, double *d_out, const LbfgsOpt *opt = nullptr);  // lbfgs.cu (dispatch + host-driven form)
+bool lbfgs_device_ok(const bvg_fit *f, const LbfgsOpt *opt);                                       // lbfgs_dev.cu: control flow on the device
+int lbfgs_run_device(bvg_fit *f, const double *d_theta0, double *d_out, const LbfgsOpt *opt);
 
 template <typename SRC, typename DST>
 int stage_y(const SRC *src, DST *dst, int64_t M, int64_t ldY, int64_t ngenes, cudaStream_t st);

@@ -17,7 +17,7 @@
 // phase (Philox + Box-Muller in fp64 is a ~1000-cycle dependent chain; the first version chained
 // three of them per block).
 template <typename T>
-__global__ void __launch_bounds__(256) k_prep(DevModel m, int mode, int tc, int gpb) {
+__global__ void __launch_bounds__(256) k_prep(DevModel m, int mode, int tc, int gpb, LsPoint ls) {
   extern __shared__ double sh[];  // [2k+5] shared zeta | [k] sigma_alpha | [gpb][k+2] gene zeta | [gpb] A_g
   griddep_wait();    // mu / omega come from the previous evaluation's k_gene
   griddep_launch();
@@ -49,6 +49,9 @@ __global__ void __launch_bounds__(256) k_prep(DevModel m, int mode, int tc, int 
     double z;
     if (mode != PREP_NONE) {
       z = m.mu[li] + exp(m.omega[li]) * bvg_normal(m.seed, stream, t, (uint64_t)gi);
+      if (is_gene || blockIdx.x == 0) zeta_o[li] = z;
+    } else if (ls.x0) {  // trial point of the device-resident line search (lbfgs_dev.cu): x0 + a p, a read from the device
+      z = ls.x0[li] + *ls.a * ls.p[li];
       if (is_gene || blockIdx.x == 0) zeta_o[li] = z;
     } else {
       z = m.zeta[li];
@@ -90,7 +93,7 @@ __global__ void __launch_bounds__(256) k_prep(DevModel m, int mode, int tc, int 
 // k_prep_big: the same three phases for any k <= BVG_MAX_K (config 5: k ~ 400).  A block owns gpb genes and
 // walks its parameters in strides of the block size.
 template <typename T>
-__global__ void __launch_bounds__(256) k_prep_big(DevModel m, int mode, int gpb) {
+__global__ void __launch_bounds__(256) k_prep_big(DevModel m, int mode, int gpb, LsPoint ls) {
   extern __shared__ double sh[];  // [2k+5] shared zeta | [k] sigma_alpha | [gpb][k+2] gene zeta | [gpb] A_g
   griddep_wait();
   griddep_launch();
@@ -116,6 +119,9 @@ __global__ void __launch_bounds__(256) k_prep_big(DevModel m, int mode, int gpb)
     double z;
     if (mode != PREP_NONE) {
       z = m.mu[li] + exp(m.omega[li]) * bvg_normal(m.seed, stream, t, (uint64_t)gi);
+      if (!is_sh || blockIdx.x == 0) m.zeta[li] = z;
+    } else if (ls.x0) {  // trial point of the device-resident line search (lbfgs_dev.cu)
+      z = ls.x0[li] + *ls.a * ls.p[li];
       if (!is_sh || blockIdx.x == 0) m.zeta[li] = z;
     } else {
       z = m.zeta[li];
@@ -155,16 +161,16 @@ int launch_prep(bvg_fit *f, int mode) {
     const int gpb = std::max(1, std::min(8, 512 / (k + 2)));
     const int grid = (int)((f->m.G + gpb - 1) / gpb);
     const size_t sh = sizeof(double) * (3 * k + 5 + gpb * (k + 3));
-    if (f->cfg.precision == BVG_PREC_FP64) CUDA_TRY(launch_pdl(k_prep_big<double>, dim3(grid), dim3(256), sh, f->stream, f->m, mode, gpb));
-    else CUDA_TRY(launch_pdl(k_prep_big<float>, dim3(grid), dim3(256), sh, f->stream, f->m, mode, gpb));
+    if (f->cfg.precision == BVG_PREC_FP64) CUDA_TRY(launch_pdl(k_prep_big<double>, dim3(grid), dim3(256), sh, f->stream, f->m, mode, gpb, f->ls));
+    else CUDA_TRY(launch_pdl(k_prep_big<float>, dim3(grid), dim3(256), sh, f->stream, f->m, mode, gpb, f->ls));
     f->st.kernel_launches++;
     return BVG_OK;
   }
   const int gpb = (256 - (2 * k + 5)) / (k + 2);
   const int grid = (int)((f->m.G + gpb - 1) / gpb);
   const size_t sh = sizeof(double) * (3 * k + 5 + gpb * (k + 3));
-  if (f->cfg.precision == BVG_PREC_FP64) CUDA_TRY(launch_pdl(k_prep<double>, dim3(grid), dim3(256), sh, f->stream, f->m, mode, 0, gpb));
-  else CUDA_TRY(launch_pdl(k_prep<float>, dim3(grid), dim3(256), sh, f->stream, f->m, mode, (int)(f->engine == BVG_ENGINE_TCGEN05 && !f->big_tc), gpb));
+  if (f->cfg.precision == BVG_PREC_FP64) CUDA_TRY(launch_pdl(k_prep<double>, dim3(grid), dim3(256), sh, f->stream, f->m, mode, 0, gpb, f->ls));
+  else CUDA_TRY(launch_pdl(k_prep<float>, dim3(grid), dim3(256), sh, f->stream, f->m, mode, (int)(f->engine == BVG_ENGINE_TCGEN05 && !f->big_tc), gpb, f->ls));
   f->st.kernel_launches++;
   return BVG_OK;
 }
@@ -177,7 +183,7 @@ int launch_prep_batch(bvg_fit *f, int mode, int B) {
   const int gpb = (256 - (2 * k + 5)) / (k + 2);
   const int grid = (int)((f->m.G + gpb - 1) / gpb);
   const size_t sh = sizeof(double) * (3 * k + 5 + gpb * (k + 3));
-  CUDA_TRY(launch_pdl(k_prep<float>, dim3(grid, B), dim3(256), sh, f->stream, f->m, mode, 1, gpb));
+  CUDA_TRY(launch_pdl(k_prep<float>, dim3(grid, B), dim3(256), sh, f->stream, f->m, mode, 1, gpb, LsPoint{nullptr, nullptr, nullptr}));
   f->st.kernel_launches++;
   return BVG_OK;
 }

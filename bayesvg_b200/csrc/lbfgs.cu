@@ -97,6 +97,7 @@ int wolfe(const EvalFn &ev, double *alpha, double *f1, double *dg1, double f0, d
 // opt (optional): jacobian / propto of the objective, iteration cap, and a callback that sees the initial point (it = 0)
 // and every accepted iterate (device x, device gradient of f = -lp, f) -- Pathfinder builds its approximations there.
 int lbfgs_run(bvg_fit *f, const double *d_theta0, double *d_out, const LbfgsOpt *opt) {
+  if (lbfgs_device_ok(f, opt)) return lbfgs_run_device(f, d_theta0, d_out, opt);  // no host round trip per evaluation (lbfgs_dev.cu)
   const DevModel &m = f->m;
   const int64_t D = m.L.D;
   const int jac = opt ? opt->jacobian : 0, propto = opt ? opt->propto : 0;
