@@ -337,6 +337,8 @@ static int set_y_impl(bvg_fit *f, const SRC *y, int64_t M, int64_t G) {
     for (int b = 0; b < 2; ++b) { CUDA_TRY(cudaEventCreateWithFlags(&f->ev_copied[b], cudaEventDisableTiming)); CUDA_TRY(cudaEventCreateWithFlags(&f->ev_staged[b], cudaEventDisableTiming)); }
   }
   CUDA_TRY(cudaStreamSynchronize(f->stream));  // earlier work on the compute stream no longer reads Y
+  const bool timing = getenv("BVG_TIMING") != nullptr;
+  const double t_alloc = now_s();
   int64_t ci = 0;
   for (int64_t g0 = 0; g0 < G; g0 += genes_per_chunk, ++ci) {
     const int b = (int)(ci & 1);
@@ -382,8 +384,11 @@ static int set_y_impl(bvg_fit *f, const SRC *y, int64_t M, int64_t G) {
     f->m.hterm = nullptr;
   }
   CUDA_TRY(cudaStreamSynchronize(f->stream));
+  const double t_copy = now_s();
   if (!reuse) BVG_TRY(finalize_model(f));
   else suff_destroy(f);  // sufficient statistics belong to the previous Y
+  if (timing) fprintf(stderr, "set_y: allocations %.1f ms, copy + staging of %.1f MB %.1f ms, finalize_model %.1f ms\n", 1e3 * (t_alloc - t0),
+                      (double)(sizeof(SRC) * M * G) / 1e6, 1e3 * (t_copy - t_alloc), 1e3 * (now_s() - t_copy));
   // nb, tcgen05 engine: the per-count lgamma / digamma terms are evaluated by 31 idle lanes per likelihood CTA --
   // only when there is a lane for every distinct count; otherwise k_gene's finish evaluates them itself
   if (f->cfg.likelihood == BVG_NB && f->engine == BVG_ENGINE_TCGEN05 && !f->big_tc &&

@@ -435,8 +435,11 @@ k_advi_persist(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ 
     if (tid == 0) {
       red_release_add(p.grid_cnt, 1u);
       if (tr && i < 32) p.trace[i * 16 + 15] = clock64();
-      wait_counter(p.grid_cnt, (uint32_t)ncta * (uint32_t)(i + 1), p.timeout);
     }
+    // while the other CTAs arrive: the normals the NEXT gene phase and the next shared update will use (the gene phase of
+    // this iteration has finished with S.nrm; buffer (i + 1) & 1 of the shared normals was last read one iteration ago)
+    if (i + 2 < p.n_iter) draw_normals(tg0 + (uint32_t)i + 2u, (i + 1) & 1, tid, TC_THREADS);
+    if (tid == 0) wait_counter(p.grid_cnt, (uint32_t)ncta * (uint32_t)(i + 1), p.timeout);
     __syncthreads();
     if (tr && i < 32) p.trace[i * 16 + 3] = clock64();
 
@@ -555,8 +558,6 @@ k_advi_persist(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ 
         S.st[0][ut] = p_mu; S.st[1][ut] = p_om; S.st[2][ut] = p_hm; S.st[3][ut] = p_ho;
         if (ahead) zn = p_mu + exp(p_om) * S.nrm_sh[i & 1][ut];
       }
-    } else if (i + 2 < p.n_iter) {
-      draw_normals(tg0 + (uint32_t)i + 2u, (i + 1) & 1, (warp < 2 ? warp : warp - 1) * 32 + lane, PS_NRM_LANES);
     }
     __syncthreads();  // every thread has read this evaluation's shared draw
     if (ahead && upd_warp && ut < NSH) {
