@@ -319,6 +319,7 @@ def extra_blocks_n1(args, local_rank, phi_cfg2, Y_cfg2):
     phi1 = bvg.basis_build(X1, C1, length_scale_kmeans(C1), "matern", 2.5, device=local_rank)
     t_basis = time.perf_counter() - t0
     Y1, amp1 = synth.expression(phi1, G_GENES, "gaussian", 312)
+    time.sleep(0.5)   # as above: let the generator's BLAS threads park before the timed fit
     t0 = time.perf_counter()
     f = bvg.Fit(phi1, Y1, "gaussian", "fast", args.engine, **cfg)
     tab = f.run()
@@ -506,6 +507,7 @@ def run_ours(args, rank, world, local_rank):
         phif = bvg.basis_build(Xf, Cf, length_scale_kmeans(Cf), "matern", 2.5, device=local_rank)
         t_kb = time.perf_counter() - t0
         Yf, _ = synth.expression(phif, G_GENES, "gaussian", 312)
+        time.sleep(0.5)   # the synthetic generator's BLAS worker threads park (they spin for a while after a matmul and slow every host call that follows)
         t0 = time.perf_counter()
         f3 = bvg.Fit(phif, Yf, "gaussian", "fast", args.engine, **cfg)
         f3.run()
