@@ -34,6 +34,7 @@
 #define PS_ROW 56                // 2k+10 <= 56 (k <= 23)
 #define PS_GROW 64               // row pitch of the block rows in global memory
 #define PS_NROWS 150             // rows per parity: gridDim.x <= 148 block rows, the rest stay zero (6 groups x 25 rows)
+#define PS_FX (2 * PS_GROW + 8)  // per buffer: 64 high words, 64 low words, poison mask
 #define PS_NSH 52                // 2k+5 <= 51
 #define PS_NPRE 24               // gene slots of a CTA's first item whose next normals are drawn ahead of the gene phase
 #define PS_KW 25                 // k + 2 <= 25 parameters per gene
@@ -49,6 +50,7 @@ struct PersistArgs {
   uint32_t *grid_cnt;               // [1]
   double *rows;                     // [2 parities][gridDim.x][PS_GROW] block rows of the cross-gene sums
   double *xtot;                     // [2 parities][PS_GROW] multi-GPU: the exchanged totals, published by CTA 0
+  unsigned long long *fx;           // [3][PS_FX] fixed-point accumulators of the cross-gene sums (see the grid meeting)
   uint32_t *xflag;                  // [1] multi-GPU: iterations whose totals CTA 0 has published
   long long timeout;                // SM cycles any intra-GPU wait may last before the kernel traps
   long long *trace;                 // optional [32 iterations][8] clock64 stamps of CTA 0, then [32 chunks][8] of the pass of iteration 8 (diagnostics)
@@ -422,12 +424,27 @@ k_advi_persist(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ 
     if (tr && i < 32) p.trace[i * 16 + 12] = clock64();
     __syncthreads();
     if (tr && i < 32) p.trace[i * 16 + 13] = clock64();
-    double *const grow = p.rows + (size_t)(i & 1) * PS_NROWS * PS_GROW;
+    // The block rows meet in FIXED-POINT accumulators: every CTA adds its row with two 64-bit integer reductions per sum
+    // (value = hi * 2^-20 + lo * 2^-72, |value| < 2^42, lo < 2^52 so that thousands of low words cannot overflow).  Integer
+    // addition commutes, so the totals are bit-reproducible whatever the order of arrival -- like the fixed-order sum of 148
+    // rows they replace -- and after the meeting a CTA reads 2 x (2k+10) words instead of 148 rows (the reduction went
+    // from 4.4 k to ~1 k cycles at cfg2).  A sum that is not finite or out of range poisons its column (-> NaN, which the
+    // update treats as any non-finite gradient).  Three buffers: CTA 0 clears the next one before it arrives.
+    unsigned long long *const fxb = p.fx + (size_t)(i % 3) * PS_FX;
     if (tid < NS) {
       double s = 0;
 #pragma unroll
       for (int w = 0; w < PS_NW; ++w) s += SC->wrow[w][tid];
-      grow[(size_t)cta * PS_GROW + tid] = s;
+      if (fabs(s) < 4398046511104.0) {   // 2^42 (false for NaN)
+        const double sc = s * 1048576.0, fl = floor(sc);
+        const unsigned long long hi = (unsigned long long)(long long)fl, lo = (unsigned long long)((sc - fl) * 4503599627370496.0);
+        asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(fxb + tid), "l"(hi) : "memory");
+        asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(fxb + PS_GROW + tid), "l"(lo) : "memory");
+      } else {
+        asm volatile("red.relaxed.gpu.global.or.b64 [%0], %1;" ::"l"(fxb + 2 * PS_GROW), "l"(1ull << tid) : "memory");
+      }
+    } else if (cta == 0 && tid >= 64 && tid < 64 + 2 * PS_GROW + 1) {
+      p.fx[(size_t)((i + 1) % 3) * PS_FX + (tid - 64)] = 0ull;   // last read two iterations ago; next written after this meeting
     }
     // grid-wide arrival counter (all CTAs are co-resident: cooperative launch)
     __syncthreads();
@@ -454,27 +471,12 @@ k_advi_persist(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ 
       wAg = __ldcg(a.W + g * TC_KW + k + 1);
     }
     const bool reducer = m.peer.world <= 1 || cta == 0 || p.xchg_all;  // multi-GPU: only CTA 0 needs the local sums (it exchanges and publishes the totals)
-    if (reducer) {
-      // 6 groups of 64 threads: group q sums rows q, q + 6, ... (all loads of a thread in flight at once), then a fixed
-      // six-term sum per column
-      const int c = tid & 63, grp = tid >> 6;
-      double acc = 0;
-      if (c < NS) {
-        // rows [ncta, 150) of the buffer are zero (set once): 25 rows per group at compile-time offsets, all loads in flight
-        const double *gp = grow + (size_t)grp * PS_GROW + c;
-        double v[25];
-#pragma unroll
-        for (int q = 0; q < 25; ++q) v[q] = __ldcg(gp + (size_t)q * 6 * PS_GROW);
-#pragma unroll
-        for (int q = 0; q < 25; ++q) acc += v[q];
-        SC->wrow[grp][c] = acc;
-      }
-    }
-    __syncthreads();
     if (reducer && tid < NS) {
-      double t = 0;
-#pragma unroll
-      for (int q = 0; q < 6; ++q) t += SC->wrow[q][tid];
+      const unsigned long long H = __ldcg(fxb + tid), Lw = __ldcg(fxb + PS_GROW + tid), poison = __ldcg(fxb + 2 * PS_GROW);
+      const long long hi = (long long)H + (long long)(Lw >> 52);
+      const unsigned long long lo = Lw & ((1ull << 52) - 1ull);
+      double t = (double)hi * (1.0 / 1048576.0) + (double)lo * (1.0 / 4722366482869645213696.0);   // 2^-20, 2^-72
+      if ((poison >> tid) & 1ull) t = __longlong_as_double(0x7ff8000000000000LL);
       if (LIK == BVG_NB && tid == S_LG) t -= m.lgam_y1;
       S.tot[tid] = t;
     }
@@ -795,6 +797,7 @@ k_elbo_persist(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ 
 struct PersistBuf {
   uint32_t *cnt;    // [ntiles] tile counters, grid counter, exchange flag
   double *rows;     // [2][ncta][PS_GROW] block rows, then [2][PS_GROW] exchanged totals
+  unsigned long long *fx;  // [3][PS_FX] fixed-point accumulators of k_advi_persist's grid meeting
   long long *trace; // [32][8]
   double *erows;    // ELBO mode: [S][ncta][8]
   int erows_cap;
@@ -810,6 +813,7 @@ void persist_destroy(bvg_fit *f) {
   PersistBuf *b = (PersistBuf *)t->persist;
   cudaFree(b->cnt);
   cudaFree(b->rows);
+  cudaFree(b->fx);
   cudaFree(b->trace);
   cudaFree(b->erows);
   delete b;
@@ -862,6 +866,8 @@ int launch_advi_persist(bvg_fit *f, int n_iter) {
     if (occ < 1) { bvg_set_error("persistent ADVI kernel does not fit an SM"); return BVG_ERR_STATE; }
   }
   CUDA_TRY(cudaMemsetAsync(b->cnt, 0, sizeof(uint32_t) * (ntiles + 2), f->stream));
+  if (!b->fx) CUDA_TRY(cudaMalloc(&b->fx, sizeof(unsigned long long) * 3 * PS_FX));
+  CUDA_TRY(cudaMemsetAsync(b->fx, 0, sizeof(unsigned long long) * 3 * PS_FX, f->stream));
   PersistArgs p;
   memset(&p, 0, sizeof(p));
   TcArgs &a = p.a;
@@ -883,6 +889,7 @@ int launch_advi_persist(bvg_fit *f, int n_iter) {
   { const char *e = getenv("BVG_XCHG_ALL"); p.xchg_all = !(e && e[0] == '0'); }   // measured at 8 GPUs (profiles/README.md): every CTA polling is the faster form
   p.tile_cnt = b->cnt; p.grid_cnt = b->cnt + ntiles;
   p.rows = b->rows;
+  p.fx = b->fx;
   p.xtot = b->rows + (size_t)2 * PS_NROWS * PS_GROW;
   p.xflag = b->cnt + ntiles + 1;
   p.timeout = 8000000000LL;  // ~4 s: longer than any legitimate wait inside one GPU
