@@ -24,6 +24,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 
 #include "bvg_vec.cuh"
@@ -178,18 +179,18 @@ __device__ void lb_ls_failed(LbDev &s) {
 __global__ void k_lb_begin(LbDev *s) { lb_ls_begin(*s); s->phase = PH_LS; }
 
 // After an accepted step: x0 <- x1, g0 <- g1 (the gradient row of the basis; k_lb_dots has read the old ones).  With a new
-// direction: p = sum of the active basis rows {s_i, y_i, g} times their coefficients (sixteen rows in flight per thread).
+// direction: p = sum of the active basis rows {s_i, y_i, g} times their coefficients (32 rows in flight per thread).
 __global__ void __launch_bounds__(256) k_lb_dir(LbDev *s, double *__restrict__ p, double *B, double *__restrict__ x0,
                                                 const double *__restrict__ x1, const double *__restrict__ grad1, int64_t D) {
-  __shared__ int sidx[LB_NB + 15];
-  __shared__ double scoef[LB_NB + 15];
+  __shared__ int sidx[LB_NB + 31];
+  __shared__ double scoef[LB_NB + 31];
   __shared__ int s_last;
   griddep_wait();     // programmatic dependent launch: this grid's launch latency hides under the previous kernel
   griddep_launch();
   const bool upd = s->n_accept != s->n_applied, fresh = s->phase == PH_LS && s->fresh_dir;
   if (!upd && !fresh) return;
   const int nact = fresh ? s->nact : 0, rg = 2 * s->mh;
-  if (threadIdx.x < LB_NB + 15) {
+  if (threadIdx.x < LB_NB + 31) {
     const bool ok = (int)threadIdx.x < nact;
     sidx[threadIdx.x] = ok ? s->act_idx[threadIdx.x] : rg;
     scoef[threadIdx.x] = ok ? s->act_coef[threadIdx.x] : 0.0;
@@ -201,12 +202,12 @@ __global__ void __launch_bounds__(256) k_lb_dir(LbDev *s, double *__restrict__ p
     if (upd) { gn = -grad1[i]; x0[i] = x1[i]; g0[i] = gn; }
     if (!fresh) continue;
     double pi = 0;
-    for (int r0 = 0; r0 < nact; r0 += 16) {
-      double bv[16];
+    for (int r0 = 0; r0 < nact; r0 += 32) {
+      double bv[32];
 #pragma unroll
-      for (int q = 0; q < 16; ++q) bv[q] = __ldcg(B + (int64_t)sidx[r0 + q] * D + i);
+      for (int q = 0; q < 32; ++q) bv[q] = __ldcg(B + (int64_t)sidx[r0 + q] * D + i);
 #pragma unroll
-      for (int q = 0; q < 16; ++q) pi += scoef[r0 + q] * ((upd && sidx[r0 + q] == rg) ? gn : bv[q]);   // the g row was just replaced by this thread
+      for (int q = 0; q < 32; ++q) pi += scoef[r0 + q] * ((upd && sidx[r0 + q] == rg) ? gn : bv[q]);   // the g row was just replaced by this thread
     }
     p[i] = pi;
   }
@@ -513,7 +514,12 @@ bool lbfgs_device_ok(const bvg_fit *f, const LbfgsOpt *opt) {
   return true;
 }
 
+static double lb_now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
 int lbfgs_run_device(bvg_fit *f, const double *d_theta0, double *d_out, const LbfgsOpt *opt) {
+  const double t_enter = lb_now();
+  double t_setup = 0, t_loop = 0, t_waited = 0;
+  int n_batches = 0;
   const DevModel &m = f->m;
   const int64_t D = m.L.D;
   const int jac = opt ? opt->jacobian : 0, propto = opt ? opt->propto : 0;
@@ -597,6 +603,7 @@ int lbfgs_run_device(bvg_fit *f, const double *d_theta0, double *d_out, const Lb
       CUDA_TRY(cudaGetLastError());
       return BVG_OK;
     };
+    t_setup = lb_now();
     const long long max_ticks = (long long)max_iter * 64 + 4096;
     long long ticks = 0;
     bool pending[2] = {false, false};
@@ -612,7 +619,11 @@ int lbfgs_run_device(bvg_fit *f, const double *d_theta0, double *d_out, const Lb
       const int prev = slot ^ 1;
       slot ^= 1;
       if (!pending[prev]) continue;
-      if (cudaEventSynchronize(evt[prev]) != cudaSuccess) { delete h; bvg_set_error("L-BFGS: device error in the search"); return fail(BVG_ERR_CUDA); }
+      ++n_batches;
+      const double tw0 = lb_now();
+      const cudaError_t es_ = cudaEventSynchronize(evt[prev]);
+      t_waited += lb_now() - tw0;
+      if (es_ != cudaSuccess) { delete h; bvg_set_error("L-BFGS: device error in the search"); return fail(BVG_ERR_CUDA); }
       pending[prev] = false;
       const LbStat &s = h_stat[prev];
       if (s.phase == PH_DONE) { done = true; break; }
@@ -638,6 +649,7 @@ int lbfgs_run_device(bvg_fit *f, const double *d_theta0, double *d_out, const Lb
       if (ticks > max_ticks) { delete h; bvg_set_error("L-BFGS: the device-resident search did not terminate"); return fail(BVG_ERR_STATE); }
     }
     cudaError_t e3 = cudaStreamSynchronize(st);
+    t_loop = lb_now();
     if (e3 == cudaSuccess) e3 = cudaMemcpy(h, dev, sizeof(LbDev), cudaMemcpyDeviceToHost);
     if (e3 != cudaSuccess) { delete h; bvg_set_error("L-BFGS: %s", cudaGetErrorString(e3)); return fail(BVG_ERR_CUDA); }
     term = h->term; it = h->it; fk = h->fk; switch_iter = h->switch_iter;
@@ -655,6 +667,9 @@ int lbfgs_run_device(bvg_fit *f, const double *d_theta0, double *d_out, const Lb
   f->st.mle_fp64_from = switch_iter;
   f->st.mle_lp = -fk;
   cleanup();
+  if (const char *e = getenv("BVG_LBFGS_TRACE")) if (e[0] == '1')
+    fprintf(stderr, "lbfgs_run_device: setup %.2f ms, loop %.2f ms (%d batches, %.2f ms of it waiting for the device), teardown %.2f ms\n",
+            1e3 * (t_setup - t_enter), 1e3 * (t_loop - t_setup), n_batches, 1e3 * t_waited, 1e3 * (lb_now() - t_loop));
   return BVG_OK;
 #undef LB_CUDA
 #undef LB_TRY
