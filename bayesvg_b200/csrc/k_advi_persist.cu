@@ -34,7 +34,7 @@
 #define PS_ROW 56                // 2k+10 <= 56 (k <= 23)
 #define PS_GROW 64               // row pitch of the block rows in global memory
 #define PS_NROWS 150             // rows per parity: gridDim.x <= 148 block rows, the rest stay zero (6 groups x 25 rows)
-#define PS_FX (2 * PS_GROW + 8)  // per buffer: 64 high words, 64 low words, poison mask
+#define PS_FX (3 * PS_GROW + 8)  // per buffer: three limbs of 64 words, poison word
 #define PS_NSH 52                // 2k+5 <= 51
 #define PS_NPRE 24               // gene slots of a CTA's first item whose next normals are drawn ahead of the gene phase
 #define PS_KW 25                 // k + 2 <= 25 parameters per gene
@@ -51,6 +51,8 @@ struct PersistArgs {
   double *rows;                     // [2 parities][gridDim.x][PS_GROW] block rows of the cross-gene sums
   double *xtot;                     // [2 parities][PS_GROW] multi-GPU: the exchanged totals, published by CTA 0
   unsigned long long *fx;           // [3][PS_FX] fixed-point accumulators of the cross-gene sums (see the grid meeting)
+  uint32_t *grid_cnt2;              // [1] second meeting of an iteration whose sums left the accumulators' range
+  int force_rows;                   // tests (BVG_PERSIST_FORCE_ROWS=1): always take that second form
   uint32_t *xflag;                  // [1] multi-GPU: iterations whose totals CTA 0 has published
   long long timeout;                // SM cycles any intra-GPU wait may last before the kernel traps
   long long *trace;                 // optional [32 iterations][8] clock64 stamps of CTA 0, then [32 chunks][8] of the pass of iteration 8 (diagnostics)
@@ -122,6 +124,7 @@ k_advi_persist(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ 
   const double eta = m.ctl->eta;
   uint32_t xseq = m.peer.world > 1 ? *m.peer.seq : 0u;
   bool peer_dead = false;
+  int nfallback = 0;   // iterations of this launch whose sums met as rows (uniform over the grid)
 
   const int nmy = cta < p.nitems ? (p.nitems - cta + ncta - 1) / ncta : 0;
   auto item_geom = [&](int j, int &tile, int &split, int &c_begin, int &n) {
@@ -424,26 +427,33 @@ k_advi_persist(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ 
     if (tr && i < 32) p.trace[i * 16 + 12] = clock64();
     __syncthreads();
     if (tr && i < 32) p.trace[i * 16 + 13] = clock64();
-    // The block rows meet in FIXED-POINT accumulators: every CTA adds its row with two 64-bit integer reductions per sum
-    // (value = hi * 2^-20 + lo * 2^-72, |value| < 2^42, lo < 2^52 so that thousands of low words cannot overflow).  Integer
-    // addition commutes, so the totals are bit-reproducible whatever the order of arrival -- like the fixed-order sum of 148
-    // rows they replace -- and after the meeting a CTA reads 2 x (2k+10) words instead of 148 rows (the reduction went
-    // from 4.4 k to ~1 k cycles at cfg2).  A sum that is not finite or out of range poisons its column (-> NaN, which the
-    // update treats as any non-finite gradient).  Three buffers: CTA 0 clears the next one before it arrives.
+    // The block rows meet in FIXED-POINT accumulators: every CTA adds its row with three 64-bit integer reductions per sum
+    // (value * 2^72 = l2 * 2^104 + l1 * 2^52 + l0 with signed 52-bit limbs: |value| < 2^84, resolution 2^-72, and thousands of
+    // limbs cannot overflow a 64-bit word).  Integer addition commutes, so the totals are bit-reproducible whatever the order of
+    // arrival -- like the fixed-order sum of 148 rows they replace -- and after the meeting a CTA reads 3 x (2k+10) words
+    // instead of 148 rows (the reduction went from 4.4 k to ~1.7 k cycles at cfg2).  A sum that is not finite or out of that
+    // range (a diverging step-size trial of adapt_eta) sets the poison word: then every CTA publishes its row as before and
+    // the rows are added after a second meeting (the same answer as ever, just slower).  Three buffers: CTA 0 clears the next
+    // one before it arrives.
     unsigned long long *const fxb = p.fx + (size_t)(i % 3) * PS_FX;
     if (tid < NS) {
       double s = 0;
 #pragma unroll
       for (int w = 0; w < PS_NW; ++w) s += SC->wrow[w][tid];
-      if (fabs(s) < 4398046511104.0) {   // 2^42 (false for NaN)
-        const double sc = s * 1048576.0, fl = floor(sc);
-        const unsigned long long hi = (unsigned long long)(long long)fl, lo = (unsigned long long)((sc - fl) * 4503599627370496.0);
-        asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(fxb + tid), "l"(hi) : "memory");
-        asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(fxb + PS_GROW + tid), "l"(lo) : "memory");
+      if (fabs(s) < 19342813113834066795298816.0 && !p.force_rows) {   // 2^84 (false for NaN)
+        // signed limbs, truncated towards zero: every remainder is the exact low part of the value
+        const double a2 = trunc(s * (1.0 / 4294967296.0));            // units of 2^32
+        const double r1 = (s - a2 * 4294967296.0) * 1048576.0;        // |r1| < 2^52: units of 2^-20, exact
+        const double a1 = trunc(r1);
+        const unsigned long long l2 = (unsigned long long)(long long)a2, l1 = (unsigned long long)(long long)a1,
+                                 l0 = (unsigned long long)(long long)((r1 - a1) * 4503599627370496.0);   // units of 2^-72, truncated
+        asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(fxb + tid), "l"(l2) : "memory");
+        asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(fxb + PS_GROW + tid), "l"(l1) : "memory");
+        asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(fxb + 2 * PS_GROW + tid), "l"(l0) : "memory");
       } else {
-        asm volatile("red.relaxed.gpu.global.or.b64 [%0], %1;" ::"l"(fxb + 2 * PS_GROW), "l"(1ull << tid) : "memory");
+        asm volatile("red.relaxed.gpu.global.or.b64 [%0], %1;" ::"l"(fxb + 3 * PS_GROW), "l"(1ull << tid) : "memory");
       }
-    } else if (cta == 0 && tid >= 64 && tid < 64 + 2 * PS_GROW + 1) {
+    } else if (cta == 0 && tid >= 64 && tid < 64 + 3 * PS_GROW + 1) {
       p.fx[(size_t)((i + 1) % 3) * PS_FX + (tid - 64)] = 0ull;   // last read two iterations ago; next written after this meeting
     }
     // grid-wide arrival counter (all CTAs are co-resident: cooperative launch)
@@ -471,14 +481,51 @@ k_advi_persist(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ 
       wAg = __ldcg(a.W + g * TC_KW + k + 1);
     }
     const bool reducer = m.peer.world <= 1 || cta == 0 || p.xchg_all;  // multi-GPU: only CTA 0 needs the local sums (it exchanges and publishes the totals)
-    if (reducer && tid < NS) {
-      const unsigned long long H = __ldcg(fxb + tid), Lw = __ldcg(fxb + PS_GROW + tid), poison = __ldcg(fxb + 2 * PS_GROW);
-      const long long hi = (long long)H + (long long)(Lw >> 52);
-      const unsigned long long lo = Lw & ((1ull << 52) - 1ull);
-      double t = (double)hi * (1.0 / 1048576.0) + (double)lo * (1.0 / 4722366482869645213696.0);   // 2^-20, 2^-72
-      if ((poison >> tid) & 1ull) t = __longlong_as_double(0x7ff8000000000000LL);
-      if (LIK == BVG_NB && tid == S_LG) t -= m.lgam_y1;
-      S.tot[tid] = t;
+    unsigned long long L2 = 0, L1 = 0, L0 = 0, pw = 0;
+    if (tid < NS) {   // limbs and poison word in one round trip
+      L2 = __ldcg(fxb + tid); L1 = __ldcg(fxb + PS_GROW + tid); L0 = __ldcg(fxb + 2 * PS_GROW + tid);
+      pw = __ldcg(fxb + 3 * PS_GROW);
+    }
+    const int poison = __syncthreads_or(pw != 0ull);   // the same word in every CTA: a uniform decision
+    if (!poison) {
+      if (reducer && tid < NS) {
+        double t = (double)(long long)L0 * (1.0 / 4722366482869645213696.0) + (double)(long long)L1 * (1.0 / 1048576.0);   // 2^-72, 2^-20
+        t += (double)(long long)L2 * 4294967296.0;
+        if (LIK == BVG_NB && tid == S_LG) t -= m.lgam_y1;
+        S.tot[tid] = t;
+      }
+    } else {
+      // out of the accumulators' range, or not finite: the rows themselves meet (round 2's first form of this reduction)
+      double *const grow = p.rows;
+      if (tid < NS) {
+        double s = 0;
+#pragma unroll
+        for (int w = 0; w < PS_NW; ++w) s += SC->wrow[w][tid];
+        grow[(size_t)cta * PS_GROW + tid] = s;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        red_release_add(p.grid_cnt2, 1u);
+        wait_counter(p.grid_cnt2, (uint32_t)ncta * (uint32_t)(nfallback + 1), p.timeout);
+      }
+      ++nfallback;
+      __syncthreads();
+      if (reducer) {
+        const int c = tid & 63, grp = tid >> 6;
+        if (c < NS) {
+          double acc = 0;
+          for (int b = grp; b < ncta; b += 6) acc += __ldcg(grow + (size_t)b * PS_GROW + c);
+          SC->wrow[grp][c] = acc;   // every thread of this CTA has read its own rows (barrier above)
+        }
+      }
+      __syncthreads();
+      if (reducer && tid < NS) {
+        double t = 0;
+#pragma unroll
+        for (int q = 0; q < 6; ++q) t += SC->wrow[q][tid];
+        if (LIK == BVG_NB && tid == S_LG) t -= m.lgam_y1;
+        S.tot[tid] = t;
+      }
     }
     __syncthreads();
     if (m.peer.world > 1) {
@@ -851,7 +898,7 @@ int launch_advi_persist(bvg_fit *f, int n_iter) {
     memset(b, 0, sizeof(*b));
     t->persist = b;
     b->ntiles = ntiles; b->ncta = ncta;
-    CUDA_TRY(cudaMalloc(&b->cnt, sizeof(uint32_t) * (ntiles + 2)));
+    CUDA_TRY(cudaMalloc(&b->cnt, sizeof(uint32_t) * (ntiles + 4)));
     CUDA_TRY(cudaMalloc(&b->rows, sizeof(double) * 2 * (PS_NROWS + 1) * PS_GROW));
     CUDA_TRY(cudaMemsetAsync(b->rows, 0, sizeof(double) * 2 * (PS_NROWS + 1) * PS_GROW, f->stream));
     CUDA_TRY(cudaMalloc(&b->trace, sizeof(long long) * (32 * 16 + 32 * 8 + 32 * 4)));
@@ -865,7 +912,7 @@ int launch_advi_persist(bvg_fit *f, int n_iter) {
     else CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_advi_persist<BVG_NB>, TC_THREADS, TC_SMEM_BYTES));
     if (occ < 1) { bvg_set_error("persistent ADVI kernel does not fit an SM"); return BVG_ERR_STATE; }
   }
-  CUDA_TRY(cudaMemsetAsync(b->cnt, 0, sizeof(uint32_t) * (ntiles + 2), f->stream));
+  CUDA_TRY(cudaMemsetAsync(b->cnt, 0, sizeof(uint32_t) * (ntiles + 4), f->stream));
   if (!b->fx) CUDA_TRY(cudaMalloc(&b->fx, sizeof(unsigned long long) * 3 * PS_FX));
   CUDA_TRY(cudaMemsetAsync(b->fx, 0, sizeof(unsigned long long) * 3 * PS_FX, f->stream));
   PersistArgs p;
@@ -890,6 +937,8 @@ int launch_advi_persist(bvg_fit *f, int n_iter) {
   p.tile_cnt = b->cnt; p.grid_cnt = b->cnt + ntiles;
   p.rows = b->rows;
   p.fx = b->fx;
+  p.grid_cnt2 = b->cnt + ntiles + 2;
+  { const char *e = getenv("BVG_PERSIST_FORCE_ROWS"); p.force_rows = e && e[0] == '1'; }
   p.xtot = b->rows + (size_t)2 * PS_NROWS * PS_GROW;
   p.xflag = b->cnt + ntiles + 1;
   p.timeout = 8000000000LL;  // ~4 s: longer than any legitimate wait inside one GPU
@@ -926,7 +975,7 @@ int launch_elbo_persist(bvg_fit *f, int S, double *d_lps) {
     memset(b, 0, sizeof(*b));
     t->persist = b;
     b->ntiles = ntiles; b->ncta = ncta;
-    CUDA_TRY(cudaMalloc(&b->cnt, sizeof(uint32_t) * (ntiles + 2)));
+    CUDA_TRY(cudaMalloc(&b->cnt, sizeof(uint32_t) * (ntiles + 4)));
     CUDA_TRY(cudaMalloc(&b->rows, sizeof(double) * 2 * (PS_NROWS + 1) * PS_GROW));
     CUDA_TRY(cudaMemsetAsync(b->rows, 0, sizeof(double) * 2 * (PS_NROWS + 1) * PS_GROW, f->stream));
     CUDA_TRY(cudaMalloc(&b->trace, sizeof(long long) * (32 * 16 + 32 * 8 + 32 * 4)));
@@ -944,7 +993,7 @@ int launch_elbo_persist(bvg_fit *f, int S, double *d_lps) {
     CUDA_TRY(cudaMalloc(&b->erows, sizeof(double) * (size_t)S * ncta * 8));
     b->erows_cap = S;
   }
-  CUDA_TRY(cudaMemsetAsync(b->cnt, 0, sizeof(uint32_t) * (ntiles + 2), f->stream));
+  CUDA_TRY(cudaMemsetAsync(b->cnt, 0, sizeof(uint32_t) * (ntiles + 4), f->stream));
   ElboArgs p;
   memset(&p, 0, sizeof(p));
   TcArgs &a = p.a;

@@ -342,6 +342,40 @@ __global__ void k_gmm_eye(GmmDev m) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m.P; i += gridDim.x * blockDim.x) m.var[(size_t)i * (i + 1) / 2 + i] = 1.0;
 }
 
+// B points in one launch, one CTA each (the ELBO draws of a Pathfinder iterate; B = 1 with a gradient for its L-BFGS):
+// CTA b evaluates thetas[b]; gradients need the per-gene responsibilities, in shared memory when they fit, else in slice b of r.
+__global__ void __launch_bounds__(GMM_THREADS) k_gmm_logprob_batch(GmmDev m, const double *__restrict__ thetas, double *__restrict__ lps,
+                                                                   double *__restrict__ grads, double *__restrict__ rbatch, int jac, int propto) {
+  GmmDev mb = m;
+  const int b = blockIdx.x;
+  if (grads) mb.grad = grads + (size_t)b * m.P;
+  if (rbatch) mb.r = rbatch + (size_t)b * m.N * m.K;
+  const GmmSh s = gmm_sh(gmm_smem, m.K, m.D, gmm_part_doubles(m.K, m.D), mb.r, m.r_smem);
+  const double lp = gmm_eval(mb, s, thetas + (size_t)b * m.P, jac, propto, grads != nullptr);
+  if (threadIdx.x == 0) lps[b] = lp;
+}
+// the posterior pass of k_gmm_post for GIVEN unconstrained draws (Pathfinder's PSIS-resampled draws instead of draws of a
+// variational family): constrained draws, soft assignments (R/clusterSVGsBayes.R:215-239), log-likelihood (:281-284)
+__global__ void __launch_bounds__(GMM_THREADS) k_gmm_post_given(GmmDev m, int nd, const double *__restrict__ thetas, double *__restrict__ draws,
+                                                                double *__restrict__ soft) {
+  const GmmSh s = gmm_sh(gmm_smem, m.K, m.D);
+  const int K = m.K, D = m.D, KD = K * D, tid = threadIdx.x;
+  for (int64_t q = tid; q < m.N * K; q += GMM_THREADS) soft[q] = 0.0;
+  __syncthreads();
+  double ll = 0;
+  for (int t = 0; t < nd; ++t) {
+    gmm_constrain(m, s, thetas + (size_t)t * m.P);
+    if (draws) {
+      double *o = draws + (size_t)t * (K + 2 * KD);
+      for (int q = tid; q < K; q += GMM_THREADS) o[q] = s.theta[q];
+      for (int q = tid; q < KD; q += GMM_THREADS) { const int j = q / D, d = q - j * D; o[K + j + K * d] = s.mu[q]; o[K + KD + q] = s.sigma[q]; }
+    }
+    ll += gmm_mixture(m, s, false, soft, 1.0 / nd);
+    __syncthreads();
+  }
+  if (tid == 0) m.scal[4] = ll / nd;
+}
+
 namespace {
 struct GmmHost {
   GmmDev m;
@@ -350,6 +384,10 @@ struct GmmHost {
   size_t smem = 0;
   double *d_init = nullptr, *d_zs = nullptr, *d_part = nullptr;
   int elbo_grid = 1;
+  // handle form (bvg_gmm_open): batch buffers of bvg_gmm_eval, grown on demand
+  double *d_batch = nullptr;   // [cap][P] points | [cap] lp | [gcap][P] gradients | [gcap][N K] responsibilities (when not in shared memory)
+  int cap = 0, gcap = 0;
+  int device = 0;
 };
 int gmm_setup(GmmHost &h, int device, const double *X, int64_t N, int D, int K, int fullrank, uint64_t seed) {
   if (!X || N < 1 || D < 1 || D > 256 || K < 2 || K > GMM_MAXK) { bvg_set_error("gmm: need N >= 1, 1 <= D <= 256, 2 <= K <= %d (Please provide a valid number of clusters.)", GMM_MAXK); return BVG_ERR_ARG; }
@@ -383,11 +421,15 @@ int gmm_setup(GmmHost &h, int device, const double *X, int64_t N, int D, int K, 
   CUDA_TRY(cudaFuncSetAttribute(k_gmm_steps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h.smem));
   CUDA_TRY(cudaFuncSetAttribute(k_gmm_elbo, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h.smem));
   CUDA_TRY(cudaFuncSetAttribute(k_gmm_post, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h.smem));
+  CUDA_TRY(cudaFuncSetAttribute(k_gmm_logprob_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h.smem));
+  CUDA_TRY(cudaFuncSetAttribute(k_gmm_post_given, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h.smem));
+  h.device = device;
   return BVG_OK;
 }
 void gmm_free(GmmHost &h) {
   if (h.st) cudaStreamDestroy(h.st);
   cudaFree(h.base);
+  cudaFree(h.d_batch);
 }
 int gmm_reset(GmmHost &h) {   // mu <- init, variational scale <- 0 (mean-field) / I (full-rank), histories <- 0
   CUDA_TRY(cudaMemsetAsync(h.m.scal + 3, 0, sizeof(double), h.st));   // failed-evaluation counter of the phase
@@ -523,4 +565,68 @@ extern "C" int bvg_gmm_fit(int device, const double *X, int64_t N, int D, int K,
   stats_out[0] = eta; stats_out[1] = it; stats_out[2] = conv; stats_out[3] = elbo; stats_out[4] = sc[4]; stats_out[5] = now_s() - t_start;
   stats_out[6] = gevals; stats_out[7] = eevals;
   return fail(BVG_OK);
+}
+
+// ---- handle form: the embedding stays on the device between evaluations (Pathfinder: R/clusterSVGsBayes.R:162-170) ----
+extern "C" int bvg_gmm_open(int device, const double *X, int64_t N, int D, int K, void **handle) {
+  if (!handle) { bvg_set_error("null argument"); return BVG_ERR_ARG; }
+  GmmHost *h = new GmmHost();
+  const int rc = gmm_setup(*h, device, X, N, D, K, 0, 0);
+  if (rc != BVG_OK || cudaStreamSynchronize(h->st) != cudaSuccess) { gmm_free(*h); delete h; *handle = nullptr; return rc != BVG_OK ? rc : BVG_ERR_CUDA; }
+  *handle = h;
+  return BVG_OK;
+}
+extern "C" void bvg_gmm_close(void *handle) {
+  if (!handle) return;
+  GmmHost *h = (GmmHost *)handle;
+  cudaSetDevice(h->device);
+  gmm_free(*h);
+  delete h;
+}
+// lp_out[b] = log_prob<propto, jacobian>(thetas[b]) for b < B; grad_out ([B][P]) may be NULL
+extern "C" int bvg_gmm_eval(void *handle, const double *thetas, int B, int jacobian, int propto, double *lp_out, double *grad_out) {
+  if (!handle || !thetas || !lp_out || B < 1) { bvg_set_error("null or empty argument"); return BVG_ERR_ARG; }
+  GmmHost &h = *(GmmHost *)handle;
+  CUDA_TRY(cudaSetDevice(h.device));
+  const int P = h.m.P;
+  const size_t nk = (size_t)h.m.N * h.m.K;
+  const int gneed = grad_out ? B : 0;
+  if (B > h.cap || gneed > h.gcap) {
+    const int cap = std::max(B, h.cap), gcap = std::max(gneed, h.gcap);
+    cudaFree(h.d_batch);
+    h.d_batch = nullptr; h.cap = h.gcap = 0;
+    const size_t nd = (size_t)cap * (P + 1) + (size_t)gcap * P + (h.m.r_smem ? 0 : (size_t)gcap * nk);
+    CUDA_TRY(cudaMalloc(&h.d_batch, sizeof(double) * std::max<size_t>(nd, 1)));
+    h.cap = cap; h.gcap = gcap;
+  }
+  double *d_th = h.d_batch, *d_lp = d_th + (size_t)h.cap * P, *d_g = d_lp + h.cap, *d_r = d_g + (size_t)h.gcap * P;
+  CUDA_TRY(cudaMemcpyAsync(d_th, thetas, sizeof(double) * (size_t)B * P, cudaMemcpyHostToDevice, h.st));
+  k_gmm_logprob_batch<<<B, GMM_THREADS, h.smem, h.st>>>(h.m, d_th, d_lp, grad_out ? d_g : nullptr, (grad_out && !h.m.r_smem) ? d_r : nullptr, jacobian, propto);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(lp_out, d_lp, sizeof(double) * B, cudaMemcpyDeviceToHost, h.st));
+  if (grad_out) CUDA_TRY(cudaMemcpyAsync(grad_out, d_g, sizeof(double) * (size_t)B * P, cudaMemcpyDeviceToHost, h.st));
+  CUDA_TRY(cudaStreamSynchronize(h.st));
+  return BVG_OK;
+}
+// posterior pass for given unconstrained draws: draws_out [nd][K + 2 K D] (theta | mu column-major | sigma) or NULL, soft_out [N][K]
+extern "C" int bvg_gmm_posterior(void *handle, const double *thetas, int nd, double *draws_out, double *soft_out, double *loglik_out) {
+  if (!handle || !thetas || !soft_out || nd < 1) { bvg_set_error("null or empty argument"); return BVG_ERR_ARG; }
+  GmmHost &h = *(GmmHost *)handle;
+  CUDA_TRY(cudaSetDevice(h.device));
+  const int P = h.m.P, K = h.m.K, D = h.m.D;
+  const size_t nk = (size_t)h.m.N * K, ncol = (size_t)K + 2 * (size_t)K * D;
+  double *buf = nullptr;
+  CUDA_TRY(cudaMalloc(&buf, sizeof(double) * ((size_t)nd * P + nk + (draws_out ? (size_t)nd * ncol : 0))));
+  double *d_th = buf, *d_soft = d_th + (size_t)nd * P, *d_draws = draws_out ? d_soft + nk : nullptr;
+  bool ok = cudaMemcpyAsync(d_th, thetas, sizeof(double) * (size_t)nd * P, cudaMemcpyHostToDevice, h.st) == cudaSuccess;
+  k_gmm_post_given<<<1, GMM_THREADS, h.smem, h.st>>>(h.m, nd, d_th, d_draws, d_soft);
+  double sc[6];
+  ok = ok && cudaMemcpyAsync(sc, h.m.scal, sizeof(sc), cudaMemcpyDeviceToHost, h.st) == cudaSuccess &&
+       cudaMemcpyAsync(soft_out, d_soft, sizeof(double) * nk, cudaMemcpyDeviceToHost, h.st) == cudaSuccess &&
+       (!draws_out || cudaMemcpyAsync(draws_out, d_draws, sizeof(double) * (size_t)nd * ncol, cudaMemcpyDeviceToHost, h.st) == cudaSuccess) &&
+       cudaStreamSynchronize(h.st) == cudaSuccess && cudaGetLastError() == cudaSuccess;
+  cudaFree(buf);
+  if (!ok) { bvg_set_error("gmm: %s", cudaGetErrorString(cudaGetLastError())); return BVG_ERR_CUDA; }
+  if (loglik_out) *loglik_out = sc[4];
+  return BVG_OK;
 }

@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(256) k_lb_gdot(LbDev *s, DevModel m, const dou
 // Gram rows of the new (s, y, g); the last CTA finishes the iteration
 // The accepted step is formed here on the fly -- s = x1 - x0, y = g1 - g0 from (zeta, grad) and the still unchanged (x0, g0 row) --
 // and the row-group-0 CTAs store the s / y rows; x0 <- x1 and g0 <- g1 wait for k_lb_dir (other CTAs of this grid still read them).
-__global__ void __launch_bounds__(256) k_lb_dots(LbDev *s, DevModel m, double *B, const double *__restrict__ x0, const double *__restrict__ w,
+__global__ void __launch_bounds__(256, 2) k_lb_dots(LbDev *s, DevModel m, double *B, const double *__restrict__ x0, const double *__restrict__ w,
                                                  double *__restrict__ part, double *dots) {
   extern __shared__ double sh[];   // last CTA: Gram matrix [nb * nb] | polling scratch
   __shared__ double red[LB_RG * 3][8];

@@ -147,6 +147,17 @@ int bvg_gmm_log_prob(int device, const double *X, int64_t N, int D, int K, const
                      double *lp, double *grad);
 int bvg_gmm_fit(int device, const double *X, int64_t N, int D, int K, int fullrank, uint64_t seed, const double *opts,
                 double *mu_out, double *var_out, double *draws_out, double *soft_out, double *stats_out);
+/* algorithm = "pathfinder" of clusterSVGsBayes() (R/clusterSVGsBayes.R:162-170: mod$pathfinder(init = 0.01, draws, num_elbo_draws,
+ * max_lbfgs_iters = 500, history_size = 100)): the host runs Pathfinder's L-BFGS paths and its (2 J)-dimensional algebra, as CmdStan
+ * does; every log density / gradient is evaluated here with the embedding resident on the device.  bvg_gmm_open keeps X (N x D
+ * column-major) on the device; bvg_gmm_eval evaluates log_prob<propto, jacobian> at B unconstrained points in ONE launch (one CTA
+ * per point: the num_elbo_draws draws of an iterate), gradients ([B][P]) optional; bvg_gmm_posterior is the posterior pass of
+ * :201-291 for GIVEN unconstrained draws [nd][P] (the PSIS-resampled draws): constrained draws [nd][K + 2 K D] or NULL, soft
+ * assignments [N][K] row-major, log-likelihood. */
+int bvg_gmm_open(int device, const double *X, int64_t N, int D, int K, void **handle);
+void bvg_gmm_close(void *handle);
+int bvg_gmm_eval(void *handle, const double *thetas, int B, int jacobian, int propto, double *lp_out, double *grad_out);
+int bvg_gmm_posterior(void *handle, const double *thetas, int nd, double *draws_out, double *soft_out, double *loglik_out);
 
 int bvg_fit_create(const bvg_config *cfg, bvg_fit **out);
 void bvg_fit_destroy(bvg_fit *);

@@ -317,6 +317,49 @@ def test_persistent_advi_kernel_equals_the_two_launch_chain(lik, depth, M, G, k)
 
 
 @pytest.mark.parametrize("lik", ["gaussian", "nb"])
+def test_persistent_advi_kernel_row_form_of_the_grid_meeting(lik):
+    """The cross-gene sums normally meet in fixed-point accumulators; sums outside their range (|s| >= 2^84) or not finite take
+    the row form (every CTA publishes its row, second meeting).  BVG_PERSIST_FORCE_ROWS=1 takes it on every iteration: same
+    trajectory as the two-launch chain and as the accumulator form."""
+    p = make_problem(1000, 257, 20, lik, seed=21)
+    mu_a, om_a, _ = _advi_run(p, lik, (7, 1, 17), False)
+    os.environ["BVG_PERSIST_FORCE_ROWS"] = "1"
+    try:
+        mu_b, om_b, _ = _advi_run(p, lik, (7, 1, 17), False)
+    finally:
+        del os.environ["BVG_PERSIST_FORCE_ROWS"]
+    mu_c, om_c, _ = _advi_run(p, lik, (25,), True)
+    assert np.all(np.isfinite(mu_b))
+    assert rel_err(mu_b, mu_c) < 1e-9 and rel_err(om_b, om_c) < 1e-9
+    assert rel_err(mu_a, mu_b) < 1e-12 and rel_err(om_a, om_b) < 1e-12
+
+
+def test_persistent_advi_kernel_survives_the_diverging_trials_of_adapt_eta():
+    """adapt_eta's first trials (eta = 100, 10) drive a few genes' amplitudes to 1e4 and beyond: cross-gene sums of 1e13 ... inf.
+    The accumulator form of the grid meeting must hand those iterations to the row form instead of poisoning the fit (a
+    192-gene fit on 2,444 spots failed with 'non-finite gradient' when the accumulators covered |s| < 2^42 only and turned
+    everything above into NaN): the persistent kernel and the two-launch chain end at the same ELBO."""
+    from bayesvg_b200 import synth
+    from bayesvg_b200.api import kmeans_centers, length_scale_kmeans
+    X = synth.scale_coords(synth.masked_blob(synth.visium_grid(), 2444))
+    Cc = kmeans_centers(X, 20, 100, 10, rng=312, device=0)
+    phi = bvg.basis_build(X, Cc, length_scale_kmeans(Cc), "matern", 2.5)
+    Y, _ = synth.expression(phi, 192, "gaussian", 312)
+    out = {}
+    for nop in ("0", "1"):
+        os.environ["BVG_NO_PERSIST"] = nop
+        try:
+            f = bvg.Fit(phi, np.asfortranarray(Y), "gaussian", "fast", "auto", seed=312)
+            f.run()
+            out[nop] = f.stats()
+            f.close()
+        finally:
+            del os.environ["BVG_NO_PERSIST"]
+    assert out["0"]["advi_iters"] == out["1"]["advi_iters"] and out["0"]["eta"] == out["1"]["eta"]
+    assert out["0"]["elbo"] == pytest.approx(out["1"]["elbo"], rel=1e-6)
+
+
+@pytest.mark.parametrize("lik", ["gaussian", "nb"])
 def test_persistent_advi_kernel_with_more_work_items_than_sms(lik):
     """157 gene tiles (x spot splits) on 148 SMs: a CTA of the persistent kernel walks several (tile, split) items per iteration"""
     p = make_problem(700, 20000, 5, lik, seed=3)
