@@ -348,15 +348,13 @@ def clusterSVGsBayes(sp_obj=None, svgs=None, n_clust=5, n_PCs=30, algorithm="ful
     algorithm = algorithm.lower()
     if algorithm not in ("meanfield", "fullrank", "pathfinder"):
         _abort("Please provide a valid variational inference approximation algorithm.")
-    if algorithm == "pathfinder":
-        raise NotImplementedError("algorithm = 'pathfinder' is not built for clusterSVGsBayes(); use 'fullrank' (the default) or 'meanfield'.")
     if opencl_params is not None:
         raise NotImplementedError("opencl.params is meaningless here: the fit always runs on the CUDA device.")
     if algorithm == "meanfield" and verbose:
         print("! The meanfield VI algorithm often does not perform well on clustering problems do to multi-modality and high "
               "correlation of the posterior. Use caution and consider utilizing the default fullrank VI algorithm instead.")
     if elbo_samples is None:
-        elbo_samples = 300
+        elbo_samples = 100 if algorithm == "pathfinder" else 300                                 # :19-25
     t_start = time.time()
     gidx = {g: i for i, g in enumerate(sp_obj.genes)}
     rows = [gidx[g] for g in svgs]
@@ -366,7 +364,13 @@ def clusterSVGsBayes(sp_obj=None, svgs=None, n_clust=5, n_PCs=30, algorithm="ful
     U, S, _ = np.linalg.svd(expr, full_matrices=False)
     n_pc = min(int(n_PCs), len(S))
     emb = U[:, :n_pc] * S[:n_pc]
-    res = E.gmm_fit(emb, n_clust, algorithm, n_iter, n_draws, elbo_samples, random_seed, device=device)
+    if algorithm == "pathfinder":
+        # mod$pathfinder(init = 0.01, draws = n.draws, num_elbo_draws = elbo.samples, max_lbfgs_iters = 500, history_size = 100) (:162-170)
+        from .gmm_pathfinder import gmm_pathfinder
+        res = gmm_pathfinder(emb, n_clust, n_draws=n_draws, elbo_samples=elbo_samples, seed=random_seed, num_paths=4,
+                             max_lbfgs_iters=500, history=100, init_radius=0.01, device=device)
+    else:
+        res = E.gmm_fit(emb, n_clust, algorithm, n_iter, n_draws, elbo_samples, random_seed, device=device)
     soft = res["soft"]
     K, D, N = int(n_clust), n_pc, emb.shape[0]
     cluster_df = pd.DataFrame(soft, columns=[f"prob_cluster_{j + 1}" for j in range(K)])
@@ -379,6 +383,9 @@ def clusterSVGsBayes(sp_obj=None, svgs=None, n_clust=5, n_PCs=30, algorithm="ful
     model_fit = VariationalFit(cols, res["draws"], trace=None, stats=res["info"], mu_unconstrained=res["mu"], var=res["var"])
     if verbose:
         i = res["info"]
-        print(f"v ADVI ({algorithm}): eta = {i['eta']}, {i['iters']} iterations, ELBO = {i['elbo']:.6g}")
+        if algorithm == "pathfinder":
+            print(f"v Pathfinder: {len(i['paths'])} paths, {i['iters']} L-BFGS iterations, best ELBO = {i['elbo']:.6g}, Pareto k = {i['khat']:.2f}")
+        else:
+            print(f"v ADVI ({algorithm}): eta = {i['eta']}, {i['iters']} iterations, ELBO = {i['elbo']:.6g}")
         print(f"v bayesVG clustering of {len(svgs)} SVGs completed in {round(time.time() - t_start, 3)} seconds.")
     return dict(pca_embedding=emb, cluster_df=cluster_df, model_fit=model_fit, log_likelihood=ll, BIC=-2 * ll + p * np.log(N))

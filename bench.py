@@ -319,15 +319,17 @@ def extra_blocks_n1(args, local_rank, phi_cfg2, Y_cfg2):
     phi1 = bvg.basis_build(X1, C1, length_scale_kmeans(C1), "matern", 2.5, device=local_rank)
     t_basis = time.perf_counter() - t0
     Y1, amp1 = synth.expression(phi1, G_GENES, "gaussian", 312)
-    time.sleep(0.5)   # as above: let the generator's BLAS threads park before the timed fit
-    t0 = time.perf_counter()
-    f = bvg.Fit(phi1, Y1, "gaussian", "fast", args.engine, **cfg)
-    tab = f.run()
-    wall = time.perf_counter() - t0 + t_basis
-    s = f.stats()
-    f.close()
+    runs1 = []
+    for _ in range(3):   # median of three fits on fresh handles (see the cfg2 fit block)
+        t0 = time.perf_counter()
+        f = bvg.Fit(phi1, Y1, "gaussian", "fast", args.engine, **cfg)
+        tab = f.run()
+        runs1.append((time.perf_counter() - t0 + t_basis, f.stats(), tab))
+        f.close()
+    runs1.sort(key=lambda r: r[0])
+    wall, s, tab = runs1[1]
     blk = {"workload": "stand-in for cfg1 (seu_brain): 2,444 spots x 3,000 genes, k=20 Matern-2.5, gaussian; k-means + basis build + L-BFGS + ADVI + draws",
-           "gpu": {"wall_s": wall, "sec_kmeans_basis": t_basis, "sec_h2d": s["sec_h2d"], "sec_mle": s["sec_mle"], "sec_adapt": s["sec_adapt"], "sec_sga": s["sec_sga"],
+           "gpu": {"wall_s": wall, "wall_s_runs": [r[0] for r in runs1], "sec_kmeans_basis": t_basis, "sec_h2d": s["sec_h2d"], "sec_mle": s["sec_mle"], "sec_adapt": s["sec_adapt"], "sec_sga": s["sec_sga"],
                    "sec_draws": s["sec_draws"], "advi_iters": s["advi_iters"], "mle_iters": s["mle_iters"], "elbo": s["elbo"], "converged": s["converged"]}}
     if not args.skip_cpu:
         # bounded CPU leg: the SAME pipeline of the fp64 C restatement (all host threads) on the first `gs` genes
@@ -507,17 +509,24 @@ def run_ours(args, rank, world, local_rank):
         phif = bvg.basis_build(Xf, Cf, length_scale_kmeans(Cf), "matern", 2.5, device=local_rank)
         t_kb = time.perf_counter() - t0
         Yf, _ = synth.expression(phif, G_GENES, "gaussian", 312)
-        time.sleep(0.5)   # the synthetic generator's BLAS worker threads park (they spin for a while after a matmul and slow every host call that follows)
-        t0 = time.perf_counter()
-        f3 = bvg.Fit(phif, Yf, "gaussian", "fast", args.engine, **cfg)
-        f3.run()
-        s3 = f3.stats()
-        fit_info = {"wall_s": time.perf_counter() - t0 + t_kb, "sec_kmeans_basis": t_kb, "sec_h2d": s3["sec_h2d"], "grad_evals": s3["grad_evals"],
+        # three whole fits, each on a fresh handle (allocation, H2D, staging, L-BFGS, ADVI, draws); the line quotes the median and
+        # lists all three: single runs on these boxes carry host-side outliers of 0.1 - 0.3 s (a slow first H2D after an idle
+        # period, a stalled driver call) that say nothing about the path
+        runs = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            f3 = bvg.Fit(phif, Yf, "gaussian", "fast", args.engine, **cfg)
+            f3.run()
+            w3 = time.perf_counter() - t0 + t_kb
+            runs.append((w3, f3.stats()))
+            f3.close()
+        runs.sort(key=lambda r: r[0])
+        w3, s3 = runs[1]
+        fit_info = {"wall_s": w3, "wall_s_runs": [r[0] for r in runs], "sec_kmeans_basis": t_kb, "sec_h2d": s3["sec_h2d"], "grad_evals": s3["grad_evals"],
                     "elbo_evals": s3["elbo_evals"], "advi_iters": s3["advi_iters"], "eta": s3["eta"], "mle_iters": s3["mle_iters"],
                     "mle_fevals": s3["mle_fevals"], "mle_term": s3["mle_term"], "sec_mle": s3["sec_mle"], "sec_adapt": s3["sec_adapt"],
                     "sec_sga": s3["sec_sga"], "sec_draws": s3["sec_draws"], "converged": s3["converged"], "elbo": s3["elbo"],
-                    "includes": "k-means (10 starts) + basis build + H2D + L-BFGS + eta adaptation + SGA + 1,000 draws + summaries"}
-        f3.close()
+                    "includes": "k-means (10 starts) + basis build + H2D + L-BFGS + eta adaptation + SGA + 1,000 draws + summaries; median of three fits on fresh handles"}
         # separately reported fast path: forward-only ELBO estimates from sufficient statistics (gaussian)
         t0 = time.perf_counter()
         f4 = bvg.Fit(phif, Yf, "gaussian", "fast", args.engine, elbo_suffstat=1, **cfg)

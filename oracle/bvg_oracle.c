@@ -987,6 +987,7 @@ static void pf_alloc(pf_approx *a, int64_t D, int J) {
   a->alpha = a->xc + D;
   a->n = 0; a->ok = 0;
 }
+static double *pf_phi_out = NULL;  /* bvgo_pf_single_phi: the unconstrained draws of the path, [num_draws][D] */
 /* one path: amp [num_draws][G] (exp of the amplitude coordinates), lp_ratio [num_draws] = lp - log q;
  * elbos (optional) [max_lbfgs_iters + 1]: the ELBO estimate at every iterate */
 int bvgo_pf_single(bvgo_ctx *c, const bvgo_pf_cfg *cfg, int path, double *amp, double *lp_ratio, bvgo_pf_info *info,
@@ -1020,12 +1021,24 @@ int bvgo_pf_single(bvgo_ctx *c, const bvgo_pf_cfg *cfg, int path, double *amp, d
       const double lq = pf_draw(&st.best, D, u, phi);
       const double lp = bvgo_log_prob(c, phi, 1, 1, NULL);
       lp_ratio[k] = isfinite(lp) ? lp - lq : -INFINITY;
+      if (pf_phi_out) memcpy(pf_phi_out + (size_t)k * D, phi, sizeof(double) * D);
       for (int64_t g = 0; g < G; ++g) amp[(size_t)k * G + g] = exp(phi[c->L.amp + g]);
     }
   }
   if (info) { info->lbfgs_iters = lr.iters; info->lbfgs_term = lr.term; info->best_iter = st.best_iter; info->best_elbo = st.best_elbo; info->n_pairs = st.best.n; }
   if (elbos) memcpy(elbos, st.elbos, sizeof(double) * st.elbo_cap);
   free(th0); free(st.elbos); free(st.cur.W); free(st.cur.xc); free(st.best.W); free(st.best.xc); free(st.alpha);
+  return rc;
+}
+/* the same path with its draws in the unconstrained space (the mixture program of clusterSVGsBayes(algorithm = "pathfinder"),
+ * R/clusterSVGsBayes.R:162-170, has no amplitude block to summarise) */
+int bvgo_pf_single_phi(bvgo_ctx *c, const bvgo_pf_cfg *cfg, int path, double *phi /*[num_draws][D]*/, double *lp_ratio,
+                       bvgo_pf_info *info, double *elbos) {
+  double *amp = (double *)malloc(sizeof(double) * (size_t)cfg->num_draws * (size_t)(c->G > 0 ? c->G : 1));
+  pf_phi_out = phi;
+  const int rc = bvgo_pf_single(c, cfg, path, amp, lp_ratio, info, elbos);
+  pf_phi_out = NULL;
+  free(amp);
   return rc;
 }
 /* Pareto-smoothed importance weights [U: stan::services::psis::psis_weights; Vehtari et al. 2015, Zhang & Stephens 2009] */

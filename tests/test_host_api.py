@@ -227,9 +227,8 @@ def test_cluster_svgs_bayes_host_logic(monkeypatch):
         f(o, ["gene1", "gene2"], n_clust=1)
     with pytest.raises(ValueError, match="valid variational inference approximation algorithm"):
         f(o, ["gene1", "gene2"], algorithm="hmc")
-    for kw in (dict(algorithm="pathfinder"), dict(opencl_params=[0, 0])):
-        with pytest.raises(NotImplementedError):
-            f(o, ["gene1", "gene2"], **kw)
+    with pytest.raises(NotImplementedError):
+        f(o, ["gene1", "gene2"], opencl_params=[0, 0])
     seen = {}
 
     def fake_fit(X, K, algorithm, n_iter, n_draws, elbo_samples, seed, device=0):
@@ -255,3 +254,55 @@ def test_cluster_svgs_bayes_host_logic(monkeypatch):
     assert res["log_likelihood"] == -50.0 and res["BIC"] == pytest.approx(100.0 + (2 + 2 * 3 * 4) * np.log(7))   # :286-291
     fit = res["model_fit"]
     assert fit.columns[:3] == ["theta[1]", "theta[2]", "theta[3]"] and fit.columns[3] == "mu[1,1]" and fit.columns[-1] == "sigma[3,4]"
+    # algorithm = "pathfinder" (:162-170): its own driver, elbo.samples defaults to 100 (:19-25), the reference's settings
+    import bayesvg_b200.gmm_pathfinder as gpf
+    seen2 = {}
+
+    def fake_pf(X, K, **kw):
+        seen2.update(kw, K=K)
+        r = fake_fit(X, K, "pathfinder", 0, kw["n_draws"], kw["elbo_samples"], kw["seed"])
+        r["info"].update(khat=0.3, paths=[{}] * kw["num_paths"])
+        r["mu"] = r["var"] = None
+        return r
+
+    monkeypatch.setattr(gpf, "gmm_pathfinder", fake_pf)
+    res = f(o, svgs, n_clust=3, n_PCs=4, n_draws=20, algorithm="pathfinder", verbose=False)
+    assert (seen2["elbo_samples"], seen2["max_lbfgs_iters"], seen2["history"], seen2["init_radius"], seen2["num_paths"]) == (100, 500, 100, 0.01, 4)
+    assert list(res["cluster_df"]["assigned_cluster"]) == [1, 2, 3, 1, 2, 3, 1]
+
+
+def test_gmm_pathfinder_host_algorithm_matches_the_oracle():
+    """bayesvg_b200/gmm_pathfinder.py (the host side of clusterSVGsBayes(algorithm = "pathfinder"): L-BFGS path, the Gaussian
+    approximation of every iterate, ELBO selection, PSIS) against the oracle's C restatement of the same algorithm on
+    inst/clusterSVGs.stan, with the ORACLE as the evaluator on both sides (the device evaluator is the GPU suite's part):
+    same Philox streams -> same path, same ELBO estimates, same draws, same importance weights."""
+    import bayesvg_b200.gmm_pathfinder as gpf
+    from oracle import oracle as orc
+    rng = np.random.default_rng(3)
+    N, D, K = 150, 4, 3
+    cent = rng.normal(0, 3, (K, D))
+    X = np.vstack([cent[j] + rng.normal(0, 0.7, (N // K, D)) for j in range(K)])
+    o = orc.GmmOracle(X, K)
+
+    class Ev:
+        P = o.D
+
+        def lp_grad(self, th):
+            return o.log_prob(th, True, True)
+
+        def lp_batch(self, ths):
+            return np.array([o.log_prob(t, True, True, grad=False) for t in ths])
+
+    kw = dict(max_lbfgs_iters=30, history=6, num_elbo_draws=8, num_draws=40, seed=11)
+    for path in (0, 1):
+        phi_o, lr_o, io = o.pf_single_phi(path, **kw)
+        phi_p, lr_p, ip = gpf.single_path(Ev(), path, 11, 40, 30, 6, 8, 0.01)
+        assert io["rc"] == 0 and (io["lbfgs_iters"], io["best_iter"], io["n_pairs"]) == (ip["lbfgs_iters"], ip["best_iter"], ip["n_pairs"])
+        eo = io["elbos"][1:1 + len(ip["elbos"])]
+        assert np.allclose(eo, ip["elbos"], rtol=1e-9)
+        assert np.linalg.norm(phi_o - phi_p) <= 1e-9 * np.linalg.norm(phi_o) and np.allclose(lr_o, lr_p, atol=1e-7)
+    w_o, k_o = o.psis_weights(lr_o)
+    w_p, k_p = gpf.psis_weights(lr_o)
+    assert np.allclose(w_o, w_p, atol=1e-14) and k_o == pytest.approx(k_p, rel=1e-12)
+    # the library's generator, restated in numpy for the host side
+    assert gpf.uniform(312, 5, 7, np.arange(4, dtype=np.uint64)) == pytest.approx([orc.lib().bvgo_uniform(312, 5, 7, i) for i in range(4)], rel=1e-15)
