@@ -21,9 +21,22 @@
 #define KM_SSFIX 1048576.0    // 2^20
 #define KM_STREAM 4u          // Philox stream of the start draws (1-3: DESIGN.md section 4.3)
 
-__global__ void __launch_bounds__(256) k_km_assign(const double *__restrict__ X, int64_t M, const double *__restrict__ C, int k,
-                                                   int32_t *__restrict__ label, unsigned long long *__restrict__ acc /* [3][k] + changed + ss */) {
+// state of one start: iteration count, done / converged flags, within-SS of its final state (device-resident control: the
+// host looks at the `done` flags of all starts once per KM_CHUNK iterations instead of synchronising after every one)
+struct KmStart { int32_t it, done, conv, pad; unsigned long long ss; };
+#define KM_CHUNK 8
+
+// blockIdx.y = start: the nstart runs advance in lockstep, one launch per iteration for all of them; a start that has
+// stopped is skipped, so its labels, centres and within-SS stay those of its own last iteration
+__global__ void __launch_bounds__(256) k_km_assign(const double *__restrict__ X, int64_t M, const double *__restrict__ Call, int k,
+                                                   int32_t *__restrict__ label_all, unsigned long long *__restrict__ acc_all /* per start: [3][k] + changed + ss */,
+                                                   const KmStart *__restrict__ stt) {
   extern __shared__ unsigned long long s_acc[];  // [3k] sums | then 2k doubles of centres
+  const int r = blockIdx.y;
+  if (stt[r].done) return;
+  const double *C = Call + (size_t)r * 2 * k;
+  int32_t *label = label_all + (size_t)r * M;
+  unsigned long long *acc = acc_all + (size_t)r * (3 * k + 2);
   double *sc = (double *)(s_acc + 3 * k);
   for (int i = threadIdx.x; i < 3 * k; i += blockDim.x) s_acc[i] = 0ull;
   for (int i = threadIdx.x; i < 2 * k; i += blockDim.x) sc[i] = C[i];
@@ -62,14 +75,33 @@ __global__ void __launch_bounds__(256) k_km_assign(const double *__restrict__ X,
   }
 }
 
-// centre = mean of its spots; an empty cluster keeps its centre
-__global__ void k_km_update(const unsigned long long *__restrict__ acc, double *__restrict__ C, int k) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= k) return;
-  const unsigned long long n = acc[2 * k + j];
-  if (!n) return;
-  C[j] = (double)(long long)acc[j] / (double)n * (1.0 / KM_FIX);
-  C[k + j] = (double)(long long)acc[k + j] / (double)n * (1.0 / KM_FIX);
+// one thread block per start: stop test of the iteration just assigned (no label changed -> converged; iter.max reached ->
+// stop, the within-SS was just measured against the final centres), else centre = mean of its spots (an empty cluster keeps
+// its centre); clears the accumulators for the next iteration
+__global__ void k_km_update(unsigned long long *__restrict__ acc_all, double *__restrict__ Call, int k, int iter_max, KmStart *__restrict__ stt) {
+  const int r = blockIdx.x;
+  KmStart &st = stt[r];
+  if (st.done) return;
+  unsigned long long *acc = acc_all + (size_t)r * (3 * k + 2);
+  double *C = Call + (size_t)r * 2 * k;
+  __shared__ int s_stop;
+  if (threadIdx.x == 0) {
+    const unsigned long long changed = acc[3 * k];
+    s_stop = changed == 0ull || st.it == iter_max;
+    if (s_stop) { st.ss = acc[3 * k + 1]; st.conv = changed == 0ull; }
+  }
+  __syncthreads();
+  const bool stop = s_stop != 0;
+  for (int j = threadIdx.x; j < k; j += blockDim.x) {
+    const unsigned long long n = acc[2 * k + j];
+    if (!stop && n) {
+      C[j] = (double)(long long)acc[j] / (double)n * (1.0 / KM_FIX);
+      C[k + j] = (double)(long long)acc[k + j] / (double)n * (1.0 / KM_FIX);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 3 * k + 2; i += blockDim.x) acc[i] = 0ull;
+  if (threadIdx.x == 0) { if (stop) st.done = 1; else st.it += 1; }
 }
 
 // start r: k distinct rows; row j = first Philox value (counter (j, attempt, r, stream 4)) mod M not drawn before
@@ -98,16 +130,19 @@ extern "C" int bvg_kmeans(int device, const double *coords, int64_t M, int k, in
   CUDA_TRY(cudaSetDevice(device));
   const size_t nacc = (size_t)3 * k + 2;
   char *d = nullptr;
-  const size_t bytes = sizeof(double) * (2 * (size_t)M + 4 * (size_t)k) + sizeof(unsigned long long) * nacc + sizeof(int32_t) * (size_t)M;
+  const size_t bytes = sizeof(double) * (2 * (size_t)M + 2 * (size_t)k * nstart) + sizeof(unsigned long long) * nacc * nstart +
+                       sizeof(KmStart) * (size_t)nstart + sizeof(int32_t) * (size_t)M * nstart;
   CUDA_TRY(cudaMalloc(&d, bytes));
-  double *dX = (double *)d, *dC = dX + 2 * M, *dBest = dC + 2 * k;
-  unsigned long long *dAcc = (unsigned long long *)(dBest + 2 * k);
-  int32_t *dLab = (int32_t *)(dAcc + nacc);
+  double *dX = (double *)d, *dC = dX + 2 * M;
+  unsigned long long *dAcc = (unsigned long long *)(dC + 2 * (size_t)k * nstart);
+  KmStart *dSt = (KmStart *)(dAcc + nacc * nstart);
+  int32_t *dLab = (int32_t *)(dSt + nstart);
   cudaStream_t st = nullptr;
   int rc = BVG_OK;
   std::vector<int64_t> rows(k);
-  std::vector<double> c0(2 * (size_t)k);
-  unsigned long long h[2], best_ss = ~0ull;
+  std::vector<double> c0(2 * (size_t)k * nstart);
+  std::vector<KmStart> hs(nstart);
+  unsigned long long best_ss = ~0ull;
   int best_start = -1, best_iters = 0, best_conv = 0;
   const int grid = (int)std::min<int64_t>((M + 255) / 256, 148 * 8);
   const size_t smem = sizeof(unsigned long long) * 3 * k + sizeof(double) * 2 * k;
@@ -116,28 +151,26 @@ extern "C" int bvg_kmeans(int device, const double *coords, int64_t M, int k, in
   KM_CHECK(cudaMemcpyAsync(dX, coords, sizeof(double) * 2 * M, cudaMemcpyHostToDevice, st));
   for (int r = 0; r < nstart; ++r) {
     km_start_rows(seed, r, M, k, rows.data());
-    for (int j = 0; j < k; ++j) { c0[j] = coords[rows[j]]; c0[k + j] = coords[M + rows[j]]; }
-    KM_CHECK(cudaMemcpyAsync(dC, c0.data(), sizeof(double) * 2 * k, cudaMemcpyHostToDevice, st));
-    KM_CHECK(cudaMemsetAsync(dLab, 0xff, sizeof(int32_t) * M, st));
-    int it = 0, conv = 0;
-    // iteration = assign every spot to its nearest centre, then move the centres; stop when no label changed
-    // (the centres then ARE the means of the final labels and ss is the within-SS of the final state)
-    for (;;) {
-      KM_CHECK(cudaMemsetAsync(dAcc, 0, sizeof(unsigned long long) * nacc, st));
-      k_km_assign<<<grid, 256, smem, st>>>(dX, M, dC, k, dLab, dAcc);
-      KM_CHECK(cudaMemcpyAsync(h, dAcc + 3 * k, sizeof(h), cudaMemcpyDeviceToHost, st));
-      KM_CHECK(cudaStreamSynchronize(st));
-      if (h[0] == 0) { conv = 1; break; }
-      if (it == iter_max) break;  // iter.max reached: ss was just measured against the final centres
-      k_km_update<<<(k + 127) / 128, 128, 0, st>>>(dAcc, dC, k);
-      ++it;
-    }
-    if (h[1] < best_ss) {
-      best_ss = h[1]; best_start = r; best_iters = it; best_conv = conv;
-      KM_CHECK(cudaMemcpyAsync(dBest, dC, sizeof(double) * 2 * k, cudaMemcpyDeviceToDevice, st));
-    }
+    for (int j = 0; j < k; ++j) { c0[(size_t)r * 2 * k + j] = coords[rows[j]]; c0[(size_t)r * 2 * k + k + j] = coords[M + rows[j]]; }
   }
-  KM_CHECK(cudaMemcpyAsync(centers_out, dBest, sizeof(double) * 2 * k, cudaMemcpyDeviceToHost, st));
+  KM_CHECK(cudaMemcpyAsync(dC, c0.data(), sizeof(double) * 2 * k * nstart, cudaMemcpyHostToDevice, st));
+  KM_CHECK(cudaMemsetAsync(dLab, 0xff, sizeof(int32_t) * M * nstart, st));
+  KM_CHECK(cudaMemsetAsync(dAcc, 0, sizeof(unsigned long long) * nacc * nstart + sizeof(KmStart) * nstart, st));
+  // iteration = assign every spot to its nearest centre, then move the centres; a start stops when no label changed (the
+  // centres then ARE the means of the final labels and ss is the within-SS of the final state) or at iter.max
+  for (int done_all = 0, itc = 0; !done_all && itc <= iter_max + KM_CHUNK; itc += KM_CHUNK) {
+    for (int q = 0; q < KM_CHUNK; ++q) {
+      k_km_assign<<<dim3(grid, nstart), 256, smem, st>>>(dX, M, dC, k, dLab, dAcc, dSt);
+      k_km_update<<<nstart, 128, 0, st>>>(dAcc, dC, k, iter_max, dSt);
+    }
+    KM_CHECK(cudaMemcpyAsync(hs.data(), dSt, sizeof(KmStart) * nstart, cudaMemcpyDeviceToHost, st));
+    KM_CHECK(cudaStreamSynchronize(st));
+    done_all = 1;
+    for (int r = 0; r < nstart; ++r) done_all &= hs[r].done;
+  }
+  for (int r = 0; r < nstart; ++r)
+    if (hs[r].ss < best_ss) { best_ss = hs[r].ss; best_start = r; best_iters = hs[r].it; best_conv = hs[r].conv; }   // ties: the first start
+  KM_CHECK(cudaMemcpyAsync(centers_out, dC + (size_t)best_start * 2 * k, sizeof(double) * 2 * k, cudaMemcpyDeviceToHost, st));
   KM_CHECK(cudaStreamSynchronize(st));
   if (tot_withinss) *tot_withinss = (double)best_ss / KM_SSFIX;
   if (info) { info[0] = best_start; info[1] = best_iters; info[2] = best_conv; }
