@@ -52,7 +52,8 @@ extern "C" void bvg_config_default(bvg_config *c) {
   c->world_size = 1;
   c->gene_offset = 0;
   c->G_total = 0;
-  c->elbo_suffstat = 0;
+  c->elbo_suffstat = 1;   /* ELBO estimates from sufficient statistics where they exist (gaussian, hierarchical intercept, k <= 30) */
+  if (const char *e = getenv("BVG_ELBO_SUFFSTAT")) c->elbo_suffstat = e[0] == '1' ? 1 : 0;   /* the test suite keeps the dense estimates */
   c->depth_adjust = 0;
   c->algorithm = BVG_ALG_MEANFIELD;
   c->pf_num_paths = 2;        /* n.cores = 2 (:94) */
@@ -506,7 +507,7 @@ static int advi_steps(bvg_fit *f, int n) {
 static int advi_elbo(bvg_fit *f, int S, double *out) {
   Ctl h;
   BVG_TRY(ctl_get(f, &h));
-  if (f->cfg.elbo_suffstat && f->cfg.likelihood == BVG_GAUSSIAN) {
+  if (f->cfg.elbo_suffstat && f->cfg.likelihood == BVG_GAUSSIAN && !f->cfg.depth_adjust && f->m.k <= BVG_SMALL_K) {
     // all S draws in two launches, from per-gene sufficient statistics (k_suff.cu)
     std::vector<double> lps(S);
     BVG_TRY(suff_elbo(f, S, lps.data()));

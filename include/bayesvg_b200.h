@@ -81,9 +81,11 @@ typedef struct {
   /* gene sharding: this process holds genes [gene_offset, gene_offset + G) of G_total */
   int32_t rank, world_size;
   int64_t gene_offset, G_total; /* G_total = 0 -> unsharded */
-  /* gaussian only, default 0: evaluate the forward-only ELBO estimates (150 draws every 100 iterations) from
-   * per-gene sufficient statistics (sum y^2, Phi'^T y, Phi'^T Phi') instead of 150 dense passes over Y.
-   * Same value up to round-off; the gradient path is always the dense kernel. */
+  /* default 1: where they exist (gaussian likelihood, hierarchical intercept, n.basis.fns <= 30) the forward-only ELBO
+   * estimates (150 draws every 100 iterations) are evaluated from per-gene sufficient statistics (sum y^2, Phi'^T y,
+   * Phi'^T Phi', fp64, built once on the device) instead of 150 dense passes over Y: the same draws and the same
+   * value up to round-off in O(k^2 G) per draw; every other model, and 0, takes the dense batched
+   * kernel (k_elbo_persist).  The gradient path is always the dense kernel. */
   int32_t elbo_suffstat;
   /* gene.depth.adjust (:85): intercept beta0 + beta1 * gene_depths[g] (approxGP2/3.stan) instead of the
    * hierarchical per-gene intercept; needs bvg_fit_set_gene_depths */

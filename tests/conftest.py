@@ -7,6 +7,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# The library's default evaluates the ELBO estimates of a gaussian fit from sufficient statistics; the suite keeps the DENSE
+# estimates (k_elbo_persist / the two-launch chain) as the default under test, so that every fit and ELBO comparison with the
+# oracle exercises the kernels every other model uses.  The sufficient-statistic path has its own tests (elbo_suffstat = 1) and
+# test_default_elbo_path_is_the_sufficient_statistic_one removes this override.
+os.environ.setdefault("BVG_ELBO_SUFFSTAT", "0")
+
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")

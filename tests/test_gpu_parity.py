@@ -257,6 +257,29 @@ def test_set_y_again_reuses_the_model_and_matches_a_fresh_fit(lik, prec, eng):
     assert lp_c == lp_d and np.array_equal(g_c, g_d)
 
 
+def test_default_elbo_path_is_the_sufficient_statistic_one(monkeypatch):
+    """bvg_config_default: elbo_suffstat = 1 -- a default gaussian fit takes its ELBO estimates from the sufficient statistics
+    and ends where the dense-ELBO fit ends (same draws, values equal to the fast path's round-off: same step size, same stopping
+    iteration); nb and depth-adjusted fits take the dense kernel whatever the flag says."""
+    monkeypatch.delenv("BVG_ELBO_SUFFSTAT", raising=False)
+    assert bvg.engine.default_config().elbo_suffstat == 1
+    p = make_problem(500, 150, 12, "gaussian", seed=7)
+    kw = dict(seed=312, n_iter=400, mle_iter=100, elbo_samples=30, n_draws=100)
+    fa = bvg.Fit(p["phi"], p["y"], "gaussian", "fast", "tcgen05", **kw)
+    fb = bvg.Fit(p["phi"], p["y"], "gaussian", "fast", "tcgen05", elbo_suffstat=0, **kw)
+    ta, tb = fa.run(), fb.run()
+    sa, sb = fa.stats(), fb.stats()
+    assert (sa["eta"], sa["advi_iters"], sa["converged"]) == (sb["eta"], sb["advi_iters"], sb["converged"])
+    assert sa["elbo"] == pytest.approx(sb["elbo"], rel=5e-6) and sa["elbo"] != sb["elbo"]     # fp64 statistics vs the bf16-split pass
+    assert np.allclose(ta[:, :6], tb[:, :6], rtol=1e-9, atol=0)     # the ELBO estimates only steer eta and the stopping test
+    fa.close()
+    fb.close()
+    pn = make_problem(300, 140, 12, "nb", seed=9)
+    fn = bvg.Fit(pn["phi"], pn["y"], "nb", "fast", "auto", seed=3, n_iter=100, mle_iter=10, elbo_samples=10, n_draws=50)
+    assert np.all(np.isfinite(fn.run()[:, :6]))
+    fn.close()
+
+
 @pytest.mark.parametrize("lik", ["gaussian", "nb"])
 def test_draw_ahead_batches_are_bitwise_identical(lik):
     """tcgen05 engine: inside a batch of steps k_gene draws the next evaluation's zeta itself; a batch boundary
