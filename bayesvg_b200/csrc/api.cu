@@ -932,6 +932,11 @@ extern "C" int bvg_fit_flush_l2(bvg_fit *f) {
 extern "C" int bvg_fit_time_lik_kernel(bvg_fit *f, int n, int flush_l2, int backward, float *ms_avg_out) {
   BVG_TRY(need_ready(f));
   if (n < 1 || !ms_avg_out) { bvg_set_error("bad argument"); return BVG_ERR_ARG; }
+  if (flush_l2 == 2) {   // input larger than L2, no flush inside the timed region
+    int ncopy = 4;
+    if (const char *e = getenv("BVG_ROT_COPIES")) { const int v = atoi(e); if (v >= 1 && v <= 64) ncopy = v; }
+    return tc_time_rotating(f, n, ncopy, backward != 0, ms_avg_out);
+  }
   if (flush_l2) BVG_TRY(ensure_flush(f));
   double total = 0;
   if (flush_l2) {

@@ -391,6 +391,7 @@ int tcbig_setup(bvg_fit *f);
 void tcbig_destroy(bvg_fit *f);
 bool tc_available();                                         // false until the tcgen05 kernel is linked in
 int tc_setup(bvg_fit *f);                                    // build TMA descriptors etc.
+int tc_time_rotating(bvg_fit *f, int n, int ncopy, bool bwd, float *ms_avg);  // measurement: back-to-back launches over rotating copies of Y (> L2)
 void tc_destroy(bvg_fit *f);
 bool persist_ok(bvg_fit *f);                                 // k_advi_persist.cu: a stretch of ADVI iterations in one cooperative launch
 int launch_advi_persist(bvg_fit *f, int n_iter);             //   (the current draw must be in place: launch_prep(PREP_GRAD) first)

@@ -27,6 +27,8 @@
 // ring full/empty (2 x 24 KB, released by the MMA that read it), D1 full/empty (2 TMEM buffers), R full/free (2).
 #include <cuda.h>
 #include <string.h>
+
+#include <vector>
 #include <cuda_bf16.h>
 
 #include "tc_roles.cuh"
@@ -253,4 +255,38 @@ int launch_lik_tc(bvg_fit *f, bool bwd) {
 #undef TCL
   f->st.kernel_launches++;
   return BVG_OK;
+}
+
+// Measurement support (bvg_fit_time_lik_kernel, mode 2): the likelihood kernel timed back to back on an input LARGER THAN L2
+// without flush kernels inside the timed region -- `ncopy` copies of the tile-major Y (4 x 60 MB at config 2 > 126 MB of L2),
+// launch i reads copy i mod ncopy, so every launch streams its Y from HBM while the launches queue behind each other as they
+// do in a real evaluation chain.  One event pair around all n launches.
+int tc_time_rotating(bvg_fit *f, int n, int ncopy, bool bwd, float *ms_avg) {
+  TcState *t = (TcState *)f->tc;
+  if (!t || !f->tiledY) { bvg_set_error("rotating-copy timing needs the fused tcgen05 engine"); return BVG_ERR_STATE; }
+  const DevModel &m = f->m;
+  const size_t y_bytes = sizeof(float) * (size_t)m.Gpad * f->ldY;
+  std::vector<void *> copies(ncopy, nullptr);
+  std::vector<CUtensorMap> maps(ncopy);
+  const CUtensorMap own = t->tmY;
+  int rc = BVG_OK;
+  for (int c = 0; c < ncopy && rc == BVG_OK; ++c) {
+    if (cudaMalloc(&copies[c], y_bytes) != cudaSuccess) { cudaGetLastError(); bvg_set_error("out of device memory for the rotating copies of Y"); rc = BVG_ERR_CUDA; break; }
+    if (cudaMemcpyAsync(copies[c], f->Y, y_bytes, cudaMemcpyDeviceToDevice, f->stream) != cudaSuccess) { rc = BVG_ERR_CUDA; break; }
+    rc = tc_make_map(&maps[c], copies[c], false, 32, (uint64_t)(m.Gpad / BVG_GENE_TILE) * (uint64_t)(f->ldY / 32) * BVG_GENE_TILE, 32, 2 * BVG_GENE_TILE);
+  }
+  if (rc == BVG_OK) {
+    for (int i = 0; i < ncopy && rc == BVG_OK; ++i) { t->tmY = maps[i]; rc = launch_lik_tc(f, bwd); }   // warm-up: one pass over every copy
+    if (rc == BVG_OK && cudaEventRecord(f->ev0, f->stream) != cudaSuccess) rc = BVG_ERR_CUDA;
+    for (int i = 0; i < n && rc == BVG_OK; ++i) { t->tmY = maps[i % ncopy]; rc = launch_lik_tc(f, bwd); }
+    if (rc == BVG_OK && (cudaEventRecord(f->ev1, f->stream) != cudaSuccess || cudaEventSynchronize(f->ev1) != cudaSuccess)) rc = BVG_ERR_CUDA;
+    float ms = 0.f;
+    if (rc == BVG_OK && cudaEventElapsedTime(&ms, f->ev0, f->ev1) != cudaSuccess) rc = BVG_ERR_CUDA;
+    *ms_avg = ms / (float)n;
+  }
+  t->tmY = own;
+  cudaStreamSynchronize(f->stream);
+  for (void *c : copies) cudaFree(c);
+  if (rc == BVG_ERR_CUDA) bvg_set_error("rotating-copy timing: %s", cudaGetErrorString(cudaGetLastError()));
+  return rc;
 }

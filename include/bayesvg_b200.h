@@ -222,7 +222,8 @@ int bvg_fit_set_cholesky(bvg_fit *, const double *L_packed);
  * ms_out (optional) = device time from CUDA events on the engine's stream */
 int bvg_fit_advi_steps(bvg_fit *, int n, double eta, int reset_counters, float *ms_out);
 int bvg_fit_elbo(bvg_fit *, int n_samples, double *elbo_out, float *ms_out);
-/* time n launches of the likelihood kernel alone; flush_l2 != 0 evicts L2 before each launch */
+/* time n launches of the likelihood kernel alone; flush_l2 = 1 evicts L2 before each launch (event pair around each), 2 (fused
+ * tcgen05 engine) launches back to back over four rotating copies of Y -- an input larger than L2 -- with one event pair */
 int bvg_fit_time_lik_kernel(bvg_fit *, int n, int flush_l2, int backward, float *ms_avg_out);
 
 /* evict the L2 (writes a 512 MB scratch buffer) -- benchmark hygiene between timed steps */
