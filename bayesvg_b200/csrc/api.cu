@@ -108,6 +108,7 @@ extern "C" int bvg_fit_create(const bvg_config *cfg, bvg_fit **out) {
 
 static void free_model(bvg_fit *f) {
   shadow_destroy(f);
+  lbfgs_cache_destroy(f);
   fr_destroy(f);
   cudaFree(f->eb_d);
   f->eb_d = nullptr; f->eb_cap = 0;

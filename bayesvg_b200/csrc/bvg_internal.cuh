@@ -362,6 +362,11 @@ struct bvg_fit {
   bool no_persist;     // diagnostics / tests (BVG_NO_PERSIST=1): keep the two-launch evaluation chain instead of k_advi_persist
   void *shadow;        // fp64 evaluator of a fast-precision fit (fp64_shadow.cu), built when the L-BFGS line search hits the fast engines' noise floor
   LsPoint ls;          // non-NULL x0 only while lbfgs_run_device() is enqueueing evaluations
+  // work space of lbfgs_run_device(), kept with the fit: cudaFree / cudaFreeHost of a 27 MB block cost anything between 1 and
+  // 400 ms on these boxes (measured: the "teardown" of an L-BFGS run), so the block is freed with the model, not per run
+  void *lb_dev_buf; size_t lb_dev_bytes;
+  void *lb_pinned;     // 512 bytes of pinned host memory (status words)
+  cudaEvent_t lb_evt[2];
   bool no_mle_fp64;    // diagnostics (BVG_NO_MLE_FP64=1): let the fast path's L-BFGS end with TERM_LSFAIL as in round 1
 };
 
@@ -400,6 +405,7 @@ void persist_destroy(bvg_fit *f);
 int shadow_enter(bvg_fit *f);                                // fp64_shadow.cu: evaluate in fp64 (SIMT kernels, Y widened on the device) until shadow_leave
 void shadow_leave(bvg_fit *f);
 void shadow_destroy(bvg_fit *f);
+void lbfgs_cache_destroy(bvg_fit *f);                        // lbfgs_dev.cu: the cached work space of lbfgs_run_device
 bool shadow_active(const bvg_fit *f);
 int gene_big_setup();                                        // k_model.cu: per-device function attributes of k_gene_big
 int launch_gene_finish(bvg_fit *f, int mode, int jacobian, int propto, int ahead = 0);  // per-gene backward (+ update, + next draw) + cross-gene finish

@@ -535,21 +535,33 @@ int lbfgs_run_device(bvg_fit *f, const double *d_theta0, double *d_out, const Lb
   auto cleanup = [&]() {
     f->ls = LsPoint{nullptr, nullptr, nullptr};
     shadow_leave(f);
-    cudaFree(B); cudaFree(dev); cudaFreeHost(h_stat); cudaFreeHost(h_scal);
-    for (auto &e : evt) if (e) cudaEventDestroy(e);
+    // B, dev, the pinned words and the events belong to the fit's cache (lbfgs_cache_destroy)
   };
   auto fail = [&](int code) { cudaStreamSynchronize(st); cleanup(); return code; };
 #define LB_CUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { bvg_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #x, cudaGetErrorString(e_)); return fail(BVG_ERR_CUDA); } } while (0)
 #define LB_TRY(x) do { int r_ = (x); if (r_ != BVG_OK) return fail(r_); } while (0)
-  LB_CUDA(cudaMalloc(&B, nd * sizeof(double)));
+  {
+    const size_t need = nd * sizeof(double) + 256 + sizeof(LbDev);
+    if (f->lb_dev_bytes < need) {
+      cudaFree(f->lb_dev_buf);
+      f->lb_dev_buf = nullptr; f->lb_dev_bytes = 0;
+      LB_CUDA(cudaMalloc(&f->lb_dev_buf, need));
+      f->lb_dev_bytes = need;
+    }
+    if (!f->lb_pinned) {
+      LB_CUDA(cudaMallocHost(&f->lb_pinned, 512));
+      for (auto &e : f->lb_evt) LB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    B = (double *)f->lb_dev_buf;
+    dev = (LbDev *)((char *)f->lb_dev_buf + ((nd * sizeof(double) + 255) & ~(size_t)255));
+    h_stat = (LbStat *)f->lb_pinned;
+    h_scal = (double *)((char *)f->lb_pinned + 256);
+    evt[0] = f->lb_evt[0]; evt[1] = f->lb_evt[1];
+  }
   LB_CUDA(cudaMemsetAsync(B, 0, nd * sizeof(double), st));
   x0 = B + (size_t)nb * D; p = x0 + D; w = p + D; part = w + D; dots = part + (size_t)nb * LB_NCHUNK * 3; scal = dots + nb * 3;
   double *gpart = scal + 8;
   double *g0 = B + (size_t)(2 * mh) * D;
-  LB_CUDA(cudaMalloc(&dev, sizeof(LbDev)));
-  LB_CUDA(cudaMallocHost(&h_stat, 2 * sizeof(LbStat)));
-  LB_CUDA(cudaMallocHost(&h_scal, 4 * sizeof(double)));
-  for (auto &e : evt) LB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   LB_TRY(vec_make_weights(st, w, m, f->cfg.rank));
   if (d_theta0) LB_CUDA(cudaMemcpyAsync(x0, d_theta0, D * sizeof(double), cudaMemcpyDeviceToDevice, st));
 
@@ -673,4 +685,14 @@ int lbfgs_run_device(bvg_fit *f, const double *d_theta0, double *d_out, const Lb
   return BVG_OK;
 #undef LB_CUDA
 #undef LB_TRY
+}
+
+void lbfgs_cache_destroy(bvg_fit *f) {
+  cudaFree(f->lb_dev_buf);
+  f->lb_dev_buf = nullptr; f->lb_dev_bytes = 0;
+  if (f->lb_pinned) {
+    cudaFreeHost(f->lb_pinned);
+    f->lb_pinned = nullptr;
+    for (auto &e : f->lb_evt) { if (e) cudaEventDestroy(e); e = nullptr; }
+  }
 }
