@@ -507,6 +507,25 @@ struct LbStat { int32_t phase, term, it, fevals, switch_iter, accept, fresh_dir,
 
 }  // namespace
 
+// Pinned host memory for the status words: ONE 32 KB block per process, cut into 512-byte slots and never freed --
+// cudaMallocHost / cudaFreeHost take the driver's big locks and were measured at up to 0.4 s apiece on these boxes, which
+// is more than a whole fit.  A slot belongs to a fit from its first L-BFGS run until the model is freed.
+#include <mutex>
+static std::mutex g_pin_mu;
+static char *g_pin_block = nullptr;
+static uint64_t g_pin_used = 0;   // bitmap of the 64 slots
+static void *pinned_slot_acquire() {
+  std::lock_guard<std::mutex> lk(g_pin_mu);
+  if (!g_pin_block && cudaMallocHost(&g_pin_block, 64 * 512) != cudaSuccess) { cudaGetLastError(); g_pin_block = nullptr; return nullptr; }
+  for (int i = 0; i < 64; ++i)
+    if (!(g_pin_used >> i & 1ull)) { g_pin_used |= 1ull << i; return g_pin_block + 512 * i; }
+  return nullptr;   // more than 64 fits with a live L-BFGS work space in one process
+}
+static void pinned_slot_release(void *p) {
+  std::lock_guard<std::mutex> lk(g_pin_mu);
+  if (p && g_pin_block) g_pin_used &= ~(1ull << (((char *)p - g_pin_block) / 512));
+}
+
 bool lbfgs_device_ok(const bvg_fit *f, const LbfgsOpt *opt) {
   if (opt && opt->on_iterate) return false;   // Pathfinder needs the host at every iterate
   if (f->comm_mode == 1) return false;        // NCCL: the all-reduce is a host call between kernels
@@ -549,7 +568,8 @@ int lbfgs_run_device(bvg_fit *f, const double *d_theta0, double *d_out, const Lb
       f->lb_dev_bytes = need;
     }
     if (!f->lb_pinned) {
-      LB_CUDA(cudaMallocHost(&f->lb_pinned, 512));
+      f->lb_pinned = pinned_slot_acquire();
+      if (!f->lb_pinned) { bvg_set_error("L-BFGS: no pinned host slot (cudaMallocHost failed, or more than 64 live fits)"); return fail(BVG_ERR_CUDA); }
       for (auto &e : f->lb_evt) LB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
     B = (double *)f->lb_dev_buf;
@@ -691,7 +711,7 @@ void lbfgs_cache_destroy(bvg_fit *f) {
   cudaFree(f->lb_dev_buf);
   f->lb_dev_buf = nullptr; f->lb_dev_bytes = 0;
   if (f->lb_pinned) {
-    cudaFreeHost(f->lb_pinned);
+    pinned_slot_release(f->lb_pinned);
     f->lb_pinned = nullptr;
     for (auto &e : f->lb_evt) { if (e) cudaEventDestroy(e); e = nullptr; }
   }
