@@ -106,7 +106,56 @@ extern "C" int bvg_fit_create(const bvg_config *cfg, bvg_fit **out) {
   return BVG_OK;
 }
 
+// The three large per-fit blocks (the staged Y, the H2D staging buffers, the L-BFGS work space) come from a small process-wide
+// cache of exact-size device blocks: cudaMalloc / cudaFree of 30 - 120 MB cost 1 ms typically and 20 - 400 ms when the driver
+// maps or trims memory, which on a 0.2 s fit is the difference between runs (bench.py lists every run).  A released block
+// is kept (up to 16 blocks / 1.5 GB per process, blocks >= 4 MB) and handed to the next fit that asks for the same size --
+// the next sample of an R session, the next fit of a test suite.  The owner synchronises its streams before releasing.
+#include <mutex>
+namespace {
+struct BigBlock { int device; void *p; size_t bytes; };
+std::mutex g_big_mu;
+std::vector<BigBlock> g_big;
+size_t g_big_total = 0;
+}  // namespace
+int bvg_big_alloc(int device, void **p, size_t bytes) {
+  {
+    std::lock_guard<std::mutex> lk(g_big_mu);
+    for (size_t i = 0; i < g_big.size(); ++i)
+      if (g_big[i].device == device && g_big[i].bytes == bytes) {
+        *p = g_big[i].p;
+        g_big_total -= bytes;
+        g_big.erase(g_big.begin() + i);
+        return BVG_OK;
+      }
+  }
+  if (cudaMalloc(p, bytes) != cudaSuccess) {
+    cudaGetLastError();
+    // out of memory: give the cached blocks back to the driver and try once more
+    std::lock_guard<std::mutex> lk(g_big_mu);
+    for (auto &b : g_big) cudaFree(b.p);
+    g_big.clear(); g_big_total = 0;
+    CUDA_TRY(cudaMalloc(p, bytes));
+  }
+  return BVG_OK;
+}
+void bvg_big_free(int device, void *p, size_t bytes) {
+  if (!p) return;
+  {
+    std::lock_guard<std::mutex> lk(g_big_mu);
+    if (bytes >= ((size_t)4 << 20) && g_big.size() < 16 && g_big_total + bytes <= ((size_t)3 << 29)) {
+      g_big.push_back({device, p, bytes});
+      g_big_total += bytes;
+      return;
+    }
+  }
+  cudaFree(p);
+}
+
 static void free_model(bvg_fit *f) {
+  // nothing of this model may be in flight when its blocks go back to the cache (cudaFree used to wait implicitly)
+  if (f->stream) cudaStreamSynchronize(f->stream);
+  if (f->copy_stream) cudaStreamSynchronize(f->copy_stream);
   shadow_destroy(f);
   lbfgs_cache_destroy(f);
   fr_destroy(f);
@@ -115,7 +164,8 @@ static void free_model(bvg_fit *f) {
   tc_destroy(f);
   tcbig_destroy(f);
   suff_destroy(f);
-  cudaFree(f->Y); cudaFree(f->Phi); cudaFree(f->dvec); cudaFree(f->summary); cudaFree(f->draws);
+  bvg_big_free(f->cfg.device, f->Y, f->Y_bytes); f->Y_bytes = 0;
+  cudaFree(f->Phi); cudaFree(f->dvec); cudaFree(f->summary); cudaFree(f->draws);
   cudaFree(f->m.C); cudaFree(f->m.Ppart); cudaFree(f->m.Spart); cudaFree(f->m.blk); cudaFree(f->m.ctl);
   cudaFree((void *)f->m.hist_val);
   cudaFree((void *)f->m.depths);
@@ -136,7 +186,7 @@ extern "C" void bvg_fit_destroy(bvg_fit *f) {
   free_model(f);
   cudaFree(f->phi64);
   cudaFree(f->flush);
-  cudaFree(f->stage_buf);
+  bvg_big_free(f->cfg.device, f->stage_buf, f->stage_bytes); f->stage_buf = nullptr; f->stage_bytes = 0;
   if (f->copy_stream) {
     cudaStreamDestroy(f->copy_stream);
     for (int b = 0; b < 2; ++b) { cudaEventDestroy(f->ev_copied[b]); cudaEventDestroy(f->ev_staged[b]); }
@@ -321,7 +371,8 @@ static int set_y_impl(bvg_fit *f, const SRC *y, int64_t M, int64_t G) {
   // separate 128-byte pieces 4*ldY bytes apart
   const size_t y_elems = tiled ? (size_t)round_up(G, BVG_GENE_TILE) * f->ldY : (size_t)G * f->ldY;
   if (!reuse) {
-    CUDA_TRY(cudaMalloc(&f->Y, ts * y_elems));
+    BVG_TRY(bvg_big_alloc(f->cfg.device, &f->Y, ts * y_elems));
+    f->Y_bytes = ts * y_elems;
     if (tiled) CUDA_TRY(cudaMemsetAsync(f->Y, 0, ts * y_elems, f->stream));  // pads stay zero: staging writes real entries only
   }
   // stage through two bounded device buffers (host layout -> compute type + padding): the H2D copy of chunk
@@ -329,9 +380,9 @@ static int set_y_impl(bvg_fit *f, const SRC *y, int64_t M, int64_t G) {
   const int64_t genes_per_chunk = std::max<int64_t>(1, std::min<int64_t>(G, (int64_t)(32u << 20) / (M * (int64_t)sizeof(SRC))));
   const size_t stage_bytes = 2 * sizeof(SRC) * genes_per_chunk * M;
   if (f->stage_bytes < stage_bytes) {
-    cudaFree(f->stage_buf);
+    bvg_big_free(f->cfg.device, f->stage_buf, f->stage_bytes);
     f->stage_buf = nullptr; f->stage_bytes = 0;
-    CUDA_TRY(cudaMalloc(&f->stage_buf, stage_bytes));
+    BVG_TRY(bvg_big_alloc(f->cfg.device, &f->stage_buf, stage_bytes));
     f->stage_bytes = stage_bytes;
   }
   if (!f->copy_stream) {

@@ -320,6 +320,7 @@ struct bvg_fit {
   DevModel m;
   int64_t ldY, Mpad;
   void *Y;             // T [G][ldY]
+  size_t Y_bytes;
   void *Phi;           // T [Mpad][KP]
   double *phi64;       // k x M? kept for basis-independent checks: col-major M x k copy
   double *dvec;        // backing store of mu|omega|hist(2D)|zeta|grad
@@ -405,6 +406,8 @@ void persist_destroy(bvg_fit *f);
 int shadow_enter(bvg_fit *f);                                // fp64_shadow.cu: evaluate in fp64 (SIMT kernels, Y widened on the device) until shadow_leave
 void shadow_leave(bvg_fit *f);
 void shadow_destroy(bvg_fit *f);
+int bvg_big_alloc(int device, void **p, size_t bytes);       // api.cu: exact-size cache of the large per-fit device blocks
+void bvg_big_free(int device, void *p, size_t bytes);
 void lbfgs_cache_destroy(bvg_fit *f);                        // lbfgs_dev.cu: the cached work space of lbfgs_run_device
 bool shadow_active(const bvg_fit *f);
 int gene_big_setup();                                        // k_model.cu: per-device function attributes of k_gene_big

@@ -562,9 +562,9 @@ int lbfgs_run_device(bvg_fit *f, const double *d_theta0, double *d_out, const Lb
   {
     const size_t need = nd * sizeof(double) + 256 + sizeof(LbDev);
     if (f->lb_dev_bytes < need) {
-      cudaFree(f->lb_dev_buf);
+      bvg_big_free(f->cfg.device, f->lb_dev_buf, f->lb_dev_bytes);
       f->lb_dev_buf = nullptr; f->lb_dev_bytes = 0;
-      LB_CUDA(cudaMalloc(&f->lb_dev_buf, need));
+      LB_TRY(bvg_big_alloc(f->cfg.device, &f->lb_dev_buf, need));
       f->lb_dev_bytes = need;
     }
     if (!f->lb_pinned) {
@@ -708,7 +708,7 @@ int lbfgs_run_device(bvg_fit *f, const double *d_theta0, double *d_out, const Lb
 }
 
 void lbfgs_cache_destroy(bvg_fit *f) {
-  cudaFree(f->lb_dev_buf);
+  bvg_big_free(f->cfg.device, f->lb_dev_buf, f->lb_dev_bytes);
   f->lb_dev_buf = nullptr; f->lb_dev_bytes = 0;
   if (f->lb_pinned) {
     pinned_slot_release(f->lb_pinned);

@@ -529,11 +529,11 @@ def run_ours(args, rank, world, local_rank):
         phif = bvg.basis_build(Xf, Cf, length_scale_kmeans(Cf), "matern", 2.5, device=local_rank)
         t_kb = time.perf_counter() - t0
         Yf, _ = synth.expression(phif, G_GENES, "gaussian", 312)
-        # three whole fits, each on a fresh handle (allocation, H2D, staging, L-BFGS, ADVI, draws); the line quotes the median and
-        # lists all three: single runs on these boxes carry host-side outliers of 0.1 - 0.3 s (a slow first H2D after an idle
+        # five whole fits, each on a fresh handle (allocation, H2D, staging, L-BFGS, ADVI, draws); the line quotes the median and
+        # lists all five: single runs on these boxes carry host-side outliers of 0.1 - 0.3 s (a slow first H2D after an idle
         # period, a stalled driver call) that say nothing about the path
         runs = []
-        for _ in range(3):
+        for _ in range(5):
             t0 = time.perf_counter()
             f3 = bvg.Fit(phif, Yf, "gaussian", "fast", args.engine, **cfg)
             f3.run()
@@ -544,14 +544,14 @@ def run_ours(args, rank, world, local_rank):
             st3["sec_close"] = time.perf_counter() - tc0   # releasing the handle (cudaFree x 25): 3 ms typically, up to 0.7 s when the driver trims
             runs.append((w3, st3))
         runs.sort(key=lambda r: r[0])
-        w3, s3 = runs[1]
+        w3, s3 = runs[len(runs) // 2]
         fit_info = {"wall_s": w3, "wall_s_runs": [r[0] for r in runs],
                     "runs_detail": [{q: round(r[1][q], 4) for q in ("sec_h2d", "sec_mle", "sec_adapt", "sec_sga", "sec_draws", "sec_total", "sec_close")} for r in runs],
                     "sec_kmeans_basis": t_kb, "sec_h2d": s3["sec_h2d"], "grad_evals": s3["grad_evals"],
                     "elbo_evals": s3["elbo_evals"], "advi_iters": s3["advi_iters"], "eta": s3["eta"], "mle_iters": s3["mle_iters"],
                     "mle_fevals": s3["mle_fevals"], "mle_term": s3["mle_term"], "sec_mle": s3["sec_mle"], "sec_adapt": s3["sec_adapt"],
                     "sec_sga": s3["sec_sga"], "sec_draws": s3["sec_draws"], "converged": s3["converged"], "elbo": s3["elbo"],
-                    "includes": "k-means (10 starts) + basis build + H2D + L-BFGS + eta adaptation + SGA + 1,000 draws + summaries; median of three fits on fresh handles"}
+                    "includes": "k-means (10 starts) + basis build + H2D + L-BFGS + eta adaptation + SGA + 1,000 draws + summaries; median of five fits on fresh handles"}
         # the library's default takes the ELBO estimates of a gaussian fit from per-gene sufficient statistics (the same draws and
         # values, O(k^2 G) per draw); the same fit with the DENSE batched ELBO kernel every other model uses, for comparison
         t0 = time.perf_counter()
