@@ -17,7 +17,7 @@ PREC_FP64, PREC_FAST = 0, 1
 ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05 = 0, 1, 2
 
 EXPORTS = [
-    "bvg_version", "bvg_last_error", "bvg_device_count", "bvg_config_default", "bvg_basis_build", "bvg_kmeans", "bvg_variogram_lscale", "bvg_gmm_log_prob", "bvg_gmm_fit", "bvg_gmm_open", "bvg_gmm_close", "bvg_gmm_eval", "bvg_gmm_posterior",
+    "bvg_version", "bvg_last_error", "bvg_release_cached_memory", "bvg_device_count", "bvg_config_default", "bvg_basis_build", "bvg_kmeans", "bvg_variogram_lscale", "bvg_gmm_log_prob", "bvg_gmm_fit", "bvg_gmm_open", "bvg_gmm_close", "bvg_gmm_eval", "bvg_gmm_posterior",
     "bvg_fit_create", "bvg_fit_destroy", "bvg_fit_set_phi", "bvg_fit_set_y_f64", "bvg_fit_set_y_i32",
     "bvg_fit_dim", "bvg_fit_shape", "bvg_fit_set_gene_depths", "bvg_comm_unique_id", "bvg_fit_comm_init", "bvg_fit_peer_handle", "bvg_fit_peer_init", "bvg_log_prob", "bvg_fit_run", "bvg_fit_mle",
     "bvg_fit_advi", "bvg_fit_summarize", "bvg_fit_set_variational", "bvg_fit_get_variational", "bvg_fit_get_cholesky", "bvg_fit_set_cholesky", "bvg_fit_pathfinder_single",
@@ -109,6 +109,8 @@ def lib():
     L.bvg_fit_get_draws.argtypes = [_vp, _dp]
     L.bvg_gmm_log_prob.argtypes = [C.c_int, _dp, C.c_int64, C.c_int, C.c_int, _dp, C.c_int, C.c_int, C.POINTER(C.c_double), _dp]
     L.bvg_gmm_fit.argtypes = [C.c_int, _dp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_uint64, _dp, _dp, _dp, _dp, _dp, _dp]
+    L.bvg_release_cached_memory.argtypes = []
+    L.bvg_release_cached_memory.restype = None
     L.bvg_gmm_open.argtypes = [C.c_int, _dp, C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
     L.bvg_gmm_close.argtypes = [C.c_void_p]
     L.bvg_gmm_close.restype = None

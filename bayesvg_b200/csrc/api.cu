@@ -152,6 +152,13 @@ void bvg_big_free(int device, void *p, size_t bytes) {
   cudaFree(p);
 }
 
+extern "C" void bvg_release_cached_memory(void) {
+  std::lock_guard<std::mutex> lk(g_big_mu);
+  for (auto &b : g_big) cudaFree(b.p);
+  g_big.clear();
+  g_big_total = 0;
+}
+
 static void free_model(bvg_fit *f) {
   // nothing of this model may be in flight when its blocks go back to the cache (cudaFree used to wait implicitly)
   if (f->stream) cudaStreamSynchronize(f->stream);

@@ -163,6 +163,10 @@ int bvg_gmm_posterior(void *handle, const double *thetas, int nd, double *draws_
 
 int bvg_fit_create(const bvg_config *cfg, bvg_fit **out);
 void bvg_fit_destroy(bvg_fit *);
+/* bvg_fit_destroy keeps the large device blocks of a fit (the staged expression matrix, the H2D staging buffers, the L-BFGS work
+ * space: up to 16 blocks / 1.5 GB per process) for the next fit that asks for the same sizes -- allocating and freeing them costs
+ * the driver up to 0.4 s, twice a whole fit.  This hands them back to the driver (e.g. before another library needs the memory). */
+void bvg_release_cached_memory(void);
 
 /* data_list$phi (M x k) and data_list$y (the gene-major long vector = M x G column-major).
  * spot_id / gene_id are implied (N = M*G). */

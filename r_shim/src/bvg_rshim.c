@@ -197,6 +197,8 @@ SEXP R_bvg_fit_posterior(SEXP p, SEXP n) {
   return out;
 }
 SEXP R_bvg_fit_destroy(SEXP p) { fit_finalizer(p); return R_NilValue; }
+/* .onUnload: hand the device blocks bvg_fit_destroy keeps for the next fit back to the driver */
+SEXP R_bvg_release_cached_memory(void) { bvg_release_cached_memory(); return R_NilValue; }
 
 static const R_CallMethodDef calls[] = {
   {"R_bvg_basis_build", (DL_FUNC)&R_bvg_basis_build, 7}, {"R_bvg_fit_create", (DL_FUNC)&R_bvg_fit_create, 1},
@@ -206,7 +208,7 @@ static const R_CallMethodDef calls[] = {
   {"R_bvg_fit_destroy", (DL_FUNC)&R_bvg_fit_destroy, 1}, {"R_bvg_fit_set_gene_depths", (DL_FUNC)&R_bvg_fit_set_gene_depths, 2},
   {"R_bvg_fit_posterior", (DL_FUNC)&R_bvg_fit_posterior, 2},
   {"R_bvg_variogram_lscale", (DL_FUNC)&R_bvg_variogram_lscale, 4}, {"R_bvg_kmeans", (DL_FUNC)&R_bvg_kmeans, 6},
-  {"R_bvg_gmm_fit", (DL_FUNC)&R_bvg_gmm_fit, 6},
+  {"R_bvg_gmm_fit", (DL_FUNC)&R_bvg_gmm_fit, 6},         {"R_bvg_release_cached_memory", (DL_FUNC)&R_bvg_release_cached_memory, 0},
   {NULL, NULL, 0}};
 void R_init_bayesVGb200(DllInfo *dll) {
   R_registerRoutines(dll, NULL, calls, NULL, NULL);
