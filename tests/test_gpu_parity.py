@@ -257,6 +257,32 @@ def test_set_y_again_reuses_the_model_and_matches_a_fresh_fit(lik, prec, eng):
     assert lp_c == lp_d and np.array_equal(g_c, g_d)
 
 
+def test_recycled_device_blocks_do_not_leak_state_between_fits():
+    """bvg_fit_destroy keeps the large device blocks (staged Y, staging buffers, L-BFGS work space) for the next fit of the same
+    sizes.  A fit that receives recycled blocks -- after a fit on DIFFERENT data of the same shape, whose padded entries and
+    history rows are still in them -- must give bit-identical results to a fit on fresh memory; bvg_release_cached_memory empties
+    the cache."""
+    from bayesvg_b200 import _lib
+    kw = dict(seed=312, n_iter=200, mle_iter=40, elbo_samples=20, n_draws=100)
+    pa = make_problem(700, 300, 20, "gaussian", seed=1)        # 300 genes in 3 tiles of 128: 84 padded gene rows
+    pb = make_problem(700, 300, 20, "gaussian", seed=2)
+    _lib.lib().bvg_release_cached_memory()
+    f = bvg.Fit(pa["phi"], pa["y"], "gaussian", "fast", "tcgen05", **kw)
+    ref = f.run()
+    f.close()
+    f = bvg.Fit(pb["phi"], pb["y"], "gaussian", "fast", "tcgen05", **kw)               # other data into the same blocks
+    f.run()
+    f.close()
+    f = bvg.Fit(pa["phi"], pa["y"], "gaussian", "fast", "tcgen05", **kw)               # recycled blocks
+    got = f.run()
+    f.close()
+    assert np.array_equal(ref, got)
+    _lib.lib().bvg_release_cached_memory()
+    f = bvg.Fit(pa["phi"], pa["y"], "gaussian", "fast", "tcgen05", **kw)               # fresh memory again
+    assert np.array_equal(ref, f.run())
+    f.close()
+
+
 def test_default_elbo_path_is_the_sufficient_statistic_one(monkeypatch):
     """bvg_config_default: elbo_suffstat = 1 -- a default gaussian fit takes its ELBO estimates from the sufficient statistics
     and ends where the dense-ELBO fit ends (same draws, values equal to the fast path's round-off: same step size, same stopping
