@@ -524,10 +524,13 @@ def run_ours(args, rank, world, local_rank):
         from bayesvg_b200 import synth
         from bayesvg_b200.api import kmeans_centers, length_scale_kmeans
         Xf = synth.scale_coords(synth.visium_grid())
-        t0 = time.perf_counter()
-        Cf = kmeans_centers(Xf, K_BASIS, 100, 10, rng=312, device=local_rank)
-        phif = bvg.basis_build(Xf, Cf, length_scale_kmeans(Cf), "matern", 2.5, device=local_rank)
-        t_kb = time.perf_counter() - t0
+        t_kb_calls = []
+        for _ in range(2):   # the first call in a process also loads the k-means / QR kernels (lazy module loading, ~14 ms); the fits are timed warm too
+            t0 = time.perf_counter()
+            Cf = kmeans_centers(Xf, K_BASIS, 100, 10, rng=312, device=local_rank)
+            phif = bvg.basis_build(Xf, Cf, length_scale_kmeans(Cf), "matern", 2.5, device=local_rank)
+            t_kb_calls.append(time.perf_counter() - t0)
+        t_kb = t_kb_calls[-1]
         Yf, _ = synth.expression(phif, G_GENES, "gaussian", 312)
         # five whole fits, each on a fresh handle (allocation, H2D, staging, L-BFGS, ADVI, draws); the line quotes the median and
         # lists all five: single runs on these boxes carry host-side outliers of 0.1 - 0.3 s (a slow first H2D after an idle
@@ -547,7 +550,7 @@ def run_ours(args, rank, world, local_rank):
         w3, s3 = runs[len(runs) // 2]
         fit_info = {"wall_s": w3, "wall_s_runs": [r[0] for r in runs],
                     "runs_detail": [{q: round(r[1][q], 4) for q in ("sec_h2d", "sec_mle", "sec_adapt", "sec_sga", "sec_draws", "sec_total", "sec_close")} for r in runs],
-                    "sec_kmeans_basis": t_kb, "sec_h2d": s3["sec_h2d"], "grad_evals": s3["grad_evals"],
+                    "sec_kmeans_basis": t_kb, "sec_kmeans_basis_calls": t_kb_calls, "sec_h2d": s3["sec_h2d"], "grad_evals": s3["grad_evals"],
                     "elbo_evals": s3["elbo_evals"], "advi_iters": s3["advi_iters"], "eta": s3["eta"], "mle_iters": s3["mle_iters"],
                     "mle_fevals": s3["mle_fevals"], "mle_term": s3["mle_term"], "sec_mle": s3["sec_mle"], "sec_adapt": s3["sec_adapt"],
                     "sec_sga": s3["sec_sga"], "sec_draws": s3["sec_draws"], "converged": s3["converged"], "elbo": s3["elbo"],
