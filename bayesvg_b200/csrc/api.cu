@@ -152,11 +152,56 @@ void bvg_big_free(int device, void *p, size_t bytes) {
   cudaFree(p);
 }
 
+// ---- pooled device allocations (bvg_internal.cuh) -----------------------------------------------------------------
+namespace {
+struct PoolDev { int state = 0; cudaStream_t st = nullptr; cudaMemPool_t pool = nullptr; };   // state: 0 unknown, 1 pooled, 2 plain
+PoolDev g_pool[64];
+std::mutex g_pool_mu;
+PoolDev *pool_of_current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { cudaGetLastError(); return nullptr; }
+  PoolDev &pd = g_pool[dev];
+  if (pd.state == 0) {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    if (pd.state == 0) {
+      int ok = 0;
+      uint64_t keep = (uint64_t)8 << 30;
+      if (getenv("BVG_NO_POOL") == nullptr && cudaDeviceGetAttribute(&ok, cudaDevAttrMemoryPoolsSupported, dev) == cudaSuccess && ok &&
+          cudaDeviceGetDefaultMemPool(&pd.pool, dev) == cudaSuccess &&
+          cudaMemPoolSetAttribute(pd.pool, cudaMemPoolAttrReleaseThreshold, &keep) == cudaSuccess &&
+          cudaStreamCreateWithFlags(&pd.st, cudaStreamNonBlocking) == cudaSuccess) pd.state = 1;
+      else { cudaGetLastError(); pd.state = 2; }
+    }
+  }
+  return pd.state == 1 ? &pd : nullptr;
+}
+}  // namespace
+cudaError_t bvg_pool_malloc(void **p, size_t bytes) {
+  PoolDev *pd = pool_of_current_device();
+  if (!pd) return (cudaMalloc)(p, bytes);
+  const cudaError_t e = cudaMallocAsync(p, bytes, pd->st);
+  if (e != cudaSuccess) return e;
+  return cudaStreamSynchronize(pd->st);   // the block is complete: usable on every stream
+}
+cudaError_t bvg_pool_free(void *p) {
+  if (!p) return cudaSuccess;
+  PoolDev *pd = pool_of_current_device();
+  if (!pd) return (cudaFree)(p);
+  cudaDeviceSynchronize();                // cudaFree's implicit wait: nothing may still use the block
+  if (cudaFreeAsync(p, pd->st) == cudaSuccess) return cudaSuccess;
+  cudaGetLastError();
+  return (cudaFree)(p);                   // a block that did not come from the pool
+}
+
 extern "C" void bvg_release_cached_memory(void) {
-  std::lock_guard<std::mutex> lk(g_big_mu);
-  for (auto &b : g_big) cudaFree(b.p);
-  g_big.clear();
-  g_big_total = 0;
+  {
+    std::lock_guard<std::mutex> lk(g_big_mu);
+    for (auto &b : g_big) cudaFree(b.p);
+    g_big.clear();
+    g_big_total = 0;
+  }
+  for (auto &pd : g_pool)
+    if (pd.state == 1) { cudaStreamSynchronize(pd.st); cudaMemPoolTrimTo(pd.pool, 0); }
 }
 
 static void free_model(bvg_fit *f) {

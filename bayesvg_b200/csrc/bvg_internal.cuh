@@ -371,6 +371,18 @@ struct bvg_fit {
   bool no_mle_fp64;    // diagnostics (BVG_NO_MLE_FP64=1): let the fast path's L-BFGS end with TERM_LSFAIL as in round 1
 };
 
+// Device allocations of a fit come from the device's stream-ordered memory pool (cudaMallocAsync / cudaFreeAsync, release
+// threshold 8 GB) instead of cudaMalloc / cudaFree: a released block stays mapped for the next allocation, where cudaFree /
+// cudaMalloc cost the driver anything from 0.1 to 700 ms per call on these boxes (bench.py: `sec_close`, `runs_detail`).
+// Same semantics as the calls they stand in for (the free waits for the device first, as cudaFree does).  comm.cu opts out:
+// the peer-exchange buffer is exported with cudaIpcGetMemHandle, which needs a cudaMalloc block.
+cudaError_t bvg_pool_malloc(void **p, size_t bytes);   // api.cu
+cudaError_t bvg_pool_free(void *p);
+#ifndef BVG_NO_POOL
+#define cudaMalloc(pp, n) bvg_pool_malloc((void **)(pp), (n))
+#define cudaFree(p) bvg_pool_free((void *)(p))
+#endif
+
 void bvg_set_error(const char *fmt, ...);
 #define CUDA_TRY(x)                                                                          \
   do {                                                                                       \

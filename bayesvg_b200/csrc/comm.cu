@@ -11,6 +11,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#define BVG_NO_POOL   // the exchange buffer is shared through CUDA IPC: a plain cudaMalloc block
 #include "bvg_internal.cuh"
 
 typedef struct ncclComm *ncclComm_t;
